@@ -1,0 +1,619 @@
+/*
+ * dvs_oracle.c — CPU ORACLE (TEST INFRASTRUCTURE, "parity unpinned" — see dvs_oracle.h).
+ *
+ * Restates the credited 3DGS tile rasterizer (EXTERNAL SPEC of
+ * graphdeco-inria/diff-gaussian-rasterization, credited at /root/reference/README.md:95)
+ * in plain C.  Every function cites the in-tree corroboration it follows.
+ *
+ * Build: gcc -O2 -ffp-contract=off -mfma -mavx2 -fopenmp -fPIC -shared  (see oracle/Makefile).
+ * -ffp-contract=off + explicit fmaf() makes the per-Gaussian arithmetic (A1) a literal
+ * operation sequence; the CUDA kernels mirror that sequence (compiled -fmad=false), which is
+ * what makes radii / tiles_touched / depth keys bit-exact.
+ */
+#include "dvs_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define TILE 16
+
+static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+/* float -> int32 with the semantics of PTX cvt.rzi.s32.f32 (truncate, saturate, NaN -> 0) */
+static inline int32_t f2i_rz(float x) {
+    if (x != x) return 0;
+    if (x >= 2147483648.0f) return 2147483647;
+    if (x <= -2147483648.0f) return (int32_t)0x80000000;
+    return (int32_t)x;
+}
+static inline int32_t imin(int32_t a, int32_t b) { return a < b ? a : b; }
+static inline int32_t imax(int32_t a, int32_t b) { return a > b ? a : b; }
+
+/* Deterministic fp32 exp: Cody-Waite reduction + degree-5 minimax on r^2 (Cephes expf
+ * coefficients), every step a single IEEE op or fmaf.  <= 2 ulp.  Used only by the
+ * activations exp(log_scale) and sigmoid(logit) (gaussian_model.cpp:145-157). */
+float orc_expf(float x) {
+    x = fminf(fmaxf(x, -87.0f), 88.0f);
+    float n = rintf(x * 1.44269504088896341f);
+    float r = fmaf(n, -0.693359375f, x);
+    r = fmaf(n, 2.12194440e-4f, r);
+    float p = 1.9875691500e-4f;
+    p = fmaf(p, r, 1.3981999507e-3f);
+    p = fmaf(p, r, 8.3334519073e-3f);
+    p = fmaf(p, r, 4.1665795894e-2f);
+    p = fmaf(p, r, 1.6666665459e-1f);
+    p = fmaf(p, r, 5.0000001201e-1f);
+    float r2 = r * r;
+    float e = fmaf(p, r2, r) + 1.0f;
+    int32_t ni = (int32_t)n;
+    return e * u2f((uint32_t)(ni + 127) << 23);
+}
+
+/* SH constants: gsplat_sh.hlsl:42-62, SH_C0 gaussian_model.cpp:128 */
+static const float SH_C0 = 0.28209479177387814f;
+static const float SH_C1 = 0.4886025119029199f;
+static const float SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                               -1.0925484305920792f, 0.5462742152960396f};
+static const float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                               0.3731763325901154f,  -0.4570457994644658f, 1.445305721320277f,
+                               -0.5900435899266435f};
+
+typedef struct {
+    float s[3];  /* activated scale * scale_modifier */
+    float q[4];  /* unit quaternion r,x,y,z */
+    float qlen;  /* |q_raw| */
+    float o;     /* activated opacity */
+} act_t;
+
+static inline void activate(const orc_camera* cam, const float* scales, const float* quats,
+                            const float* opac, int i, act_t* a) {
+    if (cam->flags & ORC_FLAG_INPUT_ACTIVATED) {
+        for (int k = 0; k < 3; k++) a->s[k] = cam->scale_modifier * scales[3 * i + k];
+        for (int k = 0; k < 4; k++) a->q[k] = quats[4 * i + k];
+        a->qlen = 1.0f;
+        a->o = opac[i];
+    } else {
+        for (int k = 0; k < 3; k++) a->s[k] = cam->scale_modifier * orc_expf(scales[3 * i + k]);
+        float q0 = quats[4 * i], q1 = quats[4 * i + 1], q2 = quats[4 * i + 2], q3 = quats[4 * i + 3];
+        float n2 = fmaf(q0, q0, fmaf(q1, q1, fmaf(q2, q2, q3 * q3)));
+        float len = sqrtf(n2);
+        float inv = 1.0f / len;
+        a->q[0] = q0 * inv; a->q[1] = q1 * inv; a->q[2] = q2 * inv; a->q[3] = q3 * inv;
+        a->qlen = len;
+        a->o = 1.0f / (1.0f + orc_expf(-opac[i]));
+    }
+}
+
+/* R(q): gsplat_intersect.hlsl:71-82 / gsplat_vs.hlsl:189-200 (row-major rows listed there) */
+static inline void quat_to_R(const float* q, float R[3][3]) {
+    float r = q[0], x = q[1], y = q[2], z = q[3];
+    R[0][0] = fmaf(-2.0f, fmaf(z, z, y * y), 1.0f);
+    R[0][1] = 2.0f * fmaf(x, y, -(r * z));
+    R[0][2] = 2.0f * fmaf(x, z, r * y);
+    R[1][0] = 2.0f * fmaf(x, y, r * z);
+    R[1][1] = fmaf(-2.0f, fmaf(z, z, x * x), 1.0f);
+    R[1][2] = 2.0f * fmaf(y, z, -(r * x));
+    R[2][0] = 2.0f * fmaf(x, z, -(r * y));
+    R[2][1] = 2.0f * fmaf(y, z, r * x);
+    R[2][2] = fmaf(-2.0f, fmaf(y, y, x * x), 1.0f);
+}
+
+/* Sigma = (R S)(R S)^T, 6 upper-triangular values: gsplat_intersect.hlsl:61-95 */
+static inline void cov3d_from(const float s[3], float R[3][3], float M[3][3], float c6[6]) {
+    for (int i = 0; i < 3; i++)
+        for (int k = 0; k < 3; k++) M[i][k] = R[i][k] * s[k];
+    c6[0] = fmaf(M[0][0], M[0][0], fmaf(M[0][1], M[0][1], M[0][2] * M[0][2]));
+    c6[1] = fmaf(M[0][0], M[1][0], fmaf(M[0][1], M[1][1], M[0][2] * M[1][2]));
+    c6[2] = fmaf(M[0][0], M[2][0], fmaf(M[0][1], M[2][1], M[0][2] * M[2][2]));
+    c6[3] = fmaf(M[1][0], M[1][0], fmaf(M[1][1], M[1][1], M[1][2] * M[1][2]));
+    c6[4] = fmaf(M[1][0], M[2][0], fmaf(M[1][1], M[2][1], M[1][2] * M[2][2]));
+    c6[5] = fmaf(M[2][0], M[2][0], fmaf(M[2][1], M[2][1], M[2][2] * M[2][2]));
+}
+
+/* t = View * p (rows 0..2), m[4c+r]: gsplat_viewz_cs.hlsl:195-203 */
+static inline void xform43(const float* m, const float* p, float t[3]) {
+    for (int r = 0; r < 3; r++)
+        t[r] = fmaf(m[r], p[0], fmaf(m[4 + r], p[1], fmaf(m[8 + r], p[2], m[12 + r])));
+}
+static inline void xform44(const float* m, const float* p, float h[4]) {
+    for (int r = 0; r < 4; r++)
+        h[r] = fmaf(m[r], p[0], fmaf(m[4 + r], p[1], fmaf(m[8 + r], p[2], m[12 + r])));
+}
+
+typedef struct {
+    float fx, fy, limx, limy;
+    float tx, ty, tz;       /* clamped t.x, t.y; t.z */
+    float txtz, tytz;       /* unclamped ratios */
+    float J00, J02, J11, J12;
+    float T[2][3];
+    float a, b, c;          /* cov2D with +0.3 */
+} ewa_t;
+
+/* EWA cov2D: gsplat_intersect.hlsl:96-134 (1.3*tanfov clamp, J, W, +0.3 low-pass) */
+static inline void ewa_cov2d(const orc_camera* cam, const float t[3], const float c6[6], ewa_t* e) {
+    const float* V = cam->view;
+    e->fx = (float)cam->width / (2.0f * cam->tanfovx);
+    e->fy = (float)cam->height / (2.0f * cam->tanfovy);
+    e->limx = 1.3f * cam->tanfovx;
+    e->limy = 1.3f * cam->tanfovy;
+    e->tz = t[2];
+    e->txtz = t[0] / t[2];
+    e->tytz = t[1] / t[2];
+    e->tx = fminf(e->limx, fmaxf(-e->limx, e->txtz)) * t[2];
+    e->ty = fminf(e->limy, fmaxf(-e->limy, e->tytz)) * t[2];
+    float tz2 = t[2] * t[2];
+    e->J00 = e->fx / t[2];
+    e->J02 = -(e->fx * e->tx) / tz2;
+    e->J11 = e->fy / t[2];
+    e->J12 = -(e->fy * e->ty) / tz2;
+    /* W_rc = V[4c+r]; T = J W (2x3) */
+    for (int j = 0; j < 3; j++) {
+        float W0j = V[4 * j + 0], W1j = V[4 * j + 1], W2j = V[4 * j + 2];
+        e->T[0][j] = fmaf(e->J00, W0j, e->J02 * W2j);
+        e->T[1][j] = fmaf(e->J11, W1j, e->J12 * W2j);
+    }
+    /* Sigma symmetric 3x3 */
+    float S[3][3] = {{c6[0], c6[1], c6[2]}, {c6[1], c6[3], c6[4]}, {c6[2], c6[4], c6[5]}};
+    float U[2][3];
+    for (int i = 0; i < 2; i++)
+        for (int j = 0; j < 3; j++)
+            U[i][j] = fmaf(e->T[i][0], S[0][j], fmaf(e->T[i][1], S[1][j], e->T[i][2] * S[2][j]));
+    e->a = fmaf(U[0][0], e->T[0][0], fmaf(U[0][1], e->T[0][1], U[0][2] * e->T[0][2])) + 0.3f;
+    e->b = fmaf(U[0][0], e->T[1][0], fmaf(U[0][1], e->T[1][1], U[0][2] * e->T[1][2]));
+    e->c = fmaf(U[1][0], e->T[1][0], fmaf(U[1][1], e->T[1][1], U[1][2] * e->T[1][2])) + 0.3f;
+}
+
+/* SH basis values b[0..K) for unit direction d: gsplat_sh.hlsl:64-103 (signs and constants) */
+static inline void sh_basis(int deg, const float d[3], float b[16]) {
+    float x = d[0], y = d[1], z = d[2];
+    b[0] = SH_C0;
+    if (deg < 1) return;
+    b[1] = -SH_C1 * y; b[2] = SH_C1 * z; b[3] = -SH_C1 * x;
+    if (deg < 2) return;
+    float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    b[4] = SH_C2[0] * xy;
+    b[5] = SH_C2[1] * yz;
+    b[6] = SH_C2[2] * (fmaf(2.0f, zz, -xx) - yy);
+    b[7] = SH_C2[3] * xz;
+    b[8] = SH_C2[4] * (xx - yy);
+    if (deg < 3) return;
+    b[9] = SH_C3[0] * y * fmaf(3.0f, xx, -yy);
+    b[10] = SH_C3[1] * xy * z;
+    b[11] = SH_C3[2] * y * (fmaf(4.0f, zz, -xx) - yy);
+    b[12] = SH_C3[3] * z * (fmaf(2.0f, zz, -(3.0f * xx)) - 3.0f * yy);
+    b[13] = SH_C3[4] * x * (fmaf(4.0f, zz, -xx) - yy);
+    b[14] = SH_C3[5] * z * (xx - yy);
+    b[15] = SH_C3[6] * x * fmaf(-3.0f, yy, xx);
+}
+
+void orc_preprocess_fwd(const orc_camera* cam, int32_t N, const float* means3D, const float* scales,
+                        const float* quats, const float* opacities, const float* sh0, const float* shN,
+                        float* depth, int32_t* radii, float* mean2D, float* cov3D, float* conic_opacity,
+                        float* rgb, uint8_t* clamped, uint32_t* tiles_touched, int32_t* rect) {
+    const int gx = (cam->width + TILE - 1) / TILE, gy = (cam->height + TILE - 1) / TILE;
+    const int deg = cam->sh_degree, K = (deg + 1) * (deg + 1), KR = cam->sh_rest_alloc;
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < N; i++) {
+        radii[i] = 0; tiles_touched[i] = 0; depth[i] = 0.0f;
+        mean2D[2 * i] = mean2D[2 * i + 1] = 0.0f;
+        for (int k = 0; k < 6; k++) cov3D[6 * i + k] = 0.0f;
+        for (int k = 0; k < 4; k++) { conic_opacity[4 * i + k] = 0.0f; rect[4 * i + k] = 0; }
+        for (int k = 0; k < 3; k++) { rgb[3 * i + k] = 0.0f; clamped[3 * i + k] = 0; }
+        const float* p = means3D + 3 * (size_t)i;
+        float t[3], h[4];
+        xform43(cam->view, p, t);
+        if (t[2] <= 0.2f) continue; /* B.1 step 1: only cull */
+        xform44(cam->proj, p, h);
+        float w_inv = 1.0f / (h[3] + 1e-7f); /* gsplat_viewz_cs.hlsl:197-199 */
+        float ndcx = h[0] * w_inv, ndcy = h[1] * w_inv;
+        act_t a; activate(cam, scales, quats, opacities, i, &a);
+        float R[3][3], M[3][3], c6[6];
+        quat_to_R(a.q, R);
+        cov3d_from(a.s, R, M, c6);
+        ewa_t e; ewa_cov2d(cam, t, c6, &e);
+        float det = fmaf(e.a, e.c, -(e.b * e.b));
+        if (det == 0.0f) continue;
+        float det_inv = 1.0f / det;
+        float cA = e.c * det_inv, cB = -e.b * det_inv, cC = e.a * det_inv;
+        float mid = 0.5f * (e.a + e.c);
+        float sq = sqrtf(fmaxf(0.1f, fmaf(mid, mid, -det)));
+        float l1 = mid + sq, l2 = mid - sq;
+        float rad_f = ceilf(3.0f * sqrtf(fmaxf(l1, l2)));
+        int32_t rad = f2i_rz(rad_f);
+        /* ndc2Pix: gsplat_vs.hlsl:211-214 */
+        float mx = fmaf(ndcx + 1.0f, (float)cam->width, -1.0f) * 0.5f;
+        float my = fmaf(ndcy + 1.0f, (float)cam->height, -1.0f) * 0.5f;
+        float radf = (float)rad;
+        int32_t minx = imin(gx, imax(0, f2i_rz((mx - radf) * 0.0625f)));
+        int32_t miny = imin(gy, imax(0, f2i_rz((my - radf) * 0.0625f)));
+        int32_t maxx = imin(gx, imax(0, f2i_rz((mx + radf + 15.0f) * 0.0625f)));
+        int32_t maxy = imin(gy, imax(0, f2i_rz((my + radf + 15.0f) * 0.0625f)));
+        int64_t area = (int64_t)(maxx - minx) * (int64_t)(maxy - miny);
+        if (area <= 0) continue;
+        /* colour: direction from camera, SH eval, +0.5, clamp at 0 (gsplat_sh.hlsl:64-126) */
+        float dir[3] = {p[0] - cam->campos[0], p[1] - cam->campos[1], p[2] - cam->campos[2]};
+        float len = sqrtf(fmaf(dir[0], dir[0], fmaf(dir[1], dir[1], dir[2] * dir[2])));
+        float linv = 1.0f / len;
+        dir[0] *= linv; dir[1] *= linv; dir[2] *= linv;
+        float bas[16]; sh_basis(deg, dir, bas);
+        for (int ch = 0; ch < 3; ch++) {
+            float acc = bas[0] * sh0[3 * (size_t)i + ch];
+            for (int k = 1; k < K; k++) acc = fmaf(bas[k], shN[3 * ((size_t)i * KR + (k - 1)) + ch], acc);
+            acc += 0.5f;
+            clamped[3 * i + ch] = acc < 0.0f;
+            rgb[3 * i + ch] = fmaxf(acc, 0.0f);
+        }
+        depth[i] = t[2];
+        radii[i] = rad;
+        mean2D[2 * i] = mx; mean2D[2 * i + 1] = my;
+        for (int k = 0; k < 6; k++) cov3D[6 * i + k] = c6[k];
+        conic_opacity[4 * i] = cA; conic_opacity[4 * i + 1] = cB; conic_opacity[4 * i + 2] = cC;
+        conic_opacity[4 * i + 3] = a.o;
+        tiles_touched[i] = (uint32_t)area;
+        rect[4 * i] = minx; rect[4 * i + 1] = miny; rect[4 * i + 2] = maxx; rect[4 * i + 3] = maxy;
+    }
+}
+
+int64_t orc_scan_tiles(int32_t N, const uint32_t* tiles_touched, uint32_t* point_offsets) {
+    uint64_t run = 0;
+    for (int i = 0; i < N; i++) { run += tiles_touched[i]; point_offsets[i] = (uint32_t)run; }
+    return (int64_t)run;
+}
+
+/* stable LSD radix sort of (key,value) pairs on the low `bits` bits (B.2: CUB SortPairs semantics) */
+static void radix_sort_pairs(uint64_t* k, uint32_t* v, int64_t n, int bits) {
+    uint64_t* k2 = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)(n > 0 ? n : 1));
+    uint32_t* v2 = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(n > 0 ? n : 1));
+    for (int sh = 0; sh < bits; sh += 8) {
+        size_t cnt[257]; memset(cnt, 0, sizeof cnt);
+        for (int64_t i = 0; i < n; i++) cnt[((k[i] >> sh) & 255) + 1]++;
+        for (int d = 0; d < 256; d++) cnt[d + 1] += cnt[d];
+        for (int64_t i = 0; i < n; i++) { size_t p = cnt[(k[i] >> sh) & 255]++; k2[p] = k[i]; v2[p] = v[i]; }
+        memcpy(k, k2, sizeof(uint64_t) * (size_t)n); memcpy(v, v2, sizeof(uint32_t) * (size_t)n);
+    }
+    free(k2); free(v2);
+}
+
+void orc_bin_sort(const orc_camera* cam, int32_t N, const float* depth, const int32_t* radii,
+                  const int32_t* rect, const uint32_t* point_offsets, int64_t D, uint64_t* keys,
+                  uint32_t* point_list, uint32_t* ranges) {
+    const int gx = (cam->width + TILE - 1) / TILE, gy = (cam->height + TILE - 1) / TILE;
+    const int T = gx * gy;
+    /* A3 duplicateWithKeys: y outer, x inner; key = tile<<32 | depth bits; value = index */
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < N; i++) {
+        if (radii[i] <= 0) continue;
+        int64_t off = i == 0 ? 0 : point_offsets[i - 1];
+        for (int y = rect[4 * i + 1]; y < rect[4 * i + 3]; y++)
+            for (int x = rect[4 * i]; x < rect[4 * i + 2]; x++) {
+                uint64_t key = (uint64_t)(uint32_t)(y * gx + x);
+                key = (key << 32) | f2u(depth[i]);
+                keys[off] = key; point_list[off] = (uint32_t)i; off++;
+            }
+    }
+    int tb = 0; while ((1 << tb) < T) tb++; /* bits needed for tile ids < T */
+    radix_sort_pairs(keys, point_list, D, 32 + tb + ((32 + tb) % 8 ? 8 - (32 + tb) % 8 : 0));
+    /* A5 identifyTileRanges */
+    memset(ranges, 0, sizeof(uint32_t) * 2 * (size_t)T);
+    for (int64_t j = 0; j < D; j++) {
+        uint32_t tile = (uint32_t)(keys[j] >> 32);
+        if (j == 0 || tile != (uint32_t)(keys[j - 1] >> 32)) {
+            ranges[2 * tile] = (uint32_t)j;
+            if (j > 0) ranges[2 * (uint32_t)(keys[j - 1] >> 32) + 1] = (uint32_t)j;
+        }
+        if (j == D - 1) ranges[2 * tile + 1] = (uint32_t)D;
+    }
+}
+
+/* A6: B.3; alpha falloff/clamp mirrored (different kernel scale) at gsplat_ps.hlsl:60-66,85 */
+void orc_render_fwd(const orc_camera* cam, const uint32_t* ranges, const uint32_t* point_list,
+                    const float* mean2D, const float* conic_opacity, const float* rgb, float* out_color,
+                    float* final_T, uint32_t* n_contrib, uint8_t* fragile, int32_t threads) {
+    const int W = cam->width, H = cam->height;
+    const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+    const size_t P = (size_t)W * H;
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int tile = 0; tile < gx * gy; tile++) {
+        const uint32_t r0 = ranges[2 * tile], r1 = ranges[2 * tile + 1];
+        const int tx0 = (tile % gx) * TILE, ty0 = (tile / gx) * TILE;
+        for (int ly = 0; ly < TILE; ly++)
+            for (int lx = 0; lx < TILE; lx++) {
+                const int px = tx0 + lx, py = ty0 + ly;
+                if (px >= W || py >= H) continue;
+                const float pxf = (float)px, pyf = (float)py;
+                float T = 1.0f, C[3] = {0, 0, 0};
+                uint32_t contributor = 0, last = 0;
+                uint8_t frag = 0;
+                for (uint32_t j = r0; j < r1; j++) {
+                    contributor++;
+                    const uint32_t g = point_list[j];
+                    const float dx = mean2D[2 * g] - pxf, dy = mean2D[2 * g + 1] - pyf;
+                    const float cA = conic_opacity[4 * g], cB = conic_opacity[4 * g + 1];
+                    const float cC = conic_opacity[4 * g + 2], o = conic_opacity[4 * g + 3];
+                    const float power = -0.5f * (cA * dx * dx + cC * dy * dy) - cB * dx * dy;
+                    const float mag = 0.5f * (fabsf(cA) * dx * dx + fabsf(cC) * dy * dy) + fabsf(cB * dx * dy);
+                    if (fabsf(power) <= 4e-6f * mag && mag > 0.0f) frag = 1;
+                    if (power > 0.0f) continue;
+                    const float araw = o * expf(power);
+                    const float alpha = fminf(0.99f, araw);
+                    if (fabsf(araw - (1.0f / 255.0f)) <= (1.0f / 255.0f) * 3e-5f) frag = 1;
+                    if (alpha < 1.0f / 255.0f) continue;
+                    const float test_T = T * (1.0f - alpha);
+                    if (fabsf(test_T - 1e-4f) <= 1e-4f * 2e-3f) frag = 1;
+                    if (test_T < 1e-4f) break;
+                    const float w = alpha * T;
+                    C[0] += rgb[3 * g] * w; C[1] += rgb[3 * g + 1] * w; C[2] += rgb[3 * g + 2] * w;
+                    T = test_T;
+                    last = contributor;
+                }
+                const size_t pix = (size_t)py * W + px;
+                final_T[pix] = T;
+                n_contrib[pix] = last;
+                if (fragile) fragile[pix] = frag;
+                for (int ch = 0; ch < 3; ch++) out_color[ch * P + pix] = C[ch] + T * cam->bg[ch];
+            }
+    }
+}
+
+static inline void atomic_addf(float* p, float v) {
+#pragma omp atomic
+    *p += v;
+}
+
+/* A7: B.4 reverse walk.  No in-tree corroboration (the viewer has no backward). */
+void orc_render_bwd(const orc_camera* cam, int32_t N, const uint32_t* ranges, const uint32_t* point_list,
+                    const float* mean2D, const float* conic_opacity, const float* rgb, const float* final_T,
+                    const uint32_t* n_contrib, const float* dL_dpix, float* dL_dmean2D,
+                    float* dL_dmean2D_abs, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+                    int32_t threads) {
+    const int W = cam->width, H = cam->height;
+    const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+    const size_t P = (size_t)W * H;
+    memset(dL_dmean2D, 0, sizeof(float) * 2 * (size_t)N);
+    if (dL_dmean2D_abs) memset(dL_dmean2D_abs, 0, sizeof(float) * 2 * (size_t)N);
+    memset(dL_dconic, 0, sizeof(float) * 3 * (size_t)N);
+    memset(dL_dopacity, 0, sizeof(float) * (size_t)N);
+    memset(dL_dcolor, 0, sizeof(float) * 3 * (size_t)N);
+    const float ddelx_dx = 0.5f * (float)W, ddely_dy = 0.5f * (float)H;
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int tile = 0; tile < gx * gy; tile++) {
+        const uint32_t r0 = ranges[2 * tile], r1 = ranges[2 * tile + 1];
+        const int tx0 = (tile % gx) * TILE, ty0 = (tile / gx) * TILE;
+        for (int ly = 0; ly < TILE; ly++)
+            for (int lx = 0; lx < TILE; lx++) {
+                const int px = tx0 + lx, py = ty0 + ly;
+                if (px >= W || py >= H) continue;
+                const size_t pix = (size_t)py * W + px;
+                const float pxf = (float)px, pyf = (float)py;
+                const float T_final = final_T[pix];
+                float T = T_final;
+                const uint32_t last_contributor = n_contrib[pix];
+                float accum_rec[3] = {0, 0, 0}, last_color[3] = {0, 0, 0}, last_alpha = 0.0f;
+                const float dp[3] = {dL_dpix[pix], dL_dpix[P + pix], dL_dpix[2 * P + pix]};
+                uint32_t contributor = r1 - r0;
+                for (uint32_t j = r1; j-- > r0;) {
+                    contributor--;
+                    if (contributor >= last_contributor) continue;
+                    const uint32_t g = point_list[j];
+                    const float dx = mean2D[2 * g] - pxf, dy = mean2D[2 * g + 1] - pyf;
+                    const float cA = conic_opacity[4 * g], cB = conic_opacity[4 * g + 1];
+                    const float cC = conic_opacity[4 * g + 2], o = conic_opacity[4 * g + 3];
+                    const float power = -0.5f * (cA * dx * dx + cC * dy * dy) - cB * dx * dy;
+                    if (power > 0.0f) continue;
+                    const float G = expf(power);
+                    const float alpha = fminf(0.99f, o * G);
+                    if (alpha < 1.0f / 255.0f) continue;
+                    T = T / (1.0f - alpha);
+                    const float dchannel_dcolor = alpha * T;
+                    float dL_dalpha = 0.0f;
+                    for (int ch = 0; ch < 3; ch++) {
+                        const float c = rgb[3 * g + ch];
+                        accum_rec[ch] = last_alpha * last_color[ch] + (1.0f - last_alpha) * accum_rec[ch];
+                        last_color[ch] = c;
+                        dL_dalpha += (c - accum_rec[ch]) * dp[ch];
+                        atomic_addf(&dL_dcolor[3 * g + ch], dchannel_dcolor * dp[ch]);
+                    }
+                    dL_dalpha *= T;
+                    last_alpha = alpha;
+                    float bg_dot = 0.0f;
+                    for (int ch = 0; ch < 3; ch++) bg_dot += cam->bg[ch] * dp[ch];
+                    dL_dalpha += (-T_final / (1.0f - alpha)) * bg_dot;
+                    const float dL_dG = o * dL_dalpha;
+                    const float gdx = G * dx, gdy = G * dy;
+                    const float dG_ddelx = -gdx * cA - gdy * cB;
+                    const float dG_ddely = -gdy * cC - gdx * cB;
+                    const float gmx = dL_dG * dG_ddelx * ddelx_dx, gmy = dL_dG * dG_ddely * ddely_dy;
+                    atomic_addf(&dL_dmean2D[2 * g], gmx);
+                    atomic_addf(&dL_dmean2D[2 * g + 1], gmy);
+                    if (dL_dmean2D_abs) {
+                        atomic_addf(&dL_dmean2D_abs[2 * g], fabsf(gmx));
+                        atomic_addf(&dL_dmean2D_abs[2 * g + 1], fabsf(gmy));
+                    }
+                    atomic_addf(&dL_dconic[3 * g], -0.5f * gdx * dx * dL_dG);
+                    atomic_addf(&dL_dconic[3 * g + 1], -gdx * dy * dL_dG); /* TOTAL off-diagonal gradient */
+                    atomic_addf(&dL_dconic[3 * g + 2], -0.5f * gdy * dy * dL_dG);
+                    atomic_addf(&dL_dopacity[g], G * dL_dalpha);
+                }
+            }
+    }
+}
+
+/* A8: B.5.  Forward counterparts: gsplat_intersect.hlsl:61-134, gsplat_sh.hlsl:64-103. */
+void orc_preprocess_bwd(const orc_camera* cam, int32_t N, const float* means3D, const float* scales,
+                        const float* quats, const float* opacities, const float* sh0, const float* shN,
+                        const int32_t* radii, const uint8_t* clamped, const float* dL_dmean2D,
+                        const float* dL_dconic, const float* dL_dopacity_act, const float* dL_dcolor,
+                        float* dL_dmeans3D, float* dL_dscales, float* dL_dquats, float* dL_dopacities,
+                        float* dL_dsh0, float* dL_dshN) {
+    const int deg = cam->sh_degree, K = (deg + 1) * (deg + 1), KR = cam->sh_rest_alloc;
+    const float* V = cam->view; const float* Pm = cam->proj;
+    (void)sh0;
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < N; i++) {
+        for (int k = 0; k < 3; k++) { dL_dmeans3D[3 * i + k] = 0; dL_dscales[3 * i + k] = 0; dL_dsh0[3 * i + k] = 0; }
+        for (int k = 0; k < 4; k++) dL_dquats[4 * i + k] = 0;
+        dL_dopacities[i] = 0;
+        for (int k = 0; k < 3 * KR; k++) dL_dshN[3 * (size_t)KR * i + k] = 0;
+        if (radii[i] <= 0) continue;
+        const float* p = means3D + 3 * (size_t)i;
+        act_t a; activate(cam, scales, quats, opacities, i, &a);
+        float R[3][3], M[3][3], c6[6];
+        quat_to_R(a.q, R);
+        cov3d_from(a.s, R, M, c6);
+        float t[3]; xform43(V, p, t);
+        ewa_t e; ewa_cov2d(cam, t, c6, &e);
+        float dmean[3] = {0, 0, 0};
+
+        /* 1. conic -> cov2D: dSigma' = -Q G Q, Q = conic matrix, G = sym(dA, dB/2, dC) */
+        const float det = e.a * e.c - e.b * e.b;
+        const float kappa = 1.0f / (det * det + 1e-7f);
+        const float dA = dL_dconic[3 * i], dBh = 0.5f * dL_dconic[3 * i + 1], dC = dL_dconic[3 * i + 2];
+        float da = 0, db = 0, dc = 0;
+        if (kappa != 0.0f) {
+            da = kappa * (-e.c * e.c * dA + 2.0f * e.b * e.c * dBh + (det - e.a * e.c) * dC);
+            dc = kappa * (-e.a * e.a * dC + 2.0f * e.a * e.b * dBh + (det - e.a * e.c) * dA);
+            db = kappa * 2.0f * (e.b * e.c * dA - (det + 2.0f * e.b * e.b) * dBh + e.a * e.b * dC);
+        }
+        /* 2. cov2D -> cov3D (6 stored values; off-diagonals carry the doubled cross terms) */
+        const float (*T)[3] = e.T;
+        float dcov[6];
+        dcov[0] = T[0][0] * T[0][0] * da + T[0][0] * T[1][0] * db + T[1][0] * T[1][0] * dc;
+        dcov[3] = T[0][1] * T[0][1] * da + T[0][1] * T[1][1] * db + T[1][1] * T[1][1] * dc;
+        dcov[5] = T[0][2] * T[0][2] * da + T[0][2] * T[1][2] * db + T[1][2] * T[1][2] * dc;
+        dcov[1] = 2 * T[0][0] * T[0][1] * da + (T[0][0] * T[1][1] + T[0][1] * T[1][0]) * db + 2 * T[1][0] * T[1][1] * dc;
+        dcov[2] = 2 * T[0][0] * T[0][2] * da + (T[0][0] * T[1][2] + T[0][2] * T[1][0]) * db + 2 * T[1][0] * T[1][2] * dc;
+        dcov[4] = 2 * T[0][2] * T[0][1] * da + (T[0][1] * T[1][2] + T[0][2] * T[1][1]) * db + 2 * T[1][1] * T[1][2] * dc;
+        /* cov2D -> T: dT = 2 G' T Sigma, G' = [[da, db/2],[db/2, dc]] */
+        const float S[3][3] = {{c6[0], c6[1], c6[2]}, {c6[1], c6[3], c6[4]}, {c6[2], c6[4], c6[5]}};
+        float TS[2][3];
+        for (int r = 0; r < 2; r++)
+            for (int j = 0; j < 3; j++) TS[r][j] = T[r][0] * S[0][j] + T[r][1] * S[1][j] + T[r][2] * S[2][j];
+        float dT[2][3];
+        for (int j = 0; j < 3; j++) {
+            dT[0][j] = 2.0f * da * TS[0][j] + db * TS[1][j];
+            dT[1][j] = 2.0f * dc * TS[1][j] + db * TS[0][j];
+        }
+        /* T = J W  ->  dJ = dT W^T (non-zero J entries only); W_rc = V[4c+r] */
+        float dJ00 = 0, dJ02 = 0, dJ11 = 0, dJ12 = 0;
+        for (int j = 0; j < 3; j++) {
+            dJ00 += V[4 * j + 0] * dT[0][j];
+            dJ02 += V[4 * j + 2] * dT[0][j];
+            dJ11 += V[4 * j + 1] * dT[1][j];
+            dJ12 += V[4 * j + 2] * dT[1][j];
+        }
+        const float tz = 1.0f / e.tz, tz2 = tz * tz, tz3 = tz2 * tz;
+        const float mx_ = (e.txtz < -e.limx || e.txtz > e.limx) ? 0.0f : 1.0f;
+        const float my_ = (e.tytz < -e.limy || e.tytz > e.limy) ? 0.0f : 1.0f;
+        float dt[3];
+        dt[0] = mx_ * (-e.fx * tz2) * dJ02;
+        dt[1] = my_ * (-e.fy * tz2) * dJ12;
+        dt[2] = -e.fx * tz2 * dJ00 - e.fy * tz2 * dJ11 + (2.0f * e.fx * e.tx) * tz3 * dJ02 +
+                (2.0f * e.fy * e.ty) * tz3 * dJ12;
+        for (int c = 0; c < 3; c++) dmean[c] += V[4 * c + 0] * dt[0] + V[4 * c + 1] * dt[1] + V[4 * c + 2] * dt[2];
+
+        /* 3. projection: mean2D (ndc-scaled gradient) -> mean3D */
+        {
+            float h[4]; xform44(Pm, p, h);
+            const float m_w = 1.0f / (h[3] + 1e-7f);
+            const float mul1 = h[0] * m_w * m_w, mul2 = h[1] * m_w * m_w;
+            const float g0 = dL_dmean2D[2 * i], g1 = dL_dmean2D[2 * i + 1];
+            for (int c = 0; c < 3; c++)
+                dmean[c] += (Pm[4 * c + 0] * m_w - Pm[4 * c + 3] * mul1) * g0 +
+                            (Pm[4 * c + 1] * m_w - Pm[4 * c + 3] * mul2) * g1;
+        }
+
+        /* 4. SH: colour -> coefficients and -> direction -> mean */
+        {
+            float dir_o[3] = {p[0] - cam->campos[0], p[1] - cam->campos[1], p[2] - cam->campos[2]};
+            const float len = sqrtf(dir_o[0] * dir_o[0] + dir_o[1] * dir_o[1] + dir_o[2] * dir_o[2]);
+            const float d[3] = {dir_o[0] / len, dir_o[1] / len, dir_o[2] / len};
+            float bas[16]; sh_basis(deg, d, bas);
+            float dcol[3];
+            for (int ch = 0; ch < 3; ch++) dcol[ch] = clamped[3 * i + ch] ? 0.0f : dL_dcolor[3 * i + ch];
+            for (int ch = 0; ch < 3; ch++) dL_dsh0[3 * i + ch] = bas[0] * dcol[ch];
+            for (int k = 1; k < K; k++)
+                for (int ch = 0; ch < 3; ch++) dL_dshN[3 * ((size_t)i * KR + (k - 1)) + ch] = bas[k] * dcol[ch];
+            /* d(basis_k)/d(x,y,z) */
+            float gb[16][3]; memset(gb, 0, sizeof gb);
+            const float x = d[0], y = d[1], z = d[2];
+            if (deg >= 1) { gb[1][1] = -SH_C1; gb[2][2] = SH_C1; gb[3][0] = -SH_C1; }
+            if (deg >= 2) {
+                const float xx = x * x, yy = y * y, zz = z * z;
+                gb[4][0] = SH_C2[0] * y; gb[4][1] = SH_C2[0] * x;
+                gb[5][1] = SH_C2[1] * z; gb[5][2] = SH_C2[1] * y;
+                gb[6][0] = SH_C2[2] * -2.0f * x; gb[6][1] = SH_C2[2] * -2.0f * y; gb[6][2] = SH_C2[2] * 4.0f * z;
+                gb[7][0] = SH_C2[3] * z; gb[7][2] = SH_C2[3] * x;
+                gb[8][0] = SH_C2[4] * 2.0f * x; gb[8][1] = SH_C2[4] * -2.0f * y;
+                if (deg >= 3) {
+                    gb[9][0] = SH_C3[0] * 6.0f * x * y; gb[9][1] = SH_C3[0] * (3.0f * xx - 3.0f * yy);
+                    gb[10][0] = SH_C3[1] * y * z; gb[10][1] = SH_C3[1] * x * z; gb[10][2] = SH_C3[1] * x * y;
+                    gb[11][0] = SH_C3[2] * -2.0f * x * y; gb[11][1] = SH_C3[2] * (4.0f * zz - xx - 3.0f * yy);
+                    gb[11][2] = SH_C3[2] * 8.0f * y * z;
+                    gb[12][0] = SH_C3[3] * -6.0f * x * z; gb[12][1] = SH_C3[3] * -6.0f * y * z;
+                    gb[12][2] = SH_C3[3] * (6.0f * zz - 3.0f * xx - 3.0f * yy);
+                    gb[13][0] = SH_C3[4] * (4.0f * zz - 3.0f * xx - yy); gb[13][1] = SH_C3[4] * -2.0f * x * y;
+                    gb[13][2] = SH_C3[4] * 8.0f * x * z;
+                    gb[14][0] = SH_C3[5] * 2.0f * x * z; gb[14][1] = SH_C3[5] * -2.0f * y * z;
+                    gb[14][2] = SH_C3[5] * (xx - yy);
+                    gb[15][0] = SH_C3[6] * (3.0f * xx - 3.0f * yy); gb[15][1] = SH_C3[6] * -6.0f * x * y;
+                }
+            }
+            float ddir[3] = {0, 0, 0};
+            for (int k = 1; k < K; k++) {
+                float s = 0.0f;
+                for (int ch = 0; ch < 3; ch++) s += shN[3 * ((size_t)i * KR + (k - 1)) + ch] * dcol[ch];
+                ddir[0] += gb[k][0] * s; ddir[1] += gb[k][1] * s; ddir[2] += gb[k][2] * s;
+            }
+            /* normalisation Jacobian: (I - d d^T)/len */
+            const float dd = d[0] * ddir[0] + d[1] * ddir[1] + d[2] * ddir[2];
+            for (int c = 0; c < 3; c++) dmean[c] += (ddir[c] - d[c] * dd) / len;
+        }
+        for (int c = 0; c < 3; c++) dL_dmeans3D[3 * i + c] = dmean[c];
+
+        /* 5. cov3D -> scale, rotation.  Sigma = Mr Mr^T, Mr = R diag(s) */
+        {
+            const float dS[3][3] = {{dcov[0], 0.5f * dcov[1], 0.5f * dcov[2]},
+                                    {0.5f * dcov[1], dcov[3], 0.5f * dcov[4]},
+                                    {0.5f * dcov[2], 0.5f * dcov[4], dcov[5]}};
+            float dM[3][3];
+            for (int r = 0; r < 3; r++)
+                for (int k = 0; k < 3; k++)
+                    dM[r][k] = 2.0f * (dS[r][0] * M[0][k] + dS[r][1] * M[1][k] + dS[r][2] * M[2][k]);
+            float ds[3], dR[3][3];
+            for (int k = 0; k < 3; k++) {
+                ds[k] = R[0][k] * dM[0][k] + R[1][k] * dM[1][k] + R[2][k] * dM[2][k];
+                for (int r = 0; r < 3; r++) dR[r][k] = dM[r][k] * a.s[k];
+            }
+            const float r = a.q[0], x = a.q[1], y = a.q[2], z = a.q[3];
+            float dq[4];
+            dq[0] = 2.0f * (z * (dR[1][0] - dR[0][1]) + y * (dR[0][2] - dR[2][0]) + x * (dR[2][1] - dR[1][2]));
+            dq[1] = 2.0f * (y * (dR[0][1] + dR[1][0]) + z * (dR[0][2] + dR[2][0]) + r * (dR[2][1] - dR[1][2])) -
+                    4.0f * x * (dR[1][1] + dR[2][2]);
+            dq[2] = 2.0f * (x * (dR[0][1] + dR[1][0]) + r * (dR[0][2] - dR[2][0]) + z * (dR[1][2] + dR[2][1])) -
+                    4.0f * y * (dR[0][0] + dR[2][2]);
+            dq[3] = 2.0f * (r * (dR[1][0] - dR[0][1]) + x * (dR[0][2] + dR[2][0]) + y * (dR[1][2] + dR[2][1])) -
+                    4.0f * z * (dR[0][0] + dR[1][1]);
+            /* 6. activations (chain rule to the stored raw parameters) */
+            if (cam->flags & ORC_FLAG_INPUT_ACTIVATED) {
+                for (int k = 0; k < 3; k++) dL_dscales[3 * i + k] = ds[k] * cam->scale_modifier;
+                for (int k = 0; k < 4; k++) dL_dquats[4 * i + k] = dq[k];
+                dL_dopacities[i] = dL_dopacity_act[i];
+            } else {
+                for (int k = 0; k < 3; k++) dL_dscales[3 * i + k] = ds[k] * a.s[k];
+                const float qd = a.q[0] * dq[0] + a.q[1] * dq[1] + a.q[2] * dq[2] + a.q[3] * dq[3];
+                for (int k = 0; k < 4; k++) dL_dquats[4 * i + k] = (dq[k] - a.q[k] * qd) / a.qlen;
+                dL_dopacities[i] = dL_dopacity_act[i] * a.o * (1.0f - a.o);
+            }
+        }
+    }
+}
