@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""bench.py — forward+backward Gaussians/s of the rasterize hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W          our CUDA path (one process per GPU; torchrun for N>1)
+  python bench.py --impl reference --gpus N ...          the CPU baseline arm (oracle port on the host cores)
+
+A "step" is one forward+backward rasterize of one view per rank (weak scaling: every extra GPU renders
+one more view of the same 1M-Gaussian scene, then a single NCCL all-reduce sums the dense per-Gaussian
+gradient arena).  N=1 is BASELINE config c3 (1M Gaussians, 1600x1000, SH degree 3); N>1 are views of c4.
+Timed with CUDA events over exactly K steps between barrier+synchronize pairs, max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "c3"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, reasons, mx = [], set(), None
+        for r in rows:
+            try:
+                r = [x.strip() for x in r]
+                sm.append(float(r[1])); mx = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if sm:
+            sm.sort()
+            load = [s for s in sm if s >= 0.5 * max(sm)]
+            out.update(sm_mhz=load[len(load) // 2], sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def algorithmic_bytes(N, K, V, D, T, P):
+    """SURVEY.md §8(d) contract figure (compulsory traffic, infinite-L2 model)."""
+    pb = 44 + 12 * K
+    stages = {
+        "preprocess_fwd": N * pb + 48 * V,
+        "binning_sort": 28 * D + 8 * T,          # tile_scan + emit + tile_sort
+        "render_fwd": 4 * D + 36 * V + 20 * P,
+        "render_bwd": 20 * P + 4 * D + 36 * V + 36 * V,
+        "preprocess_bwd": 36 * V + V * pb + N * pb,
+    }
+    return stages, sum(stages.values())
+
+
+def run_cpu_sample(threads=0, reps=1, frac_lin=2):
+    """Oracle (port) fwd+bwd on a density-preserving 1/frac_lin^2 crop of the workload; returns Gaussians/s."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from divshot_b200.scenes import crop_of
+    from oracle import oracle as orc
+    sc = crop_of(WORKLOAD, frac_lin)
+    cam = sc.cameras[0]
+    oc = orc.make_camera(cam.view, cam.proj, cam.campos, cam.tanfovx, cam.tanfovy, cam.width, cam.height, cam.bg,
+                         1.0, sc.sh_degree)
+    arrays = (sc.means3D, sc.log_scales, sc.quats, sc.logit_opac, sc.sh0, sc.shN)
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        f = orc.forward(oc, *arrays, threads=threads)
+        orc.backward(oc, f, *arrays, sc.dL_dpix[0], threads=threads)
+        times.append(time.perf_counter() - t0)
+    cores = os.cpu_count() if threads <= 0 else threads
+    sample = (f"oracle port, density-preserving 1/{frac_lin * frac_lin} crop of {WORKLOAD}: {sc.N} Gaussians, "
+              f"{cam.width}x{cam.height}, SH deg {sc.sh_degree}, fwd+bwd, OpenMP over Gaussians/tiles")
+    return sc.N, times, cores, sample
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    for _ in range(args.warmup):
+        run_cpu_sample(reps=1)
+    n, times, cores, sample = run_cpu_sample(reps=args.steps)
+    total = sum(times)
+    val = n * args.steps / total
+    line = {"impl": "reference", "metric": "fwd+bwd Gaussians/s", "value": val, "unit": "Gaussians/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{WORKLOAD} (1M Gaussians, 1600x1000, SH deg 3), CPU arm on a bounded sample"},
+            "cpu_baseline": {"value": val, "unit": "Gaussians/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "Gaussians/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "the reference ships no implementation of this path (SURVEY.md §0): kind=port is the CPU oracle"}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, help="override: c2|c3|c5 (parity/bench exploration only)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    global WORKLOAD
+    if args.workload:
+        WORKLOAD = args.workload
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from divshot_b200 import _cabi
+    from divshot_b200.rasterizer import GradBuffers, Rasterizer, scene_to_device
+    from divshot_b200.scenes import CONFIGS, make_scene
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch N>1 with torch.distributed.run)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # scene: same Gaussians on every rank (replicas), one distinct view per rank
+    views = max(world, 1)
+    sc = make_scene(WORKLOAD, views=views) if world > 1 else make_scene(WORKLOAD)
+    _, N, W, H, deg, _ = CONFIGS[WORKLOAD]
+    K = (deg + 1) ** 2
+    cam = _cabi.make_camera(sc.cameras[rank % len(sc.cameras)], deg)
+    params = scene_to_device(sc, dev)
+    dl_host = torch.from_numpy(sc.dL_dpix[rank % len(sc.dL_dpix)]).pin_memory()
+    dl = dl_host.to(dev)
+    img_host = torch.empty(3, H, W, dtype=torch.float32).pin_memory()
+    grads = GradBuffers.allocate(N, K - 1, dev)
+    rast = Rasterizer(local)
+    rast.reserve(N, W, H, 0)
+    img = torch.empty(3, H, W, device=dev)
+    radii = torch.empty(N, dtype=torch.int32, device=dev)
+
+    def step_resident():
+        rast.forward(cam, params, img, radii)
+        rast.backward(dl, grads)
+        if world > 1:
+            dist.all_reduce(grads.flat)
+
+    def step_e2e():
+        rast.step_host(cam, params, grads, dl_host, img_host)
+        if world > 1:
+            dist.all_reduce(grads.flat)
+
+    def timed(fn, steps, warmup, sample_clocks=False):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local) if sample_clocks else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stage_acc = {}
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if sampler else None
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), clocks
+
+    warm = max(args.warmup, 3)
+    ms_total, clocks = timed(step_resident, args.steps, warm, sample_clocks=True)
+    # per-stage device times (CUDA events recorded on the launch stream inside the library), averaged over a few steps
+    stage_ms = {}
+    reps = 5
+    for _ in range(reps):
+        rast.forward(cam, params, img, radii)
+        rast.backward(dl, grads)
+        for k, v in rast.stage_ms().items():
+            stage_ms[k] = stage_ms.get(k, 0.0) + v / reps
+    st = rast.stats()
+    ms_e2e, _ = timed(step_e2e, args.steps, warm)
+
+    ms_step = ms_total / args.steps
+    value = N * world / (ms_step * 1e-3)
+    e2e_value = N * world / (ms_e2e / args.steps * 1e-3)
+    peak, peak_src = _peaks()
+    V, D, T, P = st["num_visible"], st["num_dups"], st["tiles_x"] * st["tiles_y"], W * H
+    stage_bytes, total_bytes = algorithmic_bytes(N, K, V, D, T, P)
+    merged = {"preprocess_fwd": stage_ms["preprocess_fwd"],
+              "binning_sort": stage_ms["tile_scan"] + stage_ms["emit"] + stage_ms["tile_sort"],
+              "render_fwd": stage_ms["render_fwd"], "render_bwd": stage_ms["render_bwd"],
+              "preprocess_bwd": stage_ms["preprocess_bwd"]}
+    dominant = max(merged, key=merged.get)
+    stages = {k: {"ms": round(merged[k], 4), "alg_MB": round(stage_bytes[k] / 1e6, 2),
+                  "GBps": round(stage_bytes[k] / 1e9 / (merged[k] * 1e-3), 1) if merged[k] > 0 else None,
+                  "frac_hbm": round(stage_bytes[k] / 1e9 / (merged[k] * 1e-3) / peak, 4) if merged[k] > 0 else None}
+              for k in merged}
+    dom_gbs = stage_bytes[dominant] / 1e9 / (merged[dominant] * 1e-3)
+    step_gbs = total_bytes / 1e9 / (ms_step * 1e-3) if world == 1 else None
+
+    line = {
+        "metric": "fwd+bwd Gaussians/s", "value": value, "unit": "Gaussians/s", "n_gpus": world, "steps": args.steps,
+        "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{WORKLOAD}: {N} Gaussians, {W}x{H}, SH deg {deg}, 1 view per rank per step"
+                               + (", NCCL all-reduce of the dense gradient arena" if world > 1 else ""),
+                   "N": N, "width": W, "height": H, "sh_degree": deg, "views_per_step": world,
+                   "visible": V, "duplicates": D, "tiles": T, "max_tile_len": st["max_tile_len"],
+                   "l2": "inputs larger than L2 (params+grads 472 MB + 96 MB records/lists per step); no explicit flush",
+                   "parallelism": f"dp{world} (view-sharded replicas)"},
+        "roofline": {"bound": "hbm", "kernel": dominant, "achieved": dom_gbs, "peak": peak, "unit": "GB/s",
+                     "frac": dom_gbs / peak, "traffic": None, "peak_source": peak_src,
+                     "note": "algorithmic bytes per SURVEY.md §8(d) / CUDA-event stage time; compositing is issue-bound"},
+        "roofline_step": ({"achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak,
+                           "alg_bytes_per_step": total_bytes} if step_gbs else None),
+        "stages": stages,
+        "e2e": {"value": e2e_value, "unit": "Gaussians/s", "h2d_bytes_per_step": 12 * P * world,
+                "d2h_bytes_per_step": 12 * P * world, "ms_per_step": ms_e2e / args.steps,
+                "api": "dvs_rast_step_host (C-ABI): pinned dL/dpix H2D, forward, image D2H, backward; parameters and "
+                       "gradients device-resident as in the trainer"},
+        "gpu_launches": 10 * args.steps,
+        "clocks": clocks,
+    }
+    if world == 1 and rank == 0 and not args.no_cpu:
+        n_s, times, cores, sample = run_cpu_sample(reps=3)
+        best = min(times)
+        line["cpu_baseline"] = {"value": n_s / best, "unit": "Gaussians/s", "cores": cores, "kind": "port",
+                                "sample": sample + f"; best of 3 ({best:.2f} s)"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    rast.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,107 @@
+"""ctypes binding of the C-ABI in include/dvs_rast.h (the only way Python reaches the kernels).
+
+There is deliberately no CPU / PyTorch fallback: if libdvsrast.so is missing or no CUDA device is
+usable, importing the library or creating a context raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libdvsrast.so")
+
+FLAG_INPUT_ACTIVATED = 1
+FLAG_ACCUMULATE = 2
+FLAG_ABSGRAD = 4
+NUM_STAGES = 8
+
+(BUF_RADII, BUF_TILES_TOUCHED, BUF_DEPTH, BUF_MEAN2D, BUF_CONIC_OPACITY, BUF_RGB, BUF_CLAMPED, BUF_POINT_LIST,
+ BUF_RANGES, BUF_FINAL_T, BUF_N_CONTRIB, BUF_CULL_MASK, BUF_SCREEN_GRADS) = range(13)
+
+EXPORTS = [
+    "dvs_rast_create", "dvs_rast_destroy", "dvs_rast_last_error", "dvs_rast_version", "dvs_rast_reserve",
+    "dvs_rast_forward", "dvs_rast_backward", "dvs_rast_step_host", "dvs_rast_get_stats", "dvs_rast_debug_read",
+    "dvs_rast_stage_ms", "dvs_rast_stage_name",
+]
+
+
+class DvsCamera(C.Structure):
+    _fields_ = [("view", C.c_float * 16), ("proj", C.c_float * 16), ("campos", C.c_float * 3),
+                ("tanfovx", C.c_float), ("tanfovy", C.c_float), ("width", C.c_int32), ("height", C.c_int32),
+                ("bg", C.c_float * 3), ("scale_modifier", C.c_float), ("sh_degree", C.c_int32),
+                ("sh_rest_alloc", C.c_int32), ("flags", C.c_uint32)]
+
+
+class DvsParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("means3D", "scales", "quats", "opacities", "sh0", "shN")]
+
+
+class DvsGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("means3D", "scales", "quats", "opacities", "sh0", "shN", "mean2D_abs",
+                                         "mean2D")]
+
+
+class DvsStats(C.Structure):
+    _fields_ = [("num_gaussians", C.c_int64), ("num_visible", C.c_int64), ("num_dups", C.c_int64),
+                ("dup_capacity", C.c_int64), ("max_tile_len", C.c_int64), ("tiles_x", C.c_int32),
+                ("tiles_y", C.c_int32), ("overflow", C.c_int32)]
+
+
+_lib = None
+
+
+def load():
+    """Load libdvsrast.so (raises if it has not been built — no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -m divshot_b200.build` (or __graft_entry__.build()); "
+                           "there is no CPU fallback for the rasterizer")
+    L = C.CDLL(LIB_PATH)
+    L.dvs_rast_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    L.dvs_rast_create.restype = C.c_int
+    L.dvs_rast_destroy.argtypes = [C.c_void_p]
+    L.dvs_rast_destroy.restype = None
+    L.dvs_rast_last_error.argtypes = [C.c_void_p]
+    L.dvs_rast_last_error.restype = C.c_char_p
+    L.dvs_rast_version.restype = C.c_char_p
+    L.dvs_rast_reserve.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int64]
+    L.dvs_rast_reserve.restype = C.c_int
+    L.dvs_rast_forward.argtypes = [C.c_void_p, C.POINTER(DvsCamera), C.c_int64, C.POINTER(DvsParams), C.c_void_p,
+                                   C.c_void_p, C.c_void_p]
+    L.dvs_rast_forward.restype = C.c_int
+    L.dvs_rast_backward.argtypes = [C.c_void_p, C.POINTER(DvsParams), C.c_void_p, C.POINTER(DvsGrads), C.c_uint32,
+                                    C.c_void_p]
+    L.dvs_rast_backward.restype = C.c_int
+    L.dvs_rast_step_host.argtypes = [C.c_void_p, C.POINTER(DvsCamera), C.c_int64, C.POINTER(DvsParams),
+                                     C.POINTER(DvsGrads), C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    L.dvs_rast_step_host.restype = C.c_int
+    L.dvs_rast_get_stats.argtypes = [C.c_void_p, C.POINTER(DvsStats)]
+    L.dvs_rast_get_stats.restype = C.c_int
+    L.dvs_rast_debug_read.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+    L.dvs_rast_debug_read.restype = C.c_int
+    L.dvs_rast_stage_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float * NUM_STAGES)]
+    L.dvs_rast_stage_ms.restype = C.c_int
+    L.dvs_rast_stage_name.argtypes = [C.c_int]
+    L.dvs_rast_stage_name.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def make_camera(cam, sh_degree: int, sh_rest_alloc: int | None = None, flags: int = 0) -> DvsCamera:
+    """cam: divshot_b200.scenes.Camera (or anything with the same attributes)."""
+    c = DvsCamera()
+    c.view[:] = [float(x) for x in cam.view]
+    c.proj[:] = [float(x) for x in cam.proj]
+    c.campos[:] = [float(x) for x in cam.campos]
+    c.tanfovx, c.tanfovy = float(cam.tanfovx), float(cam.tanfovy)
+    c.width, c.height = int(cam.width), int(cam.height)
+    c.bg[:] = [float(x) for x in cam.bg]
+    c.scale_modifier = float(getattr(cam, "scale_modifier", 1.0))
+    c.sh_degree = int(sh_degree)
+    K = (sh_degree + 1) ** 2
+    c.sh_rest_alloc = int(K - 1 if sh_rest_alloc is None else sh_rest_alloc)
+    c.flags = int(flags)
+    return c

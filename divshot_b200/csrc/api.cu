@@ -1,0 +1,425 @@
+// api.cu — the C-ABI of include/dvs_rast.h: context, persistent arenas, stage sequencing.
+//
+// One context owns every scratch arena the rasterizer needs (screen records, tile bins, sorted lists,
+// per-pixel compositing state, screen-gradient records) so a training step allocates nothing.  The
+// credited upstream resizes byte tensors through allocator callbacks and reads the duplicate count D
+// back to the host in the middle of the pipeline; here D stays on the device —
+// the arena is sized ahead and validated once, after the forward has been enqueued.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+#include "dvs_rast.h"
+#include "kernels.h"
+
+using namespace dvs;
+
+struct dvs_rast_ctx {
+    int device = 0;
+    char err[512] = {0};
+    // per-Gaussian arenas
+    int64_t cap_gauss = 0;
+    float4* rec = nullptr;
+    uint4* aux = nullptr;
+    float4* sgrad = nullptr;
+    // per-tile
+    int64_t cap_tiles = 0;
+    uint32_t* tile_count = nullptr;
+    uint32_t* tile_base = nullptr;  // T+1
+    uint32_t* tile_cursor = nullptr;
+    // per-duplicate
+    int64_t cap_dups = 0;
+    unsigned long long* bins = nullptr;
+    uint32_t* plist = nullptr;
+    // per-pixel
+    int64_t cap_pix = 0;
+    float* final_T = nullptr;
+    uint32_t* n_contrib = nullptr;
+    float* h2d_grad = nullptr;   // [3P] staging for dvs_rast_step_host
+    float* d_image = nullptr;    // [3P]
+    // small device words + pinned mirror
+    uint32_t* info = nullptr;               // [4]: D, max len, overflow
+    unsigned long long* stats = nullptr;    // [2]: V, D
+    uint32_t* h_info = nullptr;             // pinned [4]
+    unsigned long long* h_stats = nullptr;  // pinned [2]
+    // last forward
+    bool have_fwd = false;
+    Cam cam{};
+    int64_t N = 0;
+    dvs_stats st{};
+    cudaEvent_t ev[DVS_NUM_STAGES + 2] = {};
+    bool ev_fwd = false, ev_bwd = false;
+};
+
+static int fail(dvs_rast_ctx* c, int code, const char* fmt, ...) {
+    if (c) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(c->err, sizeof c->err, fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+#define CK(call)                                                                                           \
+    do {                                                                                                   \
+        cudaError_t e__ = (call);                                                                          \
+        if (e__ != cudaSuccess)                                                                            \
+            return fail(ctx, DVS_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+template <typename T>
+static cudaError_t regrow(T*& p, size_t count) {
+    if (p) cudaFree(p);
+    p = nullptr;
+    return cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T));
+}
+
+static int ensure_gauss(dvs_rast_ctx* ctx, int64_t N) {
+    if (N <= ctx->cap_gauss) return DVS_OK;
+    const int64_t cap = N + N / 8 + 1024;
+    CK(regrow(ctx->rec, 3 * (size_t)cap));
+    CK(regrow(ctx->aux, (size_t)cap));
+    CK(regrow(ctx->sgrad, 3 * (size_t)cap));
+    CK(cudaMemset(ctx->sgrad, 0, 3 * (size_t)cap * sizeof(float4)));
+    ctx->cap_gauss = cap;
+    return DVS_OK;
+}
+static int ensure_tiles(dvs_rast_ctx* ctx, int64_t T) {
+    if (T <= ctx->cap_tiles) return DVS_OK;
+    CK(regrow(ctx->tile_count, (size_t)T));
+    CK(regrow(ctx->tile_base, (size_t)T + 1));
+    CK(regrow(ctx->tile_cursor, (size_t)T));
+    ctx->cap_tiles = T;
+    return DVS_OK;
+}
+static int ensure_dups(dvs_rast_ctx* ctx, int64_t D) {
+    if (D <= ctx->cap_dups) return DVS_OK;
+    if (D >= (int64_t)0xffffffffll) return fail(ctx, DVS_E_UNSUPPORTED, "duplicate count %lld exceeds 2^32", (long long)D);
+    CK(regrow(ctx->bins, (size_t)D));
+    CK(regrow(ctx->plist, (size_t)D));
+    ctx->cap_dups = D;
+    return DVS_OK;
+}
+static int ensure_pix(dvs_rast_ctx* ctx, int64_t P) {
+    if (P <= ctx->cap_pix) return DVS_OK;
+    CK(regrow(ctx->final_T, (size_t)P));
+    CK(regrow(ctx->n_contrib, (size_t)P));
+    if (ctx->h2d_grad) { cudaFree(ctx->h2d_grad); ctx->h2d_grad = nullptr; }
+    if (ctx->d_image) { cudaFree(ctx->d_image); ctx->d_image = nullptr; }
+    ctx->cap_pix = P;
+    return DVS_OK;
+}
+
+extern "C" {
+
+const char* dvs_rast_version(void) { return "divshot_b200 rasterizer 0.1 (sm_100a)"; }
+
+int dvs_rast_create(int device, dvs_rast_ctx** out) {
+    if (!out) return DVS_E_INVALID;
+    *out = nullptr;
+    dvs_rast_ctx* ctx = new (std::nothrow) dvs_rast_ctx();
+    if (!ctx) return DVS_E_NOMEM;
+    ctx->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->info), 4 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->stats), 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_info), 4 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_stats), 2 * sizeof(unsigned long long));
+    for (int i = 0; e == cudaSuccess && i < DVS_NUM_STAGES + 2; i++) e = cudaEventCreate(&ctx->ev[i]);
+    if (e != cudaSuccess) {
+        // the product path must fail loudly without a usable CUDA device: there is no CPU fallback.
+        fprintf(stderr, "dvs_rast_create: CUDA unavailable on device %d: %s\n", device, cudaGetErrorString(e));
+        delete ctx;
+        return DVS_E_CUDA;
+    }
+    *out = ctx;
+    return DVS_OK;
+}
+
+void dvs_rast_destroy(dvs_rast_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->rec); cudaFree(ctx->aux); cudaFree(ctx->sgrad);
+    cudaFree(ctx->tile_count); cudaFree(ctx->tile_base); cudaFree(ctx->tile_cursor);
+    cudaFree(ctx->bins); cudaFree(ctx->plist);
+    cudaFree(ctx->final_T); cudaFree(ctx->n_contrib); cudaFree(ctx->h2d_grad); cudaFree(ctx->d_image);
+    cudaFree(ctx->info); cudaFree(ctx->stats);
+    cudaFreeHost(ctx->h_info); cudaFreeHost(ctx->h_stats);
+    for (auto& e : ctx->ev)
+        if (e) cudaEventDestroy(e);
+    delete ctx;
+}
+
+const char* dvs_rast_last_error(const dvs_rast_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+
+int dvs_rast_reserve(dvs_rast_ctx* ctx, int64_t max_gaussians, int32_t max_width, int32_t max_height,
+                     int64_t dup_capacity) {
+    if (!ctx) return DVS_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if (max_gaussians > 0 && (rc = ensure_gauss(ctx, max_gaussians))) return rc;
+    if (max_width > 0 && max_height > 0) {
+        const int64_t gx = (max_width + TILE - 1) / TILE, gy = (max_height + TILE - 1) / TILE;
+        if ((rc = ensure_tiles(ctx, gx * gy))) return rc;
+        if ((rc = ensure_pix(ctx, (int64_t)max_width * max_height))) return rc;
+    }
+    if (dup_capacity > 0 && (rc = ensure_dups(ctx, dup_capacity))) return rc;
+    return DVS_OK;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int check_params(dvs_rast_ctx* ctx, const dvs_params* p, int KR) {
+    if (!p || !p->means3D || !p->scales || !p->quats || !p->opacities || !p->sh0 || (KR > 0 && !p->shN))
+        return fail(ctx, DVS_E_INVALID, "null parameter pointer");
+    if (!aligned16(p->means3D) || !aligned16(p->scales) || !aligned16(p->quats) || !aligned16(p->opacities) ||
+        !aligned16(p->sh0) || (KR > 0 && !aligned16(p->shN)))
+        return fail(ctx, DVS_E_INVALID, "parameter pointers must be 16-byte aligned");
+    return DVS_OK;
+}
+
+int dvs_rast_forward(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, const dvs_params* params,
+                     float* out_color, int32_t* out_radii, void* stream) {
+    if (!ctx) return DVS_E_INVALID;
+    if (!cam || !out_color) return fail(ctx, DVS_E_INVALID, "null camera / output");
+    if (N < 0 || N >= (int64_t)MAX_GAUSSIANS)
+        return fail(ctx, DVS_E_UNSUPPORTED, "N=%lld outside [0, 2^24)", (long long)N);
+    if (cam->width <= 0 || cam->height <= 0) return fail(ctx, DVS_E_INVALID, "bad image size");
+    if (cam->sh_degree < 0 || cam->sh_degree > 3) return fail(ctx, DVS_E_INVALID, "sh_degree must be 0..3");
+    const int K = (cam->sh_degree + 1) * (cam->sh_degree + 1);
+    if (cam->sh_rest_alloc < K - 1) return fail(ctx, DVS_E_INVALID, "sh_rest_alloc < (deg+1)^2-1");
+    int rc;
+    if (N > 0 && (rc = check_params(ctx, params, cam->sh_rest_alloc))) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(ctx->device));
+
+    Cam c{};
+    memcpy(c.view, cam->view, sizeof c.view);
+    memcpy(c.proj, cam->proj, sizeof c.proj);
+    memcpy(c.campos, cam->campos, sizeof c.campos);
+    c.tanfovx = cam->tanfovx; c.tanfovy = cam->tanfovy;
+    c.W = cam->width; c.H = cam->height;
+    memcpy(c.bg, cam->bg, sizeof c.bg);
+    c.scale_modifier = cam->scale_modifier;
+    c.deg = cam->sh_degree; c.KR = cam->sh_rest_alloc;
+    c.flags = cam->flags;
+    c.gx = (c.W + TILE - 1) / TILE; c.gy = (c.H + TILE - 1) / TILE;
+    const int64_t T = (int64_t)c.gx * c.gy, P = (int64_t)c.W * c.H;
+    if (T >= (1 << 24) || c.gx > 65535 || c.gy > 65535) return fail(ctx, DVS_E_UNSUPPORTED, "image too large");
+
+    if ((rc = ensure_gauss(ctx, N > 0 ? N : 1))) return rc;
+    if ((rc = ensure_tiles(ctx, T))) return rc;
+    if ((rc = ensure_pix(ctx, P))) return rc;
+    if (ctx->cap_dups == 0 && (rc = ensure_dups(ctx, (N > 0 ? 16 * N : 1) + 4096))) return rc;
+
+    Params prm{};
+    if (N > 0) prm = Params{params->means3D, params->scales, params->quats, params->opacities, params->sh0, params->shN};
+    ctx->have_fwd = false;
+    ctx->st.overflow = 0;
+    for (int attempt = 0; attempt < 3; attempt++) {
+        CK(cudaMemsetAsync(ctx->tile_count, 0, (size_t)T * sizeof(uint32_t), st));
+        CK(cudaMemsetAsync(ctx->stats, 0, 2 * sizeof(unsigned long long), st));
+        CK(cudaEventRecord(ctx->ev[0], st));
+        CK(launch_preprocess_fwd(c, (int)N, prm, ctx->rec, ctx->aux, ctx->tile_count, out_radii, ctx->stats, st));
+        CK(cudaEventRecord(ctx->ev[1], st));
+        CK(launch_tile_scan((int)T, ctx->tile_count, ctx->tile_base, ctx->tile_cursor, ctx->info,
+                            (uint32_t)ctx->cap_dups, st));
+        CK(cudaEventRecord(ctx->ev[2], st));
+        CK(launch_emit(c, (int)N, ctx->rec, ctx->aux, ctx->tile_cursor, ctx->bins, (uint32_t)ctx->cap_dups, st));
+        CK(cudaEventRecord(ctx->ev[3], st));
+        CK(launch_tile_sort((int)T, ctx->tile_base, ctx->bins, ctx->plist, ctx->info, st));
+        CK(cudaEventRecord(ctx->ev[4], st));
+        CK(launch_render_fwd(c, ctx->tile_base, ctx->plist, ctx->rec, out_color, ctx->final_T, ctx->n_contrib,
+                             ctx->info, st));
+        CK(cudaEventRecord(ctx->ev[5], st));
+        CK(cudaMemcpyAsync(ctx->h_info, ctx->info, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ctx->h_stats, ctx->stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (!ctx->h_info[2]) break;
+        // arena too small: grow to the exact need (+25%) and run the forward again
+        ctx->st.overflow = 1;
+        const int64_t need = (int64_t)ctx->h_stats[1];
+        if ((rc = ensure_dups(ctx, need + need / 4 + 4096))) return rc;
+        if (attempt == 2) return fail(ctx, DVS_E_NOMEM, "binning arena overflow persisted");
+    }
+    ctx->cam = c;
+    ctx->N = N;
+    ctx->st.num_gaussians = N;
+    ctx->st.num_visible = (int64_t)ctx->h_stats[0];
+    ctx->st.num_dups = (int64_t)ctx->h_info[0];
+    ctx->st.dup_capacity = ctx->cap_dups;
+    ctx->st.max_tile_len = ctx->h_info[1];
+    ctx->st.tiles_x = c.gx; ctx->st.tiles_y = c.gy;
+    ctx->have_fwd = true;
+    ctx->ev_fwd = true;
+    return DVS_OK;
+}
+
+int dvs_rast_backward(dvs_rast_ctx* ctx, const dvs_params* params, const float* dL_dpix, const dvs_grads* grads,
+                      uint32_t flags, void* stream) {
+    if (!ctx) return DVS_E_INVALID;
+    if (!ctx->have_fwd) return fail(ctx, DVS_E_STATE, "backward without a forward on this context");
+    if (!dL_dpix || !grads) return fail(ctx, DVS_E_INVALID, "null dL_dpix / grads");
+    const Cam& c = ctx->cam;
+    const int64_t N = ctx->N;
+    int rc;
+    if (N > 0) {
+        if ((rc = check_params(ctx, params, c.KR))) return rc;
+        if (!grads->means3D || !grads->scales || !grads->quats || !grads->opacities || !grads->sh0 ||
+            (c.KR > 0 && !grads->shN))
+            return fail(ctx, DVS_E_INVALID, "null gradient pointer");
+        if (!aligned16(grads->quats) || (c.KR > 0 && !aligned16(grads->shN)))
+            return fail(ctx, DVS_E_INVALID, "gradient pointers must be 16-byte aligned");
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(ctx->device));
+    Params prm{};
+    Grads g{};
+    if (N > 0) {
+        prm = Params{params->means3D, params->scales, params->quats, params->opacities, params->sh0, params->shN};
+        g = Grads{grads->means3D, grads->scales, grads->quats, grads->opacities, grads->sh0, grads->shN,
+                  (flags & DVS_FLAG_ABSGRAD) ? grads->mean2D_abs : nullptr, grads->mean2D};
+    }
+    CK(cudaEventRecord(ctx->ev[6], st));
+    CK(launch_render_bwd(c, ctx->tile_base, ctx->plist, ctx->rec, ctx->final_T, ctx->n_contrib, dL_dpix,
+                         reinterpret_cast<float*>(ctx->sgrad), (flags & DVS_FLAG_ABSGRAD) && g.mean2D_abs,
+                         ctx->info, st));
+    CK(cudaEventRecord(ctx->ev[7], st));
+    CK(launch_preprocess_bwd(c, (int)N, prm, ctx->rec, ctx->sgrad, g, flags, st));
+    CK(cudaEventRecord(ctx->ev[8], st));
+    ctx->ev_bwd = true;
+    return DVS_OK;
+}
+
+int dvs_rast_step_host(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, const dvs_params* params,
+                       const dvs_grads* grads, const float* dL_dpix_host, float* out_color_host, uint32_t bwd_flags,
+                       void* stream) {
+    if (!ctx) return DVS_E_INVALID;
+    if (!cam || !dL_dpix_host || !out_color_host) return fail(ctx, DVS_E_INVALID, "null host buffer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(ctx->device));
+    const int64_t P = (int64_t)cam->width * cam->height;
+    int rc;
+    if ((rc = ensure_pix(ctx, P))) return rc;
+    if (!ctx->h2d_grad) CK(cudaMalloc(reinterpret_cast<void**>(&ctx->h2d_grad), 3 * (size_t)ctx->cap_pix * sizeof(float)));
+    if (!ctx->d_image) CK(cudaMalloc(reinterpret_cast<void**>(&ctx->d_image), 3 * (size_t)ctx->cap_pix * sizeof(float)));
+    CK(cudaMemcpyAsync(ctx->h2d_grad, dL_dpix_host, 3 * (size_t)P * sizeof(float), cudaMemcpyHostToDevice, st));
+    if ((rc = dvs_rast_forward(ctx, cam, N, params, ctx->d_image, nullptr, stream))) return rc;
+    CK(cudaMemcpyAsync(out_color_host, ctx->d_image, 3 * (size_t)P * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if ((rc = dvs_rast_backward(ctx, params, ctx->h2d_grad, grads, bwd_flags, stream))) return rc;
+    CK(cudaStreamSynchronize(st));
+    return DVS_OK;
+}
+
+int dvs_rast_get_stats(const dvs_rast_ctx* ctx, dvs_stats* out) {
+    if (!ctx || !out) return DVS_E_INVALID;
+    *out = ctx->st;
+    return DVS_OK;
+}
+
+int dvs_rast_debug_read(dvs_rast_ctx* ctx, int which, void* dst, size_t dst_bytes) {
+    if (!ctx || !dst) return DVS_E_INVALID;
+    if (!ctx->have_fwd) return fail(ctx, DVS_E_STATE, "no forward to read from");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    const size_t N = (size_t)ctx->N, D = (size_t)ctx->st.num_dups;
+    const size_t T = (size_t)ctx->cam.gx * ctx->cam.gy, P = (size_t)ctx->cam.W * ctx->cam.H;
+    auto need = [&](size_t b) -> int {
+        return dst_bytes >= b ? DVS_OK : fail(ctx, DVS_E_INVALID, "debug_read: need %zu bytes, got %zu", b, dst_bytes);
+    };
+    int rc;
+    if (which <= DVS_BUF_CLAMPED) {
+        // unpack the records into upstream-style arrays on the device, copy the requested one
+        int32_t* radii; uint32_t* tiles; float *depth, *m2, *co, *rgb; uint8_t* cl;
+        const size_t n1 = N ? N : 1;
+        CK(cudaMalloc((void**)&radii, n1 * 4)); CK(cudaMalloc((void**)&tiles, n1 * 4));
+        CK(cudaMalloc((void**)&depth, n1 * 4)); CK(cudaMalloc((void**)&m2, n1 * 8));
+        CK(cudaMalloc((void**)&co, n1 * 16)); CK(cudaMalloc((void**)&rgb, n1 * 12)); CK(cudaMalloc((void**)&cl, n1 * 3));
+        cudaError_t e = launch_unpack((int)N, ctx->rec, radii, tiles, depth, m2, co, rgb, cl, 0);
+        const void* src = nullptr; size_t bytes = 0;
+        switch (which) {
+            case DVS_BUF_RADII: src = radii; bytes = N * 4; break;
+            case DVS_BUF_TILES_TOUCHED: src = tiles; bytes = N * 4; break;
+            case DVS_BUF_DEPTH: src = depth; bytes = N * 4; break;
+            case DVS_BUF_MEAN2D: src = m2; bytes = N * 8; break;
+            case DVS_BUF_CONIC_OPACITY: src = co; bytes = N * 16; break;
+            case DVS_BUF_RGB: src = rgb; bytes = N * 12; break;
+            default: src = cl; bytes = N * 3; break;
+        }
+        rc = need(bytes);
+        if (e == cudaSuccess && rc == DVS_OK && bytes) e = cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost);
+        cudaFree(radii); cudaFree(tiles); cudaFree(depth); cudaFree(m2); cudaFree(co); cudaFree(rgb); cudaFree(cl);
+        if (rc) return rc;
+        CK(e);
+        return DVS_OK;
+    }
+    switch (which) {
+        case DVS_BUF_POINT_LIST:
+        case DVS_BUF_CULL_MASK: {
+            const bool ids = which == DVS_BUF_POINT_LIST;
+            if ((rc = need(D * (ids ? 4 : 1)))) return rc;
+            if (!D) return DVS_OK;
+            void* tmp;
+            CK(cudaMalloc(&tmp, D * (ids ? 4 : 1)));
+            cudaError_t e = launch_unpack_plist((uint32_t)D, ctx->plist, ids ? (uint32_t*)tmp : nullptr,
+                                                ids ? nullptr : (uint8_t*)tmp, 0);
+            if (e == cudaSuccess) e = cudaMemcpy(dst, tmp, D * (ids ? 4 : 1), cudaMemcpyDeviceToHost);
+            cudaFree(tmp);
+            CK(e);
+            return DVS_OK;
+        }
+        case DVS_BUF_RANGES: {
+            if ((rc = need(T * 8))) return rc;
+            uint32_t* h = new uint32_t[T + 1];
+            cudaError_t e = cudaMemcpy(h, ctx->tile_base, (T + 1) * 4, cudaMemcpyDeviceToHost);
+            uint32_t* o = static_cast<uint32_t*>(dst);
+            for (size_t t = 0; t < T; t++) {
+                // upstream leaves untouched tiles at (0,0)
+                const bool empty = h[t + 1] == h[t];
+                o[2 * t] = empty ? 0u : h[t];
+                o[2 * t + 1] = empty ? 0u : h[t + 1];
+            }
+            delete[] h;
+            CK(e);
+            return DVS_OK;
+        }
+        case DVS_BUF_FINAL_T:
+            if ((rc = need(P * 4))) return rc;
+            CK(cudaMemcpy(dst, ctx->final_T, P * 4, cudaMemcpyDeviceToHost));
+            return DVS_OK;
+        case DVS_BUF_N_CONTRIB:
+            if ((rc = need(P * 4))) return rc;
+            CK(cudaMemcpy(dst, ctx->n_contrib, P * 4, cudaMemcpyDeviceToHost));
+            return DVS_OK;
+        case DVS_BUF_SCREEN_GRADS:
+            if ((rc = need(N * 48))) return rc;
+            CK(cudaMemcpy(dst, ctx->sgrad, N * 48, cudaMemcpyDeviceToHost));
+            return DVS_OK;
+        default:
+            return fail(ctx, DVS_E_INVALID, "unknown buffer id %d", which);
+    }
+}
+
+static const char* kStageNames[DVS_NUM_STAGES] = {"preprocess_fwd", "tile_scan", "emit", "tile_sort",
+                                                  "render_fwd",     "render_bwd", "preprocess_bwd", "reserved"};
+const char* dvs_rast_stage_name(int i) { return (i >= 0 && i < DVS_NUM_STAGES) ? kStageNames[i] : ""; }
+
+int dvs_rast_stage_ms(dvs_rast_ctx* ctx, float out_ms[DVS_NUM_STAGES]) {
+    if (!ctx || !out_ms) return DVS_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    for (int i = 0; i < DVS_NUM_STAGES; i++) out_ms[i] = 0.f;
+    if (ctx->ev_fwd)
+        for (int i = 0; i < 5; i++) CK(cudaEventElapsedTime(&out_ms[i], ctx->ev[i], ctx->ev[i + 1]));
+    if (ctx->ev_bwd) {
+        CK(cudaEventElapsedTime(&out_ms[5], ctx->ev[6], ctx->ev[7]));
+        CK(cudaEventElapsedTime(&out_ms[6], ctx->ev[7], ctx->ev[8]));
+    }
+    return DVS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,120 @@
+// common.cuh — shared device-side definitions of the B200-native rasterizer (sm_100a only).
+//
+// HBM layout (all arenas owned by dvs_rast_ctx, SoA inputs owned by the caller):
+//   rec   [N] x 48 B  screen record, three float4:
+//           q0 = { mean2D.x, mean2D.y, A2, B2 }          A2 = -0.5*log2(e)*conicA, B2 = -log2(e)*conicB
+//           q1 = { C2, lo, r, g }                        C2 = -0.5*log2(e)*conicC, lo = log2(opacity)
+//           q2 = { b, depth, radius (int bits), tiles_touched | clamped<<24 (uint bits) }
+//         so that alpha = ex2(A2*dx^2 + B2*dx*dy + C2*dy^2 + lo)  (one MUFU, no multiply by opacity)
+//   aux   [N] x 16 B  { minx|miny<<16, maxx|maxy<<16, ex, ey }   tile rect + opacity-aware half extents
+//   bins  [Dcap] x 8 B  unsorted per-tile entries  depth_bits<<32 | id<<8 | submask
+//   plist [Dcap] x 4 B  sorted entries id<<8 | submask (tile-major; the parity point_list is id)
+//   tile_count / tile_base / tile_cursor [T]
+//   final_T, n_contrib [P];  sgrad [N] x 48 B screen-space gradient record (see dvs_rast.h)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dvs_rast.h"
+
+namespace dvs {
+
+constexpr int TILE = 16;
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+constexpr float ALPHA_MIN_LOG2 = -7.994353436858858f;  // log2(1/255)
+constexpr int ID_BITS = 24;
+constexpr uint32_t MAX_GAUSSIANS = 1u << ID_BITS;
+
+struct Cam {
+    float view[16];
+    float proj[16];
+    float campos[3];
+    float tanfovx, tanfovy;
+    int W, H;
+    float bg[3];
+    float scale_modifier;
+    int deg, KR;
+    uint32_t flags;
+    int gx, gy;
+};
+
+struct Params {
+    const float* means3D;
+    const float* scales;
+    const float* quats;
+    const float* opacities;
+    const float* sh0;
+    const float* shN;
+};
+
+struct Grads {
+    float* means3D;
+    float* scales;
+    float* quats;
+    float* opacities;
+    float* sh0;
+    float* shN;
+    float* mean2D_abs;
+    float* mean2D;
+};
+
+// ---- small PTX wrappers -------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ldg_f4(const float4* p) { return __ldg(p); }
+__device__ __forceinline__ void stg_cs_f4(float4* p, float4 v) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP) ------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "W_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra D_%=;\n"
+        "bra W_%=;\n"
+        "D_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+}  // namespace dvs

@@ -1,0 +1,46 @@
+// kernels.h — host-side launcher declarations (one per stage of SURVEY.md §8 A1-A8).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace dvs {
+
+// A1 (+ per-tile duplicate counts)
+cudaError_t launch_preprocess_fwd(const Cam& cam, int N, const Params& prm, float4* rec, uint4* aux,
+                                  uint32_t* tile_count, int32_t* out_radii, unsigned long long* stats,
+                                  cudaStream_t st);
+
+// A2/A5: exclusive scan of tile counts -> tile_base[T+1], cursor[T]; info[0]=D, info[1]=max len, info[2]=overflow
+cudaError_t launch_tile_scan(int T, const uint32_t* tile_count, uint32_t* tile_base, uint32_t* tile_cursor,
+                             uint32_t* info, uint32_t dup_capacity, cudaStream_t st);
+
+// A3: emit (depth | id | sub-tile mask) entries into per-tile bins
+cudaError_t launch_emit(const Cam& cam, int N, const float4* rec, const uint4* aux, uint32_t* tile_cursor,
+                        unsigned long long* bins, uint32_t dup_capacity, cudaStream_t st);
+
+// A4: tile-local sort (CUB-free) -> plist (id<<8 | mask), tile-major
+cudaError_t launch_tile_sort(int T, const uint32_t* tile_base, unsigned long long* bins, uint32_t* plist,
+                             const uint32_t* info, cudaStream_t st);
+
+// A6
+cudaError_t launch_render_fwd(const Cam& cam, const uint32_t* tile_base, const uint32_t* plist, const float4* rec,
+                              float* out_color, float* final_T, uint32_t* n_contrib, const uint32_t* info,
+                              cudaStream_t st);
+
+// A7
+cudaError_t launch_render_bwd(const Cam& cam, const uint32_t* tile_base, const uint32_t* plist, const float4* rec,
+                              const float* final_T, const uint32_t* n_contrib, const float* dL_dpix, float* sgrad,
+                              bool absgrad, const uint32_t* info, cudaStream_t st);
+
+// A8
+cudaError_t launch_preprocess_bwd(const Cam& cam, int N, const Params& prm, const float4* rec, float4* sgrad,
+                                  const Grads& g, uint32_t flags, cudaStream_t st);
+
+// debug helpers (parity tests): unpack records into the upstream-style arrays
+cudaError_t launch_unpack(int N, const float4* rec, int32_t* radii, uint32_t* tiles, float* depth, float* mean2D,
+                          float* conic_opacity, float* rgb, uint8_t* clamped, cudaStream_t st);
+cudaError_t launch_unpack_plist(uint32_t D, const uint32_t* plist, uint32_t* ids, uint8_t* masks, cudaStream_t st);
+
+}  // namespace dvs

@@ -90,7 +90,9 @@ def look_at_camera(eye, target, width, height, fovx_deg=60.0, znear=0.01, zfar=1
 
 
 def make_scene(name: str = None, *, N=None, width=None, height=None, sh_degree=None, views=None,
-               seed=None, normalise_quats=True, bg=(0, 0, 0), with_grad=True) -> Scene:
+               seed=None, normalise_quats=True, bg=(0, 0, 0), with_grad=True, tanfovx=None, mu_s=None) -> Scene:
+    """tanfovx / mu_s override the 60-degree FOV and the N-dependent mean log-scale (used for
+    density-preserving crops of a config: same focal length and splat size, fewer splats and pixels)."""
     if name is not None and name in CONFIGS:
         idx, N0, W0, H0, d0, v0 = CONFIGS[name]
         N = N0 if N is None else N; width = W0 if width is None else width
@@ -102,13 +104,14 @@ def make_scene(name: str = None, *, N=None, width=None, height=None, sh_degree=N
         seed = 1234 if seed is None else seed
         name = name or f"custom_{N}_{width}x{height}_d{sh_degree}"
     g = torch.Generator(device="cpu"); g.manual_seed(int(seed))
-    tanfovx = math.tan(math.radians(60.0) * 0.5)
+    tanfovx = math.tan(math.radians(60.0) * 0.5) if tanfovx is None else float(tanfovx)
+    fovx_deg = math.degrees(2.0 * math.atan(tanfovx))
     tanfovy = tanfovx * height / width
     z = torch.empty(N).uniform_(2.0, 10.0, generator=g)
     ux = torch.empty(N).uniform_(-1.15, 1.15, generator=g)
     uy = torch.empty(N).uniform_(-1.15, 1.15, generator=g)
     means = torch.stack([ux * tanfovx * z, uy * tanfovy * z, z], 1)
-    mu_s = math.log(0.012 * (1.0e6 / N) ** (1.0 / 3.0))
+    mu_s = math.log(0.012 * (1.0e6 / N) ** (1.0 / 3.0)) if mu_s is None else float(mu_s)
     log_scales = torch.randn(N, 3, generator=g) * 0.5 + mu_s
     quats = torch.randn(N, 4, generator=g)
     if normalise_quats:
@@ -124,9 +127,19 @@ def make_scene(name: str = None, *, N=None, width=None, height=None, sh_degree=N
         else:
             ang = 2.0 * math.pi * v / views
             eye, tgt = (0.5 * math.cos(ang), 0.5 * math.sin(ang), 0.0), (0.0, 0.0, 6.0)
-        cams.append(look_at_camera(eye, tgt, width, height, bg=bg))
+        cams.append(look_at_camera(eye, tgt, width, height, fovx_deg=fovx_deg, bg=bg))
         if with_grad:
             gv = torch.Generator(device="cpu"); gv.manual_seed(int(seed) * 1000 + v)
             grads.append(torch.randn(3, height, width, generator=gv).numpy())
     f = lambda t: np.ascontiguousarray(t.numpy().astype(np.float32))
     return Scene(name, f(means), f(log_scales), f(quats), f(logit), f(sh0), f(shN), int(sh_degree), cams, grads)
+
+
+def crop_of(name: str, frac_lin: int, seed=None) -> Scene:
+    """Density-preserving crop of a config: image and FOV shrunk by `frac_lin` per axis, N by frac_lin^2,
+    same focal length and the config's own splat-size distribution.  Used as the bounded CPU sample."""
+    idx, N0, W0, H0, d0, _ = CONFIGS[name]
+    tan0 = math.tan(math.radians(60.0) * 0.5)
+    return make_scene(None, N=N0 // (frac_lin * frac_lin), width=W0 // frac_lin, height=H0 // frac_lin,
+                      sh_degree=d0, seed=(1234 + idx if seed is None else seed), tanfovx=tan0 / frac_lin,
+                      mu_s=math.log(0.012 * (1.0e6 / N0) ** (1.0 / 3.0)))

@@ -1,0 +1,161 @@
+/*
+ * dvs_rast.h — C-ABI of the B200-native differentiable 3D-Gaussian-splatting rasterizer.
+ *
+ * This is the drop-in boundary for DIVSHOT's closed `diverse_utils/gsplatrast` operator
+ * (named at /root/reference/diverse_utils/CMakeLists.txt:1, CMakeLists.txt:103,
+ * premake-dependencies.lua:40; source absent from the reference tree — README.md:32,46).
+ * The trainer plugin (`libgstrain.so`, include/gaussian_trainer_scene.hpp, symbols resolved at
+ * application/diverseshot-cli/source/gs_train.cpp:24-179) and the libtorch
+ * `torch::CustomClassHolder` operator both sit on top of exactly these entry points.
+ *
+ * Plain C: pointers and sizes only, no torch / CUDA types (streams travel as void*).
+ * All data pointers are DEVICE pointers unless the name ends in `_host`; they must be
+ * 16-byte aligned and contiguous fp32.  One context per (device, stream-at-a-time); a context
+ * is not thread-safe.  Every entry point returns 0 on success or a negative DVS_E_* code and
+ * records a message retrievable with dvs_rast_last_error().
+ *
+ * Parameter conventions (the tensors the trainer exports, proven by the only in-tree consumer
+ * diverse/source/assets/gaussian_model.cpp:43-68,145-157,579-583):
+ *   means3D [N,3]; log_scales [N,3] (exp activation); quats [N,4] (r,x,y,z, normalised inside);
+ *   logit_opacities [N] (sigmoid activation); sh0 [N,3]; shN [N,sh_rest_alloc,3] RGB-interleaved.
+ * With DVS_FLAG_INPUT_ACTIVATED the scale / quaternion / opacity inputs are taken as already
+ * activated (the credited upstream operator's convention) and gradients are w.r.t. those.
+ */
+#ifndef DVS_RAST_H
+#define DVS_RAST_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DVS_API __attribute__((visibility("default")))
+
+#define DVS_OK 0
+#define DVS_E_INVALID (-1)     /* bad argument (null / misaligned pointer, bad size, bad degree) */
+#define DVS_E_CUDA (-2)        /* a CUDA runtime call failed; see dvs_rast_last_error */
+#define DVS_E_NOMEM (-3)       /* arena allocation failed */
+#define DVS_E_STATE (-4)       /* backward without a matching forward, etc. */
+#define DVS_E_UNSUPPORTED (-5) /* N >= 2^24, image wider/taller than 4080 px, ... */
+
+#define DVS_FLAG_INPUT_ACTIVATED 1u /* scales/quats/opacities already activated */
+#define DVS_FLAG_ACCUMULATE 2u      /* backward: add into the gradient buffers instead of overwriting */
+#define DVS_FLAG_ABSGRAD 4u         /* backward: also write sum|dL/dmean2D| (densify statistic, main.cpp:44-45) */
+
+typedef struct dvs_rast_ctx dvs_rast_ctx;
+
+typedef struct dvs_camera {
+    float view[16];  /* world->view, flat: element [4*c + r] = row r, column c */
+    float proj[16];  /* full view-projection, same layout */
+    float campos[3];
+    float tanfovx, tanfovy;
+    int32_t width, height;
+    float bg[3];
+    float scale_modifier;
+    int32_t sh_degree;     /* active degree 0..3 */
+    int32_t sh_rest_alloc; /* rest coefficients per Gaussian allocated in shN (>= (deg+1)^2 - 1) */
+    uint32_t flags;        /* DVS_FLAG_* */
+} dvs_camera;
+
+typedef struct dvs_params { /* device pointers, caller-owned, read-only */
+    const float* means3D;
+    const float* scales;
+    const float* quats;
+    const float* opacities;
+    const float* sh0;
+    const float* shN; /* may be NULL when sh_rest_alloc == 0 */
+} dvs_params;
+
+typedef struct dvs_grads { /* device pointers, caller-owned, same shapes as dvs_params */
+    float* means3D;
+    float* scales;
+    float* quats;
+    float* opacities;
+    float* sh0;
+    float* shN;
+    float* mean2D_abs; /* [N,2] optional (DVS_FLAG_ABSGRAD), may be NULL */
+    float* mean2D;     /* [N,2] optional: screen-space dL/dmean2D (ndc-scaled), may be NULL */
+} dvs_grads;
+
+typedef struct dvs_stats {
+    int64_t num_gaussians; /* N of the last forward */
+    int64_t num_visible;   /* V: radius > 0 */
+    int64_t num_dups;      /* D: sum of tiles_touched */
+    int64_t dup_capacity;  /* entries the binning arena can hold */
+    int64_t max_tile_len;  /* longest tile list */
+    int32_t tiles_x, tiles_y;
+    int32_t overflow;      /* 1 if the last forward needed a bigger arena (it was re-run) */
+} dvs_stats;
+
+/* ids of internal buffers readable through dvs_rast_debug_read (parity tests only) */
+enum {
+    DVS_BUF_RADII = 0,         /* int32 [N] */
+    DVS_BUF_TILES_TOUCHED = 1, /* uint32 [N] */
+    DVS_BUF_DEPTH = 2,         /* float [N] */
+    DVS_BUF_MEAN2D = 3,        /* float [N,2] */
+    DVS_BUF_CONIC_OPACITY = 4, /* float [N,4]: A,B,C,opacity (un-scaled back from the record) */
+    DVS_BUF_RGB = 5,           /* float [N,3] */
+    DVS_BUF_CLAMPED = 6,       /* uint8 [N,3] */
+    DVS_BUF_POINT_LIST = 7,    /* uint32 [D] sorted Gaussian ids, tile-major */
+    DVS_BUF_RANGES = 8,        /* uint32 [T,2] */
+    DVS_BUF_FINAL_T = 9,       /* float [H*W] */
+    DVS_BUF_N_CONTRIB = 10,    /* uint32 [H*W] */
+    DVS_BUF_CULL_MASK = 11,    /* uint8 [D] per-entry 8-bit sub-tile mask (ours; no upstream analogue) */
+    DVS_BUF_SCREEN_GRADS = 12  /* float [N,12]: dmean2D(2), dconic A,B,C(3), dopacity(1), dcolor(3), |dmean2D|(2), pad */
+};
+
+/* Create a context on CUDA device `device`.  Scratch arenas grow on demand and persist. */
+DVS_API int dvs_rast_create(int device, dvs_rast_ctx** out);
+DVS_API void dvs_rast_destroy(dvs_rast_ctx* ctx);
+DVS_API const char* dvs_rast_last_error(const dvs_rast_ctx* ctx);
+DVS_API const char* dvs_rast_version(void);
+
+/* Pre-size the arenas (optional; avoids the grow-and-rerun path and any allocation in the step). */
+DVS_API int dvs_rast_reserve(dvs_rast_ctx* ctx, int64_t max_gaussians, int32_t max_width, int32_t max_height,
+                             int64_t dup_capacity);
+
+/*
+ * Forward: preprocess (A1) -> tile binning (A2,A3) -> tile-local sort (A4,A5) -> compositing (A6).
+ *   out_color : float [3,H,W] planar
+ *   out_radii : int32 [N] or NULL
+ * Replaces the forward half of the absent gsplatrast operator.
+ * Synchronises `stream` once at the end to validate the binning arena size (the credited
+ * upstream synchronises mid-pipeline to read D back); on overflow the arena is grown and the
+ * forward re-run transparently.
+ */
+DVS_API int dvs_rast_forward(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, const dvs_params* params,
+                             float* out_color, int32_t* out_radii, void* stream);
+
+/*
+ * Backward of the last forward on this context: reverse-walk compositing gradients (A7) ->
+ * per-Gaussian backward (A8) to the stored parameters.
+ *   dL_dpix : float [3,H,W]
+ * `flags`: DVS_FLAG_ACCUMULATE, DVS_FLAG_ABSGRAD.
+ */
+DVS_API int dvs_rast_backward(dvs_rast_ctx* ctx, const dvs_params* params, const float* dL_dpix,
+                              const dvs_grads* grads, uint32_t flags, void* stream);
+
+/*
+ * Host-buffer step (the end-to-end path a trainer without device-resident images uses):
+ * copies dL_dpix_host (pinned or pageable) to the device, runs forward + backward with the
+ * device-resident parameters/gradients, copies the rendered image back to out_color_host.
+ */
+DVS_API int dvs_rast_step_host(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, const dvs_params* params,
+                               const dvs_grads* grads, const float* dL_dpix_host, float* out_color_host,
+                               uint32_t bwd_flags, void* stream);
+
+DVS_API int dvs_rast_get_stats(const dvs_rast_ctx* ctx, dvs_stats* out);
+
+/* Copy an internal buffer of the last forward/backward to HOST memory (parity tests). */
+DVS_API int dvs_rast_debug_read(dvs_rast_ctx* ctx, int which, void* dst_host, size_t dst_bytes);
+
+/* Per-stage device time of the last forward/backward in milliseconds (CUDA events; syncs). */
+#define DVS_NUM_STAGES 8
+DVS_API int dvs_rast_stage_ms(dvs_rast_ctx* ctx, float out_ms[DVS_NUM_STAGES]);
+DVS_API const char* dvs_rast_stage_name(int i);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -362,7 +362,10 @@ void orc_render_fwd(const orc_camera* cam, const uint32_t* ranges, const uint32_
     }
 }
 
-static inline void atomic_addf(float* p, float v) {
+/* Per-Gaussian sums are accumulated in double and rounded once: the credited upstream sums with fp32
+ * atomics in a non-deterministic order, so every fp32 summation order is "the reference"; the double sum
+ * is the centre of that family and keeps the oracle's own rounding noise out of the 1e-4 parity budget. */
+static inline void atomic_addd(double* p, double v) {
 #pragma omp atomic
     *p += v;
 }
@@ -376,11 +379,12 @@ void orc_render_bwd(const orc_camera* cam, int32_t N, const uint32_t* ranges, co
     const int W = cam->width, H = cam->height;
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
     const size_t P = (size_t)W * H;
-    memset(dL_dmean2D, 0, sizeof(float) * 2 * (size_t)N);
-    if (dL_dmean2D_abs) memset(dL_dmean2D_abs, 0, sizeof(float) * 2 * (size_t)N);
-    memset(dL_dconic, 0, sizeof(float) * 3 * (size_t)N);
-    memset(dL_dopacity, 0, sizeof(float) * (size_t)N);
-    memset(dL_dcolor, 0, sizeof(float) * 3 * (size_t)N);
+    double* acc = (double*)calloc((size_t)(N > 0 ? N : 1) * 11, sizeof(double));
+    double* a_m2 = acc;                      /* [N,2] */
+    double* a_abs = acc + 2 * (size_t)N;     /* [N,2] */
+    double* a_con = acc + 4 * (size_t)N;     /* [N,3] */
+    double* a_op = acc + 7 * (size_t)N;      /* [N]   */
+    double* a_col = acc + 8 * (size_t)N;     /* [N,3] */
     const float ddelx_dx = 0.5f * (float)W, ddely_dy = 0.5f * (float)H;
 #ifdef _OPENMP
     if (threads > 0) omp_set_num_threads(threads);
@@ -421,7 +425,7 @@ void orc_render_bwd(const orc_camera* cam, int32_t N, const uint32_t* ranges, co
                         accum_rec[ch] = last_alpha * last_color[ch] + (1.0f - last_alpha) * accum_rec[ch];
                         last_color[ch] = c;
                         dL_dalpha += (c - accum_rec[ch]) * dp[ch];
-                        atomic_addf(&dL_dcolor[3 * g + ch], dchannel_dcolor * dp[ch]);
+                        atomic_addd(&a_col[3 * g + ch], dchannel_dcolor * dp[ch]);
                     }
                     dL_dalpha *= T;
                     last_alpha = alpha;
@@ -433,22 +437,31 @@ void orc_render_bwd(const orc_camera* cam, int32_t N, const uint32_t* ranges, co
                     const float dG_ddelx = -gdx * cA - gdy * cB;
                     const float dG_ddely = -gdy * cC - gdx * cB;
                     const float gmx = dL_dG * dG_ddelx * ddelx_dx, gmy = dL_dG * dG_ddely * ddely_dy;
-                    atomic_addf(&dL_dmean2D[2 * g], gmx);
-                    atomic_addf(&dL_dmean2D[2 * g + 1], gmy);
-                    if (dL_dmean2D_abs) {
-                        atomic_addf(&dL_dmean2D_abs[2 * g], fabsf(gmx));
-                        atomic_addf(&dL_dmean2D_abs[2 * g + 1], fabsf(gmy));
-                    }
-                    atomic_addf(&dL_dconic[3 * g], -0.5f * gdx * dx * dL_dG);
-                    atomic_addf(&dL_dconic[3 * g + 1], -gdx * dy * dL_dG); /* TOTAL off-diagonal gradient */
-                    atomic_addf(&dL_dconic[3 * g + 2], -0.5f * gdy * dy * dL_dG);
-                    atomic_addf(&dL_dopacity[g], G * dL_dalpha);
+                    atomic_addd(&a_m2[2 * g], gmx);
+                    atomic_addd(&a_m2[2 * g + 1], gmy);
+                    atomic_addd(&a_abs[2 * g], fabsf(gmx));
+                    atomic_addd(&a_abs[2 * g + 1], fabsf(gmy));
+                    atomic_addd(&a_con[3 * g], -0.5f * gdx * dx * dL_dG);
+                    atomic_addd(&a_con[3 * g + 1], -gdx * dy * dL_dG); /* TOTAL off-diagonal gradient */
+                    atomic_addd(&a_con[3 * g + 2], -0.5f * gdy * dy * dL_dG);
+                    atomic_addd(&a_op[g], G * dL_dalpha);
                 }
             }
     }
+    for (size_t i = 0; i < (size_t)N; i++) {
+        dL_dmean2D[2 * i] = (float)a_m2[2 * i]; dL_dmean2D[2 * i + 1] = (float)a_m2[2 * i + 1];
+        if (dL_dmean2D_abs) { dL_dmean2D_abs[2 * i] = (float)a_abs[2 * i]; dL_dmean2D_abs[2 * i + 1] = (float)a_abs[2 * i + 1]; }
+        for (int k = 0; k < 3; k++) { dL_dconic[3 * i + k] = (float)a_con[3 * i + k]; dL_dcolor[3 * i + k] = (float)a_col[3 * i + k]; }
+        dL_dopacity[i] = (float)a_op[i];
+    }
+    free(acc);
 }
 
-/* A8: B.5.  Forward counterparts: gsplat_intersect.hlsl:61-134, gsplat_sh.hlsl:64-103. */
+/* A8: B.5.  Forward counterparts: gsplat_intersect.hlsl:61-134, gsplat_sh.hlsl:64-103.
+ * Evaluated in double from the fp32 inputs and rounded once at the end: the chain conic -> cov2D -> T -> J / Sigma
+ * -> (scale, rotation) cancels heavily, so two fp32 evaluation orders (with / without FMA contraction) of the
+ * credited formulas differ by ~1e-4 relative on some elements; the double evaluation is the centre of that family
+ * and keeps the oracle's own rounding out of the parity budget.  Nothing here is part of the bit-exact contract. */
 void orc_preprocess_bwd(const orc_camera* cam, int32_t N, const float* means3D, const float* scales,
                         const float* quats, const float* opacities, const float* sh0, const float* shN,
                         const int32_t* radii, const uint8_t* clamped, const float* dL_dmean2D,
@@ -456,7 +469,8 @@ void orc_preprocess_bwd(const orc_camera* cam, int32_t N, const float* means3D, 
                         float* dL_dmeans3D, float* dL_dscales, float* dL_dquats, float* dL_dopacities,
                         float* dL_dsh0, float* dL_dshN) {
     const int deg = cam->sh_degree, K = (deg + 1) * (deg + 1), KR = cam->sh_rest_alloc;
-    const float* V = cam->view; const float* Pm = cam->proj;
+    double V[16], Pm[16];
+    for (int k = 0; k < 16; k++) { V[k] = cam->view[k]; Pm[k] = cam->proj[k]; }
     (void)sh0;
 #pragma omp parallel for schedule(static)
     for (int i = 0; i < N; i++) {
@@ -465,154 +479,169 @@ void orc_preprocess_bwd(const orc_camera* cam, int32_t N, const float* means3D, 
         dL_dopacities[i] = 0;
         for (int k = 0; k < 3 * KR; k++) dL_dshN[3 * (size_t)KR * i + k] = 0;
         if (radii[i] <= 0) continue;
-        const float* p = means3D + 3 * (size_t)i;
-        act_t a; activate(cam, scales, quats, opacities, i, &a);
-        float R[3][3], M[3][3], c6[6];
-        quat_to_R(a.q, R);
-        cov3d_from(a.s, R, M, c6);
-        float t[3]; xform43(V, p, t);
-        ewa_t e; ewa_cov2d(cam, t, c6, &e);
-        float dmean[3] = {0, 0, 0};
+        const double p[3] = {means3D[3 * (size_t)i], means3D[3 * (size_t)i + 1], means3D[3 * (size_t)i + 2]};
+        /* activations */
+        double s[3], q[4], qlen = 1.0, o;
+        const int activated = cam->flags & ORC_FLAG_INPUT_ACTIVATED;
+        if (activated) {
+            for (int k = 0; k < 3; k++) s[k] = (double)cam->scale_modifier * scales[3 * i + k];
+            for (int k = 0; k < 4; k++) q[k] = quats[4 * i + k];
+            o = opacities[i];
+        } else {
+            for (int k = 0; k < 3; k++) s[k] = (double)cam->scale_modifier * exp((double)scales[3 * i + k]);
+            double n2 = 0; for (int k = 0; k < 4; k++) n2 += (double)quats[4 * i + k] * quats[4 * i + k];
+            qlen = sqrt(n2);
+            for (int k = 0; k < 4; k++) q[k] = quats[4 * i + k] / qlen;
+            o = 1.0 / (1.0 + exp(-(double)opacities[i]));
+        }
+        const double r = q[0], x = q[1], y = q[2], z = q[3];
+        const double R[3][3] = {{1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y)},
+                                {2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x)},
+                                {2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)}};
+        double M[3][3], S[3][3];
+        for (int a = 0; a < 3; a++) for (int k = 0; k < 3; k++) M[a][k] = R[a][k] * s[k];
+        for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) S[a][b] = M[a][0] * M[b][0] + M[a][1] * M[b][1] + M[a][2] * M[b][2];
+        double t[3];
+        for (int a = 0; a < 3; a++) t[a] = V[a] * p[0] + V[4 + a] * p[1] + V[8 + a] * p[2] + V[12 + a];
+        const double fx = cam->width / (2.0 * cam->tanfovx), fy = cam->height / (2.0 * cam->tanfovy);
+        const double limx = 1.3 * cam->tanfovx, limy = 1.3 * cam->tanfovy;
+        const double txtz = t[0] / t[2], tytz = t[1] / t[2];
+        const double tx = fmin(limx, fmax(-limx, txtz)) * t[2], ty = fmin(limy, fmax(-limy, tytz)) * t[2];
+        const double tzi = 1.0 / t[2], tz2 = tzi * tzi, tz3 = tz2 * tzi;
+        const double J00 = fx * tzi, J02 = -fx * tx * tz2, J11 = fy * tzi, J12 = -fy * ty * tz2;
+        double T[2][3], TS[2][3];
+        for (int j = 0; j < 3; j++) {
+            T[0][j] = J00 * V[4 * j + 0] + J02 * V[4 * j + 2];
+            T[1][j] = J11 * V[4 * j + 1] + J12 * V[4 * j + 2];
+        }
+        for (int a = 0; a < 2; a++) for (int j = 0; j < 3; j++) TS[a][j] = T[a][0] * S[0][j] + T[a][1] * S[1][j] + T[a][2] * S[2][j];
+        const double ca = TS[0][0] * T[0][0] + TS[0][1] * T[0][1] + TS[0][2] * T[0][2] + 0.3;
+        const double cb = TS[0][0] * T[1][0] + TS[0][1] * T[1][1] + TS[0][2] * T[1][2];
+        const double cc = TS[1][0] * T[1][0] + TS[1][1] * T[1][1] + TS[1][2] * T[1][2] + 0.3;
+        double dmean[3] = {0, 0, 0};
 
         /* 1. conic -> cov2D: dSigma' = -Q G Q, Q = conic matrix, G = sym(dA, dB/2, dC) */
-        const float det = e.a * e.c - e.b * e.b;
-        const float kappa = 1.0f / (det * det + 1e-7f);
-        const float dA = dL_dconic[3 * i], dBh = 0.5f * dL_dconic[3 * i + 1], dC = dL_dconic[3 * i + 2];
-        float da = 0, db = 0, dc = 0;
-        if (kappa != 0.0f) {
-            da = kappa * (-e.c * e.c * dA + 2.0f * e.b * e.c * dBh + (det - e.a * e.c) * dC);
-            dc = kappa * (-e.a * e.a * dC + 2.0f * e.a * e.b * dBh + (det - e.a * e.c) * dA);
-            db = kappa * 2.0f * (e.b * e.c * dA - (det + 2.0f * e.b * e.b) * dBh + e.a * e.b * dC);
-        }
-        /* 2. cov2D -> cov3D (6 stored values; off-diagonals carry the doubled cross terms) */
-        const float (*T)[3] = e.T;
-        float dcov[6];
-        dcov[0] = T[0][0] * T[0][0] * da + T[0][0] * T[1][0] * db + T[1][0] * T[1][0] * dc;
-        dcov[3] = T[0][1] * T[0][1] * da + T[0][1] * T[1][1] * db + T[1][1] * T[1][1] * dc;
-        dcov[5] = T[0][2] * T[0][2] * da + T[0][2] * T[1][2] * db + T[1][2] * T[1][2] * dc;
-        dcov[1] = 2 * T[0][0] * T[0][1] * da + (T[0][0] * T[1][1] + T[0][1] * T[1][0]) * db + 2 * T[1][0] * T[1][1] * dc;
-        dcov[2] = 2 * T[0][0] * T[0][2] * da + (T[0][0] * T[1][2] + T[0][2] * T[1][0]) * db + 2 * T[1][0] * T[1][2] * dc;
-        dcov[4] = 2 * T[0][2] * T[0][1] * da + (T[0][1] * T[1][2] + T[0][2] * T[1][1]) * db + 2 * T[1][1] * T[1][2] * dc;
-        /* cov2D -> T: dT = 2 G' T Sigma, G' = [[da, db/2],[db/2, dc]] */
-        const float S[3][3] = {{c6[0], c6[1], c6[2]}, {c6[1], c6[3], c6[4]}, {c6[2], c6[4], c6[5]}};
-        float TS[2][3];
-        for (int r = 0; r < 2; r++)
-            for (int j = 0; j < 3; j++) TS[r][j] = T[r][0] * S[0][j] + T[r][1] * S[1][j] + T[r][2] * S[2][j];
-        float dT[2][3];
+        const double det = ca * cc - cb * cb;
+        const double kappa = 1.0 / (det * det + 1e-7);
+        const double dA = dL_dconic[3 * i], dBh = 0.5 * dL_dconic[3 * i + 1], dC = dL_dconic[3 * i + 2];
+        const double da = kappa * (-cc * cc * dA + 2.0 * cb * cc * dBh + (det - ca * cc) * dC);
+        const double dc = kappa * (-ca * ca * dC + 2.0 * ca * cb * dBh + (det - ca * cc) * dA);
+        const double db = kappa * 2.0 * (cb * cc * dA - (det + 2.0 * cb * cb) * dBh + ca * cb * dC);
+        /* 2. cov2D -> Sigma (symmetric gradient) and -> T -> J -> t */
+        double dS[3][3];
+        for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++)
+            dS[a][b] = T[0][a] * T[0][b] * da + 0.5 * (T[0][a] * T[1][b] + T[1][a] * T[0][b]) * db + T[1][a] * T[1][b] * dc;
+        double dT[2][3];
         for (int j = 0; j < 3; j++) {
-            dT[0][j] = 2.0f * da * TS[0][j] + db * TS[1][j];
-            dT[1][j] = 2.0f * dc * TS[1][j] + db * TS[0][j];
+            dT[0][j] = 2.0 * da * TS[0][j] + db * TS[1][j];
+            dT[1][j] = 2.0 * dc * TS[1][j] + db * TS[0][j];
         }
-        /* T = J W  ->  dJ = dT W^T (non-zero J entries only); W_rc = V[4c+r] */
-        float dJ00 = 0, dJ02 = 0, dJ11 = 0, dJ12 = 0;
+        double dJ00 = 0, dJ02 = 0, dJ11 = 0, dJ12 = 0;
         for (int j = 0; j < 3; j++) {
-            dJ00 += V[4 * j + 0] * dT[0][j];
-            dJ02 += V[4 * j + 2] * dT[0][j];
-            dJ11 += V[4 * j + 1] * dT[1][j];
-            dJ12 += V[4 * j + 2] * dT[1][j];
+            dJ00 += V[4 * j + 0] * dT[0][j]; dJ02 += V[4 * j + 2] * dT[0][j];
+            dJ11 += V[4 * j + 1] * dT[1][j]; dJ12 += V[4 * j + 2] * dT[1][j];
         }
-        const float tz = 1.0f / e.tz, tz2 = tz * tz, tz3 = tz2 * tz;
-        const float mx_ = (e.txtz < -e.limx || e.txtz > e.limx) ? 0.0f : 1.0f;
-        const float my_ = (e.tytz < -e.limy || e.tytz > e.limy) ? 0.0f : 1.0f;
-        float dt[3];
-        dt[0] = mx_ * (-e.fx * tz2) * dJ02;
-        dt[1] = my_ * (-e.fy * tz2) * dJ12;
-        dt[2] = -e.fx * tz2 * dJ00 - e.fy * tz2 * dJ11 + (2.0f * e.fx * e.tx) * tz3 * dJ02 +
-                (2.0f * e.fy * e.ty) * tz3 * dJ12;
+        const double mx_ = (txtz < -limx || txtz > limx) ? 0.0 : 1.0;
+        const double my_ = (tytz < -limy || tytz > limy) ? 0.0 : 1.0;
+        double dt[3];
+        dt[0] = mx_ * (-fx * tz2) * dJ02;
+        dt[1] = my_ * (-fy * tz2) * dJ12;
+        dt[2] = -fx * tz2 * dJ00 - fy * tz2 * dJ11 + (2.0 * fx * tx) * tz3 * dJ02 + (2.0 * fy * ty) * tz3 * dJ12;
         for (int c = 0; c < 3; c++) dmean[c] += V[4 * c + 0] * dt[0] + V[4 * c + 1] * dt[1] + V[4 * c + 2] * dt[2];
 
         /* 3. projection: mean2D (ndc-scaled gradient) -> mean3D */
         {
-            float h[4]; xform44(Pm, p, h);
-            const float m_w = 1.0f / (h[3] + 1e-7f);
-            const float mul1 = h[0] * m_w * m_w, mul2 = h[1] * m_w * m_w;
-            const float g0 = dL_dmean2D[2 * i], g1 = dL_dmean2D[2 * i + 1];
+            double h[4];
+            for (int a = 0; a < 4; a++) h[a] = Pm[a] * p[0] + Pm[4 + a] * p[1] + Pm[8 + a] * p[2] + Pm[12 + a];
+            const double m_w = 1.0 / (h[3] + 1e-7);
+            const double mul1 = h[0] * m_w * m_w, mul2 = h[1] * m_w * m_w;
+            const double g0 = dL_dmean2D[2 * i], g1 = dL_dmean2D[2 * i + 1];
             for (int c = 0; c < 3; c++)
-                dmean[c] += (Pm[4 * c + 0] * m_w - Pm[4 * c + 3] * mul1) * g0 +
-                            (Pm[4 * c + 1] * m_w - Pm[4 * c + 3] * mul2) * g1;
+                dmean[c] += (Pm[4 * c + 0] * m_w - Pm[4 * c + 3] * mul1) * g0 + (Pm[4 * c + 1] * m_w - Pm[4 * c + 3] * mul2) * g1;
         }
 
         /* 4. SH: colour -> coefficients and -> direction -> mean */
         {
-            float dir_o[3] = {p[0] - cam->campos[0], p[1] - cam->campos[1], p[2] - cam->campos[2]};
-            const float len = sqrtf(dir_o[0] * dir_o[0] + dir_o[1] * dir_o[1] + dir_o[2] * dir_o[2]);
-            const float d[3] = {dir_o[0] / len, dir_o[1] / len, dir_o[2] / len};
-            float bas[16]; sh_basis(deg, d, bas);
-            float dcol[3];
-            for (int ch = 0; ch < 3; ch++) dcol[ch] = clamped[3 * i + ch] ? 0.0f : dL_dcolor[3 * i + ch];
-            for (int ch = 0; ch < 3; ch++) dL_dsh0[3 * i + ch] = bas[0] * dcol[ch];
-            for (int k = 1; k < K; k++)
-                for (int ch = 0; ch < 3; ch++) dL_dshN[3 * ((size_t)i * KR + (k - 1)) + ch] = bas[k] * dcol[ch];
-            /* d(basis_k)/d(x,y,z) */
-            float gb[16][3]; memset(gb, 0, sizeof gb);
-            const float x = d[0], y = d[1], z = d[2];
-            if (deg >= 1) { gb[1][1] = -SH_C1; gb[2][2] = SH_C1; gb[3][0] = -SH_C1; }
+            const double dir_o[3] = {p[0] - cam->campos[0], p[1] - cam->campos[1], p[2] - cam->campos[2]};
+            const double len = sqrt(dir_o[0] * dir_o[0] + dir_o[1] * dir_o[1] + dir_o[2] * dir_o[2]);
+            const double d[3] = {dir_o[0] / len, dir_o[1] / len, dir_o[2] / len};
+            double dcol[3];
+            for (int ch = 0; ch < 3; ch++) dcol[ch] = clamped[3 * i + ch] ? 0.0 : (double)dL_dcolor[3 * i + ch];
+            const double X = d[0], Y = d[1], Z = d[2];
+            double bas[16], gb[16][3]; memset(gb, 0, sizeof gb); memset(bas, 0, sizeof bas);
+            bas[0] = SH_C0;
+            if (deg >= 1) {
+                bas[1] = -(double)SH_C1 * Y; bas[2] = (double)SH_C1 * Z; bas[3] = -(double)SH_C1 * X;
+                gb[1][1] = -SH_C1; gb[2][2] = SH_C1; gb[3][0] = -SH_C1;
+            }
             if (deg >= 2) {
-                const float xx = x * x, yy = y * y, zz = z * z;
-                gb[4][0] = SH_C2[0] * y; gb[4][1] = SH_C2[0] * x;
-                gb[5][1] = SH_C2[1] * z; gb[5][2] = SH_C2[1] * y;
-                gb[6][0] = SH_C2[2] * -2.0f * x; gb[6][1] = SH_C2[2] * -2.0f * y; gb[6][2] = SH_C2[2] * 4.0f * z;
-                gb[7][0] = SH_C2[3] * z; gb[7][2] = SH_C2[3] * x;
-                gb[8][0] = SH_C2[4] * 2.0f * x; gb[8][1] = SH_C2[4] * -2.0f * y;
+                const double xx = X * X, yy = Y * Y, zz = Z * Z;
+                bas[4] = SH_C2[0] * X * Y; bas[5] = SH_C2[1] * Y * Z; bas[6] = SH_C2[2] * (2 * zz - xx - yy);
+                bas[7] = SH_C2[3] * X * Z; bas[8] = SH_C2[4] * (xx - yy);
+                gb[4][0] = SH_C2[0] * Y; gb[4][1] = SH_C2[0] * X;
+                gb[5][1] = SH_C2[1] * Z; gb[5][2] = SH_C2[1] * Y;
+                gb[6][0] = SH_C2[2] * -2.0 * X; gb[6][1] = SH_C2[2] * -2.0 * Y; gb[6][2] = SH_C2[2] * 4.0 * Z;
+                gb[7][0] = SH_C2[3] * Z; gb[7][2] = SH_C2[3] * X;
+                gb[8][0] = SH_C2[4] * 2.0 * X; gb[8][1] = SH_C2[4] * -2.0 * Y;
                 if (deg >= 3) {
-                    gb[9][0] = SH_C3[0] * 6.0f * x * y; gb[9][1] = SH_C3[0] * (3.0f * xx - 3.0f * yy);
-                    gb[10][0] = SH_C3[1] * y * z; gb[10][1] = SH_C3[1] * x * z; gb[10][2] = SH_C3[1] * x * y;
-                    gb[11][0] = SH_C3[2] * -2.0f * x * y; gb[11][1] = SH_C3[2] * (4.0f * zz - xx - 3.0f * yy);
-                    gb[11][2] = SH_C3[2] * 8.0f * y * z;
-                    gb[12][0] = SH_C3[3] * -6.0f * x * z; gb[12][1] = SH_C3[3] * -6.0f * y * z;
-                    gb[12][2] = SH_C3[3] * (6.0f * zz - 3.0f * xx - 3.0f * yy);
-                    gb[13][0] = SH_C3[4] * (4.0f * zz - 3.0f * xx - yy); gb[13][1] = SH_C3[4] * -2.0f * x * y;
-                    gb[13][2] = SH_C3[4] * 8.0f * x * z;
-                    gb[14][0] = SH_C3[5] * 2.0f * x * z; gb[14][1] = SH_C3[5] * -2.0f * y * z;
-                    gb[14][2] = SH_C3[5] * (xx - yy);
-                    gb[15][0] = SH_C3[6] * (3.0f * xx - 3.0f * yy); gb[15][1] = SH_C3[6] * -6.0f * x * y;
+                    bas[9] = SH_C3[0] * Y * (3 * xx - yy); bas[10] = SH_C3[1] * X * Y * Z;
+                    bas[11] = SH_C3[2] * Y * (4 * zz - xx - yy); bas[12] = SH_C3[3] * Z * (2 * zz - 3 * xx - 3 * yy);
+                    bas[13] = SH_C3[4] * X * (4 * zz - xx - yy); bas[14] = SH_C3[5] * Z * (xx - yy);
+                    bas[15] = SH_C3[6] * X * (xx - 3 * yy);
+                    gb[9][0] = SH_C3[0] * 6.0 * X * Y; gb[9][1] = SH_C3[0] * (3.0 * xx - 3.0 * yy);
+                    gb[10][0] = SH_C3[1] * Y * Z; gb[10][1] = SH_C3[1] * X * Z; gb[10][2] = SH_C3[1] * X * Y;
+                    gb[11][0] = SH_C3[2] * -2.0 * X * Y; gb[11][1] = SH_C3[2] * (4.0 * zz - xx - 3.0 * yy);
+                    gb[11][2] = SH_C3[2] * 8.0 * Y * Z;
+                    gb[12][0] = SH_C3[3] * -6.0 * X * Z; gb[12][1] = SH_C3[3] * -6.0 * Y * Z;
+                    gb[12][2] = SH_C3[3] * (6.0 * zz - 3.0 * xx - 3.0 * yy);
+                    gb[13][0] = SH_C3[4] * (4.0 * zz - 3.0 * xx - yy); gb[13][1] = SH_C3[4] * -2.0 * X * Y;
+                    gb[13][2] = SH_C3[4] * 8.0 * X * Z;
+                    gb[14][0] = SH_C3[5] * 2.0 * X * Z; gb[14][1] = SH_C3[5] * -2.0 * Y * Z; gb[14][2] = SH_C3[5] * (xx - yy);
+                    gb[15][0] = SH_C3[6] * (3.0 * xx - 3.0 * yy); gb[15][1] = SH_C3[6] * -6.0 * X * Y;
                 }
             }
-            float ddir[3] = {0, 0, 0};
+            for (int ch = 0; ch < 3; ch++) dL_dsh0[3 * i + ch] = (float)(bas[0] * dcol[ch]);
+            for (int k = 1; k < K; k++)
+                for (int ch = 0; ch < 3; ch++) dL_dshN[3 * ((size_t)i * KR + (k - 1)) + ch] = (float)(bas[k] * dcol[ch]);
+            double ddir[3] = {0, 0, 0};
             for (int k = 1; k < K; k++) {
-                float s = 0.0f;
-                for (int ch = 0; ch < 3; ch++) s += shN[3 * ((size_t)i * KR + (k - 1)) + ch] * dcol[ch];
-                ddir[0] += gb[k][0] * s; ddir[1] += gb[k][1] * s; ddir[2] += gb[k][2] * s;
+                double sk = 0.0;
+                for (int ch = 0; ch < 3; ch++) sk += (double)shN[3 * ((size_t)i * KR + (k - 1)) + ch] * dcol[ch];
+                ddir[0] += gb[k][0] * sk; ddir[1] += gb[k][1] * sk; ddir[2] += gb[k][2] * sk;
             }
-            /* normalisation Jacobian: (I - d d^T)/len */
-            const float dd = d[0] * ddir[0] + d[1] * ddir[1] + d[2] * ddir[2];
+            const double dd = d[0] * ddir[0] + d[1] * ddir[1] + d[2] * ddir[2];
             for (int c = 0; c < 3; c++) dmean[c] += (ddir[c] - d[c] * dd) / len;
         }
-        for (int c = 0; c < 3; c++) dL_dmeans3D[3 * i + c] = dmean[c];
+        for (int c = 0; c < 3; c++) dL_dmeans3D[3 * i + c] = (float)dmean[c];
 
-        /* 5. cov3D -> scale, rotation.  Sigma = Mr Mr^T, Mr = R diag(s) */
+        /* 5. Sigma -> scale, rotation.  Sigma = Mr Mr^T, Mr = R diag(s) */
         {
-            const float dS[3][3] = {{dcov[0], 0.5f * dcov[1], 0.5f * dcov[2]},
-                                    {0.5f * dcov[1], dcov[3], 0.5f * dcov[4]},
-                                    {0.5f * dcov[2], 0.5f * dcov[4], dcov[5]}};
-            float dM[3][3];
-            for (int r = 0; r < 3; r++)
-                for (int k = 0; k < 3; k++)
-                    dM[r][k] = 2.0f * (dS[r][0] * M[0][k] + dS[r][1] * M[1][k] + dS[r][2] * M[2][k]);
-            float ds[3], dR[3][3];
+            double dM[3][3];
+            for (int a = 0; a < 3; a++) for (int k = 0; k < 3; k++)
+                dM[a][k] = 2.0 * (dS[a][0] * M[0][k] + dS[a][1] * M[1][k] + dS[a][2] * M[2][k]);
+            double ds[3], dR[3][3];
             for (int k = 0; k < 3; k++) {
                 ds[k] = R[0][k] * dM[0][k] + R[1][k] * dM[1][k] + R[2][k] * dM[2][k];
-                for (int r = 0; r < 3; r++) dR[r][k] = dM[r][k] * a.s[k];
+                for (int a = 0; a < 3; a++) dR[a][k] = dM[a][k] * s[k];
             }
-            const float r = a.q[0], x = a.q[1], y = a.q[2], z = a.q[3];
-            float dq[4];
-            dq[0] = 2.0f * (z * (dR[1][0] - dR[0][1]) + y * (dR[0][2] - dR[2][0]) + x * (dR[2][1] - dR[1][2]));
-            dq[1] = 2.0f * (y * (dR[0][1] + dR[1][0]) + z * (dR[0][2] + dR[2][0]) + r * (dR[2][1] - dR[1][2])) -
-                    4.0f * x * (dR[1][1] + dR[2][2]);
-            dq[2] = 2.0f * (x * (dR[0][1] + dR[1][0]) + r * (dR[0][2] - dR[2][0]) + z * (dR[1][2] + dR[2][1])) -
-                    4.0f * y * (dR[0][0] + dR[2][2]);
-            dq[3] = 2.0f * (r * (dR[1][0] - dR[0][1]) + x * (dR[0][2] + dR[2][0]) + y * (dR[1][2] + dR[2][1])) -
-                    4.0f * z * (dR[0][0] + dR[1][1]);
+            double dq[4];
+            dq[0] = 2.0 * (z * (dR[1][0] - dR[0][1]) + y * (dR[0][2] - dR[2][0]) + x * (dR[2][1] - dR[1][2]));
+            dq[1] = 2.0 * (y * (dR[0][1] + dR[1][0]) + z * (dR[0][2] + dR[2][0]) + r * (dR[2][1] - dR[1][2])) -
+                    4.0 * x * (dR[1][1] + dR[2][2]);
+            dq[2] = 2.0 * (x * (dR[0][1] + dR[1][0]) + r * (dR[0][2] - dR[2][0]) + z * (dR[1][2] + dR[2][1])) -
+                    4.0 * y * (dR[0][0] + dR[2][2]);
+            dq[3] = 2.0 * (r * (dR[1][0] - dR[0][1]) + x * (dR[0][2] + dR[2][0]) + y * (dR[1][2] + dR[2][1])) -
+                    4.0 * z * (dR[0][0] + dR[1][1]);
             /* 6. activations (chain rule to the stored raw parameters) */
-            if (cam->flags & ORC_FLAG_INPUT_ACTIVATED) {
-                for (int k = 0; k < 3; k++) dL_dscales[3 * i + k] = ds[k] * cam->scale_modifier;
-                for (int k = 0; k < 4; k++) dL_dquats[4 * i + k] = dq[k];
+            if (activated) {
+                for (int k = 0; k < 3; k++) dL_dscales[3 * i + k] = (float)(ds[k] * cam->scale_modifier);
+                for (int k = 0; k < 4; k++) dL_dquats[4 * i + k] = (float)dq[k];
                 dL_dopacities[i] = dL_dopacity_act[i];
             } else {
-                for (int k = 0; k < 3; k++) dL_dscales[3 * i + k] = ds[k] * a.s[k];
-                const float qd = a.q[0] * dq[0] + a.q[1] * dq[1] + a.q[2] * dq[2] + a.q[3] * dq[3];
-                for (int k = 0; k < 4; k++) dL_dquats[4 * i + k] = (dq[k] - a.q[k] * qd) / a.qlen;
-                dL_dopacities[i] = dL_dopacity_act[i] * a.o * (1.0f - a.o);
+                for (int k = 0; k < 3; k++) dL_dscales[3 * i + k] = (float)(ds[k] * s[k]);
+                const double qd = q[0] * dq[0] + q[1] * dq[1] + q[2] * dq[2] + q[3] * dq[3];
+                for (int k = 0; k < 4; k++) dL_dquats[4 * i + k] = (float)((dq[k] - q[k] * qd) / qlen);
+                dL_dopacities[i] = (float)((double)dL_dopacity_act[i] * o * (1.0 - o));
             }
         }
     }

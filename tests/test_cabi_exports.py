@@ -1,0 +1,51 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/dvs_rast.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "dvs_rast.h")).read()
+    return sorted(set(re.findall(r"DVS_API\s+[\w\s\*]+?\b(dvs_rast_\w+)\s*\(", src)))
+
+
+def test_header_declares_the_expected_entry_points():
+    names = _declared()
+    for n in ("dvs_rast_create", "dvs_rast_destroy", "dvs_rast_forward", "dvs_rast_backward", "dvs_rast_step_host",
+              "dvs_rast_last_error", "dvs_rast_get_stats", "dvs_rast_debug_read", "dvs_rast_reserve"):
+        assert n in names
+
+
+def test_library_exports_every_declared_symbol():
+    from divshot_b200 import _cabi, build
+    build.build_rast()
+    lib = ctypes.CDLL(_cabi.LIB_PATH)
+    for n in _declared():
+        assert hasattr(lib, n), f"libdvsrast.so does not export {n}"
+    assert set(_cabi.EXPORTS) == set(_declared())
+    lib.dvs_rast_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.dvs_rast_version()
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from divshot_b200.rasterizer import Rasterizer, RasterizerError
+    with pytest.raises(RasterizerError):
+        Rasterizer(0)
+    # and the raw C-ABI refuses too (no silent CPU path)
+    from divshot_b200 import _cabi
+    h = ctypes.c_void_p()
+    assert _cabi.load().dvs_rast_create(0, ctypes.byref(h)) != 0
+
+
+def test_struct_layouts_match_header():
+    from divshot_b200 import _cabi
+    assert ctypes.sizeof(_cabi.DvsCamera) == 4 * (16 + 16 + 3 + 2 + 2 + 3 + 1 + 3)
+    assert ctypes.sizeof(_cabi.DvsParams) == 6 * 8 and ctypes.sizeof(_cabi.DvsGrads) == 8 * 8
+    assert ctypes.sizeof(_cabi.DvsStats) == 5 * 8 + 3 * 4 + 4
