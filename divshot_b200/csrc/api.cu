@@ -31,6 +31,7 @@ struct dvs_rast_ctx {
     uint32_t* tile_count = nullptr;
     uint32_t* tile_base = nullptr;  // T+1
     uint32_t* tile_cursor = nullptr;
+    uint32_t* class_tiles = nullptr;  // [5][T] per-sort-class tile lists
     // per-duplicate
     int64_t cap_dups = 0;
     unsigned long long* bins = nullptr;
@@ -42,7 +43,7 @@ struct dvs_rast_ctx {
     float* h2d_grad = nullptr;   // [3P] staging for dvs_rast_step_host
     float* d_image = nullptr;    // [3P]
     // small device words + pinned mirror
-    uint32_t* info = nullptr;               // [4]: D, max len, overflow
+    uint32_t* info = nullptr;               // [16]: D, max len, overflow, -, tiles per sort class [5]
     unsigned long long* stats = nullptr;    // [2]: V, D
     uint32_t* h_info = nullptr;             // pinned [4]
     unsigned long long* h_stats = nullptr;  // pinned [2]
@@ -52,6 +53,9 @@ struct dvs_rast_ctx {
     int64_t N = 0;
     dvs_stats st{};
     cudaEvent_t ev[DVS_NUM_STAGES + 2] = {};
+    // dvs_rast_step_host: copies run on their own stream so the H2D overlaps the forward and the D2H the backward
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_img = nullptr, ev_d2h = nullptr;
     bool ev_fwd = false, ev_bwd = false;
 };
 
@@ -90,9 +94,10 @@ static int ensure_gauss(dvs_rast_ctx* ctx, int64_t N) {
 }
 static int ensure_tiles(dvs_rast_ctx* ctx, int64_t T) {
     if (T <= ctx->cap_tiles) return DVS_OK;
-    CK(regrow(ctx->tile_count, (size_t)T));
+    CK(regrow(ctx->tile_count, (size_t)T * TILE_CTR_STRIDE));
     CK(regrow(ctx->tile_base, (size_t)T + 1));
-    CK(regrow(ctx->tile_cursor, (size_t)T));
+    CK(regrow(ctx->tile_cursor, (size_t)T * TILE_CTR_STRIDE));
+    CK(regrow(ctx->class_tiles, 5 * (size_t)T));
     ctx->cap_tiles = T;
     return DVS_OK;
 }
@@ -125,11 +130,15 @@ int dvs_rast_create(int device, dvs_rast_ctx** out) {
     if (!ctx) return DVS_E_NOMEM;
     ctx->device = device;
     cudaError_t e = cudaSetDevice(device);
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->info), 4 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->info), 16 * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->stats), 2 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_info), 4 * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_stats), 2 * sizeof(unsigned long long));
     for (int i = 0; e == cudaSuccess && i < DVS_NUM_STAGES + 2; i++) e = cudaEventCreate(&ctx->ev[i]);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_h2d, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_img, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_d2h, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         // the product path must fail loudly without a usable CUDA device: there is no CPU fallback.
         fprintf(stderr, "dvs_rast_create: CUDA unavailable on device %d: %s\n", device, cudaGetErrorString(e));
@@ -144,13 +153,17 @@ void dvs_rast_destroy(dvs_rast_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaFree(ctx->rec); cudaFree(ctx->aux); cudaFree(ctx->sgrad);
-    cudaFree(ctx->tile_count); cudaFree(ctx->tile_base); cudaFree(ctx->tile_cursor);
+    cudaFree(ctx->tile_count); cudaFree(ctx->tile_base); cudaFree(ctx->tile_cursor); cudaFree(ctx->class_tiles);
     cudaFree(ctx->bins); cudaFree(ctx->plist);
     cudaFree(ctx->final_T); cudaFree(ctx->n_contrib); cudaFree(ctx->h2d_grad); cudaFree(ctx->d_image);
     cudaFree(ctx->info); cudaFree(ctx->stats);
     cudaFreeHost(ctx->h_info); cudaFreeHost(ctx->h_stats);
     for (auto& e : ctx->ev)
         if (e) cudaEventDestroy(e);
+    if (ctx->ev_h2d) cudaEventDestroy(ctx->ev_h2d);
+    if (ctx->ev_img) cudaEventDestroy(ctx->ev_img);
+    if (ctx->ev_d2h) cudaEventDestroy(ctx->ev_d2h);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
 }
 
@@ -221,17 +234,17 @@ int dvs_rast_forward(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, const 
     ctx->have_fwd = false;
     ctx->st.overflow = 0;
     for (int attempt = 0; attempt < 3; attempt++) {
-        CK(cudaMemsetAsync(ctx->tile_count, 0, (size_t)T * sizeof(uint32_t), st));
+        CK(cudaMemsetAsync(ctx->tile_count, 0, (size_t)T * TILE_CTR_STRIDE * sizeof(uint32_t), st));
         CK(cudaMemsetAsync(ctx->stats, 0, 2 * sizeof(unsigned long long), st));
         CK(cudaEventRecord(ctx->ev[0], st));
         CK(launch_preprocess_fwd(c, (int)N, prm, ctx->rec, ctx->aux, ctx->tile_count, out_radii, ctx->stats, st));
         CK(cudaEventRecord(ctx->ev[1], st));
         CK(launch_tile_scan((int)T, ctx->tile_count, ctx->tile_base, ctx->tile_cursor, ctx->info,
-                            (uint32_t)ctx->cap_dups, st));
+                            (uint32_t)ctx->cap_dups, ctx->class_tiles, st));
         CK(cudaEventRecord(ctx->ev[2], st));
-        CK(launch_emit(c, (int)N, ctx->rec, ctx->aux, ctx->tile_cursor, ctx->bins, (uint32_t)ctx->cap_dups, st));
+        CK(launch_emit(c, (int)N, ctx->aux, ctx->tile_cursor, ctx->bins, (uint32_t)ctx->cap_dups, st));
         CK(cudaEventRecord(ctx->ev[3], st));
-        CK(launch_tile_sort((int)T, ctx->tile_base, ctx->bins, ctx->plist, ctx->info, st));
+        CK(launch_tile_sort((int)T, c.gx, ctx->tile_base, ctx->bins, ctx->plist, ctx->info, ctx->class_tiles, ctx->rec, st));
         CK(cudaEventRecord(ctx->ev[4], st));
         CK(launch_render_fwd(c, ctx->tile_base, ctx->plist, ctx->rec, out_color, ctx->final_T, ctx->n_contrib,
                              ctx->info, st));
@@ -289,7 +302,7 @@ int dvs_rast_backward(dvs_rast_ctx* ctx, const dvs_params* params, const float* 
                          reinterpret_cast<float*>(ctx->sgrad), (flags & DVS_FLAG_ABSGRAD) && g.mean2D_abs,
                          ctx->info, st));
     CK(cudaEventRecord(ctx->ev[7], st));
-    CK(launch_preprocess_bwd(c, (int)N, prm, ctx->rec, ctx->sgrad, g, flags, st));
+    CK(launch_preprocess_bwd(c, (int)N, prm, ctx->aux, ctx->sgrad, g, flags, st));
     CK(cudaEventRecord(ctx->ev[8], st));
     ctx->ev_bwd = true;
     return DVS_OK;
@@ -307,10 +320,22 @@ int dvs_rast_step_host(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, cons
     if ((rc = ensure_pix(ctx, P))) return rc;
     if (!ctx->h2d_grad) CK(cudaMalloc(reinterpret_cast<void**>(&ctx->h2d_grad), 3 * (size_t)ctx->cap_pix * sizeof(float)));
     if (!ctx->d_image) CK(cudaMalloc(reinterpret_cast<void**>(&ctx->d_image), 3 * (size_t)ctx->cap_pix * sizeof(float)));
-    CK(cudaMemcpyAsync(ctx->h2d_grad, dL_dpix_host, 3 * (size_t)P * sizeof(float), cudaMemcpyHostToDevice, st));
+    // H2D of dL/dpix on the copy stream (overlaps the forward, which does not need it)
+    CK(cudaEventRecord(ctx->ev_img, st));  // orders the copy after whatever the caller queued before this step
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_img, 0));
+    CK(cudaMemcpyAsync(ctx->h2d_grad, dL_dpix_host, 3 * (size_t)P * sizeof(float), cudaMemcpyHostToDevice,
+                       ctx->copy_stream));
+    CK(cudaEventRecord(ctx->ev_h2d, ctx->copy_stream));
     if ((rc = dvs_rast_forward(ctx, cam, N, params, ctx->d_image, nullptr, stream))) return rc;
-    CK(cudaMemcpyAsync(out_color_host, ctx->d_image, 3 * (size_t)P * sizeof(float), cudaMemcpyDeviceToHost, st));
+    // D2H of the image on the copy stream (overlaps the backward)
+    CK(cudaEventRecord(ctx->ev_img, st));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_img, 0));
+    CK(cudaMemcpyAsync(out_color_host, ctx->d_image, 3 * (size_t)P * sizeof(float), cudaMemcpyDeviceToHost,
+                       ctx->copy_stream));
+    CK(cudaEventRecord(ctx->ev_d2h, ctx->copy_stream));
+    CK(cudaStreamWaitEvent(st, ctx->ev_h2d, 0));
     if ((rc = dvs_rast_backward(ctx, params, ctx->h2d_grad, grads, bwd_flags, stream))) return rc;
+    CK(cudaStreamWaitEvent(st, ctx->ev_d2h, 0));
     CK(cudaStreamSynchronize(st));
     return DVS_OK;
 }

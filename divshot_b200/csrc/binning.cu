@@ -4,14 +4,12 @@
 // the absent gsplatrast operator with a CUB-free design:
 //   * per-tile counts come from the preprocess kernel (RED per (Gaussian,tile));
 //   * one CTA scans the T counts with warp-shuffle prefix sums -> tile_base (= `ranges`);
-//   * emission claims a slot in its tile's bin with one atomic and writes an 8-byte entry
-//       depth_bits<<32 | id<<8 | submask
-//     (submask: which of the tile's eight 8x4-pixel sub-rectangles the opacity-aware AABB of the
-//     splat {alpha >= 1/255} overlaps — ours, used by A6/A7 to skip work; it never changes the lists);
-//   * one CTA per tile sorts its bin in shared memory (normalised bitonic network, all-ascending
-//     comparators, virtual +inf padding) and writes the low 32 bits (id<<8|submask) to plist.
-// Sorting the 64-bit entry ascending == the credited total order (tile, depth bits, Gaussian index),
-// because within a tile ids are unique and the mask sits below the id.
+//   * emission claims a slot in its tile's bin with one atomic and writes an 8-byte entry depth_bits<<32 | id;
+//   * one CTA per tile sorts its bin in shared memory (adaptive two-level bucket sort; bitonic network as
+//     the always-exact fallback) and writes id<<8 | submask to plist, where submask says which of the
+//     tile's eight 8x4-pixel sub-rectangles the splat's {alpha >= 1/255} ellipse can reach (ours, used by
+//     A6/A7 to skip work; it never changes the lists).
+// Sorting the 64-bit entry ascending == the credited total order (tile, depth bits, Gaussian index).
 // The order of arrival in a bin is non-deterministic; the sort makes the output deterministic.
 //
 // Roofline: HBM-light (8 B written + 8 B read + 4 B written per duplicate); sort is shared-memory /
@@ -26,22 +24,37 @@ namespace dvs {
 // ---------------------------------------------------------------------------------------------
 constexpr int SCAN_THREADS = 1024;
 
+// sort classes by tile-list length (see tile sort below)
+constexpr int NUM_SORT_CLASSES = 5;
+__host__ __device__ __forceinline__ int sort_class_of(uint32_t n) {
+    return n <= 1024u ? 0 : n <= 2048u ? 1 : n <= 4096u ? 2 : n <= 16384u ? 3 : 4;
+}
+
+constexpr int SCAN_MAX_PER_THREAD = 8;  // register-blocked fast path for T <= 8192 tiles
+
 __global__ void __launch_bounds__(SCAN_THREADS)
 tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_base,
-                 uint32_t* __restrict__ tile_cursor, uint32_t* __restrict__ info, uint32_t dup_capacity) {
+                 uint32_t* __restrict__ tile_cursor, uint32_t* __restrict__ info, uint32_t dup_capacity,
+                 uint32_t* __restrict__ class_tiles /* [NUM_SORT_CLASSES][T] */) {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t warp_max[32];
-    __shared__ uint32_t carry_s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
+    // chunked over [0,T) in slabs of SCAN_THREADS * SCAN_MAX_PER_THREAD; within a slab thread t owns the
+    // SCAN_MAX_PER_THREAD consecutive tiles starting at slab + t * SCAN_MAX_PER_THREAD (all loads in flight at once)
+    unsigned long long carry = 0;
     uint32_t mx = 0;
-    unsigned long long total64 = 0;
-    for (int base = 0; base < T; base += SCAN_THREADS) {
-        const int t = base + threadIdx.x;
-        const uint32_t c = t < T ? tile_count[t] : 0u;
-        mx = max(mx, c);
-        uint32_t v = c;  // inclusive warp scan
+    for (int slab = 0; slab < T; slab += SCAN_THREADS * SCAN_MAX_PER_THREAD) {
+        const int first = slab + threadIdx.x * SCAN_MAX_PER_THREAD;
+        uint32_t c[SCAN_MAX_PER_THREAD];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_MAX_PER_THREAD; k++) {
+            const int t = first + k;
+            c[k] = t < T ? tile_count[(size_t)t * TILE_CTR_STRIDE] : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < SCAN_MAX_PER_THREAD; k++) { sum += c[k]; mx = max(mx, c[k]); }
+        uint32_t v = sum;  // inclusive warp scan of the per-thread sums
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
             const uint32_t n = __shfl_up_sync(0xffffffffu, v, off);
@@ -59,123 +72,157 @@ tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint32_t* __res
             warp_sums[lane] = w;  // inclusive over warps
         }
         __syncthreads();
-        const uint32_t carry = carry_s;
-        const uint32_t excl = carry + (warp ? warp_sums[warp - 1] : 0u) + v - c;
-        if (t < T) {
-            tile_base[t] = excl;
-            tile_cursor[t] = excl;
+        uint32_t run = (uint32_t)carry + (warp ? warp_sums[warp - 1] : 0u) + v - sum;
+        const uint32_t slab_total = warp_sums[31];
+#pragma unroll
+        for (int k = 0; k < SCAN_MAX_PER_THREAD; k++) {
+            const int t = first + k;
+            if (t < T) {
+                tile_base[t] = run;
+                tile_cursor[(size_t)t * TILE_CTR_STRIDE] = run;
+            }
+            // per-class work lists for the sort kernels: warp-aggregated slot allocation (info[4+cls] = count)
+            const int cls = (t < T && c[k]) ? sort_class_of(c[k]) : -1;
+#pragma unroll
+            for (int q = 0; q < NUM_SORT_CLASSES; q++) {
+                const unsigned m = __ballot_sync(0xffffffffu, cls == q);
+                if (m) {
+                    uint32_t b = 0;
+                    if (lane == __ffs(m) - 1) b = atomicAdd(info + 4 + q, (uint32_t)__popc(m));
+                    b = __shfl_sync(0xffffffffu, b, __ffs(m) - 1);
+                    if (cls == q) class_tiles[(size_t)q * T + b + __popc(m & ((1u << lane) - 1u))] = (uint32_t)t;
+                }
+            }
+            run += c[k];
         }
-        __syncthreads();
-        if (threadIdx.x == SCAN_THREADS - 1) {
-            total64 += (unsigned long long)warp_sums[31];
-            carry_s = carry + warp_sums[31];
-        }
+        carry += slab_total;
         __syncthreads();
     }
-    // max tile length
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
     if (lane == 0) warp_max[warp] = mx;
     __syncthreads();
-    if (threadIdx.x == SCAN_THREADS - 1) {
+    if (threadIdx.x == 0) {
         uint32_t m = 0;
         for (int w = 0; w < SCAN_THREADS / 32; w++) m = max(m, warp_max[w]);
-        tile_base[T] = carry_s;
-        info[0] = carry_s;
+        tile_base[T] = (uint32_t)carry;
+        info[0] = (uint32_t)carry;
         info[1] = m;
-        info[2] = (total64 > (unsigned long long)dup_capacity) ? 1u : 0u;
+        info[2] = (carry > (unsigned long long)dup_capacity) ? 1u : 0u;
     }
 }
 
 cudaError_t launch_tile_scan(int T, const uint32_t* tile_count, uint32_t* tile_base, uint32_t* tile_cursor,
-                             uint32_t* info, uint32_t dup_capacity, cudaStream_t st) {
-    tile_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(T, tile_count, tile_base, tile_cursor, info, dup_capacity);
+                             uint32_t* info, uint32_t dup_capacity, uint32_t* class_tiles, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(info + 4, 0, NUM_SORT_CLASSES * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    tile_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(T, tile_count, tile_base, tile_cursor, info, dup_capacity,
+                                                 class_tiles);
     return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------
-// A3: emission.  One lane per Gaussian for small rects; rects with more than 32 tiles are
-// spread over the whole warp (upstream's per-thread loop serialises on them).
+// A3: emission.  Warp-cooperative: the 32 Gaussians of a warp flatten their tile rects into one work
+// list (warp-shuffle prefix scan of the duplication counts) and every lane takes every 32nd item, so a
+// big splat does not serialise its warp (upstream's per-thread loop does).  Reads only the 16-byte aux
+// word (rect + depth key); writes depth_bits<<32 | id.
 // ---------------------------------------------------------------------------------------------
 constexpr int EMIT_THREADS = 256;
 
-__device__ __forceinline__ uint32_t sub_mask(float mx, float my, float ex, float ey, int tx, int ty) {
-    // 8 sub-rectangles of 8x4 pixels: bit w -> x in [X0, X0+7], y in [Y0, Y0+3],
-    // X0 = 16*tx + 8*(w&1), Y0 = 16*ty + 4*(w>>1).  AABB overlap factorises into columns x rows.
-    const float X0 = (float)(tx * TILE), Y0 = (float)(ty * TILE);
-    const float xl = mx - ex, xh = mx + ex, yl = my - ey, yh = my + ey;
-    uint32_t col = 0, rowm = 0;
-    if (xl <= X0 + 7.0f && xh >= X0) col |= 1u;
-    if (xl <= X0 + 15.0f && xh >= X0 + 8.0f) col |= 2u;
-#pragma unroll
-    for (int r = 0; r < 4; r++)
-        if (yl <= Y0 + (float)(4 * r + 3) && yh >= Y0 + (float)(4 * r)) rowm |= 1u << r;
-    uint32_t m = 0;
-#pragma unroll
-    for (int r = 0; r < 4; r++)
-        if (rowm & (1u << r)) m |= col << (2 * r);
-    return (ex < 0.0f) ? 0u : m;
-}
-
-__device__ __forceinline__ void emit_one(int id, uint32_t depth_bits, float mx, float my, float ex, float ey,
-                                         int tx, int ty, int gx, uint32_t* tile_cursor, unsigned long long* bins,
-                                         uint32_t cap) {
-    const uint32_t m = sub_mask(mx, my, ex, ey, tx, ty);
-    const uint32_t slot = atomicAdd(tile_cursor + ty * gx + tx, 1u);
-    if (slot < cap)
-        bins[slot] = ((unsigned long long)depth_bits << 32) | ((unsigned long long)((uint32_t)id << 8) | m);
-}
-
 __global__ void __launch_bounds__(EMIT_THREADS)
-emit_kernel(Cam cam, int N, const float4* __restrict__ rec, const uint4* __restrict__ aux,
-            uint32_t* __restrict__ tile_cursor, unsigned long long* __restrict__ bins, uint32_t cap) {
+emit_kernel(int gx, int N, const uint4* __restrict__ aux, uint32_t* __restrict__ tile_cursor,
+            unsigned long long* __restrict__ bins, uint32_t cap) {
     const int i = blockIdx.x * EMIT_THREADS + threadIdx.x;
     const int lane = threadIdx.x & 31;
     uint4 ax = make_uint4(0, 0, 0, 0);
-    float mx = 0.f, my = 0.f;
-    uint32_t depth_bits = 0;
-    int minx = 0, miny = 0, maxx = 0, maxy = 0;
-    if (i < N) {
-        ax = __ldg(aux + i);
-        minx = ax.x & 0xffff; miny = ax.x >> 16; maxx = ax.y & 0xffff; maxy = ax.y >> 16;
+    if (i < N) ax = __ldg(aux + i);
+    const int minx = ax.x & 0xffff, miny = ax.x >> 16;
+    const int w = (int)(ax.y & 0xffff) - minx, h = (int)((ax.y >> 16) & 0x1fff) - miny;
+    const int area = (w > 0 && h > 0) ? w * h : 0;
+    int incl = area;  // inclusive warp scan of the duplication counts
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += n;
     }
-    const int w = maxx - minx, h = maxy - miny;
-    const int area = w * h;
-    if (area > 0) {
-        const float4 q0 = __ldg(rec + 3 * (size_t)i);
-        const float4 q2 = __ldg(rec + 3 * (size_t)i + 2);
-        mx = q0.x; my = q0.y;
-        depth_bits = __float_as_uint(q2.y);
-    }
-    const float ex = __uint_as_float(ax.z), ey = __uint_as_float(ax.w);
-    if (area > 0 && area <= 32) {
-        for (int y = miny; y < maxy; y++)
-            for (int x = minx; x < maxx; x++)
-                emit_one(i, depth_bits, mx, my, ex, ey, x, y, cam.gx, tile_cursor, bins, cap);
-    }
-    // warp-cooperative path for big rects
-    unsigned big = __ballot_sync(0xffffffffu, area > 32);
-    while (big) {
-        const int src = __ffs(big) - 1;
-        big &= big - 1;
-        const int b_id = __shfl_sync(0xffffffffu, i, src);
-        const uint32_t b_depth = __shfl_sync(0xffffffffu, depth_bits, src);
-        const float b_mx = __shfl_sync(0xffffffffu, mx, src), b_my = __shfl_sync(0xffffffffu, my, src);
-        const float b_ex = __shfl_sync(0xffffffffu, ex, src), b_ey = __shfl_sync(0xffffffffu, ey, src);
-        const int b_minx = __shfl_sync(0xffffffffu, minx, src), b_miny = __shfl_sync(0xffffffffu, miny, src);
-        const int b_w = __shfl_sync(0xffffffffu, w, src), b_area = __shfl_sync(0xffffffffu, area, src);
-        for (int k = lane; k < b_area; k += 32)
-            emit_one(b_id, b_depth, b_mx, b_my, b_ex, b_ey, b_minx + k % b_w, b_miny + k / b_w, cam.gx,
-                     tile_cursor, bins, cap);
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    for (int j0 = 0; j0 < total; j0 += 32) {
+        const int j = j0 + lane;
+        // source lane = number of lanes whose inclusive offset is <= j (binary search over the sorted offsets)
+        int pos = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const int v = __shfl_sync(0xffffffffu, incl, pos + step - 1);
+            if (v <= j) pos += step;
+        }
+        const int src = min(pos, 31);
+        const int s_incl = __shfl_sync(0xffffffffu, incl, src);
+        const int s_area = __shfl_sync(0xffffffffu, area, src);
+        const int s_minx = __shfl_sync(0xffffffffu, minx, src), s_miny = __shfl_sync(0xffffffffu, miny, src);
+        const int s_w = __shfl_sync(0xffffffffu, w, src);
+        const uint32_t s_depth = __shfl_sync(0xffffffffu, ax.z, src);
+        const int s_id = __shfl_sync(0xffffffffu, i, src);
+        if (j < total) {
+            const int k = j - (s_incl - s_area);
+            const int ty = s_miny + k / s_w, tx = s_minx + k % s_w;
+            const uint32_t slot = atomicAdd(tile_cursor + (size_t)(ty * gx + tx) * TILE_CTR_STRIDE, 1u);
+            if (slot < cap) bins[slot] = ((unsigned long long)s_depth << 32) | (uint32_t)s_id;
+        }
     }
 }
 
-cudaError_t launch_emit(const Cam& cam, int N, const float4* rec, const uint4* aux, uint32_t* tile_cursor,
-                        unsigned long long* bins, uint32_t dup_capacity, cudaStream_t st) {
+cudaError_t launch_emit(const Cam& cam, int N, const uint4* aux, uint32_t* tile_cursor, unsigned long long* bins,
+                        uint32_t dup_capacity, cudaStream_t st) {
     if (N <= 0) return cudaSuccess;
-    emit_kernel<<<(N + EMIT_THREADS - 1) / EMIT_THREADS, EMIT_THREADS, 0, st>>>(cam, N, rec, aux, tile_cursor,
-                                                                                 bins, dup_capacity);
+    emit_kernel<<<(N + EMIT_THREADS - 1) / EMIT_THREADS, EMIT_THREADS, 0, st>>>(cam.gx, N, aux, tile_cursor, bins,
+                                                                                 dup_capacity);
     return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sub-tile cull mask (ours; no upstream analogue).  For the sorted entry (tile, Gaussian): which of the
+// tile's eight 8x4-pixel sub-rectangles (bit w: x in [16tx+8(w&1), +7], y in [16ty+4(w>>1), +3]) can hold a
+// pixel with alpha >= 1/255, i.e. Q(d) = -(A2 dx^2 + B2 dx dy + C2 dy^2) <= lo - log2(1/255) for some d in
+// the box.  Q is convex with its minimum at d = 0, so the box minimum is on the edges facing the origin:
+//   q = min( Q(ex, clamp(-b ex / 2c)),  Q(clamp(-b ey / 2a), ey) ),  (ex, ey) = box point nearest to 0
+// evaluated branch-free for all 8 boxes (2 column ranges x 4 row ranges).  Conservative by a small margin
+// w.r.t. the per-pixel test of the compositing kernels; computed once per sorted entry, one thread each.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mask_from_record(uint32_t id, const float4 q0, const float4 q1, float X0,
+                                                     float Y0) {
+    const float mx = q0.x - X0, my = q0.y - Y0;  // mean relative to the tile origin
+    const float a = -q0.z, b = -q0.w, c = -q1.x;
+    const float m = (q1.y - ALPHA_MIN_LOG2) * 1.0001f + 1e-3f;
+    if (!(m > 0.0f)) return id << 8;                       // opacity < 1/255: never contributes
+    if (!(a > 0.0f && c > 0.0f)) return (id << 8) | 0xffu;  // degenerate conic: no culling
+    const float hbc = __fdividef(-0.5f * b, c), hba = __fdividef(-0.5f * b, a);
+    uint32_t mask = 0;
+    float dxlo[2], dxhi[2], exn[2];
+#pragma unroll
+    for (int cx = 0; cx < 2; cx++) {  // d = mean - pixel, pixel x in [8cx, 8cx+7]
+        dxhi[cx] = mx - (float)(8 * cx);
+        dxlo[cx] = dxhi[cx] - 7.0f;
+        exn[cx] = fminf(fmaxf(0.0f, dxlo[cx]), dxhi[cx]);
+    }
+#pragma unroll
+    for (int ry = 0; ry < 4; ry++) {
+        const float dyhi = my - (float)(4 * ry), dylo = dyhi - 3.0f;
+        const float eyn = fminf(fmaxf(0.0f, dylo), dyhi);
+        const float dxs = hba * eyn;  // unclamped minimiser along the horizontal edge
+#pragma unroll
+        for (int cx = 0; cx < 2; cx++) {
+            const float ex = exn[cx];
+            const float dy = fminf(fmaxf(hbc * ex, dylo), dyhi);
+            const float q1v = fmaf(a * ex, ex, fmaf(b, ex, c * dy) * dy);
+            const float dx = fminf(fmaxf(dxs, dxlo[cx]), dxhi[cx]);
+            const float q2v = fmaf(c * eyn, eyn, fmaf(b, eyn, a * dx) * dx);
+            if (fminf(q1v, q2v) <= m) mask |= 1u << (2 * ry + cx);
+        }
+    }
+    return (id << 8) | mask;
+}
+__device__ __forceinline__ uint32_t entry_with_mask(uint32_t id, const float4* __restrict__ rec, float X0, float Y0) {
+    return mask_from_record(id, __ldg(rec + 3 * (size_t)id), __ldg(rec + 3 * (size_t)id + 1), X0, Y0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -215,43 +262,245 @@ __device__ void bitonic_sort_u64(unsigned long long* a, int n) {
     }
 }
 
-// CTA handles its tile iff lo < n <= hi.  IN_SMEM: stage through dynamic shared memory.
-template <int THREADS, bool IN_SMEM>
+// ---- adaptive two-level bucket sort (the common path) ---------------------------------------
+// Depth keys are positive floats, so their bit patterns are monotone in depth and bucket =
+// (bits - min) >> shift is a monotone, purely integer map.  Level 1: 256 coarse buckets over the tile's own
+// [min,max]; level 2: each non-empty coarse bucket is subdivided over ITS OWN [min,max] into ~count
+// sub-buckets (adapts to depth clusters: surfaces).  Entries are scattered to their fine bucket in
+// arrival order and then ranked inside the bucket by the full 64-bit key (depth, id) — exact total
+// order, O(1) expected work per entry.  If any fine bucket holds more than RANK_MAX entries (many
+// equal / nearly equal depths) the tile falls back to the bitonic network above, which is always exact.
+constexpr uint32_t RANK_MAX = 96;
+
+__device__ __forceinline__ uint32_t next_pow2_u32(uint32_t c) { return c <= 1u ? 1u : 1u << (32 - __clz(c - 1u)); }
+
+// In-place exclusive scan of a[0..len) by the whole CTA; returns the total (to every thread).
+template <int THREADS>
+__device__ uint32_t block_exclusive_scan(uint32_t* a, int len, uint32_t* s_part /* [THREADS/32 + 1] */) {
+    constexpr int NW = THREADS / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int per = ((len + NW - 1) / NW + 31) & ~31;  // contiguous region per warp, multiple of 32
+    const int beg = warp * per, end = min(len, beg + per);
+    uint32_t run = 0;
+    for (int i = beg; i < end; i += 32) {
+        const uint32_t c = (i + lane < end) ? a[i + lane] : 0u;
+        uint32_t v = c;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, v, off);
+            if (lane >= off) v += n;
+        }
+        if (i + lane < end) a[i + lane] = run + v - c;
+        run += __shfl_sync(0xffffffffu, v, 31);
+    }
+    if (lane == 0) s_part[warp] = run;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t c = lane < NW ? s_part[lane] : 0u;
+        uint32_t v = c;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, v, off);
+            if (lane >= off) v += n;
+        }
+        if (lane < NW) s_part[lane] = v - c;
+        if (lane == 31) s_part[NW] = v;
+    }
+    __syncthreads();
+    const uint32_t add = s_part[warp];
+    if (add)
+        for (int i = beg + lane; i < end; i += 32) a[i] += add;
+    const uint32_t total = s_part[NW];
+    __syncthreads();
+    return total;
+}
+
+template <int THREADS, int NMAX>
 __global__ void __launch_bounds__(THREADS)
-tile_sort_kernel(const uint32_t* __restrict__ tile_base, unsigned long long* __restrict__ bins,
-                 uint32_t* __restrict__ plist, const uint32_t* __restrict__ info, uint32_t lo, uint32_t hi) {
+tile_bucket_sort_kernel(int T, int gx, int cls, const uint32_t* __restrict__ tile_base,
+                        const unsigned long long* __restrict__ bins, uint32_t* __restrict__ plist,
+                        const uint32_t* __restrict__ info, const uint32_t* __restrict__ class_tiles,
+                        const float4* __restrict__ rec) {
     extern __shared__ unsigned long long s_keys[];
-    if (info[2]) return;                  // arena overflow: forward is re-run by the host
-    if (info[1] <= lo) return;            // no tile is this long
-    const uint32_t b0 = tile_base[blockIdx.x], b1 = tile_base[blockIdx.x + 1];
-    const uint32_t n = b1 - b0;
-    if (n <= lo || n > hi) return;
-    unsigned long long* g = bins + b0;
-    if (IN_SMEM) {
-        for (uint32_t t = threadIdx.x; t < n; t += THREADS) s_keys[t] = g[t];
+    unsigned long long* A = s_keys;                        // [NMAX] keys as loaded
+    unsigned long long* tmp = A + NMAX;                    // [NMAX] keys grouped by fine bucket
+    uint32_t* eb = reinterpret_cast<uint32_t*>(tmp + NMAX);  // [NMAX] fine bucket | arrival rank << 16
+    uint32_t* cnt2 = eb + NMAX;                            // [2*NMAX + 32] fine-bucket counts -> bases
+    uint32_t* cnt1 = cnt2 + 2 * NMAX + 32;                 // [256]
+    uint32_t* min1 = cnt1 + 256;
+    uint32_t* max1 = min1 + 256;
+    uint32_t* sh2 = max1 + 256;
+    uint32_t* off2 = sh2 + 256;                            // [257]
+    uint16_t* eb2 = reinterpret_cast<uint16_t*>(off2 + 260);  // [NMAX] fine bucket of tmp[p]
+    __shared__ uint32_t s_part[THREADS / 32 + 1];
+    __shared__ uint32_t s_min[THREADS / 32], s_max[THREADS / 32];
+    if (info[2]) return;
+    const uint32_t ntiles = info[4 + cls];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
+        const uint32_t tile = class_tiles[(size_t)cls * T + ti];
+        const uint32_t b0 = tile_base[tile];
+        const int n = (int)(tile_base[tile + 1] - b0);
+        // phase 0: load, depth range
+        uint32_t lmin = 0xffffffffu, lmax = 0u;
+        for (int i = threadIdx.x; i < n; i += THREADS) {
+            const unsigned long long k = bins[b0 + i];
+            A[i] = k;
+            const uint32_t d = (uint32_t)(k >> 32);
+            lmin = min(lmin, d); lmax = max(lmax, d);
+        }
+        if (threadIdx.x < 256) { cnt1[threadIdx.x] = 0u; min1[threadIdx.x] = 0xffffffffu; max1[threadIdx.x] = 0u; }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, off));
+            lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, off));
+        }
+        if (lane == 0) { s_min[warp] = lmin; s_max[warp] = lmax; }
         __syncthreads();
-        bitonic_sort_u64<THREADS>(s_keys, (int)n);
-        for (uint32_t t = threadIdx.x; t < n; t += THREADS) plist[b0 + t] = (uint32_t)s_keys[t];
-    } else {
+        uint32_t kmin = 0xffffffffu, kmax = 0u;
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; w++) { kmin = min(kmin, s_min[w]); kmax = max(kmax, s_max[w]); }
+        const uint32_t range = kmax - kmin;
+        const uint32_t sh1 = range < 256u ? 0u : (uint32_t)(32 - __clz(range)) - 8u;
+        // phase 1: coarse histogram + per-coarse-bucket range
+        for (int i = threadIdx.x; i < n; i += THREADS) {
+            const uint32_t d = (uint32_t)(A[i] >> 32);
+            const uint32_t b1 = (d - kmin) >> sh1;
+            atomicAdd(cnt1 + b1, 1u);
+            atomicMin(min1 + b1, d);
+            atomicMax(max1 + b1, d);
+        }
         __syncthreads();
-        bitonic_sort_u64<THREADS>(g, (int)n);  // in place in global/L2 (rare: > 16384 entries in one tile)
-        for (uint32_t t = threadIdx.x; t < n; t += THREADS) plist[b0 + t] = (uint32_t)g[t];
+        // phase 2: sub-bucket layout (threads 0..255 = coarse buckets), scan of sub-bucket counts
+        if (threadIdx.x < 256) {
+            const uint32_t c = cnt1[threadIdx.x];
+            uint32_t nsub = 0u, sh = 0u;
+            if (c) {
+                const uint32_t r = max1[threadIdx.x] - min1[threadIdx.x];
+                const uint32_t lg = 31u - (uint32_t)__clz(next_pow2_u32(c));
+                const uint32_t bits = r ? (uint32_t)(32 - __clz(r)) : 0u;
+                sh = bits > lg ? bits - lg : 0u;
+                nsub = (r >> sh) + 1u;
+            }
+            sh2[threadIdx.x] = sh;
+            off2[threadIdx.x] = nsub;
+        }
+        __syncthreads();
+        const int NS = (int)block_exclusive_scan<THREADS>(off2, 256, s_part);  // off2[b1] = first fine bucket
+        for (int i = threadIdx.x; i <= NS; i += THREADS) cnt2[i] = 0u;
+        __syncthreads();
+        // phase 3: fine histogram; remember (fine bucket, arrival rank)
+        for (int i = threadIdx.x; i < n; i += THREADS) {
+            const uint32_t d = (uint32_t)(A[i] >> 32);
+            const uint32_t b1 = (d - kmin) >> sh1;
+            const uint32_t b2 = off2[b1] + ((d - min1[b1]) >> sh2[b1]);
+            const uint32_t r = atomicAdd(cnt2 + b2, 1u);
+            eb[i] = b2 | (r << 16);
+        }
+        __syncthreads();
+        // phase 4: largest fine bucket (fallback decision) + exclusive scan -> fine bucket bases
+        uint32_t mx = 0u;
+        for (int i = threadIdx.x; i < NS; i += THREADS) mx = max(mx, cnt2[i]);
+        const bool crowded = __syncthreads_or(mx > RANK_MAX);
+        if (crowded) {
+            bitonic_sort_u64<THREADS>(A, n);
+            for (int i = threadIdx.x; i < n; i += THREADS) plist[b0 + i] = (uint32_t)A[i] << 8;
+            __syncthreads();
+            continue;
+        }
+        block_exclusive_scan<THREADS>(cnt2, NS + 1, s_part);  // cnt2[NS] = n afterwards
+        // phase 5: group by fine bucket
+        for (int i = threadIdx.x; i < n; i += THREADS) {
+            const uint32_t e = eb[i];
+            const uint32_t b2 = e & 0xffffu;
+            const uint32_t pos = cnt2[b2] + (e >> 16);
+            tmp[pos] = A[i];
+            eb2[pos] = (uint16_t)b2;
+        }
+        __syncthreads();
+        // phase 6: rank inside the fine bucket by the full key, write the sorted list (id<<8; the sub-tile mask
+        // is OR-ed in by tile_mask_kernel, which runs at full occupancy)
+        for (int p = threadIdx.x; p < n; p += THREADS) {
+            const unsigned long long k = tmp[p];
+            const uint32_t b2 = eb2[p];
+            const uint32_t s0 = cnt2[b2], s1 = cnt2[b2 + 1];
+            uint32_t rank = 0;
+            for (uint32_t q = s0; q < s1; q++) rank += tmp[q] < k ? 1u : 0u;
+            plist[b0 + s0 + rank] = (uint32_t)k << 8;
+        }
+        __syncthreads();
     }
 }
 
-cudaError_t launch_tile_sort(int T, const uint32_t* tile_base, unsigned long long* bins, uint32_t* plist,
-                             const uint32_t* info, cudaStream_t st) {
+// bitonic classes (long lists): shared memory up to 16384 entries, else in place in global/L2
+template <int THREADS, bool IN_SMEM>
+__global__ void __launch_bounds__(THREADS)
+tile_bitonic_sort_kernel(int T, int gx, int cls, const uint32_t* __restrict__ tile_base,
+                         unsigned long long* __restrict__ bins, uint32_t* __restrict__ plist,
+                         const uint32_t* __restrict__ info, const uint32_t* __restrict__ class_tiles,
+                         const float4* __restrict__ rec) {
+    extern __shared__ unsigned long long s_keys[];
+    if (info[2]) return;
+    const uint32_t ntiles = info[4 + cls];
+    for (uint32_t ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
+        const uint32_t tile = class_tiles[(size_t)cls * T + ti];
+        const uint32_t b0 = tile_base[tile];
+        const uint32_t n = tile_base[tile + 1] - b0;
+        unsigned long long* g = bins + b0;
+        if (IN_SMEM) {
+            for (uint32_t t = threadIdx.x; t < n; t += THREADS) s_keys[t] = g[t];
+            __syncthreads();
+            bitonic_sort_u64<THREADS>(s_keys, (int)n);
+            for (uint32_t t = threadIdx.x; t < n; t += THREADS) plist[b0 + t] = (uint32_t)s_keys[t] << 8;
+        } else {
+            __syncthreads();
+            bitonic_sort_u64<THREADS>(g, (int)n);  // rare: > 16384 entries in one tile
+            for (uint32_t t = threadIdx.x; t < n; t += THREADS) plist[b0 + t] = (uint32_t)g[t] << 8;
+        }
+        __syncthreads();
+    }
+}
+
+// One CTA per tile, one thread per sorted entry: OR the sub-tile mask into plist (id<<8 -> id<<8 | mask).
+constexpr int MASK_THREADS = 256;
+__global__ void __launch_bounds__(MASK_THREADS)
+tile_mask_kernel(int gx, const uint32_t* __restrict__ tile_base, uint32_t* __restrict__ plist,
+                 const uint32_t* __restrict__ info, const float4* __restrict__ rec) {
+    if (info[2]) return;
+    const uint32_t b0 = tile_base[blockIdx.x], b1 = tile_base[blockIdx.x + 1];
+    const float X0 = (float)((blockIdx.x % gx) * TILE), Y0 = (float)((blockIdx.x / gx) * TILE);
+    for (uint32_t i = b0 + threadIdx.x; i < b1; i += MASK_THREADS)
+        plist[i] = entry_with_mask(plist[i] >> 8, rec, X0, Y0);
+}
+
+template <int NMAX>
+constexpr size_t bucket_smem_bytes() {
+    return (size_t)NMAX * 8 * 2 + (size_t)NMAX * 4 + (size_t)(2 * NMAX + 32) * 4 + 256 * 4 * 4 + 260 * 4 + (size_t)NMAX * 2;
+}
+
+cudaError_t launch_tile_sort(int T, int gx, const uint32_t* tile_base, unsigned long long* bins, uint32_t* plist,
+                             const uint32_t* info, const uint32_t* class_tiles, const float4* rec, cudaStream_t st) {
     if (T <= 0) return cudaSuccess;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(tile_sort_kernel<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
-        cudaFuncSetAttribute(tile_sort_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
+        cudaFuncSetAttribute(tile_bucket_sort_kernel<256, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)bucket_smem_bytes<1024>());
+        cudaFuncSetAttribute(tile_bucket_sort_kernel<512, 2048>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)bucket_smem_bytes<2048>());
+        cudaFuncSetAttribute(tile_bucket_sort_kernel<1024, 4096>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)bucket_smem_bytes<4096>());
+        cudaFuncSetAttribute(tile_bitonic_sort_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             16384 * 8);
         attr_done = true;
     }
-    tile_sort_kernel<256, true><<<T, 256, 1024 * 8, st>>>(tile_base, bins, plist, info, 0u, 1024u);
-    tile_sort_kernel<512, true><<<T, 512, 4096 * 8, st>>>(tile_base, bins, plist, info, 1024u, 4096u);
-    tile_sort_kernel<1024, true><<<T, 1024, 16384 * 8, st>>>(tile_base, bins, plist, info, 4096u, 16384u);
-    tile_sort_kernel<1024, false><<<T, 1024, 0, st>>>(tile_base, bins, plist, info, 16384u, 0xffffffffu);
+    const int g_small = min(T, 148 * 6), g_mid = min(T, 148 * 3), g_big = min(T, 148);
+    tile_bucket_sort_kernel<256, 1024><<<g_small, 256, bucket_smem_bytes<1024>(), st>>>(T, gx, 0, tile_base, bins, plist, info, class_tiles, rec);
+    tile_bucket_sort_kernel<512, 2048><<<g_mid, 512, bucket_smem_bytes<2048>(), st>>>(T, gx, 1, tile_base, bins, plist, info, class_tiles, rec);
+    tile_bucket_sort_kernel<1024, 4096><<<g_big, 1024, bucket_smem_bytes<4096>(), st>>>(T, gx, 2, tile_base, bins, plist, info, class_tiles, rec);
+    tile_bitonic_sort_kernel<1024, true><<<g_big, 1024, 16384 * 8, st>>>(T, gx, 3, tile_base, bins, plist, info,
+                                                                         class_tiles, rec);
+    tile_bitonic_sort_kernel<1024, false><<<g_big, 1024, 0, st>>>(T, gx, 4, tile_base, bins, plist, info, class_tiles, rec);
+    tile_mask_kernel<<<T, MASK_THREADS, 0, st>>>(gx, tile_base, plist, info, rec);
     return cudaGetLastError();
 }
 

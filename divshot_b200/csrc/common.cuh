@@ -6,7 +6,7 @@
 //           q1 = { C2, lo, r, g }                        C2 = -0.5*log2(e)*conicC, lo = log2(opacity)
 //           q2 = { b, depth, radius (int bits), tiles_touched | clamped<<24 (uint bits) }
 //         so that alpha = ex2(A2*dx^2 + B2*dx*dy + C2*dy^2 + lo)  (one MUFU, no multiply by opacity)
-//   aux   [N] x 16 B  { minx|miny<<16, maxx|maxy<<16, ex, ey }   tile rect + opacity-aware half extents
+//   aux   [N] x 16 B  { minx|miny<<16, maxx|maxy<<16|clamped<<29, depth bits, 0 }
 //   bins  [Dcap] x 8 B  unsorted per-tile entries  depth_bits<<32 | id<<8 | submask
 //   plist [Dcap] x 4 B  sorted entries id<<8 | submask (tile-major; the parity point_list is id)
 //   tile_count / tile_base / tile_cursor [T]
@@ -25,6 +25,9 @@ constexpr float LN2 = 0.6931471805599453f;
 constexpr float ALPHA_MIN_LOG2 = -7.994353436858858f;  // log2(1/255)
 constexpr int ID_BITS = 24;
 constexpr uint32_t MAX_GAUSSIANS = 1u << ID_BITS;
+// per-tile atomic counters live 32 B apart: 7.6 M atomics onto 25 KB of packed counters serialise on a few
+// L2 lines; one counter per sector spreads them over the L2 slices
+constexpr int TILE_CTR_STRIDE = 8;
 
 struct Cam {
     float view[16];
@@ -85,6 +88,32 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// explicit shared-window accessors (32-bit shared addresses; keeps address arithmetic to one IMAD)
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float lds_f1(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u1(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f4(uint32_t a, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts_f1(uint32_t a, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sts_u1(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
 // mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP) ------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -112,6 +141,14 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// shared -> global bulk store (TMA engine), bulk-group completion
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }

@@ -12,17 +12,18 @@ cudaError_t launch_preprocess_fwd(const Cam& cam, int N, const Params& prm, floa
                                   uint32_t* tile_count, int32_t* out_radii, unsigned long long* stats,
                                   cudaStream_t st);
 
-// A2/A5: exclusive scan of tile counts -> tile_base[T+1], cursor[T]; info[0]=D, info[1]=max len, info[2]=overflow
+// A2/A5: exclusive scan of tile counts -> tile_base[T+1], cursor[T]; info[0]=D, info[1]=max len, info[2]=overflow,
+// info[4..8] = tiles per sort class, class_tiles[5][T] = their ids
 cudaError_t launch_tile_scan(int T, const uint32_t* tile_count, uint32_t* tile_base, uint32_t* tile_cursor,
-                             uint32_t* info, uint32_t dup_capacity, cudaStream_t st);
+                             uint32_t* info, uint32_t dup_capacity, uint32_t* class_tiles, cudaStream_t st);
 
 // A3: emit (depth | id | sub-tile mask) entries into per-tile bins
-cudaError_t launch_emit(const Cam& cam, int N, const float4* rec, const uint4* aux, uint32_t* tile_cursor,
-                        unsigned long long* bins, uint32_t dup_capacity, cudaStream_t st);
+cudaError_t launch_emit(const Cam& cam, int N, const uint4* aux, uint32_t* tile_cursor, unsigned long long* bins,
+                        uint32_t dup_capacity, cudaStream_t st);
 
 // A4: tile-local sort (CUB-free) -> plist (id<<8 | mask), tile-major
-cudaError_t launch_tile_sort(int T, const uint32_t* tile_base, unsigned long long* bins, uint32_t* plist,
-                             const uint32_t* info, cudaStream_t st);
+cudaError_t launch_tile_sort(int T, int gx, const uint32_t* tile_base, unsigned long long* bins, uint32_t* plist,
+                             const uint32_t* info, const uint32_t* class_tiles, const float4* rec, cudaStream_t st);
 
 // A6
 cudaError_t launch_render_fwd(const Cam& cam, const uint32_t* tile_base, const uint32_t* plist, const float4* rec,
@@ -35,7 +36,7 @@ cudaError_t launch_render_bwd(const Cam& cam, const uint32_t* tile_base, const u
                               bool absgrad, const uint32_t* info, cudaStream_t st);
 
 // A8
-cudaError_t launch_preprocess_bwd(const Cam& cam, int N, const Params& prm, const float4* rec, float4* sgrad,
+cudaError_t launch_preprocess_bwd(const Cam& cam, int N, const Params& prm, const uint4* aux, float4* sgrad,
                                   const Grads& g, uint32_t flags, cudaStream_t st);
 
 // debug helpers (parity tests): unpack records into the upstream-style arrays

@@ -17,39 +17,92 @@
 namespace dvs {
 
 constexpr int PB_THREADS = 128;
+constexpr int PB_WARPS = PB_THREADS / 32;
+
+// Per-warp staging layout (bytes).  Inputs (parameters, aux words, screen-gradient records) arrive through
+// 1-D bulk copies on the warp's mbarrier; the dense gradients are written in place over the consumed
+// inputs and leave through bulk shared->global stores, as does the re-zeroed screen-gradient block.
+struct PbLayout {
+    int means, scales, quats, opac, sh0, shN, sgrad, aux, total;
+    __host__ __device__ explicit PbLayout(int row_floats) {
+        int o = 0;
+        means = o; o += 32 * 12;
+        scales = o; o += 32 * 12;
+        quats = o; o += 32 * 16;
+        opac = o; o += 32 * 4;
+        sh0 = o; o += 32 * 12;
+        shN = o; o += 32 * row_floats * 4;
+        sgrad = o; o += 32 * 48;
+        aux = o; o += 32 * 16;
+        total = (o + 127) & ~127;
+    }
+};
 
 template <int DEG>
 __global__ void __launch_bounds__(PB_THREADS)
-preprocess_bwd_kernel(Cam cam, int N, Params prm, const float4* __restrict__ rec, float4* __restrict__ sgrad,
+preprocess_bwd_kernel(Cam cam, int N, Params prm, const uint4* __restrict__ aux, float4* __restrict__ sgrad,
                       Grads g, uint32_t flags) {
     constexpr int K = (DEG + 1) * (DEG + 1);
-    extern __shared__ float sh_stage[];
+    extern __shared__ __align__(128) unsigned char pb_smem[];
     const int KR = cam.KR;
     const int row = 3 * KR;
+    const PbLayout L(row);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i = blockIdx.x * PB_THREADS + threadIdx.x;
     const int warp_first = blockIdx.x * PB_THREADS + warp * 32;
     const bool accumulate = flags & DVS_FLAG_ACCUMULATE;
-    float* mysh = sh_stage + (size_t)warp * 32 * row;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(pb_smem) + warp;
+    unsigned char* base = pb_smem + 64 + (size_t)warp * L.total;
+    float* s_means = reinterpret_cast<float*>(base + L.means);
+    float* s_scales = reinterpret_cast<float*>(base + L.scales);
+    float4* s_quats = reinterpret_cast<float4*>(base + L.quats);
+    float* s_opac = reinterpret_cast<float*>(base + L.opac);
+    float* s_sh0 = reinterpret_cast<float*>(base + L.sh0);
+    float* mysh = reinterpret_cast<float*>(base + L.shN);
+    float4* s_sg = reinterpret_cast<float4*>(base + L.sgrad);
+    uint4* s_aux = reinterpret_cast<uint4*>(base + L.aux);
     if (warp_first >= N) return;
     const int nrows = min(32, N - warp_first);
     const int nflt = nrows * row;
+    const bool full = nrows == 32;
 
-    // visibility of my Gaussian (radius > 0) and warp vote: a warp of invisible Gaussians only writes zeros
-    float4 q2 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i < N) q2 = __ldg(rec + 3 * (size_t)i + 2);
-    const bool vis = i < N && __float_as_int(q2.z) > 0;
-    const bool any_vis = __any_sync(0xffffffffu, vis);
-
-    if (K > 1 && any_vis) {  // stage shN rows (coalesced)
-        const float* src = prm.shN + (size_t)warp_first * row;
-        const int nvec = nflt >> 2;
-        const float4* src4 = reinterpret_cast<const float4*>(src);
-        float4* dst4 = reinterpret_cast<float4*>(mysh);
-        for (int v = lane; v < nvec; v += 32) dst4[v] = ldg_nc_f4(src4 + v);
-        for (int t = (nvec << 2) + lane; t < nflt; t += 32) mysh[t] = __ldg(src + t);
+    if (full) {
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            fence_mbar_init();
+            const uint32_t bytes = 32u * (12u + 12u + 16u + 4u + 48u + 16u) + (K > 1 ? 32u * (uint32_t)row * 4u : 0u);
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(s_aux, aux + warp_first, 32 * 16, bar);
+            bulk_g2s(s_sg, sgrad + 3 * (size_t)warp_first, 32 * 48, bar);
+            bulk_g2s(s_means, prm.means3D + 3 * (size_t)warp_first, 32 * 12, bar);
+            bulk_g2s(s_scales, prm.scales + 3 * (size_t)warp_first, 32 * 12, bar);
+            bulk_g2s(s_quats, prm.quats + 4 * (size_t)warp_first, 32 * 16, bar);
+            bulk_g2s(s_opac, prm.opacities + warp_first, 32 * 4, bar);
+            if (K > 1) bulk_g2s(mysh, prm.shN + (size_t)warp_first * row, 32u * (uint32_t)row * 4u, bar);
+        }
+        __syncwarp();
+        mbar_wait(bar, 0);
+    } else {
+        for (int t = lane; t < nrows * 3; t += 32) {
+            s_means[t] = __ldg(prm.means3D + 3 * (size_t)warp_first + t);
+            s_scales[t] = __ldg(prm.scales + 3 * (size_t)warp_first + t);
+        }
+        for (int t = lane; t < nrows * 3; t += 32) s_sg[t] = sgrad[3 * (size_t)warp_first + t];
+        if (lane < nrows) {
+            s_quats[lane] = __ldg(reinterpret_cast<const float4*>(prm.quats) + warp_first + lane);
+            s_opac[lane] = __ldg(prm.opacities + warp_first + lane);
+            s_aux[lane] = __ldg(aux + warp_first + lane);
+        }
+        if (K > 1)
+            for (int t = lane; t < nflt; t += 32) mysh[t] = __ldg(prm.shN + (size_t)warp_first * row + t);
+        __syncwarp();
     }
-    __syncwarp();
+
+    // visibility (tile rect area > 0) and SH clamp mask come from the aux word
+    uint4 ax = make_uint4(0u, 0u, 0u, 0u);
+    if (i < N) ax = s_aux[lane];
+    const bool vis = ((ax.y & 0xffffu) > (ax.x & 0xffffu)) && (((ax.y >> 16) & 0x1fffu) > (ax.x >> 16));
+    const bool any_vis = __any_sync(0xffffffffu, vis);
 
     float dmean0 = 0.f, dmean1 = 0.f, dmean2 = 0.f;
     float dsc0 = 0.f, dsc1 = 0.f, dsc2 = 0.f;
@@ -59,17 +112,18 @@ preprocess_bwd_kernel(Cam cam, int N, Params prm, const float4* __restrict__ rec
     float gm2x = 0.f, gm2y = 0.f, gabx = 0.f, gaby = 0.f;
     float* myrow = mysh + lane * row;
 
-    if (vis) {
-        const float4 sg0 = sgrad[3 * (size_t)i], sg1 = sgrad[3 * (size_t)i + 1], sg2 = sgrad[3 * (size_t)i + 2];
+    // consume my screen-gradient record, leave zeros behind (the whole block is stored back below)
+    const float4 sg0 = s_sg[3 * lane], sg1 = s_sg[3 * lane + 1], sg2 = s_sg[3 * lane + 2];
+    {
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        sgrad[3 * (size_t)i] = z4; sgrad[3 * (size_t)i + 1] = z4; sgrad[3 * (size_t)i + 2] = z4;
-        const uint32_t clamped = __float_as_uint(q2.w) >> 24;
-        const float px = __ldg(prm.means3D + 3 * (size_t)i), py = __ldg(prm.means3D + 3 * (size_t)i + 1),
-                    pz = __ldg(prm.means3D + 3 * (size_t)i + 2);
-        const float a0 = __ldg(prm.scales + 3 * (size_t)i), a1 = __ldg(prm.scales + 3 * (size_t)i + 1),
-                    a2 = __ldg(prm.scales + 3 * (size_t)i + 2);
-        const float4 qq = __ldg(reinterpret_cast<const float4*>(prm.quats) + i);
-        const float oo = __ldg(prm.opacities + i);
+        s_sg[3 * lane] = z4; s_sg[3 * lane + 1] = z4; s_sg[3 * lane + 2] = z4;
+    }
+    if (vis) {
+        const uint32_t clamped = ax.y >> 29;
+        const float px = s_means[3 * lane], py = s_means[3 * lane + 1], pz = s_means[3 * lane + 2];
+        const float a0 = s_scales[3 * lane], a1 = s_scales[3 * lane + 1], a2 = s_scales[3 * lane + 2];
+        const float4 qq = s_quats[lane];
+        const float oo = s_opac[lane];
         const bool activated = cam.flags & DVS_FLAG_INPUT_ACTIVATED;
         float s0, s1, s2, qr, qx, qy, qz, o, qlen = 1.0f;
         if (activated) {
@@ -82,14 +136,12 @@ preprocess_bwd_kernel(Cam cam, int N, Params prm, const float4* __restrict__ rec
             qr = qq.x * inv; qx = qq.y * inv; qy = qq.z * inv; qz = qq.w * inv;
             o = 1.0f / (1.0f + expf(-oo));
         }
-        // screen-space gradients with the per-splat factors applied (render_bwd.cu accumulates moments)
-        const float gmx = (LN2 * 0.5f * (float)cam.W) * sg0.x;  // dL/dmean2D.x, ndc-scaled
-        const float gmy = (LN2 * 0.5f * (float)cam.H) * sg0.y;
+        // screen-space sums left by render_bwd.cu (moments of s = dL/dpower over the splat's pixels):
+        //   sg0 = {Sx, Sy, Sxx, Sxy}, sg1 = {Syy, S0, sum w*dL/dpix r, g}, sg2 = {b, sum|gx|, sum|gy|, -}
         const float dA = -0.5f * sg0.z, dBh = -0.5f * sg0.w, dC = -0.5f * sg1.x;  // dBh = half the off-diagonal
         const float dL_dopacity = sg1.y / o;
         const float dcol_in[3] = {sg1.z, sg1.w, sg2.x};
-        gm2x = gmx; gm2y = gmy;
-        gabx = (LN2 * 0.5f * (float)cam.W) * sg2.y; gaby = (LN2 * 0.5f * (float)cam.H) * sg2.z;
+        gabx = 0.5f * (float)cam.W * sg2.y; gaby = 0.5f * (float)cam.H * sg2.z;
 
         const float* V = cam.view;
         const float* Pm = cam.proj;
@@ -134,6 +186,11 @@ preprocess_bwd_kernel(Cam cam, int N, Params prm, const float4* __restrict__ rec
         const float cc = TS[1][0] * Tm[1][0] + TS[1][1] * Tm[1][1] + TS[1][2] * Tm[1][2] + 0.3f;
         // 1. conic -> cov2D
         const float det = ca * cc - cb * cb;
+        // dL/dmean2D (ndc-scaled): dpower/ddx = -(A dx + B dy) with the conic (A,B,C) = (cc,-cb,ca)/det
+        const float det_inv = 1.0f / det;
+        const float gmx = -0.5f * (float)cam.W * det_inv * (cc * sg0.x - cb * sg0.y);
+        const float gmy = -0.5f * (float)cam.H * det_inv * (ca * sg0.y - cb * sg0.x);
+        gm2x = gmx; gm2y = gmy;
         const float kappa = 1.0f / (det * det + 1e-7f);
         const float da = kappa * (-cc * cc * dA + 2.0f * cb * cc * dBh + (det - ca * cc) * dC);
         const float dc = kappa * (-ca * ca * dC + 2.0f * ca * cb * dBh + (det - ca * cc) * dA);
@@ -281,6 +338,38 @@ preprocess_bwd_kernel(Cam cam, int N, Params prm, const float4* __restrict__ rec
         for (int t = 0; t < row; t++) myrow[t] = 0.f;
 
     // ---- write dense gradients ----
+    if (full && !accumulate) {
+        // in place over the consumed inputs, then out through the TMA engine
+        __syncwarp();
+        s_means[3 * lane] = dmean0; s_means[3 * lane + 1] = dmean1; s_means[3 * lane + 2] = dmean2;
+        s_scales[3 * lane] = dsc0; s_scales[3 * lane + 1] = dsc1; s_scales[3 * lane + 2] = dsc2;
+        s_quats[lane] = make_float4(dq0, dq1, dq2, dq3);
+        s_opac[lane] = dop;
+        s_sh0[3 * lane] = dsh0[0]; s_sh0[3 * lane + 1] = dsh0[1]; s_sh0[3 * lane + 2] = dsh0[2];
+        if (row > 0 && !any_vis)
+            for (int t = 0; t < row; t++) myrow[t] = 0.f;
+        if (g.mean2D) reinterpret_cast<float2*>(g.mean2D)[i] = make_float2(gm2x, gm2y);
+        if (g.mean2D_abs) reinterpret_cast<float2*>(g.mean2D_abs)[i] = make_float2(gabx, gaby);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            bulk_s2g(g.means3D + 3 * (size_t)warp_first, s_means, 32 * 12);
+            bulk_s2g(g.scales + 3 * (size_t)warp_first, s_scales, 32 * 12);
+            bulk_s2g(g.quats + 4 * (size_t)warp_first, s_quats, 32 * 16);
+            bulk_s2g(g.opacities + warp_first, s_opac, 32 * 4);
+            bulk_s2g(g.sh0 + 3 * (size_t)warp_first, s_sh0, 32 * 12);
+            if (row > 0) bulk_s2g(g.shN + (size_t)warp_first * row, mysh, 32u * (uint32_t)row * 4u);
+            if (any_vis) bulk_s2g(sgrad + 3 * (size_t)warp_first, s_sg, 32 * 48);
+            bulk_commit();
+            bulk_wait_read0();
+        }
+        return;
+    }
+    // generic path: tail warp, or DVS_FLAG_ACCUMULATE (read-modify-write)
+    if (vis) {
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        sgrad[3 * (size_t)i] = z4; sgrad[3 * (size_t)i + 1] = z4; sgrad[3 * (size_t)i + 2] = z4;
+    }
     if (i < N) {
         float* gm = g.means3D + 3 * (size_t)i;
         float* gs = g.scales + 3 * (size_t)i;
@@ -306,7 +395,7 @@ preprocess_bwd_kernel(Cam cam, int N, Params prm, const float4* __restrict__ rec
             if (g.mean2D_abs) { g.mean2D_abs[2 * (size_t)i] = gabx; g.mean2D_abs[2 * (size_t)i + 1] = gaby; }
         }
     }
-    // SH rest gradients: coalesced 128-bit stores of the staged rows
+    // SH rest gradients: coalesced stores of the staged rows
     if (row > 0) {
         __syncwarp();
         float* dst = g.shN + (size_t)warp_first * row;
@@ -332,17 +421,17 @@ preprocess_bwd_kernel(Cam cam, int N, Params prm, const float4* __restrict__ rec
     }
 }
 
-cudaError_t launch_preprocess_bwd(const Cam& cam, int N, const Params& prm, const float4* rec, float4* sgrad,
+cudaError_t launch_preprocess_bwd(const Cam& cam, int N, const Params& prm, const uint4* aux, float4* sgrad,
                                   const Grads& g, uint32_t flags, cudaStream_t st) {
     if (N <= 0) return cudaSuccess;
     const int grid = (N + PB_THREADS - 1) / PB_THREADS;
-    const size_t smem = (size_t)(PB_THREADS / 32) * 32 * 3 * cam.KR * sizeof(float);
+    const size_t smem = 64 + (size_t)PB_WARPS * PbLayout(3 * cam.KR).total;
 #define DVS_LAUNCH_PB(D)                                                                                 \
     do {                                                                                                 \
         if (smem > 48 * 1024)                                                                            \
             cudaFuncSetAttribute(preprocess_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                  (int)smem);                                                             \
-        preprocess_bwd_kernel<D><<<grid, PB_THREADS, smem, st>>>(cam, N, prm, rec, sgrad, g, flags);     \
+        preprocess_bwd_kernel<D><<<grid, PB_THREADS, smem, st>>>(cam, N, prm, aux, sgrad, g, flags);     \
     } while (0)
     switch (cam.deg) {
         case 0: DVS_LAUNCH_PB(0); break;

@@ -61,6 +61,28 @@ __device__ __forceinline__ void sh_basis_dev(int deg, float x, float y, float z,
 }
 
 constexpr int PF_THREADS = 128;
+constexpr int PF_WARPS = PF_THREADS / 32;
+
+// Per-warp staging layout (bytes).  Inputs arrive by ONE elected lane issuing six 1-D bulk copies
+// (cp.async.bulk, TMA engine) that complete on the warp's mbarrier; the 48-byte screen records, the
+// 16-byte aux words and the radii leave the same way (bulk shared->global stores).
+struct PfLayout {
+    int means, scales, quats, opac, sh0, shN, rec, aux, radii, total;
+    __host__ __device__ explicit PfLayout(int row_floats) {
+        int o = 0;
+        means = o; o += 32 * 12;
+        scales = o; o += 32 * 12;
+        quats = o; o += 32 * 16;
+        opac = o; o += 32 * 4;
+        sh0 = o; o += 32 * 12;
+        // the outgoing records / aux words / radii reuse the SH rows once those have been consumed
+        shN = o;
+        rec = o; aux = rec + 32 * 48; radii = aux + 32 * 16;
+        const int out_bytes = 32 * (48 + 16 + 4), sh_bytes = 32 * row_floats * 4;
+        o += sh_bytes > out_bytes ? sh_bytes : out_bytes;
+        total = (o + 127) & ~127;
+    }
+};
 
 template <int DEG>
 __global__ void __launch_bounds__(PF_THREADS)
@@ -68,35 +90,66 @@ preprocess_fwd_kernel(Cam cam, int N, Params prm, float4* __restrict__ rec, uint
                       uint32_t* __restrict__ tile_count, int32_t* __restrict__ out_radii,
                       unsigned long long* __restrict__ stats /* [0]=V, [1]=D */) {
     constexpr int K = (DEG + 1) * (DEG + 1);
-    extern __shared__ float sh_stage[];  // [warps][32 * 3 * KR] floats
+    extern __shared__ __align__(128) unsigned char pf_smem[];
     const int KR = cam.KR;
     const int row = 3 * KR;  // floats of shN per Gaussian
+    const PfLayout L(row);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i = blockIdx.x * PF_THREADS + threadIdx.x;
     const int warp_first = blockIdx.x * PF_THREADS + warp * 32;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(pf_smem) + warp;
+    unsigned char* base = pf_smem + 64 + (size_t)warp * L.total;
+    float* s_means = reinterpret_cast<float*>(base + L.means);
+    float* s_scales = reinterpret_cast<float*>(base + L.scales);
+    float4* s_quats = reinterpret_cast<float4*>(base + L.quats);
+    float* s_opac = reinterpret_cast<float*>(base + L.opac);
+    float* s_sh0 = reinterpret_cast<float*>(base + L.sh0);
+    float* mysh = reinterpret_cast<float*>(base + L.shN);
+    float4* s_rec = reinterpret_cast<float4*>(base + L.rec);
+    uint4* s_aux = reinterpret_cast<uint4*>(base + L.aux);
+    int32_t* s_radii = reinterpret_cast<int32_t*>(base + L.radii);
+    if (warp_first >= N) return;
+    const int nrows = min(32, N - warp_first);
+    const bool full = nrows == 32;  // full warps use the bulk-copy path, the single tail warp plain loads
 
-    // ---- stage this warp's shN rows: 32*row contiguous floats, 128-bit coalesced ----
-    float* mysh = sh_stage + (size_t)warp * 32 * row;
-    if (K > 1 && warp_first < N) {
-        const int nrows = min(32, N - warp_first);
-        const int nflt = nrows * row;
-        const float* src = prm.shN + (size_t)warp_first * row;
-        const int nvec = nflt >> 2;
-        const float4* src4 = reinterpret_cast<const float4*>(src);
-        float4* dst4 = reinterpret_cast<float4*>(mysh);
-        for (int v = lane; v < nvec; v += 32) dst4[v] = ldg_nc_f4(src4 + v);
-        for (int t = (nvec << 2) + lane; t < nflt; t += 32) mysh[t] = __ldg(src + t);
+    if (full) {
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            fence_mbar_init();
+            const uint32_t bytes = 32u * (12u + 12u + 16u + 4u + 12u) + (K > 1 ? 32u * (uint32_t)row * 4u : 0u);
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(s_means, prm.means3D + 3 * (size_t)warp_first, 32 * 12, bar);
+            bulk_g2s(s_scales, prm.scales + 3 * (size_t)warp_first, 32 * 12, bar);
+            bulk_g2s(s_quats, prm.quats + 4 * (size_t)warp_first, 32 * 16, bar);
+            bulk_g2s(s_opac, prm.opacities + warp_first, 32 * 4, bar);
+            bulk_g2s(s_sh0, prm.sh0 + 3 * (size_t)warp_first, 32 * 12, bar);
+            if (K > 1) bulk_g2s(mysh, prm.shN + (size_t)warp_first * row, 32u * (uint32_t)row * 4u, bar);
+        }
+        __syncwarp();
+        mbar_wait(bar, 0);
+    } else {
+        for (int t = lane; t < nrows * 3; t += 32) {
+            s_means[t] = __ldg(prm.means3D + 3 * (size_t)warp_first + t);
+            s_scales[t] = __ldg(prm.scales + 3 * (size_t)warp_first + t);
+            s_sh0[t] = __ldg(prm.sh0 + 3 * (size_t)warp_first + t);
+        }
+        if (lane < nrows) {
+            s_quats[lane] = __ldg(reinterpret_cast<const float4*>(prm.quats) + warp_first + lane);
+            s_opac[lane] = __ldg(prm.opacities + warp_first + lane);
+        }
+        if (K > 1)
+            for (int t = lane; t < nrows * row; t += 32) mysh[t] = __ldg(prm.shN + (size_t)warp_first * row + t);
+        __syncwarp();
     }
-    __syncwarp();
 
     bool visible = false;
     uint32_t tiles = 0;
+    int minx = 0, miny = 0, maxx = 0, maxy = 0;
+    float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0, q2 = q0;
+    uint4 ax = make_uint4(0u, 0u, 0u, 0u);
+    int rad = 0;
     if (i < N) {
-        float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0, q2 = q0;
-        uint4 ax = make_uint4(0u, 0u, 0u, 0u);
-        int rad = 0;
-        const float px = __ldg(prm.means3D + 3 * (size_t)i), py = __ldg(prm.means3D + 3 * (size_t)i + 1),
-                    pz = __ldg(prm.means3D + 3 * (size_t)i + 2);
+        const float px = s_means[3 * lane], py = s_means[3 * lane + 1], pz = s_means[3 * lane + 2];
         const float* V = cam.view;
         const float* P = cam.proj;
         const float t0 = fmaf(V[0], px, fmaf(V[4], py, fmaf(V[8], pz, V[12])));
@@ -112,10 +165,9 @@ preprocess_fwd_kernel(Cam cam, int N, Params prm, float4* __restrict__ rec, uint
             // activations
             float s0, s1, s2, qr, qx, qy, qz, o;
             {
-                const float a0 = __ldg(prm.scales + 3 * (size_t)i), a1 = __ldg(prm.scales + 3 * (size_t)i + 1),
-                            a2 = __ldg(prm.scales + 3 * (size_t)i + 2);
-                const float4 qq = __ldg(reinterpret_cast<const float4*>(prm.quats) + i);
-                const float oo = __ldg(prm.opacities + i);
+                const float a0 = s_scales[3 * lane], a1 = s_scales[3 * lane + 1], a2 = s_scales[3 * lane + 2];
+                const float4 qq = s_quats[lane];
+                const float oo = s_opac[lane];
                 if (cam.flags & DVS_FLAG_INPUT_ACTIVATED) {
                     s0 = cam.scale_modifier * a0; s1 = cam.scale_modifier * a1; s2 = cam.scale_modifier * a2;
                     qr = qq.x; qx = qq.y; qy = qq.z; qz = qq.w;
@@ -182,12 +234,13 @@ preprocess_fwd_kernel(Cam cam, int N, Params prm, float4* __restrict__ rec, uint
             const float mx = fmaf(ndcx + 1.0f, (float)cam.W, -1.0f) * 0.5f;
             const float my = fmaf(ndcy + 1.0f, (float)cam.H, -1.0f) * 0.5f;
             const float radf = (float)radius;
-            const int minx = min(cam.gx, max(0, (int)((mx - radf) * 0.0625f)));
-            const int miny = min(cam.gy, max(0, (int)((my - radf) * 0.0625f)));
-            const int maxx = min(cam.gx, max(0, (int)((mx + radf + 15.0f) * 0.0625f)));
-            const int maxy = min(cam.gy, max(0, (int)((my + radf + 15.0f) * 0.0625f)));
-            const long long area = (long long)(maxx - minx) * (long long)(maxy - miny);
+            const int rminx = min(cam.gx, max(0, (int)((mx - radf) * 0.0625f)));
+            const int rminy = min(cam.gy, max(0, (int)((my - radf) * 0.0625f)));
+            const int rmaxx = min(cam.gx, max(0, (int)((mx + radf + 15.0f) * 0.0625f)));
+            const int rmaxy = min(cam.gy, max(0, (int)((my + radf + 15.0f) * 0.0625f)));
+            const long long area = (long long)(rmaxx - rminx) * (long long)(rmaxy - rminy);
             if (area <= 0) break;
+            minx = rminx; miny = rminy; maxx = rmaxx; maxy = rmaxy;
             // colour
             float d0 = px - cam.campos[0], d1 = py - cam.campos[1], d2 = pz - cam.campos[2];
             const float len = sqrtf(fmaf(d0, d0, fmaf(d1, d1, d2 * d2)));
@@ -200,7 +253,7 @@ preprocess_fwd_kernel(Cam cam, int N, Params prm, float4* __restrict__ rec, uint
             const float* myrow = mysh + lane * row;
 #pragma unroll
             for (int ch = 0; ch < 3; ch++) {
-                float acc = bas[0] * __ldg(prm.sh0 + 3 * (size_t)i + ch);
+                float acc = bas[0] * s_sh0[3 * lane + ch];
 #pragma unroll
                 for (int k = 1; k < K; k++) acc = fmaf(bas[k], myrow[3 * (k - 1) + ch], acc);
                 acc += 0.5f;
@@ -215,25 +268,39 @@ preprocess_fwd_kernel(Cam cam, int N, Params prm, float4* __restrict__ rec, uint
             q0 = make_float4(mx, my, (-0.5f * LOG2E) * cA, (-LOG2E) * cB);
             q1 = make_float4((-0.5f * LOG2E) * cC, lo, col[0], col[1]);
             q2 = make_float4(col[2], t2, __int_as_float(radius), __uint_as_float(tiles | (clamped << 24)));
-            // opacity-aware AABB half extents of {alpha >= 1/255}: d^T conic d <= 2 ln2 (lo - log2(1/255))
-            const float m = lo - ALPHA_MIN_LOG2;
-            float ex = -1.0f, ey = -1.0f;  // negative: never contributes
-            if (m > 0.0f) {
-                const float k2 = 2.0f * LN2 * m;
-                ex = sqrtf(k2 * ca) * 1.0001f + 0.01f;
-                ey = sqrtf(k2 * cc) * 1.0001f + 0.01f;
-            }
-            ax = make_uint4((uint32_t)minx | ((uint32_t)miny << 16), (uint32_t)maxx | ((uint32_t)maxy << 16),
-                            __float_as_uint(ex), __float_as_uint(ey));
-            // per-tile duplicate counts (RED, no return)
-            for (int y = miny; y < maxy; y++)
-                for (int x = minx; x < maxx; x++) atomicAdd(tile_count + y * cam.gx + x, 1u);
+            // aux: tile rect, SH clamp mask (bits 29..31 of .y) and the depth key — all the emission kernel and
+            // the preprocess backward need, so neither touches the 48-byte records
+            ax = make_uint4((uint32_t)minx | ((uint32_t)miny << 16),
+                            (uint32_t)maxx | ((uint32_t)maxy << 16) | (clamped << 29), __float_as_uint(t2), 0u);
         } while (false);
-        float4* r = rec + 3 * (size_t)i;
-        r[0] = q0; r[1] = q1; r[2] = q2;
-        aux[i] = ax;
-        if (out_radii) out_radii[i] = rad;
     }
+    __syncwarp();  // every lane is done with its SH row: the region now becomes the output staging
+    s_rec[3 * lane] = q0; s_rec[3 * lane + 1] = q1; s_rec[3 * lane + 2] = q2;
+    s_aux[lane] = ax;
+    s_radii[lane] = rad;
+    // ---- records / aux / radii leave through the TMA engine (full warps) ----
+    if (full) {
+        fence_proxy_async();  // my generic-proxy smem writes -> visible to the async proxy
+        __syncwarp();
+        if (lane == 0) {
+            bulk_s2g(rec + 3 * (size_t)warp_first, s_rec, 32 * 48);
+            bulk_s2g(aux + warp_first, s_aux, 32 * 16);
+            if (out_radii) bulk_s2g(out_radii + warp_first, s_radii, 32 * 4);
+            bulk_commit();
+        }
+    } else {
+        __syncwarp();
+        if (i < N) {
+            float4* r = rec + 3 * (size_t)i;
+            r[0] = s_rec[3 * lane]; r[1] = s_rec[3 * lane + 1]; r[2] = s_rec[3 * lane + 2];
+            aux[i] = s_aux[lane];
+            if (out_radii) out_radii[i] = s_radii[lane];
+        }
+    }
+    // per-tile duplicate counts (RED, no return); overlaps the bulk stores
+    if (visible)
+        for (int y = miny; y < maxy; y++)
+            for (int x = minx; x < maxx; x++) atomicAdd(tile_count + (size_t)(y * cam.gx + x) * TILE_CTR_STRIDE, 1u);
     // stats: V and D
     const unsigned vm = __ballot_sync(0xffffffffu, visible);
     uint32_t tsum = tiles;
@@ -243,6 +310,7 @@ preprocess_fwd_kernel(Cam cam, int N, Params prm, float4* __restrict__ rec, uint
         atomicAdd(stats + 0, (unsigned long long)__popc(vm));
         atomicAdd(stats + 1, (unsigned long long)tsum);
     }
+    if (full && lane == 0) bulk_wait_read0();  // shared memory must outlive the bulk stores' reads
 }
 
 cudaError_t launch_preprocess_fwd(const Cam& cam, int N, const Params& prm, float4* rec, uint4* aux,
@@ -250,7 +318,7 @@ cudaError_t launch_preprocess_fwd(const Cam& cam, int N, const Params& prm, floa
                                   cudaStream_t st) {
     if (N <= 0) return cudaSuccess;
     const int grid = (N + PF_THREADS - 1) / PF_THREADS;
-    const size_t smem = (size_t)(PF_THREADS / 32) * 32 * 3 * cam.KR * sizeof(float);
+    const size_t smem = 64 + (size_t)PF_WARPS * PfLayout(3 * cam.KR).total;
 #define DVS_LAUNCH_PF(D)                                                                                  \
     do {                                                                                                  \
         if (smem > 48 * 1024)                                                                             \

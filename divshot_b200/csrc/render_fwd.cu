@@ -25,11 +25,11 @@ __global__ void __launch_bounds__(RF_THREADS)
 render_fwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const uint32_t* __restrict__ plist,
                   const float4* __restrict__ rec, float* __restrict__ out_color, float* __restrict__ final_T,
                   uint32_t* __restrict__ n_contrib, const uint32_t* __restrict__ info) {
-    __shared__ float4 s_q0[RF_THREADS];
-    __shared__ float4 s_q1[RF_THREADS];
-    __shared__ float s_b[RF_THREADS];
+    // staged entries: 48 B each {q0, q1, b, -, -, -}; masks in their own bank-conflict-free array
+    __shared__ __align__(16) unsigned char s_stage[RF_THREADS * 48];
     __shared__ uint32_t s_mask[RF_THREADS];
     if (info[2]) return;
+    const uint32_t sb = smem_u32(s_stage), sm = smem_u32(s_mask);
     const int tile = blockIdx.x;
     const int tx = tile % cam.gx, ty = tile / cam.gx;
     const uint32_t r0 = tile_base[tile], n = tile_base[tile + 1] - r0;
@@ -53,27 +53,28 @@ render_fwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const uint32_
         const uint32_t nxt = (rd + 1) * RF_THREADS + threadIdx.x;
         e_next = (nxt < n) ? __ldg(plist + r0 + nxt) : 0u;
         const uint32_t m = e & 0xffu;
-        s_mask[threadIdx.x] = m;
+        sts_u1(sm + threadIdx.x * 4, m);
         if (m) {
             const float4* r = rec + 3 * (size_t)(e >> 8);
             const float4 q0 = __ldg(r), q1 = __ldg(r + 1);
             const float b = __ldg(reinterpret_cast<const float*>(r + 2));
-            s_q0[threadIdx.x] = q0;
-            s_q1[threadIdx.x] = q1;
-            s_b[threadIdx.x] = b;
+            sts_f4(sb + threadIdx.x * 48, q0);
+            sts_f4(sb + threadIdx.x * 48 + 16, q1);
+            sts_f1(sb + threadIdx.x * 48 + 32, b);
         }
         __syncthreads();
         if (!warp_done) {
             const uint32_t base_idx = rd * RF_THREADS;
             const int cnt = (int)min((uint32_t)RF_THREADS, n - base_idx);
             for (int c = 0; c < cnt; c += 32) {
-                uint32_t bits = __ballot_sync(0xffffffffu, (s_mask[c + lane] & wbit) != 0u);
+                uint32_t bits = __ballot_sync(0xffffffffu, (lds_u1(sm + (c + lane) * 4) & wbit) != 0u);
                 while (bits) {
                     const int j = __ffs(bits) - 1;
                     bits &= bits - 1;
                     const int k = c + j;
-                    const float4 q0 = s_q0[k];
-                    const float4 q1 = s_q1[k];
+                    const uint32_t ea = sb + k * 48;
+                    const float4 q0 = lds_f4(ea);
+                    const float4 q1 = lds_f4(ea + 16);
                     const float dx = q0.x - pxf, dy = q0.y - pyf;
                     const float t = fmaf(q0.w, dy, q0.z * dx);
                     const float pw = fmaf(q1.x * dy, dy, t * dx);
@@ -87,7 +88,7 @@ render_fwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const uint32_
                             const float w = alpha * T;
                             C0 = fmaf(q1.z, w, C0);
                             C1 = fmaf(q1.w, w, C1);
-                            C2 = fmaf(s_b[k], w, C2);
+                            C2 = fmaf(lds_f1(ea + 32), w, C2);
                             T = test_T;
                             last = base_idx + (uint32_t)k + 1u;
                         }

@@ -27,3 +27,29 @@ def rel_err(a, b):
 def assert_close(a, b, tol, what=""):
     e = rel_err(a, b)
     assert e <= tol, f"{what}: rel err {e:.3e} > {tol:.1e}"
+
+
+def elem_err(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    floor = np.sqrt(np.mean(b * b)) + 1e-30
+    return np.abs(a - b) / (np.abs(b) + floor)
+
+
+def assert_close_robust(a, b, tol, what="", frac=0.999, loose=50.0):
+    """Parity check that tolerates threshold ties.  The compositor takes hard decisions (alpha >= 1/255,
+    T >= 1e-4) on values that differ in the last bits between two correct implementations (exp vs ex2,
+    summation order).  A flipped decision moves the few affected elements by up to ~1/255 of one pixel's
+    contribution, far above 1e-4 of a small element but invisible in the tensor norm.  So: (1) the norm-wise
+    relative error must be within `tol`; (2) at least `frac` of the elements must be within `tol` element-wise
+    (metric: rel_err); (3) no element may be off by more than `loose`*tol."""
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    if b.size == 0:
+        return
+    nrm = np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30)
+    e = elem_err(a, b)
+    good = float((e <= tol).mean())
+    msg = (f"{what}: norm-wise {nrm:.2e}, elements within {tol:.0e}: {100 * good:.3f}%, worst {e.max():.2e}, "
+           f"p99.9 {np.quantile(e, 0.999):.2e}")
+    assert nrm <= tol, msg
+    assert good >= frac, msg
+    assert e.max() <= loose * tol, msg
