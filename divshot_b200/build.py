@@ -81,8 +81,86 @@ def build_rast(force: bool = False, verbose: bool = False) -> str:
     return so
 
 
-def build_all(force: bool = False, verbose: bool = False):
-    return {"libdvsrast": build_rast(force, verbose)}
+def build_gstrain(force: bool = False) -> str:
+    """libgstrain.so: the trainer plugin (nine C symbols) + the rasterizer objects, one self-contained library."""
+    build_rast(force)
+    src = os.path.join(CSRC, "gstrain.cu")
+    hdr = os.path.join(ROOT, "include", "gaussian_trainer_scene.hpp")
+    obj = os.path.join(OBJ, "gstrain.o")
+    if force or _stale(obj, [src, hdr, os.path.join(ROOT, "include", "dvs_rast.h")]):
+        subprocess.check_call([nvcc(), "-ccbin", host_cxx(), *ARCH, *COMMON, "-c", src, "-o", obj])
+    objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in CU_SOURCES] + [obj]
+    so = os.path.join(OUT, "libgstrain.so")
+    if force or _stale(so, objs):
+        subprocess.check_call([nvcc(), "-ccbin", host_cxx(), *ARCH, "-shared", "-o", so, *objs, "-cudart", "static"])
+    return so
+
+
+def build_torch_binding(force: bool = False) -> str:
+    """libdvs_torch.so: torch::CustomClassHolder + autograd op over the C-ABI (g++ only, links libdvsrast.so)."""
+    build_rast(force)
+    src = os.path.join(CSRC, "torch_binding.cpp")
+    so = os.path.join(OUT, "libdvs_torch.so")
+    if not (force or _stale(so, [src, os.path.join(ROOT, "include", "dvs_rast.h")])):
+        return so
+    import torch
+    from torch.utils import cpp_extension as ce
+    inc = [f"-I{p}" for p in ce.include_paths()] + ["-I/usr/local/cuda/include", f"-I{os.path.join(ROOT, 'include')}"]
+    tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    abi = int(torch.compiled_with_cxx11_abi())
+    cmd = [host_cxx(), "-O2", "-std=c++17", "-fPIC", "-shared", f"-D_GLIBCXX_USE_CXX11_ABI={abi}", *inc, src, "-o", so,
+           f"-L{tlib}", "-ltorch", "-ltorch_cpu", "-lc10", "-ltorch_cuda", "-lc10_cuda", f"-L{OUT}", "-ldvsrast",
+           f"-Wl,-rpath,{tlib}", "-Wl,-rpath,$ORIGIN"]
+    subprocess.check_call(cmd)
+    return so
+
+
+def build_reference_cli(force: bool = False):
+    """Compile the reference's UNMODIFIED diverseshot-cli sources against include/gaussian_trainer_scene.hpp
+    (recipe verified in SURVEY.md section 8-b).  Only possible where /root/reference exists; the binary goes to
+    build/refcli/ (git-ignored, travels to the GPU box).  plugin.cpp has a g++-13 compile error on Linux
+    (plugin.cpp:93,125: std::format with a runtime string) so the loader is provided by tools/plugin_shim.cpp
+    implementing the same core/plugin.h interface."""
+    ref = "/root/reference"
+    out_dir = os.path.join(ROOT, "build", "refcli")
+    exe = os.path.join(out_dir, "diverseshot-cli")
+    if not os.path.isdir(ref):
+        return exe if os.path.exists(exe) else None
+    shim = os.path.join(ROOT, "tools", "plugin_shim.cpp")
+    if os.path.exists(exe) and not force and os.path.getmtime(exe) > os.path.getmtime(shim):
+        return exe
+    os.makedirs(out_dir, exist_ok=True)
+    import glob
+    inc = [os.path.join(ROOT, "include"), f"{ref}/application/diverseshot-cli/source", f"{ref}/diverse/diverse_base/source",
+           f"{ref}/external/CLI11/include", f"{ref}/external", f"{ref}/external/spdlog/include", f"{ref}/external/glm"]
+    srcs = [f"{ref}/application/diverseshot-cli/source/main.cpp", f"{ref}/application/diverseshot-cli/source/gs_train.cpp",
+            f"{ref}/diverse/diverse_base/source/utility/file_utils.cpp", f"{ref}/diverse/diverse_base/source/core/ds_log.cpp",
+            shim] + sorted(glob.glob(f"{ref}/external/spdlog/src/*.cpp"))
+    cmd = [host_cxx(), "-std=c++20", "-O1", "-w", "-DDS_PLATFORM_LINUX", "-DDS_PLATFORM_UNIX", "-DSPDLOG_COMPILED_LIB",
+           *[f"-I{i}" for i in inc], *srcs, "-o", exe, "-ldl", "-lpthread"]
+    subprocess.check_call(cmd)
+    return exe
+
+
+def build_driver(force: bool = False) -> str:
+    """tools/gstrain_driver.cpp -> build/gstrain_driver (dlopens libgstrain.so like the reference CLI does)."""
+    src = os.path.join(ROOT, "tools", "gstrain_driver.cpp")
+    exe = os.path.join(ROOT, "build", "gstrain_driver")
+    if force or _stale(exe, [src, os.path.join(ROOT, "include", "gaussian_trainer_scene.hpp")]):
+        os.makedirs(os.path.dirname(exe), exist_ok=True)
+        subprocess.check_call([host_cxx(), "-std=c++17", "-O1", f"-I{os.path.join(ROOT, 'include')}", src, "-o", exe, "-ldl"])
+    return exe
+
+
+def build_all(force: bool = False, verbose: bool = False, torch_binding: bool = True):
+    libs = {"libdvsrast": build_rast(force, verbose), "libgstrain": build_gstrain(force),
+            "gstrain_driver": build_driver(force)}
+    cli = build_reference_cli(force)
+    if cli:
+        libs["reference_cli"] = cli
+    if torch_binding:
+        libs["libdvs_torch"] = build_torch_binding(force)
+    return libs
 
 
 if __name__ == "__main__":

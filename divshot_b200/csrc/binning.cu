@@ -74,23 +74,43 @@ tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint32_t* __res
         __syncthreads();
         uint32_t run = (uint32_t)carry + (warp ? warp_sums[warp - 1] : 0u) + v - sum;
         const uint32_t slab_total = warp_sums[31];
+        // per-class work lists for the sort kernels (info[4+q] = count of class q): count my tiles per class,
+        // warp-scan the counts, ONE atomic per (warp, class) — the five atomics are independent and overlap
+        uint32_t mycnt[NUM_SORT_CLASSES];
+#pragma unroll
+        for (int q = 0; q < NUM_SORT_CLASSES; q++) mycnt[q] = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_MAX_PER_THREAD; k++)
+            if (first + k < T && c[k]) {
+                const int cls = sort_class_of(c[k]);
+#pragma unroll
+                for (int q = 0; q < NUM_SORT_CLASSES; q++) mycnt[q] += (cls == q) ? 1u : 0u;
+            }
+        uint32_t slot[NUM_SORT_CLASSES];
+#pragma unroll
+        for (int q = 0; q < NUM_SORT_CLASSES; q++) {
+            uint32_t inc = mycnt[q];
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t n = __shfl_up_sync(0xffffffffu, inc, off);
+                if (lane >= off) inc += n;
+            }
+            const uint32_t wtot = __shfl_sync(0xffffffffu, inc, 31);
+            uint32_t b = 0;
+            if (lane == 0 && wtot) b = atomicAdd(info + 4 + q, wtot);
+            slot[q] = __shfl_sync(0xffffffffu, b, 0) + inc - mycnt[q];
+        }
 #pragma unroll
         for (int k = 0; k < SCAN_MAX_PER_THREAD; k++) {
             const int t = first + k;
             if (t < T) {
                 tile_base[t] = run;
                 tile_cursor[(size_t)t * TILE_CTR_STRIDE] = run;
-            }
-            // per-class work lists for the sort kernels: warp-aggregated slot allocation (info[4+cls] = count)
-            const int cls = (t < T && c[k]) ? sort_class_of(c[k]) : -1;
+                if (c[k]) {
+                    const int cls = sort_class_of(c[k]);
 #pragma unroll
-            for (int q = 0; q < NUM_SORT_CLASSES; q++) {
-                const unsigned m = __ballot_sync(0xffffffffu, cls == q);
-                if (m) {
-                    uint32_t b = 0;
-                    if (lane == __ffs(m) - 1) b = atomicAdd(info + 4 + q, (uint32_t)__popc(m));
-                    b = __shfl_sync(0xffffffffu, b, __ffs(m) - 1);
-                    if (cls == q) class_tiles[(size_t)q * T + b + __popc(m & ((1u << lane) - 1u))] = (uint32_t)t;
+                    for (int q = 0; q < NUM_SORT_CLASSES; q++)
+                        if (cls == q) class_tiles[(size_t)q * T + slot[q]++] = (uint32_t)t;
                 }
             }
             run += c[k];

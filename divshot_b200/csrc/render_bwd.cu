@@ -96,7 +96,8 @@ render_bwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const uint32_
                   float* __restrict__ sgrad, const uint32_t* __restrict__ info) {
     extern __shared__ __align__(16) unsigned char rb_smem[];
     if (info[2]) return;
-    const uint32_t sb0 = smem_u32(rb_smem);
+    uint32_t sb0 = smem_u32(rb_smem);
+    asm volatile("" : "+r"(sb0));  // keep the shared base address in a register (no re-derivation per pair)
     const uint32_t sb = sb0 + RbSmem::stage, se = sb0 + RbSmem::ent, swm = sb0 + RbSmem::wmax;
     const int tile = blockIdx.x;
     const int tx = tile % cam.gx, ty = tile / cam.gx;

@@ -29,7 +29,8 @@ render_fwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const uint32_
     __shared__ __align__(16) unsigned char s_stage[RF_THREADS * 48];
     __shared__ uint32_t s_mask[RF_THREADS];
     if (info[2]) return;
-    const uint32_t sb = smem_u32(s_stage), sm = smem_u32(s_mask);
+    uint32_t sb = smem_u32(s_stage), sm = smem_u32(s_mask);
+    asm volatile("" : "+r"(sb), "+r"(sm));  // keep the shared base addresses in registers (no re-derivation per pair)
     const int tile = blockIdx.x;
     const int tx = tile % cam.gx, ty = tile / cam.gx;
     const uint32_t r0 = tile_base[tile], n = tile_base[tile + 1] - r0;

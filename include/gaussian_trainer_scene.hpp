@@ -1,0 +1,131 @@
+/*
+ * gaussian_trainer_scene.hpp — public header of the `gstrain` trainer plugin.
+ *
+ * The reference includes this file (application/diverseshot-cli/source/gs_train.cpp:3,
+ * application/editor/source/editor.cpp) from `${GSTRAIN_INCLUDE_DIR}` = diverse_utils/gstrain/src
+ * (CMakeLists.txt:101, application/diverseshot-cli/CMakeLists.txt:52) but does not ship it — the trainer is
+ * closed (README.md:32,46).  This header is authored from the *usage* in the reference:
+ *   - every GaussianTrainConfig field assigned at gs_train.cpp:50-99 and editor.cpp:1750-2020,2206;
+ *   - GSPackLevel::{PackF32ToU8,PackTileID} (gs_train.cpp:94-96, editor.cpp:1581);
+ *   - the nine C symbols resolved at gs_train.cpp:24-179 (signatures from the typedefs there);
+ *   - the GaussianTrainerScene methods the editor calls (editor.cpp:846-855,1426-1654,2023-2045).
+ * Defaults are the CLI defaults (application/diverseshot-cli/source/main.cpp:12-70).
+ *
+ * ABI note: create_splat / load_train_data pass C++ objects by reference across the .so boundary
+ * (gs_train.cpp:105-110), so the plugin and its caller must be built against this same header and the
+ * same libstdc++ ABI.
+ */
+#pragma once
+#include <array>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+enum GSPackLevel : int { PackNone = 0, PackF32ToU8 = 1, PackTileID = 2 };
+
+struct GaussianTrainConfig {
+    // paths
+    std::string sourcePath, modelPath, cameraPosePath, pointCloudPath;
+    // schedule (main.cpp:19-33)
+    int numIters = 30000;
+    int warmupLength = 500;
+    int refineEvery = 100;
+    int resetAlphaEvery = 3000;
+    int refineStopIter = 15000;
+    int refineScale2dStopIter = 0;
+    int modelType = 0;        // 0 = 3DGS, 1 = 2DGS
+    int densifyStrategy = 1;  // 0 = ADC, 1 = MCMC, 2 = ADC+
+    int pruneInterval = 0;
+    int pruneStrategy = 0;
+    int maxImageWidth = 2048, maxImageHeight = 2048, maxImageCount = 0;
+    int capMax = 3000000;
+    int packLevel = PackF32ToU8;
+    int meshResolution = 0, resolutionSchedule = 0, datasetType = 0, cameraModel = 0, quality = 0;
+    int mapperType = 0, videoStrategy = 0, videoFps = 0;
+    // learning rates / thresholds (3DGS defaults where the CLI leaves them unset)
+    float growGrad2d = 2e-4f;
+    float ssimWeight = 0.2f;
+    float noiselr = 1e5f;
+    float poslrInit = 1.6e-4f, poslrFinal = 1.6e-6f;
+    float rotationlr = 1e-3f, scalinglr = 5e-3f, featurelr = 2.5e-3f, opacitylr = 5e-2f;
+    float min_opacity = 0.005f, pruneOpacity = 0.005f, pruneScale3d = 0.1f, pruneScale2d = 0.15f;
+    // switches
+    bool revisedOpacity = false, progressiveTrain = false, useAbsGrad = true, pixelGradScale = false;
+    bool verbose = false, mipAntiliased = false, exportMesh = false, useMask = false;
+    bool normalConsistencyLoss = false, bestQuality = false, visibleAdam = false, enableBg = false;
+    bool enableFocusRegion = false, cullSH = false, singleCamera = false, outputSparsePoints = false;
+};
+
+enum class TrainingStatus : int {
+    Loading_Prepare = 0,
+    Loading_Data,
+    Colmap_Sfm,
+    Preprocess_Done,
+    Training,
+    Training_Done,
+    GS2Mesh,
+    Loading_Failed,
+};
+
+struct GaussianTrainerImpl;  // B200 rasterizer context + device-resident parameters (gstrain.cu)
+
+class GaussianTrainerScene {
+public:
+    GaussianTrainerScene(const GaussianTrainConfig& config, int loadItr);
+    ~GaussianTrainerScene();
+    GaussianTrainerScene(const GaussianTrainerScene&) = delete;
+    GaussianTrainerScene& operator=(const GaussianTrainerScene&) = delete;
+
+    bool loadTrainData(const std::string& path);
+    void trainSetup();
+    void trainStep();
+    void startTrain() { train_ = true; }
+    void pauseTrain() { train_ = false; }
+    bool& isTrain() { return train_; }
+    bool isTerminate() const { return terminate_; }
+    bool isPruningSplat() const { return false; }
+    void saveGaussianModel();
+    void exportMesh(const std::string& path);
+    void setModelPath(const std::string& p) { config_.modelPath = p; }
+    void setTrainingStatus(TrainingStatus s) { status_ = s; }
+    TrainingStatus getCurrentTrainingStatus() const { return status_; }
+    int getCurrentIterations() const { return curIteration; }
+    int& maxIteriaons() { return config_.numIters; }
+    float getCurrentLoss() const { return loss_; }
+    GaussianTrainConfig& getTrainConfig() { return config_; }
+    int64_t getNumGaussians() const;
+    // CPU copies of the stored (raw) parameters, layouts of gaussian_model.cpp:43-68
+    std::vector<float> getGaussianPositionCpu() const;
+    std::vector<float> getGaussianSH0Cpu() const;
+    std::vector<float> getGaussianSHNCpu() const;
+    std::vector<float> getGaussianOpcaitiesCpu() const;
+    std::vector<float> getGaussianScalingsCpu() const;
+    std::vector<float> getGaussianRotationsCpu() const;
+    int getNumCameras() const;
+    std::array<float, 16> getCameraProjection(int i) const;  // flat [4c+r]
+    std::array<float, 16> getCameraView(int i) const;
+
+    bool ShowTrainView = false;
+    int curIteration = 0;
+    std::vector<int> pruenIteraions;
+
+private:
+    GaussianTrainConfig config_;
+    TrainingStatus status_ = TrainingStatus::Loading_Prepare;
+    bool train_ = true, terminate_ = false;
+    float loss_ = 0.f;
+    GaussianTrainerImpl* impl_ = nullptr;
+};
+
+// The nine symbols the unmodified CLI resolves with dlsym (gs_train.cpp:24,105-110,144-150,178-179).
+extern "C" {
+void gstrain_init();
+void* create_splat(const GaussianTrainConfig& config, int loadItr);
+bool load_train_data(GaussianTrainerScene* scene, const std::string& path);
+void train_step(GaussianTrainerScene* scene);
+void save_splat_model(GaussianTrainerScene* scene);
+void export_mesh(GaussianTrainerScene* scene);
+void delete_splat(GaussianTrainerScene* scene);
+int get_cur_step(GaussianTrainerScene* scene);
+void gstrain_destroy();
+}

@@ -1,0 +1,119 @@
+"""The drop-in boundary (SURVEY.md §8 b): libgstrain.so exports what the unmodified reference CLI resolves
+(application/diverseshot-cli/source/gs_train.cpp:24-179), the reference CLI builds against our authored header,
+and — on a GPU — trains through that boundary; the libtorch CustomClassHolder matches the C-ABI path."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "divshot_b200", "lib")
+NINE = ["gstrain_init", "create_splat", "load_train_data", "train_step", "save_splat_model", "export_mesh",
+        "delete_splat", "get_cur_step", "gstrain_destroy"]
+
+
+def _build():
+    from divshot_b200 import build
+    return build.build_all()
+
+
+def test_plugin_exports_the_nine_symbols_with_c_linkage():
+    libs = _build()
+    out = subprocess.check_output(["nm", "-D", "--defined-only", libs["libgstrain"]], text=True)
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    for s in NINE + ["get_description", "create_instance"]:
+        assert s in exported, f"libgstrain.so does not export {s}"
+
+
+def test_reference_cli_builds_unmodified_against_our_header():
+    libs = _build()
+    cli = libs.get("reference_cli")
+    if not cli:
+        pytest.skip("reference sources not present (GPU box) and no prebuilt CLI")
+    out = subprocess.run([cli, "--help"], capture_output=True, text=True, env={**os.environ, "LD_LIBRARY_PATH": LIB})
+    assert out.returncode == 0 and "--inputPath" in out.stdout and "--maxIteration" in out.stdout
+
+
+def test_plugin_fails_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    libs = _build()
+    r = subprocess.run([libs["gstrain_driver"], "synthetic:N=100,W=32,H=32,views=1", "2", "/tmp/x.ply"],
+                       capture_output=True, text=True, env={**os.environ, "LD_LIBRARY_PATH": LIB})
+    assert r.returncode != 0 and "CUDA" in (r.stderr + r.stdout)
+
+
+def _read_ply(path):
+    raw = open(path, "rb").read()
+    head, body = raw.split(b"end_header\n", 1)
+    lines = head.decode().splitlines()
+    n = int([l for l in lines if l.startswith("element vertex")][0].split()[-1])
+    props = [l.split()[-1] for l in lines if l.startswith("property float")]
+    return n, props, np.frombuffer(body, np.float32).reshape(n, len(props))
+
+
+@pytest.mark.gpu
+def test_driver_trains_through_the_plugin_boundary(tmp_path):
+    libs = _build()
+    out = str(tmp_path / "model.ply")
+    r = subprocess.run([libs["gstrain_driver"], "synthetic:N=20000,W=320,H=240,views=4,deg=1", "300", out],
+                       capture_output=True, text=True, env={**os.environ, "LD_LIBRARY_PATH": LIB}, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr  # exit 0 <=> loss fell by > 20 %
+    n, props, rows = _read_ply(out)
+    # PLY row layout of external/tinygsplat/tiny_gsplat.cpp:168-241
+    assert n == 20000 and props[:6] == ["x", "y", "z", "f_dc_0", "f_dc_1", "f_dc_2"]
+    assert props[6] == "f_rest_0" and props[50] == "f_rest_44" and props[51] == "opacity"
+    assert props[52:55] == ["scale_0", "scale_1", "scale_2"] and props[55:] == ["rot_0", "rot_1", "rot_2", "rot_3"]
+    assert np.isfinite(rows).all()
+
+
+@pytest.mark.gpu
+def test_reference_cli_end_to_end(tmp_path):
+    libs = _build()
+    cli = libs.get("reference_cli")
+    if not cli:
+        pytest.skip("no prebuilt reference CLI on this box")
+    out = str(tmp_path / "cli_model.ply")
+    r = subprocess.run([cli, "--inputPath", "synthetic:N=20000,W=320,H=240,views=4,deg=1", "--outputPath", out,
+                        "--maxIteration", "200"], capture_output=True, text=True,
+                       env={**os.environ, "LD_LIBRARY_PATH": LIB}, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    n, props, rows = _read_ply(out)
+    assert n == 20000 and len(props) == 59 and np.isfinite(rows).all()
+
+
+@pytest.mark.gpu
+def test_libtorch_custom_class_matches_c_abi():
+    import torch
+    from divshot_b200 import _cabi
+    from divshot_b200.rasterizer import GradBuffers, Rasterizer, scene_to_device
+    from divshot_b200.scenes import make_scene
+    libs = _build()
+    torch.classes.load_library(libs["libdvs_torch"])
+    sc = make_scene(N=5000, width=128, height=96, sh_degree=2, seed=5)
+    sc.log_scales += 0.8
+    dev = torch.device("cuda", 0)
+    params = scene_to_device(sc, dev)
+    cam = sc.cameras[0]
+    packed = np.zeros(48, np.float32)
+    packed[0:16] = cam.view; packed[16:32] = cam.proj; packed[32:35] = cam.campos
+    packed[35:37] = (cam.tanfovx, cam.tanfovy); packed[37:39] = (cam.width, cam.height); packed[39:42] = cam.bg
+    packed[42:46] = (1.0, 2, 8, 0)
+    camt = torch.from_numpy(packed)
+    r = torch.classes.dvs.Rasterizer(0)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    img, radii = torch.ops.dvs.rasterize(r, camt, leaves["means3D"], leaves["scales"], leaves["quats"],
+                                         leaves["opacities"], leaves["sh0"], leaves["shN"])
+    dl = torch.from_numpy(sc.dL_dpix[0]).to(dev)
+    (img * dl).sum().backward()
+    ref = Rasterizer(0)
+    rimg, rradii = ref.forward(_cabi.make_camera(cam, 2), params)
+    g = GradBuffers.allocate(sc.N, 8, dev)
+    ref.backward(dl, g)
+    assert torch.equal(img.detach(), rimg) and torch.equal(radii, rradii)
+    for k in ("means3D", "scales", "quats", "opacities", "sh0", "shN"):
+        a, b = leaves[k].grad, getattr(g, k)
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-6 * float(b.abs().max())), k

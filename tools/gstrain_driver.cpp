@@ -1,0 +1,50 @@
+// gstrain_driver.cpp — minimal stand-in for the reference CLI loop (application/diverseshot-cli/source/gs_train.cpp:20-179):
+// dlopen("libgstrain.so"), resolve the nine symbols by name, create_splat -> load_train_data -> train_step loop ->
+// save_splat_model -> delete_splat -> gstrain_destroy.  Used by tests/test_plugin.py on the GPU box, where the
+// reference sources (and therefore the real CLI build) may be absent.  Prints the loss trajectory.
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+
+#include "gaussian_trainer_scene.hpp"
+
+int main(int argc, char** argv) {
+    const std::string data = argc > 1 ? argv[1] : "synthetic:N=20000,W=320,H=240,views=4,deg=1";
+    const int iters = argc > 2 ? std::atoi(argv[2]) : 300;
+    const std::string out = argc > 3 ? argv[3] : "/tmp/gstrain_driver.ply";
+    void* h = dlopen("libgstrain.so", RTLD_LAZY | RTLD_LOCAL);
+    if (!h) { std::fprintf(stderr, "dlopen: %s\n", dlerror()); return 2; }
+    auto sym = [&](const char* n) { void* p = dlsym(h, n); if (!p) { std::fprintf(stderr, "missing symbol %s\n", n); std::exit(3); } return p; };
+    auto init = (void (*)())sym("gstrain_init");
+    auto create = (void* (*)(const GaussianTrainConfig&, int))sym("create_splat");
+    auto load = (bool (*)(GaussianTrainerScene*, const std::string&))sym("load_train_data");
+    auto step = (void (*)(GaussianTrainerScene*))sym("train_step");
+    auto save = (void (*)(GaussianTrainerScene*))sym("save_splat_model");
+    auto mesh = (void (*)(GaussianTrainerScene*))sym("export_mesh");
+    auto del = (void (*)(GaussianTrainerScene*))sym("delete_splat");
+    auto cur = (int (*)(GaussianTrainerScene*))sym("get_cur_step");
+    auto destroy = (void (*)())sym("gstrain_destroy");
+    (void)mesh;
+    init();
+    GaussianTrainConfig cfg;
+    cfg.sourcePath = data; cfg.modelPath = out; cfg.numIters = iters; cfg.verbose = true;
+    auto* scene = (GaussianTrainerScene*)create(cfg, -1);
+    if (!load(scene, data)) { std::fprintf(stderr, "load_train_data failed\n"); return 4; }
+    float first = -1.f, last = -1.f;
+    while (true) {
+        const int i = cur(scene);
+        if (i >= iters) break;
+        step(scene);
+        last = scene->getCurrentLoss();
+        if (i == 0) first = last;
+        if (i % 50 == 0) std::printf("iter %d loss %.6f\n", i, last);
+    }
+    save(scene);
+    std::printf("steps %d first_loss %.6f last_loss %.6f\n", cur(scene), first, last);
+    del(scene);
+    destroy();
+    dlclose(h);
+    return last < 0.8f * first ? 0 : 5;
+}
