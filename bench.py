@@ -139,6 +139,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, help="override: c2|c3|c5 (parity/bench exploration only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--allreduce", default="auto", choices=["auto", "nvls", "nccl"],
+                    help="gradient all-reduce: NVSwitch in-switch reduction over symmetric memory, or plain NCCL")
     args = ap.parse_args()
     global WORKLOAD
     if args.workload:
@@ -146,11 +148,16 @@ def main():
     if args.impl == "reference":
         return reference_arm(args)
 
+    # only the JSON line may reach stdout (NCCL prints its version banner there when NCCL_DEBUG is set)
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import numpy as np
     import torch
     import torch.distributed as dist
     from divshot_b200 import _cabi
     from divshot_b200.rasterizer import GradBuffers, Rasterizer, scene_to_device
+    from divshot_b200.dp import GradientReducer
     from divshot_b200.scenes import CONFIGS, make_scene
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -171,7 +178,8 @@ def main():
     dl_host = torch.from_numpy(sc.dL_dpix[rank % len(sc.dL_dpix)]).pin_memory()
     dl = dl_host.to(dev)
     img_host = torch.empty(3, H, W, dtype=torch.float32).pin_memory()
-    grads = GradBuffers.allocate(N, K - 1, dev)
+    reducer = GradientReducer(GradBuffers.numel_for(N, K - 1), dev, backend=args.allreduce)
+    grads = GradBuffers.allocate(N, K - 1, dev, flat=reducer.flat)
     rast = Rasterizer(local)
     rast.reserve(N, W, H, 0)
     img = torch.empty(3, H, W, device=dev)
@@ -181,12 +189,12 @@ def main():
         rast.forward(cam, params, img, radii)
         rast.backward(dl, grads)
         if world > 1:
-            dist.all_reduce(grads.flat)
+            reducer.all_reduce()
 
     def step_e2e():
         rast.step_host(cam, params, grads, dl_host, img_host)
         if world > 1:
-            dist.all_reduce(grads.flat)
+            reducer.all_reduce()
 
     def timed(fn, steps, warmup, sample_clocks=False):
         for _ in range(warmup):
@@ -225,6 +233,10 @@ def main():
             stage_ms[k] = stage_ms.get(k, 0.0) + v / reps
     st = rast.stats()
     ms_e2e, _ = timed(step_e2e, args.steps, warm)
+    ms_ar = None
+    if world > 1:  # the collective alone (device time, max over ranks), for the scaling breakdown
+        ms_ar, _ = timed(lambda: reducer.all_reduce(), args.steps, warm)
+        ms_ar /= args.steps
 
     ms_step = ms_total / args.steps
     value = N * world / (ms_step * 1e-3)
@@ -264,7 +276,10 @@ def main():
                 "d2h_bytes_per_step": 12 * P * world, "ms_per_step": ms_e2e / args.steps,
                 "api": "dvs_rast_step_host (C-ABI): pinned dL/dpix H2D, forward, image D2H, backward; parameters and "
                        "gradients device-resident as in the trainer"},
-        "gpu_launches": 10 * args.steps,
+        "gpu_launches": 12 * args.steps,
+        "allreduce": ({"backend": reducer.backend, "note": reducer.note, "bytes": int(reducer.flat.numel()) * 4, "ms": ms_ar,
+                       "busbw_GBps": (2 * (world - 1) / world * reducer.flat.numel() * 4 / 1e9 / (ms_ar * 1e-3))}
+                      if world > 1 else None),
         "clocks": clocks,
     }
     if world == 1 and rank == 0 and not args.no_cpu:
@@ -273,7 +288,9 @@ def main():
         line["cpu_baseline"] = {"value": n_s / best, "unit": "Gaussians/s", "cores": cores, "kind": "port",
                                 "sample": sample + f"; best of 3 ({best:.2f} s)"}
     if rank == 0:
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     rast.close()

@@ -24,6 +24,7 @@ EXPORTS = [
     "dvs_rast_forward", "dvs_rast_backward", "dvs_rast_step_host", "dvs_rast_get_stats", "dvs_rast_debug_read",
     "dvs_rast_stage_ms", "dvs_rast_stage_name",
 ]
+COLL_EXPORTS = ["dvs_coll_allreduce_nvls"]
 
 
 class DvsCamera(C.Structure):
@@ -86,6 +87,8 @@ def load():
     L.dvs_rast_stage_ms.restype = C.c_int
     L.dvs_rast_stage_name.argtypes = [C.c_int]
     L.dvs_rast_stage_name.restype = C.c_char_p
+    L.dvs_coll_allreduce_nvls.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.dvs_coll_allreduce_nvls.restype = C.c_int
     _lib = L
     return L
 

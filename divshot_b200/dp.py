@@ -1,0 +1,108 @@
+"""View-sharded data parallelism (SURVEY.md §8 e): Gaussians replicated on every rank, the views of a batch
+partitioned across ranks, ONE sum all-reduce of the dense per-Gaussian gradient arena per step.
+
+The reference has no multi-GPU path at all (zero hits for nccl / MPI / ProcessGroup); this is new
+functionality required by BASELINE.json's north_star.  torch.distributed is only the plumbing (NCCL over
+NVLink 5 / NVSwitch on the GPU box, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def views_for_rank(num_views: int, rank: int, world: int) -> list[int]:
+    """Round-robin partition of a batch of views: rank r renders views r, r+world, ... (independent units,
+    no data-path exchange until the gradient sum)."""
+    return list(range(rank, num_views, world))
+
+
+def allreduce_gradients(flat: torch.Tensor, group=None, average: bool = False) -> torch.Tensor:
+    """Sum (or average) the flat gradient arena (GradBuffers.flat: all six parameter gradients in one
+    contiguous fp32 buffer, so the exchange is a single collective call)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            flat.div_(dist.get_world_size(group))
+    return flat
+
+
+class GradientReducer:
+    """Owns the flat gradient arena and the collective that sums it.
+
+    backend "nccl": ncclAllReduce (the baseline).
+    backend "nvls": the arena lives in symmetric memory (torch.distributed._symmetric_memory) and is summed by the
+        NVSwitch itself with our own two-shot multimem kernel (csrc/collective.cu), bracketed by symmetric-memory
+        barriers.  Each GPU moves ~(1+1/W)x the arena per direction instead of the ring's 2(W-1)/W x.
+    backend "auto": NCCL unless the NVLS path initialises AND measures faster on this machine (3 timed runs each).
+    """
+
+    def __init__(self, numel: int, device: torch.device, backend: str = "auto", group=None, ctas: int = 0):
+        self.group = group
+        self.backend = "nccl"
+        self.flat = None
+        self.ctas = ctas
+        self.note = ""
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        numel = (numel + 1023) // 1024 * 1024
+        self._hdl = None
+        if world > 1 and backend in ("auto", "nvls") and device.type == "cuda":
+            try:
+                import ctypes as C
+
+                import torch.distributed._symmetric_memory as symm_mem
+
+                from . import _cabi
+                self._lib = _cabi.load()
+                self.group_name = (group or dist.group.WORLD).group_name
+                buf = symm_mem.empty(numel, dtype=torch.float32, device=device)
+                hdl = symm_mem.rendezvous(buf, self.group_name)
+                if not getattr(hdl, "multicast_ptr", 0):
+                    raise RuntimeError("no NVLS multicast mapping for this allocation")
+                self._hdl, self._C = hdl, C
+                self.flat = buf
+                buf.zero_()
+                self.backend = "nvls"
+                self.all_reduce()
+                torch.cuda.synchronize(device)
+                if backend == "auto":  # keep NVLS only if it beats NCCL here
+                    t_nvls = self._time(device)
+                    self.backend = "nccl"
+                    t_nccl = self._time(device)
+                    self.backend = "nvls" if t_nvls < t_nccl else "nccl"
+                    self.note = f"auto: nvls {t_nvls:.3f} ms vs nccl {t_nccl:.3f} ms"
+            except Exception as e:  # no NVSwitch multicast / unsupported build: NCCL
+                if backend == "nvls":
+                    raise
+                self.note = f"nvls unavailable ({type(e).__name__}: {e})"
+                self.backend = "nccl"
+        if self.flat is None:
+            self.flat = torch.zeros(numel, dtype=torch.float32, device=device)
+
+    def _time(self, device, reps: int = 3) -> float:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.all_reduce(); torch.cuda.synchronize(device)
+        dist.barrier(self.group); torch.cuda.synchronize(device)
+        e0.record()
+        for _ in range(reps):
+            self.all_reduce()
+        e1.record(); torch.cuda.synchronize(device)
+        t = torch.tensor([e0.elapsed_time(e1) / reps], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return float(t.item())
+
+    def all_reduce(self):
+        if not (dist.is_initialized() and dist.get_world_size(self.group) > 1):
+            return self.flat
+        if self.backend == "nvls":
+            hdl = self._hdl
+            st = torch.cuda.current_stream(self.flat.device).cuda_stream
+            hdl.barrier(channel=0)  # every rank's gradients are in place
+            rc = self._lib.dvs_coll_allreduce_nvls(self._C.c_void_p(hdl.multicast_ptr), self.flat.numel(), hdl.rank,
+                                                   hdl.world_size, self.ctas, self._C.c_void_p(st))
+            if rc != 0:
+                raise RuntimeError(f"dvs_coll_allreduce_nvls failed ({rc})")
+            hdl.barrier(channel=1)  # every shard has been re-broadcast
+        else:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+        return self.flat

@@ -34,7 +34,14 @@ class GradBuffers:
     shN: torch.Tensor
 
     @staticmethod
-    def allocate(N: int, sh_rest: int, device) -> "GradBuffers":
+    def numel_for(N: int, sh_rest: int) -> int:
+        total = 0
+        for sz in (4 * N, 3 * sh_rest * N, 3 * N, 3 * N, 3 * N, N):
+            total = (total + 3) // 4 * 4 + sz
+        return max(total, 4)
+
+    @staticmethod
+    def allocate(N: int, sh_rest: int, device, flat: torch.Tensor | None = None) -> "GradBuffers":
         # every view starts on a 16-byte boundary: order quats, shN first (16 B rows), then the 12 B / 4 B rows
         sizes = [("quats", 4 * N), ("shN", 3 * sh_rest * N), ("means3D", 3 * N), ("scales", 3 * N), ("sh0", 3 * N),
                  ("opacities", N)]
@@ -43,7 +50,9 @@ class GradBuffers:
             total = (total + 3) // 4 * 4
             offs[name] = (total, sz)
             total += sz
-        flat = torch.zeros(max(total, 4), dtype=torch.float32, device=device)
+        if flat is None:
+            flat = torch.zeros(max(total, 4), dtype=torch.float32, device=device)
+        assert flat.numel() >= total and flat.is_contiguous()
         v = {n: flat[o:o + s] for n, (o, s) in offs.items()}
         return GradBuffers(flat, v["means3D"].view(N, 3), v["scales"].view(N, 3), v["quats"].view(N, 4),
                            v["opacities"].view(N), v["sh0"].view(N, 3), v["shN"].view(N, sh_rest, 3))

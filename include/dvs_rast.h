@@ -102,7 +102,7 @@ enum {
     DVS_BUF_FINAL_T = 9,       /* float [H*W] */
     DVS_BUF_N_CONTRIB = 10,    /* uint32 [H*W] */
     DVS_BUF_CULL_MASK = 11,    /* uint8 [D] per-entry 8-bit sub-tile mask (ours; no upstream analogue) */
-    DVS_BUF_SCREEN_GRADS = 12  /* float [N,12]: dmean2D(2), dconic A,B,C(3), dopacity(1), dcolor(3), |dmean2D|(2), pad */
+    DVS_BUF_SCREEN_GRADS = 12  /* float [N,12]: moments of s=dL/dpower {Sx,Sy,Sxx,Sxy,Syy,S0}, colour sums (3), |gx|,|gy|, pad */
 };
 
 /* Create a context on CUDA device `device`.  Scratch arenas grow on demand and persist. */
@@ -154,6 +154,16 @@ DVS_API int dvs_rast_debug_read(dvs_rast_ctx* ctx, int which, void* dst_host, si
 #define DVS_NUM_STAGES 8
 DVS_API int dvs_rast_stage_ms(dvs_rast_ctx* ctx, float out_ms[DVS_NUM_STAGES]);
 DVS_API const char* dvs_rast_stage_name(int i);
+
+/*
+ * NVSwitch in-switch all-reduce (sum, fp32, in place) of a symmetric buffer through its multicast mapping
+ * (multimem.ld_reduce + multimem.st, two-shot: rank r reduces and re-broadcasts shard r).  `multicast_ptr` is the
+ * NVLS multicast address of the buffer (e.g. torch.distributed._symmetric_memory handle.multicast_ptr), numel_f32 a
+ * multiple of 4.  The caller must bracket the call with cross-rank barriers on `stream`.  New functionality: the
+ * reference has no multi-GPU path; this is the exchange step of SURVEY.md section 8(e).
+ */
+DVS_API int dvs_coll_allreduce_nvls(void* multicast_ptr, size_t numel_f32, int rank, int world, int ctas,
+                                    void* stream);
 
 #ifdef __cplusplus
 }

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _declared():
     src = open(os.path.join(ROOT, "include", "dvs_rast.h")).read()
-    return sorted(set(re.findall(r"DVS_API\s+[\w\s\*]+?\b(dvs_rast_\w+)\s*\(", src)))
+    return sorted(set(re.findall(r"DVS_API\s+[\w\s\*]+?\b(dvs_(?:rast|coll)_\w+)\s*\(", src)))
 
 
 def test_header_declares_the_expected_entry_points():
@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_cabi.LIB_PATH)
     for n in _declared():
         assert hasattr(lib, n), f"libdvsrast.so does not export {n}"
-    assert set(_cabi.EXPORTS) == set(_declared())
+    assert set(_cabi.EXPORTS + _cabi.COLL_EXPORTS) == set(_declared())
     lib.dvs_rast_version.restype = ctypes.c_char_p
     assert b"sm_100a" in lib.dvs_rast_version()
 
