@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libdvsrast.so")
 FLAG_INPUT_ACTIVATED = 1
 FLAG_ACCUMULATE = 2
 FLAG_ABSGRAD = 4
+FLAG_DEFER_CHECK = 8
 NUM_STAGES = 8
 
 (BUF_RADII, BUF_TILES_TOUCHED, BUF_DEPTH, BUF_MEAN2D, BUF_CONIC_OPACITY, BUF_RGB, BUF_CLAMPED, BUF_POINT_LIST,

@@ -45,7 +45,7 @@ struct dvs_rast_ctx {
     // small device words + pinned mirror
     uint32_t* info = nullptr;               // [16]: D, max len, overflow, -, tiles per sort class [5]
     unsigned long long* stats = nullptr;    // [2]: V, D
-    uint32_t* h_info = nullptr;             // pinned [4]
+    uint32_t* h_info = nullptr;             // pinned [16]
     unsigned long long* h_stats = nullptr;  // pinned [2]
     // last forward
     bool have_fwd = false;
@@ -57,6 +57,11 @@ struct dvs_rast_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_h2d = nullptr, ev_img = nullptr, ev_d2h = nullptr;
     bool ev_fwd = false, ev_bwd = false;
+    // deferred arena validation (DVS_FLAG_DEFER_CHECK)
+    cudaEvent_t ev_check = nullptr;
+    bool pending_check = false;
+    bool arena_sized = false;      // a synchronous forward has validated the capacity
+    uint32_t seen_overflows = 0;   // value of the sticky device counter info[3] already handled
 };
 
 static int fail(dvs_rast_ctx* c, int code, const char* fmt, ...) {
@@ -119,6 +124,40 @@ static int ensure_pix(dvs_rast_ctx* ctx, int64_t P) {
     return DVS_OK;
 }
 
+static void publish_stats(dvs_rast_ctx* ctx) {
+    ctx->st.num_visible = (int64_t)ctx->h_stats[0];
+    ctx->st.num_dups = (int64_t)ctx->h_info[0];
+    ctx->st.dup_capacity = ctx->cap_dups;
+    ctx->st.max_tile_len = ctx->h_info[1];
+}
+
+// Deferred validation: if the last DEFER_CHECK forward has finished (or `block`), look at the sticky overflow
+// counter; on overflow grow the arena and report DVS_E_OVERFLOW.
+static int resolve_pending(dvs_rast_ctx* ctx, bool block) {
+    if (!ctx->pending_check) return DVS_OK;
+    if (block) {
+        CK(cudaEventSynchronize(ctx->ev_check));
+    } else {
+        cudaError_t q = cudaEventQuery(ctx->ev_check);
+        if (q == cudaErrorNotReady) return DVS_OK;
+        CK(q);
+    }
+    ctx->pending_check = false;
+    if (ctx->h_info[3] != ctx->seen_overflows) {
+        ctx->seen_overflows = ctx->h_info[3];
+        const int64_t need = (int64_t)ctx->h_info[9];
+        ctx->st.overflow = 1;
+        ctx->have_fwd = false;
+        ctx->arena_sized = false;
+        int rc = ensure_dups(ctx, need + need / 4 + 4096);
+        if (rc) return rc;
+        return fail(ctx, DVS_E_OVERFLOW, "a deferred-check forward needed %lld binning entries (> capacity); arena grown, redo the step",
+                    (long long)need);
+    }
+    publish_stats(ctx);
+    return DVS_OK;
+}
+
 extern "C" {
 
 const char* dvs_rast_version(void) { return "divshot_b200 rasterizer 0.1 (sm_100a)"; }
@@ -132,9 +171,11 @@ int dvs_rast_create(int device, dvs_rast_ctx** out) {
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->info), 16 * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->stats), 2 * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_info), 4 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_info), 16 * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_stats), 2 * sizeof(unsigned long long));
     for (int i = 0; e == cudaSuccess && i < DVS_NUM_STAGES + 2; i++) e = cudaEventCreate(&ctx->ev[i]);
+    if (e == cudaSuccess) e = cudaMemset(ctx->info, 0, 16 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_check, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_h2d, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_img, cudaEventDisableTiming);
@@ -160,6 +201,7 @@ void dvs_rast_destroy(dvs_rast_ctx* ctx) {
     cudaFreeHost(ctx->h_info); cudaFreeHost(ctx->h_stats);
     for (auto& e : ctx->ev)
         if (e) cudaEventDestroy(e);
+    if (ctx->ev_check) cudaEventDestroy(ctx->ev_check);
     if (ctx->ev_h2d) cudaEventDestroy(ctx->ev_h2d);
     if (ctx->ev_img) cudaEventDestroy(ctx->ev_img);
     if (ctx->ev_d2h) cudaEventDestroy(ctx->ev_d2h);
@@ -209,6 +251,8 @@ int dvs_rast_forward(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, const 
     if (N > 0 && (rc = check_params(ctx, params, cam->sh_rest_alloc))) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(cudaSetDevice(ctx->device));
+    if ((rc = resolve_pending(ctx, false))) return rc;
+    const bool defer = (cam->flags & DVS_FLAG_DEFER_CHECK) && ctx->arena_sized;
 
     Cam c{};
     memcpy(c.view, cam->view, sizeof c.view);
@@ -228,6 +272,9 @@ int dvs_rast_forward(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, const 
     if ((rc = ensure_tiles(ctx, T))) return rc;
     if ((rc = ensure_pix(ctx, P))) return rc;
     if (ctx->cap_dups == 0 && (rc = ensure_dups(ctx, (N > 0 ? 16 * N : 1) + 4096))) return rc;
+    if (!ctx->arena_sized && ctx->st.num_dups > 0 && !ctx->pending_check &&
+        (rc = ensure_dups(ctx, ctx->st.num_dups + ctx->st.num_dups / 2 + 4096)))
+        return rc;
 
     Params prm{};
     if (N > 0) prm = Params{params->means3D, params->scales, params->quats, params->opacities, params->sh0, params->shN};
@@ -249,9 +296,18 @@ int dvs_rast_forward(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, const 
         CK(launch_render_fwd(c, ctx->tile_base, ctx->plist, ctx->rec, out_color, ctx->final_T, ctx->n_contrib,
                              ctx->info, st));
         CK(cudaEventRecord(ctx->ev[5], st));
-        CK(cudaMemcpyAsync(ctx->h_info, ctx->info, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ctx->h_info, ctx->info, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(ctx->h_stats, ctx->stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        if (defer) {  // no host synchronisation: validated later by resolve_pending()
+            CK(cudaEventRecord(ctx->ev_check, st));
+            ctx->pending_check = true;
+            ctx->cam = c; ctx->N = N;
+            ctx->st.num_gaussians = N; ctx->st.tiles_x = c.gx; ctx->st.tiles_y = c.gy;
+            ctx->have_fwd = true; ctx->ev_fwd = true;
+            return DVS_OK;
+        }
         CK(cudaStreamSynchronize(st));
+        ctx->seen_overflows = ctx->h_info[3];
         if (!ctx->h_info[2]) break;
         // arena too small: grow to the exact need (+25%) and run the forward again
         ctx->st.overflow = 1;
@@ -262,11 +318,15 @@ int dvs_rast_forward(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, const 
     ctx->cam = c;
     ctx->N = N;
     ctx->st.num_gaussians = N;
-    ctx->st.num_visible = (int64_t)ctx->h_stats[0];
-    ctx->st.num_dups = (int64_t)ctx->h_info[0];
-    ctx->st.dup_capacity = ctx->cap_dups;
-    ctx->st.max_tile_len = ctx->h_info[1];
+    publish_stats(ctx);
     ctx->st.tiles_x = c.gx; ctx->st.tiles_y = c.gy;
+    // leave head-room so that slowly drifting parameters / other views do not overflow a deferred-check step
+    if (ctx->cap_dups < (int64_t)ctx->h_info[0] + (int64_t)ctx->h_info[0] / 2) {
+        // (arena contents are dead after the forward only if no backward follows; grow lazily at the next forward)
+        ctx->arena_sized = false;
+    } else {
+        ctx->arena_sized = true;
+    }
     ctx->have_fwd = true;
     ctx->ev_fwd = true;
     return DVS_OK;
@@ -275,6 +335,10 @@ int dvs_rast_forward(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, const 
 int dvs_rast_backward(dvs_rast_ctx* ctx, const dvs_params* params, const float* dL_dpix, const dvs_grads* grads,
                       uint32_t flags, void* stream) {
     if (!ctx) return DVS_E_INVALID;
+    {
+        int rcp = resolve_pending(ctx, false);
+        if (rcp) return rcp;
+    }
     if (!ctx->have_fwd) return fail(ctx, DVS_E_STATE, "backward without a forward on this context");
     if (!dL_dpix || !grads) return fail(ctx, DVS_E_INVALID, "null dL_dpix / grads");
     const Cam& c = ctx->cam;
@@ -340,14 +404,19 @@ int dvs_rast_step_host(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, cons
     return DVS_OK;
 }
 
-int dvs_rast_get_stats(const dvs_rast_ctx* ctx, dvs_stats* out) {
+int dvs_rast_get_stats(dvs_rast_ctx* ctx, dvs_stats* out) {
     if (!ctx || !out) return DVS_E_INVALID;
+    int rc = resolve_pending(ctx, true);  // blocking: this is where a deferred check is finally settled
     *out = ctx->st;
-    return DVS_OK;
+    return rc;
 }
 
 int dvs_rast_debug_read(dvs_rast_ctx* ctx, int which, void* dst, size_t dst_bytes) {
     if (!ctx || !dst) return DVS_E_INVALID;
+    {
+        int rcp = resolve_pending(ctx, true);
+        if (rcp) return rcp;
+    }
     if (!ctx->have_fwd) return fail(ctx, DVS_E_STATE, "no forward to read from");
     CK(cudaSetDevice(ctx->device));
     CK(cudaDeviceSynchronize());

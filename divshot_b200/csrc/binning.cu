@@ -128,7 +128,9 @@ tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint32_t* __res
         tile_base[T] = (uint32_t)carry;
         info[0] = (uint32_t)carry;
         info[1] = m;
-        info[2] = (carry > (unsigned long long)dup_capacity) ? 1u : 0u;
+        const bool ovf = carry > (unsigned long long)dup_capacity;
+        info[2] = ovf ? 1u : 0u;
+        if (ovf) { info[3] += 1u; info[9] = (uint32_t)min(carry, 0xffffffffull); }  // sticky (deferred-check mode)
     }
 }
 
@@ -335,15 +337,16 @@ __device__ uint32_t block_exclusive_scan(uint32_t* a, int len, uint32_t* s_part 
     return total;
 }
 
-template <int THREADS, int NMAX>
+// KEYS_IN_SMEM = false (long lists): the unsorted keys stay in the global bin (L2-resident, re-read three
+// times) so that two CTAs fit per SM.
+template <int THREADS, int NMAX, bool KEYS_IN_SMEM>
 __global__ void __launch_bounds__(THREADS)
 tile_bucket_sort_kernel(int T, int gx, int cls, const uint32_t* __restrict__ tile_base,
-                        const unsigned long long* __restrict__ bins, uint32_t* __restrict__ plist,
+                        unsigned long long* __restrict__ bins, uint32_t* __restrict__ plist,
                         const uint32_t* __restrict__ info, const uint32_t* __restrict__ class_tiles,
                         const float4* __restrict__ rec) {
     extern __shared__ unsigned long long s_keys[];
-    unsigned long long* A = s_keys;                        // [NMAX] keys as loaded
-    unsigned long long* tmp = A + NMAX;                    // [NMAX] keys grouped by fine bucket
+    unsigned long long* tmp = s_keys + (KEYS_IN_SMEM ? NMAX : 0);  // [NMAX] keys grouped by fine bucket
     uint32_t* eb = reinterpret_cast<uint32_t*>(tmp + NMAX);  // [NMAX] fine bucket | arrival rank << 16
     uint32_t* cnt2 = eb + NMAX;                            // [2*NMAX + 32] fine-bucket counts -> bases
     uint32_t* cnt1 = cnt2 + 2 * NMAX + 32;                 // [256]
@@ -361,11 +364,12 @@ tile_bucket_sort_kernel(int T, int gx, int cls, const uint32_t* __restrict__ til
         const uint32_t tile = class_tiles[(size_t)cls * T + ti];
         const uint32_t b0 = tile_base[tile];
         const int n = (int)(tile_base[tile + 1] - b0);
+        unsigned long long* A = KEYS_IN_SMEM ? s_keys : bins + b0;  // keys as emitted
         // phase 0: load, depth range
         uint32_t lmin = 0xffffffffu, lmax = 0u;
         for (int i = threadIdx.x; i < n; i += THREADS) {
             const unsigned long long k = bins[b0 + i];
-            A[i] = k;
+            if (KEYS_IN_SMEM) A[i] = k;
             const uint32_t d = (uint32_t)(k >> 32);
             lmin = min(lmin, d); lmax = max(lmax, d);
         }
@@ -493,9 +497,10 @@ tile_mask_kernel(int gx, const uint32_t* __restrict__ tile_base, uint32_t* __res
         plist[i] = entry_with_mask(plist[i] >> 8, rec, X0, Y0);
 }
 
-template <int NMAX>
+template <int NMAX, bool KEYS_IN_SMEM>
 constexpr size_t bucket_smem_bytes() {
-    return (size_t)NMAX * 8 * 2 + (size_t)NMAX * 4 + (size_t)(2 * NMAX + 32) * 4 + 256 * 4 * 4 + 260 * 4 + (size_t)NMAX * 2;
+    return (size_t)NMAX * 8 * (KEYS_IN_SMEM ? 2 : 1) + (size_t)NMAX * 4 + (size_t)(2 * NMAX + 32) * 4 + 256 * 4 * 4 +
+           260 * 4 + (size_t)NMAX * 2;
 }
 
 cudaError_t launch_tile_sort(int T, int gx, const uint32_t* tile_base, unsigned long long* bins, uint32_t* plist,
@@ -503,20 +508,23 @@ cudaError_t launch_tile_sort(int T, int gx, const uint32_t* tile_base, unsigned 
     if (T <= 0) return cudaSuccess;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(tile_bucket_sort_kernel<256, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)bucket_smem_bytes<1024>());
-        cudaFuncSetAttribute(tile_bucket_sort_kernel<512, 2048>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)bucket_smem_bytes<2048>());
-        cudaFuncSetAttribute(tile_bucket_sort_kernel<1024, 4096>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)bucket_smem_bytes<4096>());
+        cudaFuncSetAttribute(tile_bucket_sort_kernel<256, 1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)bucket_smem_bytes<1024, true>());
+        cudaFuncSetAttribute(tile_bucket_sort_kernel<512, 2048, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)bucket_smem_bytes<2048, true>());
+        cudaFuncSetAttribute(tile_bucket_sort_kernel<1024, 4096, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)bucket_smem_bytes<4096, false>());
         cudaFuncSetAttribute(tile_bitonic_sort_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              16384 * 8);
         attr_done = true;
     }
-    const int g_small = min(T, 148 * 6), g_mid = min(T, 148 * 3), g_big = min(T, 148);
-    tile_bucket_sort_kernel<256, 1024><<<g_small, 256, bucket_smem_bytes<1024>(), st>>>(T, gx, 0, tile_base, bins, plist, info, class_tiles, rec);
-    tile_bucket_sort_kernel<512, 2048><<<g_mid, 512, bucket_smem_bytes<2048>(), st>>>(T, gx, 1, tile_base, bins, plist, info, class_tiles, rec);
-    tile_bucket_sort_kernel<1024, 4096><<<g_big, 1024, bucket_smem_bytes<4096>(), st>>>(T, gx, 2, tile_base, bins, plist, info, class_tiles, rec);
+    const int g_small = min(T, 148 * 6), g_mid = min(T, 148 * 3), g_long = min(T, 148 * 2), g_big = min(T, 148);
+    tile_bucket_sort_kernel<256, 1024, true><<<g_small, 256, bucket_smem_bytes<1024, true>(), st>>>(
+        T, gx, 0, tile_base, bins, plist, info, class_tiles, rec);
+    tile_bucket_sort_kernel<512, 2048, true><<<g_mid, 512, bucket_smem_bytes<2048, true>(), st>>>(
+        T, gx, 1, tile_base, bins, plist, info, class_tiles, rec);
+    tile_bucket_sort_kernel<1024, 4096, false><<<g_long, 1024, bucket_smem_bytes<4096, false>(), st>>>(
+        T, gx, 2, tile_base, bins, plist, info, class_tiles, rec);
     tile_bitonic_sort_kernel<1024, true><<<g_big, 1024, 16384 * 8, st>>>(T, gx, 3, tile_base, bins, plist, info,
                                                                          class_tiles, rec);
     tile_bitonic_sort_kernel<1024, false><<<g_big, 1024, 0, st>>>(T, gx, 4, tile_base, bins, plist, info, class_tiles, rec);

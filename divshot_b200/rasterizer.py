@@ -102,8 +102,14 @@ class Rasterizer:
         self._check(self._lib.dvs_rast_reserve(self._h, N, width, height, dup_capacity))
 
     def forward(self, cam: _cabi.DvsCamera, params: dict, out_color: torch.Tensor | None = None,
-                out_radii: torch.Tensor | None = None):
+                out_radii: torch.Tensor | None = None, defer_check: bool = False):
+        """defer_check: no host synchronisation in the call (DVS_FLAG_DEFER_CHECK); a binning-arena overflow is then
+        raised by a later call (RasterizerError, code DVS_E_OVERFLOW) and the step must be redone."""
         N = params["means3D"].shape[0]
+        if defer_check != bool(cam.flags & _cabi.FLAG_DEFER_CHECK):
+            cam2 = _cabi.DvsCamera.from_buffer_copy(cam)
+            cam2.flags = (cam.flags | _cabi.FLAG_DEFER_CHECK) if defer_check else (cam.flags & ~_cabi.FLAG_DEFER_CHECK)
+            cam = cam2
         if out_color is None:
             out_color = torch.empty(3, cam.height, cam.width, dtype=torch.float32, device=self.device)
         if out_radii is None:

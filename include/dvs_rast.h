@@ -37,11 +37,16 @@ extern "C" {
 #define DVS_E_CUDA (-2)        /* a CUDA runtime call failed; see dvs_rast_last_error */
 #define DVS_E_NOMEM (-3)       /* arena allocation failed */
 #define DVS_E_STATE (-4)       /* backward without a matching forward, etc. */
-#define DVS_E_UNSUPPORTED (-5) /* N >= 2^24, image wider/taller than 4080 px, ... */
+#define DVS_E_UNSUPPORTED (-5) /* N >= 2^24, more than 2^24 tiles, ... */
+#define DVS_E_OVERFLOW (-6)    /* a forward run with DVS_FLAG_DEFER_CHECK overflowed the binning arena: its outputs
+                                  (and those of its backward) are invalid; the arena has been grown, redo the step */
 
 #define DVS_FLAG_INPUT_ACTIVATED 1u /* scales/quats/opacities already activated */
 #define DVS_FLAG_ACCUMULATE 2u      /* backward: add into the gradient buffers instead of overwriting */
 #define DVS_FLAG_ABSGRAD 4u         /* backward: also write sum|dL/dmean2D| (densify statistic, main.cpp:44-45) */
+#define DVS_FLAG_DEFER_CHECK 8u     /* forward: do not synchronise the stream to validate the binning arena; the check is
+                                       made by a later call (non-blocking) or by dvs_rast_get_stats (blocking).  Only
+                                       honoured once a synchronous forward has sized the arena. */
 
 typedef struct dvs_rast_ctx dvs_rast_ctx;
 
@@ -122,7 +127,9 @@ DVS_API int dvs_rast_reserve(dvs_rast_ctx* ctx, int64_t max_gaussians, int32_t m
  * Replaces the forward half of the absent gsplatrast operator.
  * Synchronises `stream` once at the end to validate the binning arena size (the credited
  * upstream synchronises mid-pipeline to read D back); on overflow the arena is grown and the
- * forward re-run transparently.
+ * forward re-run transparently.  With DVS_FLAG_DEFER_CHECK in cam->flags the call returns without any
+ * host synchronisation (a training loop keeps the GPU queue full); an overflow is then reported as
+ * DVS_E_OVERFLOW by a later call.
  */
 DVS_API int dvs_rast_forward(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, const dvs_params* params,
                              float* out_color, int32_t* out_radii, void* stream);
@@ -145,7 +152,7 @@ DVS_API int dvs_rast_step_host(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t
                                const dvs_grads* grads, const float* dL_dpix_host, float* out_color_host,
                                uint32_t bwd_flags, void* stream);
 
-DVS_API int dvs_rast_get_stats(const dvs_rast_ctx* ctx, dvs_stats* out);
+DVS_API int dvs_rast_get_stats(dvs_rast_ctx* ctx, dvs_stats* out);
 
 /* Copy an internal buffer of the last forward/backward to HOST memory (parity tests). */
 DVS_API int dvs_rast_debug_read(dvs_rast_ctx* ctx, int which, void* dst_host, size_t dst_bytes);

@@ -264,3 +264,32 @@ def test_gpu_gradients_vs_float64_autograd(rast):
     for k, name in [("means3D", "means3D"), ("scales", "scales"), ("quats", "quats"), ("opacities", "opac"),
                     ("sh0", "sh0"), ("shN", "shN")]:
         assert_close_robust(got["grads"][k], g[name].reshape(got["grads"][k].shape), TOL, f"dL_d{k} vs fp64 autograd")
+
+
+def test_deferred_check_mode_matches_and_reports_overflow(rast):
+    """DVS_FLAG_DEFER_CHECK: no host sync in the step; same results; an arena overflow is reported later."""
+    from divshot_b200.rasterizer import GradBuffers, Rasterizer, RasterizerError, scene_to_device
+    sc = make_scene(N=6000, width=128, height=96, sh_degree=1, seed=91)
+    r = Rasterizer(0)
+    try:
+        dev = r.device
+        params = scene_to_device(sc, dev)
+        cam = _cabi.make_camera(sc.cameras[0], 1)
+        dl = torch.from_numpy(sc.dL_dpix[0]).to(dev)
+        img0, _ = r.forward(cam, params)             # synchronous: sizes the arena
+        g0 = GradBuffers.allocate(sc.N, 3, dev); r.backward(dl, g0)
+        img0b, _ = r.forward(cam, params)            # second synchronous forward (head-room growth)
+        for _ in range(3):
+            img1, _ = r.forward(cam, params, defer_check=True)
+            g1 = GradBuffers.allocate(sc.N, 3, dev); r.backward(dl, g1)
+        assert torch.equal(img0, img1) and rel_err(g1.flat.cpu().numpy(), g0.flat.cpu().numpy()) < 5e-5
+        assert r.stats()["num_dups"] > 0
+        # blow the splats up: D grows far beyond the sized arena -> overflow must be reported, then a redo works
+        big = dict(params); big["scales"] = params["scales"] + 3.0
+        r.forward(cam, big, defer_check=True)
+        with pytest.raises(RasterizerError, match="-6|redo the step"):
+            r.stats()
+        img2, _ = r.forward(cam, big)                # synchronous redo
+        assert torch.isfinite(img2).all() and r.stats()["overflow"] in (0, 1)
+    finally:
+        r.close()
