@@ -196,8 +196,11 @@ def main():
         if world > 1:
             reducer.all_reduce()
 
+    cam_defer = _cabi.DvsCamera.from_buffer_copy(cam)
+    cam_defer.flags |= _cabi.FLAG_DEFER_CHECK
+
     def step_e2e():
-        rast.step_host(cam, params, grads, dl_host, img_host)
+        rast.step_host(cam_defer, params, grads, dl_host, img_host)
         if world > 1:
             reducer.all_reduce()
 

@@ -391,6 +391,8 @@ int dvs_rast_step_host(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, cons
                        ctx->copy_stream));
     CK(cudaEventRecord(ctx->ev_h2d, ctx->copy_stream));
     if ((rc = dvs_rast_forward(ctx, cam, N, params, ctx->d_image, nullptr, stream))) return rc;
+    // (with DVS_FLAG_DEFER_CHECK in cam->flags the forward above did not synchronise; the blocking settle of the
+    //  arena check happens below, after the whole step has been queued)
     // D2H of the image on the copy stream (overlaps the backward)
     CK(cudaEventRecord(ctx->ev_img, st));
     CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_img, 0));
@@ -401,7 +403,7 @@ int dvs_rast_step_host(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, cons
     if ((rc = dvs_rast_backward(ctx, params, ctx->h2d_grad, grads, bwd_flags, stream))) return rc;
     CK(cudaStreamWaitEvent(st, ctx->ev_d2h, 0));
     CK(cudaStreamSynchronize(st));
-    return DVS_OK;
+    return resolve_pending(ctx, true);  // DVS_E_OVERFLOW if a deferred-check forward overflowed (redo the step)
 }
 
 int dvs_rast_get_stats(dvs_rast_ctx* ctx, dvs_stats* out) {

@@ -168,28 +168,42 @@ emit_kernel(int gx, int N, const uint4* __restrict__ aux, uint32_t* __restrict__
         if (lane >= off) incl += n;
     }
     const int total = __shfl_sync(0xffffffffu, incl, 31);
-    for (int j0 = 0; j0 < total; j0 += 32) {
-        const int j = j0 + lane;
-        // source lane = number of lanes whose inclusive offset is <= j (binary search over the sorted offsets)
-        int pos = 0;
+    // EMIT_UNROLL items per lane per trip: all their slot-claiming atomics are issued before the first
+    // dependent store, so several L2 round trips overlap (one atomic in flight per warp otherwise)
+    constexpr int EMIT_UNROLL = 4;
+    for (int j0 = 0; j0 < total; j0 += 32 * EMIT_UNROLL) {
+        uint32_t slot[EMIT_UNROLL];
+        unsigned long long key[EMIT_UNROLL];
+        bool ok[EMIT_UNROLL];
 #pragma unroll
-        for (int step = 16; step > 0; step >>= 1) {
-            const int v = __shfl_sync(0xffffffffu, incl, pos + step - 1);
-            if (v <= j) pos += step;
+        for (int u = 0; u < EMIT_UNROLL; u++) {
+            const int j = j0 + 32 * u + lane;
+            // source lane = number of lanes whose inclusive offset is <= j (binary search over the sorted offsets)
+            int pos = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const int v = __shfl_sync(0xffffffffu, incl, pos + step - 1);
+                if (v <= j) pos += step;
+            }
+            const int src = min(pos, 31);
+            const int s_incl = __shfl_sync(0xffffffffu, incl, src);
+            const int s_area = __shfl_sync(0xffffffffu, area, src);
+            const int s_minx = __shfl_sync(0xffffffffu, minx, src), s_miny = __shfl_sync(0xffffffffu, miny, src);
+            const int s_w = __shfl_sync(0xffffffffu, w, src);
+            const uint32_t s_depth = __shfl_sync(0xffffffffu, ax.z, src);
+            const int s_id = __shfl_sync(0xffffffffu, i, src);
+            ok[u] = j < total;
+            slot[u] = 0xffffffffu;
+            key[u] = ((unsigned long long)s_depth << 32) | (uint32_t)s_id;
+            if (ok[u]) {
+                const int k = j - (s_incl - s_area);
+                const int ty = s_miny + k / s_w, tx = s_minx + k % s_w;
+                slot[u] = atomicAdd(tile_cursor + (size_t)(ty * gx + tx) * TILE_CTR_STRIDE, 1u);
+            }
         }
-        const int src = min(pos, 31);
-        const int s_incl = __shfl_sync(0xffffffffu, incl, src);
-        const int s_area = __shfl_sync(0xffffffffu, area, src);
-        const int s_minx = __shfl_sync(0xffffffffu, minx, src), s_miny = __shfl_sync(0xffffffffu, miny, src);
-        const int s_w = __shfl_sync(0xffffffffu, w, src);
-        const uint32_t s_depth = __shfl_sync(0xffffffffu, ax.z, src);
-        const int s_id = __shfl_sync(0xffffffffu, i, src);
-        if (j < total) {
-            const int k = j - (s_incl - s_area);
-            const int ty = s_miny + k / s_w, tx = s_minx + k % s_w;
-            const uint32_t slot = atomicAdd(tile_cursor + (size_t)(ty * gx + tx) * TILE_CTR_STRIDE, 1u);
-            if (slot < cap) bins[slot] = ((unsigned long long)s_depth << 32) | (uint32_t)s_id;
-        }
+#pragma unroll
+        for (int u = 0; u < EMIT_UNROLL; u++)
+            if (ok[u] && slot[u] < cap) bins[slot[u]] = key[u];
     }
 }
 

@@ -138,6 +138,11 @@ render_bwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const uint32_
     if (cmax == 0) return;
     const uint32_t wbit = 1u << warp;
     int nbuf = 0;
+    // per-lane row addresses of the phase-1 buffer, kept in registers (no re-derivation from tid per pair)
+    uint32_t myS = wbase + RbSmem::S + lane * 4, myW = wbase + RbSmem::W + lane * 4;
+    uint32_t mmeta = wbase + RbSmem::meta;
+    asm volatile("" : "+r"(myS), "+r"(myW), "+r"(mmeta));
+    const bool lane0 = lane == 0;
 
     // staging is software-pipelined: while a round is being walked, the next round's entry words and records
     // are already in flight into registers of the first RB_ROUND threads
@@ -208,10 +213,10 @@ render_bwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const uint32_
                     dL_dalpha = fmaf(dL_dalpha, T, nTf_bg * rinv);
                     s = a_raw * dL_dalpha;  // dL/dpower (the 0.99 clamp is straight-through)
                 }
-                sts_f1(wbase + RbSmem::S + (nbuf * RB_ROW + lane) * 4, s);
-                sts_f1(wbase + RbSmem::W + (nbuf * RB_ROW + lane) * 4, wgt);
-                if (lane == 0) {
-                    const uint32_t mrow = wbase + RbSmem::meta + nbuf * 32;
+                sts_f1(myS + nbuf * (RB_ROW * 4), s);
+                sts_f1(myW + nbuf * (RB_ROW * 4), wgt);
+                if (lane0) {
+                    const uint32_t mrow = mmeta + nbuf * 32;
                     sts_u1(mrow, lds_u1(se + k * 4) >> 8);
                     sts_f1(mrow + 4, q0.x);
                     sts_f1(mrow + 8, q0.y);

@@ -114,6 +114,8 @@ def test_libtorch_custom_class_matches_c_abi():
     g = GradBuffers.allocate(sc.N, 8, dev)
     ref.backward(dl, g)
     assert torch.equal(img.detach(), rimg) and torch.equal(radii, rradii)
+    from util import rel_err
     for k in ("means3D", "scales", "quats", "opacities", "sh0", "shN"):
         a, b = leaves[k].grad, getattr(g, k)
-        assert torch.allclose(a, b, rtol=1e-4, atol=1e-6 * float(b.abs().max())), k
+        # two runs of the same kernels: only the order of the fp32 atomics differs
+        assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 5e-5, k

@@ -26,6 +26,13 @@ red.all_reduce()
 torch.cuda.synchronize()
 err = float((red.flat - ref).abs().max() / ref.abs().max())
 t_nvls = red._time(dev, reps=10)
+sweep = {}
+for ctas in (148, 296, 592, 1184):
+    red.ctas = ctas
+    sweep[ctas] = round(red._time(dev, reps=10), 3)
+red.ctas = 0
+if rank == 0:
+    print("nvls ms by CTA count:", sweep)
 red.backend = "nccl"
 t_nccl = red._time(dev, reps=10)
 if rank == 0:
