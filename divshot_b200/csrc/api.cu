@@ -289,7 +289,7 @@ int dvs_rast_forward(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, const 
         CK(launch_tile_scan((int)T, ctx->tile_count, ctx->tile_base, ctx->tile_cursor, ctx->info,
                             (uint32_t)ctx->cap_dups, ctx->class_tiles, st));
         CK(cudaEventRecord(ctx->ev[2], st));
-        CK(launch_emit(c, (int)N, ctx->aux, ctx->tile_cursor, ctx->bins, (uint32_t)ctx->cap_dups, st));
+        CK(launch_emit(c, (int)N, ctx->aux, ctx->rec, ctx->tile_cursor, ctx->bins, (uint32_t)ctx->cap_dups, st));
         CK(cudaEventRecord(ctx->ev[3], st));
         CK(launch_tile_sort((int)T, c.gx, ctx->tile_base, ctx->bins, ctx->plist, ctx->info, ctx->class_tiles, ctx->rec, st));
         CK(cudaEventRecord(ctx->ev[4], st));

@@ -4,12 +4,14 @@
 // the absent gsplatrast operator with a CUB-free design:
 //   * per-tile counts come from the preprocess kernel (RED per (Gaussian,tile));
 //   * one CTA scans the T counts with warp-shuffle prefix sums -> tile_base (= `ranges`);
-//   * emission claims a slot in its tile's bin with one atomic and writes an 8-byte entry depth_bits<<32 | id;
+//   * emission claims a slot in its tile's bin with one atomic and writes an 8-byte entry
+//       depth_bits<<32 | id<<8 | submask
+//     where submask says which of the tile's eight 8x4-pixel sub-rectangles the splat's {alpha >= 1/255}
+//     ellipse can reach (ours, used by A6/A7 to skip work; it never changes the lists);
 //   * one CTA per tile sorts its bin in shared memory (adaptive two-level bucket sort; bitonic network as
-//     the always-exact fallback) and writes id<<8 | submask to plist, where submask says which of the
-//     tile's eight 8x4-pixel sub-rectangles the splat's {alpha >= 1/255} ellipse can reach (ours, used by
-//     A6/A7 to skip work; it never changes the lists).
-// Sorting the 64-bit entry ascending == the credited total order (tile, depth bits, Gaussian index).
+//     the always-exact fallback) and writes the low word (id<<8 | submask) to plist.
+// Sorting the 64-bit entry ascending == the credited total order (tile, depth bits, Gaussian index), because
+// within a tile ids are unique and the mask sits below the id.
 // The order of arrival in a bin is non-deterministic; the sort makes the output deterministic.
 //
 // Roofline: HBM-light (8 B written + 8 B read + 4 B written per duplicate); sort is shared-memory /
@@ -144,16 +146,70 @@ cudaError_t launch_tile_scan(int T, const uint32_t* tile_count, uint32_t* tile_b
 }
 
 // ---------------------------------------------------------------------------------------------
+// Sub-tile cull mask (ours; no upstream analogue).  For the entry (tile, Gaussian): which of the tile's
+// eight 8x4-pixel sub-rectangles (bit w: x in [16tx+8(w&1), +7], y in [16ty+4(w>>1), +3]) can hold a
+// pixel with alpha >= 1/255, i.e. Q(d) = a dx^2 + b dx dy + c dy^2 <= m for some d = mean - pixel in the
+// box, with (a,b,c) = -(A2,B2,C2) and m = lo - log2(1/255) (+ a small conservative margin).  Q is convex
+// with its minimum at d = 0, so the box minimum is on the edges facing the origin:
+//   q = min( Q(ex, clamp(-b ex / 2c)),  Q(clamp(-b ey / 2a), ey) ),  (ex, ey) = box point nearest to 0
+// evaluated branch-free for all 8 boxes (2 column ranges x 4 row ranges).  It is computed at emission —
+// that kernel is bound by the L2 atomic rate and has ~80 % of its issue slots free — and rides in the low
+// byte of the sort key, below the Gaussian id.
+// ---------------------------------------------------------------------------------------------
+struct CullParams {  // per Gaussian
+    float mx, my, a, b, c, m, hbc, hba;
+};
+__device__ __forceinline__ CullParams cull_params(const float4 q0, const float4 q1) {
+    CullParams p;
+    p.mx = q0.x; p.my = q0.y;
+    p.a = -q0.z; p.b = -q0.w; p.c = -q1.x;
+    p.m = (q1.y - ALPHA_MIN_LOG2) * 1.0001f + 1e-3f;
+    const bool ok = p.a > 0.0f && p.c > 0.0f;
+    p.hbc = ok ? __fdividef(-0.5f * p.b, p.c) : 0.0f;
+    p.hba = ok ? __fdividef(-0.5f * p.b, p.a) : 0.0f;
+    if (!ok) p.m = 3.0e38f;  // degenerate conic: no culling (every box passes)
+    return p;
+}
+__device__ __forceinline__ uint32_t sub_tile_mask(const CullParams& g, float X0, float Y0) {
+    if (!(g.m > 0.0f)) return 0u;  // opacity < 1/255: never contributes
+    const float mx = g.mx - X0, my = g.my - Y0;  // mean relative to the tile origin
+    uint32_t mask = 0;
+    float dxlo[2], dxhi[2], exn[2];
+#pragma unroll
+    for (int cx = 0; cx < 2; cx++) {  // d = mean - pixel, pixel x in [8cx, 8cx+7]
+        dxhi[cx] = mx - (float)(8 * cx);
+        dxlo[cx] = dxhi[cx] - 7.0f;
+        exn[cx] = fminf(fmaxf(0.0f, dxlo[cx]), dxhi[cx]);
+    }
+#pragma unroll
+    for (int ry = 0; ry < 4; ry++) {
+        const float dyhi = my - (float)(4 * ry), dylo = dyhi - 3.0f;
+        const float eyn = fminf(fmaxf(0.0f, dylo), dyhi);
+        const float dxs = g.hba * eyn;  // unclamped minimiser along the horizontal edge
+#pragma unroll
+        for (int cx = 0; cx < 2; cx++) {
+            const float ex = exn[cx];
+            const float dy = fminf(fmaxf(g.hbc * ex, dylo), dyhi);
+            const float q1v = fmaf(g.a * ex, ex, fmaf(g.b, ex, g.c * dy) * dy);
+            const float dx = fminf(fmaxf(dxs, dxlo[cx]), dxhi[cx]);
+            const float q2v = fmaf(g.c * eyn, eyn, fmaf(g.b, eyn, g.a * dx) * dx);
+            if (fminf(q1v, q2v) <= g.m) mask |= 1u << (2 * ry + cx);
+        }
+    }
+    return mask;
+}
+
+// ---------------------------------------------------------------------------------------------
 // A3: emission.  Warp-cooperative: the 32 Gaussians of a warp flatten their tile rects into one work
 // list (warp-shuffle prefix scan of the duplication counts) and every lane takes every 32nd item, so a
-// big splat does not serialise its warp (upstream's per-thread loop does).  Reads only the 16-byte aux
-// word (rect + depth key); writes depth_bits<<32 | id.
+// big splat does not serialise its warp (upstream's per-thread loop does).  Writes
+// depth_bits<<32 | id<<8 | sub-tile mask.
 // ---------------------------------------------------------------------------------------------
 constexpr int EMIT_THREADS = 256;
 
 __global__ void __launch_bounds__(EMIT_THREADS)
-emit_kernel(int gx, int N, const uint4* __restrict__ aux, uint32_t* __restrict__ tile_cursor,
-            unsigned long long* __restrict__ bins, uint32_t cap) {
+emit_kernel(int gx, int N, const uint4* __restrict__ aux, const float4* __restrict__ rec,
+            uint32_t* __restrict__ tile_cursor, unsigned long long* __restrict__ bins, uint32_t cap) {
     const int i = blockIdx.x * EMIT_THREADS + threadIdx.x;
     const int lane = threadIdx.x & 31;
     uint4 ax = make_uint4(0, 0, 0, 0);
@@ -161,6 +217,8 @@ emit_kernel(int gx, int N, const uint4* __restrict__ aux, uint32_t* __restrict__
     const int minx = ax.x & 0xffff, miny = ax.x >> 16;
     const int w = (int)(ax.y & 0xffff) - minx, h = (int)((ax.y >> 16) & 0x1fff) - miny;
     const int area = (w > 0 && h > 0) ? w * h : 0;
+    CullParams cp = {0.f, 0.f, 1.f, 0.f, 1.f, -1.f, 0.f, 0.f};
+    if (area > 0) cp = cull_params(__ldg(rec + 3 * (size_t)i), __ldg(rec + 3 * (size_t)i + 1));
     int incl = area;  // inclusive warp scan of the duplication counts
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -170,7 +228,7 @@ emit_kernel(int gx, int N, const uint4* __restrict__ aux, uint32_t* __restrict__
     const int total = __shfl_sync(0xffffffffu, incl, 31);
     // EMIT_UNROLL items per lane per trip: all their slot-claiming atomics are issued before the first
     // dependent store, so several L2 round trips overlap (one atomic in flight per warp otherwise)
-    constexpr int EMIT_UNROLL = 4;
+    constexpr int EMIT_UNROLL = 2;
     for (int j0 = 0; j0 < total; j0 += 32 * EMIT_UNROLL) {
         uint32_t slot[EMIT_UNROLL];
         unsigned long long key[EMIT_UNROLL];
@@ -192,13 +250,21 @@ emit_kernel(int gx, int N, const uint4* __restrict__ aux, uint32_t* __restrict__
             const int s_w = __shfl_sync(0xffffffffu, w, src);
             const uint32_t s_depth = __shfl_sync(0xffffffffu, ax.z, src);
             const int s_id = __shfl_sync(0xffffffffu, i, src);
+            CullParams g;
+            g.mx = __shfl_sync(0xffffffffu, cp.mx, src); g.my = __shfl_sync(0xffffffffu, cp.my, src);
+            g.a = __shfl_sync(0xffffffffu, cp.a, src); g.b = __shfl_sync(0xffffffffu, cp.b, src);
+            g.c = __shfl_sync(0xffffffffu, cp.c, src); g.m = __shfl_sync(0xffffffffu, cp.m, src);
+            g.hbc = __shfl_sync(0xffffffffu, cp.hbc, src); g.hba = __shfl_sync(0xffffffffu, cp.hba, src);
             ok[u] = j < total;
             slot[u] = 0xffffffffu;
-            key[u] = ((unsigned long long)s_depth << 32) | (uint32_t)s_id;
+            key[u] = 0ull;
             if (ok[u]) {
                 const int k = j - (s_incl - s_area);
                 const int ty = s_miny + k / s_w, tx = s_minx + k % s_w;
                 slot[u] = atomicAdd(tile_cursor + (size_t)(ty * gx + tx) * TILE_CTR_STRIDE, 1u);
+                // the mask computation overlaps the atomic's round trip
+                const uint32_t m8 = sub_tile_mask(g, (float)(tx * TILE), (float)(ty * TILE));
+                key[u] = ((unsigned long long)s_depth << 32) | (((uint32_t)s_id << 8) | m8);
             }
         }
 #pragma unroll
@@ -207,58 +273,12 @@ emit_kernel(int gx, int N, const uint4* __restrict__ aux, uint32_t* __restrict__
     }
 }
 
-cudaError_t launch_emit(const Cam& cam, int N, const uint4* aux, uint32_t* tile_cursor, unsigned long long* bins,
-                        uint32_t dup_capacity, cudaStream_t st) {
+cudaError_t launch_emit(const Cam& cam, int N, const uint4* aux, const float4* rec, uint32_t* tile_cursor,
+                        unsigned long long* bins, uint32_t dup_capacity, cudaStream_t st) {
     if (N <= 0) return cudaSuccess;
-    emit_kernel<<<(N + EMIT_THREADS - 1) / EMIT_THREADS, EMIT_THREADS, 0, st>>>(cam.gx, N, aux, tile_cursor, bins,
-                                                                                 dup_capacity);
+    emit_kernel<<<(N + EMIT_THREADS - 1) / EMIT_THREADS, EMIT_THREADS, 0, st>>>(cam.gx, N, aux, rec, tile_cursor,
+                                                                                 bins, dup_capacity);
     return cudaGetLastError();
-}
-
-// ---------------------------------------------------------------------------------------------
-// Sub-tile cull mask (ours; no upstream analogue).  For the sorted entry (tile, Gaussian): which of the
-// tile's eight 8x4-pixel sub-rectangles (bit w: x in [16tx+8(w&1), +7], y in [16ty+4(w>>1), +3]) can hold a
-// pixel with alpha >= 1/255, i.e. Q(d) = -(A2 dx^2 + B2 dx dy + C2 dy^2) <= lo - log2(1/255) for some d in
-// the box.  Q is convex with its minimum at d = 0, so the box minimum is on the edges facing the origin:
-//   q = min( Q(ex, clamp(-b ex / 2c)),  Q(clamp(-b ey / 2a), ey) ),  (ex, ey) = box point nearest to 0
-// evaluated branch-free for all 8 boxes (2 column ranges x 4 row ranges).  Conservative by a small margin
-// w.r.t. the per-pixel test of the compositing kernels; computed once per sorted entry, one thread each.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t mask_from_record(uint32_t id, const float4 q0, const float4 q1, float X0,
-                                                     float Y0) {
-    const float mx = q0.x - X0, my = q0.y - Y0;  // mean relative to the tile origin
-    const float a = -q0.z, b = -q0.w, c = -q1.x;
-    const float m = (q1.y - ALPHA_MIN_LOG2) * 1.0001f + 1e-3f;
-    if (!(m > 0.0f)) return id << 8;                       // opacity < 1/255: never contributes
-    if (!(a > 0.0f && c > 0.0f)) return (id << 8) | 0xffu;  // degenerate conic: no culling
-    const float hbc = __fdividef(-0.5f * b, c), hba = __fdividef(-0.5f * b, a);
-    uint32_t mask = 0;
-    float dxlo[2], dxhi[2], exn[2];
-#pragma unroll
-    for (int cx = 0; cx < 2; cx++) {  // d = mean - pixel, pixel x in [8cx, 8cx+7]
-        dxhi[cx] = mx - (float)(8 * cx);
-        dxlo[cx] = dxhi[cx] - 7.0f;
-        exn[cx] = fminf(fmaxf(0.0f, dxlo[cx]), dxhi[cx]);
-    }
-#pragma unroll
-    for (int ry = 0; ry < 4; ry++) {
-        const float dyhi = my - (float)(4 * ry), dylo = dyhi - 3.0f;
-        const float eyn = fminf(fmaxf(0.0f, dylo), dyhi);
-        const float dxs = hba * eyn;  // unclamped minimiser along the horizontal edge
-#pragma unroll
-        for (int cx = 0; cx < 2; cx++) {
-            const float ex = exn[cx];
-            const float dy = fminf(fmaxf(hbc * ex, dylo), dyhi);
-            const float q1v = fmaf(a * ex, ex, fmaf(b, ex, c * dy) * dy);
-            const float dx = fminf(fmaxf(dxs, dxlo[cx]), dxhi[cx]);
-            const float q2v = fmaf(c * eyn, eyn, fmaf(b, eyn, a * dx) * dx);
-            if (fminf(q1v, q2v) <= m) mask |= 1u << (2 * ry + cx);
-        }
-    }
-    return (id << 8) | mask;
-}
-__device__ __forceinline__ uint32_t entry_with_mask(uint32_t id, const float4* __restrict__ rec, float X0, float Y0) {
-    return mask_from_record(id, __ldg(rec + 3 * (size_t)id), __ldg(rec + 3 * (size_t)id + 1), X0, Y0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -442,7 +462,7 @@ tile_bucket_sort_kernel(int T, int gx, int cls, const uint32_t* __restrict__ til
         const bool crowded = __syncthreads_or(mx > RANK_MAX);
         if (crowded) {
             bitonic_sort_u64<THREADS>(A, n);
-            for (int i = threadIdx.x; i < n; i += THREADS) plist[b0 + i] = (uint32_t)A[i] << 8;
+            for (int i = threadIdx.x; i < n; i += THREADS) plist[b0 + i] = (uint32_t)A[i];
             __syncthreads();
             continue;
         }
@@ -456,15 +476,14 @@ tile_bucket_sort_kernel(int T, int gx, int cls, const uint32_t* __restrict__ til
             eb2[pos] = (uint16_t)b2;
         }
         __syncthreads();
-        // phase 6: rank inside the fine bucket by the full key, write the sorted list (id<<8; the sub-tile mask
-        // is OR-ed in by tile_mask_kernel, which runs at full occupancy)
+        // phase 6: rank inside the fine bucket by the full key, write the sorted list (low word = id<<8 | mask)
         for (int p = threadIdx.x; p < n; p += THREADS) {
             const unsigned long long k = tmp[p];
             const uint32_t b2 = eb2[p];
             const uint32_t s0 = cnt2[b2], s1 = cnt2[b2 + 1];
             uint32_t rank = 0;
             for (uint32_t q = s0; q < s1; q++) rank += tmp[q] < k ? 1u : 0u;
-            plist[b0 + s0 + rank] = (uint32_t)k << 8;
+            plist[b0 + s0 + rank] = (uint32_t)k;
         }
         __syncthreads();
     }
@@ -489,26 +508,14 @@ tile_bitonic_sort_kernel(int T, int gx, int cls, const uint32_t* __restrict__ ti
             for (uint32_t t = threadIdx.x; t < n; t += THREADS) s_keys[t] = g[t];
             __syncthreads();
             bitonic_sort_u64<THREADS>(s_keys, (int)n);
-            for (uint32_t t = threadIdx.x; t < n; t += THREADS) plist[b0 + t] = (uint32_t)s_keys[t] << 8;
+            for (uint32_t t = threadIdx.x; t < n; t += THREADS) plist[b0 + t] = (uint32_t)s_keys[t];
         } else {
             __syncthreads();
             bitonic_sort_u64<THREADS>(g, (int)n);  // rare: > 16384 entries in one tile
-            for (uint32_t t = threadIdx.x; t < n; t += THREADS) plist[b0 + t] = (uint32_t)g[t] << 8;
+            for (uint32_t t = threadIdx.x; t < n; t += THREADS) plist[b0 + t] = (uint32_t)g[t];
         }
         __syncthreads();
     }
-}
-
-// One CTA per tile, one thread per sorted entry: OR the sub-tile mask into plist (id<<8 -> id<<8 | mask).
-constexpr int MASK_THREADS = 256;
-__global__ void __launch_bounds__(MASK_THREADS)
-tile_mask_kernel(int gx, const uint32_t* __restrict__ tile_base, uint32_t* __restrict__ plist,
-                 const uint32_t* __restrict__ info, const float4* __restrict__ rec) {
-    if (info[2]) return;
-    const uint32_t b0 = tile_base[blockIdx.x], b1 = tile_base[blockIdx.x + 1];
-    const float X0 = (float)((blockIdx.x % gx) * TILE), Y0 = (float)((blockIdx.x / gx) * TILE);
-    for (uint32_t i = b0 + threadIdx.x; i < b1; i += MASK_THREADS)
-        plist[i] = entry_with_mask(plist[i] >> 8, rec, X0, Y0);
 }
 
 template <int NMAX, bool KEYS_IN_SMEM>
@@ -542,7 +549,6 @@ cudaError_t launch_tile_sort(int T, int gx, const uint32_t* tile_base, unsigned 
     tile_bitonic_sort_kernel<1024, true><<<g_big, 1024, 16384 * 8, st>>>(T, gx, 3, tile_base, bins, plist, info,
                                                                          class_tiles, rec);
     tile_bitonic_sort_kernel<1024, false><<<g_big, 1024, 0, st>>>(T, gx, 4, tile_base, bins, plist, info, class_tiles, rec);
-    tile_mask_kernel<<<T, MASK_THREADS, 0, st>>>(gx, tile_base, plist, info, rec);
     return cudaGetLastError();
 }
 

@@ -18,8 +18,8 @@ cudaError_t launch_tile_scan(int T, const uint32_t* tile_count, uint32_t* tile_b
                              uint32_t* info, uint32_t dup_capacity, uint32_t* class_tiles, cudaStream_t st);
 
 // A3: emit (depth | id | sub-tile mask) entries into per-tile bins
-cudaError_t launch_emit(const Cam& cam, int N, const uint4* aux, uint32_t* tile_cursor, unsigned long long* bins,
-                        uint32_t dup_capacity, cudaStream_t st);
+cudaError_t launch_emit(const Cam& cam, int N, const uint4* aux, const float4* rec, uint32_t* tile_cursor,
+                        unsigned long long* bins, uint32_t dup_capacity, cudaStream_t st);
 
 // A4: tile-local sort (CUB-free) -> plist (id<<8 | mask), tile-major
 cudaError_t launch_tile_sort(int T, int gx, const uint32_t* tile_base, unsigned long long* bins, uint32_t* plist,
