@@ -281,7 +281,8 @@ def main():
                    "visible": V, "duplicates": D, "tiles": T, "max_tile_len": st["max_tile_len"],
                    "l2": "inputs larger than L2 (params+grads 472 MB + 96 MB records/lists per step); no explicit flush",
                    "parallelism": f"dp{world} (view-sharded replicas)",
-                   "host_sync": "none per step (binning arena validated by deferred check, DVS_FLAG_DEFER_CHECK)"},
+                   "host_sync": "none per step (binning arena validated by deferred check, DVS_FLAG_DEFER_CHECK; "
+                                "single-pass binning into fixed-stride tile bins sized by the warm-up forwards)"},
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": dom_gbs, "peak": peak, "unit": "GB/s",
                      "frac": dom_gbs / peak, "traffic": None, "peak_source": peak_src,
                      "note": "algorithmic bytes per SURVEY.md §8(d) / CUDA-event stage time; compositing is issue-bound"},
@@ -292,7 +293,7 @@ def main():
                 "d2h_bytes_per_step": 12 * P * world, "ms_per_step": ms_e2e / args.steps,
                 "api": "dvs_rast_step_host (C-ABI): pinned dL/dpix H2D, forward, image D2H, backward; parameters and "
                        "gradients device-resident as in the trainer"},
-        "gpu_launches": 11 * args.steps,
+        "gpu_launches": 10 * args.steps,
         "allreduce": ({"backend": reducer.backend, "note": reducer.note, "bytes": int(reducer.flat.numel()) * 4, "ms": ms_ar,
                        "busbw_GBps": (2 * (world - 1) / world * reducer.flat.numel() * 4 / 1e9 / (ms_ar * 1e-3))}
                       if world > 1 else None),

@@ -9,6 +9,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -33,9 +34,13 @@ struct dvs_rast_ctx {
     uint32_t* tile_cursor = nullptr;
     uint32_t* class_tiles = nullptr;  // [5][T] per-sort-class tile lists
     // per-duplicate
-    int64_t cap_dups = 0;
+    int64_t cap_dups = 0;   // entries plist (and, in two-pass mode, bins) can hold
+    int64_t cap_bins = 0;   // entries of the bins arena (>= cap_dups; >= T * bin_stride in single-pass mode)
     unsigned long long* bins = nullptr;
     uint32_t* plist = nullptr;
+    // single-pass binning (only with DVS_FLAG_DEFER_CHECK): fixed per-tile bin stride sized by the last synchronous forward
+    uint32_t bin_stride = 0;
+    int64_t bin_stride_tiles = 0;
     // per-pixel
     int64_t cap_pix = 0;
     float* final_T = nullptr;
@@ -109,9 +114,18 @@ static int ensure_tiles(dvs_rast_ctx* ctx, int64_t T) {
 static int ensure_dups(dvs_rast_ctx* ctx, int64_t D) {
     if (D <= ctx->cap_dups) return DVS_OK;
     if (D >= (int64_t)0xffffffffll) return fail(ctx, DVS_E_UNSUPPORTED, "duplicate count %lld exceeds 2^32", (long long)D);
-    CK(regrow(ctx->bins, (size_t)D));
+    if (D > ctx->cap_bins) {
+        CK(regrow(ctx->bins, (size_t)D));
+        ctx->cap_bins = D;
+    }
     CK(regrow(ctx->plist, (size_t)D));
     ctx->cap_dups = D;
+    return DVS_OK;
+}
+static int ensure_bins(dvs_rast_ctx* ctx, int64_t entries) {
+    if (entries <= ctx->cap_bins) return DVS_OK;
+    CK(regrow(ctx->bins, (size_t)entries));
+    ctx->cap_bins = entries;
     return DVS_OK;
 }
 static int ensure_pix(dvs_rast_ctx* ctx, int64_t P) {
@@ -275,23 +289,39 @@ int dvs_rast_forward(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, const 
     if (!ctx->arena_sized && ctx->st.num_dups > 0 && !ctx->pending_check &&
         (rc = ensure_dups(ctx, ctx->st.num_dups + ctx->st.num_dups / 2 + 4096)))
         return rc;
+    if (!ctx->pending_check && ctx->bin_stride > 0 && ctx->bin_stride_tiles == T &&
+        (rc = ensure_bins(ctx, (int64_t)ctx->bin_stride * T)))
+        return rc;
 
     Params prm{};
     if (N > 0) prm = Params{params->means3D, params->scales, params->quats, params->opacities, params->sh0, params->shN};
     ctx->have_fwd = false;
     ctx->st.overflow = 0;
+    // single-pass binning: only in deferred-check mode, with a bin stride sized by an earlier synchronous forward
+    // of the same tile grid (an overflowing bin is reported like an arena overflow: DVS_E_OVERFLOW, redo the step)
+    const bool fused = defer && ctx->bin_stride > 0 && ctx->bin_stride_tiles == T &&
+                       (int64_t)ctx->bin_stride * T <= ctx->cap_bins && !getenv("DVS_TWO_PASS");
     for (int attempt = 0; attempt < 3; attempt++) {
-        CK(cudaMemsetAsync(ctx->tile_count, 0, (size_t)T * TILE_CTR_STRIDE * sizeof(uint32_t), st));
+        CK(cudaMemsetAsync(fused ? ctx->tile_cursor : ctx->tile_count, 0, (size_t)T * TILE_CTR_STRIDE * sizeof(uint32_t), st));
         CK(cudaMemsetAsync(ctx->stats, 0, 2 * sizeof(unsigned long long), st));
+        CK(cudaMemsetAsync(ctx->info + 10, 0, sizeof(uint32_t), st));
         CK(cudaEventRecord(ctx->ev[0], st));
-        CK(launch_preprocess_fwd(c, (int)N, prm, ctx->rec, ctx->aux, ctx->tile_count, out_radii, ctx->stats, st));
+        const FusedEmit fe{ctx->tile_cursor, ctx->bins, fused ? ctx->bin_stride : 0u, ctx->info + 10};
+        CK(launch_preprocess_fwd(c, (int)N, prm, ctx->rec, ctx->aux, ctx->tile_count, out_radii, ctx->stats, fe, st));
         CK(cudaEventRecord(ctx->ev[1], st));
-        CK(launch_tile_scan((int)T, ctx->tile_count, ctx->tile_base, ctx->tile_cursor, ctx->info,
-                            (uint32_t)ctx->cap_dups, ctx->class_tiles, st));
-        CK(cudaEventRecord(ctx->ev[2], st));
-        CK(launch_emit(c, (int)N, ctx->aux, ctx->rec, ctx->tile_cursor, ctx->bins, (uint32_t)ctx->cap_dups, st));
+        if (fused) {
+            CK(launch_tile_scan((int)T, ctx->tile_cursor, ctx->tile_base, nullptr, ctx->info, (uint32_t)ctx->cap_dups,
+                                ctx->class_tiles, st));
+            CK(cudaEventRecord(ctx->ev[2], st));
+        } else {
+            CK(launch_tile_scan((int)T, ctx->tile_count, ctx->tile_base, ctx->tile_cursor, ctx->info,
+                                (uint32_t)ctx->cap_dups, ctx->class_tiles, st));
+            CK(cudaEventRecord(ctx->ev[2], st));
+            CK(launch_emit(c, (int)N, ctx->aux, ctx->rec, ctx->tile_cursor, ctx->bins, (uint32_t)ctx->cap_dups, st));
+        }
         CK(cudaEventRecord(ctx->ev[3], st));
-        CK(launch_tile_sort((int)T, c.gx, ctx->tile_base, ctx->bins, ctx->plist, ctx->info, ctx->class_tiles, ctx->rec, st));
+        CK(launch_tile_sort((int)T, fused ? ctx->bin_stride : 0u, ctx->tile_base, ctx->bins, ctx->plist, ctx->info,
+                            ctx->class_tiles, st));
         CK(cudaEventRecord(ctx->ev[4], st));
         CK(launch_render_fwd(c, ctx->tile_base, ctx->plist, ctx->rec, out_color, ctx->final_T, ctx->n_contrib,
                              ctx->info, st));
@@ -320,6 +350,17 @@ int dvs_rast_forward(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, const 
     ctx->st.num_gaussians = N;
     publish_stats(ctx);
     ctx->st.tiles_x = c.gx; ctx->st.tiles_y = c.gy;
+    // size the fixed per-tile bin stride for single-pass binning of later deferred-check forwards
+    {
+        const int64_t stride = ((int64_t)ctx->h_info[1] * 3 / 2 + 64 + 63) / 64 * 64;
+        const int64_t want = stride * T;
+        if (want <= 4 * (int64_t)ctx->h_info[0] + (16 << 20)) {  // skewed scenes (one huge tile) stay two-pass
+            ctx->bin_stride = (uint32_t)stride;
+            ctx->bin_stride_tiles = T;
+        } else {
+            ctx->bin_stride = 0;
+        }
+    }
     // leave head-room so that slowly drifting parameters / other views do not overflow a deferred-check step
     if (ctx->cap_dups < (int64_t)ctx->h_info[0] + (int64_t)ctx->h_info[0] / 2) {
         // (arena contents are dead after the forward only if no backward follows; grow lazily at the next forward)

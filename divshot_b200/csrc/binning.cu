@@ -17,6 +17,7 @@
 // Roofline: HBM-light (8 B written + 8 B read + 4 B written per duplicate); sort is shared-memory /
 // issue bound.  Algorithmic bytes per SURVEY.md §8(d): 28 B per duplicate (we move 20).
 #include "common.cuh"
+#include "emit.cuh"
 #include "kernels.h"
 
 namespace dvs {
@@ -36,7 +37,8 @@ constexpr int SCAN_MAX_PER_THREAD = 8;  // register-blocked fast path for T <= 8
 
 __global__ void __launch_bounds__(SCAN_THREADS)
 tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_base,
-                 uint32_t* __restrict__ tile_cursor, uint32_t* __restrict__ info, uint32_t dup_capacity,
+                 uint32_t* __restrict__ tile_cursor /* nullptr: single-pass mode, counts ARE the cursors */,
+                 uint32_t* __restrict__ info, uint32_t dup_capacity,
                  uint32_t* __restrict__ class_tiles /* [NUM_SORT_CLASSES][T] */) {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t warp_max[32];
@@ -107,7 +109,7 @@ tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint32_t* __res
             const int t = first + k;
             if (t < T) {
                 tile_base[t] = run;
-                tile_cursor[(size_t)t * TILE_CTR_STRIDE] = run;
+                if (tile_cursor) tile_cursor[(size_t)t * TILE_CTR_STRIDE] = run;
                 if (c[k]) {
                     const int cls = sort_class_of(c[k]);
 #pragma unroll
@@ -130,7 +132,7 @@ tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint32_t* __res
         tile_base[T] = (uint32_t)carry;
         info[0] = (uint32_t)carry;
         info[1] = m;
-        const bool ovf = carry > (unsigned long long)dup_capacity;
+        const bool ovf = carry > (unsigned long long)dup_capacity || info[10] != 0u;  // info[10]: a fixed-stride bin overflowed
         info[2] = ovf ? 1u : 0u;
         if (ovf) { info[3] += 1u; info[9] = (uint32_t)min(carry, 0xffffffffull); }  // sticky (deferred-check mode)
     }
@@ -146,64 +148,8 @@ cudaError_t launch_tile_scan(int T, const uint32_t* tile_count, uint32_t* tile_b
 }
 
 // ---------------------------------------------------------------------------------------------
-// Sub-tile cull mask (ours; no upstream analogue).  For the entry (tile, Gaussian): which of the tile's
-// eight 8x4-pixel sub-rectangles (bit w: x in [16tx+8(w&1), +7], y in [16ty+4(w>>1), +3]) can hold a
-// pixel with alpha >= 1/255, i.e. Q(d) = a dx^2 + b dx dy + c dy^2 <= m for some d = mean - pixel in the
-// box, with (a,b,c) = -(A2,B2,C2) and m = lo - log2(1/255) (+ a small conservative margin).  Q is convex
-// with its minimum at d = 0, so the box minimum is on the edges facing the origin:
-//   q = min( Q(ex, clamp(-b ex / 2c)),  Q(clamp(-b ey / 2a), ey) ),  (ex, ey) = box point nearest to 0
-// evaluated branch-free for all 8 boxes (2 column ranges x 4 row ranges).  It is computed at emission —
-// that kernel is bound by the L2 atomic rate and has ~80 % of its issue slots free — and rides in the low
-// byte of the sort key, below the Gaussian id.
-// ---------------------------------------------------------------------------------------------
-struct CullParams {  // per Gaussian
-    float mx, my, a, b, c, m, hbc, hba;
-};
-__device__ __forceinline__ CullParams cull_params(const float4 q0, const float4 q1) {
-    CullParams p;
-    p.mx = q0.x; p.my = q0.y;
-    p.a = -q0.z; p.b = -q0.w; p.c = -q1.x;
-    p.m = (q1.y - ALPHA_MIN_LOG2) * 1.0001f + 1e-3f;
-    const bool ok = p.a > 0.0f && p.c > 0.0f;
-    p.hbc = ok ? __fdividef(-0.5f * p.b, p.c) : 0.0f;
-    p.hba = ok ? __fdividef(-0.5f * p.b, p.a) : 0.0f;
-    if (!ok) p.m = 3.0e38f;  // degenerate conic: no culling (every box passes)
-    return p;
-}
-__device__ __forceinline__ uint32_t sub_tile_mask(const CullParams& g, float X0, float Y0) {
-    if (!(g.m > 0.0f)) return 0u;  // opacity < 1/255: never contributes
-    const float mx = g.mx - X0, my = g.my - Y0;  // mean relative to the tile origin
-    uint32_t mask = 0;
-    float dxlo[2], dxhi[2], exn[2];
-#pragma unroll
-    for (int cx = 0; cx < 2; cx++) {  // d = mean - pixel, pixel x in [8cx, 8cx+7]
-        dxhi[cx] = mx - (float)(8 * cx);
-        dxlo[cx] = dxhi[cx] - 7.0f;
-        exn[cx] = fminf(fmaxf(0.0f, dxlo[cx]), dxhi[cx]);
-    }
-#pragma unroll
-    for (int ry = 0; ry < 4; ry++) {
-        const float dyhi = my - (float)(4 * ry), dylo = dyhi - 3.0f;
-        const float eyn = fminf(fmaxf(0.0f, dylo), dyhi);
-        const float dxs = g.hba * eyn;  // unclamped minimiser along the horizontal edge
-#pragma unroll
-        for (int cx = 0; cx < 2; cx++) {
-            const float ex = exn[cx];
-            const float dy = fminf(fmaxf(g.hbc * ex, dylo), dyhi);
-            const float q1v = fmaf(g.a * ex, ex, fmaf(g.b, ex, g.c * dy) * dy);
-            const float dx = fminf(fmaxf(dxs, dxlo[cx]), dxhi[cx]);
-            const float q2v = fmaf(g.c * eyn, eyn, fmaf(g.b, eyn, g.a * dx) * dx);
-            if (fminf(q1v, q2v) <= g.m) mask |= 1u << (2 * ry + cx);
-        }
-    }
-    return mask;
-}
-
-// ---------------------------------------------------------------------------------------------
-// A3: emission.  Warp-cooperative: the 32 Gaussians of a warp flatten their tile rects into one work
-// list (warp-shuffle prefix scan of the duplication counts) and every lane takes every 32nd item, so a
-// big splat does not serialise its warp (upstream's per-thread loop does).  Writes
-// depth_bits<<32 | id<<8 | sub-tile mask.
+// A3: emission (two-pass mode).  The warp-cooperative emission itself lives in emit.cuh and is shared with the
+// fused single-pass mode of preprocess_fwd.cu.
 // ---------------------------------------------------------------------------------------------
 constexpr int EMIT_THREADS = 256;
 
@@ -211,7 +157,6 @@ __global__ void __launch_bounds__(EMIT_THREADS)
 emit_kernel(int gx, int N, const uint4* __restrict__ aux, const float4* __restrict__ rec,
             uint32_t* __restrict__ tile_cursor, unsigned long long* __restrict__ bins, uint32_t cap) {
     const int i = blockIdx.x * EMIT_THREADS + threadIdx.x;
-    const int lane = threadIdx.x & 31;
     uint4 ax = make_uint4(0, 0, 0, 0);
     if (i < N) ax = __ldg(aux + i);
     const int minx = ax.x & 0xffff, miny = ax.x >> 16;
@@ -219,58 +164,7 @@ emit_kernel(int gx, int N, const uint4* __restrict__ aux, const float4* __restri
     const int area = (w > 0 && h > 0) ? w * h : 0;
     CullParams cp = {0.f, 0.f, 1.f, 0.f, 1.f, -1.f, 0.f, 0.f};
     if (area > 0) cp = cull_params(__ldg(rec + 3 * (size_t)i), __ldg(rec + 3 * (size_t)i + 1));
-    int incl = area;  // inclusive warp scan of the duplication counts
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        const int n = __shfl_up_sync(0xffffffffu, incl, off);
-        if (lane >= off) incl += n;
-    }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    // EMIT_UNROLL items per lane per trip: all their slot-claiming atomics are issued before the first
-    // dependent store, so several L2 round trips overlap (one atomic in flight per warp otherwise)
-    constexpr int EMIT_UNROLL = 2;
-    for (int j0 = 0; j0 < total; j0 += 32 * EMIT_UNROLL) {
-        uint32_t slot[EMIT_UNROLL];
-        unsigned long long key[EMIT_UNROLL];
-        bool ok[EMIT_UNROLL];
-#pragma unroll
-        for (int u = 0; u < EMIT_UNROLL; u++) {
-            const int j = j0 + 32 * u + lane;
-            // source lane = number of lanes whose inclusive offset is <= j (binary search over the sorted offsets)
-            int pos = 0;
-#pragma unroll
-            for (int step = 16; step > 0; step >>= 1) {
-                const int v = __shfl_sync(0xffffffffu, incl, pos + step - 1);
-                if (v <= j) pos += step;
-            }
-            const int src = min(pos, 31);
-            const int s_incl = __shfl_sync(0xffffffffu, incl, src);
-            const int s_area = __shfl_sync(0xffffffffu, area, src);
-            const int s_minx = __shfl_sync(0xffffffffu, minx, src), s_miny = __shfl_sync(0xffffffffu, miny, src);
-            const int s_w = __shfl_sync(0xffffffffu, w, src);
-            const uint32_t s_depth = __shfl_sync(0xffffffffu, ax.z, src);
-            const int s_id = __shfl_sync(0xffffffffu, i, src);
-            CullParams g;
-            g.mx = __shfl_sync(0xffffffffu, cp.mx, src); g.my = __shfl_sync(0xffffffffu, cp.my, src);
-            g.a = __shfl_sync(0xffffffffu, cp.a, src); g.b = __shfl_sync(0xffffffffu, cp.b, src);
-            g.c = __shfl_sync(0xffffffffu, cp.c, src); g.m = __shfl_sync(0xffffffffu, cp.m, src);
-            g.hbc = __shfl_sync(0xffffffffu, cp.hbc, src); g.hba = __shfl_sync(0xffffffffu, cp.hba, src);
-            ok[u] = j < total;
-            slot[u] = 0xffffffffu;
-            key[u] = 0ull;
-            if (ok[u]) {
-                const int k = j - (s_incl - s_area);
-                const int ty = s_miny + k / s_w, tx = s_minx + k % s_w;
-                slot[u] = atomicAdd(tile_cursor + (size_t)(ty * gx + tx) * TILE_CTR_STRIDE, 1u);
-                // the mask computation overlaps the atomic's round trip
-                const uint32_t m8 = sub_tile_mask(g, (float)(tx * TILE), (float)(ty * TILE));
-                key[u] = ((unsigned long long)s_depth << 32) | (((uint32_t)s_id << 8) | m8);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < EMIT_UNROLL; u++)
-            if (ok[u] && slot[u] < cap) bins[slot[u]] = key[u];
-    }
+    warp_emit(gx, i, minx, miny, w, area, ax.z, cp, tile_cursor, bins, /*bin_stride=*/0u, cap, nullptr);
 }
 
 cudaError_t launch_emit(const Cam& cam, int N, const uint4* aux, const float4* rec, uint32_t* tile_cursor,
@@ -375,10 +269,9 @@ __device__ uint32_t block_exclusive_scan(uint32_t* a, int len, uint32_t* s_part 
 // times) so that two CTAs fit per SM.
 template <int THREADS, int NMAX, bool KEYS_IN_SMEM>
 __global__ void __launch_bounds__(THREADS)
-tile_bucket_sort_kernel(int T, int gx, int cls, const uint32_t* __restrict__ tile_base,
-                        unsigned long long* __restrict__ bins, uint32_t* __restrict__ plist,
-                        const uint32_t* __restrict__ info, const uint32_t* __restrict__ class_tiles,
-                        const float4* __restrict__ rec) {
+tile_bucket_sort_kernel(int T, uint32_t bin_stride, int cls, const uint32_t* __restrict__ tile_base,
+                        unsigned long long* __restrict__ bins_all, uint32_t* __restrict__ plist,
+                        const uint32_t* __restrict__ info, const uint32_t* __restrict__ class_tiles) {
     extern __shared__ unsigned long long s_keys[];
     unsigned long long* tmp = s_keys + (KEYS_IN_SMEM ? NMAX : 0);  // [NMAX] keys grouped by fine bucket
     uint32_t* eb = reinterpret_cast<uint32_t*>(tmp + NMAX);  // [NMAX] fine bucket | arrival rank << 16
@@ -398,11 +291,12 @@ tile_bucket_sort_kernel(int T, int gx, int cls, const uint32_t* __restrict__ til
         const uint32_t tile = class_tiles[(size_t)cls * T + ti];
         const uint32_t b0 = tile_base[tile];
         const int n = (int)(tile_base[tile + 1] - b0);
-        unsigned long long* A = KEYS_IN_SMEM ? s_keys : bins + b0;  // keys as emitted
+        unsigned long long* bins = bins_all + (bin_stride ? (size_t)tile * bin_stride : (size_t)b0);  // this tile's bin
+        unsigned long long* A = KEYS_IN_SMEM ? s_keys : bins;  // keys as emitted
         // phase 0: load, depth range
         uint32_t lmin = 0xffffffffu, lmax = 0u;
         for (int i = threadIdx.x; i < n; i += THREADS) {
-            const unsigned long long k = bins[b0 + i];
+            const unsigned long long k = bins[i];
             if (KEYS_IN_SMEM) A[i] = k;
             const uint32_t d = (uint32_t)(k >> 32);
             lmin = min(lmin, d); lmax = max(lmax, d);
@@ -492,10 +386,9 @@ tile_bucket_sort_kernel(int T, int gx, int cls, const uint32_t* __restrict__ til
 // bitonic classes (long lists): shared memory up to 16384 entries, else in place in global/L2
 template <int THREADS, bool IN_SMEM>
 __global__ void __launch_bounds__(THREADS)
-tile_bitonic_sort_kernel(int T, int gx, int cls, const uint32_t* __restrict__ tile_base,
+tile_bitonic_sort_kernel(int T, uint32_t bin_stride, int cls, const uint32_t* __restrict__ tile_base,
                          unsigned long long* __restrict__ bins, uint32_t* __restrict__ plist,
-                         const uint32_t* __restrict__ info, const uint32_t* __restrict__ class_tiles,
-                         const float4* __restrict__ rec) {
+                         const uint32_t* __restrict__ info, const uint32_t* __restrict__ class_tiles) {
     extern __shared__ unsigned long long s_keys[];
     if (info[2]) return;
     const uint32_t ntiles = info[4 + cls];
@@ -503,7 +396,7 @@ tile_bitonic_sort_kernel(int T, int gx, int cls, const uint32_t* __restrict__ ti
         const uint32_t tile = class_tiles[(size_t)cls * T + ti];
         const uint32_t b0 = tile_base[tile];
         const uint32_t n = tile_base[tile + 1] - b0;
-        unsigned long long* g = bins + b0;
+        unsigned long long* g = bins + (bin_stride ? (size_t)tile * bin_stride : (size_t)b0);
         if (IN_SMEM) {
             for (uint32_t t = threadIdx.x; t < n; t += THREADS) s_keys[t] = g[t];
             __syncthreads();
@@ -524,8 +417,8 @@ constexpr size_t bucket_smem_bytes() {
            260 * 4 + (size_t)NMAX * 2;
 }
 
-cudaError_t launch_tile_sort(int T, int gx, const uint32_t* tile_base, unsigned long long* bins, uint32_t* plist,
-                             const uint32_t* info, const uint32_t* class_tiles, const float4* rec, cudaStream_t st) {
+cudaError_t launch_tile_sort(int T, uint32_t bin_stride, const uint32_t* tile_base, unsigned long long* bins,
+                             uint32_t* plist, const uint32_t* info, const uint32_t* class_tiles, cudaStream_t st) {
     if (T <= 0) return cudaSuccess;
     static bool attr_done = false;
     if (!attr_done) {
@@ -540,15 +433,11 @@ cudaError_t launch_tile_sort(int T, int gx, const uint32_t* tile_base, unsigned 
         attr_done = true;
     }
     const int g_small = min(T, 148 * 6), g_mid = min(T, 148 * 3), g_long = min(T, 148 * 2), g_big = min(T, 148);
-    tile_bucket_sort_kernel<256, 1024, true><<<g_small, 256, bucket_smem_bytes<1024, true>(), st>>>(
-        T, gx, 0, tile_base, bins, plist, info, class_tiles, rec);
-    tile_bucket_sort_kernel<512, 2048, true><<<g_mid, 512, bucket_smem_bytes<2048, true>(), st>>>(
-        T, gx, 1, tile_base, bins, plist, info, class_tiles, rec);
-    tile_bucket_sort_kernel<1024, 4096, false><<<g_long, 1024, bucket_smem_bytes<4096, false>(), st>>>(
-        T, gx, 2, tile_base, bins, plist, info, class_tiles, rec);
-    tile_bitonic_sort_kernel<1024, true><<<g_big, 1024, 16384 * 8, st>>>(T, gx, 3, tile_base, bins, plist, info,
-                                                                         class_tiles, rec);
-    tile_bitonic_sort_kernel<1024, false><<<g_big, 1024, 0, st>>>(T, gx, 4, tile_base, bins, plist, info, class_tiles, rec);
+    tile_bucket_sort_kernel<256, 1024, true><<<g_small, 256, bucket_smem_bytes<1024, true>(), st>>>(T, bin_stride, 0, tile_base, bins, plist, info, class_tiles);
+    tile_bucket_sort_kernel<512, 2048, true><<<g_mid, 512, bucket_smem_bytes<2048, true>(), st>>>(T, bin_stride, 1, tile_base, bins, plist, info, class_tiles);
+    tile_bucket_sort_kernel<1024, 4096, false><<<g_long, 1024, bucket_smem_bytes<4096, false>(), st>>>(T, bin_stride, 2, tile_base, bins, plist, info, class_tiles);
+    tile_bitonic_sort_kernel<1024, true><<<g_big, 1024, 16384 * 8, st>>>(T, bin_stride, 3, tile_base, bins, plist, info, class_tiles);
+    tile_bitonic_sort_kernel<1024, false><<<g_big, 1024, 0, st>>>(T, bin_stride, 4, tile_base, bins, plist, info, class_tiles);
     return cudaGetLastError();
 }
 

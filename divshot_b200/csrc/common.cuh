@@ -62,6 +62,14 @@ struct Grads {
     float* mean2D;
 };
 
+// single-pass binning (fused into preprocess_fwd): tile t owns bins[t * bin_stride ..); bin_stride == 0 -> two-pass
+struct FusedEmit {
+    uint32_t* tile_cursor;
+    unsigned long long* bins;
+    uint32_t bin_stride;
+    uint32_t* overflow_word;
+};
+
 // ---- small PTX wrappers -------------------------------------------------------------------
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;

@@ -10,7 +10,7 @@ namespace dvs {
 // A1 (+ per-tile duplicate counts)
 cudaError_t launch_preprocess_fwd(const Cam& cam, int N, const Params& prm, float4* rec, uint4* aux,
                                   uint32_t* tile_count, int32_t* out_radii, unsigned long long* stats,
-                                  cudaStream_t st);
+                                  const FusedEmit& fe, cudaStream_t st);
 
 // A2/A5: exclusive scan of tile counts -> tile_base[T+1], cursor[T]; info[0]=D, info[1]=max len, info[2]=overflow,
 // info[4..8] = tiles per sort class, class_tiles[5][T] = their ids
@@ -22,8 +22,8 @@ cudaError_t launch_emit(const Cam& cam, int N, const uint4* aux, const float4* r
                         unsigned long long* bins, uint32_t dup_capacity, cudaStream_t st);
 
 // A4: tile-local sort (CUB-free) -> plist (id<<8 | mask), tile-major
-cudaError_t launch_tile_sort(int T, int gx, const uint32_t* tile_base, unsigned long long* bins, uint32_t* plist,
-                             const uint32_t* info, const uint32_t* class_tiles, const float4* rec, cudaStream_t st);
+cudaError_t launch_tile_sort(int T, uint32_t bin_stride, const uint32_t* tile_base, unsigned long long* bins,
+                             uint32_t* plist, const uint32_t* info, const uint32_t* class_tiles, cudaStream_t st);
 
 // A6
 cudaError_t launch_render_fwd(const Cam& cam, const uint32_t* tile_base, const uint32_t* plist, const float4* rec,

@@ -14,6 +14,7 @@
 // for visible ones.  One thread per Gaussian for the geometry; the 12*(K-1)-byte SH row is
 // staged per warp through shared memory with 128-bit coalesced loads.
 #include "common.cuh"
+#include "emit.cuh"
 #include "kernels.h"
 
 namespace dvs {
@@ -88,7 +89,7 @@ template <int DEG>
 __global__ void __launch_bounds__(PF_THREADS)
 preprocess_fwd_kernel(Cam cam, int N, Params prm, float4* __restrict__ rec, uint4* __restrict__ aux,
                       uint32_t* __restrict__ tile_count, int32_t* __restrict__ out_radii,
-                      unsigned long long* __restrict__ stats /* [0]=V, [1]=D */) {
+                      unsigned long long* __restrict__ stats /* [0]=V, [1]=D */, FusedEmit fe) {
     constexpr int K = (DEG + 1) * (DEG + 1);
     extern __shared__ __align__(128) unsigned char pf_smem[];
     const int KR = cam.KR;
@@ -297,10 +298,17 @@ preprocess_fwd_kernel(Cam cam, int N, Params prm, float4* __restrict__ rec, uint
             if (out_radii) out_radii[i] = s_radii[lane];
         }
     }
-    // per-tile duplicate counts (RED, no return); overlaps the bulk stores
-    if (visible)
+    if (fe.bin_stride) {
+        // single-pass binning: emit the duplicates right here (the slot-claiming atomic is also the count);
+        // the tile bins have a fixed stride sized from an earlier forward (see api.cu)
+        const CullParams cp = cull_params(q0, q1);
+        warp_emit(cam.gx, i, minx, miny, maxx - minx, visible ? (int)tiles : 0, __float_as_uint(q2.y), cp,
+                  fe.tile_cursor, fe.bins, fe.bin_stride, 0u, fe.overflow_word);
+    } else if (visible) {
+        // two-pass binning: per-tile duplicate counts (RED, no return); overlaps the bulk stores
         for (int y = miny; y < maxy; y++)
             for (int x = minx; x < maxx; x++) atomicAdd(tile_count + (size_t)(y * cam.gx + x) * TILE_CTR_STRIDE, 1u);
+    }
     // stats: V and D
     const unsigned vm = __ballot_sync(0xffffffffu, visible);
     uint32_t tsum = tiles;
@@ -315,7 +323,7 @@ preprocess_fwd_kernel(Cam cam, int N, Params prm, float4* __restrict__ rec, uint
 
 cudaError_t launch_preprocess_fwd(const Cam& cam, int N, const Params& prm, float4* rec, uint4* aux,
                                   uint32_t* tile_count, int32_t* out_radii, unsigned long long* stats,
-                                  cudaStream_t st) {
+                                  const FusedEmit& fe, cudaStream_t st) {
     if (N <= 0) return cudaSuccess;
     const int grid = (N + PF_THREADS - 1) / PF_THREADS;
     const size_t smem = 64 + (size_t)PF_WARPS * PfLayout(3 * cam.KR).total;
@@ -325,7 +333,7 @@ cudaError_t launch_preprocess_fwd(const Cam& cam, int N, const Params& prm, floa
             cudaFuncSetAttribute(preprocess_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                  (int)smem);                                                              \
         preprocess_fwd_kernel<D><<<grid, PF_THREADS, smem, st>>>(cam, N, prm, rec, aux, tile_count,       \
-                                                                  out_radii, stats);                      \
+                                                                  out_radii, stats, fe);                  \
     } while (0)
     switch (cam.deg) {
         case 0: DVS_LAUNCH_PF(0); break;

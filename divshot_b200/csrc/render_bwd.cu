@@ -124,7 +124,7 @@ render_bwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const uint32_
     sts_f1(wbase + RbSmem::dp + 256 + lane * 4, dp2);
     const float nTf_bg = -T_final * (cam.bg[0] * dp0 + cam.bg[1] * dp1 + cam.bg[2] * dp2);
     float T = T_final;
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
 
     uint32_t wmax = last;
 #pragma unroll
@@ -202,14 +202,15 @@ render_bwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const uint32_
                     T = T * rinv;
                     wgt = alpha * T;
                     const float cb = lds_f1(ea + 32);
-                    acc0 = fmaf(last_alpha, lc0 - acc0, acc0);
-                    acc1 = fmaf(last_alpha, lc1 - acc1, acc1);
-                    acc2 = fmaf(last_alpha, lc2 - acc2, acc2);
-                    lc0 = q1.z; lc1 = q1.w; lc2 = cb;
-                    float dL_dalpha = (lc0 - acc0) * dp0;
-                    dL_dalpha = fmaf(lc1 - acc1, dp1, dL_dalpha);
-                    dL_dalpha = fmaf(lc2 - acc2, dp2, dL_dalpha);
-                    last_alpha = alpha;
+                    // R = colour accumulated behind this splat (what upstream calls accum_rec at the time of use);
+                    // dL/dalpha = sum_ch (c - R) dL/dpix, then R <- alpha c + (1 - alpha) R = R + alpha (c - R)
+                    const float d0 = q1.z - acc0, d1 = q1.w - acc1, d2 = cb - acc2;
+                    float dL_dalpha = d0 * dp0;
+                    dL_dalpha = fmaf(d1, dp1, dL_dalpha);
+                    dL_dalpha = fmaf(d2, dp2, dL_dalpha);
+                    acc0 = fmaf(alpha, d0, acc0);
+                    acc1 = fmaf(alpha, d1, acc1);
+                    acc2 = fmaf(alpha, d2, acc2);
                     dL_dalpha = fmaf(dL_dalpha, T, nTf_bg * rinv);
                     s = a_raw * dL_dalpha;  // dL/dpower (the 0.99 clamp is straight-through)
                 }

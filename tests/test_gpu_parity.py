@@ -284,6 +284,15 @@ def test_deferred_check_mode_matches_and_reports_overflow(rast):
             g1 = GradBuffers.allocate(sc.N, 3, dev); r.backward(dl, g1)
         assert torch.equal(img0, img1) and rel_err(g1.flat.cpu().numpy(), g0.flat.cpu().numpy()) < 5e-5
         assert r.stats()["num_dups"] > 0
+        # deferred steps use single-pass binning (fixed-stride tile bins): the sorted lists must not change
+        r.forward(cam, params); pl_sync = r.debug_read(_cabi.BUF_POINT_LIST); rg_sync = r.debug_read(_cabi.BUF_RANGES)
+        mk_sync = r.debug_read(_cabi.BUF_CULL_MASK)
+        r.forward(cam, params, defer_check=True)
+        assert np.array_equal(r.debug_read(_cabi.BUF_POINT_LIST), pl_sync)
+        assert np.array_equal(r.debug_read(_cabi.BUF_RANGES), rg_sync)
+        assert np.array_equal(r.debug_read(_cabi.BUF_CULL_MASK), mk_sync)
+        f, _ = _oracle(sc, bwd=False)
+        assert np.array_equal(pl_sync, f.point_list)
         # blow the splats up: D grows far beyond the sized arena -> overflow must be reported, then a redo works
         big = dict(params); big["scales"] = params["scales"] + 3.0
         r.forward(cam, big, defer_check=True)
