@@ -7,8 +7,8 @@
 //   * same tiling / sub-tile masks as the forward: warp w owns an 8x4-pixel sub-rectangle and only touches
 //     splats whose footprint reaches it and that lie in front of the warp's deepest last-contributor;
 //   * PHASE 1 (lane = pixel): the reverse walk proper.  Per (pixel, splat) pair only two numbers are
-//     produced: s = dL/dpower and w = alpha*T (colour weight).  They go to a per-warp shared-memory buffer
-//     S[slot][pixel], W[slot][pixel] (16 splats deep) — no cross-lane reduction here;
+//     produced: s = dL/dpower and w = alpha*T (colour weight).  They go, as one 64-bit store, to a per-warp
+//     shared-memory buffer SW[slot][pixel] (16 splats deep) — no cross-lane reduction here;
 //   * PHASE 2 (lane = splat x pixel-half): every 16 buffered splats the lanes switch roles.  Lane (k, h)
 //     walks 16 of the 32 pixels for splat k and accumulates the nine sums
 //         S0 = sum s, Sx = sum s dx, Sy = sum s dy, Sxx, Sxy, Syy, and sum w*dL/dpix[0..2]
@@ -34,11 +34,10 @@ struct RbSmem {
     static constexpr int ent = stage + RB_ROUND * 48;            // RB_ROUND * 4
     static constexpr int wmax = ent + RB_ROUND * 4;              // 8 * 4
     static constexpr int warp0 = wmax + 64;                      // per-warp region start
-    static constexpr int S = 0;                                  // RB_NB * RB_ROW * 4
-    static constexpr int W = S + RB_NB * RB_ROW * 4;             // RB_NB * RB_ROW * 4
-    static constexpr int meta = W + RB_NB * RB_ROW * 4;          // RB_NB * 8 words {id, mx, my, A, B, C, -, -}
-    static constexpr int dp = meta + RB_NB * 8 * 4;              // 3 * 32 * 4
-    static constexpr int per_warp = dp + 3 * 32 * 4;
+    static constexpr int SW = 0;                                 // RB_NB * RB_ROW float2 {s, w} per (slot, pixel)
+    static constexpr int meta = SW + RB_NB * RB_ROW * 8;         // RB_NB * 8 words {id, mx, my, A, B, C, -, -}
+    static constexpr int dp = meta + RB_NB * 8 * 4;              // 32 float4 {dL/dpix r, g, b, -}
+    static constexpr int per_warp = dp + 32 * 16;
     static constexpr int total = warp0 + (RB_THREADS / 32) * per_warp;
 };
 
@@ -54,22 +53,30 @@ __device__ __forceinline__ void rb_phase2(uint32_t wbase, int nbuf, int lane, fl
     if (ABSGRAD) { cA = lds_f1(mrow + 12); cB = lds_f1(mrow + 16); cC = lds_f1(mrow + 20); }
     float S0 = 0.f, Sx = 0.f, Sy = 0.f, Sxx = 0.f, Sxy = 0.f, Syy = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
     float ax = 0.f, ay = 0.f;
-    const uint32_t srow = wbase + RbSmem::S + (k * RB_ROW + 16 * h) * 4;
-    const uint32_t wrow = wbase + RbSmem::W + (k * RB_ROW + 16 * h) * 4;
-    const uint32_t dpb = wbase + RbSmem::dp + 16 * h * 4;
+    const uint32_t swrow = wbase + RbSmem::SW + (k * RB_ROW + 16 * h) * 8;
+    const uint32_t dpb = wbase + RbSmem::dp + 16 * h * 16;
+    // 16 pixels of my half: 4 groups of 4 consecutive pixels (same row of the 8x4 sub-rectangle); the inner
+    // group is unrolled, the outer loop is not (keeps the kernel at 64 registers without spills)
+#pragma unroll 1
+    for (int jo = 0; jo < 4; jo++) {
+        const float Xg = X - (float)((4 * jo) & 7), dy = Y - (float)(jo >> 1);
 #pragma unroll
-    for (int j = 0; j < 16; j++) {
-        const float s = lds_f1(srow + 4 * j), w = lds_f1(wrow + 4 * j);
-        const float dx = X - (float)(j & 7), dy = Y - (float)(j >> 3);
-        const float sdx = s * dx, sdy = s * dy;
-        S0 += s; Sx += sdx; Sy += sdy;
-        Sxx = fmaf(sdx, dx, Sxx); Sxy = fmaf(sdx, dy, Sxy); Syy = fmaf(sdy, dy, Syy);
-        c0 = fmaf(w, lds_f1(dpb + 4 * j), c0);
-        c1 = fmaf(w, lds_f1(dpb + 128 + 4 * j), c1);
-        c2 = fmaf(w, lds_f1(dpb + 256 + 4 * j), c2);
-        if (ABSGRAD) {
-            ax += fabsf(fmaf(cA, sdx, cB * sdy));
-            ay += fabsf(fmaf(cB, sdx, cC * sdy));
+        for (int ji = 0; ji < 4; ji++) {
+            const int j = 4 * jo + ji;
+            const float2 sw = lds_f2(swrow + 8 * j);   // one 64-bit load: {s, w}
+            const float4 dpx = lds_f4(dpb + 16 * j);   // one 128-bit broadcast load: dL/dpix of pixel 16h+j
+            const float s = sw.x, w = sw.y;
+            const float dx = Xg - (float)ji;
+            const float sdx = s * dx, sdy = s * dy;
+            S0 += s; Sx += sdx; Sy += sdy;
+            Sxx = fmaf(sdx, dx, Sxx); Sxy = fmaf(sdx, dy, Sxy); Syy = fmaf(sdy, dy, Syy);
+            c0 = fmaf(w, dpx.x, c0);
+            c1 = fmaf(w, dpx.y, c1);
+            c2 = fmaf(w, dpx.z, c2);
+            if (ABSGRAD) {
+                ax += fabsf(fmaf(cA, sdx, cB * sdy));
+                ay += fabsf(fmaf(cB, sdx, cC * sdy));
+            }
         }
     }
     S0 += __shfl_xor_sync(0xffffffffu, S0, 16); Sx += __shfl_xor_sync(0xffffffffu, Sx, 16);
@@ -119,9 +126,7 @@ render_bwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const uint32_
         dp1 = __ldg(dL_dpix + P + pix);
         dp2 = __ldg(dL_dpix + 2 * P + pix);
     }
-    sts_f1(wbase + RbSmem::dp + lane * 4, dp0);
-    sts_f1(wbase + RbSmem::dp + 128 + lane * 4, dp1);
-    sts_f1(wbase + RbSmem::dp + 256 + lane * 4, dp2);
+    sts_f4(wbase + RbSmem::dp + lane * 16, make_float4(dp0, dp1, dp2, 0.f));
     const float nTf_bg = -T_final * (cam.bg[0] * dp0 + cam.bg[1] * dp1 + cam.bg[2] * dp2);
     float T = T_final;
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
@@ -139,9 +144,9 @@ render_bwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const uint32_
     const uint32_t wbit = 1u << warp;
     int nbuf = 0;
     // per-lane row addresses of the phase-1 buffer, kept in registers (no re-derivation from tid per pair)
-    uint32_t myS = wbase + RbSmem::S + lane * 4, myW = wbase + RbSmem::W + lane * 4;
+    uint32_t mySW = wbase + RbSmem::SW + lane * 8;
     uint32_t mmeta = wbase + RbSmem::meta;
-    asm volatile("" : "+r"(myS), "+r"(myW), "+r"(mmeta));
+    asm volatile("" : "+r"(mySW), "+r"(mmeta));
     const bool lane0 = lane == 0;
 
     // staging is software-pipelined: while a round is being walked, the next round's entry words and records
@@ -214,8 +219,7 @@ render_bwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const uint32_
                     dL_dalpha = fmaf(dL_dalpha, T, nTf_bg * rinv);
                     s = a_raw * dL_dalpha;  // dL/dpower (the 0.99 clamp is straight-through)
                 }
-                sts_f1(myS + nbuf * (RB_ROW * 4), s);
-                sts_f1(myW + nbuf * (RB_ROW * 4), wgt);
+                sts_f2(mySW + nbuf * (RB_ROW * 8), s, wgt);
                 if (lane0) {
                     const uint32_t mrow = mmeta + nbuf * 32;
                     sts_u1(mrow, lds_u1(se + k * 4) >> 8);

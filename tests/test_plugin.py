@@ -114,8 +114,9 @@ def test_libtorch_custom_class_matches_c_abi():
     g = GradBuffers.allocate(sc.N, 8, dev)
     ref.backward(dl, g)
     assert torch.equal(img.detach(), rimg) and torch.equal(radii, rradii)
-    from util import rel_err
+    from util import assert_close_robust
     for k in ("means3D", "scales", "quats", "opacities", "sh0", "shN"):
         a, b = leaves[k].grad, getattr(g, k)
-        # two runs of the same kernels: only the order of the fp32 atomics differs
-        assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 5e-5, k
+        # two runs of the same kernels: only the order of the fp32 atomics differs (amplified where the rotation /
+        # scale gradients cancel), so the same robust metric as the oracle parity tests applies
+        assert_close_robust(a.cpu().numpy(), b.cpu().numpy(), 1e-4, k)
