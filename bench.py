@@ -76,6 +76,13 @@ class ClockSampler:
         return out
 
 
+# DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of each stage's kernels at c3 on one B200,
+# from the committed `ncu --set full` capture profiles/r1_v3_step_ncu_full.md (MB).  Only valid for workload c3.
+NCU_TRAFFIC_MB_C3 = {"preprocess_fwd": 236.83 + 97.70, "binning_sort": 0.23 + 61.45 + 3.39 + 0.1,
+                     "render_fwd": 39.38 + 3.09, "render_bwd": 62.00 + 1.60, "preprocess_bwd": 288.09 + 228.42}
+NCU_ISSUE_ACTIVE_PCT_C3 = {"preprocess_fwd": 72.9, "render_fwd": 91.2, "render_bwd": 73.1, "preprocess_bwd": 49.6}
+
+
 def algorithmic_bytes(N, K, V, D, T, P):
     """SURVEY.md §8(d) contract figure (compulsory traffic, infinite-L2 model)."""
     pb = 44 + 12 * K
@@ -284,8 +291,15 @@ def main():
                    "host_sync": "none per step (binning arena validated by deferred check, DVS_FLAG_DEFER_CHECK; "
                                 "single-pass binning into fixed-stride tile bins sized by the warm-up forwards)"},
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": dom_gbs, "peak": peak, "unit": "GB/s",
-                     "frac": dom_gbs / peak, "traffic": None, "peak_source": peak_src,
-                     "note": "algorithmic bytes per SURVEY.md §8(d) / CUDA-event stage time; compositing is issue-bound"},
+                     "frac": dom_gbs / peak,
+                     "traffic": (NCU_TRAFFIC_MB_C3.get(dominant, 0) * 1e6 if WORKLOAD == "c3" else None),
+                     "traffic_source": "profiles/r1_v3_step_ncu_full.md (ncu --set full, per launch)",
+                     "issue_active_pct": NCU_ISSUE_ACTIVE_PCT_C3.get(dominant) if WORKLOAD == "c3" else None,
+                     "peak_source": peak_src,
+                     "note": "algorithmic bytes per SURVEY.md §8(d) / CUDA-event stage time.  The dominant kernel is the "
+                             "compositing backward: 256*D potential pair evaluations against ~0.12 GB of compulsory "
+                             "traffic, so it is bound by instruction issue (see issue_active_pct), not by HBM; the "
+                             "streaming stages' HBM fractions are in `stages`"},
         "roofline_step": ({"achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak,
                            "alg_bytes_per_step": total_bytes} if step_gbs else None),
         "stages": stages,
