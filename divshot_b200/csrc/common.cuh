@@ -7,7 +7,7 @@
 //           q2 = { b, depth, radius (int bits), tiles_touched | clamped<<24 (uint bits) }
 //         so that alpha = ex2(A2*dx^2 + B2*dx*dy + C2*dy^2 + lo)  (one MUFU, no multiply by opacity)
 //   aux   [N] x 16 B  { minx|miny<<16, maxx|maxy<<16|clamped<<29, depth bits, 0 }
-//   bins  [Dcap] x 8 B  unsorted per-tile entries  depth_bits<<32 | id<<8 | submask
+//   bins  [max(Dcap, T*stride)] x 8 B  unsorted per-tile entries  depth_bits<<32 | id<<8 | submask
 //   plist [Dcap] x 4 B  sorted entries id<<8 | submask (tile-major; the parity point_list is id)
 //   tile_count / tile_base / tile_cursor [T]
 //   final_T, n_contrib [P];  sgrad [N] x 48 B screen-space gradient record (see dvs_rast.h)
@@ -86,11 +86,6 @@ __device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
-}
-__device__ __forceinline__ float4 ldg_f4(const float4* p) { return __ldg(p); }
-__device__ __forceinline__ void stg_cs_f4(float4* p, float4 v) {
-    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-                 : "memory");
 }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

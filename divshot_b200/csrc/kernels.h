@@ -7,7 +7,7 @@
 
 namespace dvs {
 
-// A1 (+ per-tile duplicate counts)
+// A1 (+ per-tile duplicate counts, or with fe.bin_stride > 0 the duplicate emission itself: single-pass binning)
 cudaError_t launch_preprocess_fwd(const Cam& cam, int N, const Params& prm, float4* rec, uint4* aux,
                                   uint32_t* tile_count, int32_t* out_radii, unsigned long long* stats,
                                   const FusedEmit& fe, cudaStream_t st);
@@ -17,7 +17,7 @@ cudaError_t launch_preprocess_fwd(const Cam& cam, int N, const Params& prm, floa
 cudaError_t launch_tile_scan(int T, const uint32_t* tile_count, uint32_t* tile_base, uint32_t* tile_cursor,
                              uint32_t* info, uint32_t dup_capacity, uint32_t* class_tiles, cudaStream_t st);
 
-// A3: emit (depth | id | sub-tile mask) entries into per-tile bins
+// A3 (two-pass mode): emit (depth | id | sub-tile mask) entries into per-tile bins
 cudaError_t launch_emit(const Cam& cam, int N, const uint4* aux, const float4* rec, uint32_t* tile_cursor,
                         unsigned long long* bins, uint32_t dup_capacity, cudaStream_t st);
 

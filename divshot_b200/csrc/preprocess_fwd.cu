@@ -1,5 +1,5 @@
 // preprocess_fwd.cu — A1: per-Gaussian forward (3D->2D EWA covariance projection + SH evaluation)
-// plus per-tile duplicate counting (first half of A2/A3).
+// plus per-tile duplicate counting (two-pass binning) or the duplicate emission itself (single-pass binning).
 //
 // Replaces `preprocessCUDA` of the absent gsplatrast operator (algorithm: Appendix
 // B.1; in-tree corroboration of the maths: diverse/assets/shaders/gaussian/gsplat_intersect.hlsl:61-134
@@ -10,9 +10,10 @@
 // every fmaf() is one, so that radius / tile rect / depth key / mean2D / rgb are the literal
 // operation sequence of SURVEY.md Appendix B.6 and come out bit-identical to the CPU oracle.
 //
-// Roofline: HBM.  Algorithmic bytes per Gaussian: (44+12K) read + 48 (record) + 16 (aux) written
-// for visible ones.  One thread per Gaussian for the geometry; the 12*(K-1)-byte SH row is
-// staged per warp through shared memory with 128-bit coalesced loads.
+// Roofline: HBM.  Algorithmic bytes per Gaussian: (44+12K) read + 48 (record) + 16 (aux) written.
+// One thread per Gaussian for the geometry; each warp's six parameter rows (incl. the 12*(K-1)-byte SH rows)
+// are staged in shared memory by ONE lane issuing 1-D bulk copies (cp.async.bulk -> SASS UBLKCP) that complete
+// on the warp's mbarrier, and the records / aux words / radii leave by bulk shared->global stores.
 #include "common.cuh"
 #include "emit.cuh"
 #include "kernels.h"
