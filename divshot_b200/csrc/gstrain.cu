@@ -4,9 +4,10 @@
 //
 // Scope (SURVEY.md §8 b, F1/F2 "next"): this file exists so that the B200 rasterizer can be driven through the
 // reference's own plugin boundary.  The step around the rasterizer is deliberately small — pick a view,
-// rasterize forward (dvs_rast_forward), L1 photometric loss, rasterize backward (dvs_rast_backward), fused Adam
-// with the per-group learning rates of GaussianTrainConfig — and keeps every tensor device-resident.
-// Densification / pruning / D-SSIM / COLMAP SfM / mesh export of the closed trainer are NOT rebuilt here.
+// rasterize forward (dvs_rast_forward), photometric loss (1-w)*L1 + w*(1-SSIM) with w = ssimWeight (main.cpp:24),
+// rasterize backward (dvs_rast_backward), fused Adam with the per-group learning rates of GaussianTrainConfig —
+// and keeps every tensor device-resident.
+// Densification / pruning / COLMAP SfM / mesh export of the closed trainer are NOT rebuilt here.
 //
 // Data sources accepted by load_train_data:
 //   "synthetic:N=100000,W=800,H=600,views=8,deg=1,seed=7"  — a random ground-truth splat scene is rendered with
@@ -44,17 +45,130 @@ void ckr(int rc, dvs_rast_ctx* ctx, const char* what) {
     if (rc != DVS_OK) throw std::runtime_error(std::string("gstrain: ") + what + ": " + dvs_rast_last_error(ctx));
 }
 
-__global__ void l1_loss_kernel(const float* __restrict__ render, const float* __restrict__ target,
-                               float* __restrict__ dL_dpix, float* __restrict__ loss, size_t n, float inv_n) {
-    float acc = 0.f;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const float d = render[i] - target[i];
-        acc += fabsf(d);
-        dL_dpix[i] = (d > 0.f ? inv_n : (d < 0.f ? -inv_n : 0.f));
+// ---------------------------------------------------------------------------------------------------------
+// Photometric loss of the trainer step: L = (1 - w) * L1 + w * (1 - SSIM), w = ssimWeight
+// (application/diverseshot-cli/source/main.cpp:24 "ssim", default 0.2), and its gradient dL/dpixel — the only
+// thing the rasterizer backward needs.  SSIM uses the standard 11x11 Gaussian window (sigma 1.5), zero padding,
+// C1 = 0.01^2, C2 = 0.03^2, mean over the 3*H*W map.  Two tiled kernels with separable convolutions in shared
+// memory: (A) window statistics -> SSIM map -> per-pixel partials d/d(mu_x), d/d(E[x^2]), d/d(E[xy]);
+// (B) convolve the partials back (the window is symmetric) and add the L1 term.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SS_T = 16, SS_H = 5, SS_W = SS_T + 2 * SS_H;  // tile, halo, padded tile
+__constant__ float c_gauss[11] = {0.00102838f, 0.00759876f, 0.03600077f, 0.10936069f, 0.21300553f, 0.26601172f,
+                                  0.21300553f, 0.10936069f, 0.03600077f, 0.00759876f, 0.00102838f};
+
+__global__ void __launch_bounds__(SS_T* SS_T)
+ssim_partials_kernel(const float* __restrict__ X, const float* __restrict__ Y, float* __restrict__ dm,
+                     float* __restrict__ d2, float* __restrict__ dxy, float* __restrict__ loss, int W, int H,
+                     float w_ssim, float inv_n) {
+    __shared__ float sx[SS_W][SS_W + 1], sy[SS_W][SS_W + 1];
+    __shared__ float h[5][SS_W][SS_T + 1];
+    const int ch = blockIdx.z, x0 = blockIdx.x * SS_T, y0 = blockIdx.y * SS_T;
+    const size_t plane = (size_t)ch * W * H;
+    const int tid = threadIdx.y * SS_T + threadIdx.x;
+    for (int t = tid; t < SS_W * SS_W; t += SS_T * SS_T) {
+        const int r = t / SS_W, c = t % SS_W, gx = x0 + c - SS_H, gy = y0 + r - SS_H;
+        const bool in = gx >= 0 && gx < W && gy >= 0 && gy < H;
+        sx[r][c] = in ? X[plane + (size_t)gy * W + gx] : 0.f;
+        sy[r][c] = in ? Y[plane + (size_t)gy * W + gx] : 0.f;
+    }
+    __syncthreads();
+    for (int t = tid; t < SS_W * SS_T; t += SS_T * SS_T) {  // horizontal pass
+        const int r = t / SS_T, c = t % SS_T;
+        float a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+#pragma unroll
+        for (int k = 0; k < 11; k++) {
+            const float g = c_gauss[k], xv = sx[r][c + k], yv = sy[r][c + k];
+            a0 = fmaf(g, xv, a0); a1 = fmaf(g, yv, a1); a2 = fmaf(g, xv * xv, a2); a3 = fmaf(g, yv * yv, a3);
+            a4 = fmaf(g, xv * yv, a4);
+        }
+        h[0][r][c] = a0; h[1][r][c] = a1; h[2][r][c] = a2; h[3][r][c] = a3; h[4][r][c] = a4;
+    }
+    __syncthreads();
+    const int px = x0 + threadIdx.x, py = y0 + threadIdx.y;
+    float local = 0.f;
+    if (px < W && py < H) {
+        float mx = 0, my = 0, ex2 = 0, ey2 = 0, exy = 0;
+#pragma unroll
+        for (int k = 0; k < 11; k++) {
+            const float g = c_gauss[k];
+            mx = fmaf(g, h[0][threadIdx.y + k][threadIdx.x], mx); my = fmaf(g, h[1][threadIdx.y + k][threadIdx.x], my);
+            ex2 = fmaf(g, h[2][threadIdx.y + k][threadIdx.x], ex2); ey2 = fmaf(g, h[3][threadIdx.y + k][threadIdx.x], ey2);
+            exy = fmaf(g, h[4][threadIdx.y + k][threadIdx.x], exy);
+        }
+        const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+        const float sxx = ex2 - mx * mx, syy = ey2 - my * my, sxy = exy - mx * my;
+        const float A1 = 2.f * mx * my + C1, A2 = 2.f * sxy + C2, B1 = mx * mx + my * my + C1, B2 = sxx + syy + C2;
+        const float iB = 1.f / (B1 * B2);
+        const float ssim = A1 * A2 * iB;
+        // dL/dssim = -w/n ; chain to the three window statistics that depend on X
+        const float gs = -w_ssim * inv_n;
+        const float dmu = 2.f * my * (A2 - A1) * iB - 2.f * mx * A1 * A2 * (B2 - B1) * iB * iB;
+        const float de2 = -A1 * A2 * iB / B2;
+        const float dex = 2.f * A1 * iB;
+        const size_t o = plane + (size_t)py * W + px;
+        dm[o] = gs * dmu; d2[o] = gs * de2; dxy[o] = gs * dex;
+        const float dlt = sx[threadIdx.y + SS_H][threadIdx.x + SS_H] - sy[threadIdx.y + SS_H][threadIdx.x + SS_H];
+        local = (w_ssim * (1.f - ssim) + (1.f - w_ssim) * fabsf(dlt)) * inv_n;
     }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if ((threadIdx.x & 31) == 0) atomicAdd(loss, acc * inv_n);
+    for (int off = 16; off > 0; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
+    if ((tid & 31) == 0) atomicAdd(loss, local);
+}
+
+__global__ void __launch_bounds__(SS_T* SS_T)
+ssim_backward_kernel(const float* __restrict__ X, const float* __restrict__ Y, const float* __restrict__ dm,
+                     const float* __restrict__ d2, const float* __restrict__ dxy, float* __restrict__ dL_dpix, int W,
+                     int H, float w_ssim, float inv_n) {
+    __shared__ float s[3][SS_W][SS_W + 1];
+    __shared__ float h[3][SS_W][SS_T + 1];
+    const int ch = blockIdx.z, x0 = blockIdx.x * SS_T, y0 = blockIdx.y * SS_T;
+    const size_t plane = (size_t)ch * W * H;
+    const int tid = threadIdx.y * SS_T + threadIdx.x;
+    for (int t = tid; t < SS_W * SS_W; t += SS_T * SS_T) {
+        const int r = t / SS_W, c = t % SS_W, gx = x0 + c - SS_H, gy = y0 + r - SS_H;
+        const bool in = gx >= 0 && gx < W && gy >= 0 && gy < H;
+        const size_t o = plane + (size_t)gy * W + gx;
+        s[0][r][c] = in ? dm[o] : 0.f; s[1][r][c] = in ? d2[o] : 0.f; s[2][r][c] = in ? dxy[o] : 0.f;
+    }
+    __syncthreads();
+    for (int t = tid; t < SS_W * SS_T; t += SS_T * SS_T) {
+        const int r = t / SS_T, c = t % SS_T;
+        float a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll
+        for (int k = 0; k < 11; k++) {
+            const float g = c_gauss[k];
+            a0 = fmaf(g, s[0][r][c + k], a0); a1 = fmaf(g, s[1][r][c + k], a1); a2 = fmaf(g, s[2][r][c + k], a2);
+        }
+        h[0][r][c] = a0; h[1][r][c] = a1; h[2][r][c] = a2;
+    }
+    __syncthreads();
+    const int px = x0 + threadIdx.x, py = y0 + threadIdx.y;
+    if (px < W && py < H) {
+        float c0 = 0, c1 = 0, c2 = 0;
+#pragma unroll
+        for (int k = 0; k < 11; k++) {
+            const float g = c_gauss[k];
+            c0 = fmaf(g, h[0][threadIdx.y + k][threadIdx.x], c0); c1 = fmaf(g, h[1][threadIdx.y + k][threadIdx.x], c1);
+            c2 = fmaf(g, h[2][threadIdx.y + k][threadIdx.x], c2);
+        }
+        const size_t o = plane + (size_t)py * W + px;
+        const float xv = X[o], yv = Y[o], d = xv - yv;
+        const float l1 = (1.f - w_ssim) * inv_n * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+        dL_dpix[o] = c0 + 2.f * xv * c1 + yv * c2 + l1;
+    }
+}
+
+// loss + dL/dpix on `stream`; scratch: 9*W*H floats.  *loss (device) must be zeroed by the caller.
+static void launch_photometric_loss(const float* render, const float* target, float* dL_dpix, float* loss,
+                                    float* scratch, int W, int H, float w_ssim, cudaStream_t st) {
+    const size_t P3 = (size_t)3 * W * H;
+    const float inv_n = 1.f / (float)P3;
+    const dim3 grid((W + SS_T - 1) / SS_T, (H + SS_T - 1) / SS_T, 3), block(SS_T, SS_T);
+    ssim_partials_kernel<<<grid, block, 0, st>>>(render, target, scratch, scratch + P3, scratch + 2 * P3, loss, W, H,
+                                                 w_ssim, inv_n);
+    ssim_backward_kernel<<<grid, block, 0, st>>>(render, target, scratch, scratch + P3, scratch + 2 * P3, dL_dpix, W,
+                                                 H, w_ssim, inv_n);
 }
 
 // fused Adam over one parameter group (4 streams in, 3 out, 128-bit where aligned is left to the compiler)
@@ -134,6 +248,7 @@ struct GaussianTrainerImpl {
     std::vector<View> views;
     float* d_render = nullptr;
     float* d_dLdpix = nullptr;
+    float* d_scratch = nullptr;  // 9*W*H floats for the SSIM partial maps
     float* d_loss = nullptr;
     float* h_loss = nullptr;  // pinned
     size_t img_cap = 0;
@@ -147,8 +262,10 @@ struct GaussianTrainerImpl {
         if (floats <= img_cap) return;
         if (d_render) cudaFree(d_render);
         if (d_dLdpix) cudaFree(d_dLdpix);
+        if (d_scratch) cudaFree(d_scratch);
         ck(cudaMalloc(&d_render, floats * sizeof(float)), "cudaMalloc render");
         ck(cudaMalloc(&d_dLdpix, floats * sizeof(float)), "cudaMalloc dLdpix");
+        ck(cudaMalloc(&d_scratch, 3 * floats * sizeof(float)), "cudaMalloc loss scratch");
         img_cap = floats;
     }
     void upload(const std::vector<float>& means, const std::vector<float>& lscales, const std::vector<float>& quats,
@@ -188,7 +305,8 @@ GaussianTrainerScene::~GaussianTrainerScene() {
     cudaDeviceSynchronize();
     for (auto& v : impl_->views) cudaFree(v.d_target);
     impl_->params.release(); impl_->grads.release(); impl_->m1.release(); impl_->m2.release();
-    cudaFree(impl_->d_render); cudaFree(impl_->d_dLdpix); cudaFree(impl_->d_loss); cudaFreeHost(impl_->h_loss);
+    cudaFree(impl_->d_render); cudaFree(impl_->d_dLdpix); cudaFree(impl_->d_scratch); cudaFree(impl_->d_loss);
+    cudaFreeHost(impl_->h_loss);
     if (impl_->ctx) dvs_rast_destroy(impl_->ctx);
     if (impl_->stream) cudaStreamDestroy(impl_->stream);
     delete impl_;
@@ -338,7 +456,9 @@ void GaussianTrainerScene::trainStep() {
     dvs_grads G = I.G();
     ckr(dvs_rast_forward(I.ctx, &cam, I.N, &P, I.d_render, nullptr, I.stream), I.ctx, "forward");
     ck(cudaMemsetAsync(I.d_loss, 0, sizeof(float), I.stream), "memset loss");
-    l1_loss_kernel<<<592, 256, 0, I.stream>>>(I.d_render, vw.d_target, I.d_dLdpix, I.d_loss, n, 1.f / (float)n);
+    (void)n;
+    launch_photometric_loss(I.d_render, vw.d_target, I.d_dLdpix, I.d_loss, I.d_scratch, cam.width, cam.height,
+                            std::min(1.f, std::max(0.f, config_.ssimWeight)), I.stream);
     ckr(dvs_rast_backward(I.ctx, &P, I.d_dLdpix, &G, 0u, I.stream), I.ctx, "backward");
     // Adam, per-group learning rates (GaussianTrainConfig); position lr decays exponentially init -> final
     const float t = std::min(1.f, (float)step / (float)std::max(1, config_.numIters));
@@ -429,6 +549,11 @@ GS_EXPORT void export_mesh(GaussianTrainerScene* scene) { scene->exportMesh("");
 GS_EXPORT void delete_splat(GaussianTrainerScene* scene) { delete scene; }
 GS_EXPORT int get_cur_step(GaussianTrainerScene* scene) { return scene->getCurrentIterations(); }
 GS_EXPORT void gstrain_destroy() { cudaDeviceSynchronize(); }
+// test hook (device pointers): the trainer's photometric loss and its gradient; scratch = 9*W*H floats, *loss zeroed by the caller
+GS_EXPORT void gstrain_photometric_loss(const float* render, const float* target, float* dL_dpix, float* loss,
+                                        float* scratch, int W, int H, float ssim_weight, void* stream) {
+    launch_photometric_loss(render, target, dL_dpix, loss, scratch, W, H, ssim_weight, static_cast<cudaStream_t>(stream));
+}
 GS_EXPORT const char* get_description() { return "gstrain: B200-native 3DGS trainer plugin (divshot_b200)"; }
 GS_EXPORT void* create_instance() { return nullptr; }
 }

@@ -120,3 +120,40 @@ def test_libtorch_custom_class_matches_c_abi():
         # two runs of the same kernels: only the order of the fp32 atomics differs (amplified where the rotation /
         # scale gradients cancel), so the same robust metric as the oracle parity tests applies
         assert_close_robust(a.cpu().numpy(), b.cpu().numpy(), 1e-4, k)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W,H,w", [(67, 45, 0.2), (128, 96, 0.0), (160, 100, 1.0)])
+def test_photometric_loss_matches_torch(W, H, w):
+    """The trainer's fused (1-w)*L1 + w*(1-SSIM) loss and dL/dpixel vs a torch conv2d/autograd reference."""
+    import ctypes as C
+
+    import torch
+    import torch.nn.functional as F
+    libs = _build()
+    lib = C.CDLL(libs["libgstrain"])
+    lib.gstrain_photometric_loss.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_float, C.c_void_p]
+    lib.gstrain_photometric_loss.restype = None
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device="cpu"); g.manual_seed(3)
+    x = torch.rand(3, H, W, generator=g).to(dev).requires_grad_(True)
+    y = (x.detach() * 0.7 + 0.3 * torch.rand(3, H, W, generator=g).to(dev)).contiguous()
+    # reference
+    k = torch.arange(11, dtype=torch.float64) - 5
+    gk = torch.exp(-k ** 2 / (2 * 1.5 ** 2)); gk = (gk / gk.sum()).float().to(dev)
+    win = (gk[:, None] * gk[None, :]).expand(3, 1, 11, 11).contiguous()
+    conv = lambda t: F.conv2d(t[None], win, padding=5, groups=3)[0]
+    mx, my = conv(x), conv(y)
+    sxx, syy, sxy = conv(x * x) - mx * mx, conv(y * y) - my * my, conv(x * y) - mx * my
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    ssim = ((2 * mx * my + C1) * (2 * sxy + C2)) / ((mx * mx + my * my + C1) * (sxx + syy + C2))
+    loss_ref = (1 - w) * (x - y).abs().mean() + w * (1 - ssim.mean())
+    loss_ref.backward()
+    # ours
+    dl = torch.empty(3, H, W, device=dev); loss = torch.zeros(1, device=dev); scratch = torch.empty(9 * H * W, device=dev)
+    lib.gstrain_photometric_loss(x.detach().contiguous().data_ptr(), y.data_ptr(), dl.data_ptr(), loss.data_ptr(),
+                                 scratch.data_ptr(), W, H, C.c_float(w), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(loss_ref)) <= 1e-5 * max(1.0, abs(float(loss_ref)))
+    ref = x.grad
+    assert float((dl - ref).abs().max()) <= 1e-4 * float(ref.abs().max()) + 1e-9
