@@ -157,3 +157,36 @@ def test_photometric_loss_matches_torch(W, H, w):
     assert abs(float(loss) - float(loss_ref)) <= 1e-5 * max(1.0, abs(float(loss_ref)))
     ref = x.grad
     assert float((dl - ref).abs().max()) <= 1e-4 * float(ref.abs().max()) + 1e-9
+
+
+def test_model_writers_ply_and_splat(tmp_path):
+    """F2: the plugin's writers (no GPU needed) against the layouts of external/tinygsplat/tiny_gsplat.cpp:168-291."""
+    import ctypes as C
+    libs = _build()
+    lib = C.CDLL(libs["libgstrain"])
+    lib.gstrain_write_model.argtypes = [C.c_char_p, C.c_longlong] + [C.c_void_p] * 6
+    lib.gstrain_write_model.restype = C.c_int
+    rng = np.random.default_rng(0)
+    N = 37
+    pos = rng.normal(size=(N, 3)).astype(np.float32); sh0 = rng.normal(size=(N, 3)).astype(np.float32)
+    shn = rng.normal(size=(N, 15, 3)).astype(np.float32); op = rng.normal(size=N).astype(np.float32)
+    sc = rng.normal(-3, 0.5, size=(N, 3)).astype(np.float32); rot = rng.normal(size=(N, 4)).astype(np.float32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    ply = str(tmp_path / "m.ply"); spl = str(tmp_path / "m.splat")
+    assert lib.gstrain_write_model(ply.encode(), N, p(pos), p(sh0), p(shn), p(op), p(sc), p(rot)) == 0
+    assert lib.gstrain_write_model(spl.encode(), N, p(pos), p(sh0), p(shn), p(op), p(sc), p(rot)) == 0
+    n, props, rows = _read_ply(ply)
+    assert n == N and len(props) == 59
+    assert np.array_equal(rows[:, 0:3], pos) and np.array_equal(rows[:, 3:6], sh0)
+    # f_rest is channel-major: f_rest[c*15 + j] = shN[j][c]
+    assert np.array_equal(rows[:, 6:51].reshape(N, 3, 15), shn.transpose(0, 2, 1))
+    assert np.array_equal(rows[:, 51], op) and np.array_equal(rows[:, 52:55], sc) and np.array_equal(rows[:, 55:59], rot)
+    raw = np.fromfile(spl, np.uint8).reshape(N, 32)
+    f = raw[:, :24].copy().view(np.float32).reshape(N, 6)
+    assert np.array_equal(f[:, :3], pos) and np.allclose(f[:, 3:], np.exp(sc), rtol=1e-6)
+    rgb = np.clip((0.5 + 0.28209479177387814 * sh0) * 255, 0, 255).astype(np.uint8)
+    assert (np.abs(raw[:, 24:27].astype(int) - rgb.astype(int)) <= 1).all()
+    a = np.clip(255 / (1 + np.exp(-op)), 0, 255).astype(np.uint8)
+    assert (np.abs(raw[:, 27].astype(int) - a.astype(int)) <= 1).all()
+    q = rot / np.linalg.norm(rot, axis=1, keepdims=True)
+    assert (np.abs(raw[:, 28:32].astype(int) - np.clip(q * 128 + 128, 0, 255).astype(np.uint8).astype(int)) <= 1).all()
