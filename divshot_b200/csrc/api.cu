@@ -7,6 +7,7 @@
 // the arena is sized ahead and validated once, after the forward has been enqueued.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -353,7 +354,8 @@ int dvs_rast_forward(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, const 
     ctx->st.tiles_x = c.gx; ctx->st.tiles_y = c.gy;
     // size the fixed per-tile bin stride for single-pass binning of later deferred-check forwards
     {
-        const int64_t stride = ((int64_t)ctx->h_info[1] * 3 / 2 + 64 + 63) / 64 * 64;
+        int64_t stride = ((int64_t)ctx->h_info[1] * 3 / 2 + 64 + 63) / 64 * 64;
+        if (ctx->bin_stride_tiles == T) stride = std::max<int64_t>(stride, ctx->bin_stride);  // never shrink: views alternate
         const int64_t want = stride * T;
         if (want <= 4 * (int64_t)ctx->h_info[0] + (16 << 20)) {  // skewed scenes (one huge tile) stay two-pass
             ctx->bin_stride = (uint32_t)stride;

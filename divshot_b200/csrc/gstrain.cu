@@ -455,12 +455,23 @@ void GaussianTrainerScene::trainStep() {
     const size_t n = (size_t)3 * cam.width * cam.height;
     dvs_params P = I.P();
     dvs_grads G = I.G();
-    ckr(dvs_rast_forward(I.ctx, &cam, I.N, &P, I.d_render, nullptr, I.stream), I.ctx, "forward");
-    ck(cudaMemsetAsync(I.d_loss, 0, sizeof(float), I.stream), "memset loss");
+    // Steps run without any host synchronisation (DVS_FLAG_DEFER_CHECK; honoured once a synchronous forward has
+    // sized the binning arena).  A late DVS_E_OVERFLOW means a deferred step overflowed the arena: its kernels
+    // exited early (zero gradients, so the Adam update it fed was harmless) and this step is simply redone.
+    cam.flags |= DVS_FLAG_DEFER_CHECK;
+    for (int attempt = 0;; attempt++) {
+        int rc = dvs_rast_forward(I.ctx, &cam, I.N, &P, I.d_render, nullptr, I.stream);
+        if (rc == DVS_E_OVERFLOW && attempt < 2) continue;
+        ckr(rc, I.ctx, "forward");
+        ck(cudaMemsetAsync(I.d_loss, 0, sizeof(float), I.stream), "memset loss");
+        launch_photometric_loss(I.d_render, vw.d_target, I.d_dLdpix, I.d_loss, I.d_scratch, cam.width, cam.height,
+                                std::min(1.f, std::max(0.f, config_.ssimWeight)), I.stream);
+        rc = dvs_rast_backward(I.ctx, &P, I.d_dLdpix, &G, 0u, I.stream);
+        if (rc == DVS_E_OVERFLOW && attempt < 2) continue;
+        ckr(rc, I.ctx, "backward");
+        break;
+    }
     (void)n;
-    launch_photometric_loss(I.d_render, vw.d_target, I.d_dLdpix, I.d_loss, I.d_scratch, cam.width, cam.height,
-                            std::min(1.f, std::max(0.f, config_.ssimWeight)), I.stream);
-    ckr(dvs_rast_backward(I.ctx, &P, I.d_dLdpix, &G, 0u, I.stream), I.ctx, "backward");
     // Adam, per-group learning rates (GaussianTrainConfig); position lr decays exponentially init -> final
     const float t = std::min(1.f, (float)step / (float)std::max(1, config_.numIters));
     const float lr_pos = std::exp((1.f - t) * std::log(config_.poslrInit) + t * std::log(config_.poslrFinal)) * I.scene_extent;
