@@ -15,6 +15,7 @@ FLAG_INPUT_ACTIVATED = 1
 FLAG_ACCUMULATE = 2
 FLAG_ABSGRAD = 4
 FLAG_DEFER_CHECK = 8
+FLAG_ANTIALIAS = 16
 NUM_STAGES = 8
 
 (BUF_RADII, BUF_TILES_TOUCHED, BUF_DEPTH, BUF_MEAN2D, BUF_CONIC_OPACITY, BUF_RGB, BUF_CLAMPED, BUF_POINT_LIST,

@@ -459,6 +459,7 @@ void GaussianTrainerScene::trainStep() {
     // sized the binning arena).  A late DVS_E_OVERFLOW means a deferred step overflowed the arena: its kernels
     // exited early (zero gradients, so the Adam update it fed was harmless) and this step is simply redone.
     cam.flags |= DVS_FLAG_DEFER_CHECK;
+    if (config_.mipAntiliased) cam.flags |= DVS_FLAG_ANTIALIAS;  // --mipAntiliased (main.cpp, docs/userGuide.md:58)
     for (int attempt = 0;; attempt++) {
         int rc = dvs_rast_forward(I.ctx, &cam, I.N, &P, I.d_render, nullptr, I.stream);
         if (rc == DVS_E_OVERFLOW && attempt < 2) continue;

@@ -181,9 +181,10 @@ preprocess_bwd_kernel(Cam cam, int N, Params prm, const uint4* __restrict__ aux,
         for (int r = 0; r < 2; r++)
 #pragma unroll
             for (int j = 0; j < 3; j++) TS[r][j] = Tm[r][0] * S[0][j] + Tm[r][1] * S[1][j] + Tm[r][2] * S[2][j];
-        const float ca = TS[0][0] * Tm[0][0] + TS[0][1] * Tm[0][1] + TS[0][2] * Tm[0][2] + 0.3f;
+        const float ca0 = TS[0][0] * Tm[0][0] + TS[0][1] * Tm[0][1] + TS[0][2] * Tm[0][2];
         const float cb = TS[0][0] * Tm[1][0] + TS[0][1] * Tm[1][1] + TS[0][2] * Tm[1][2];
-        const float cc = TS[1][0] * Tm[1][0] + TS[1][1] * Tm[1][1] + TS[1][2] * Tm[1][2] + 0.3f;
+        const float cc0 = TS[1][0] * Tm[1][0] + TS[1][1] * Tm[1][1] + TS[1][2] * Tm[1][2];
+        const float ca = ca0 + 0.3f, cc = cc0 + 0.3f;
         // 1. conic -> cov2D
         const float det = ca * cc - cb * cb;
         // dL/dmean2D (ndc-scaled): dpower/ddx = -(A dx + B dy) with the conic (A,B,C) = (cc,-cb,ca)/det
@@ -192,9 +193,20 @@ preprocess_bwd_kernel(Cam cam, int N, Params prm, const uint4* __restrict__ aux,
         const float gmy = -0.5f * (float)cam.H * det_inv * (ca * sg0.y - cb * sg0.x);
         gm2x = gmx; gm2y = gmy;
         const float kappa = 1.0f / (det * det + 1e-7f);
-        const float da = kappa * (-cc * cc * dA + 2.0f * cb * cc * dBh + (det - ca * cc) * dC);
-        const float dc = kappa * (-ca * ca * dC + 2.0f * ca * cb * dBh + (det - ca * cc) * dA);
-        const float db = kappa * 2.0f * (cb * cc * dA - (det + 2.0f * cb * cb) * dBh + ca * cb * dC);
+        float da = kappa * (-cc * cc * dA + 2.0f * cb * cc * dBh + (det - ca * cc) * dC);
+        float dc = kappa * (-ca * ca * dC + 2.0f * ca * cb * dBh + (det - ca * cc) * dA);
+        float db = kappa * 2.0f * (cb * cc * dA - (det + 2.0f * cb * cb) * dBh + ca * cb * dC);
+        if (cam.flags & DVS_FLAG_ANTIALIAS) {
+            // opacity' = o * rho, rho = sqrt(max(0, r)), r = det0/det.  S0 = sum s = o' dL/do', so dL/drho = S0 / rho and
+            // dL/dr = S0 / (2 r); dL/do (used below) stays S0 / o.
+            const float det0 = ca0 * cc0 - cb * cb, r = det0 * det_inv;
+            if (r > 0.0f) {
+                const float gr = 0.5f * sg1.y / r * det_inv * det_inv;
+                da += gr * (cc0 * det - det0 * cc);
+                dc += gr * (ca0 * det - det0 * ca);
+                db += gr * (-2.0f * cb * (det - det0));
+            }
+        }
         // 2. cov2D -> Sigma (symmetric 3x3 gradient dS) and -> T -> J -> t
         float dS[3][3];
 #pragma unroll

@@ -221,9 +221,10 @@ preprocess_fwd_kernel(Cam cam, int N, Params prm, float4* __restrict__ rec, uint
             const float U10 = fmaf(T10, S00, fmaf(T11, S01, T12 * S02));
             const float U11 = fmaf(T10, S01, fmaf(T11, S11, T12 * S12));
             const float U12 = fmaf(T10, S02, fmaf(T11, S12, T12 * S22));
-            const float ca = fmaf(U00, T00, fmaf(U01, T01, U02 * T02)) + 0.3f;
+            const float ca0 = fmaf(U00, T00, fmaf(U01, T01, U02 * T02));
             const float cb = fmaf(U00, T10, fmaf(U01, T11, U02 * T12));
-            const float cc = fmaf(U10, T10, fmaf(U11, T11, U12 * T12)) + 0.3f;
+            const float cc0 = fmaf(U10, T10, fmaf(U11, T11, U12 * T12));
+            const float ca = ca0 + 0.3f, cc = cc0 + 0.3f;
             const float det = fmaf(ca, cc, -(cb * cb));
             if (det == 0.0f) break;
             const float det_inv = 1.0f / det;
@@ -266,6 +267,10 @@ preprocess_fwd_kernel(Cam cam, int N, Params prm, float4* __restrict__ rec, uint
             visible = true;
             tiles = (uint32_t)area;
             rad = radius;
+            if (cam.flags & DVS_FLAG_ANTIALIAS) {  // mip-splatting opacity compensation (gsplat_vs.hlsl:296-301,373)
+                const float det0 = fmaf(ca0, cc0, -(cb * cb));
+                o = o * sqrtf(fmaxf(0.0f, det0 / det));
+            }
             const float lo = log2f(o);
             q0 = make_float4(mx, my, (-0.5f * LOG2E) * cA, (-LOG2E) * cB);
             q1 = make_float4((-0.5f * LOG2E) * cC, lo, col[0], col[1]);

@@ -44,6 +44,8 @@ extern "C" {
 #define DVS_FLAG_INPUT_ACTIVATED 1u /* scales/quats/opacities already activated */
 #define DVS_FLAG_ACCUMULATE 2u      /* backward: add into the gradient buffers instead of overwriting */
 #define DVS_FLAG_ABSGRAD 4u         /* backward: also write sum|dL/dmean2D| (densify statistic, main.cpp:44-45) */
+#define DVS_FLAG_ANTIALIAS 16u      /* mip-splatting opacity compensation: opacity *= sqrt(max(0, det(S')/det(S'+0.3I)))
+                                       (GaussianTrainConfig::mipAntiliased, docs/userGuide.md:58; gsplat_vs.hlsl:296-301) */
 #define DVS_FLAG_DEFER_CHECK 8u     /* forward: do not synchronise the stream to validate the binning arena; the check is
                                        made by a later call (non-blocking) or by dvs_rast_get_stats (blocking).  Only
                                        honoured once a synchronous forward has sized the arena. */

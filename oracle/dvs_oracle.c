@@ -131,6 +131,7 @@ typedef struct {
     float J00, J02, J11, J12;
     float T[2][3];
     float a, b, c;          /* cov2D with +0.3 */
+    float a0, c0;           /* cov2D diagonal before the +0.3 low-pass */
 } ewa_t;
 
 /* EWA cov2D: gsplat_intersect.hlsl:96-134 (1.3*tanfov clamp, J, W, +0.3 low-pass) */
@@ -162,9 +163,11 @@ static inline void ewa_cov2d(const orc_camera* cam, const float t[3], const floa
     for (int i = 0; i < 2; i++)
         for (int j = 0; j < 3; j++)
             U[i][j] = fmaf(e->T[i][0], S[0][j], fmaf(e->T[i][1], S[1][j], e->T[i][2] * S[2][j]));
-    e->a = fmaf(U[0][0], e->T[0][0], fmaf(U[0][1], e->T[0][1], U[0][2] * e->T[0][2])) + 0.3f;
+    e->a0 = fmaf(U[0][0], e->T[0][0], fmaf(U[0][1], e->T[0][1], U[0][2] * e->T[0][2]));
     e->b = fmaf(U[0][0], e->T[1][0], fmaf(U[0][1], e->T[1][1], U[0][2] * e->T[1][2]));
-    e->c = fmaf(U[1][0], e->T[1][0], fmaf(U[1][1], e->T[1][1], U[1][2] * e->T[1][2])) + 0.3f;
+    e->c0 = fmaf(U[1][0], e->T[1][0], fmaf(U[1][1], e->T[1][1], U[1][2] * e->T[1][2]));
+    e->a = e->a0 + 0.3f;
+    e->c = e->c0 + 0.3f;
 }
 
 /* SH basis values b[0..K) for unit direction d: gsplat_sh.hlsl:64-103 (signs and constants) */
@@ -252,7 +255,12 @@ void orc_preprocess_fwd(const orc_camera* cam, int32_t N, const float* means3D, 
         mean2D[2 * i] = mx; mean2D[2 * i + 1] = my;
         for (int k = 0; k < 6; k++) cov3D[6 * i + k] = c6[k];
         conic_opacity[4 * i] = cA; conic_opacity[4 * i + 1] = cB; conic_opacity[4 * i + 2] = cC;
-        conic_opacity[4 * i + 3] = a.o;
+        float opac = a.o;
+        if (cam->flags & ORC_FLAG_ANTIALIAS) { /* mip-splatting compensation: gsplat_vs.hlsl:296-301,373 */
+            const float det0 = fmaf(e.a0, e.c0, -(e.b * e.b));
+            opac = a.o * sqrtf(fmaxf(0.0f, det0 / det));
+        }
+        conic_opacity[4 * i + 3] = opac;
         tiles_touched[i] = (uint32_t)area;
         rect[4 * i] = minx; rect[4 * i + 1] = miny; rect[4 * i + 2] = maxx; rect[4 * i + 3] = maxy;
     }
@@ -515,18 +523,31 @@ void orc_preprocess_bwd(const orc_camera* cam, int32_t N, const float* means3D, 
             T[1][j] = J11 * V[4 * j + 1] + J12 * V[4 * j + 2];
         }
         for (int a = 0; a < 2; a++) for (int j = 0; j < 3; j++) TS[a][j] = T[a][0] * S[0][j] + T[a][1] * S[1][j] + T[a][2] * S[2][j];
-        const double ca = TS[0][0] * T[0][0] + TS[0][1] * T[0][1] + TS[0][2] * T[0][2] + 0.3;
+        const double ca0 = TS[0][0] * T[0][0] + TS[0][1] * T[0][1] + TS[0][2] * T[0][2];
         const double cb = TS[0][0] * T[1][0] + TS[0][1] * T[1][1] + TS[0][2] * T[1][2];
-        const double cc = TS[1][0] * T[1][0] + TS[1][1] * T[1][1] + TS[1][2] * T[1][2] + 0.3;
+        const double cc0 = TS[1][0] * T[1][0] + TS[1][1] * T[1][1] + TS[1][2] * T[1][2];
+        const double ca = ca0 + 0.3, cc = cc0 + 0.3;
         double dmean[3] = {0, 0, 0};
 
         /* 1. conic -> cov2D: dSigma' = -Q G Q, Q = conic matrix, G = sym(dA, dB/2, dC) */
         const double det = ca * cc - cb * cb;
         const double kappa = 1.0 / (det * det + 1e-7);
         const double dA = dL_dconic[3 * i], dBh = 0.5 * dL_dconic[3 * i + 1], dC = dL_dconic[3 * i + 2];
-        const double da = kappa * (-cc * cc * dA + 2.0 * cb * cc * dBh + (det - ca * cc) * dC);
-        const double dc = kappa * (-ca * ca * dC + 2.0 * ca * cb * dBh + (det - ca * cc) * dA);
-        const double db = kappa * 2.0 * (cb * cc * dA - (det + 2.0 * cb * cb) * dBh + ca * cb * dC);
+        double da = kappa * (-cc * cc * dA + 2.0 * cb * cc * dBh + (det - ca * cc) * dC);
+        double dc = kappa * (-ca * ca * dC + 2.0 * ca * cb * dBh + (det - ca * cc) * dA);
+        double db = kappa * 2.0 * (cb * cc * dA - (det + 2.0 * cb * cb) * dBh + ca * cb * dC);
+        double rho = 1.0; /* anti-aliasing factor: o' = o * rho, rho = sqrt(max(0, det0/det)) */
+        if (cam->flags & ORC_FLAG_ANTIALIAS) {
+            const double det0 = ca0 * cc0 - cb * cb, r = det0 / det;
+            rho = r > 0.0 ? sqrt(r) : 0.0;
+            if (r > 0.0) {
+                /* dL/do' arrives as dL_dopacity_act; dL/drho = o * dL/do'; drho/dr = 1/(2 rho) */
+                const double gr = o * (double)dL_dopacity_act[i] * 0.5 / rho;
+                da += gr * (cc0 * det - det0 * cc) / (det * det);
+                dc += gr * (ca0 * det - det0 * ca) / (det * det);
+                db += gr * (-2.0 * cb * (det - det0)) / (det * det);
+            }
+        }
         /* 2. cov2D -> Sigma (symmetric gradient) and -> T -> J -> t */
         double dS[3][3];
         for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++)
@@ -636,12 +657,12 @@ void orc_preprocess_bwd(const orc_camera* cam, int32_t N, const float* means3D, 
             if (activated) {
                 for (int k = 0; k < 3; k++) dL_dscales[3 * i + k] = (float)(ds[k] * cam->scale_modifier);
                 for (int k = 0; k < 4; k++) dL_dquats[4 * i + k] = (float)dq[k];
-                dL_dopacities[i] = dL_dopacity_act[i];
+                dL_dopacities[i] = (float)(rho * (double)dL_dopacity_act[i]);
             } else {
                 for (int k = 0; k < 3; k++) dL_dscales[3 * i + k] = (float)(ds[k] * s[k]);
                 const double qd = q[0] * dq[0] + q[1] * dq[1] + q[2] * dq[2] + q[3] * dq[3];
                 for (int k = 0; k < 4; k++) dL_dquats[4 * i + k] = (float)((dq[k] - q[k] * qd) / qlen);
-                dL_dopacities[i] = (float)((double)dL_dopacity_act[i] * o * (1.0 - o));
+                dL_dopacities[i] = (float)(rho * (double)dL_dopacity_act[i] * o * (1.0 - o));
             }
         }
     }

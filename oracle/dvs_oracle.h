@@ -28,6 +28,7 @@ extern "C" {
 #endif
 
 #define ORC_FLAG_INPUT_ACTIVATED 1 /* scales/opacity/quats are already activated (upstream-style inputs) */
+#define ORC_FLAG_ANTIALIAS 2       /* mip-splatting opacity compensation sqrt(max(0, det(S')/det(S'+0.3I))), gsplat_vs.hlsl:296-301 */
 
 typedef struct {
     float view[16];   /* world->view, flat m[4c+r] */

@@ -17,6 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 FLAG_INPUT_ACTIVATED = 1
+FLAG_ANTIALIAS = 2
 
 
 class OrcCamera(C.Structure):

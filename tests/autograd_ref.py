@@ -45,7 +45,7 @@ def sh_basis(deg, d):
     return torch.stack(b, 1)  # [N,K]
 
 
-def project(cam, means, log_scales, quats, logit, sh0, shN, sh_degree, activated=False):
+def project(cam, means, log_scales, quats, logit, sh0, shN, sh_degree, activated=False, antialias=False):
     """Per-Gaussian forward (Appendix B.1) in float64; returns dict of differentiable tensors."""
     V = _mat(cam.view); PV = _mat(cam.proj)
     W, H = cam.width, cam.height
@@ -83,6 +83,9 @@ def project(cam, means, log_scales, quats, logit, sh0, shN, sh_degree, activated
     cov = Tm @ Sigma @ Tm.transpose(1, 2)
     a = cov[:, 0, 0] + 0.3; b = cov[:, 0, 1]; c = cov[:, 1, 1] + 0.3
     det = a * c - b * b
+    if antialias:  # mip-splatting opacity compensation (gsplat_vs.hlsl:296-301)
+        det0 = cov[:, 0, 0] * cov[:, 1, 1] - b * b
+        o = o * torch.sqrt(torch.clamp(det0 / det, min=0.0))
     conic = torch.stack([c / det, -b / det, a / det], 1)
     mid = 0.5 * (a + c)
     lam = mid + torch.sqrt(torch.clamp(mid * mid - det, min=0.1))
@@ -151,12 +154,12 @@ def composite(cam, proj, ranges, point_list, visible):
     return img, n_contrib, final_T
 
 
-def render_and_grad(cam, scene_arrays, sh_degree, ranges, point_list, radii, dL_dpix, activated=False):
+def render_and_grad(cam, scene_arrays, sh_degree, ranges, point_list, radii, dL_dpix, activated=False, antialias=False):
     """Returns (image float64 numpy, dict of gradient numpy arrays w.r.t. the stored parameters)."""
     names = ["means3D", "scales", "quats", "opac", "sh0", "shN"]
     ts = {k: torch.tensor(np.asarray(v, np.float64), requires_grad=True) for k, v in zip(names, scene_arrays)}
     proj = project(cam, ts["means3D"], ts["scales"], ts["quats"], ts["opac"].reshape(-1), ts["sh0"],
-                   ts["shN"], sh_degree, activated)
+                   ts["shN"], sh_degree, activated, antialias)
     visible = np.asarray(radii) > 0
     img, n_contrib, final_T = composite(cam, proj, np.asarray(ranges), point_list, visible)
     loss = (img * torch.tensor(np.asarray(dL_dpix, np.float64))).sum()

@@ -302,3 +302,16 @@ def test_deferred_check_mode_matches_and_reports_overflow(rast):
         assert torch.isfinite(img2).all() and r.stats()["overflow"] in (0, 1)
     finally:
         r.close()
+
+
+def test_antialias_flag(rast):
+    """DVS_FLAG_ANTIALIAS (GaussianTrainConfig::mipAntiliased): opacity compensation and its gradient."""
+    sc = make_scene(N=5000, width=112, height=80, sh_degree=2, seed=101, normalise_quats=False)
+    sc.log_scales += 0.4
+    got = _run(rast, sc, flags=_cabi.FLAG_ANTIALIAS)
+    f, b = _oracle(sc, flags=orc.FLAG_ANTIALIAS)
+    plain, _ = _oracle(sc, bwd=False)
+    vis = f.radii > 0
+    assert (f.conic_opacity[vis, 3] < 0.98 * plain.conic_opacity[vis, 3]).mean() > 0.3  # the flag changes the opacities
+    _check_forward(sc, got, f)
+    _check_backward(got, b)
