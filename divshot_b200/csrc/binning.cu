@@ -420,6 +420,9 @@ constexpr size_t bucket_smem_bytes() {
 cudaError_t launch_tile_sort(int T, uint32_t bin_stride, const uint32_t* tile_base, unsigned long long* bins,
                              uint32_t* plist, const uint32_t* info, const uint32_t* class_tiles, cudaStream_t st) {
     if (T <= 0) return cudaSuccess;
+    // In single-pass mode no tile can hold more than bin_stride entries (a longer one overflows its bin and the
+    // step is redone), so the kernels of the length classes above that bound are not launched at all.
+    const uint32_t max_len = bin_stride ? bin_stride : 0xffffffffu;
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(tile_bucket_sort_kernel<256, 1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -435,9 +438,12 @@ cudaError_t launch_tile_sort(int T, uint32_t bin_stride, const uint32_t* tile_ba
     const int g_small = min(T, 148 * 6), g_mid = min(T, 148 * 3), g_long = min(T, 148 * 2), g_big = min(T, 148);
     tile_bucket_sort_kernel<256, 1024, true><<<g_small, 256, bucket_smem_bytes<1024, true>(), st>>>(T, bin_stride, 0, tile_base, bins, plist, info, class_tiles);
     tile_bucket_sort_kernel<512, 2048, true><<<g_mid, 512, bucket_smem_bytes<2048, true>(), st>>>(T, bin_stride, 1, tile_base, bins, plist, info, class_tiles);
-    tile_bucket_sort_kernel<1024, 4096, false><<<g_long, 1024, bucket_smem_bytes<4096, false>(), st>>>(T, bin_stride, 2, tile_base, bins, plist, info, class_tiles);
-    tile_bitonic_sort_kernel<1024, true><<<g_big, 1024, 16384 * 8, st>>>(T, bin_stride, 3, tile_base, bins, plist, info, class_tiles);
-    tile_bitonic_sort_kernel<1024, false><<<g_big, 1024, 0, st>>>(T, bin_stride, 4, tile_base, bins, plist, info, class_tiles);
+    if (max_len > 2048u)
+        tile_bucket_sort_kernel<1024, 4096, false><<<g_long, 1024, bucket_smem_bytes<4096, false>(), st>>>(T, bin_stride, 2, tile_base, bins, plist, info, class_tiles);
+    if (max_len > 4096u)
+        tile_bitonic_sort_kernel<1024, true><<<g_big, 1024, 16384 * 8, st>>>(T, bin_stride, 3, tile_base, bins, plist, info, class_tiles);
+    if (max_len > 16384u)
+        tile_bitonic_sort_kernel<1024, false><<<g_big, 1024, 0, st>>>(T, bin_stride, 4, tile_base, bins, plist, info, class_tiles);
     return cudaGetLastError();
 }
 
