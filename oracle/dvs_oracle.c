@@ -272,6 +272,13 @@ int64_t orc_scan_tiles(int32_t N, const uint32_t* tiles_touched, uint32_t* point
     return (int64_t)run;
 }
 
+typedef struct { uint64_t key; uint32_t id; } orc_pair;
+static int orc_pair_cmp(const void* a, const void* b) {
+    const orc_pair* x = (const orc_pair*)a; const orc_pair* y = (const orc_pair*)b;
+    if (x->key != y->key) return x->key < y->key ? -1 : 1;
+    return x->id < y->id ? -1 : (x->id > y->id ? 1 : 0);
+}
+
 /* stable LSD radix sort of (key,value) pairs on the low `bits` bits (B.2: CUB SortPairs semantics) */
 static void radix_sort_pairs(uint64_t* k, uint32_t* v, int64_t n, int bits) {
     uint64_t* k2 = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)(n > 0 ? n : 1));
@@ -303,9 +310,41 @@ void orc_bin_sort(const orc_camera* cam, int32_t N, const float* depth, const in
                 keys[off] = key; point_list[off] = (uint32_t)i; off++;
             }
     }
+    /* A4: sort.  The credited design is one stable radix sort of all D (tile|depth) keys; the total order it
+     * produces is (tile, depth bits, Gaussian index).  For the CPU baseline to use all host cores the same order is
+     * produced here by a counting sort on the tile id (one serial O(D) pass) followed by independent per-tile sorts
+     * on (depth bits, index), run in parallel over tiles.  orc_radix_check() below keeps the literal radix variant
+     * for cross-checking in the tests. */
+    memset(ranges, 0, sizeof(uint32_t) * 2 * (size_t)T);
+    {
+        uint32_t* cnt = (uint32_t*)calloc((size_t)T + 1, sizeof(uint32_t));
+        for (int64_t j = 0; j < D; j++) cnt[(uint32_t)(keys[j] >> 32) + 1]++;
+        for (int t = 0; t < T; t++) cnt[t + 1] += cnt[t];
+        orc_pair* tmp = (orc_pair*)malloc(sizeof(orc_pair) * (size_t)(D > 0 ? D : 1));
+        uint32_t* cur = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)T);
+        memcpy(cur, cnt, sizeof(uint32_t) * (size_t)T);
+        for (int64_t j = 0; j < D; j++) {
+            const uint32_t t = (uint32_t)(keys[j] >> 32);
+            tmp[cur[t]].key = keys[j]; tmp[cur[t]].id = point_list[j]; cur[t]++;
+        }
+#pragma omp parallel for schedule(dynamic, 8)
+        for (int t = 0; t < T; t++) {
+            const uint32_t b = cnt[t], e = cnt[t + 1];
+            if (e > b) {
+                qsort(tmp + b, e - b, sizeof(orc_pair), orc_pair_cmp);
+                ranges[2 * t] = b; ranges[2 * t + 1] = e; /* A5 identifyTileRanges */
+                for (uint32_t j = b; j < e; j++) { keys[j] = tmp[j].key; point_list[j] = tmp[j].id; }
+            }
+        }
+        free(cnt); free(tmp); free(cur);
+    }
+}
+
+/* The literal variant of A4/A5 (one stable LSD radix sort over all keys + range detection), kept so the tests can
+ * check that the parallel per-tile sort above yields the identical lists. */
+void orc_radix_check(int32_t T, int64_t D, uint64_t* keys, uint32_t* point_list, uint32_t* ranges) {
     int tb = 0; while ((1 << tb) < T) tb++; /* bits needed for tile ids < T */
     radix_sort_pairs(keys, point_list, D, 32 + tb + ((32 + tb) % 8 ? 8 - (32 + tb) % 8 : 0));
-    /* A5 identifyTileRanges */
     memset(ranges, 0, sizeof(uint32_t) * 2 * (size_t)T);
     for (int64_t j = 0; j < D; j++) {
         uint32_t tile = (uint32_t)(keys[j] >> 32);

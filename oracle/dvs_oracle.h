@@ -61,6 +61,9 @@ void orc_bin_sort(const orc_camera* cam, int32_t N, const float* depth, const in
                   uint64_t* keys_sorted /*[D]*/, uint32_t* point_list /*[D]*/,
                   uint32_t* ranges /*[T,2]*/);
 
+/* literal A4/A5 (single stable radix sort of already-emitted keys); test cross-check of orc_bin_sort's parallel sort */
+void orc_radix_check(int32_t T, int64_t D, uint64_t* keys, uint32_t* point_list, uint32_t* ranges);
+
 /* A6: tile compositing forward.  fragile[p]=1 when a threshold decision of pixel p is within
  * a few ulp of flipping (alpha vs 1/255, T vs 1e-4, power vs 0) — integer outputs of such
  * pixels may legitimately differ on hardware with a different exp().  threads<=0: all cores. */

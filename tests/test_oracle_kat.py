@@ -132,3 +132,30 @@ def test_g6_sh_colour_and_clamp_mask():
     assert np.allclose(f.rgb[vis], np.maximum(col[vis], 0), atol=3e-6)
     sure = np.abs(col) > 1e-5
     assert ((f.clamped.astype(bool) == (col < 0)) | ~sure)[vis].all()
+
+
+def test_parallel_tile_sort_equals_literal_radix_sort():
+    """orc_bin_sort (counting sort by tile + per-tile sorts, parallel) vs the literal single stable radix sort."""
+    import ctypes as C
+
+    from divshot_b200.scenes import make_scene
+    from util import scene_arrays
+    sc = make_scene(N=20000, width=160, height=128, sh_degree=0, seed=77)
+    sc.means3D[:, 2] = np.round(sc.means3D[:, 2] * 4) / 4  # plenty of equal depths -> index tie-breaks
+    sc.log_scales += 0.6
+    oc = orc_cam(sc.cameras[0], 0)
+    f = orc.forward(oc, *scene_arrays(sc), render=False)
+    # rebuild the unsorted keys exactly as A3 emits them, then sort them the literal way
+    L = orc.lib()
+    gx = (160 + 15) // 16; T = gx * ((128 + 15) // 16)
+    keys = []; vals = []
+    for i in np.nonzero(f.radii > 0)[0]:
+        x0, y0, x1, y1 = f.rect[i]
+        for y in range(y0, y1):
+            for x in range(x0, x1):
+                keys.append(((y * gx + x) << 32) | int(f.depth[i:i + 1].view(np.uint32)[0])); vals.append(i)
+    keys = np.array(keys, np.uint64); vals = np.array(vals, np.uint32); rng = np.zeros((T, 2), np.uint32)
+    L.orc_radix_check(C.c_int32(T), C.c_int64(len(keys)), keys.ctypes.data_as(C.c_void_p),
+                      vals.ctypes.data_as(C.c_void_p), rng.ctypes.data_as(C.c_void_p))
+    assert len(keys) == f.D and np.array_equal(vals, f.point_list) and np.array_equal(keys, f.keys)
+    assert np.array_equal(rng, f.ranges)
