@@ -220,7 +220,6 @@ def main():
         torch.cuda.synchronize()
         sampler = ClockSampler(local) if sample_clocks else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        stage_acc = {}
         e0.record()
         for _ in range(steps):
             fn()

@@ -301,8 +301,9 @@ int dvs_rast_forward(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, const 
     // single-pass binning: only in deferred-check mode, with a bin stride sized by an earlier synchronous forward
     // of the same tile grid (an overflowing bin is reported like an arena overflow: DVS_E_OVERFLOW, redo the step)
     // (DVS_TWO_PASS=1 in the environment forces two-pass binning: A/B measurements only)
+    static const bool force_two_pass = getenv("DVS_TWO_PASS") != nullptr;
     const bool fused = defer && ctx->bin_stride > 0 && ctx->bin_stride_tiles == T &&
-                       (int64_t)ctx->bin_stride * T <= ctx->cap_bins && !getenv("DVS_TWO_PASS");
+                       (int64_t)ctx->bin_stride * T <= ctx->cap_bins && !force_two_pass;
     for (int attempt = 0; attempt < 3; attempt++) {
         CK(cudaMemsetAsync(fused ? ctx->tile_cursor : ctx->tile_count, 0, (size_t)T * TILE_CTR_STRIDE * sizeof(uint32_t), st));
         CK(cudaMemsetAsync(ctx->stats, 0, 2 * sizeof(unsigned long long), st));
