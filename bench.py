@@ -101,6 +101,9 @@ def run_cpu_sample(threads=0, reps=1, frac_lin=2):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from divshot_b200.scenes import crop_of
     from oracle import oracle as orc
+    if threads <= 0:
+        threads = os.cpu_count() or 1  # torchrun exports OMP_NUM_THREADS=1: ask for every host core explicitly
+    orc.set_threads(threads)
     sc = crop_of(WORKLOAD, frac_lin)
     cam = sc.cameras[0]
     oc = orc.make_camera(cam.view, cam.proj, cam.campos, cam.tanfovx, cam.tanfovy, cam.width, cam.height, cam.bg,
@@ -112,7 +115,7 @@ def run_cpu_sample(threads=0, reps=1, frac_lin=2):
         f = orc.forward(oc, *arrays, threads=threads)
         orc.backward(oc, f, *arrays, sc.dL_dpix[0], threads=threads)
         times.append(time.perf_counter() - t0)
-    cores = os.cpu_count() if threads <= 0 else threads
+    cores = threads
     sample = (f"oracle port, density-preserving 1/{frac_lin * frac_lin} crop of {WORKLOAD}: {sc.N} Gaussians, "
               f"{cam.width}x{cam.height}, SH deg {sc.sh_degree}, fwd+bwd, OpenMP over Gaussians/tiles")
     return sc.N, times, cores, sample

@@ -36,6 +36,15 @@ static inline int32_t imax(int32_t a, int32_t b) { return a > b ? a : b; }
 /* Deterministic fp32 exp: Cody-Waite reduction + degree-5 minimax on r^2 (Cephes expf
  * coefficients), every step a single IEEE op or fmaf.  <= 2 ulp.  Used only by the
  * activations exp(log_scale) and sigmoid(logit) (gaussian_model.cpp:145-157). */
+/* number of OpenMP threads used by every parallel region of the oracle (torchrun exports OMP_NUM_THREADS=1) */
+void orc_set_threads(int32_t n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 float orc_expf(float x) {
     x = fminf(fmaxf(x, -87.0f), 88.0f);
     float n = rintf(x * 1.44269504088896341f);

@@ -93,6 +93,9 @@ void orc_preprocess_bwd(const orc_camera* cam, int32_t N,
                         float* dL_dmeans3D, float* dL_dscales, float* dL_dquats,
                         float* dL_dopacities, float* dL_dsh0, float* dL_dshN);
 
+/* OpenMP thread count for all oracle stages (n <= 0: leave as is) */
+void orc_set_threads(int32_t n);
+
 /* deterministic fp32 exp used by the activations (bit-identical on CPU and GPU by construction) */
 float orc_expf(float x);
 

@@ -179,5 +179,9 @@ def backward(cam: OrcCamera, fwd: Forward, means3D, scales, quats, opacities, sh
     return Backward(g_m2, g_abs, g_con, g_op, g_col, d_means, d_scales, d_quats, d_opac, d_sh0, d_shN)
 
 
+def set_threads(n: int) -> None:
+    lib().orc_set_threads(C.c_int32(int(n)))
+
+
 def expf(x: float) -> float:
     return float(lib().orc_expf(C.c_float(x)))
