@@ -102,7 +102,9 @@ def run_cpu_sample(threads=0, reps=1, frac_lin=2):
     from divshot_b200.scenes import crop_of
     from oracle import oracle as orc
     if threads <= 0:
-        threads = os.cpu_count() or 1  # torchrun exports OMP_NUM_THREADS=1: ask for every host core explicitly
+        # torchrun exports OMP_NUM_THREADS=1: ask explicitly for every core this process may run on (the affinity
+        # mask, not os.cpu_count(): a container is often pinned to a subset of the host's cores)
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     orc.set_threads(threads)
     sc = crop_of(WORKLOAD, frac_lin)
     cam = sc.cameras[0]
