@@ -449,6 +449,10 @@ void orc_render_bwd(const orc_camera* cam, int32_t N, const uint32_t* ranges, co
     for (int tile = 0; tile < gx * gy; tile++) {
         const uint32_t r0 = ranges[2 * tile], r1 = ranges[2 * tile + 1];
         const int tx0 = (tile % gx) * TILE, ty0 = (tile / gx) * TILE;
+        if (r1 <= r0) continue;
+        /* per-tile partial sums (11 per list entry), flushed with one atomic per (tile, splat, component): the
+         * per-pixel atomics of the literal formulation do not scale beyond a few cores */
+        double* loc = (double*)calloc((size_t)(r1 - r0) * 11, sizeof(double));
         for (int ly = 0; ly < TILE; ly++)
             for (int lx = 0; lx < TILE; lx++) {
                 const int px = tx0 + lx, py = ty0 + ly;
@@ -481,7 +485,7 @@ void orc_render_bwd(const orc_camera* cam, int32_t N, const uint32_t* ranges, co
                         accum_rec[ch] = last_alpha * last_color[ch] + (1.0f - last_alpha) * accum_rec[ch];
                         last_color[ch] = c;
                         dL_dalpha += (c - accum_rec[ch]) * dp[ch];
-                        atomic_addd(&a_col[3 * g + ch], dchannel_dcolor * dp[ch]);
+                        loc[(size_t)(j - r0) * 11 + 8 + ch] += dchannel_dcolor * dp[ch];
                     }
                     dL_dalpha *= T;
                     last_alpha = alpha;
@@ -493,16 +497,26 @@ void orc_render_bwd(const orc_camera* cam, int32_t N, const uint32_t* ranges, co
                     const float dG_ddelx = -gdx * cA - gdy * cB;
                     const float dG_ddely = -gdy * cC - gdx * cB;
                     const float gmx = dL_dG * dG_ddelx * ddelx_dx, gmy = dL_dG * dG_ddely * ddely_dy;
-                    atomic_addd(&a_m2[2 * g], gmx);
-                    atomic_addd(&a_m2[2 * g + 1], gmy);
-                    atomic_addd(&a_abs[2 * g], fabsf(gmx));
-                    atomic_addd(&a_abs[2 * g + 1], fabsf(gmy));
-                    atomic_addd(&a_con[3 * g], -0.5f * gdx * dx * dL_dG);
-                    atomic_addd(&a_con[3 * g + 1], -gdx * dy * dL_dG); /* TOTAL off-diagonal gradient */
-                    atomic_addd(&a_con[3 * g + 2], -0.5f * gdy * dy * dL_dG);
-                    atomic_addd(&a_op[g], G * dL_dalpha);
+                    double* lg = loc + (size_t)(j - r0) * 11;
+                    lg[0] += gmx; lg[1] += gmy; lg[2] += fabsf(gmx); lg[3] += fabsf(gmy);
+                    lg[4] += -0.5f * gdx * dx * dL_dG;
+                    lg[5] += -gdx * dy * dL_dG; /* TOTAL off-diagonal gradient */
+                    lg[6] += -0.5f * gdy * dy * dL_dG;
+                    lg[7] += G * dL_dalpha;
                 }
             }
+        for (uint32_t j = r0; j < r1; j++) {
+            const uint32_t g = point_list[j];
+            const double* lg = loc + (size_t)(j - r0) * 11;
+            if (lg[0] != 0.0) atomic_addd(&a_m2[2 * g], lg[0]);
+            if (lg[1] != 0.0) atomic_addd(&a_m2[2 * g + 1], lg[1]);
+            if (lg[2] != 0.0) atomic_addd(&a_abs[2 * g], lg[2]);
+            if (lg[3] != 0.0) atomic_addd(&a_abs[2 * g + 1], lg[3]);
+            for (int k = 0; k < 3; k++) if (lg[4 + k] != 0.0) atomic_addd(&a_con[3 * g + k], lg[4 + k]);
+            if (lg[7] != 0.0) atomic_addd(&a_op[g], lg[7]);
+            for (int k = 0; k < 3; k++) if (lg[8 + k] != 0.0) atomic_addd(&a_col[3 * g + k], lg[8 + k]);
+        }
+        free(loc);
     }
     for (size_t i = 0; i < (size_t)N; i++) {
         dL_dmean2D[2 * i] = (float)a_m2[2 * i]; dL_dmean2D[2 * i + 1] = (float)a_m2[2 * i + 1];
