@@ -315,3 +315,20 @@ def test_antialias_flag(rast):
     assert (f.conic_opacity[vis, 3] < 0.98 * plain.conic_opacity[vis, 3]).mean() > 0.3  # the flag changes the opacities
     _check_forward(sc, got, f)
     _check_backward(got, b)
+
+
+def test_zero_gaussians(rast):
+    """N = 0: the image is the background, nothing is emitted, backward is a no-op."""
+    from divshot_b200.rasterizer import GradBuffers
+    from divshot_b200.scenes import look_at_camera
+    dev = rast.device
+    cam = _cabi.make_camera(look_at_camera((0, 0, 0), (0, 0, 1), 50, 34, bg=(0.25, 0.5, 0.75)), 0)
+    z = lambda *s: torch.zeros(*s, device=dev)
+    params = {"means3D": z(0, 3), "scales": z(0, 3), "quats": z(0, 4), "opacities": z(0), "sh0": z(0, 3), "shN": z(0, 0, 3)}
+    img, radii = rast.forward(cam, params)
+    assert radii.numel() == 0 and rast.stats()["num_dups"] == 0
+    for ch, v in enumerate((0.25, 0.5, 0.75)):
+        assert torch.allclose(img[ch], torch.full_like(img[ch], v))
+    g = GradBuffers.allocate(0, 0, dev)
+    rast.backward(torch.ones(3, 34, 50, device=dev), g)
+    torch.cuda.synchronize()
