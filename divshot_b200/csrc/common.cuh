@@ -102,6 +102,11 @@ __device__ __forceinline__ float2 lds_f2(uint32_t a) {
     asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
     return v;
 }
+// 128-bit vector reduction to global memory (sm_90+: REDG.E.ADD.F32x4); `g` must be 16-byte aligned.
+__device__ __forceinline__ void red_add_f4(float* g, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
 __device__ __forceinline__ void sts_f2(uint32_t a, float x, float y) {
     asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(a), "f"(x), "f"(y) : "memory");
 }
