@@ -102,6 +102,43 @@ __device__ __forceinline__ float2 lds_f2(uint32_t a) {
     asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
     return v;
 }
+// ---- packed fp32x2 arithmetic (new on sm_100: FFMA2 / FMUL2 / FADD2 — two IEEE fp32 operations per issue slot).
+// A pair lives in one 64-bit register, .x in the low half.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float sum2(f32x2 v) {  // lo + hi
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return lo + hi;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 abs2(f32x2 a) { return a & 0x7fffffff7fffffffull; }
+__device__ __forceinline__ f32x2 lds_p2(uint32_t a) {  // 64-bit shared load of one pair
+    f32x2 v;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void lds_p4(uint32_t a, f32x2& v0, f32x2& v1) {  // 128-bit shared load of two pairs
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v0), "=l"(v1) : "r"(a));
+}
 // 128-bit vector reduction to global memory (sm_90+: REDG.E.ADD.F32x4); `g` must be 16-byte aligned.
 __device__ __forceinline__ void red_add_f4(float* g, float4 v) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)

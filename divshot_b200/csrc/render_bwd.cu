@@ -26,7 +26,7 @@ namespace dvs {
 constexpr int RB_THREADS = 256;
 constexpr int RB_ROUND = 128;  // entries staged per round (64 + 5 CTAs/SM measured no faster)
 constexpr int RB_NB = 16;      // splats buffered per warp between phase 1 and phase 2
-constexpr int RB_ROW = 33;     // padded row (bank-conflict-free in both phases)
+constexpr int RB_SROW = 34;    // floats per buffer row (32 pixels + 2: the 64-bit pair loads of phase 2 are bank-conflict-free)
 
 struct RbSmem {
     // byte offsets inside dynamic shared memory
@@ -34,10 +34,12 @@ struct RbSmem {
     static constexpr int ent = stage + RB_ROUND * 48;            // RB_ROUND * 4
     static constexpr int wmax = ent + RB_ROUND * 4;              // 8 * 4
     static constexpr int warp0 = wmax + 64;                      // per-warp region start
-    static constexpr int SW = 0;                                 // RB_NB * RB_ROW float2 {s, w} per (slot, pixel)
-    static constexpr int meta = SW + RB_NB * RB_ROW * 8;         // RB_NB * 8 words {entry word (id << 8 | mask), -, mx, my, A, B, C, -}
-    static constexpr int dp = meta + RB_NB * 8 * 4;              // 32 float4 {dL/dpix r, g, b, -}
-    static constexpr int per_warp = dp + 32 * 16;
+    static constexpr int S = 0;                                  // RB_NB rows of RB_SROW floats: s = dL/dpower per (slot, pixel)
+    static constexpr int Wt = S + RB_NB * RB_SROW * 4;           // same shape: w = alpha*T (colour weight)
+    static constexpr int meta = Wt + RB_NB * RB_SROW * 4;        // RB_NB * 8 words {entry word (id << 8 | mask), -, mx, my, A, B, C, -}
+    static constexpr int dpA = meta + RB_NB * 8 * 4;             // 16 pixel pairs x {r0, r1, g0, g1} of dL/dpix
+    static constexpr int dpB = dpA + 16 * 16;                    // 16 pixel pairs x {b0, b1}
+    static constexpr int per_warp = dpB + 16 * 8;
     static constexpr int total = warp0 + (RB_THREADS / 32) * per_warp;
 };
 
@@ -48,44 +50,80 @@ __device__ __forceinline__ void rb_phase2(uint32_t wbase, int nbuf, int lane, fl
     const int k = lane & 15, h = lane >> 4;
     const uint32_t mrow = wbase + RbSmem::meta + k * 32;
     const float2 mxy = lds_f2(mrow + 8);
-    const float X = mxy.x - px0f;
-    const float Y = mxy.y - (py0f + (float)(2 * h));
-    float cA = 0.f, cB = 0.f, cC = 0.f;
-    if (ABSGRAD) { cA = lds_f1(mrow + 16); cB = lds_f1(mrow + 20); cC = lds_f1(mrow + 24); }
-    float S0 = 0.f, Sx = 0.f, Sy = 0.f, Sxx = 0.f, Sxy = 0.f, Syy = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
-    float ax = 0.f, ay = 0.f;
-    const uint32_t swrow = wbase + RbSmem::SW + (k * RB_ROW + 16 * h) * 8;
-    const uint32_t dpb = wbase + RbSmem::dp + 16 * h * 16;
-    // 16 pixels of my half: 4 groups of 4 consecutive pixels (same row of the 8x4 sub-rectangle); the inner
-    // group is unrolled, the outer loop is not (keeps the kernel at 64 registers without spills)
-#pragma unroll 1
-    for (int jo = 0; jo < 4; jo++) {
-        const float Xg = X - (float)((4 * jo) & 7), dy = Y - (float)(jo >> 1);
+    const float X = mxy.x - px0f;                     // dx of pixel column 0 of the sub-rectangle
+    const float Y = mxy.y - (py0f + (float)(2 * h));  // dy of the first of my two pixel rows
+    const uint32_t srow = wbase + RbSmem::S + (k * RB_SROW + 16 * h) * 4;
+    const f32x2 Xp = pk2(X, X - 1.0f), m2 = pk2(-2.0f, -2.0f), m1 = pk2(-1.0f, -1.0f);
+    // My 16 pixels are 8 horizontally adjacent PAIRS (2 rows x 4 pairs); every quantity is carried as a packed
+    // fp32x2 {even pixel, odd pixel}: 10 FFMA2/FMUL2/FADD2 per pair instead of 24 scalar operations.
+    // Pass A: the six geometric moments of s.
+    f32x2 aS0 = 0ull, aSx = 0ull, aSy = 0ull, aSxx = 0ull, aSxy = 0ull, aSyy = 0ull;
+    {
+        f32x2 dyp = pk2(Y, Y);
 #pragma unroll
-        for (int ji = 0; ji < 4; ji++) {
-            const int j = 4 * jo + ji;
-            const float2 sw = lds_f2(swrow + 8 * j);   // one 64-bit load: {s, w}
-            const float4 dpx = lds_f4(dpb + 16 * j);   // one 128-bit broadcast load: dL/dpix of pixel 16h+j
-            const float s = sw.x, w = sw.y;
-            const float dx = Xg - (float)ji;
-            const float sdx = s * dx, sdy = s * dy;
-            S0 += s; Sx += sdx; Sy += sdy;
-            Sxx = fmaf(sdx, dx, Sxx); Sxy = fmaf(sdx, dy, Sxy); Syy = fmaf(sdy, dy, Syy);
-            c0 = fmaf(w, dpx.x, c0);
-            c1 = fmaf(w, dpx.y, c1);
-            c2 = fmaf(w, dpx.z, c2);
-            if (ABSGRAD) {
-                ax += fabsf(fmaf(cA, sdx, cB * sdy));
-                ay += fabsf(fmaf(cB, sdx, cC * sdy));
+        for (int r = 0; r < 2; r++) {
+            f32x2 dxp = Xp;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const f32x2 s = lds_p2(srow + (8 * r + 2 * q) * 4);
+                const f32x2 sdx = mul2(s, dxp), sdy = mul2(s, dyp);
+                aS0 = add2(aS0, s);
+                aSx = add2(aSx, sdx);
+                aSy = add2(aSy, sdy);
+                aSxx = fma2(sdx, dxp, aSxx);
+                aSxy = fma2(sdx, dyp, aSxy);
+                aSyy = fma2(sdy, dyp, aSyy);
+                if (q < 3) dxp = add2(dxp, m2);
             }
+            if (r == 0) dyp = add2(dyp, m1);
         }
     }
+    float S0 = sum2(aS0), Sx = sum2(aSx), Sy = sum2(aSy), Sxx = sum2(aSxx), Sxy = sum2(aSxy), Syy = sum2(aSyy);
     S0 += __shfl_xor_sync(0xffffffffu, S0, 16); Sx += __shfl_xor_sync(0xffffffffu, Sx, 16);
     Sy += __shfl_xor_sync(0xffffffffu, Sy, 16); Sxx += __shfl_xor_sync(0xffffffffu, Sxx, 16);
     Sxy += __shfl_xor_sync(0xffffffffu, Sxy, 16); Syy += __shfl_xor_sync(0xffffffffu, Syy, 16);
+    // Pass B: colour sums  sum_pixels w * dL/dpix[ch].
+    float c0, c1, c2;
+    {
+        f32x2 a0 = 0ull, a1 = 0ull, a2 = 0ull;
+        const uint32_t wrow = srow + (RbSmem::Wt - RbSmem::S);
+        const uint32_t pa = wbase + RbSmem::dpA + 8 * h * 16, pb = wbase + RbSmem::dpB + 8 * h * 8;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const f32x2 w = lds_p2(wrow + 8 * q);
+            f32x2 rr, gg;
+            lds_p4(pa + 16 * q, rr, gg);
+            const f32x2 bb = lds_p2(pb + 8 * q);
+            a0 = fma2(w, rr, a0);
+            a1 = fma2(w, gg, a1);
+            a2 = fma2(w, bb, a2);
+        }
+        c0 = sum2(a0); c1 = sum2(a1); c2 = sum2(a2);
+    }
     c0 += __shfl_xor_sync(0xffffffffu, c0, 16); c1 += __shfl_xor_sync(0xffffffffu, c1, 16);
     c2 += __shfl_xor_sync(0xffffffffu, c2, 16);
-    if (ABSGRAD) { ax += __shfl_xor_sync(0xffffffffu, ax, 16); ay += __shfl_xor_sync(0xffffffffu, ay, 16); }
+    float ax = 0.f, ay = 0.f;
+    if (ABSGRAD) {  // Pass C: sum_pixels |dL/dmean2D contribution| (densification statistic), natural-units conic
+        const f32x2 cA = pk2(lds_f1(mrow + 16), lds_f1(mrow + 16)), cB = pk2(lds_f1(mrow + 20), lds_f1(mrow + 20)),
+                    cC = pk2(lds_f1(mrow + 24), lds_f1(mrow + 24));
+        f32x2 bx = 0ull, by = 0ull;
+        f32x2 dyp = pk2(Y, Y);
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            f32x2 dxp = Xp;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const f32x2 s = lds_p2(srow + (8 * r + 2 * q) * 4);
+                const f32x2 sdx = mul2(s, dxp), sdy = mul2(s, dyp);
+                bx = add2(bx, abs2(fma2(cA, sdx, mul2(cB, sdy))));
+                by = add2(by, abs2(fma2(cB, sdx, mul2(cC, sdy))));
+                if (q < 3) dxp = add2(dxp, m2);
+            }
+            if (r == 0) dyp = add2(dyp, m1);
+        }
+        ax = sum2(bx); ay = sum2(by);
+        ax += __shfl_xor_sync(0xffffffffu, ax, 16); ay += __shfl_xor_sync(0xffffffffu, ay, 16);
+    }
     // both halves hold the totals: half 0 sends floats 0-3 of the 48-byte record, half 1 floats 4-7, as ONE
     // 128-bit vector reduction (REDG.E.ADD.F32x4) — 2 reduction instructions per 16 splats instead of 9, and
     // ~4x fewer L1TEX tag wavefronts (every lane's record is a different cache line)
@@ -132,7 +170,12 @@ render_bwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const uint32_
         dp1 = __ldg(dL_dpix + P + pix);
         dp2 = __ldg(dL_dpix + 2 * P + pix);
     }
-    sts_f4(wbase + RbSmem::dp + lane * 16, make_float4(dp0, dp1, dp2, 0.f));
+    {   // dL/dpix of the warp's 32 pixels, pair-interleaved for the packed loads of phase 2
+        const uint32_t pr = (uint32_t)(lane >> 1), odd = (uint32_t)(lane & 1);
+        sts_f1(wbase + RbSmem::dpA + pr * 16 + odd * 4, dp0);
+        sts_f1(wbase + RbSmem::dpA + pr * 16 + 8 + odd * 4, dp1);
+        sts_f1(wbase + RbSmem::dpB + pr * 8 + odd * 4, dp2);
+    }
     const float nTf_bg = -T_final * (cam.bg[0] * dp0 + cam.bg[1] * dp1 + cam.bg[2] * dp2);
     float T = T_final;
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
@@ -150,7 +193,7 @@ render_bwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const uint32_
     const uint32_t wbit = 1u << warp;
     int nbuf = 0;
     // per-lane row addresses of the phase-1 buffer, kept in registers (no re-derivation from tid per pair)
-    uint32_t mySW = wbase + RbSmem::SW + lane * 8;
+    uint32_t mySW = wbase + RbSmem::S + lane * 4;
     uint32_t mmeta = wbase + RbSmem::meta;
     asm volatile("" : "+r"(mySW), "+r"(mmeta));
 
@@ -225,7 +268,8 @@ render_bwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const uint32_
                     dL_dalpha = fmaf(dL_dalpha, T, nTf_bg * rinv);
                     s = a_raw * dL_dalpha;  // dL/dpower (the 0.99 clamp is straight-through)
                 }
-                sts_f2(mySW + nbuf * (RB_ROW * 8), s, wgt);
+                sts_f1(mySW + nbuf * (RB_SROW * 4), s);
+                sts_f1(mySW + nbuf * (RB_SROW * 4) + (RbSmem::Wt - RbSmem::S), wgt);
                 {   // slot metadata, stored by all lanes to one address with one value (a single wavefront each):
                     // the entry word comes by shuffle from the lane that owns the ballot bit
                     const uint32_t mrow = mmeta + nbuf * 32;
