@@ -158,7 +158,8 @@ render_bwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const uint32_
     const int px0 = tx * TILE + (warp & 1) * 8, py0 = ty * TILE + (warp >> 1) * 4;
     const int px = px0 + (lane & 7), py = py0 + (lane >> 3);
     const bool inside = px < cam.W && py < cam.H;
-    const float pxf = (float)px, pyf = (float)py, px0f = (float)px0, py0f = (float)py0;
+    const float px0f = (float)px0, py0f = (float)py0;
+    const f32x2 npxy = pk2(-(float)px, -(float)py);
     const size_t P = (size_t)cam.W * cam.H;
     const size_t pix = (size_t)py * cam.W + px;
 
@@ -221,8 +222,9 @@ render_bwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const uint32_
         if (threadIdx.x < RB_ROUND) {
             sts_u1(se + threadIdx.x * 4, e_n);
             if (e_n & 0xffu) {
-                sts_f4(sb + threadIdx.x * 48, q0_n);
-                sts_f4(sb + threadIdx.x * 48 + 16, q1_n);
+                // staged as {mx, my, A2, C2} {B2, lo, r, g} (register pairs for FADD2 / FMUL2, as in the forward)
+                sts_f4(sb + threadIdx.x * 48, make_float4(q0_n.x, q0_n.y, q0_n.z, q1_n.x));
+                sts_f4(sb + threadIdx.x * 48 + 16, make_float4(q0_n.w, q1_n.y, q1_n.z, q1_n.w));
                 sts_f1(sb + threadIdx.x * 48 + 32, b_n);
             }
         }
@@ -240,11 +242,15 @@ render_bwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const uint32_
                 bits &= ~(1u << j);
                 const int k = c + j;
                 const uint32_t ea = sb + k * 48;
-                const float4 q0 = lds_f4(ea);
-                const float4 q1 = lds_f4(ea + 16);
-                const float dx = q0.x - pxf, dy = q0.y - pyf;
-                const float t = fmaf(q0.w, dy, q0.z * dx);
-                const float pw = fmaf(q1.x * dy, dy, t * dx);
+                f32x2 mxy, AC;
+                lds_p4(ea, mxy, AC);
+                const float4 q1 = lds_f4(ea + 16);  // {B2, lo, r, g}
+                float dx, dy, adx, cdy;
+                const f32x2 d = add2(mxy, npxy);    // same arithmetic, bit for bit, as the forward kernel
+                upk2(d, dx, dy);
+                upk2(mul2(AC, d), adx, cdy);
+                const float t = fmaf(q1.x, dy, adx);
+                const float pw = fmaf(cdy, dy, t * dx);
                 const float ee = pw + q1.y;
                 const bool act = k < lastr && pw <= 0.0f && ee >= ALPHA_MIN_LOG2;
                 if (!__any_sync(0xffffffffu, act)) continue;
@@ -274,10 +280,12 @@ render_bwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const uint32_
                     // the entry word comes by shuffle from the lane that owns the ballot bit
                     const uint32_t mrow = mmeta + nbuf * 32;
                     sts_u1(mrow, __shfl_sync(0xffffffffu, myw, j));
-                    sts_f2(mrow + 8, q0.x, q0.y);
+                    sts_p2(mrow + 8, mxy);
                     if (ABSGRAD) {  // natural-units conic for the |dL/dmean2D| statistic
-                        sts_f2(mrow + 16, q0.z * (-2.0f * LN2), q0.w * (-LN2));
-                        sts_f1(mrow + 24, q1.x * (-2.0f * LN2));
+                        float A2, C2;
+                        upk2(AC, A2, C2);
+                        sts_f2(mrow + 16, A2 * (-2.0f * LN2), q1.x * (-LN2));
+                        sts_f1(mrow + 24, C2 * (-2.0f * LN2));
                     }
                 }
                 if (++nbuf == RB_NB) {

@@ -38,7 +38,7 @@ render_fwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const uint32_
     const int px = tx * TILE + (warp & 1) * 8 + (lane & 7);
     const int py = ty * TILE + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = px < cam.W && py < cam.H;
-    const float pxf = (float)px, pyf = (float)py;
+    const f32x2 npxy = pk2(-(float)px, -(float)py);
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
     uint32_t last = 0;
     bool done = !inside;
@@ -59,8 +59,9 @@ render_fwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const uint32_
             const float4* r = rec + 3 * (size_t)(e >> 8);
             const float4 q0 = __ldg(r), q1 = __ldg(r + 1);
             const float b = __ldg(reinterpret_cast<const float*>(r + 2));
-            sts_f4(sb + threadIdx.x * 48, q0);
-            sts_f4(sb + threadIdx.x * 48 + 16, q1);
+            // staged as {mx, my, A2, C2} {B2, lo, r, g}: {mx, my} and {A2, C2} are then register pairs for FADD2 / FMUL2
+            sts_f4(sb + threadIdx.x * 48, make_float4(q0.x, q0.y, q0.z, q1.x));
+            sts_f4(sb + threadIdx.x * 48 + 16, make_float4(q0.w, q1.y, q1.z, q1.w));
             sts_f1(sb + threadIdx.x * 48 + 32, b);
         }
         __syncthreads();
@@ -74,11 +75,15 @@ render_fwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const uint32_
                     bits &= bits - 1;
                     const int k = c + j;
                     const uint32_t ea = sb + k * 48;
-                    const float4 q0 = lds_f4(ea);
-                    const float4 q1 = lds_f4(ea + 16);
-                    const float dx = q0.x - pxf, dy = q0.y - pyf;
-                    const float t = fmaf(q0.w, dy, q0.z * dx);
-                    const float pw = fmaf(q1.x * dy, dy, t * dx);
+                    f32x2 mxy, AC;
+                    lds_p4(ea, mxy, AC);
+                    const float4 q1 = lds_f4(ea + 16);  // {B2, lo, r, g}
+                    float dx, dy, adx, cdy;
+                    const f32x2 d = add2(mxy, npxy);    // {dx, dy}: one FADD2
+                    upk2(d, dx, dy);
+                    upk2(mul2(AC, d), adx, cdy);        // {A2 dx, C2 dy}: one FMUL2
+                    const float t = fmaf(q1.x, dy, adx);
+                    const float pw = fmaf(cdy, dy, t * dx);
                     const float ee = pw + q1.y;
                     if (!done && pw <= 0.0f && ee >= ALPHA_MIN_LOG2) {
                         const float alpha = fminf(0.99f, ex2_approx(ee));
