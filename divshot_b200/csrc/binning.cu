@@ -435,7 +435,10 @@ cudaError_t launch_tile_sort(int T, uint32_t bin_stride, const uint32_t* tile_ba
                              16384 * 8);
         attr_done = true;
     }
-    const int g_small = min(T, 148 * 6), g_mid = min(T, 148 * 3), g_long = min(T, 148 * 2), g_big = min(T, 148);
+#ifndef DVS_SORT_GMULT
+#define DVS_SORT_GMULT 1
+#endif
+    const int g_small = min(T, 148 * 6 * DVS_SORT_GMULT), g_mid = min(T, 148 * 3 * DVS_SORT_GMULT), g_long = min(T, 148 * 2), g_big = min(T, 148);
     tile_bucket_sort_kernel<256, 1024, true><<<g_small, 256, bucket_smem_bytes<1024, true>(), st>>>(T, bin_stride, 0, tile_base, bins, plist, info, class_tiles);
     tile_bucket_sort_kernel<512, 2048, true><<<g_mid, 512, bucket_smem_bytes<2048, true>(), st>>>(T, bin_stride, 1, tile_base, bins, plist, info, class_tiles);
     if (max_len > 2048u)

@@ -24,7 +24,13 @@
 namespace dvs {
 
 constexpr int RB_THREADS = 256;
-constexpr int RB_ROUND = 128;  // entries staged per round (64 + 5 CTAs/SM measured no faster)
+#ifndef DVS_RB_ROUND
+#define DVS_RB_ROUND 256
+#endif
+#ifndef DVS_RB_MINCTA
+#define DVS_RB_MINCTA 4
+#endif
+constexpr int RB_ROUND = DVS_RB_ROUND;  // entries staged per round (128: +1%; 64 with 5 CTAs/SM: no faster)
 constexpr int RB_NB = 16;      // splats buffered per warp between phase 1 and phase 2
 constexpr int RB_SROW = 34;    // floats per buffer row (32 pixels + 2: the 64-bit pair loads of phase 2 are bank-conflict-free)
 
@@ -140,7 +146,7 @@ __device__ __forceinline__ void rb_phase2(uint32_t wbase, int nbuf, int lane, fl
 }
 
 template <bool ABSGRAD>
-__global__ void __launch_bounds__(RB_THREADS, 4)
+__global__ void __launch_bounds__(RB_THREADS, DVS_RB_MINCTA)
 render_bwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const uint32_t* __restrict__ plist,
                   const float4* __restrict__ rec, const float* __restrict__ final_T,
                   const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpix,

@@ -21,7 +21,11 @@ namespace dvs {
 
 constexpr int RF_THREADS = 256;
 
+#ifdef DVS_RF_MINCTA
+__global__ void __launch_bounds__(RF_THREADS, DVS_RF_MINCTA)
+#else
 __global__ void __launch_bounds__(RF_THREADS)
+#endif
 render_fwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const uint32_t* __restrict__ plist,
                   const float4* __restrict__ rec, float* __restrict__ out_color, float* __restrict__ final_T,
                   uint32_t* __restrict__ n_contrib, const uint32_t* __restrict__ info) {
