@@ -77,10 +77,11 @@ class ClockSampler:
 
 
 # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of each stage's kernels at c3 on one B200,
-# from the committed `ncu --set full` capture profiles/r1_v3_step_ncu_full.md (MB).  Only valid for workload c3.
-NCU_TRAFFIC_MB_C3 = {"preprocess_fwd": 236.83 + 97.70, "binning_sort": 0.23 + 61.45 + 3.39 + 0.1,
-                     "render_fwd": 39.38 + 3.09, "render_bwd": 62.00 + 1.60, "preprocess_bwd": 288.09 + 228.42}
-NCU_ISSUE_ACTIVE_PCT_C3 = {"preprocess_fwd": 72.9, "render_fwd": 91.2, "render_bwd": 73.1, "preprocess_bwd": 49.6}
+# from the committed `ncu --set full` capture profiles/r1_v4_step_ncu_full.md (MB).  Only valid for workload c3.
+NCU_TRAFFIC_MB_C3 = {"preprocess_fwd": 236.79 + 96.09, "binning_sort": 0.23 + 61.45 + 4.09 + 0.1,
+                     "render_fwd": 39.36 + 3.66, "render_bwd": 62.05 + 2.20, "preprocess_bwd": 288.06 + 228.73}
+NCU_ISSUE_ACTIVE_PCT_C3 = {"preprocess_fwd": 71.3, "render_fwd": 89.1, "render_bwd": 72.6, "preprocess_bwd": 50.0}
+NCU_SMEM_WAVEFRONT_PCT_C3 = {"render_bwd": 64.6}  # l1tex__data_pipe_lsu_wavefronts_mem_shared, % of peak
 
 
 def algorithmic_bytes(N, K, V, D, T, P):
@@ -311,12 +312,14 @@ def main():
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": dom_gbs, "peak": peak, "unit": "GB/s",
                      "frac": dom_gbs / peak,
                      "traffic": (NCU_TRAFFIC_MB_C3.get(dominant, 0) * 1e6 if WORKLOAD == "c3" else None),
-                     "traffic_source": "profiles/r1_v3_step_ncu_full.md (ncu --set full, per launch)",
+                     "traffic_source": "profiles/r1_v4_step_ncu_full.md (ncu --set full, per launch)",
                      "issue_active_pct": NCU_ISSUE_ACTIVE_PCT_C3.get(dominant) if WORKLOAD == "c3" else None,
+                     "smem_wavefront_pct": NCU_SMEM_WAVEFRONT_PCT_C3.get(dominant) if WORKLOAD == "c3" else None,
                      "peak_source": peak_src,
                      "note": "algorithmic bytes per SURVEY.md §8(d) / CUDA-event stage time.  The dominant kernel is the "
                              "compositing backward: 256*D potential pair evaluations against ~0.12 GB of compulsory "
-                             "traffic, so it is bound by instruction issue (see issue_active_pct), not by HBM; the "
+                             "traffic, so it is bound by instruction issue and shared-memory wavefronts (see issue_active_pct, "
+                             "smem_wavefront_pct), not by HBM; the "
                              "streaming stages' HBM fractions are in `stages`"},
         "roofline_step": ({"achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak,
                            "alg_bytes_per_step": total_bytes} if step_gbs else None),

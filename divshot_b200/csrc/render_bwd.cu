@@ -7,17 +7,18 @@
 //   * same tiling / sub-tile masks as the forward: warp w owns an 8x4-pixel sub-rectangle and only touches
 //     splats whose footprint reaches it and that lie in front of the warp's deepest last-contributor;
 //   * PHASE 1 (lane = pixel): the reverse walk proper.  Per (pixel, splat) pair only two numbers are
-//     produced: s = dL/dpower and w = alpha*T (colour weight).  They go, as one 64-bit store, to a per-warp
-//     shared-memory buffer SW[slot][pixel] (16 splats deep) — no cross-lane reduction here;
+//     produced: s = dL/dpower and w = alpha*T (colour weight).  They go to two per-warp shared-memory
+//     buffers S[slot][pixel], Wt[slot][pixel] (16 splats deep) — no cross-lane reduction here;
 //   * PHASE 2 (lane = splat x pixel-half): every 16 buffered splats the lanes switch roles.  Lane (k, h)
-//     walks 16 of the 32 pixels for splat k and accumulates the nine sums
+//     walks 16 of the 32 pixels for splat k as 8 horizontally adjacent PAIRS held in packed fp32x2
+//     registers (FFMA2 / FMUL2 / FADD2, new on sm_100) and accumulates the nine sums
 //         S0 = sum s, Sx = sum s dx, Sy = sum s dy, Sxx, Sxy, Syy, and sum w*dL/dpix[0..2]
-//     in registers (18 instructions per pixel, no shuffles), the two halves meet with one shuffle per sum
-//     and leave with RED.ADD.F32 into the 48-byte screen-gradient record.
+//     (10 packed operations per pixel pair, no shuffles); the two halves meet with one shuffle per sum and
+//     each leaves with ONE 128-bit vector reduction (REDG.E.ADD.F32x4) into the 48-byte screen-gradient record;
 //   * all per-splat constant factors (conic, W/2, -1/2, 1/opacity) are applied once per splat in the
 //     preprocess backward, not per pair.
-// Versus a shuffle-tree reduction per (warp, splat) this is ~2x fewer issued instructions and ~20x fewer
-// SHFL.  Bound: issue (FMA pipe), not HBM.
+// Versus a shuffle-tree reduction per (warp, splat) this is ~2.5x fewer issued instructions and ~20x fewer
+// SHFL.  Bound: instruction issue and shared-memory wavefronts (profiles/r1_v4_step_ncu_full.md), not HBM.
 #include "common.cuh"
 #include "kernels.h"
 
