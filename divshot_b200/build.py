@@ -82,18 +82,33 @@ def build_rast(force: bool = False, verbose: bool = False) -> str:
     return so
 
 
+def build_model_io(force: bool = False) -> str:
+    """model_io.o: the host-only model writers/readers (include/dvs_model_io.h).  g++, -ffp-contract=off and the
+    x86-64 baseline ISA (no FMA): its quantisers are literal operation sequences, byte-exact vs the reference."""
+    os.makedirs(OBJ, exist_ok=True)
+    src = os.path.join(CSRC, "model_io.cpp")
+    obj = os.path.join(OBJ, "model_io.o")
+    if force or _stale(obj, [src, os.path.join(ROOT, "include", "dvs_model_io.h")]):
+        subprocess.check_call([host_cxx(), "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-fvisibility=hidden",
+                               "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), "-c", src, "-o", obj])
+    return obj
+
+
 def build_gstrain(force: bool = False) -> str:
-    """libgstrain.so: the trainer plugin (nine C symbols) + the rasterizer objects, one self-contained library."""
+    """libgstrain.so: the trainer plugin (nine C symbols) + the rasterizer objects + the model writers/readers,
+    one self-contained library."""
     build_rast(force)
+    io_obj = build_model_io(force)
     src = os.path.join(CSRC, "gstrain.cu")
     hdr = os.path.join(ROOT, "include", "gaussian_trainer_scene.hpp")
     obj = os.path.join(OBJ, "gstrain.o")
-    if force or _stale(obj, [src, hdr, os.path.join(ROOT, "include", "dvs_rast.h")]):
+    if force or _stale(obj, [src, hdr, os.path.join(ROOT, "include", "dvs_rast.h"),
+                             os.path.join(ROOT, "include", "dvs_model_io.h")]):
         subprocess.check_call([nvcc(), "-ccbin", host_cxx(), *ARCH, *COMMON, "-c", src, "-o", obj])
-    objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in CU_SOURCES] + [obj]
+    objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in CU_SOURCES] + [obj, io_obj]
     so = os.path.join(OUT, "libgstrain.so")
     if force or _stale(so, objs):
-        subprocess.check_call([nvcc(), "-ccbin", host_cxx(), *ARCH, "-shared", "-o", so, *objs, "-cudart", "static"])
+        subprocess.check_call([nvcc(), "-ccbin", host_cxx(), *ARCH, "-shared", "-o", so, *objs, "-cudart", "static", "-lz"])
     return so
 
 

@@ -30,6 +30,7 @@
 #include <string>
 #include <vector>
 
+#include "dvs_model_io.h"
 #include "dvs_rast.h"
 #include "gaussian_trainer_scene.hpp"
 
@@ -498,61 +499,17 @@ void GaussianTrainerScene::trainStep() {
     curIteration++;
 }
 
-// ---- model writers.  Dispatch by extension like diverse/source/assets/gaussian_model.cpp:439-463.
-//   .ply   : row layout of external/tinygsplat/tiny_gsplat.cpp:168-241 (raw parameters, 59 floats per vertex)
-//   .splat : 32-byte records of tiny_gsplat.cpp:243-291 (position, exp(scale), RGBA8 from the DC term and
-//            sigmoid(opacity), normalised quaternion as 4 x u8)
-static bool write_ply(const std::string& path, int64_t N, const float* pos, const float* sh0, const float* shn,
-                      const float* op, const float* sc, const float* rot) {
-    std::ofstream out(path, std::ios::binary);
-    if (!out.good()) return false;
-    out << "ply\nformat binary_little_endian 1.0\ncomment generated by divshot_b200 gstrain\n";
-    out << "element vertex " << N << "\nproperty float x\nproperty float y\nproperty float z\n";
-    for (int i = 0; i < 3; i++) out << "property float f_dc_" << i << "\n";
-    for (int i = 0; i < 45; i++) out << "property float f_rest_" << i << "\n";
-    out << "property float opacity\n";
-    for (int i = 0; i < 3; i++) out << "property float scale_" << i << "\n";
-    for (int i = 0; i < 4; i++) out << "property float rot_" << i << "\n";
-    out << "end_header\n";
-    std::vector<float> row(59);
-    for (int64_t i = 0; i < N; i++) {
-        for (int k = 0; k < 3; k++) row[k] = pos[3 * i + k];
-        for (int k = 0; k < 3; k++) row[3 + k] = sh0[3 * i + k];
-        for (int j = 0; j < 15; j++)  // channel-major rest block (tiny_gsplat.cpp:231-236)
-            for (int c = 0; c < 3; c++) row[6 + c * 15 + j] = shn[(size_t)45 * i + 3 * j + c];
-        row[51] = op[i];
-        for (int k = 0; k < 3; k++) row[52 + k] = sc[3 * i + k];
-        for (int k = 0; k < 4; k++) row[55 + k] = rot[4 * i + k];
-        out.write(reinterpret_cast<const char*>(row.data()), 59 * sizeof(float));
-    }
-    return out.good();
-}
-
-static bool write_splat(const std::string& path, int64_t N, const float* pos, const float* sh0, const float* op,
-                        const float* sc, const float* rot) {
-    std::ofstream out(path, std::ios::binary);
-    if (!out.good()) return false;
-    auto u8 = [](float v) { return (unsigned char)std::min(255.f, std::max(0.f, v)); };
-    unsigned char rec[32];
-    for (int64_t i = 0; i < N; i++) {
-        float f[6] = {pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], std::exp(sc[3 * i]), std::exp(sc[3 * i + 1]),
-                      std::exp(sc[3 * i + 2])};
-        std::memcpy(rec, f, 24);
-        for (int k = 0; k < 3; k++) rec[24 + k] = u8((0.5f + 0.28209479177387814f * sh0[3 * i + k]) * 255.f);
-        rec[27] = u8(255.f / (1.f + std::exp(-op[i])));
-        float n2 = 0;
-        for (int k = 0; k < 4; k++) n2 += rot[4 * i + k] * rot[4 * i + k];
-        const float inv = n2 > 0 ? 1.f / std::sqrt(n2) : 0.f;
-        for (int k = 0; k < 4; k++) rec[28 + k] = u8(rot[4 * i + k] * inv * 128.f + 128.f);
-        out.write(reinterpret_cast<const char*>(rec), 32);
-    }
-    return out.good();
-}
-
+// ---- model writers: csrc/model_io.cpp behind include/dvs_model_io.h — PLY, .splat, compressed
+// PLY, .dvsplat and .spz, byte-identical to external/tinygsplat's writers.  Dispatch by extension like
+// diverse/source/assets/gaussian_model.cpp:439-463; anything else is written as PLY.
 static bool write_model(const std::string& path, int64_t N, const float* pos, const float* sh0, const float* shn,
-                        const float* op, const float* sc, const float* rot) {
-    const bool splat = path.size() >= 6 && path.compare(path.size() - 6, 6, ".splat") == 0;
-    return splat ? write_splat(path, N, pos, sh0, op, sc, rot) : write_ply(path, N, pos, sh0, shn, op, sc, rot);
+                        const float* op, const float* sc, const float* rot, bool antialiased) {
+    int fmt = dvs_model_format_from_path(path.c_str());
+    if (fmt == DVS_FMT_AUTO) fmt = DVS_FMT_PLY;
+    const int rc = dvs_model_write(path.c_str(), fmt, N, pos, sh0, shn, op, sc, rot, nullptr,
+                                   antialiased ? DVS_IO_ANTIALIASED : 0u);
+    if (rc != 0) std::fprintf(stderr, "gstrain: %s\n", dvs_model_io_last_error());
+    return rc == 0;
 }
 
 void GaussianTrainerScene::saveGaussianModel() {
@@ -560,7 +517,8 @@ void GaussianTrainerScene::saveGaussianModel() {
     if (config_.modelPath.empty() || I.N == 0) return;
     const auto pos = getGaussianPositionCpu(), sh0 = getGaussianSH0Cpu(), shn = getGaussianSHNCpu();
     const auto op = getGaussianOpcaitiesCpu(), sc = getGaussianScalingsCpu(), rot = getGaussianRotationsCpu();
-    if (!write_model(config_.modelPath, I.N, pos.data(), sh0.data(), shn.data(), op.data(), sc.data(), rot.data()))
+    if (!write_model(config_.modelPath, I.N, pos.data(), sh0.data(), shn.data(), op.data(), sc.data(), rot.data(),
+                     config_.mipAntiliased))
         std::fprintf(stderr, "gstrain: cannot write %s\n", config_.modelPath.c_str());
 }
 
@@ -608,7 +566,7 @@ GS_EXPORT void gstrain_photometric_loss(const float* render, const float* target
 // test hook (host pointers): the model writers without a trainer / GPU
 GS_EXPORT int gstrain_write_model(const char* path, long long N, const float* pos, const float* sh0, const float* shn,
                                   const float* op, const float* sc, const float* rot) {
-    return write_model(path, N, pos, sh0, shn, op, sc, rot) ? 0 : -1;
+    return write_model(path, N, pos, sh0, shn, op, sc, rot, false) ? 0 : -1;
 }
 GS_EXPORT const char* get_description() { return "gstrain: B200-native 3DGS trainer plugin (divshot_b200)"; }
 GS_EXPORT void* create_instance() { return nullptr; }

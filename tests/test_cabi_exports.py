@@ -31,6 +31,17 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in lib.dvs_rast_version()
 
 
+def test_plugin_library_exports_every_model_io_symbol():
+    """include/dvs_model_io.h is exported by libgstrain.so, which loads without a GPU."""
+    from divshot_b200 import build
+    src = open(os.path.join(ROOT, "include", "dvs_model_io.h")).read()
+    names = sorted(set(re.findall(r"DVS_API\s+[\w\s\*]+?\b(dvs_model_\w+)\s*\(", src)))
+    assert names == ["dvs_model_format_from_path", "dvs_model_io_last_error", "dvs_model_read", "dvs_model_write"]
+    lib = ctypes.CDLL(build.build_gstrain())
+    for n in names:
+        assert hasattr(lib, n), f"libgstrain.so does not export {n}"
+
+
 def test_no_cpu_fallback_without_cuda():
     import torch
     if torch.cuda.is_available():
