@@ -14,6 +14,11 @@
  * and the tensor conventions of the only in-tree consumer).  Its analytic backward is pinned
  * independently by a float64 torch-autograd re-expression (tests/autograd_ref.py) and by
  * closed-form known-answer cases (tests/test_oracle_kat.py).
+ * PARTLY PINNED since: the reference's shader functions for cov3D, EWA cov2D (clamp, blur),
+ * ndc2Pix, SH evaluation and the anti-aliasing factor are compiled as C++ from /root/reference
+ * (oracle/_ref/libhlsl_ref.so) and orc_preprocess_fwd is checked against them
+ * (tests/test_oracle_vs_reference_hlsl.py).  Culling, radius, tile rects, binning order,
+ * compositing and both backward passes have no executable counterpart in the reference.
  *
  * Conventions: matrices are flat float[16], element m[4*c + r] = row r,
  * column c of the column-vector 4x4 (same indexing as gsplat_vs.hlsl:54-72).  Quaternion order
