@@ -103,9 +103,12 @@ def build_gstrain(force: bool = False) -> str:
     hdr = os.path.join(ROOT, "include", "gaussian_trainer_scene.hpp")
     obj = os.path.join(OBJ, "gstrain.o")
     if force or _stale(obj, [src, hdr, os.path.join(ROOT, "include", "dvs_rast.h"),
-                             os.path.join(ROOT, "include", "dvs_model_io.h")]):
+                             os.path.join(ROOT, "include", "dvs_model_io.h"), os.path.join(CSRC, "densify.h")]):
         subprocess.check_call([nvcc(), "-ccbin", host_cxx(), *ARCH, *COMMON, "-c", src, "-o", obj])
-    objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in CU_SOURCES] + [obj, io_obj]
+    dsrc, dobj = os.path.join(CSRC, "densify.cu"), os.path.join(OBJ, "densify.o")  # trainer refinement step (F1)
+    if force or _stale(dobj, [dsrc, os.path.join(CSRC, "densify.h"), os.path.join(CSRC, "densify_ops.h")]):
+        subprocess.check_call([nvcc(), "-ccbin", host_cxx(), *ARCH, *COMMON, "-c", dsrc, "-o", dobj])
+    objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in CU_SOURCES] + [obj, io_obj, dobj]
     so = os.path.join(OUT, "libgstrain.so")
     if force or _stale(so, objs):
         subprocess.check_call([nvcc(), "-ccbin", host_cxx(), *ARCH, "-shared", "-o", so, *objs, "-cudart", "static", "-lz"])

@@ -7,7 +7,11 @@
 // rasterize forward (dvs_rast_forward), photometric loss (1-w)*L1 + w*(1-SSIM) with w = ssimWeight (main.cpp:24),
 // rasterize backward (dvs_rast_backward), fused Adam with the per-group learning rates of GaussianTrainConfig —
 // and keeps every tensor device-resident.
-// Densification / pruning / COLMAP SfM / mesh export of the closed trainer are NOT rebuilt here.
+// Refinement (csrc/densify.cu): `densifyStrategy` 1 = MCMC (relocation of dead Gaussians, 5 % growth up
+// to `capMax`, exploration noise `noiselr`, opacity/scale regularisers), 0 / 2 = ADC (clone / split / prune on the
+// accumulated screen-space gradient, opacity reset every `resetAlphaEvery`).  It acts every `refineEvery` iterations
+// for warmupLength < iteration < refineStopIter; a run that ends before `warmupLength` never enters it.
+// COLMAP SfM / mesh export of the closed trainer are NOT rebuilt here.
 //
 // Data sources accepted by load_train_data:
 //   "synthetic:N=100000,W=800,H=600,views=8,deg=1,seed=7"  — a random ground-truth splat scene is rendered with
@@ -30,6 +34,7 @@
 #include <string>
 #include <vector>
 
+#include "densify.h"
 #include "dvs_model_io.h"
 #include "dvs_rast.h"
 #include "gaussian_trainer_scene.hpp"
@@ -202,7 +207,7 @@ struct Arena {  // one flat buffer, six 16-byte-aligned views (same order as Gra
         off_scales = take(3 * N); off_sh0 = take(3 * N); off_opac = take(N);
         total = (o + 3) / 4 * 4;
     }
-    void alloc(int64_t N) {
+    void alloc(int64_t N) {  // N = capacity in Gaussians; the live count is GaussianTrainerImpl::N
         layout(N);
         ck(cudaMalloc(&flat, total * sizeof(float)), "cudaMalloc arena");
         ck(cudaMemset(flat, 0, total * sizeof(float)), "memset arena");
@@ -256,6 +261,19 @@ struct GaussianTrainerImpl {
     size_t img_cap = 0;
     std::mt19937 rng{1234};
     float scene_extent = 1.f;
+    // refinement (densify.cu): arenas hold `capacity` Gaussians, N of them live
+    int64_t capacity = 0;
+    dvs_densify::Workspace* dws = nullptr;
+    float* d_accum = nullptr;      // [capacity] ADC: sum of ||dL/dmean2D||
+    float* d_denom = nullptr;      // [capacity] ADC: visibility count
+    float* d_mean2D = nullptr;     // [capacity,2] screen-space gradient of the last backward
+    float* d_mean2D_abs = nullptr; // [capacity,2] (useAbsGrad)
+    int32_t* d_radii = nullptr;    // [capacity] radii of the last forward
+    bool refine_enabled = false;   // the schedule reaches the refinement window (set before upload)
+    bool resync_next = false;      // N changed: the next forward re-sizes the binning arena synchronously
+    dvs_densify::RefineReport last_report;
+
+    dvs_densify::Tensors T(const Arena& a) const { return dvs_densify::Tensors{a.means(), a.scales(), a.quats(), a.opac(), a.sh0(), a.shN()}; }
 
     dvs_params P() const { return dvs_params{params.means(), params.scales(), params.quats(), params.opac(), params.sh0(), params.shN()}; }
     dvs_grads G() const { return dvs_grads{grads.means(), grads.scales(), grads.quats(), grads.opac(), grads.sh0(), grads.shN(), nullptr, nullptr}; }
@@ -273,7 +291,18 @@ struct GaussianTrainerImpl {
     void upload(const std::vector<float>& means, const std::vector<float>& lscales, const std::vector<float>& quats,
                 const std::vector<float>& logit, const std::vector<float>& sh0, const std::vector<float>& shN) {
         N = (int64_t)logit.size();
-        params.alloc(N); grads.alloc(N); m1.alloc(N); m2.alloc(N);
+        capacity = std::max(N, capacity);
+        params.alloc(capacity); grads.alloc(capacity); m1.alloc(capacity); m2.alloc(capacity);
+        if (refine_enabled) {  // refinement statistics and the buffers they are fed from
+            ck(cudaMalloc(&d_accum, capacity * sizeof(float)), "cudaMalloc accum");
+            ck(cudaMalloc(&d_denom, capacity * sizeof(float)), "cudaMalloc denom");
+            ck(cudaMalloc(&d_mean2D, 2 * capacity * sizeof(float)), "cudaMalloc mean2D");
+            ck(cudaMalloc(&d_mean2D_abs, 2 * capacity * sizeof(float)), "cudaMalloc mean2D_abs");
+            ck(cudaMalloc(&d_radii, capacity * sizeof(int32_t)), "cudaMalloc radii");
+            ck(cudaMemset(d_accum, 0, capacity * sizeof(float)), "memset accum");
+            ck(cudaMemset(d_denom, 0, capacity * sizeof(float)), "memset denom");
+            dws = dvs_densify::workspace_create();
+        }
         auto up = [&](float* d, const std::vector<float>& h) {
             ck(cudaMemcpy(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice), "upload");
         };
@@ -308,10 +337,22 @@ GaussianTrainerScene::~GaussianTrainerScene() {
     for (auto& v : impl_->views) cudaFree(v.d_target);
     impl_->params.release(); impl_->grads.release(); impl_->m1.release(); impl_->m2.release();
     cudaFree(impl_->d_render); cudaFree(impl_->d_dLdpix); cudaFree(impl_->d_scratch); cudaFree(impl_->d_loss);
+    cudaFree(impl_->d_accum); cudaFree(impl_->d_denom); cudaFree(impl_->d_mean2D); cudaFree(impl_->d_mean2D_abs);
+    cudaFree(impl_->d_radii);
+    dvs_densify::workspace_destroy(impl_->dws);
     cudaFreeHost(impl_->h_loss);
     if (impl_->ctx) dvs_rast_destroy(impl_->ctx);
     if (impl_->stream) cudaStreamDestroy(impl_->stream);
     delete impl_;
+}
+
+// Refinement can only happen for warmupLength < iteration < min(refineStopIter, numIters): a run that never gets there
+// keeps arenas of exactly N Gaussians (and never touches densify.cu).
+static bool refinementPossible(const GaussianTrainConfig& c) {
+    return c.refineEvery > 0 && c.warmupLength + 1 < std::min(c.refineStopIter, c.numIters);
+}
+int64_t GaussianTrainerScene::plannedCapacity(int64_t N) const {
+    return refinementPossible(config_) ? std::max<int64_t>(N, config_.capMax) : N;
 }
 
 static void parse_kv(const std::string& s, const char* key, long& out) {
@@ -349,6 +390,8 @@ bool GaussianTrainerScene::loadTrainData(const std::string& path) {
                 const int Kact = (I.max_degree + 1) * (I.max_degree + 1) - 1;
                 for (int c = 0; c < Kact * 3; c++) shN[(size_t)3 * KR * i + c] = 0.2f * G(I.rng);
             }
+            I.capacity = plannedCapacity((int64_t)lo.size());
+            I.refine_enabled = refinementPossible(config_);
             I.upload(means, ls, q, lo, sh0, shN);
             // target views on a ring, rendered from the ground truth with this rasterizer
             I.ensure_images((size_t)3 * W * H);
@@ -427,6 +470,8 @@ bool GaussianTrainerScene::loadTrainData(const std::string& path) {
             }
             if (lo.empty()) return false;
             std::vector<float> shN((size_t)3 * KR * lo.size(), 0.f);
+            I.capacity = plannedCapacity((int64_t)lo.size());
+            I.refine_enabled = refinementPossible(config_);
             I.upload(means, ls, q, lo, sh0, shN);
         }
     } catch (const std::exception& e) {
@@ -442,7 +487,7 @@ void GaussianTrainerScene::trainSetup() {
     auto& I = *impl_;
     int W = 0, H = 0;
     for (auto& v : I.views) { W = std::max(W, v.cam.width); H = std::max(H, v.cam.height); }
-    ckr(dvs_rast_reserve(I.ctx, I.N, W, H, 0), I.ctx, "reserve");
+    ckr(dvs_rast_reserve(I.ctx, std::max(I.N, I.capacity), W, H, 0), I.ctx, "reserve");  // per-Gaussian records for every row refinement may add
     status_ = TrainingStatus::Preprocess_Done;
 }
 
@@ -459,21 +504,37 @@ void GaussianTrainerScene::trainStep() {
     // Steps run without any host synchronisation (DVS_FLAG_DEFER_CHECK; honoured once a synchronous forward has
     // sized the binning arena).  A late DVS_E_OVERFLOW means a deferred step overflowed the arena: its kernels
     // exited early (zero gradients, so the Adam update it fed was harmless) and this step is simply redone.
-    cam.flags |= DVS_FLAG_DEFER_CHECK;
+    // refinement window (densify.cu): warmupLength < step < refineStopIter; MCMC is strategy 1, ADC 0 and 2
+    const bool refining = I.dws && step > config_.warmupLength && step < config_.refineStopIter;
+    const bool mcmc = config_.densifyStrategy == 1;
+    if (!I.resync_next) cam.flags |= DVS_FLAG_DEFER_CHECK;
+    I.resync_next = false;
     if (config_.mipAntiliased) cam.flags |= DVS_FLAG_ANTIALIAS;  // --mipAntiliased (main.cpp, docs/userGuide.md:58)
+    uint32_t bwd_flags = 0u;
+    if (refining && !mcmc) {  // ADC feeds on the screen-space gradient of every step
+        G.mean2D = I.d_mean2D;
+        if (config_.useAbsGrad) { G.mean2D_abs = I.d_mean2D_abs; bwd_flags |= DVS_FLAG_ABSGRAD; }
+    }
     for (int attempt = 0;; attempt++) {
-        int rc = dvs_rast_forward(I.ctx, &cam, I.N, &P, I.d_render, nullptr, I.stream);
+        int rc = dvs_rast_forward(I.ctx, &cam, I.N, &P, I.d_render, (refining && !mcmc) ? I.d_radii : nullptr, I.stream);
         if (rc == DVS_E_OVERFLOW && attempt < 2) continue;
         ckr(rc, I.ctx, "forward");
         ck(cudaMemsetAsync(I.d_loss, 0, sizeof(float), I.stream), "memset loss");
         launch_photometric_loss(I.d_render, vw.d_target, I.d_dLdpix, I.d_loss, I.d_scratch, cam.width, cam.height,
                                 std::min(1.f, std::max(0.f, config_.ssimWeight)), I.stream);
-        rc = dvs_rast_backward(I.ctx, &P, I.d_dLdpix, &G, 0u, I.stream);
+        rc = dvs_rast_backward(I.ctx, &P, I.d_dLdpix, &G, bwd_flags, I.stream);
         if (rc == DVS_E_OVERFLOW && attempt < 2) continue;
         ckr(rc, I.ctx, "backward");
         break;
     }
     (void)n;
+    if (refining) {
+        if (mcmc)  // L1 regularisers of the MCMC strategy: 0.01 mean(opacity) + 0.01 mean(scale)
+            ck(dvs_densify::mcmc_regularise(I.T(I.params), I.T(I.grads), I.N, 0.01f, 0.01f, I.stream), "mcmc_regularise");
+        else
+            ck(dvs_densify::adc_accumulate(I.d_mean2D, config_.useAbsGrad ? I.d_mean2D_abs : nullptr, I.d_radii, I.d_accum,
+                                           I.d_denom, I.N, I.stream), "adc_accumulate");
+    }
     // Adam, per-group learning rates (GaussianTrainConfig); position lr decays exponentially init -> final
     const float t = std::min(1.f, (float)step / (float)std::max(1, config_.numIters));
     const float lr_pos = std::exp((1.f - t) * std::log(config_.poslrInit) + t * std::log(config_.poslrFinal)) * I.scene_extent;
@@ -489,6 +550,32 @@ void GaussianTrainerScene::trainStep() {
     adam(I.params.off_opac, I.N, config_.opacitylr);
     adam(I.params.off_sh0, 3 * I.N, config_.featurelr);
     adam(I.params.off_shN, (size_t)3 * KR * I.N, config_.featurelr / 20.f);
+    if (refining) {
+        const uint64_t seed = 0x5DEECE66Dull * (uint64_t)(step + 1);
+        if (mcmc)  // exploration noise after the optimizer step: Sigma eps gate(opacity) noiselr lr_xyz
+            ck(dvs_densify::mcmc_noise(I.T(I.params), I.N, config_.noiselr * lr_pos, seed, I.stream), "mcmc_noise");
+        if (step % config_.refineEvery == 0) {
+            const int64_t before = I.N;
+            I.last_report = dvs_densify::RefineReport{};
+            if (mcmc) {
+                ck(dvs_densify::mcmc_refine(I.dws, I.T(I.params), I.T(I.m1), I.T(I.m2), &I.N, I.capacity, config_.capMax,
+                                            config_.min_opacity, seed, I.stream, &I.last_report), "mcmc_refine");
+            } else {
+                const dvs_densify::AdcConfig ac{config_.growGrad2d, 0.01f, I.scene_extent, config_.pruneOpacity,
+                                                config_.pruneScale3d};
+                ck(dvs_densify::adc_refine(I.dws, I.T(I.params), I.T(I.m1), I.T(I.m2), I.d_accum, I.d_denom, &I.N,
+                                           I.capacity, config_.capMax, ac, seed, I.stream, &I.last_report), "adc_refine");
+                if (config_.resetAlphaEvery > 0 && step % config_.resetAlphaEvery == 0)
+                    ck(dvs_densify::adc_reset_opacity(I.T(I.params), I.T(I.m1), I.T(I.m2), I.N, I.stream), "reset_opacity");
+            }
+            if (I.N != before) I.resync_next = true;
+            if (config_.verbose)
+                std::fprintf(stderr, "gstrain: refine @%d: N %lld -> %lld (dead %lld relocated %lld added %lld grown %lld pruned %lld)\n",
+                             step, (long long)before, (long long)I.N, (long long)I.last_report.dead,
+                             (long long)I.last_report.relocated, (long long)I.last_report.added,
+                             (long long)I.last_report.cloned, (long long)I.last_report.pruned);
+        }
+    }
     ck(cudaMemcpyAsync(I.h_loss, I.d_loss, sizeof(float), cudaMemcpyDeviceToHost, I.stream), "loss D2H");
     if (step % 100 == 0 || config_.verbose) {
         ck(cudaStreamSynchronize(I.stream), "sync");

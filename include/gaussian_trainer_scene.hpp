@@ -110,6 +110,7 @@ public:
     std::vector<int> pruenIteraions;
 
 private:
+    int64_t plannedCapacity(int64_t N) const;  // arena size: capMax when the schedule reaches the refinement window
     GaussianTrainConfig config_;
     TrainingStatus status_ = TrainingStatus::Loading_Prepare;
     bool train_ = true, terminate_ = false;

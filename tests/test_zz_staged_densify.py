@@ -1,0 +1,53 @@
+"""STAGED (marker `gpu_staged`, not part of `-m gpu`): the refinement step of divshot_b200/csrc/densify.cu on a B200,
+through the dvs_densify_test_* hooks of libgstrain.so.  Written while no GPU was available to this round; the same test
+bodies (tests/densify_cases.py) pass on the CPU against the host build of the same source (tests/test_densify_emul.py).
+Promote to `gpu` after the first green run:  python -m pytest tests -m gpu_staged -q"""
+import ctypes as C
+import os
+
+import pytest
+
+import densify_cases as dc
+from test_densify_ops import ops  # noqa: F401
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu_staged
+
+
+@pytest.fixture(scope="module")
+def be():
+    import torch
+    assert torch.cuda.is_available()
+    torch.zeros(1, device="cuda")  # primary context first: libgstrain.so links the static runtime and shares it
+    return dc.torch_backend(C.CDLL(os.path.join(ROOT, "divshot_b200", "lib", "libgstrain.so")))
+
+
+@pytest.mark.parametrize("case", dc.CASES_PLAIN, ids=lambda c: c.__name__)
+def test_refinement_step_on_the_gpu(be, case):
+    case(be)
+
+
+@pytest.mark.parametrize("case", dc.CASES_WITH_OPS, ids=lambda c: c.__name__)
+def test_refinement_step_on_the_gpu_vs_per_element_ops(be, ops, case):  # noqa: F811
+    case(be, ops)
+
+
+def test_trainer_refines_through_the_plugin_boundary(tmp_path):
+    """600 iterations with warmupLength 100 / refineEvery 100: the MCMC strategy (CLI default) grows the model by 5 % per
+    refinement up to capMax; the saved model holds the grown count and finite rows."""
+    import subprocess
+
+    import numpy as np
+    from divshot_b200 import build
+    from test_plugin import LIB, _read_ply
+    libs = build.build_all()
+    for strategy, expect_growth in (("1", True), ("0", None)):
+        out = str(tmp_path / f"refined_{strategy}.ply")
+        r = subprocess.run([libs["gstrain_driver"], "synthetic:N=20000,W=320,H=240,views=4,deg=1", "600", out,
+                            "warmup=100", "refineEvery=100", "capMax=24000", "strategy=" + strategy],
+                           capture_output=True, text=True, env={**os.environ, "LD_LIBRARY_PATH": LIB}, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        n, props, rows = _read_ply(out)
+        assert np.isfinite(rows).all() and 0 < n <= 24000
+        if expect_growth:
+            assert n == 24000, f"MCMC: 20000 * 1.05^k capped at capMax, got {n}"

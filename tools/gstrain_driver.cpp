@@ -2,6 +2,8 @@
 // dlopen("libgstrain.so"), resolve the nine symbols by name, create_splat -> load_train_data -> train_step loop ->
 // save_splat_model -> delete_splat -> gstrain_destroy.  Used by tests/test_plugin.py on the GPU box, where the
 // reference sources (and therefore the real CLI build) may be absent.  Prints the loss trajectory.
+// Optional trailing key=value arguments set schedule fields the CLI takes as flags (main.cpp:19-70):
+// warmup= refineEvery= refineStop= resetAlphaEvery= capMax= strategy= (densifyStrategy: 0 ADC, 1 MCMC, 2 ADC+).
 #include <dlfcn.h>
 
 #include <cstdio>
@@ -30,6 +32,20 @@ int main(int argc, char** argv) {
     init();
     GaussianTrainConfig cfg;
     cfg.sourcePath = data; cfg.modelPath = out; cfg.numIters = iters; cfg.verbose = true;
+    for (int a = 4; a < argc; a++) {
+        const std::string kv = argv[a];
+        const size_t eq = kv.find('=');
+        if (eq == std::string::npos) { std::fprintf(stderr, "expected key=value, got %s\n", argv[a]); return 6; }
+        const std::string k = kv.substr(0, eq);
+        const int v = std::atoi(kv.c_str() + eq + 1);
+        if (k == "warmup") cfg.warmupLength = v;
+        else if (k == "refineEvery") cfg.refineEvery = v;
+        else if (k == "refineStop") cfg.refineStopIter = v;
+        else if (k == "resetAlphaEvery") cfg.resetAlphaEvery = v;
+        else if (k == "capMax") cfg.capMax = v;
+        else if (k == "strategy") cfg.densifyStrategy = v;
+        else { std::fprintf(stderr, "unknown option %s\n", k.c_str()); return 6; }
+    }
     auto* scene = (GaussianTrainerScene*)create(cfg, -1);
     if (!load(scene, data)) { std::fprintf(stderr, "load_train_data failed\n"); return 4; }
     float first = -1.f, last = -1.f;
