@@ -103,12 +103,17 @@ def build_gstrain(force: bool = False) -> str:
     hdr = os.path.join(ROOT, "include", "gaussian_trainer_scene.hpp")
     obj = os.path.join(OBJ, "gstrain.o")
     if force or _stale(obj, [src, hdr, os.path.join(ROOT, "include", "dvs_rast.h"),
-                             os.path.join(ROOT, "include", "dvs_model_io.h"), os.path.join(CSRC, "densify.h")]):
+                             os.path.join(ROOT, "include", "dvs_model_io.h"), os.path.join(ROOT, "include", "dvs_viewer_pack.h"),
+                             os.path.join(CSRC, "densify.h")]):
         subprocess.check_call([nvcc(), "-ccbin", host_cxx(), *ARCH, *COMMON, "-c", src, "-o", obj])
     dsrc, dobj = os.path.join(CSRC, "densify.cu"), os.path.join(OBJ, "densify.o")  # trainer refinement step (F1)
     if force or _stale(dobj, [dsrc, os.path.join(CSRC, "densify.h"), os.path.join(CSRC, "densify_ops.h")]):
         subprocess.check_call([nvcc(), "-ccbin", host_cxx(), *ARCH, *COMMON, "-c", dsrc, "-o", dobj])
-    objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in CU_SOURCES] + [obj, io_obj, dobj]
+    # trainer -> viewer hand-off (F3): literal operation sequence, contraction off like preprocess_fwd.cu
+    vsrc, vobj = os.path.join(CSRC, "viewer_pack.cu"), os.path.join(OBJ, "viewer_pack.o")
+    if force or _stale(vobj, [vsrc, os.path.join(CSRC, "viewer_pack_ops.h"), os.path.join(ROOT, "include", "dvs_viewer_pack.h")]):
+        subprocess.check_call([nvcc(), "-ccbin", host_cxx(), *ARCH, *COMMON, "-fmad=false", "-c", vsrc, "-o", vobj])
+    objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in CU_SOURCES] + [obj, io_obj, dobj, vobj]
     so = os.path.join(OUT, "libgstrain.so")
     if force or _stale(so, objs):
         subprocess.check_call([nvcc(), "-ccbin", host_cxx(), *ARCH, "-shared", "-o", so, *objs, "-cudart", "static", "-lz"])
@@ -171,9 +176,21 @@ def build_driver(force: bool = False) -> str:
     return exe
 
 
+def build_editor_probe(force: bool = False) -> str:
+    """tools/editor_link_probe.cpp -> build/editor_link_probe, LINKED against libgstrain.so the way the reference editor
+    links its trainer (class methods, not dlsym)."""
+    src = os.path.join(ROOT, "tools", "editor_link_probe.cpp")
+    exe = os.path.join(ROOT, "build", "editor_link_probe")
+    so = build_gstrain(force)
+    if force or _stale(exe, [src, so, os.path.join(ROOT, "include", "gaussian_trainer_scene.hpp")]):
+        subprocess.check_call([host_cxx(), "-std=c++17", "-O1", f"-I{os.path.join(ROOT, 'include')}", src, "-o", exe,
+                               f"-L{OUT}", "-lgstrain", f"-Wl,-rpath,{OUT}", "-Wl,-rpath,$ORIGIN/../divshot_b200/lib"])
+    return exe
+
+
 def build_all(force: bool = False, verbose: bool = False, torch_binding: bool = True):
     libs = {"libdvsrast": build_rast(force, verbose), "libgstrain": build_gstrain(force),
-            "gstrain_driver": build_driver(force)}
+            "gstrain_driver": build_driver(force), "editor_link_probe": build_editor_probe(force)}
     cli = build_reference_cli(force)
     if cli:
         libs["reference_cli"] = cli

@@ -37,6 +37,7 @@
 #include "densify.h"
 #include "dvs_model_io.h"
 #include "dvs_rast.h"
+#include "dvs_viewer_pack.h"
 #include "gaussian_trainer_scene.hpp"
 
 #define GS_EXPORT __attribute__((visibility("default")))
@@ -272,6 +273,19 @@ struct GaussianTrainerImpl {
     bool refine_enabled = false;   // the schedule reaches the refinement window (set before upload)
     bool resync_next = false;      // N changed: the next forward re-sizes the binning arena synchronously
     dvs_densify::RefineReport last_report;
+    // viewer hand-off (viewer_pack.cu): two snapshots in flight at most, device staging + pinned host copy each
+    struct ViewerSlot {
+        uint8_t* d = nullptr;     // [vp_cap * 104 + 32] device: gaussians | colors | sh | bbox (ordered uint32 x 6)
+        uint8_t* h = nullptr;     // pinned host mirror
+        cudaEvent_t ready = nullptr;
+        int64_t count = 0;
+        int iteration = -1;
+        bool requested = false;
+    } vp[2];
+    int64_t vp_cap = 0;
+    int vp_next = 0, vp_last = -1;
+    cudaStream_t vp_stream = nullptr;
+    cudaEvent_t vp_packed = nullptr;
 
     dvs_densify::Tensors T(const Arena& a) const { return dvs_densify::Tensors{a.means(), a.scales(), a.quats(), a.opac(), a.sh0(), a.shN()}; }
 
@@ -339,6 +353,9 @@ GaussianTrainerScene::~GaussianTrainerScene() {
     cudaFree(impl_->d_render); cudaFree(impl_->d_dLdpix); cudaFree(impl_->d_scratch); cudaFree(impl_->d_loss);
     cudaFree(impl_->d_accum); cudaFree(impl_->d_denom); cudaFree(impl_->d_mean2D); cudaFree(impl_->d_mean2D_abs);
     cudaFree(impl_->d_radii);
+    for (auto& v : impl_->vp) { cudaFree(v.d); if (v.h) cudaFreeHost(v.h); if (v.ready) cudaEventDestroy(v.ready); }
+    if (impl_->vp_packed) cudaEventDestroy(impl_->vp_packed);
+    if (impl_->vp_stream) cudaStreamDestroy(impl_->vp_stream);
     dvs_densify::workspace_destroy(impl_->dws);
     cudaFreeHost(impl_->h_loss);
     if (impl_->ctx) dvs_rast_destroy(impl_->ctx);
@@ -611,6 +628,75 @@ void GaussianTrainerScene::saveGaussianModel() {
 
 void GaussianTrainerScene::exportMesh(const std::string&) {
     std::fprintf(stderr, "gstrain: mesh export is outside the rasterizer hot path (SURVEY.md section 8) - skipped\n");
+}
+
+// ---- trainer -> viewer hand-off: one fused pack kernel + one 104 B/Gaussian copy
+static size_t vp_offset_colors(int64_t cap) { return (size_t)cap * DVS_VP_GAUSSIAN_BYTES; }
+static size_t vp_offset_sh(int64_t cap) { return vp_offset_colors(cap) + (size_t)cap * DVS_VP_COLOR_BYTES; }
+static size_t vp_offset_bbox(int64_t cap) { return vp_offset_sh(cap) + (size_t)cap * DVS_VP_SH_BYTES; }
+static size_t vp_bytes(int64_t cap) { return vp_offset_bbox(cap) + 32; }
+
+void GaussianTrainerScene::requestViewerPack() {
+    auto& I = *impl_;
+    if (I.N <= 0) return;
+    if (!I.vp_stream) {
+        ck(cudaStreamCreateWithFlags(&I.vp_stream, cudaStreamNonBlocking), "viewer stream");
+        ck(cudaEventCreateWithFlags(&I.vp_packed, cudaEventDisableTiming), "viewer event");
+        for (auto& v : I.vp) ck(cudaEventCreateWithFlags(&v.ready, cudaEventDisableTiming), "viewer event");
+    }
+    const int64_t need = std::max(I.N, I.capacity);
+    if (need > I.vp_cap) {  // (re)size both slots; rows are 8 / 16-byte records, offsets stay 16-byte aligned for cap % 2 == 0
+        ck(cudaStreamSynchronize(I.vp_stream), "viewer sync");
+        const int64_t cap = (need + 1) / 2 * 2;
+        for (auto& v : I.vp) {
+            cudaFree(v.d); if (v.h) cudaFreeHost(v.h);
+            v.d = nullptr; v.h = nullptr; v.requested = false; v.count = 0;
+            ck(cudaMalloc(&v.d, vp_bytes(cap)), "cudaMalloc viewer pack");
+            ck(cudaMallocHost(&v.h, vp_bytes(cap)), "cudaMallocHost viewer pack");
+        }
+        I.vp_cap = cap;
+        I.vp_last = -1;
+    }
+    auto& v = I.vp[I.vp_next];
+    // the slot's previous copy (two requests ago) must have left the device staging before it is overwritten
+    if (v.requested) ck(cudaStreamWaitEvent(I.stream, v.ready, 0), "viewer wait");
+    const dvs_params P = I.P();
+    const int rc = dvs_viewer_pack(P.means3D, P.scales, P.quats, P.opacities, P.sh0, P.shN, I.N, v.d, v.d + vp_offset_colors(I.vp_cap),
+                                   v.d + vp_offset_sh(I.vp_cap), reinterpret_cast<uint32_t*>(v.d + vp_offset_bbox(I.vp_cap)), I.stream);
+    ck((cudaError_t)rc, "dvs_viewer_pack");
+    ck(cudaEventRecord(I.vp_packed, I.stream), "viewer record");
+    ck(cudaStreamWaitEvent(I.vp_stream, I.vp_packed, 0), "viewer wait");
+    // four contiguous pieces: only the live rows of each buffer travel
+    const size_t offs[4] = {0, vp_offset_colors(I.vp_cap), vp_offset_sh(I.vp_cap), vp_offset_bbox(I.vp_cap)};
+    const size_t lens[4] = {(size_t)I.N * DVS_VP_GAUSSIAN_BYTES, (size_t)I.N * DVS_VP_COLOR_BYTES, (size_t)I.N * DVS_VP_SH_BYTES, 24};
+    for (int k = 0; k < 4; k++)
+        ck(cudaMemcpyAsync(v.h + offs[k], v.d + offs[k], lens[k], cudaMemcpyDeviceToHost, I.vp_stream), "viewer D2H");
+    ck(cudaEventRecord(v.ready, I.vp_stream), "viewer record");
+    v.count = I.N;
+    v.iteration = curIteration;
+    v.requested = true;
+    I.vp_last = I.vp_next;
+    I.vp_next ^= 1;
+}
+
+bool GaussianTrainerScene::acquireViewerPack(GaussianViewerPack& out, bool wait) {
+    auto& I = *impl_;
+    if (I.vp_last < 0) return false;
+    int slot = I.vp_last;
+    if (wait) {
+        ck(cudaEventSynchronize(I.vp[slot].ready), "viewer sync");
+    } else if (cudaEventQuery(I.vp[slot].ready) != cudaSuccess) {
+        slot ^= 1;  // the newest is still in flight: fall back to the one before, if it exists and has landed
+        if (!I.vp[slot].requested || cudaEventQuery(I.vp[slot].ready) != cudaSuccess) return false;
+    }
+    const auto& v = I.vp[slot];
+    out.gaussians = v.h;
+    out.colors = v.h + vp_offset_colors(I.vp_cap);
+    out.sh = v.h + vp_offset_sh(I.vp_cap);
+    out.count = v.count;
+    out.iteration = v.iteration;
+    dvs_viewer_pack_decode_bbox(reinterpret_cast<const uint32_t*>(v.h + vp_offset_bbox(I.vp_cap)), out.bboxMin, out.bboxMax);
+    return true;
 }
 
 int64_t GaussianTrainerScene::getNumGaussians() const { return impl_->N; }

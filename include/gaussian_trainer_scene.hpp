@@ -21,6 +21,14 @@
 #include <string>
 #include <vector>
 
+// The editor links the trainer instead of dlopen-ing it (application/editor/source/editor.cpp:846-855,1426-1654 call the
+// class directly), so the class is exported; the CLI only needs the nine C symbols at the bottom.
+#if defined(_WIN32)
+#define GSTRAIN_API
+#else
+#define GSTRAIN_API __attribute__((visibility("default")))
+#endif
+
 enum GSPackLevel : int { PackNone = 0, PackF32ToU8 = 1, PackTileID = 2 };
 
 struct GaussianTrainConfig {
@@ -67,9 +75,22 @@ enum class TrainingStatus : int {
     Loading_Failed,
 };
 
+// Trainer -> viewer hand-off (include/dvs_viewer_pack.h).  The three buffers that
+// GaussianModel::create_gpu_buffer (diverse/source/assets/gaussian_model.cpp:115-212) quantises on the CPU from the six
+// getGaussian*Cpu() vectors, produced on the device instead and delivered in pinned host memory, byte-identical:
+// a maintainer copies them straight into the mapped gaussians_buf / gaussians_sh_0_buf / gaussians_sh_n_buf.
+struct GaussianViewerPack {
+    const void* gaussians = nullptr;  // [count] x 32 B  Gaussian           (gaussian_model.h:46-50)
+    const void* colors = nullptr;     // [count] x  8 B  PackedVertexColor  (gaussian_model.h:64)
+    const void* sh = nullptr;         // [count] x 64 B  PackedVertexSH     (gaussian_model.h:52-58)
+    int64_t count = 0;
+    float bboxMin[3] = {0, 0, 0}, bboxMax[3] = {0, 0, 0};  // local_bounding_box (gaussian_model.cpp:292-299)
+    int iteration = -1;               // training iteration the snapshot was taken after
+};
+
 struct GaussianTrainerImpl;  // B200 rasterizer context + device-resident parameters (gstrain.cu)
 
-class GaussianTrainerScene {
+class GSTRAIN_API GaussianTrainerScene {
 public:
     GaussianTrainerScene(const GaussianTrainConfig& config, int loadItr);
     ~GaussianTrainerScene();
@@ -101,6 +122,12 @@ public:
     std::vector<float> getGaussianOpcaitiesCpu() const;
     std::vector<float> getGaussianScalingsCpu() const;
     std::vector<float> getGaussianRotationsCpu() const;
+    // Viewer hand-off without the 236 B/Gaussian round trip and the CPU quantisation pass (see GaussianViewerPack).
+    // requestViewerPack queues the pack kernel behind the training work already queued and a device->host copy on a
+    // side stream, and returns at once; acquireViewerPack hands out the newest finished snapshot (wait = true blocks
+    // for the newest requested one).  The pointers stay valid until the next-but-one request.
+    void requestViewerPack();
+    bool acquireViewerPack(GaussianViewerPack& out, bool wait);
     int getNumCameras() const;
     std::array<float, 16> getCameraProjection(int i) const;  // flat [4c+r]
     std::array<float, 16> getCameraView(int i) const;

@@ -1,0 +1,173 @@
+"""SURVEY.md §8 row F3 — trainer -> viewer hand-off (include/dvs_viewer_pack.h, divshot_b200/csrc/viewer_pack.cu).
+
+The product quantises the raw parameters into the splat viewer's three buffers on the device; the reference does it on
+the CPU in GaussianModel::create_gpu_buffer (diverse/source/assets/gaussian_model.cpp:115-212).  Parity is byte-exact
+and PINNED BY THE REFERENCE: oracle/_ref/libviewerpack_ref.so is those reference lines compiled unmodified with the
+reference's glm (oracle/ref_viewer_pack_shim.cpp).  CPU tier: the per-Gaussian arithmetic the kernel calls
+(viewer_pack_ops.h, host build) against the reference library and against digests frozen from it.  GPU tier (staged,
+written without a GPU): the kernel and the plugin path against the same bytes."""
+import ctypes as C
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import viewer_pack_util as u
+from golden.make_viewer_pack_golden import CASES
+
+ROOT = u.ROOT
+GOLDEN = json.load(open(os.path.join(ROOT, "tests", "golden", "viewer_pack.json")))["sha256"]
+needs_ref = pytest.mark.skipif(not os.path.exists(u.REF_SO), reason="oracle/_ref/libviewerpack_ref.so not built (no /root/reference)")
+
+
+@pytest.fixture(scope="module")
+def ops():
+    return u.host_ops()
+
+
+def test_half_conversion_is_round_to_nearest_ties_away(ops):
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.normal(0, 1, 20000), rng.normal(0, 1e-6, 5000), rng.normal(0, 3e4, 5000),
+                        [0.0, -0.0, 65504.0, 65520.0, 1e9, -1e9, 6e-8, 2.9e-8, 3.1e-8, np.inf, -np.inf]]).astype(np.float32)
+    got = np.array([ops.t_f32_to_f16_glm(float(v)) for v in x], np.uint16)
+    with np.errstate(over="ignore"):
+        rne = x.astype(np.float16).view(np.uint16)  # ties-to-even: equal except on exact ties and the flush threshold
+    bits = x.view(np.uint32)
+    tie = (bits & 0x1FFF) == 0x1000
+    tiny = np.abs(x) < 2.0 ** -24  # glm flushes everything below 2^-25 .. and rounds [2^-25, 2^-24) up to the smallest subnormal
+    ok = got == rne
+    assert ok[~tie & ~tiny].all()
+    # planted ties: 1 + 2^-11 -> 1 + 2^-10 (away), where ties-to-even gives 1.0
+    t = np.array([0x3F801000, 0xBF801000, 0x3F803000], np.uint32).view(np.float32)
+    assert [ops.t_f32_to_f16_glm(float(v)) for v in t] == [0x3C01, 0xBC01, 0x3C02]
+    assert ops.t_f32_to_f16_glm(float("nan")) & 0x7C00 == 0x7C00 and ops.t_f32_to_f16_glm(float("nan")) & 0x3FF
+
+
+def test_ordered_float_map_is_monotone_and_invertible(ops):
+    x = np.sort(np.concatenate([np.random.default_rng(1).normal(0, 1e3, 5000), [-3.4e38, -1e-45, -0.0, 0.0, 1e-45, 3.4e38]]).astype(np.float32))
+    o = np.array([ops.t_f32_to_ordered(float(v)) for v in x], np.uint64)
+    assert (np.diff(o.astype(np.int64)) >= 0).all()
+    assert all(np.float32(ops.t_ordered_to_f32(int(k))).tobytes() == v.tobytes() for k, v in zip(o, x))
+
+
+@pytest.mark.parametrize("N,seed,deg", CASES)
+def test_host_build_of_the_kernel_arithmetic_matches_the_frozen_reference_bytes(ops, N, seed, deg):
+    assert u.digest(*u.pack_with_host_ops(ops, u.make_model(N, seed, deg))) == GOLDEN[f"N{N}_seed{seed}_deg{deg}"]
+
+
+@needs_ref
+@pytest.mark.parametrize("N,seed,deg", [(30000, 21, 3), (4097, 22, 2), (64, 23, 0)])
+def test_host_build_matches_the_reference_quantiser_byte_for_byte(ops, N, seed, deg):
+    m = u.make_model(N, seed, deg)
+    for name, a, b in zip(("gaussians", "colors", "sh", "bbox"), u.pack_with_host_ops(ops, m), u.pack_with_reference(m)):
+        assert a.tobytes() == b.tobytes(), f"{name}: {np.argwhere(a.view(np.uint32) != b.view(np.uint32))[:5].tolist()}"
+
+
+@needs_ref
+def test_frozen_digests_are_the_reference_library_output():
+    for N, seed, deg in CASES[:4]:
+        assert u.digest(*u.pack_with_reference(u.make_model(N, seed, deg))) == GOLDEN[f"N{N}_seed{seed}_deg{deg}"]
+
+
+def test_plugin_library_exports_the_viewer_pack_abi_and_the_trainer_class():
+    import re
+    from divshot_b200 import build
+    src = open(os.path.join(ROOT, "include", "dvs_viewer_pack.h")).read()
+    names = sorted(set(re.findall(r"\b(dvs_viewer_pack\w*)\s*\(", src)))
+    assert names == ["dvs_viewer_pack", "dvs_viewer_pack_decode_bbox"]
+    so = build.build_gstrain()
+    lib = C.CDLL(so)
+    for n in names:
+        assert hasattr(lib, n), f"libgstrain.so does not export {n}"
+    # host helper needs no GPU
+    b = (C.c_uint32 * 6)(*[u.host_ops().t_f32_to_ordered(v) for v in (-1.5, 0.0, 2.0, 3.0, 4.5, 1e30)])
+    lo, hi = (C.c_float * 3)(), (C.c_float * 3)()
+    lib.dvs_viewer_pack_decode_bbox(b, lo, hi)
+    assert list(lo) == [-1.5, 0.0, 2.0] and list(hi) == [3.0, 4.5, np.float32(1e30)]
+    # the editor links the class (editor.cpp:846-855): its methods are exported, the probe links against them
+    syms = subprocess.check_output(["nm", "-DC", "--defined-only", so], text=True)
+    for meth in ("requestViewerPack", "acquireViewerPack", "getGaussianPositionCpu", "trainStep", "loadTrainData"):
+        assert f"GaussianTrainerScene::{meth}" in syms
+    assert os.path.exists(build.build_editor_probe())
+
+
+# ------------------------------------------------------------------------------------------------ GPU (staged)
+def _device_pack(m):
+    import torch
+    from divshot_b200 import build
+    torch.zeros(1, device="cuda")
+    lib = C.CDLL(build.build_gstrain())
+    lib.dvs_viewer_pack.argtypes = [C.c_void_p] * 6 + [C.c_int64] + [C.c_void_p] * 5
+    N = m["opac"].shape[0]
+    t = {k: torch.from_numpy(np.ascontiguousarray(m[k])).cuda() for k in u.KEYS}
+    g = torch.full((max(N, 1), 8), 0x5A5A5A5A, dtype=torch.int32, device="cuda")
+    c = torch.full((max(N, 1), 2), 0x5A5A5A5A, dtype=torch.int32, device="cuda")
+    sh = torch.full((max(N, 1), 16), 0x5A5A5A5A, dtype=torch.int32, device="cuda")
+    bb = torch.zeros(6, dtype=torch.int32, device="cuda")
+    rc = lib.dvs_viewer_pack(*[t[k].data_ptr() for k in u.KEYS], N, g.data_ptr(), c.data_ptr(), sh.data_ptr(), bb.data_ptr(),
+                             torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, f"dvs_viewer_pack -> cudaError {rc}"
+    torch.cuda.synchronize()
+    lo, hi = (C.c_float * 3)(), (C.c_float * 3)()
+    lib.dvs_viewer_pack_decode_bbox(bb.cpu().numpy().view(np.uint32).ctypes.data_as(C.POINTER(C.c_uint32)), lo, hi)
+    box = np.array(list(lo) + list(hi), np.float32)
+    return (g.cpu().numpy().view(np.uint32)[:N], c.cpu().numpy().view(np.uint32)[:N], sh.cpu().numpy().view(np.uint32)[:N], box)
+
+
+@pytest.mark.gpu_staged
+@pytest.mark.parametrize("N,seed,deg", CASES + [(1000000, 9, 3)])
+def test_kernel_bytes_match_the_reference(ops, N, seed, deg):
+    m = u.make_model(N, seed, deg)
+    got = _device_pack(m)
+    key = f"N{N}_seed{seed}_deg{deg}"
+    if key in GOLDEN:
+        assert u.digest(*got) == GOLDEN[key], "device bytes differ from the reference quantiser's"
+    for name, a, b in zip(("gaussians", "colors", "sh", "bbox"), got, u.pack_with_host_ops(ops, m)):
+        assert a.tobytes() == b.tobytes(), f"{name}: {np.argwhere(a.view(np.uint32) != b.view(np.uint32))[:5].tolist()}"
+
+
+@pytest.mark.gpu_staged
+def test_kernel_empty_model_and_misuse():
+    import torch
+    from divshot_b200 import build
+    torch.zeros(1, device="cuda")
+    lib = C.CDLL(build.build_gstrain())
+    lib.dvs_viewer_pack.argtypes = [C.c_void_p] * 6 + [C.c_int64] + [C.c_void_p] * 5
+    bb = torch.zeros(6, dtype=torch.int32, device="cuda")
+    assert lib.dvs_viewer_pack(None, None, None, None, None, None, 0, None, None, None, bb.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    lo, hi = (C.c_float * 3)(), (C.c_float * 3)()
+    lib.dvs_viewer_pack_decode_bbox(bb.cpu().numpy().view(np.uint32).ctypes.data_as(C.POINTER(C.c_uint32)), lo, hi)
+    fmax = float(np.finfo(np.float32).max)
+    assert list(lo) == [fmax] * 3 and list(hi) == [-fmax] * 3  # the reference's empty box (gaussian_model.cpp:292-293)
+    assert lib.dvs_viewer_pack(None, None, None, None, None, None, 5, None, None, None, bb.data_ptr(), None) != 0
+    assert lib.dvs_viewer_pack(None, None, None, None, None, None, 5, None, None, None, None, None) != 0
+
+
+@pytest.mark.gpu_staged
+def test_editor_style_hand_off_through_the_plugin(ops, tmp_path):
+    """tools/editor_link_probe.cpp: train 30 iterations through the class interface, then the fused pack must equal the
+    reference's CPU quantisation of the six getGaussian*Cpu() vectors taken at the same iteration."""
+    from divshot_b200 import build
+    exe = build.build_editor_probe()
+    out = str(tmp_path / "probe")
+    r = subprocess.run([exe, "synthetic:N=20000,W=320,H=240,views=4,deg=1", "30", out], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    raw = open(out + ".raw", "rb").read()
+    n = int(np.frombuffer(raw[:8], np.int64)[0])
+    f = np.frombuffer(raw[8:], np.float32)
+    assert n == 20000 and f.size == n * 59
+    cuts = np.cumsum([0, 3 * n, 3 * n, 4 * n, n, 3 * n, 45 * n])
+    shapes = [(n, 3), (n, 3), (n, 4), (n,), (n, 3), (n, 45)]
+    m = {k: f[cuts[i]:cuts[i + 1]].reshape(shapes[i]).copy() for i, k in enumerate(u.KEYS)}
+    pk = open(out + ".pack", "rb").read()
+    assert int(np.frombuffer(pk[:8], np.int64)[0]) == n
+    box = np.frombuffer(pk[8:32], np.float32)
+    g = np.frombuffer(pk[32:32 + 32 * n], np.uint32).reshape(n, 8)
+    c = np.frombuffer(pk[32 + 32 * n:32 + 40 * n], np.uint32).reshape(n, 2)
+    sh = np.frombuffer(pk[32 + 40 * n:32 + 104 * n], np.uint32).reshape(n, 16)
+    ref = u.pack_with_reference(m) if os.path.exists(u.REF_SO) else u.pack_with_host_ops(ops, m)
+    for name, a, b in zip(("gaussians", "colors", "sh", "bbox"), (g, c, sh, box), ref):
+        assert a.tobytes() == b.tobytes(), name
