@@ -90,6 +90,39 @@ def test_g3_near_cull_boundary():
     assert list(f.radii > 0) == [False, True, False, False]
 
 
+def test_g4_off_axis_beyond_the_ewa_clamp_closed_form():
+    """A splat at x/z = 1.6 tanfov: the EWA Jacobian is evaluated at the clamped ray 1.3 tanfov (in-tree restatement:
+    gsplat_intersect.hlsl:88-94) while mean2D is the true projection; the gradient through the clamped coordinate is
+    zero (Appendix B.5), so dL/dmean.x comes from the mean2D path alone."""
+    cam = _cam()
+    z0, s, o = 4.0, 0.6, 0.7
+    x0 = 1.6 * cam.tanfovx * z0
+    oc, arr = _one([(x0, 0, z0)], s, o, (0.9, 0.5, 0.2), cam)
+    f = orc.forward(oc, *arr, threads=1)
+    fx = W / (2 * cam.tanfovx)
+    fy = H / (2 * cam.tanfovy)
+    tx = 1.3 * cam.tanfovx * z0  # clamped
+    cxx = s * s * ((fx / z0) ** 2 + (fx * tx / z0 ** 2) ** 2) + 0.3
+    cyy = s * s * (fy / z0) ** 2 + 0.3
+    assert abs(f.conic_opacity[0, 0] - 1 / cxx) < 2e-5 / cxx and abs(f.conic_opacity[0, 2] - 1 / cyy) < 2e-5 / cyy
+    assert abs(f.conic_opacity[0, 1]) < 1e-7
+    mid = 0.5 * (cxx + cyy)
+    assert f.radii[0] == math.ceil(3 * math.sqrt(mid + math.sqrt(max(0.1, mid * mid - cxx * cyy))))
+    # mean2D is NOT clamped: ndc = x / (z tanfov) = 1.6 -> pixel ((1.6 + 1) W - 1) / 2, right of the image
+    assert abs(f.mean2D[0, 0] - ((1.6 + 1) * W - 1) / 2) < 1e-3 and f.mean2D[0, 0] > W
+    assert f.tiles_touched[0] > 0 and f.image.max() > 0.01  # its footprint still reaches the screen
+    g = np.random.default_rng(0).normal(size=(3, H, W)).astype(np.float32)
+    b = orc.backward(oc, f, *arr, g, threads=1)
+    # dL_dmean2D is w.r.t. the ndc coordinate (the 0.5 W pixel factor already applied): d ndc.x / dx = 1 / (tanfov z)
+    k = 1.0 / (cam.tanfovx * z0)
+    assert abs(b.dL_dmeans3D[0, 0] - b.dL_dmean2D[0, 0] * k) <= 2e-5 * abs(b.dL_dmeans3D[0, 0]) + 1e-9
+    # an unclamped twin (x/z = 1.2 tanfov) for contrast: there the covariance path does contribute to dL/dx
+    oc2, arr2 = _one([(1.2 * cam.tanfovx * z0, 0, z0)], s, o, (0.9, 0.5, 0.2), cam)
+    f2 = orc.forward(oc2, *arr2, threads=1)
+    b2 = orc.backward(oc2, f2, *arr2, g, threads=1)
+    assert abs(b2.dL_dmeans3D[0, 0] - b2.dL_dmean2D[0, 0] * k) > 1e-3 * abs(b2.dL_dmeans3D[0, 0])
+
+
 def test_g5_opaque_stack_early_out():
     cam = _cam()
     n = 12
