@@ -188,12 +188,32 @@ def build_editor_probe(force: bool = False) -> str:
     return exe
 
 
+def build_editor_api_probe(force: bool = False):
+    """tools/editor_api_probe.cpp -> build/editor_api_probe: the editor's call patterns on the trainer class, compiled
+    with the REFERENCE's glm on the include path (so only where /root/reference exists; the GPU box uses the prebuilt
+    binary that travels in build/)."""
+    src = os.path.join(ROOT, "tools", "editor_api_probe.cpp")
+    exe = os.path.join(ROOT, "build", "editor_api_probe")
+    glm = "/root/reference/external/glm"
+    if not os.path.isdir(glm):
+        return exe if os.path.exists(exe) else None
+    so = build_gstrain(force)
+    if force or _stale(exe, [src, so, os.path.join(ROOT, "include", "gaussian_trainer_scene.hpp")]):
+        subprocess.check_call([host_cxx(), "-std=c++20", "-O1", "-Wall", f"-I{os.path.join(ROOT, 'include')}", f"-I{glm}",
+                               "-DGLM_FORCE_INTRINSICS", "-DGLM_FORCE_DEPTH_ZERO_TO_ONE", "-DGLM_FORCE_SWIZZLE",
+                               src, "-o", exe, f"-L{OUT}", "-lgstrain", f"-Wl,-rpath,{OUT}", "-Wl,-rpath,$ORIGIN/../divshot_b200/lib"])
+    return exe
+
+
 def build_all(force: bool = False, verbose: bool = False, torch_binding: bool = True):
     libs = {"libdvsrast": build_rast(force, verbose), "libgstrain": build_gstrain(force),
             "gstrain_driver": build_driver(force), "editor_link_probe": build_editor_probe(force)}
     cli = build_reference_cli(force)
     if cli:
         libs["reference_cli"] = cli
+    probe = build_editor_api_probe(force)
+    if probe:
+        libs["editor_api_probe"] = probe
     if torch_binding:
         libs["libdvs_torch"] = build_torch_binding(force)
     return libs

@@ -24,6 +24,8 @@
 // `.splat` records of tiny_gsplat.cpp:243-291.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -195,6 +197,11 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 struct View {
     dvs_camera cam;
     float* d_target = nullptr;  // [3,H,W] device
+    float Rt[12] = {0};         // world -> camera rows [R | t] as loaded
+    float P[16] = {0};          // the perspective matrix alone, flat [4c+r]
+    float fx = 0.f, fy = 0.f;
+    std::string name;
+    std::vector<uint8_t> rgba;  // lazily built RGBA8 copy of the target (getSplatImageView)
 };
 
 struct Arena {  // one flat buffer, six 16-byte-aligned views (same order as GradBuffers in rasterizer.py)
@@ -222,7 +229,7 @@ struct Arena {  // one flat buffer, six 16-byte-aligned views (same order as Gra
     float* opac() const { return flat + off_opac; }
 };
 
-void make_projection(dvs_camera& c, const float Rt[12], int W, int H, float fx, float fy) {
+void make_projection(dvs_camera& c, const float Rt[12], int W, int H, float fx, float fy, float Pflat[16] = nullptr) {
     // view (world->camera), flat [4c+r]
     float V[4][4] = {{Rt[0], Rt[1], Rt[2], Rt[3]}, {Rt[4], Rt[5], Rt[6], Rt[7]}, {Rt[8], Rt[9], Rt[10], Rt[11]},
                      {0, 0, 0, 1}};
@@ -237,7 +244,10 @@ void make_projection(dvs_camera& c, const float Rt[12], int W, int H, float fx, 
             PV[r][cc] = s;
         }
     for (int r = 0; r < 4; r++)
-        for (int cc = 0; cc < 4; cc++) { c.view[4 * cc + r] = V[r][cc]; c.proj[4 * cc + r] = PV[r][cc]; }
+        for (int cc = 0; cc < 4; cc++) {
+            c.view[4 * cc + r] = V[r][cc]; c.proj[4 * cc + r] = PV[r][cc];
+            if (Pflat) Pflat[4 * cc + r] = P[r][cc];
+        }
     // camera centre = -R^T t
     for (int k = 0; k < 3; k++) c.campos[k] = -(Rt[0 + k] * Rt[3] + Rt[4 + k] * Rt[7] + Rt[8 + k] * Rt[11]);
     c.tanfovx = tanx; c.tanfovy = tany; c.width = W; c.height = H;
@@ -273,6 +283,12 @@ struct GaussianTrainerImpl {
     bool refine_enabled = false;   // the schedule reaches the refinement window (set before upload)
     bool resync_next = false;      // N changed: the next forward re-sizes the binning arena synchronously
     dvs_densify::RefineReport last_report;
+    // editor surface: the initial model (resetGaussian), the initialisation points, time spent training
+    std::vector<float> init[6];  // means, scales, quats, opac, sh0, shN as first uploaded
+    std::vector<GsPoint3D> points3d;
+    double train_seconds = 0.0;
+    std::chrono::steady_clock::time_point last_step{};
+    bool have_last_step = false;
     // viewer hand-off (viewer_pack.cu): two snapshots in flight at most, device staging + pinned host copy each
     struct ViewerSlot {
         uint8_t* d = nullptr;     // [vp_cap * 104 + 32] device: gaussians | colors | sh | bbox (ordered uint32 x 6)
@@ -302,10 +318,13 @@ struct GaussianTrainerImpl {
         ck(cudaMalloc(&d_scratch, 3 * floats * sizeof(float)), "cudaMalloc loss scratch");
         img_cap = floats;
     }
-    void upload(const std::vector<float>& means, const std::vector<float>& lscales, const std::vector<float>& quats,
-                const std::vector<float>& logit, const std::vector<float>& sh0, const std::vector<float>& shN) {
-        N = (int64_t)logit.size();
-        capacity = std::max(N, capacity);
+    void release_model() {
+        params.release(); grads.release(); m1.release(); m2.release();
+        cudaFree(d_accum); cudaFree(d_denom); cudaFree(d_mean2D); cudaFree(d_mean2D_abs); cudaFree(d_radii);
+        d_accum = d_denom = d_mean2D = d_mean2D_abs = nullptr; d_radii = nullptr;
+    }
+    void allocate(int64_t cap) {  // arenas for `cap` Gaussians, zero-filled
+        capacity = cap;
         params.alloc(capacity); grads.alloc(capacity); m1.alloc(capacity); m2.alloc(capacity);
         if (refine_enabled) {  // refinement statistics and the buffers they are fed from
             ck(cudaMalloc(&d_accum, capacity * sizeof(float)), "cudaMalloc accum");
@@ -315,13 +334,32 @@ struct GaussianTrainerImpl {
             ck(cudaMalloc(&d_radii, capacity * sizeof(int32_t)), "cudaMalloc radii");
             ck(cudaMemset(d_accum, 0, capacity * sizeof(float)), "memset accum");
             ck(cudaMemset(d_denom, 0, capacity * sizeof(float)), "memset denom");
-            dws = dvs_densify::workspace_create();
+            if (!dws) dws = dvs_densify::workspace_create();
         }
-        auto up = [&](float* d, const std::vector<float>& h) {
-            ck(cudaMemcpy(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice), "upload");
+    }
+    // n rows of raw parameters from the host into the (already allocated) arenas; n <= capacity
+    void set_model(const float* means, const float* lscales, const float* quats, const float* logit, const float* sh0,
+                   const float* shN, int64_t n) {
+        N = n;
+        auto up = [&](float* d, const float* h, size_t cnt) {
+            if (cnt) ck(cudaMemcpy(d, h, cnt * sizeof(float), cudaMemcpyHostToDevice), "upload");
         };
-        up(params.means(), means); up(params.scales(), lscales); up(params.quats(), quats);
-        up(params.opac(), logit); up(params.sh0(), sh0); up(params.shN(), shN);
+        up(params.means(), means, 3 * (size_t)n); up(params.scales(), lscales, 3 * (size_t)n); up(params.quats(), quats, 4 * (size_t)n);
+        up(params.opac(), logit, (size_t)n); up(params.sh0(), sh0, 3 * (size_t)n); up(params.shN(), shN, (size_t)3 * KR * n);
+    }
+    void upload(const std::vector<float>& means, const std::vector<float>& lscales, const std::vector<float>& quats,
+                const std::vector<float>& logit, const std::vector<float>& sh0, const std::vector<float>& shN) {
+        const int64_t n = (int64_t)logit.size();
+        allocate(std::max(n, capacity));
+        set_model(means.data(), lscales.data(), quats.data(), logit.data(), sh0.data(), shN.data(), n);
+    }
+    void zero_optimizer_state() {
+        ck(cudaMemsetAsync(m1.flat, 0, m1.total * sizeof(float), stream), "memset m1");
+        ck(cudaMemsetAsync(m2.flat, 0, m2.total * sizeof(float), stream), "memset m2");
+        if (d_accum) {
+            ck(cudaMemsetAsync(d_accum, 0, capacity * sizeof(float), stream), "memset accum");
+            ck(cudaMemsetAsync(d_denom, 0, capacity * sizeof(float), stream), "memset denom");
+        }
     }
     std::vector<float> download(const float* d, size_t n) const {
         std::vector<float> h(n);
@@ -349,10 +387,8 @@ GaussianTrainerScene::~GaussianTrainerScene() {
     if (!impl_) return;
     cudaDeviceSynchronize();
     for (auto& v : impl_->views) cudaFree(v.d_target);
-    impl_->params.release(); impl_->grads.release(); impl_->m1.release(); impl_->m2.release();
+    impl_->release_model();
     cudaFree(impl_->d_render); cudaFree(impl_->d_dLdpix); cudaFree(impl_->d_scratch); cudaFree(impl_->d_loss);
-    cudaFree(impl_->d_accum); cudaFree(impl_->d_denom); cudaFree(impl_->d_mean2D); cudaFree(impl_->d_mean2D_abs);
-    cudaFree(impl_->d_radii);
     for (auto& v : impl_->vp) { cudaFree(v.d); if (v.h) cudaFreeHost(v.h); if (v.ready) cudaEventDestroy(v.ready); }
     if (impl_->vp_packed) cudaEventDestroy(impl_->vp_packed);
     if (impl_->vp_stream) cudaStreamDestroy(impl_->vp_stream);
@@ -361,6 +397,24 @@ GaussianTrainerScene::~GaussianTrainerScene() {
     if (impl_->ctx) dvs_rast_destroy(impl_->ctx);
     if (impl_->stream) cudaStreamDestroy(impl_->stream);
     delete impl_;
+}
+
+GaussianTrainerScene::GaussianTrainerScene(GaussianTrainerScene&& o) noexcept
+    : ShowTrainView(o.ShowTrainView), curIteration(o.curIteration), pruenIteraions(std::move(o.pruenIteraions)),
+      focus_region_position(o.focus_region_position), focus_region_rotation(o.focus_region_rotation),
+      focus_region_scale(o.focus_region_scale), config_(std::move(o.config_)), status_(o.status_), train_(o.train_),
+      terminate_(o.terminate_), loss_(o.loss_), impl_(o.impl_) {
+    o.impl_ = nullptr;
+}
+GaussianTrainerScene& GaussianTrainerScene::operator=(GaussianTrainerScene&& o) noexcept {
+    if (this != &o) {
+        std::swap(impl_, o.impl_);  // the moved-from object releases our old device state in its destructor
+        ShowTrainView = o.ShowTrainView; curIteration = o.curIteration; pruenIteraions = std::move(o.pruenIteraions);
+        focus_region_position = o.focus_region_position; focus_region_rotation = o.focus_region_rotation;
+        focus_region_scale = o.focus_region_scale;
+        config_ = std::move(o.config_); status_ = o.status_; train_ = o.train_; terminate_ = o.terminate_; loss_ = o.loss_;
+    }
+    return *this;
 }
 
 // Refinement can only happen for warmupLength < iteration < min(refineStopIter, numIters): a run that never gets there
@@ -425,7 +479,10 @@ bool GaussianTrainerScene::loadTrainData(const std::string& path) {
                 float Rt[12] = {r[0], r[1], r[2], 0, u[0], u[1], u[2], 0, f[0], f[1], f[2], 0};
                 for (int a = 0; a < 3; a++) Rt[4 * a + 3] = -(Rt[4 * a] * eye[0] + Rt[4 * a + 1] * eye[1] + Rt[4 * a + 2] * eye[2]);
                 View vw;
-                make_projection(vw.cam, Rt, (int)W, (int)H, W / (2.f * tanx), H / (2.f * tany));
+                vw.fx = W / (2.f * tanx); vw.fy = H / (2.f * tany);
+                std::memcpy(vw.Rt, Rt, sizeof Rt);
+                vw.name = "synthetic_view_" + std::to_string(v);
+                make_projection(vw.cam, Rt, (int)W, (int)H, vw.fx, vw.fy, vw.P);
                 vw.cam.sh_degree = I.max_degree;
                 ck(cudaMalloc(&vw.d_target, (size_t)3 * W * H * sizeof(float)), "cudaMalloc target");
                 dvs_params P = I.P();
@@ -466,7 +523,9 @@ bool GaussianTrainerScene::loadTrainData(const std::string& path) {
                 for (size_t p = 0; p < (size_t)W * H; p++)
                     for (int c = 0; c < 3; c++) host[c * (size_t)W * H + p] = rgb[3 * p + c] / 255.f;
                 View vw;
-                make_projection(vw.cam, Rt, W, H, fx, fy);
+                vw.fx = fx; vw.fy = fy; vw.name = img;
+                std::memcpy(vw.Rt, Rt, sizeof Rt);
+                make_projection(vw.cam, Rt, W, H, fx, fy, vw.P);
                 ck(cudaMalloc(&vw.d_target, host.size() * sizeof(float)), "cudaMalloc target");
                 ck(cudaMemcpy(vw.d_target, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice), "upload image");
                 I.views.push_back(vw);
@@ -496,6 +555,21 @@ bool GaussianTrainerScene::loadTrainData(const std::string& path) {
         status_ = TrainingStatus::Loading_Failed;
         return false;
     }
+    // the editor surface: remember the initial model (resetGaussian) and expose it as the initialisation point cloud
+    const float* src[6] = {I.params.means(), I.params.scales(), I.params.quats(), I.params.opac(), I.params.sh0(), I.params.shN()};
+    const size_t width[6] = {3, 3, 4, 1, 3, (size_t)3 * KR};
+    for (int k = 0; k < 6; k++) I.init[k] = I.download(src[k], width[k] * (size_t)I.N);
+    I.points3d.resize((size_t)I.N);
+    for (int64_t i = 0; i < I.N; i++) {
+        GsPoint3D& pt = I.points3d[(size_t)i];
+        pt.x = I.init[0][3 * i]; pt.y = I.init[0][3 * i + 1]; pt.z = I.init[0][3 * i + 2];
+        uint8_t* rgb[3] = {&pt.r, &pt.g, &pt.b};
+        for (int c = 0; c < 3; c++) {
+            const float v = I.init[4][3 * i + c] * 0.28209479177387814f + 0.5f;
+            *rgb[c] = (uint8_t)std::lround(255.f * std::min(1.f, std::max(0.f, v)));
+        }
+        pt.a = 255;
+    }
     trainSetup();
     return true;
 }
@@ -511,6 +585,14 @@ void GaussianTrainerScene::trainSetup() {
 void GaussianTrainerScene::trainStep() {
     auto& I = *impl_;
     if (I.views.empty() || I.N == 0) throw std::runtime_error("gstrain: train_step without data");
+    {   // time spent training: gaps between consecutive steps, pauses (> 2 s) dropped
+        const auto now = std::chrono::steady_clock::now();
+        if (I.have_last_step) {
+            const double dt = std::chrono::duration<double>(now - I.last_step).count();
+            if (dt < 2.0) I.train_seconds += dt;
+        }
+        I.last_step = now; I.have_last_step = true;
+    }
     const int step = curIteration;
     View& vw = I.views[(size_t)step % I.views.size()];
     dvs_camera cam = vw.cam;
@@ -707,11 +789,173 @@ std::vector<float> GaussianTrainerScene::getGaussianOpcaitiesCpu() const { retur
 std::vector<float> GaussianTrainerScene::getGaussianScalingsCpu() const { return impl_->download(impl_->params.scales(), 3 * impl_->N); }
 std::vector<float> GaussianTrainerScene::getGaussianRotationsCpu() const { return impl_->download(impl_->params.quats(), 4 * impl_->N); }
 int GaussianTrainerScene::getNumCameras() const { return (int)impl_->views.size(); }
-std::array<float, 16> GaussianTrainerScene::getCameraProjection(int i) const {
-    std::array<float, 16> a; std::memcpy(a.data(), impl_->views.at(i).cam.proj, sizeof(float) * 16); return a;
+std::array<float, 16> GaussianTrainerScene::getCameraProjectionFlat(int i) const {
+    std::array<float, 16> a; std::memcpy(a.data(), impl_->views.at(i).P, sizeof(float) * 16); return a;
 }
 std::array<float, 16> GaussianTrainerScene::getCameraView(int i) const {
     std::array<float, 16> a; std::memcpy(a.data(), impl_->views.at(i).cam.view, sizeof(float) * 16); return a;
+}
+void GaussianTrainerScene::getCameraPosXYZ(int i, float p[3]) const {
+    for (int k = 0; k < 3; k++) p[k] = impl_->views.at(i).cam.campos[k];
+}
+// camera -> world rotation = R^T of the loaded world -> camera rows, as a unit quaternion (w, x, y, z)
+void GaussianTrainerScene::getCameraRotationWXYZ(int i, float q[4]) const {
+    const float* Rt = impl_->views.at(i).Rt;
+    const float m[3][3] = {{Rt[0], Rt[4], Rt[8]}, {Rt[1], Rt[5], Rt[9]}, {Rt[2], Rt[6], Rt[10]}};  // transpose
+    const float tr = m[0][0] + m[1][1] + m[2][2];
+    if (tr > 0.f) {
+        const float s = std::sqrt(tr + 1.f) * 2.f;
+        q[0] = 0.25f * s; q[1] = (m[2][1] - m[1][2]) / s; q[2] = (m[0][2] - m[2][0]) / s; q[3] = (m[1][0] - m[0][1]) / s;
+    } else if (m[0][0] > m[1][1] && m[0][0] > m[2][2]) {
+        const float s = std::sqrt(1.f + m[0][0] - m[1][1] - m[2][2]) * 2.f;
+        q[0] = (m[2][1] - m[1][2]) / s; q[1] = 0.25f * s; q[2] = (m[0][1] + m[1][0]) / s; q[3] = (m[0][2] + m[2][0]) / s;
+    } else if (m[1][1] > m[2][2]) {
+        const float s = std::sqrt(1.f + m[1][1] - m[0][0] - m[2][2]) * 2.f;
+        q[0] = (m[0][2] - m[2][0]) / s; q[1] = (m[0][1] + m[1][0]) / s; q[2] = 0.25f * s; q[3] = (m[1][2] + m[2][1]) / s;
+    } else {
+        const float s = std::sqrt(1.f + m[2][2] - m[0][0] - m[1][1]) * 2.f;
+        q[0] = (m[1][0] - m[0][1]) / s; q[1] = (m[0][2] + m[2][0]) / s; q[2] = (m[1][2] + m[2][1]) / s; q[3] = 0.25f * s;
+    }
+}
+
+// ---- the rest of the editor surface
+void GaussianTrainerScene::resetGaussian() {
+    auto& I = *impl_;
+    if (I.init[3].empty()) return;
+    ck(cudaStreamSynchronize(I.stream), "sync");
+    I.set_model(I.init[0].data(), I.init[1].data(), I.init[2].data(), I.init[3].data(), I.init[4].data(), I.init[5].data(),
+                (int64_t)I.init[3].size());
+    I.zero_optimizer_state();
+    I.resync_next = true;
+    I.train_seconds = 0.0; I.have_last_step = false;
+    curIteration = 0;
+    loss_ = 0.f;
+    status_ = TrainingStatus::Preprocess_Done;
+}
+void GaussianTrainerScene::setDensifyStrategy(int strategy) {
+    auto& I = *impl_;
+    config_.densifyStrategy = std::min(2, std::max(0, strategy));
+    if (I.d_accum) {  // the ADC statistics restart with the strategy
+        ck(cudaMemsetAsync(I.d_accum, 0, I.capacity * sizeof(float), I.stream), "memset accum");
+        ck(cudaMemsetAsync(I.d_denom, 0, I.capacity * sizeof(float), I.stream), "memset denom");
+    }
+}
+float GaussianTrainerScene::getProgressOnCurrentPhase() const {
+    switch (status_) {
+        case TrainingStatus::Training: return std::min(1.f, (float)curIteration / (float)std::max(1, config_.numIters));
+        case TrainingStatus::Training_Done: case TrainingStatus::Preprocess_Done: return 1.f;
+        default: return 0.f;
+    }
+}
+std::string GaussianTrainerScene::getCurrentTrainingPhaseName() const {
+    switch (status_) {
+        case TrainingStatus::Loading_Prepare: return "Preparing";
+        case TrainingStatus::Loading_Data: return "Loading data";
+        case TrainingStatus::Colmap_Sfm: return "Structure from motion";
+        case TrainingStatus::Preprocess_Done: return "Ready";
+        case TrainingStatus::Training: return "Training";
+        case TrainingStatus::Training_Done: return "Done";
+        case TrainingStatus::GS2Mesh: return "Extracting mesh";
+        case TrainingStatus::Loading_Failed: return "Failed";
+    }
+    return "";
+}
+float GaussianTrainerScene::getTrainingElpasedTime() const { return (float)impl_->train_seconds; }
+float GaussianTrainerScene::getEstimateTrainingTime() const {
+    if (curIteration <= 0) return 0.f;
+    const int left = std::max(0, config_.numIters - curIteration);
+    return (float)(impl_->train_seconds / (double)curIteration * (double)left);
+}
+void GaussianTrainerScene::updateTensorFromHost(const float* pos, const float* rot, const float* scale, const float* opacity,
+                                                const float* sh0, const float* shn, int64_t n) {
+    auto& I = *impl_;
+    if (n <= 0 || !pos || !rot || !scale || !opacity || !sh0 || !shn) throw std::runtime_error("gstrain: updateTensorFromHost with an empty model");
+    ck(cudaStreamSynchronize(I.stream), "sync");
+    if (n > I.capacity) {  // the edited model outgrew the arenas: re-allocate (pointers change, so nothing may be in flight)
+        ck(cudaDeviceSynchronize(), "sync");
+        I.release_model();
+        I.allocate(plannedCapacity(n));
+        ckr(dvs_rast_reserve(I.ctx, I.capacity, 0, 0, 0), I.ctx, "reserve");
+        I.vp_last = -1;  // snapshots of the old model are stale
+    }
+    I.set_model(pos, scale, rot, opacity, sh0, shn, n);
+    I.zero_optimizer_state();
+    I.resync_next = true;
+}
+const std::vector<GsPoint3D>& GaussianTrainerScene::getPoints3D(int) const { return impl_->points3d; }
+GsImageView GaussianTrainerScene::getSplatImageView(int id) {
+    auto& I = *impl_;
+    View& v = I.views.at((size_t)id);
+    const size_t P = (size_t)v.cam.width * v.cam.height;
+    if (v.rgba.empty()) {
+        const std::vector<float> chw = I.download(v.d_target, 3 * P);
+        v.rgba.resize(4 * P);
+        for (size_t p = 0; p < P; p++) {
+            for (int c = 0; c < 3; c++) v.rgba[4 * p + c] = (uint8_t)std::lround(255.f * std::min(1.f, std::max(0.f, chw[c * P + p])));
+            v.rgba[4 * p + 3] = 255;
+        }
+    }
+    GsImageView out;
+    out.width = v.cam.width; out.height = v.cam.height; out.data = v.rgba.data(); out.name = v.name;
+    return out;
+}
+// cameras.json in the layout the public 3DGS tooling writes: one object per view with the camera centre and the
+// camera -> world rotation rows
+bool GaussianTrainerScene::saveCameraDatas(const std::string& jsonPath) const {
+    std::ofstream f(jsonPath);
+    if (!f.good()) return false;
+    f.precision(9);
+    f << "[";
+    for (size_t i = 0; i < impl_->views.size(); i++) {
+        const View& v = impl_->views[i];
+        f << (i ? ",\n " : "\n ") << "{\"id\": " << i << ", \"img_name\": \"" << v.name << "\", \"width\": " << v.cam.width
+          << ", \"height\": " << v.cam.height << ", \"position\": [" << v.cam.campos[0] << ", " << v.cam.campos[1] << ", "
+          << v.cam.campos[2] << "], \"rotation\": [";
+        for (int r = 0; r < 3; r++)  // row r of R^T
+            f << (r ? ", " : "") << "[" << v.Rt[r] << ", " << v.Rt[4 + r] << ", " << v.Rt[8 + r] << "]";
+        f << "], \"fx\": " << v.fx << ", \"fy\": " << v.fy << "}";
+    }
+    f << "\n]\n";
+    return f.good();
+}
+bool GaussianTrainerScene::exportSparsePointCloud(const std::string& plyPath) const {
+    std::ofstream f(plyPath, std::ios::binary);
+    if (!f.good()) return false;
+    const auto& pts = impl_->points3d;
+    f << "ply\nformat binary_little_endian 1.0\nelement vertex " << pts.size()
+      << "\nproperty float x\nproperty float y\nproperty float z\nproperty uchar red\nproperty uchar green\nproperty uchar blue\nend_header\n";
+    for (const auto& p : pts) {
+        f.write(reinterpret_cast<const char*>(&p.x), 12);
+        f.write(reinterpret_cast<const char*>(&p.r), 3);
+    }
+    return f.good();
+}
+void GaussianTrainerScene::updateFocusRegion(const GsVec3& position, const GsVec3& rotationDegrees, const GsVec3& scale) {
+    focus_region_position = position; focus_region_rotation = rotationDegrees; focus_region_scale = scale;
+}
+void GaussianTrainerScene::getFocusRegionMinMax(float mn[3], float mx[3]) const {
+    const auto& pts = impl_->points3d;
+    for (int k = 0; k < 3; k++) { mn[k] = pts.empty() ? -1.f : 3.4e38f; mx[k] = pts.empty() ? 1.f : -3.4e38f; }
+    for (const auto& p : pts) {
+        const float v[3] = {p.x, p.y, p.z};
+        for (int k = 0; k < 3; k++) { mn[k] = std::min(mn[k], v[k]); mx[k] = std::max(mx[k], v[k]); }
+    }
+}
+void GaussianTrainerScene::getFocusRegionTransformFlat(float m[16]) const {
+    const float d2r = 3.14159265358979f / 180.f;
+    const float cx = std::cos(focus_region_rotation.x * d2r), sx = std::sin(focus_region_rotation.x * d2r);
+    const float cy = std::cos(focus_region_rotation.y * d2r), sy = std::sin(focus_region_rotation.y * d2r);
+    const float cz = std::cos(focus_region_rotation.z * d2r), sz = std::sin(focus_region_rotation.z * d2r);
+    const float R[3][3] = {{cz * cy, cz * sy * sx - sz * cx, cz * sy * cx + sz * sx},
+                           {sz * cy, sz * sy * sx + cz * cx, sz * sy * cx - cz * sx},
+                           {-sy, cy * sx, cy * cx}};  // Rz * Ry * Rx
+    const float sc[3] = {focus_region_scale.x, focus_region_scale.y, focus_region_scale.z};
+    const float t[3] = {focus_region_position.x, focus_region_position.y, focus_region_position.z};
+    for (int c = 0; c < 3; c++) {
+        for (int r = 0; r < 3; r++) m[4 * c + r] = R[r][c] * sc[c];
+        m[4 * c + 3] = 0.f;
+    }
+    m[12] = t[0]; m[13] = t[1]; m[14] = t[2]; m[15] = 1.f;
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -19,7 +19,21 @@
 #include <array>
 #include <cstdint>
 #include <string>
+#include <utility>
 #include <vector>
+
+// The editor-facing methods speak glm (editor.cpp:852-856 passes their results to glm::translate / glm::mat4_cast /
+// maths::Frustum).  They are INLINE wrappers over glm-free exported methods, present only when glm is on the include
+// path (it is for both reference targets: ${GLM_INCLUDE_DIR}, application/diverseshot-cli/CMakeLists.txt:42), so the
+// class layout and the exported symbols are the same with or without it.
+#if defined(__has_include) && !defined(GSTRAIN_NO_GLM)
+#if __has_include(<glm/glm.hpp>) && __has_include(<glm/gtc/quaternion.hpp>)
+#include <glm/glm.hpp>
+#include <glm/gtc/quaternion.hpp>
+#include <glm/gtc/type_ptr.hpp>
+#define GSTRAIN_HAS_GLM 1
+#endif
+#endif
 
 // The editor links the trainer instead of dlopen-ing it (application/editor/source/editor.cpp:846-855,1426-1654 call the
 // class directly), so the class is exported; the CLI only needs the nine C symbols at the bottom.
@@ -88,6 +102,31 @@ struct GaussianViewerPack {
     int iteration = -1;               // training iteration the snapshot was taken after
 };
 
+// Three floats that convert from and to any vec3-like type (x, y, z members; V(x, y, z) constructor) — glm::vec3 in the
+// editor: `gs_train.focus_region_position = glm::vec3(0.0f)` (editor.cpp:1486), `glm::vec3 p = gsTrain->focus_region_position`
+// (inspector_panel.cpp:909), `gs->updateFocusRegion(focus_pos, focus_rot, focus_scale)` (:933).
+struct GsVec3 {
+    float x = 0.f, y = 0.f, z = 0.f;
+    GsVec3() = default;
+    GsVec3(float a, float b, float c) : x(a), y(b), z(c) {}
+    template <class V, class = decltype(std::declval<const V&>().x + std::declval<const V&>().y + std::declval<const V&>().z)>
+    GsVec3(const V& v) : x((float)v.x), y((float)v.y), z((float)v.z) {}
+    template <class V, class = decltype(V(0.f, 0.f, 0.f).x)>
+    operator V() const { return V(x, y, z); }
+};
+// One SfM / initialisation point: 16 bytes, the record GaussianModel::update_from_pos_color reads
+// (gaussian_model.cpp:70-95: three floats, then r, g, b bytes); editor.cpp:1523-1527 casts getPoints3D(0).data() to it.
+struct GsPoint3D {
+    float x, y, z;
+    uint8_t r, g, b, a;
+};
+// A training image for the dataset panel (img2d_dataset_panel.cpp:113-115: width, height, data as R8G8B8A8, name).
+struct GsImageView {
+    int width = 0, height = 0;
+    const uint8_t* data = nullptr;
+    std::string name;
+};
+
 struct GaussianTrainerImpl;  // B200 rasterizer context + device-resident parameters (gstrain.cu)
 
 class GSTRAIN_API GaussianTrainerScene {
@@ -96,6 +135,10 @@ public:
     ~GaussianTrainerScene();
     GaussianTrainerScene(const GaussianTrainerScene&) = delete;
     GaussianTrainerScene& operator=(const GaussianTrainerScene&) = delete;
+    // the editor keeps the trainer as an entt component (editor.cpp:2024 add_component<GaussianTrainerScene>(config, -1)),
+    // which needs a movable type
+    GaussianTrainerScene(GaussianTrainerScene&& o) noexcept;
+    GaussianTrainerScene& operator=(GaussianTrainerScene&& o) noexcept;
 
     bool loadTrainData(const std::string& path);
     void trainSetup();
@@ -129,12 +172,55 @@ public:
     void requestViewerPack();
     bool acquireViewerPack(GaussianViewerPack& out, bool wait);
     int getNumCameras() const;
-    std::array<float, 16> getCameraProjection(int i) const;  // flat [4c+r]
-    std::array<float, 16> getCameraView(int i) const;
+    std::array<float, 16> getCameraProjectionFlat(int i) const;  // the perspective matrix alone, flat [4c+r] (column-major)
+    std::array<float, 16> getCameraView(int i) const;            // world -> camera, flat [4c+r]
+    void getCameraRotationWXYZ(int i, float q[4]) const;         // camera -> world rotation as a unit quaternion
+    void getCameraPosXYZ(int i, float p[3]) const;               // camera centre in world space
+
+    // ---- the rest of the surface the editor calls (SURVEY.md §8-B "methods used by the editor")
+    void resetGaussian();                    // back to the initial parameters, optimizer state and iteration 0 (inspector_panel.cpp:837,1017)
+    void setDensifyStrategy(int strategy);   // 0 ADC, 1 MCMC, 2 ADC+ (inspector_panel.cpp:789); statistics restart
+    float getProgressOnCurrentPhase() const;               // 0..1 (scene_view_panel.cpp:1022)
+    std::string getCurrentTrainingPhaseName() const;       // scene_view_panel.cpp:1056, inspector_panel.cpp:997
+    float getTrainingElpasedTime() const;                  // seconds spent in trainStep (inspector_panel.cpp:998)
+    float getEstimateTrainingTime() const;                 // seconds remaining at the current rate
+    // editor -> trainer: replace the model by edited host arrays (raw parameters, the getters' layouts); the optimizer
+    // state restarts.  n may differ from the current count (inspector_panel.cpp:1037-1044 after splat editing).
+    void updateTensorFromHost(const float* pos, const float* rot, const float* scale, const float* opacity, const float* sh0,
+                              const float* shn, int64_t n);
+    const std::vector<GsPoint3D>& getPoints3D(int which) const;   // the initialisation point cloud (editor.cpp:1523)
+    GsImageView getSplatImageView(int id);                        // training image `id` as RGBA8 (img2d_dataset_panel.cpp:113)
+    bool saveCameraDatas(const std::string& jsonPath) const;      // editor.cpp:3512: cameras.json (id, img_name, width, height, position, rotation, fx, fy)
+    bool exportSparsePointCloud(const std::string& plyPath) const;  // editor.cpp:3535: x y z + red green blue
+    void updateFocusRegion(const GsVec3& position, const GsVec3& rotationDegrees, const GsVec3& scale);
+    void getFocusRegionMinMax(float mn[3], float mx[3]) const;   // the region's box before its transform (the points' bounding box)
+    void getFocusRegionTransformFlat(float m[16]) const;          // T * Rz * Ry * Rx * S, flat [4c+r]
+
+#ifdef GSTRAIN_HAS_GLM
+    glm::mat4 getCameraProjection(int i) const { return glm::make_mat4(getCameraProjectionFlat(i).data()); }  // editor.cpp:852
+    glm::quat getCameraRotation(int i) const { float q[4]; getCameraRotationWXYZ(i, q); return glm::quat(q[0], q[1], q[2], q[3]); }  // :854
+    glm::vec3 getCameraPos(int i) const { float p[3]; getCameraPosXYZ(i, p); return glm::vec3(p[0], p[1], p[2]); }  // :855
+    std::pair<glm::vec3, glm::vec3> getFocusRegion() const {  // scene_view_panel.cpp:1393
+        float a[3], b[3]; getFocusRegionMinMax(a, b);
+        return {glm::vec3(a[0], a[1], a[2]), glm::vec3(b[0], b[1], b[2])};
+    }
+    glm::mat4 getFocusRegionTransform() const { float m[16]; getFocusRegionTransformFlat(m); return glm::make_mat4(m); }  // :1394
+    // inspector_panel.cpp:1037-1044: the GaussianModel accessors' types (gaussian_model.h:88-95,134-139)
+    void updateTensorFromGaussianData(const std::vector<glm::vec3>& pos, const std::vector<glm::vec4>& rot,
+                                      const std::vector<glm::vec3>& scale, const std::vector<float>& opacity,
+                                      const std::vector<std::array<float, 3>>& sh0, const std::vector<std::array<float, 45>>& shn) {
+        static_assert(sizeof(glm::vec3) == 12 && sizeof(glm::vec4) == 16, "packed glm vectors");
+        updateTensorFromHost(pos.empty() ? nullptr : &pos[0].x, rot.empty() ? nullptr : &rot[0].x, scale.empty() ? nullptr : &scale[0].x,
+                             opacity.data(), sh0.empty() ? nullptr : sh0[0].data(), shn.empty() ? nullptr : shn[0].data(), (int64_t)pos.size());
+    }
+#else
+    std::array<float, 16> getCameraProjection(int i) const { return getCameraProjectionFlat(i); }
+#endif
 
     bool ShowTrainView = false;
     int curIteration = 0;
     std::vector<int> pruenIteraions;
+    GsVec3 focus_region_position{0.f, 0.f, 0.f}, focus_region_rotation{0.f, 0.f, 0.f}, focus_region_scale{1.f, 1.f, 1.f};
 
 private:
     int64_t plannedCapacity(int64_t N) const;  // arena size: capMax when the schedule reaches the refinement window
