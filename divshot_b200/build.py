@@ -139,25 +139,26 @@ def build_torch_binding(force: bool = False) -> str:
     return so
 
 
-def build_reference_cli(force: bool = False):
-    """Compile the reference's UNMODIFIED diverseshot-cli sources against include/gaussian_trainer_scene.hpp
+def build_reference_cli(force: bool = False, app: str = "diverseshot-cli"):
+    """Compile the reference's UNMODIFIED CLI sources (application/diverseshot-cli, or its older sibling
+    application/splatx-cli) against include/gaussian_trainer_scene.hpp
     (recipe verified in SURVEY.md section 8-b).  Only possible where /root/reference exists; the binary goes to
     build/refcli/ (git-ignored, travels to the GPU box).  plugin.cpp has a g++-13 compile error on Linux
     (plugin.cpp:93,125: std::format with a runtime string) so the loader is provided by tools/plugin_shim.cpp
     implementing the same core/plugin.h interface."""
     ref = "/root/reference"
     out_dir = os.path.join(ROOT, "build", "refcli")
-    exe = os.path.join(out_dir, "diverseshot-cli")
+    exe = os.path.join(out_dir, app)
     if not os.path.isdir(ref):
         return exe if os.path.exists(exe) else None
     shim = os.path.join(ROOT, "tools", "plugin_shim.cpp")
-    if os.path.exists(exe) and not force and os.path.getmtime(exe) > os.path.getmtime(shim):
+    if not force and not _stale(exe, [shim, os.path.join(ROOT, "include", "gaussian_trainer_scene.hpp")]):
         return exe
     os.makedirs(out_dir, exist_ok=True)
     import glob
-    inc = [os.path.join(ROOT, "include"), f"{ref}/application/diverseshot-cli/source", f"{ref}/diverse/diverse_base/source",
+    inc = [os.path.join(ROOT, "include"), f"{ref}/application/{app}/source", f"{ref}/diverse/diverse_base/source",
            f"{ref}/external/CLI11/include", f"{ref}/external", f"{ref}/external/spdlog/include", f"{ref}/external/glm"]
-    srcs = [f"{ref}/application/diverseshot-cli/source/main.cpp", f"{ref}/application/diverseshot-cli/source/gs_train.cpp",
+    srcs = [f"{ref}/application/{app}/source/main.cpp", f"{ref}/application/{app}/source/gs_train.cpp",
             f"{ref}/diverse/diverse_base/source/utility/file_utils.cpp", f"{ref}/diverse/diverse_base/source/core/ds_log.cpp",
             shim] + sorted(glob.glob(f"{ref}/external/spdlog/src/*.cpp"))
     cmd = [host_cxx(), "-std=c++20", "-O1", "-w", "-DDS_PLATFORM_LINUX", "-DDS_PLATFORM_UNIX", "-DSPDLOG_COMPILED_LIB",
@@ -211,6 +212,9 @@ def build_all(force: bool = False, verbose: bool = False, torch_binding: bool = 
     cli = build_reference_cli(force)
     if cli:
         libs["reference_cli"] = cli
+    cli2 = build_reference_cli(force, app="splatx-cli")
+    if cli2:
+        libs["reference_splatx_cli"] = cli2
     probe = build_editor_api_probe(force)
     if probe:
         libs["editor_api_probe"] = probe

@@ -36,6 +36,16 @@ def test_reference_cli_builds_unmodified_against_our_header():
     assert out.returncode == 0 and "--inputPath" in out.stdout and "--maxIteration" in out.stdout
 
 
+def test_reference_splatx_cli_builds_unmodified_against_our_header():
+    """application/splatx-cli — the reference's older CLI over the same nine symbols (for-loop instead of get_cur_step)."""
+    libs = _build()
+    cli = libs.get("reference_splatx_cli")
+    if not cli:
+        pytest.skip("reference sources not present (GPU box) and no prebuilt CLI")
+    out = subprocess.run([cli, "--help"], capture_output=True, text=True, env={**os.environ, "LD_LIBRARY_PATH": LIB})
+    assert out.returncode == 0 and "--inputPath" in out.stdout and "--maxIteration" in out.stdout
+
+
 def test_plugin_fails_loudly_without_cuda():
     import torch
     if torch.cuda.is_available():

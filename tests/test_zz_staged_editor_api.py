@@ -69,3 +69,20 @@ def test_editor_call_patterns_run(tmp_path):
     from test_plugin import _read_ply
     n, props, rows = _read_ply(out + ".ply")
     assert n == 5000 and np.isfinite(rows).all()
+
+
+@pytest.mark.gpu_staged
+def test_reference_splatx_cli_end_to_end(tmp_path):
+    """The unmodified application/splatx-cli trains through the plugin like diverseshot-cli does (tests/test_plugin.py)."""
+    from divshot_b200 import build
+    from test_plugin import LIB, _read_ply
+    cli = build.build_all(torch_binding=False).get("reference_splatx_cli")
+    if not cli:
+        pytest.skip("no prebuilt splatx-cli")
+    out = str(tmp_path / "splatx.ply")
+    r = subprocess.run([cli, "--inputPath", "synthetic:N=20000,W=320,H=240,views=4,deg=1", "--outputPath", out,
+                        "--maxIteration", "120"], capture_output=True, text=True,
+                       env={**os.environ, "LD_LIBRARY_PATH": LIB}, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    n, props, rows = _read_ply(out)
+    assert n == 20000 and len(props) == 59 and np.isfinite(rows).all()
