@@ -66,6 +66,25 @@ def test_host_build_matches_the_reference_quantiser_byte_for_byte(ops, N, seed, 
 
 
 @needs_ref
+def test_host_build_matches_the_reference_on_random_bit_patterns(ops):
+    """Every float32 bit pattern as input (infinities, subnormals, huge and tiny magnitudes): same bytes as the
+    reference, for every Gaussian whose inputs hold no NaN (NaN inputs are outside the contract, viewer_pack_ops.h)."""
+    rng = np.random.default_rng(123)
+    N = 100000
+    bits = lambda shape: rng.integers(0, 2 ** 32, size=shape, dtype=np.uint64).astype(np.uint32).view(np.float32)  # noqa: E731
+    m = dict(means=bits((N, 3)), scales=bits((N, 3)), quats=bits((N, 4)), opac=bits(N), sh0=bits((N, 3)), shN=bits((N, 45)))
+    m["quats"][:500] = np.where(rng.random((500, 4)) < 0.5, np.inf, m["quats"][:500])  # inf / inf: generated NaNs
+    clean = ~(np.isnan(m["means"]).any(1) | np.isnan(m["scales"]).any(1) | np.isnan(m["quats"]).any(1) | np.isnan(m["opac"])
+              | np.isnan(m["sh0"]).any(1) | np.isnan(m["shN"]).any(1))
+    assert clean.mean() > 0.7
+    with np.errstate(all="ignore"):
+        a, b = u.pack_with_host_ops(ops, m), u.pack_with_reference(m)
+    for name, x, y in zip(("gaussians", "colors", "sh"), a, b):
+        bad = np.flatnonzero((x != y).any(1) & clean)
+        assert bad.size == 0, f"{name}: rows {bad[:5].tolist()}"
+
+
+@needs_ref
 def test_frozen_digests_are_the_reference_library_output():
     for N, seed, deg in CASES[:4]:
         assert u.digest(*u.pack_with_reference(u.make_model(N, seed, deg))) == GOLDEN[f"N{N}_seed{seed}_deg{deg}"]
