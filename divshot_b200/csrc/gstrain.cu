@@ -422,8 +422,10 @@ GaussianTrainerScene& GaussianTrainerScene::operator=(GaussianTrainerScene&& o) 
 static bool refinementPossible(const GaussianTrainConfig& c) {
     return c.refineEvery > 0 && c.warmupLength + 1 < std::min(c.refineStopIter, c.numIters);
 }
+// the rasterizer addresses Gaussians with 24 bits (dvs_rast_forward: N < 2^24), so growth stops there whatever capMax says
+static int64_t effectiveCapMax(const GaussianTrainConfig& c) { return std::min<int64_t>(std::max(c.capMax, 1), (1 << 24) - 1); }
 int64_t GaussianTrainerScene::plannedCapacity(int64_t N) const {
-    return refinementPossible(config_) ? std::max<int64_t>(N, config_.capMax) : N;
+    return refinementPossible(config_) ? std::max<int64_t>(N, effectiveCapMax(config_)) : N;
 }
 
 static void parse_kv(const std::string& s, const char* key, long& out) {
@@ -657,13 +659,13 @@ void GaussianTrainerScene::trainStep() {
             const int64_t before = I.N;
             I.last_report = dvs_densify::RefineReport{};
             if (mcmc) {
-                ck(dvs_densify::mcmc_refine(I.dws, I.T(I.params), I.T(I.m1), I.T(I.m2), &I.N, I.capacity, config_.capMax,
+                ck(dvs_densify::mcmc_refine(I.dws, I.T(I.params), I.T(I.m1), I.T(I.m2), &I.N, I.capacity, effectiveCapMax(config_),
                                             config_.min_opacity, seed, I.stream, &I.last_report), "mcmc_refine");
             } else {
                 const dvs_densify::AdcConfig ac{config_.growGrad2d, 0.01f, I.scene_extent, config_.pruneOpacity,
                                                 config_.pruneScale3d};
                 ck(dvs_densify::adc_refine(I.dws, I.T(I.params), I.T(I.m1), I.T(I.m2), I.d_accum, I.d_denom, &I.N,
-                                           I.capacity, config_.capMax, ac, seed, I.stream, &I.last_report), "adc_refine");
+                                           I.capacity, effectiveCapMax(config_), ac, seed, I.stream, &I.last_report), "adc_refine");
                 if (config_.resetAlphaEvery > 0 && step % config_.resetAlphaEvery == 0)
                     ck(dvs_densify::adc_reset_opacity(I.T(I.params), I.T(I.m1), I.T(I.m2), I.N, I.stream), "reset_opacity");
             }
