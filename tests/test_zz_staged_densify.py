@@ -51,3 +51,26 @@ def test_trainer_refines_through_the_plugin_boundary(tmp_path):
         assert np.isfinite(rows).all() and 0 < n <= 24000
         if expect_growth:
             assert n == 24000, f"MCMC: 20000 * 1.05^k capped at capMax, got {n}"
+
+
+def test_unmodified_reference_cli_refines(tmp_path):
+    """The reference's own CLI with its own flags (main.cpp:54-57): warmupLength 100, refineEvery 100, 700 iterations,
+    MCMC (its default strategy), capMax 3 000 000 (hard-coded at gs_train.cpp:89): five refinements of +5 %."""
+    import subprocess
+
+    import numpy as np
+    from divshot_b200 import build
+    from test_plugin import LIB, _read_ply
+    cli = build.build_all(torch_binding=False).get("reference_cli")
+    if not cli:
+        pytest.skip("no prebuilt reference CLI")
+    out = str(tmp_path / "cli_refined.ply")
+    r = subprocess.run([cli, "--inputPath", "synthetic:N=20000,W=320,H=240,views=4,deg=1", "--outputPath", out,
+                        "--maxIteration", "700", "--warmupLength", "100", "--refineEvery", "100"], capture_output=True, text=True,
+                       env={**os.environ, "LD_LIBRARY_PATH": LIB}, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    n, props, rows = _read_ply(out)
+    expect = 20000
+    for _ in range(5):  # refinements after iterations 200 .. 600
+        expect = int(1.05 * expect)
+    assert n == expect and len(props) == 59 and np.isfinite(rows).all()
