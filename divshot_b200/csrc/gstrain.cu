@@ -181,6 +181,21 @@ static void launch_photometric_loss(const float* render, const float* target, fl
                                                  H, w_ssim, inv_n);
 }
 
+// useMask (main.cpp:69-70): a per-view mask M in [0,1] restricts the photometric loss to the masked region.  The loss sees
+// render' = M render + (1 - M) target (identical to the target where M = 0, so neither L1 nor SSIM reports a difference
+// there) and the chain rule gives dL/drender = M dL/drender'.  Two element-wise passes around the unchanged loss kernels.
+__global__ void mask_blend_kernel(float* __restrict__ render, const float* __restrict__ target, const float* __restrict__ mask,
+                                  size_t P) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < 3 * P; i += (size_t)gridDim.x * blockDim.x) {
+        const float m = mask[i % P];
+        render[i] = fmaf(m, render[i] - target[i], target[i]);
+    }
+}
+__global__ void mask_grad_kernel(float* __restrict__ dL_dpix, const float* __restrict__ mask, size_t P) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < 3 * P; i += (size_t)gridDim.x * blockDim.x)
+        dL_dpix[i] *= mask[i % P];
+}
+
 // fused Adam over one parameter group (4 streams in, 3 out, 128-bit where aligned is left to the compiler)
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps, float c1,
@@ -197,6 +212,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 struct View {
     dvs_camera cam;
     float* d_target = nullptr;  // [3,H,W] device
+    float* d_mask = nullptr;    // [H,W] device, optional (useMask)
     float Rt[12] = {0};         // world -> camera rows [R | t] as loaded
     float P[16] = {0};          // the perspective matrix alone, flat [4c+r]
     float fx = 0.f, fy = 0.f;
@@ -386,7 +402,7 @@ GaussianTrainerScene::GaussianTrainerScene(const GaussianTrainConfig& config, in
 GaussianTrainerScene::~GaussianTrainerScene() {
     if (!impl_) return;
     cudaDeviceSynchronize();
-    for (auto& v : impl_->views) cudaFree(v.d_target);
+    for (auto& v : impl_->views) { cudaFree(v.d_target); cudaFree(v.d_mask); }
     impl_->release_model();
     cudaFree(impl_->d_render); cudaFree(impl_->d_dLdpix); cudaFree(impl_->d_scratch); cudaFree(impl_->d_loss);
     for (auto& v : impl_->vp) { cudaFree(v.d); if (v.h) cudaFreeHost(v.h); if (v.ready) cudaEventDestroy(v.ready); }
@@ -530,6 +546,20 @@ bool GaussianTrainerScene::loadTrainData(const std::string& path) {
                 make_projection(vw.cam, Rt, W, H, fx, fy, vw.P);
                 ck(cudaMalloc(&vw.d_target, host.size() * sizeof(float)), "cudaMalloc target");
                 ck(cudaMemcpy(vw.d_target, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice), "upload image");
+                if (config_.useMask) {  // optional <image>.mask.pgm (binary P5, same size): 255 = train on this pixel
+                    std::ifstream mf(path + "/" + img + ".mask.pgm", std::ios::binary);
+                    std::string mm; int mw = 0, mh = 0, mv = 0;
+                    mf >> mm >> mw >> mh >> mv;
+                    mf.get();
+                    if (mf.good() && mm == "P5" && mw == W && mh == H && mv == 255) {
+                        std::vector<unsigned char> g((size_t)W * H);
+                        mf.read(reinterpret_cast<char*>(g.data()), g.size());
+                        std::vector<float> mk(g.size());
+                        for (size_t p = 0; p < g.size(); p++) mk[p] = g[p] / 255.f;
+                        ck(cudaMalloc(&vw.d_mask, mk.size() * sizeof(float)), "cudaMalloc mask");
+                        ck(cudaMemcpy(vw.d_mask, mk.data(), mk.size() * sizeof(float), cudaMemcpyHostToDevice), "upload mask");
+                    }
+                }
                 I.views.push_back(vw);
                 I.ensure_images(host.size());
             }
@@ -621,8 +651,11 @@ void GaussianTrainerScene::trainStep() {
         if (rc == DVS_E_OVERFLOW && attempt < 2) continue;
         ckr(rc, I.ctx, "forward");
         ck(cudaMemsetAsync(I.d_loss, 0, sizeof(float), I.stream), "memset loss");
+        const size_t npix = (size_t)cam.width * cam.height;
+        if (vw.d_mask) mask_blend_kernel<<<1184, 256, 0, I.stream>>>(I.d_render, vw.d_target, vw.d_mask, npix);
         launch_photometric_loss(I.d_render, vw.d_target, I.d_dLdpix, I.d_loss, I.d_scratch, cam.width, cam.height,
                                 std::min(1.f, std::max(0.f, config_.ssimWeight)), I.stream);
+        if (vw.d_mask) mask_grad_kernel<<<1184, 256, 0, I.stream>>>(I.d_dLdpix, vw.d_mask, npix);
         rc = dvs_rast_backward(I.ctx, &P, I.d_dLdpix, &G, bwd_flags, I.stream);
         if (rc == DVS_E_OVERFLOW && attempt < 2) continue;
         ckr(rc, I.ctx, "backward");
@@ -981,6 +1014,15 @@ GS_EXPORT void gstrain_destroy() { cudaDeviceSynchronize(); }
 GS_EXPORT void gstrain_photometric_loss(const float* render, const float* target, float* dL_dpix, float* loss,
                                         float* scratch, int W, int H, float ssim_weight, void* stream) {
     launch_photometric_loss(render, target, dL_dpix, loss, scratch, W, H, ssim_weight, static_cast<cudaStream_t>(stream));
+}
+// test hook (device pointers): the same with a per-pixel mask [H,W] (useMask); `render` is overwritten by the blended image
+GS_EXPORT void gstrain_masked_photometric_loss(float* render, const float* target, const float* mask, float* dL_dpix,
+                                               float* loss, float* scratch, int W, int H, float ssim_weight, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t npix = (size_t)W * H;
+    mask_blend_kernel<<<1184, 256, 0, st>>>(render, target, mask, npix);
+    launch_photometric_loss(render, target, dL_dpix, loss, scratch, W, H, ssim_weight, st);
+    mask_grad_kernel<<<1184, 256, 0, st>>>(dL_dpix, mask, npix);
 }
 // test hook (host pointers): the model writers without a trainer / GPU
 GS_EXPORT int gstrain_write_model(const char* path, long long N, const float* pos, const float* sh0, const float* shn,

@@ -74,3 +74,40 @@ def test_unmodified_reference_cli_refines(tmp_path):
     for _ in range(5):  # refinements after iterations 200 .. 600
         expect = int(1.05 * expect)
     assert n == expect and len(props) == 59 and np.isfinite(rows).all()
+
+
+@pytest.mark.parametrize("W,H,w", [(97, 61, 0.2), (64, 48, 1.0)])
+def test_masked_photometric_loss_matches_torch(W, H, w):
+    """useMask: loss(M x + (1 - M) y, y) and its gradient w.r.t. x against torch autograd (the unmasked loss kernels
+    are GPU-verified by tests/test_plugin.py::test_photometric_loss_matches_torch)."""
+    import torch
+    import torch.nn.functional as F
+    from divshot_b200 import build
+    lib = C.CDLL(build.build_gstrain())
+    lib.gstrain_masked_photometric_loss.argtypes = [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_float, C.c_void_p]
+    lib.gstrain_masked_photometric_loss.restype = None
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device="cpu"); g.manual_seed(5)
+    x = torch.rand(3, H, W, generator=g).to(dev).requires_grad_(True)
+    y = (x.detach() * 0.7 + 0.3 * torch.rand(3, H, W, generator=g).to(dev)).contiguous()
+    m = (torch.rand(H, W, generator=g) > 0.4).float()
+    m[: H // 3] = torch.rand(H // 3, W, generator=g)  # soft values too
+    m = m.to(dev).contiguous()
+    k = torch.arange(11, dtype=torch.float64) - 5
+    gk = torch.exp(-k ** 2 / (2 * 1.5 ** 2)); gk = (gk / gk.sum()).float().to(dev)
+    win = (gk[:, None] * gk[None, :]).expand(3, 1, 11, 11).contiguous()
+    conv = lambda t: F.conv2d(t[None], win, padding=5, groups=3)[0]  # noqa: E731
+    xb = m[None] * x + (1 - m[None]) * y
+    mx, my = conv(xb), conv(y)
+    sxx, syy, sxy = conv(xb * xb) - mx * mx, conv(y * y) - my * my, conv(xb * y) - mx * my
+    ssim = ((2 * mx * my + 0.01 ** 2) * (2 * sxy + 0.03 ** 2)) / ((mx * mx + my * my + 0.01 ** 2) * (sxx + syy + 0.03 ** 2))
+    loss_ref = (1 - w) * (xb - y).abs().mean() + w * (1 - ssim.mean())
+    loss_ref.backward()
+    xr = x.detach().clone().contiguous()
+    dl = torch.empty(3, H, W, device=dev); loss = torch.zeros(1, device=dev); scratch = torch.empty(9 * H * W, device=dev)
+    lib.gstrain_masked_photometric_loss(xr.data_ptr(), y.data_ptr(), m.data_ptr(), dl.data_ptr(), loss.data_ptr(), scratch.data_ptr(),
+                                        W, H, C.c_float(w), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(loss_ref)) <= 1e-5 * max(1.0, abs(float(loss_ref)))
+    assert float((dl - x.grad).abs().max()) <= 1e-4 * float(x.grad.abs().max()) + 1e-9
+    assert float(dl[:, m == 0].abs().max()) == 0.0
