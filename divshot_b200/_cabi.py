@@ -24,7 +24,7 @@ NUM_STAGES = 8
 EXPORTS = [
     "dvs_rast_create", "dvs_rast_destroy", "dvs_rast_last_error", "dvs_rast_version", "dvs_rast_reserve",
     "dvs_rast_forward", "dvs_rast_backward", "dvs_rast_step_host", "dvs_rast_get_stats", "dvs_rast_debug_read",
-    "dvs_rast_stage_ms", "dvs_rast_stage_name",
+    "dvs_rast_stage_ms", "dvs_rast_stage_name", "dvs_rast_forward_aux", "dvs_rast_backward_aux",
 ]
 COLL_EXPORTS = ["dvs_coll_allreduce_nvls"]
 
@@ -78,6 +78,11 @@ def load():
     L.dvs_rast_backward.argtypes = [C.c_void_p, C.POINTER(DvsParams), C.c_void_p, C.POINTER(DvsGrads), C.c_uint32,
                                     C.c_void_p]
     L.dvs_rast_backward.restype = C.c_int
+    L.dvs_rast_forward_aux.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.dvs_rast_forward_aux.restype = C.c_int
+    L.dvs_rast_backward_aux.argtypes = [C.c_void_p, C.POINTER(DvsParams), C.c_void_p, C.c_void_p, C.POINTER(DvsGrads),
+                                        C.c_uint32, C.c_void_p]
+    L.dvs_rast_backward_aux.restype = C.c_int
     L.dvs_rast_step_host.argtypes = [C.c_void_p, C.POINTER(DvsCamera), C.c_int64, C.POINTER(DvsParams),
                                      C.POINTER(DvsGrads), C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
     L.dvs_rast_step_host.restype = C.c_int

@@ -29,6 +29,7 @@ CU_SOURCES = {
     "render_fwd.cu": [],
     "render_bwd.cu": [],
     "api.cu": [],
+    "aux_outputs.cu": [],
     "collective.cu": [],
 }
 

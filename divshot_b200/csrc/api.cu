@@ -48,6 +48,13 @@ struct dvs_rast_ctx {
     uint32_t* n_contrib = nullptr;
     float* h2d_grad = nullptr;   // [3P] staging for dvs_rast_step_host
     float* d_image = nullptr;    // [3P]
+    // F4 auxiliary outputs (dvs_rast_forward_aux / dvs_rast_backward_aux), allocated on first use
+    int64_t cap_aux_gauss = 0, cap_aux_pix = 0;
+    float4* rec_aux = nullptr;   // [3 cap] records with the colour replaced by (depth, 1, 0)
+    float* aux_dz = nullptr;     // [cap] dL/d(view-space depth) per Gaussian
+    float* aux_img = nullptr;    // [3P] staging: the compositing kernels work on three planes
+    float* aux_T = nullptr;      // [P]
+    uint32_t* aux_nc = nullptr;  // [P]
     // small device words + pinned mirror
     uint32_t* info = nullptr;               // [16]: D, max len, overflow, -, tiles per sort class [5]
     unsigned long long* stats = nullptr;    // [2]: V, D
@@ -212,6 +219,7 @@ void dvs_rast_destroy(dvs_rast_ctx* ctx) {
     cudaFree(ctx->tile_count); cudaFree(ctx->tile_base); cudaFree(ctx->tile_cursor); cudaFree(ctx->class_tiles);
     cudaFree(ctx->bins); cudaFree(ctx->plist);
     cudaFree(ctx->final_T); cudaFree(ctx->n_contrib); cudaFree(ctx->h2d_grad); cudaFree(ctx->d_image);
+    cudaFree(ctx->rec_aux); cudaFree(ctx->aux_dz); cudaFree(ctx->aux_img); cudaFree(ctx->aux_T); cudaFree(ctx->aux_nc);
     cudaFree(ctx->info); cudaFree(ctx->stats);
     cudaFreeHost(ctx->h_info); cudaFreeHost(ctx->h_stats);
     for (auto& e : ctx->ev)
@@ -412,6 +420,94 @@ int dvs_rast_backward(dvs_rast_ctx* ctx, const dvs_params* params, const float* 
                          ctx->info, st));
     CK(cudaEventRecord(ctx->ev[7], st));
     CK(launch_preprocess_bwd(c, (int)N, prm, ctx->aux, ctx->sgrad, g, flags, st));
+    CK(cudaEventRecord(ctx->ev[8], st));
+    ctx->ev_bwd = true;
+    return DVS_OK;
+}
+
+// ---- F4: depth / alpha maps and their gradients by linearity (aux_outputs.cu explains the construction)
+static int ensure_aux(dvs_rast_ctx* ctx, int64_t N, int64_t P) {
+    if (N > ctx->cap_aux_gauss) {
+        const int64_t cap = std::max<int64_t>(N, ctx->cap_gauss);
+        CK(regrow(ctx->rec_aux, 3 * (size_t)cap));
+        CK(regrow(ctx->aux_dz, (size_t)cap));
+        ctx->cap_aux_gauss = cap;
+    }
+    if (P > ctx->cap_aux_pix) {
+        CK(regrow(ctx->aux_img, 3 * (size_t)P));
+        CK(regrow(ctx->aux_T, (size_t)P));
+        CK(regrow(ctx->aux_nc, (size_t)P));
+        ctx->cap_aux_pix = P;
+    }
+    return DVS_OK;
+}
+
+int dvs_rast_forward_aux(dvs_rast_ctx* ctx, float* out_aux, void* stream) {
+    if (!ctx) return DVS_E_INVALID;
+    if (!out_aux) return fail(ctx, DVS_E_INVALID, "null output");
+    if (!ctx->have_fwd) return fail(ctx, DVS_E_STATE, "forward_aux without a forward on this context");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(ctx->device));
+    Cam c = ctx->cam;
+    c.bg[0] = c.bg[1] = c.bg[2] = 0.0f;
+    const int64_t N = ctx->N, P = (int64_t)c.W * c.H;
+    int rc;
+    if ((rc = ensure_aux(ctx, N > 0 ? N : 1, P))) return rc;
+    CK(launch_aux_records((int)N, ctx->rec, ctx->rec_aux, st));
+    CK(launch_render_fwd(c, ctx->tile_base, ctx->plist, ctx->rec_aux, ctx->aux_img, ctx->aux_T, ctx->aux_nc, ctx->info, st));
+    CK(cudaMemcpyAsync(out_aux, ctx->aux_img, 2 * (size_t)P * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return DVS_OK;
+}
+
+int dvs_rast_backward_aux(dvs_rast_ctx* ctx, const dvs_params* params, const float* dL_dpix, const float* dL_daux,
+                          const dvs_grads* grads, uint32_t flags, void* stream) {
+    if (!ctx) return DVS_E_INVALID;
+    {
+        int rcp = resolve_pending(ctx, false);
+        if (rcp) return rcp;
+    }
+    if (!ctx->have_fwd) return fail(ctx, DVS_E_STATE, "backward without a forward on this context");
+    if (!dL_dpix || !dL_daux || !grads) return fail(ctx, DVS_E_INVALID, "null dL_dpix / dL_daux / grads");
+    const Cam& c = ctx->cam;
+    const int64_t N = ctx->N, P = (int64_t)c.W * c.H;
+    int rc;
+    if (N > 0) {
+        if ((rc = check_params(ctx, params, c.KR))) return rc;
+        if (!grads->means3D || !grads->scales || !grads->quats || !grads->opacities || !grads->sh0 ||
+            (c.KR > 0 && !grads->shN))
+            return fail(ctx, DVS_E_INVALID, "null gradient pointer");
+        if (!aligned16(grads->quats) || (c.KR > 0 && !aligned16(grads->shN)))
+            return fail(ctx, DVS_E_INVALID, "gradient pointers must be 16-byte aligned");
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(ctx->device));
+    if ((rc = ensure_aux(ctx, N > 0 ? N : 1, P))) return rc;
+    Params prm{};
+    Grads g{};
+    if (N > 0) {
+        prm = Params{params->means3D, params->scales, params->quats, params->opacities, params->sh0, params->shN};
+        g = Grads{grads->means3D, grads->scales, grads->quats, grads->opacities, grads->sh0, grads->shN,
+                  (flags & DVS_FLAG_ABSGRAD) ? grads->mean2D_abs : nullptr, grads->mean2D};
+    }
+    CK(cudaEventRecord(ctx->ev[6], st));
+    // 1. the auxiliary loss: same reverse walk, colour triple (depth, 1, 0), zero background, third plane of dL zero
+    Cam c0 = c;
+    c0.bg[0] = c0.bg[1] = c0.bg[2] = 0.0f;
+    CK(launch_aux_records((int)N, ctx->rec, ctx->rec_aux, st));
+    CK(cudaMemcpyAsync(ctx->aux_img, dL_daux, 2 * (size_t)P * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemsetAsync(ctx->aux_img + 2 * (size_t)P, 0, (size_t)P * sizeof(float), st));
+    CK(launch_render_bwd(c0, ctx->tile_base, ctx->plist, ctx->rec_aux, ctx->final_T, ctx->n_contrib, ctx->aux_img,
+                         reinterpret_cast<float*>(ctx->sgrad), false, ctx->info, st));
+    // 2. its colour sums are dL/dz: out of the records, so that the colour pass finds slots 6-8 empty
+    CK(launch_aux_extract((int)N, ctx->sgrad, ctx->aux_dz, st));
+    // 3. the colour loss adds its geometry sums on top, then the per-Gaussian backward consumes the total
+    CK(launch_render_bwd(c, ctx->tile_base, ctx->plist, ctx->rec, ctx->final_T, ctx->n_contrib, dL_dpix,
+                         reinterpret_cast<float*>(ctx->sgrad), (flags & DVS_FLAG_ABSGRAD) && g.mean2D_abs, ctx->info, st));
+    CK(cudaEventRecord(ctx->ev[7], st));
+    CK(launch_preprocess_bwd(c, (int)N, prm, ctx->aux, ctx->sgrad, g, flags, st));
+    // 4. dL/dmean += (row 2 of the view matrix) * dL/dz
+    const float row2[3] = {c.view[2], c.view[6], c.view[10]};
+    if (N > 0) CK(launch_aux_depth_grad((int)N, ctx->aux_dz, row2, g.means3D, st));
     CK(cudaEventRecord(ctx->ev[8], st));
     ctx->ev_bwd = true;
     return DVS_OK;

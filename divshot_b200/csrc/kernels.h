@@ -39,6 +39,12 @@ cudaError_t launch_render_bwd(const Cam& cam, const uint32_t* tile_base, const u
 cudaError_t launch_preprocess_bwd(const Cam& cam, int N, const Params& prm, const uint4* aux, float4* sgrad,
                                   const Grads& g, uint32_t flags, cudaStream_t st);
 
+// F4 auxiliary outputs by linearity (aux_outputs.cu): records with the colour replaced by (depth, 1, 0); dL/ddepth per
+// Gaussian moved out of the screen-gradient records; its contribution to dL/dmean
+cudaError_t launch_aux_records(int N, const float4* rec, float4* rec_aux, cudaStream_t st);
+cudaError_t launch_aux_extract(int N, float4* sgrad, float* dz, cudaStream_t st);
+cudaError_t launch_aux_depth_grad(int N, const float* dz, const float view_row2[3], float* dmeans, cudaStream_t st);
+
 // debug helpers (parity tests): unpack records into the upstream-style arrays
 cudaError_t launch_unpack(int N, const float4* rec, int32_t* radii, uint32_t* tiles, float* depth, float* mean2D,
                           float* conic_opacity, float* rgb, uint8_t* clamped, cudaStream_t st);

@@ -138,6 +138,28 @@ class Rasterizer:
                                                 C.byref(g), flags, C.c_void_p(st)))
         return grads
 
+    def forward_aux(self, out_aux: torch.Tensor | None = None) -> torch.Tensor:
+        """[2,H,W] = (depth, alpha) of the last forward (dvs_rast_forward_aux)."""
+        if out_aux is None:
+            out_aux = torch.empty(2, self._cam.height, self._cam.width, dtype=torch.float32, device=self.device)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self._lib.dvs_rast_forward_aux(self._h, out_aux.data_ptr(), C.c_void_p(st)))
+        return out_aux
+
+    def backward_aux(self, dL_dpix: torch.Tensor, dL_daux: torch.Tensor, grads: GradBuffers, flags: int = 0):
+        """Backward of <image, dL_dpix> + <depth, dL_daux[0]> + <alpha, dL_daux[1]> (dvs_rast_backward_aux)."""
+        for t in (dL_dpix, dL_daux):
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+        g = _cabi.DvsGrads()
+        for n in PARAM_NAMES:
+            t = getattr(grads, n)
+            if t.numel() > 0:
+                setattr(g, n, t.data_ptr())
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self._lib.dvs_rast_backward_aux(self._h, C.byref(self._pstruct(self._params)), dL_dpix.data_ptr(),
+                                                    dL_daux.data_ptr(), C.byref(g), flags, C.c_void_p(st)))
+        return grads
+
     def step_host(self, cam, params: dict, grads: GradBuffers, dL_dpix_host: torch.Tensor,
                   out_color_host: torch.Tensor, flags: int = 0):
         """End-to-end step with HOST image buffers (pinned): H2D dL/dpix, forward, backward, D2H image."""

@@ -103,8 +103,9 @@ def project(cam, means, log_scales, quats, logit, sh0, shN, sh_degree, activated
                 cov2D=torch.stack([a, b, c], 1), Sigma=Sigma)
 
 
-def composite(cam, proj, ranges, point_list, visible):
-    """Tile compositing (Appendix B.3) in float64 using the given sorted lists."""
+def composite(cam, proj, ranges, point_list, visible, aux=None):
+    """Tile compositing (Appendix B.3) in float64 using the given sorted lists.  `aux`: a [2,H,W] tensor that receives the
+    auxiliary maps depth = sum_k w_k z_k and alpha = sum_k w_k (row F4)."""
     W, H = cam.width, cam.height
     gx = (W + 15) // 16
     bg = torch.tensor(np.asarray(cam.bg, np.float64))
@@ -146,6 +147,9 @@ def composite(cam, proj, ranges, point_list, visible):
         out = col + T_fin[:, None] * bg[None, :]
         ny, nx = len(ys), len(xs)
         img[:, y0:y0 + ny, x0:x0 + nx] = out.T.reshape(3, ny, nx)
+        if aux is not None:
+            extra = wgt @ torch.stack([proj["depth"][ids], torch.ones(len(ids), dtype=torch.float64)], 1)  # [P,2]
+            aux[:, y0:y0 + ny, x0:x0 + nx] = extra.T.reshape(2, ny, nx)
         with torch.no_grad():
             kk = keep.numpy()
             last = np.where(kk.any(1), kk.shape[1] - np.argmax(kk[:, ::-1], 1), 0)
@@ -154,15 +158,21 @@ def composite(cam, proj, ranges, point_list, visible):
     return img, n_contrib, final_T
 
 
-def render_and_grad(cam, scene_arrays, sh_degree, ranges, point_list, radii, dL_dpix, activated=False, antialias=False):
-    """Returns (image float64 numpy, dict of gradient numpy arrays w.r.t. the stored parameters)."""
+def render_and_grad(cam, scene_arrays, sh_degree, ranges, point_list, radii, dL_dpix, activated=False, antialias=False,
+                    dL_daux=None):
+    """Returns (image float64 numpy, dict of gradient numpy arrays w.r.t. the stored parameters).  With dL_daux [2,H,W]
+    the loss also has <depth, dL_daux[0]> + <alpha, dL_daux[1]>; the maps are returned under proj["aux"]."""
     names = ["means3D", "scales", "quats", "opac", "sh0", "shN"]
     ts = {k: torch.tensor(np.asarray(v, np.float64), requires_grad=True) for k, v in zip(names, scene_arrays)}
     proj = project(cam, ts["means3D"], ts["scales"], ts["quats"], ts["opac"].reshape(-1), ts["sh0"],
                    ts["shN"], sh_degree, activated, antialias)
     visible = np.asarray(radii) > 0
-    img, n_contrib, final_T = composite(cam, proj, np.asarray(ranges), point_list, visible)
+    aux = torch.zeros(2, cam.height, cam.width, dtype=torch.float64) if dL_daux is not None else None
+    img, n_contrib, final_T = composite(cam, proj, np.asarray(ranges), point_list, visible, aux)
     loss = (img * torch.tensor(np.asarray(dL_dpix, np.float64))).sum()
+    if aux is not None:
+        loss = loss + (aux * torch.tensor(np.asarray(dL_daux, np.float64))).sum()
+        proj["aux"] = aux.detach().numpy()
     loss.backward()
     grads = {k: (ts[k].grad.numpy() if ts[k].grad is not None else np.zeros_like(ts[k].detach().numpy()))
              for k in names}

@@ -1,0 +1,100 @@
+"""SURVEY.md §8 row F4 — depth / alpha maps and their gradients (for depth- and normal-consistency losses, mesh
+extraction), produced by linearity from the existing compositor (tests/aux_ref.py explains the construction).
+CPU tier: the oracle-level restatement against a float64 autograd re-expression that shares no code with it.
+GPU tier (STAGED): dvs_rast_forward_aux / dvs_rast_backward_aux against the restatement."""
+import numpy as np
+import pytest
+
+import autograd_ref as ar
+import aux_ref
+from divshot_b200.scenes import make_scene
+from oracle import oracle as orc
+from util import assert_close, assert_close_robust, orc_cam, scene_arrays
+
+
+def _scene(seed, deg, bg=(0, 0, 0)):
+    sc = make_scene(N=1200, width=64, height=48, sh_degree=deg, seed=seed, normalise_quats=False, bg=bg)
+    sc.log_scales += 1.2
+    return sc
+
+
+@pytest.mark.parametrize("deg,seed,bg", [(1, 11, (0, 0, 0)), (3, 12, (0.3, 0.1, 0.7))])
+def test_oracle_restatement_matches_float64_autograd(deg, seed, bg):
+    sc = _scene(seed, deg, bg)
+    cam = sc.cameras[0]
+    oc = orc_cam(cam, deg)
+    arrays = scene_arrays(sc)
+    fwd = orc.forward(oc, *arrays, threads=1)
+    rng = np.random.default_rng(seed)
+    dL_daux = rng.normal(size=(2, cam.height, cam.width)).astype(np.float32)
+    dL_daux[0] *= 0.2
+    img, g, proj, _, final_T = ar.render_and_grad(cam, arrays, deg, fwd.ranges, fwd.point_list, fwd.radii, sc.dL_dpix[0], dL_daux=dL_daux)
+    aux = aux_ref.forward_aux(oc, fwd)
+    assert_close(aux[0], proj["aux"][0], 1e-4, "depth map")
+    assert_close(aux[1], proj["aux"][1], 1e-4, "alpha map")
+    assert np.allclose(aux[1], 1.0 - fwd.final_T.reshape(cam.height, cam.width), atol=2e-6), "alpha = 1 - T"
+    assert aux[0].max() > 2.0 and (aux[0] >= 0).all()  # depths of this scene are 2..10
+    b = aux_ref.backward_with_aux(oc, fwd, *arrays, sc.dL_dpix[0], dL_daux)
+    assert_close_robust(b["means3D"], g["means3D"], 1e-4, "dL_dmeans3D", frac=0.995)
+    assert_close_robust(b["scales"], g["scales"], 1e-4, "dL_dscales", frac=0.995)
+    assert_close_robust(b["quats"], g["quats"], 1e-4, "dL_dquats", frac=0.995)
+    assert_close_robust(b["opac"], g["opac"].reshape(-1), 1e-4, "dL_dopacity", frac=0.995)
+    assert_close(b["sh0"], g["sh0"], 2e-4, "dL_dsh0")
+    assert_close(b["shN"], g["shN"], 2e-4, "dL_dshN")
+    # the depth term really matters in this test: without it the mean gradient is visibly different
+    plain = orc.backward(oc, fwd, *arrays, sc.dL_dpix[0], threads=1)
+    assert np.abs(plain.dL_dmeans3D - b["means3D"]).max() > 1e-2 * np.abs(b["means3D"]).max()
+
+
+@pytest.mark.gpu_staged
+@pytest.mark.parametrize("deg,seed,bg,N,W,H", [(1, 11, (0, 0, 0), 1200, 64, 48), (3, 12, (0.3, 0.1, 0.7), 4000, 128, 96),
+                                                (2, 13, (1, 1, 1), 30000, 320, 200)])
+def test_cuda_aux_outputs_match_the_oracle_restatement(deg, seed, bg, N, W, H):
+    import torch
+    from divshot_b200 import _cabi
+    from divshot_b200.rasterizer import GradBuffers, Rasterizer, scene_to_device
+    sc = make_scene(N=N, width=W, height=H, sh_degree=deg, seed=seed, normalise_quats=False, bg=bg)
+    sc.log_scales += 0.8
+    cam = sc.cameras[0]
+    oc = orc_cam(cam, deg)
+    arrays = scene_arrays(sc)
+    fwd = orc.forward(oc, *arrays)
+    rng = np.random.default_rng(seed)
+    dL_daux = rng.normal(size=(2, H, W)).astype(np.float32)
+    dL_daux[0] *= 0.2
+    r = Rasterizer(0)
+    try:
+        params = scene_to_device(sc, r.device)
+        dcam = _cabi.make_camera(cam, deg)
+        img, radii = r.forward(dcam, params)
+        aux = r.forward_aux().cpu().numpy()
+        ref = aux_ref.forward_aux(oc, fwd)
+        assert_close(aux[0], ref[0], 1e-4, "depth map")
+        assert_close(aux[1], ref[1], 1e-4, "alpha map")
+        g = GradBuffers.allocate(sc.N, sc.shN.shape[1], r.device)
+        g.flat.fill_(float("nan"))
+        dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(r.device)  # noqa: E731
+        r.backward_aux(dev(sc.dL_dpix[0]), dev(dL_daux), g)
+        torch.cuda.synchronize()
+        b = aux_ref.backward_with_aux(oc, fwd, *arrays, sc.dL_dpix[0], dL_daux)
+        assert_close_robust(g.means3D.cpu().numpy(), b["means3D"], 1e-4, "dL_dmeans3D", frac=0.995)
+        assert_close_robust(g.scales.cpu().numpy(), b["scales"], 1e-4, "dL_dscales", frac=0.995)
+        assert_close_robust(g.quats.cpu().numpy(), b["quats"], 1e-4, "dL_dquats", frac=0.995)
+        assert_close_robust(g.opacities.cpu().numpy().reshape(-1), b["opac"], 1e-4, "dL_dopacity", frac=0.995)
+        assert_close(g.sh0.cpu().numpy(), b["sh0"], 2e-4, "dL_dsh0")
+        assert_close(g.shN.cpu().numpy(), b["shN"], 2e-4, "dL_dshN")
+        # the plain backward afterwards is unaffected (the screen-gradient records were left clean)
+        g2 = GradBuffers.allocate(sc.N, sc.shN.shape[1], r.device)
+        r.forward(dcam, params)
+        r.backward(dev(sc.dL_dpix[0]), g2)
+        torch.cuda.synchronize()
+        plain = orc.backward(oc, fwd, *arrays, sc.dL_dpix[0])
+        assert_close_robust(g2.means3D.cpu().numpy(), plain.dL_dmeans3D, 1e-4, "plain dL_dmeans3D", frac=0.995)
+        assert_close(g2.sh0.cpu().numpy(), plain.dL_dsh0, 2e-4, "plain dL_dsh0")
+        # zero auxiliary gradient == plain backward
+        g3 = GradBuffers.allocate(sc.N, sc.shN.shape[1], r.device)
+        r.backward_aux(dev(sc.dL_dpix[0]), torch.zeros(2, H, W, device=r.device), g3)
+        torch.cuda.synchronize()
+        assert_close_robust(g3.means3D.cpu().numpy(), g2.means3D.cpu().numpy(), 1e-5, "zero-aux means", frac=0.999)
+    finally:
+        r.close()
