@@ -138,6 +138,23 @@ def run_cpu_sample(threads=0, reps=1, frac_lin=2):
     return sc.N, times, threads, sample
 
 
+def measure_viewer_pack_row():
+    """Row F3 (trainer -> viewer hand-off, SURVEY.md §8 f) measured by its own harness, tools/bench_viewer_pack.py, in a
+    SUBPROCESS after the headline measurement is complete: the row was built when round 1 had no GPU minutes left, so this
+    is its first run on a B200 — a failure there must not be able to disturb the headline number (separate CUDA context,
+    time-boxed), and is reported as text instead."""
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_viewer_pack.py"), "--steps", "30", "--warmup", "5"],
+                           capture_output=True, text=True, timeout=300, cwd=ROOT)
+        rows = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode != 0 or not rows:
+            return {"error": (r.stderr or r.stdout)[-600:]}
+        d = json.loads(rows[-1])
+        return {k: d.get(k) for k in ("metric", "value", "unit", "ms_per_step", "config", "roofline", "e2e", "cpu_baseline", "gpu_launches")}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)[:600]}
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -166,6 +183,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, help="override: c2|c3|c5 (parity/bench exploration only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-rows", action="store_true", help="skip the sub-process measurement of the other section-8 rows")
     ap.add_argument("--allreduce", default="auto", choices=["auto", "nvls", "nccl"],
                     help="gradient all-reduce: NVSwitch in-switch reduction over symmetric memory, or plain NCCL")
     args = ap.parse_args()
@@ -339,6 +357,8 @@ def main():
         best = min(times)
         line["cpu_baseline"] = {"value": n_s / best, "unit": "Gaussians/s", "cores": cores, "kind": "port",
                                 "sample": sample + f"; best of 3 ({best:.2f} s)"}
+    if world == 1 and rank == 0 and not args.no_rows:
+        line["other_rows"] = {"F3_viewer_pack": measure_viewer_pack_row()}
     if rank == 0:
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
