@@ -78,9 +78,9 @@ def load():
     L.dvs_rast_backward.argtypes = [C.c_void_p, C.POINTER(DvsParams), C.c_void_p, C.POINTER(DvsGrads), C.c_uint32,
                                     C.c_void_p]
     L.dvs_rast_backward.restype = C.c_int
-    L.dvs_rast_forward_aux.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.dvs_rast_forward_aux.argtypes = [C.c_void_p, C.POINTER(DvsParams), C.c_void_p, C.c_void_p, C.c_void_p]
     L.dvs_rast_forward_aux.restype = C.c_int
-    L.dvs_rast_backward_aux.argtypes = [C.c_void_p, C.POINTER(DvsParams), C.c_void_p, C.c_void_p, C.POINTER(DvsGrads),
+    L.dvs_rast_backward_aux.argtypes = [C.c_void_p, C.POINTER(DvsParams), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(DvsGrads),
                                         C.c_uint32, C.c_void_p]
     L.dvs_rast_backward_aux.restype = C.c_int
     L.dvs_rast_step_host.argtypes = [C.c_void_p, C.POINTER(DvsCamera), C.c_int64, C.POINTER(DvsParams),

@@ -52,6 +52,7 @@ struct dvs_rast_ctx {
     int64_t cap_aux_gauss = 0, cap_aux_pix = 0;
     float4* rec_aux = nullptr;   // [3 cap] records with the colour replaced by (depth, 1, 0)
     float* aux_dz = nullptr;     // [cap] dL/d(view-space depth) per Gaussian
+    float* aux_dn = nullptr;     // [3 cap] dL/d(view-space normal) per Gaussian
     float* aux_img = nullptr;    // [3P] staging: the compositing kernels work on three planes
     float* aux_T = nullptr;      // [P]
     uint32_t* aux_nc = nullptr;  // [P]
@@ -219,7 +220,7 @@ void dvs_rast_destroy(dvs_rast_ctx* ctx) {
     cudaFree(ctx->tile_count); cudaFree(ctx->tile_base); cudaFree(ctx->tile_cursor); cudaFree(ctx->class_tiles);
     cudaFree(ctx->bins); cudaFree(ctx->plist);
     cudaFree(ctx->final_T); cudaFree(ctx->n_contrib); cudaFree(ctx->h2d_grad); cudaFree(ctx->d_image);
-    cudaFree(ctx->rec_aux); cudaFree(ctx->aux_dz); cudaFree(ctx->aux_img); cudaFree(ctx->aux_T); cudaFree(ctx->aux_nc);
+    cudaFree(ctx->rec_aux); cudaFree(ctx->aux_dz); cudaFree(ctx->aux_dn); cudaFree(ctx->aux_img); cudaFree(ctx->aux_T); cudaFree(ctx->aux_nc);
     cudaFree(ctx->info); cudaFree(ctx->stats);
     cudaFreeHost(ctx->h_info); cudaFreeHost(ctx->h_stats);
     for (auto& e : ctx->ev)
@@ -431,6 +432,7 @@ static int ensure_aux(dvs_rast_ctx* ctx, int64_t N, int64_t P) {
         const int64_t cap = std::max<int64_t>(N, ctx->cap_gauss);
         CK(regrow(ctx->rec_aux, 3 * (size_t)cap));
         CK(regrow(ctx->aux_dz, (size_t)cap));
+        CK(regrow(ctx->aux_dn, 3 * (size_t)cap));
         ctx->cap_aux_gauss = cap;
     }
     if (P > ctx->cap_aux_pix) {
@@ -442,9 +444,9 @@ static int ensure_aux(dvs_rast_ctx* ctx, int64_t N, int64_t P) {
     return DVS_OK;
 }
 
-int dvs_rast_forward_aux(dvs_rast_ctx* ctx, float* out_aux, void* stream) {
+int dvs_rast_forward_aux(dvs_rast_ctx* ctx, const dvs_params* params, float* out_aux, float* out_normal, void* stream) {
     if (!ctx) return DVS_E_INVALID;
-    if (!out_aux) return fail(ctx, DVS_E_INVALID, "null output");
+    if (!out_aux && !out_normal) return fail(ctx, DVS_E_INVALID, "null outputs");
     if (!ctx->have_fwd) return fail(ctx, DVS_E_STATE, "forward_aux without a forward on this context");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(cudaSetDevice(ctx->device));
@@ -452,22 +454,31 @@ int dvs_rast_forward_aux(dvs_rast_ctx* ctx, float* out_aux, void* stream) {
     c.bg[0] = c.bg[1] = c.bg[2] = 0.0f;
     const int64_t N = ctx->N, P = (int64_t)c.W * c.H;
     int rc;
+    if (out_normal && N > 0 && (rc = check_params(ctx, params, c.KR))) return rc;
     if ((rc = ensure_aux(ctx, N > 0 ? N : 1, P))) return rc;
-    CK(launch_aux_records((int)N, ctx->rec, ctx->rec_aux, st));
-    CK(launch_render_fwd(c, ctx->tile_base, ctx->plist, ctx->rec_aux, ctx->aux_img, ctx->aux_T, ctx->aux_nc, ctx->info, st));
-    CK(cudaMemcpyAsync(out_aux, ctx->aux_img, 2 * (size_t)P * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (out_aux) {
+        CK(launch_aux_records((int)N, ctx->rec, ctx->rec_aux, st));
+        CK(launch_render_fwd(c, ctx->tile_base, ctx->plist, ctx->rec_aux, ctx->aux_img, ctx->aux_T, ctx->aux_nc, ctx->info, st));
+        CK(cudaMemcpyAsync(out_aux, ctx->aux_img, 2 * (size_t)P * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    if (out_normal) {
+        Params prm{};
+        if (N > 0) prm = Params{params->means3D, params->scales, params->quats, params->opacities, params->sh0, params->shN};
+        CK(launch_aux_normal_records(c, (int)N, prm, ctx->rec, ctx->rec_aux, st));
+        CK(launch_render_fwd(c, ctx->tile_base, ctx->plist, ctx->rec_aux, out_normal, ctx->aux_T, ctx->aux_nc, ctx->info, st));
+    }
     return DVS_OK;
 }
 
 int dvs_rast_backward_aux(dvs_rast_ctx* ctx, const dvs_params* params, const float* dL_dpix, const float* dL_daux,
-                          const dvs_grads* grads, uint32_t flags, void* stream) {
+                          const float* dL_dnormal, const dvs_grads* grads, uint32_t flags, void* stream) {
     if (!ctx) return DVS_E_INVALID;
     {
         int rcp = resolve_pending(ctx, false);
         if (rcp) return rcp;
     }
     if (!ctx->have_fwd) return fail(ctx, DVS_E_STATE, "backward without a forward on this context");
-    if (!dL_dpix || !dL_daux || !grads) return fail(ctx, DVS_E_INVALID, "null dL_dpix / dL_daux / grads");
+    if (!dL_dpix || !grads) return fail(ctx, DVS_E_INVALID, "null dL_dpix / grads");
     const Cam& c = ctx->cam;
     const int64_t N = ctx->N, P = (int64_t)c.W * c.H;
     int rc;
@@ -490,24 +501,36 @@ int dvs_rast_backward_aux(dvs_rast_ctx* ctx, const dvs_params* params, const flo
                   (flags & DVS_FLAG_ABSGRAD) ? grads->mean2D_abs : nullptr, grads->mean2D};
     }
     CK(cudaEventRecord(ctx->ev[6], st));
-    // 1. the auxiliary loss: same reverse walk, colour triple (depth, 1, 0), zero background, third plane of dL zero
-    Cam c0 = c;
+    Cam c0 = c;  // the auxiliary passes composite over a zero background
     c0.bg[0] = c0.bg[1] = c0.bg[2] = 0.0f;
-    CK(launch_aux_records((int)N, ctx->rec, ctx->rec_aux, st));
-    CK(cudaMemcpyAsync(ctx->aux_img, dL_daux, 2 * (size_t)P * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    CK(cudaMemsetAsync(ctx->aux_img + 2 * (size_t)P, 0, (size_t)P * sizeof(float), st));
-    CK(launch_render_bwd(c0, ctx->tile_base, ctx->plist, ctx->rec_aux, ctx->final_T, ctx->n_contrib, ctx->aux_img,
-                         reinterpret_cast<float*>(ctx->sgrad), false, ctx->info, st));
-    // 2. its colour sums are dL/dz: out of the records, so that the colour pass finds slots 6-8 empty
-    CK(launch_aux_extract((int)N, ctx->sgrad, ctx->aux_dz, st));
+    if (dL_daux) {
+        // 1. depth / alpha loss: same reverse walk, colour triple (depth, 1, 0), third plane of dL zero
+        CK(launch_aux_records((int)N, ctx->rec, ctx->rec_aux, st));
+        CK(cudaMemcpyAsync(ctx->aux_img, dL_daux, 2 * (size_t)P * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemsetAsync(ctx->aux_img + 2 * (size_t)P, 0, (size_t)P * sizeof(float), st));
+        CK(launch_render_bwd(c0, ctx->tile_base, ctx->plist, ctx->rec_aux, ctx->final_T, ctx->n_contrib, ctx->aux_img,
+                             reinterpret_cast<float*>(ctx->sgrad), false, ctx->info, st));
+        // its colour sums are dL/dz: out of the records, so that the next pass finds slots 6-8 empty
+        CK(launch_aux_extract((int)N, ctx->sgrad, ctx->aux_dz, st));
+    }
+    if (dL_dnormal) {
+        // 2. normal-map loss: colour triple = view-space normal; its colour sums are dL/dn
+        CK(launch_aux_normal_records(c0, (int)N, prm, ctx->rec, ctx->rec_aux, st));
+        CK(launch_render_bwd(c0, ctx->tile_base, ctx->plist, ctx->rec_aux, ctx->final_T, ctx->n_contrib, dL_dnormal,
+                             reinterpret_cast<float*>(ctx->sgrad), false, ctx->info, st));
+        CK(launch_aux_extract3((int)N, ctx->sgrad, ctx->aux_dn, st));
+    }
     // 3. the colour loss adds its geometry sums on top, then the per-Gaussian backward consumes the total
     CK(launch_render_bwd(c, ctx->tile_base, ctx->plist, ctx->rec, ctx->final_T, ctx->n_contrib, dL_dpix,
                          reinterpret_cast<float*>(ctx->sgrad), (flags & DVS_FLAG_ABSGRAD) && g.mean2D_abs, ctx->info, st));
     CK(cudaEventRecord(ctx->ev[7], st));
     CK(launch_preprocess_bwd(c, (int)N, prm, ctx->aux, ctx->sgrad, g, flags, st));
-    // 4. dL/dmean += (row 2 of the view matrix) * dL/dz
-    const float row2[3] = {c.view[2], c.view[6], c.view[10]};
-    if (N > 0) CK(launch_aux_depth_grad((int)N, ctx->aux_dz, row2, g.means3D, st));
+    // 4. dL/dmean += (row 2 of the view matrix) * dL/dz ;  dL/dquat += d n / d quat ^T dL/dn
+    if (N > 0 && dL_daux) {
+        const float row2[3] = {c.view[2], c.view[6], c.view[10]};
+        CK(launch_aux_depth_grad((int)N, ctx->aux_dz, row2, g.means3D, st));
+    }
+    if (N > 0 && dL_dnormal) CK(launch_aux_normal_grad(c, (int)N, prm, ctx->aux_dn, g.quats, st));
     CK(cudaEventRecord(ctx->ev[8], st));
     ctx->ev_bwd = true;
     return DVS_OK;

@@ -44,6 +44,10 @@ cudaError_t launch_preprocess_bwd(const Cam& cam, int N, const Params& prm, cons
 cudaError_t launch_aux_records(int N, const float4* rec, float4* rec_aux, cudaStream_t st);
 cudaError_t launch_aux_extract(int N, float4* sgrad, float* dz, cudaStream_t st);
 cudaError_t launch_aux_depth_grad(int N, const float* dz, const float view_row2[3], float* dmeans, cudaStream_t st);
+// ... and the normal map: records with the colour replaced by the view-space normal; dL/dn per Gaussian; its chain to dL/dquat
+cudaError_t launch_aux_normal_records(const Cam& cam, int N, const Params& prm, const float4* rec, float4* rec_aux, cudaStream_t st);
+cudaError_t launch_aux_extract3(int N, float4* sgrad, float* dn, cudaStream_t st);
+cudaError_t launch_aux_normal_grad(const Cam& cam, int N, const Params& prm, const float* dn, float* dquats, cudaStream_t st);
 
 // debug helpers (parity tests): unpack records into the upstream-style arrays
 cudaError_t launch_unpack(int N, const float4* rec, int32_t* radii, uint32_t* tiles, float* depth, float* mean2D,

@@ -138,18 +138,23 @@ class Rasterizer:
                                                 C.byref(g), flags, C.c_void_p(st)))
         return grads
 
-    def forward_aux(self, out_aux: torch.Tensor | None = None) -> torch.Tensor:
-        """[2,H,W] = (depth, alpha) of the last forward (dvs_rast_forward_aux)."""
-        if out_aux is None:
-            out_aux = torch.empty(2, self._cam.height, self._cam.width, dtype=torch.float32, device=self.device)
+    def forward_aux(self, normals: bool = False):
+        """(depth, alpha) [2,H,W] of the last forward, and with normals=True also the normal map [3,H,W]
+        (dvs_rast_forward_aux)."""
+        H, W = self._cam.height, self._cam.width
+        out_aux = torch.empty(2, H, W, dtype=torch.float32, device=self.device)
+        out_n = torch.empty(3, H, W, dtype=torch.float32, device=self.device) if normals else None
         st = torch.cuda.current_stream(self.device).cuda_stream
-        self._check(self._lib.dvs_rast_forward_aux(self._h, out_aux.data_ptr(), C.c_void_p(st)))
-        return out_aux
+        self._check(self._lib.dvs_rast_forward_aux(self._h, C.byref(self._pstruct(self._params)), out_aux.data_ptr(),
+                                                   out_n.data_ptr() if normals else None, C.c_void_p(st)))
+        return (out_aux, out_n) if normals else out_aux
 
-    def backward_aux(self, dL_dpix: torch.Tensor, dL_daux: torch.Tensor, grads: GradBuffers, flags: int = 0):
-        """Backward of <image, dL_dpix> + <depth, dL_daux[0]> + <alpha, dL_daux[1]> (dvs_rast_backward_aux)."""
-        for t in (dL_dpix, dL_daux):
-            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+    def backward_aux(self, dL_dpix: torch.Tensor, dL_daux: torch.Tensor | None, grads: GradBuffers, flags: int = 0,
+                     dL_dnormal: torch.Tensor | None = None):
+        """Backward of <image, dL_dpix> + <depth, dL_daux[0]> + <alpha, dL_daux[1]> + <normal map, dL_dnormal>
+        (dvs_rast_backward_aux)."""
+        for t in (dL_dpix, dL_daux, dL_dnormal):
+            assert t is None or (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous())
         g = _cabi.DvsGrads()
         for n in PARAM_NAMES:
             t = getattr(grads, n)
@@ -157,7 +162,9 @@ class Rasterizer:
                 setattr(g, n, t.data_ptr())
         st = torch.cuda.current_stream(self.device).cuda_stream
         self._check(self._lib.dvs_rast_backward_aux(self._h, C.byref(self._pstruct(self._params)), dL_dpix.data_ptr(),
-                                                    dL_daux.data_ptr(), C.byref(g), flags, C.c_void_p(st)))
+                                                    dL_daux.data_ptr() if dL_daux is not None else None,
+                                                    dL_dnormal.data_ptr() if dL_dnormal is not None else None,
+                                                    C.byref(g), flags, C.c_void_p(st)))
         return grads
 
     def step_host(self, cam, params: dict, grads: GradBuffers, dL_dpix_host: torch.Tensor,

@@ -147,17 +147,22 @@ DVS_API int dvs_rast_backward(dvs_rast_ctx* ctx, const dvs_params* params, const
 
 /*
  * Auxiliary maps of the last forward (what depth- / normal-consistency losses and mesh extraction
- * read):  out_aux : float [2,H,W] = { depth = sum_k w_k z_k (view-space z, not normalised), alpha = sum_k w_k = 1 - T }.
- * Computed by linearity with the same compositing kernel on records whose colour is (z, 1, 0); no host synchronisation.
+ * read).  Either output may be NULL.
+ *   out_aux    : float [2,H,W] = { depth = sum_k w_k z_k (view-space z, not normalised), alpha = sum_k w_k = 1 - T }
+ *   out_normal : float [3,H,W] = sum_k w_k n_k, n_k = the shortest axis of Gaussian k's ellipsoid in view space, turned
+ *                towards the camera (needs `params`: the tensors of the forward)
+ * Computed by linearity with the same compositing kernel on records whose colour is (z, 1, 0) resp. n_k, over a zero
+ * background; no host synchronisation.
  */
-DVS_API int dvs_rast_forward_aux(dvs_rast_ctx* ctx, float* out_aux, void* stream);
+DVS_API int dvs_rast_forward_aux(dvs_rast_ctx* ctx, const dvs_params* params, float* out_aux, float* out_normal, void* stream);
 
 /*
- * Backward of  <image, dL_dpix> + <depth, dL_daux[0]> + <alpha, dL_daux[1]>  (use instead of dvs_rast_backward when the
- * loss also reads the auxiliary maps).  dL_dpix : float [3,H,W], dL_daux : float [2,H,W]; flags as dvs_rast_backward.
+ * Backward of  <image, dL_dpix> + <depth, dL_daux[0]> + <alpha, dL_daux[1]> + <normal map, dL_dnormal>  (use instead of
+ * dvs_rast_backward when the loss also reads the auxiliary maps).  dL_dpix : float [3,H,W]; dL_daux : float [2,H,W] or
+ * NULL; dL_dnormal : float [3,H,W] or NULL; flags as dvs_rast_backward.
  */
 DVS_API int dvs_rast_backward_aux(dvs_rast_ctx* ctx, const dvs_params* params, const float* dL_dpix, const float* dL_daux,
-                                  const dvs_grads* grads, uint32_t flags, void* stream);
+                                  const float* dL_dnormal, const dvs_grads* grads, uint32_t flags, void* stream);
 
 /*
  * Host-buffer step (the end-to-end path a trainer without device-resident images uses):

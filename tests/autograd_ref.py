@@ -99,13 +99,19 @@ def project(cam, means, log_scales, quats, logit, sh0, shN, sh_degree, activated
     coeffs = torch.cat([sh0[:, None, :], shN[:, :K - 1, :]], 1) if K > 1 else sh0[:, None, :]
     col = (bas[:, :, None] * coeffs).sum(1) + 0.5
     rgb = torch.clamp(col, min=0.0)
+    # F4 normal: the shortest axis of the ellipsoid, in view space, turned towards the camera (piecewise-constant choices)
+    with torch.no_grad():
+        jmin = s.argmin(1)
+    n_v = R[torch.arange(N), :, jmin] @ V[:3, :3].T
+    with torch.no_grad():
+        sign = torch.where((n_v * t).sum(1) > 0, -torch.ones(N, dtype=torch.float64), torch.ones(N, dtype=torch.float64))
     return dict(t=t, depth=tz, mean2D=mean2D, conic=conic, opacity=o, rgb=rgb, radius=radius, det=det,
-                cov2D=torch.stack([a, b, c], 1), Sigma=Sigma)
+                cov2D=torch.stack([a, b, c], 1), Sigma=Sigma, normal=n_v * sign[:, None])
 
 
 def composite(cam, proj, ranges, point_list, visible, aux=None):
-    """Tile compositing (Appendix B.3) in float64 using the given sorted lists.  `aux`: a [2,H,W] tensor that receives the
-    auxiliary maps depth = sum_k w_k z_k and alpha = sum_k w_k (row F4)."""
+    """Tile compositing (Appendix B.3) in float64 using the given sorted lists.  `aux`: a [2,H,W] or [5,H,W] tensor that
+    receives the auxiliary maps depth = sum_k w_k z_k, alpha = sum_k w_k and (5 channels) normal = sum_k w_k n_k (row F4)."""
     W, H = cam.width, cam.height
     gx = (W + 15) // 16
     bg = torch.tensor(np.asarray(cam.bg, np.float64))
@@ -148,8 +154,11 @@ def composite(cam, proj, ranges, point_list, visible, aux=None):
         ny, nx = len(ys), len(xs)
         img[:, y0:y0 + ny, x0:x0 + nx] = out.T.reshape(3, ny, nx)
         if aux is not None:
-            extra = wgt @ torch.stack([proj["depth"][ids], torch.ones(len(ids), dtype=torch.float64)], 1)  # [P,2]
-            aux[:, y0:y0 + ny, x0:x0 + nx] = extra.T.reshape(2, ny, nx)
+            feats = torch.stack([proj["depth"][ids], torch.ones(len(ids), dtype=torch.float64)], 1)
+            if aux.shape[0] == 5:
+                feats = torch.cat([feats, proj["normal"][ids]], 1)
+            extra = wgt @ feats  # [P, 2 or 5]
+            aux[:, y0:y0 + ny, x0:x0 + nx] = extra.T.reshape(aux.shape[0], ny, nx)
         with torch.no_grad():
             kk = keep.numpy()
             last = np.where(kk.any(1), kk.shape[1] - np.argmax(kk[:, ::-1], 1), 0)
@@ -161,13 +170,14 @@ def composite(cam, proj, ranges, point_list, visible, aux=None):
 def render_and_grad(cam, scene_arrays, sh_degree, ranges, point_list, radii, dL_dpix, activated=False, antialias=False,
                     dL_daux=None):
     """Returns (image float64 numpy, dict of gradient numpy arrays w.r.t. the stored parameters).  With dL_daux [2,H,W]
-    the loss also has <depth, dL_daux[0]> + <alpha, dL_daux[1]>; the maps are returned under proj["aux"]."""
+    (or [5,H,W]) the loss also has <depth, dL_daux[0]> + <alpha, dL_daux[1]> (+ <normal, dL_daux[2:5]>); the maps are
+    returned under proj["aux"]."""
     names = ["means3D", "scales", "quats", "opac", "sh0", "shN"]
     ts = {k: torch.tensor(np.asarray(v, np.float64), requires_grad=True) for k, v in zip(names, scene_arrays)}
     proj = project(cam, ts["means3D"], ts["scales"], ts["quats"], ts["opac"].reshape(-1), ts["sh0"],
                    ts["shN"], sh_degree, activated, antialias)
     visible = np.asarray(radii) > 0
-    aux = torch.zeros(2, cam.height, cam.width, dtype=torch.float64) if dL_daux is not None else None
+    aux = torch.zeros(np.asarray(dL_daux).shape[0], cam.height, cam.width, dtype=torch.float64) if dL_daux is not None else None
     img, n_contrib, final_T = composite(cam, proj, np.asarray(ranges), point_list, visible, aux)
     loss = (img * torch.tensor(np.asarray(dL_dpix, np.float64))).sum()
     if aux is not None:

@@ -7,6 +7,8 @@ backward for that triple — its geometry part (dL/dmean2D, dL/dconic, dL/dopaci
 kernels; tests/test_aux_outputs.py checks this restatement against float64 autograd and the CUDA path against it."""
 import copy
 import ctypes as C
+import os
+import subprocess
 
 import numpy as np
 
@@ -21,6 +23,34 @@ def _cam_bg0(cam):
     c = copy.copy(cam)
     c.bg[:] = [0.0, 0.0, 0.0]
     return c
+
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def normal_ops():
+    """Host build of divshot_b200/csrc/aux_normal_ops.h (the arithmetic the CUDA kernels call)."""
+    src = os.path.join(ROOT, "tests", "native", "aux_normal_host.cpp")
+    hdr = os.path.join(ROOT, "divshot_b200", "csrc", "aux_normal_ops.h")
+    out = os.path.join(ROOT, "build", "test_aux_normal_host.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wextra", "-I", os.path.dirname(hdr), src, "-o", out])
+    L = C.CDLL(out)
+    L.t_normals_forward.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_longlong] + [C.c_void_p] * 3
+    L.t_normals_backward.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_longlong] + [C.c_void_p] * 2
+    return L
+
+
+def normals(cam, means3D, scales, quats, activated=False):
+    """-> (n_v [N,3], axis [N], flip [N]): view-space normal of every Gaussian and the decisions behind it."""
+    f32 = lambda a: np.ascontiguousarray(np.asarray(a, np.float32))  # noqa: E731
+    means3D, scales, quats = f32(means3D), f32(scales), f32(quats)
+    N = means3D.shape[0]
+    view = np.array(list(cam.view), np.float32)
+    n_v = np.zeros((N, 3), np.float32); axis = np.zeros(N, np.int32); flip = np.zeros(N, np.float32)
+    normal_ops().t_normals_forward(_p(quats), _p(scales), _p(means3D), _p(view), int(activated), N, _p(n_v), _p(axis), _p(flip))
+    return n_v, axis, flip
 
 
 def aux_colours(fwd):
@@ -47,8 +77,25 @@ def forward_aux(cam, fwd):
     return image[:2].copy()
 
 
-def backward_with_aux(cam, fwd, means3D, scales, quats, opacities, sh0, shN, dL_dpix, dL_daux):
-    """Gradients of <image, dL_dpix> + <depth, dL_daux[0]> + <alpha, dL_daux[1]> w.r.t. the stored parameters."""
+def forward_normals(cam, fwd, means3D, scales, quats, activated=False):
+    """-> [3,H,W] float32: normal map = sum_k w_k n_k from the lists of an oracle forward."""
+    L = orc.lib()
+    W, H = cam.width, cam.height
+    image = np.zeros((3, H, W), np.float32); final_T = np.zeros(H * W, np.float32)
+    n_contrib = np.zeros(H * W, np.uint32); fragile = np.zeros(H * W, np.uint8)
+    n_v, _, _ = normals(cam, means3D, scales, quats, activated)
+    n_v[fwd.radii <= 0] = 0
+    plist = fwd.point_list if fwd.D else np.zeros(1, np.uint32)
+    c0 = _cam_bg0(cam)
+    L.orc_render_fwd(C.byref(c0), _p(fwd.ranges), _p(plist), _p(fwd.mean2D), _p(fwd.conic_opacity), _p(n_v), _p(image),
+                     _p(final_T), _p(n_contrib), _p(fragile), C.c_int32(1))
+    return image
+
+
+def backward_with_aux(cam, fwd, means3D, scales, quats, opacities, sh0, shN, dL_dpix, dL_daux, dL_dnormal=None,
+                      activated=False):
+    """Gradients of <image, dL_dpix> + <depth, dL_daux[0]> + <alpha, dL_daux[1]> (+ <normal map, dL_dnormal>) w.r.t. the
+    stored parameters."""
     L = orc.lib()
     f32 = lambda a: np.ascontiguousarray(np.asarray(a, np.float32))  # noqa: E731
     means3D, scales, quats, sh0 = f32(means3D), f32(scales), f32(quats), f32(sh0)
@@ -71,6 +118,16 @@ def backward_with_aux(cam, fwd, means3D, scales, quats, opacities, sh0, shN, dL_
     daux3 = np.zeros((3, H, W), np.float32); daux3[:2] = np.asarray(dL_daux, np.float32).reshape(2, H, W)
     m2b, conb, opb, colb = render_bwd(_cam_bg0(cam), aux_colours(fwd), daux3)
     g_m2, g_con, g_op = m2a + m2b, cona + conb, opa + opb
+    dq_normal = None
+    if dL_dnormal is not None:  # third pass: colour = view-space normal; its colour sums are dL/dn_k
+        n_v, axis, flip = normals(cam, means3D, scales, quats, activated)
+        n_v[fwd.radii <= 0] = 0
+        m2c, conc, opc, colc = render_bwd(_cam_bg0(cam), n_v, np.asarray(dL_dnormal, np.float32).reshape(3, H, W))
+        g_m2, g_con, g_op = g_m2 + m2c, g_con + conc, g_op + opc
+        dn = f32(colc * (fwd.radii > 0)[:, None])
+        dq_normal = np.zeros((N, 4), np.float32)
+        view = np.array(list(cam.view), np.float32)
+        normal_ops().t_normals_backward(_p(quats), _p(axis), _p(flip), _p(view), int(activated), N, _p(dn), _p(dq_normal))
     d_means = np.empty((N, 3), np.float32); d_scales = np.empty((N, 3), np.float32); d_quats = np.empty((N, 4), np.float32)
     d_opac = np.empty(N, np.float32); d_sh0 = np.empty((N, 3), np.float32); d_shN = np.zeros((N, max(KR, 0), 3), np.float32)
     L.orc_preprocess_bwd(C.byref(cam), C.c_int32(N), _p(means3D), _p(scales), _p(quats), _p(opacities), _p(sh0), _p(shN),
@@ -79,4 +136,6 @@ def backward_with_aux(cam, fwd, means3D, scales, quats, opacities, sh0, shN, dL_
     dz = colb[:, 0] * (fwd.radii > 0)
     row2 = np.array([cam.view[4 * c + 2] for c in range(3)], np.float32)  # d z_view / d mean
     d_means = d_means + dz[:, None] * row2[None, :]
+    if dq_normal is not None:
+        d_quats = d_quats + dq_normal
     return dict(means3D=d_means, scales=d_scales, quats=d_quats, opac=d_opac, sh0=d_sh0, shN=d_shN, dz=dz)

@@ -46,6 +46,37 @@ def test_oracle_restatement_matches_float64_autograd(deg, seed, bg):
     assert np.abs(plain.dL_dmeans3D - b["means3D"]).max() > 1e-2 * np.abs(b["means3D"]).max()
 
 
+@pytest.mark.parametrize("deg,seed,normq", [(1, 21, False), (2, 22, True)])
+def test_normal_map_restatement_matches_float64_autograd(deg, seed, normq):
+    sc = _scene(seed, deg)
+    if normq:
+        sc.quats /= np.linalg.norm(sc.quats, axis=1, keepdims=True)
+    else:
+        sc.quats *= np.random.default_rng(seed).uniform(0.3, 3.0, (sc.N, 1)).astype(np.float32)  # the kernel normalises
+    cam = sc.cameras[0]
+    oc = orc_cam(cam, deg)
+    arrays = scene_arrays(sc)
+    fwd = orc.forward(oc, *arrays, threads=1)
+    rng = np.random.default_rng(seed)
+    dL_d5 = rng.normal(size=(5, cam.height, cam.width)).astype(np.float32)
+    dL_d5[0] *= 0.2
+    img, g, proj, _, _ = ar.render_and_grad(cam, arrays, deg, fwd.ranges, fwd.point_list, fwd.radii, sc.dL_dpix[0], dL_daux=dL_d5)
+    nmap = aux_ref.forward_normals(oc, fwd, *arrays[:3])
+    assert_close(nmap, proj["aux"][2:5], 1e-4, "normal map")
+    n_v, axis, flip = aux_ref.normals(oc, *arrays[:3])
+    vis = fwd.radii > 0
+    assert np.allclose(np.linalg.norm(n_v[vis], axis=1), 1.0, atol=1e-5) and set(np.unique(axis)) <= {0, 1, 2}
+    assert np.allclose(n_v[vis], proj["normal"].detach().numpy()[vis], atol=2e-6)
+    b = aux_ref.backward_with_aux(oc, fwd, *arrays, sc.dL_dpix[0], dL_d5[:2], dL_d5[2:5])
+    assert_close_robust(b["quats"], g["quats"], 1e-4, "dL_dquats", frac=0.995)
+    assert_close_robust(b["means3D"], g["means3D"], 1e-4, "dL_dmeans3D", frac=0.995)
+    assert_close_robust(b["scales"], g["scales"], 1e-4, "dL_dscales", frac=0.995)
+    assert_close_robust(b["opac"], g["opac"].reshape(-1), 1e-4, "dL_dopacity", frac=0.995)
+    # the normal term really reaches the rotations
+    plain = aux_ref.backward_with_aux(oc, fwd, *arrays, sc.dL_dpix[0], dL_d5[:2])
+    assert np.abs(plain["quats"] - b["quats"]).max() > 1e-2 * np.abs(b["quats"]).max()
+
+
 @pytest.mark.gpu_staged
 @pytest.mark.parametrize("deg,seed,bg,N,W,H", [(1, 11, (0, 0, 0), 1200, 64, 48), (3, 12, (0.3, 0.1, 0.7), 4000, 128, 96),
                                                 (2, 13, (1, 1, 1), 30000, 320, 200)])
@@ -62,21 +93,25 @@ def test_cuda_aux_outputs_match_the_oracle_restatement(deg, seed, bg, N, W, H):
     rng = np.random.default_rng(seed)
     dL_daux = rng.normal(size=(2, H, W)).astype(np.float32)
     dL_daux[0] *= 0.2
+    dL_dn = rng.normal(size=(3, H, W)).astype(np.float32)
     r = Rasterizer(0)
     try:
         params = scene_to_device(sc, r.device)
         dcam = _cabi.make_camera(cam, deg)
         img, radii = r.forward(dcam, params)
-        aux = r.forward_aux().cpu().numpy()
+        aux, nmap = r.forward_aux(normals=True)
+        aux, nmap = aux.cpu().numpy(), nmap.cpu().numpy()
         ref = aux_ref.forward_aux(oc, fwd)
         assert_close(aux[0], ref[0], 1e-4, "depth map")
         assert_close(aux[1], ref[1], 1e-4, "alpha map")
+        assert_close(nmap, aux_ref.forward_normals(oc, fwd, *arrays[:3]), 1e-4, "normal map")
+        assert np.array_equal(r.forward_aux().cpu().numpy(), aux)  # depth / alpha alone, repeatable
         g = GradBuffers.allocate(sc.N, sc.shN.shape[1], r.device)
         g.flat.fill_(float("nan"))
         dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(r.device)  # noqa: E731
-        r.backward_aux(dev(sc.dL_dpix[0]), dev(dL_daux), g)
+        r.backward_aux(dev(sc.dL_dpix[0]), dev(dL_daux), g, dL_dnormal=dev(dL_dn))
         torch.cuda.synchronize()
-        b = aux_ref.backward_with_aux(oc, fwd, *arrays, sc.dL_dpix[0], dL_daux)
+        b = aux_ref.backward_with_aux(oc, fwd, *arrays, sc.dL_dpix[0], dL_daux, dL_dn)
         assert_close_robust(g.means3D.cpu().numpy(), b["means3D"], 1e-4, "dL_dmeans3D", frac=0.995)
         assert_close_robust(g.scales.cpu().numpy(), b["scales"], 1e-4, "dL_dscales", frac=0.995)
         assert_close_robust(g.quats.cpu().numpy(), b["quats"], 1e-4, "dL_dquats", frac=0.995)
@@ -91,10 +126,16 @@ def test_cuda_aux_outputs_match_the_oracle_restatement(deg, seed, bg, N, W, H):
         plain = orc.backward(oc, fwd, *arrays, sc.dL_dpix[0])
         assert_close_robust(g2.means3D.cpu().numpy(), plain.dL_dmeans3D, 1e-4, "plain dL_dmeans3D", frac=0.995)
         assert_close(g2.sh0.cpu().numpy(), plain.dL_dsh0, 2e-4, "plain dL_dsh0")
-        # zero auxiliary gradient == plain backward
+        # zero auxiliary gradients == plain backward; each auxiliary loss can be given alone
         g3 = GradBuffers.allocate(sc.N, sc.shN.shape[1], r.device)
-        r.backward_aux(dev(sc.dL_dpix[0]), torch.zeros(2, H, W, device=r.device), g3)
+        r.backward_aux(dev(sc.dL_dpix[0]), torch.zeros(2, H, W, device=r.device), g3, dL_dnormal=torch.zeros(3, H, W, device=r.device))
         torch.cuda.synchronize()
         assert_close_robust(g3.means3D.cpu().numpy(), g2.means3D.cpu().numpy(), 1e-5, "zero-aux means", frac=0.999)
+        assert_close_robust(g3.quats.cpu().numpy(), g2.quats.cpu().numpy(), 1e-5, "zero-aux quats", frac=0.999)
+        g4 = GradBuffers.allocate(sc.N, sc.shN.shape[1], r.device)
+        r.backward_aux(dev(sc.dL_dpix[0]), None, g4, dL_dnormal=dev(dL_dn))
+        torch.cuda.synchronize()
+        b4 = aux_ref.backward_with_aux(oc, fwd, *arrays, sc.dL_dpix[0], np.zeros((2, H, W), np.float32), dL_dn)
+        assert_close_robust(g4.quats.cpu().numpy(), b4["quats"], 1e-4, "normal-only dL_dquats", frac=0.995)
     finally:
         r.close()
