@@ -30,6 +30,7 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <mutex>
 #include <random>
 #include <sstream>
 #include <stdexcept>
@@ -299,6 +300,10 @@ struct GaussianTrainerImpl {
     bool refine_enabled = false;   // the schedule reaches the refinement window (set before upload)
     bool resync_next = false;      // N changed: the next forward re-sizes the binning arena synchronously
     dvs_densify::RefineReport last_report;
+    // The editor drives trainStep from a worker thread and reads the model from its UI thread (editor.cpp:1559-1574 vs
+    // :1603-1620): every public entry that touches the device state takes this lock, so a reader never sees the model
+    // half-way through a refinement (N and the rows would disagree).  Recursive: saveGaussianModel calls the getters.
+    std::recursive_mutex mu;
     // editor surface: the initial model (resetGaussian), the initialisation points, time spent training
     std::vector<float> init[6];  // means, scales, quats, opac, sh0, shN as first uploaded
     std::vector<GsPoint3D> points3d;
@@ -451,6 +456,7 @@ static void parse_kv(const std::string& s, const char* key, long& out) {
 }
 
 bool GaussianTrainerScene::loadTrainData(const std::string& path) {
+    std::lock_guard<std::recursive_mutex> lock(impl_->mu);
     auto& I = *impl_;
     status_ = TrainingStatus::Loading_Data;
     try {
@@ -607,6 +613,7 @@ bool GaussianTrainerScene::loadTrainData(const std::string& path) {
 }
 
 void GaussianTrainerScene::trainSetup() {
+    std::lock_guard<std::recursive_mutex> lock(impl_->mu);
     auto& I = *impl_;
     int W = 0, H = 0;
     for (auto& v : I.views) { W = std::max(W, v.cam.width); H = std::max(H, v.cam.height); }
@@ -615,6 +622,7 @@ void GaussianTrainerScene::trainSetup() {
 }
 
 void GaussianTrainerScene::trainStep() {
+    std::lock_guard<std::recursive_mutex> lock(impl_->mu);
     auto& I = *impl_;
     if (I.views.empty() || I.N == 0) throw std::runtime_error("gstrain: train_step without data");
     {   // time spent training: gaps between consecutive steps, pauses (> 2 s) dropped
@@ -734,6 +742,7 @@ static bool write_model(const std::string& path, int64_t N, const float* pos, co
 }
 
 void GaussianTrainerScene::saveGaussianModel() {
+    std::lock_guard<std::recursive_mutex> lock(impl_->mu);
     auto& I = *impl_;
     if (config_.modelPath.empty() || I.N == 0) return;
     const auto pos = getGaussianPositionCpu(), sh0 = getGaussianSH0Cpu(), shn = getGaussianSHNCpu();
@@ -754,6 +763,7 @@ static size_t vp_offset_bbox(int64_t cap) { return vp_offset_sh(cap) + (size_t)c
 static size_t vp_bytes(int64_t cap) { return vp_offset_bbox(cap) + 32; }
 
 void GaussianTrainerScene::requestViewerPack() {
+    std::lock_guard<std::recursive_mutex> lock(impl_->mu);
     auto& I = *impl_;
     if (I.N <= 0) return;
     if (!I.vp_stream) {
@@ -797,6 +807,7 @@ void GaussianTrainerScene::requestViewerPack() {
 }
 
 bool GaussianTrainerScene::acquireViewerPack(GaussianViewerPack& out, bool wait) {
+    std::lock_guard<std::recursive_mutex> lock(impl_->mu);
     auto& I = *impl_;
     if (I.vp_last < 0) return false;
     int slot = I.vp_last;
@@ -816,13 +827,34 @@ bool GaussianTrainerScene::acquireViewerPack(GaussianViewerPack& out, bool wait)
     return true;
 }
 
-int64_t GaussianTrainerScene::getNumGaussians() const { return impl_->N; }
-std::vector<float> GaussianTrainerScene::getGaussianPositionCpu() const { return impl_->download(impl_->params.means(), 3 * impl_->N); }
-std::vector<float> GaussianTrainerScene::getGaussianSH0Cpu() const { return impl_->download(impl_->params.sh0(), 3 * impl_->N); }
-std::vector<float> GaussianTrainerScene::getGaussianSHNCpu() const { return impl_->download(impl_->params.shN(), (size_t)45 * impl_->N); }
-std::vector<float> GaussianTrainerScene::getGaussianOpcaitiesCpu() const { return impl_->download(impl_->params.opac(), impl_->N); }
-std::vector<float> GaussianTrainerScene::getGaussianScalingsCpu() const { return impl_->download(impl_->params.scales(), 3 * impl_->N); }
-std::vector<float> GaussianTrainerScene::getGaussianRotationsCpu() const { return impl_->download(impl_->params.quats(), 4 * impl_->N); }
+int64_t GaussianTrainerScene::getNumGaussians() const {
+    std::lock_guard<std::recursive_mutex> lock(impl_->mu);
+    return impl_->N;
+}
+std::vector<float> GaussianTrainerScene::getGaussianPositionCpu() const {
+    std::lock_guard<std::recursive_mutex> lock(impl_->mu);
+    return impl_->download(impl_->params.means(), 3 * impl_->N);
+}
+std::vector<float> GaussianTrainerScene::getGaussianSH0Cpu() const {
+    std::lock_guard<std::recursive_mutex> lock(impl_->mu);
+    return impl_->download(impl_->params.sh0(), 3 * impl_->N);
+}
+std::vector<float> GaussianTrainerScene::getGaussianSHNCpu() const {
+    std::lock_guard<std::recursive_mutex> lock(impl_->mu);
+    return impl_->download(impl_->params.shN(), (size_t)45 * impl_->N);
+}
+std::vector<float> GaussianTrainerScene::getGaussianOpcaitiesCpu() const {
+    std::lock_guard<std::recursive_mutex> lock(impl_->mu);
+    return impl_->download(impl_->params.opac(), impl_->N);
+}
+std::vector<float> GaussianTrainerScene::getGaussianScalingsCpu() const {
+    std::lock_guard<std::recursive_mutex> lock(impl_->mu);
+    return impl_->download(impl_->params.scales(), 3 * impl_->N);
+}
+std::vector<float> GaussianTrainerScene::getGaussianRotationsCpu() const {
+    std::lock_guard<std::recursive_mutex> lock(impl_->mu);
+    return impl_->download(impl_->params.quats(), 4 * impl_->N);
+}
 int GaussianTrainerScene::getNumCameras() const { return (int)impl_->views.size(); }
 std::array<float, 16> GaussianTrainerScene::getCameraProjectionFlat(int i) const {
     std::array<float, 16> a; std::memcpy(a.data(), impl_->views.at(i).P, sizeof(float) * 16); return a;
@@ -855,6 +887,7 @@ void GaussianTrainerScene::getCameraRotationWXYZ(int i, float q[4]) const {
 
 // ---- the rest of the editor surface
 void GaussianTrainerScene::resetGaussian() {
+    std::lock_guard<std::recursive_mutex> lock(impl_->mu);
     auto& I = *impl_;
     if (I.init[3].empty()) return;
     ck(cudaStreamSynchronize(I.stream), "sync");
@@ -868,6 +901,7 @@ void GaussianTrainerScene::resetGaussian() {
     status_ = TrainingStatus::Preprocess_Done;
 }
 void GaussianTrainerScene::setDensifyStrategy(int strategy) {
+    std::lock_guard<std::recursive_mutex> lock(impl_->mu);
     auto& I = *impl_;
     config_.densifyStrategy = std::min(2, std::max(0, strategy));
     if (I.d_accum) {  // the ADC statistics restart with the strategy
@@ -903,6 +937,7 @@ float GaussianTrainerScene::getEstimateTrainingTime() const {
 }
 void GaussianTrainerScene::updateTensorFromHost(const float* pos, const float* rot, const float* scale, const float* opacity,
                                                 const float* sh0, const float* shn, int64_t n) {
+    std::lock_guard<std::recursive_mutex> lock(impl_->mu);
     auto& I = *impl_;
     if (n <= 0 || !pos || !rot || !scale || !opacity || !sh0 || !shn) throw std::runtime_error("gstrain: updateTensorFromHost with an empty model");
     ck(cudaStreamSynchronize(I.stream), "sync");
@@ -919,6 +954,7 @@ void GaussianTrainerScene::updateTensorFromHost(const float* pos, const float* r
 }
 const std::vector<GsPoint3D>& GaussianTrainerScene::getPoints3D(int) const { return impl_->points3d; }
 GsImageView GaussianTrainerScene::getSplatImageView(int id) {
+    std::lock_guard<std::recursive_mutex> lock(impl_->mu);
     auto& I = *impl_;
     View& v = I.views.at((size_t)id);
     const size_t P = (size_t)v.cam.width * v.cam.height;
