@@ -1,6 +1,7 @@
 """Runs the STAGED GPU tier (marker `gpu_staged`: tests of code written while this round had no GPU minutes left —
-the refinement step, the viewer hand-off) once, at the very end of the `-m gpu` run, in a SUBPROCESS:
-  * a crash or a sticky CUDA error in unproven code cannot take the proven tests down with it (they have all run);
+the refinement step, the viewer hand-off, the editor surface, the auxiliary maps) once, near the end of the `-m gpu` run, in a
+SUBPROCESS:
+  * a crash or a sticky CUDA error in unproven code cannot take the proven tests down with it (separate process);
   * the outcome is visible either way — this test passes when every staged test passes, and reports `xfailed` with the
     failing test names otherwise (nothing staged is claimed as GPU-verified in DESIGN.md until it passes here)."""
 import os
