@@ -184,8 +184,9 @@ def main():
     ap.add_argument("--workload", default=None, help="override: c2|c3|c5 (parity/bench exploration only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-rows", action="store_true", help="skip the sub-process measurement of the other section-8 rows")
-    ap.add_argument("--allreduce", default="auto", choices=["auto", "nvls", "nccl"],
-                    help="gradient all-reduce: NVSwitch in-switch reduction over symmetric memory, or plain NCCL")
+    ap.add_argument("--allreduce", default="auto", choices=["auto", "nvls", "nccl", "factored"],
+                    help="gradient exchange: NVSwitch in-switch reduction over symmetric memory, plain NCCL, or (STAGED, not "
+                         "yet run on GPUs) the factored exchange: all-gather dL/dsh0, all-reduce 56 B/Gaussian, form dL/dshN locally")
     args = ap.parse_args()
     global WORKLOAD
     if args.workload:
@@ -223,8 +224,19 @@ def main():
     dl_host = torch.from_numpy(sc.dL_dpix[rank % len(sc.dL_dpix)]).pin_memory()
     dl = dl_host.to(dev)
     img_host = torch.empty(3, H, W, dtype=torch.float32).pin_memory()
-    reducer = GradientReducer(GradBuffers.numel_for(N, K - 1), dev, backend=args.allreduce)
+    factored = args.allreduce == "factored"
+    reducer = GradientReducer(GradBuffers.numel_for(N, K - 1), dev, backend="nccl" if factored else args.allreduce)
     grads = GradBuffers.allocate(N, K - 1, dev, flat=reducer.flat)
+    exchange = reducer.all_reduce
+    if factored and world > 1:
+        from divshot_b200.dp import FactoredGradientExchange
+        fx = FactoredGradientExchange(grads)
+        campos = torch.tensor(np.asarray(sc.cameras[rank % len(sc.cameras)].campos, np.float32))
+        fx.set_cameras(campos)
+        exchange = lambda: fx.exchange(params["means3D"], campos, deg)  # noqa: E731
+        reducer.backend = "factored"
+        reducer.note = (f"all-gather dL/dsh0 + all-reduce 56 B/Gaussian + local SH accumulation: "
+                        f"{fx.wire_bytes_per_gaussian(world):.0f} B/Gaussian received instead of {fx.plain_wire_bytes_per_gaussian(world):.0f}")
     rast = Rasterizer(local)
     rast.reserve(N, W, H, 0)
     img = torch.empty(3, H, W, device=dev)
@@ -239,7 +251,7 @@ def main():
         rast.forward(cam, params, img, radii, defer_check=True)
         rast.backward(dl, grads)
         if world > 1:
-            reducer.all_reduce()
+            exchange()
 
     cam_defer = _cabi.DvsCamera.from_buffer_copy(cam)
     cam_defer.flags |= _cabi.FLAG_DEFER_CHECK
@@ -247,7 +259,7 @@ def main():
     def step_e2e():
         rast.step_host(cam_defer, params, grads, dl_host, img_host)
         if world > 1:
-            reducer.all_reduce()
+            exchange()
 
     def timed(fn, steps, warmup, sample_clocks=False):
         for _ in range(warmup):
@@ -294,7 +306,7 @@ def main():
     clocks = sampler_all.stop()
     ms_ar = None
     if world > 1:  # the collective alone (device time, max over ranks), for the scaling breakdown
-        ms_ar, _ = timed(lambda: reducer.all_reduce(), args.steps, warm)
+        ms_ar, _ = timed(lambda: exchange(), args.steps, warm)
         ms_ar /= args.steps
 
     ms_step = ms_total / args.steps

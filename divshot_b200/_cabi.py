@@ -26,7 +26,7 @@ EXPORTS = [
     "dvs_rast_forward", "dvs_rast_backward", "dvs_rast_step_host", "dvs_rast_get_stats", "dvs_rast_debug_read",
     "dvs_rast_stage_ms", "dvs_rast_stage_name", "dvs_rast_forward_aux", "dvs_rast_backward_aux",
 ]
-COLL_EXPORTS = ["dvs_coll_allreduce_nvls"]
+COLL_EXPORTS = ["dvs_coll_allreduce_nvls", "dvs_coll_sh_grad_from_dsh0"]
 
 
 class DvsCamera(C.Structure):
@@ -96,6 +96,9 @@ def load():
     L.dvs_rast_stage_name.restype = C.c_char_p
     L.dvs_coll_allreduce_nvls.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_void_p]
     L.dvs_coll_allreduce_nvls.restype = C.c_int
+    L.dvs_coll_sh_grad_from_dsh0.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                             C.c_void_p]
+    L.dvs_coll_sh_grad_from_dsh0.restype = C.c_int
     _lib = L
     return L
 

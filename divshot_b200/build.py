@@ -31,6 +31,7 @@ CU_SOURCES = {
     "api.cu": [],
     "aux_outputs.cu": [],
     "collective.cu": [],
+    "sh_exchange.cu": [],
 }
 
 

@@ -106,3 +106,75 @@ class GradientReducer:
         else:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
         return self.flat
+
+
+class FactoredGradientExchange:
+    """The gradient exchange with the SH tensor factored out (SURVEY.md §8 e; csrc/sh_grad_ops.h explains the identity).
+
+    76 % of the dense gradient arena is dL/dshN (180 of 236 B per Gaussian at SH degree 3), yet per view it is the outer
+    product B(dir) (x) dL/dcolour and the band-0 gradient already carries dL/dcolour.  So instead of all-reducing the whole
+    arena, every rank
+      1. all-gathers each view's dL/dsh0 (12 B per Gaussian and view) and camera centre,
+      2. all-reduces everything except shN (quats | means, scales, sh0, opacities: 56 B per Gaussian, two contiguous ranges),
+      3. forms sum_v B(dir_v) (x) dL/dsh0_v / SH_C0 locally (dvs_coll_sh_grad_from_dsh0) into grads.shN.
+    Bytes received per GPU and Gaussian: (W-1) * 12 + 2 (W-1)/W * 56 instead of 2 (W-1)/W * 236 (8 ranks: 182 vs 413).
+    Valid with ONE view per rank and step (each rank's dL/dsh0 must belong to a single camera).
+    `accumulate(means, campos_all, dsh0_all, deg, out_shN)` defaults to the CUDA kernel; the CPU tests inject a stand-in.
+    """
+
+    def __init__(self, grads, group=None, accumulate=None):
+        self.g, self.group = grads, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        flat = grads.flat
+        N = grads.opacities.shape[0]
+        self.N = N
+        off = lambda t: (t.data_ptr() - flat.data_ptr()) // 4  # noqa: E731
+        # arena order: quats | shN | means3D | scales | sh0 | opacities (rasterizer.GradBuffers.allocate)
+        assert off(grads.quats) < off(grads.shN) < off(grads.means3D) < off(grads.scales) < off(grads.sh0) < off(grads.opacities)
+        self.range_a = flat[off(grads.quats):off(grads.quats) + 4 * N]
+        self.range_b = flat[off(grads.means3D):off(grads.opacities) + N]
+        self.dsh0_all = torch.zeros(self.world, N, 3, dtype=torch.float32, device=flat.device)
+        self.campos_all = torch.zeros(self.world, 3, dtype=torch.float32, device=flat.device)
+        self._accumulate = accumulate or self._accumulate_cuda
+
+    def _accumulate_cuda(self, means, campos_all, dsh0_all, deg, out_shN):
+        if not out_shN.is_cuda:
+            raise RuntimeError("FactoredGradientExchange: the SH accumulation runs on the GPU only (no CPU path)")
+        import ctypes as C
+
+        from . import _cabi
+        cam_host = campos_all.cpu().contiguous()  # V x 3 floats; the kernel takes them by value
+        st = torch.cuda.current_stream(out_shN.device).cuda_stream
+        rc = _cabi.load().dvs_coll_sh_grad_from_dsh0(means.data_ptr(), cam_host.data_ptr(), dsh0_all.data_ptr(), self.N,
+                                                     dsh0_all.shape[0], deg, out_shN.shape[1], out_shN.data_ptr(), C.c_void_p(st))
+        if rc != 0:
+            raise RuntimeError(f"dvs_coll_sh_grad_from_dsh0 failed ({rc})")
+
+    def set_cameras(self, campos_local: torch.Tensor):
+        """Camera centres change per step only if the views do; gather them once per view assignment."""
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.campos_all.view(-1), campos_local.to(self.campos_all.device).reshape(3).contiguous(),
+                                        group=self.group)
+        else:
+            self.campos_all[0] = campos_local
+        self._cams_set = True
+
+    def exchange(self, means: torch.Tensor, campos_local: torch.Tensor, deg: int):
+        if self.world == 1:
+            return self.g
+        if not getattr(self, "_cams_set", False):
+            self.set_cameras(campos_local)
+        dist.all_gather_into_tensor(self.dsh0_all.view(-1), self.g.sh0.reshape(-1), group=self.group)
+        dist.all_reduce(self.range_a, op=dist.ReduceOp.SUM, group=self.group)
+        dist.all_reduce(self.range_b, op=dist.ReduceOp.SUM, group=self.group)
+        if self.g.shN.numel():
+            self._accumulate(means, self.campos_all, self.dsh0_all, deg, self.g.shN)
+        return self.g
+
+    @staticmethod
+    def wire_bytes_per_gaussian(world: int, sh_rest: int = 15) -> float:
+        return (world - 1) * 12 + 2 * (world - 1) / world * 56
+
+    @staticmethod
+    def plain_wire_bytes_per_gaussian(world: int, sh_rest: int = 15) -> float:
+        return 2 * (world - 1) / world * (56 + 12 * sh_rest)

@@ -193,6 +193,18 @@ DVS_API const char* dvs_rast_stage_name(int i);
 DVS_API int dvs_coll_allreduce_nvls(void* multicast_ptr, size_t numel_f32, int rank, int world, int ctas,
                                     void* stream);
 
+/*
+ * Local half of the FACTORED gradient exchange: per view the gradient of the higher SH bands is the outer product
+ * B(dir) (x) dL/dcolour, and the band-0 gradient the rasterizer writes is SH_C0 * dL/dcolour, so a rank that holds every
+ * view's dL/dsh0 (all-gathered, 12 B per Gaussian and view) and camera centre forms the summed dL/dshN itself instead of
+ * all-reducing that 180 B per Gaussian tensor:
+ *   out_dshN[i][k][c] = sum_v B_{k+1}(normalize(means[i] - campos[v])) * dsh0_all[v][i][c] / SH_C0
+ * means [N,3], dsh0_all [V,N,3], out_dshN [N,sh_rest_alloc,3]: device; campos_all_host [V,3]: HOST; V <= 64.
+ * Valid when every view's dL/dsh0 is kept apart (one view per rank and step, or one slice per view).
+ */
+DVS_API int dvs_coll_sh_grad_from_dsh0(const float* means, const float* campos_all_host, const float* dsh0_all, int64_t N,
+                                       int num_views, int sh_degree, int sh_rest_alloc, float* out_dshN, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
