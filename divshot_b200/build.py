@@ -53,6 +53,12 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _variant_flags():
+    """A/B experiments only: DVS_NVCC_DEFINES="DVS_TIGHT_TILES DVS_RB_ROUND=128" adds -D macros to every kernel file (use
+    with force=True into a scratch copy of the tree; the default build defines none)."""
+    return [f"-D{d}" for d in os.environ.get("DVS_NVCC_DEFINES", "").split() if d]
+
+
 def build_rast(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OUT, exist_ok=True)
     os.makedirs(OBJ, exist_ok=True)
@@ -65,7 +71,7 @@ def build_rast(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(OBJ, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc(), "-ccbin", host_cxx(), *ARCH, *COMMON, *extra, "-c", s, "-o", o]
+            cmd = [nvcc(), "-ccbin", host_cxx(), *ARCH, *COMMON, *extra, *_variant_flags(), "-c", s, "-o", o]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -116,9 +116,19 @@ __device__ __forceinline__ void warp_emit(int gx, int id, int minx, int miny, in
                 const int k = j - (s_incl - s_area);
                 const int ty = s_miny + k / s_w, tx = s_minx + k % s_w;
                 tile[u] = (uint32_t)(ty * gx + tx);
+#ifdef DVS_TIGHT_TILES
+                // EXPERIMENT (round-2 A/B, never in the default build): in single-pass mode an entry whose sub-tile mask is
+                // empty — no pixel of the tile reaches alpha >= 1/255, ~39 % of D at c3 (profiles/r1_pair_counts.md) — is not
+                // emitted at all: fewer atomics, shorter sorts and list scans, same image and gradients; the index outputs
+                // (ranges / point_list) then differ from the reference's whole-rectangle lists, and two-pass mode keeps them.
+                const uint32_t m8 = sub_tile_mask(g, (float)(tx * TILE), (float)(ty * TILE));
+                if (bin_stride && m8 == 0u) { ok[u] = false; continue; }
+                slot[u] = atomicAdd(tile_cursor + (size_t)tile[u] * TILE_CTR_STRIDE, 1u);
+#else
                 slot[u] = atomicAdd(tile_cursor + (size_t)tile[u] * TILE_CTR_STRIDE, 1u);
                 // the mask computation overlaps the atomic's round trip
                 const uint32_t m8 = sub_tile_mask(g, (float)(tx * TILE), (float)(ty * TILE));
+#endif
                 key[u] = ((unsigned long long)s_depth << 32) | (((uint32_t)s_id << 8) | m8);
             }
         }
