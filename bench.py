@@ -138,6 +138,63 @@ def run_cpu_sample(threads=0, reps=1, frac_lin=2):
     return sc.N, times, threads, sample
 
 
+def choose_exchange(args, reducer, fx, grads, params, campos, deg, dev, dist, torch):
+    """N > 1: which gradient exchange the timed steps use.  `--allreduce factored` forces the factored exchange
+    (dp.FactoredGradientExchange: all-gather dL/dsh0, all-reduce 56 B/Gaussian, dL/dshN formed locally); `auto` adopts it only
+    if (1) on the real gradients of the warm-up step it reproduces the plain all-reduce of the whole arena (every tensor
+    within 1e-4, checked on every rank, decision taken collectively) and (2) it is faster here (3 timed runs each, max over
+    ranks).  Anything else keeps the reducer's own choice (NCCL / NVLS)."""
+    plain = reducer.all_reduce
+    names = ("means3D", "scales", "quats", "opacities", "sh0", "shN")
+    ok = 1
+    err = float("nan")
+    try:
+        ref = reducer.flat.clone()
+        dist.all_reduce(ref)  # plain NCCL sum of the whole arena, the semantics to reproduce
+        ref_g = type(grads).allocate(grads.opacities.shape[0], grads.shN.shape[1], dev, flat=ref)
+        fx.exchange(params["means3D"], campos, deg)
+        torch.cuda.synchronize()
+        err = 0.0
+        for n in names:
+            a, b = getattr(grads, n).double(), getattr(ref_g, n).double()
+            if b.numel():
+                err = max(err, float((a - b).norm() / (b.norm() + 1e-30)))
+        ok = int(err < 1e-4)
+    except Exception as e:  # noqa: BLE001  (a local failure must not leave the ranks disagreeing: it becomes a vote)
+        ok = 0
+        sys.stderr.write(f"factored exchange unavailable: {type(e).__name__}: {e}\n")
+    vote = torch.tensor([ok], device=dev, dtype=torch.int32)
+    dist.all_reduce(vote, op=dist.ReduceOp.MIN)
+    if int(vote.item()) == 0:
+        if args.allreduce == "factored":
+            raise RuntimeError(f"--allreduce factored: the factored exchange does not reproduce the plain all-reduce (rel err {err:.2e})")
+        reducer.note += f"; factored exchange rejected by its self-check (rel err {err:.2e})"
+        return plain
+
+    def timed_ms(fn, reps=3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fn(); torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    factored_fn = lambda: fx.exchange(params["means3D"], campos, deg)  # noqa: E731
+    t_f, t_p = timed_ms(factored_fn), timed_ms(plain)
+    world = dist.get_world_size()
+    detail = (f"factored exchange {t_f:.3f} ms vs {reducer.backend} all-reduce {t_p:.3f} ms; self-check rel err {err:.1e}; "
+              f"{fx.wire_bytes_per_gaussian(world):.0f} B/Gaussian received instead of {fx.plain_wire_bytes_per_gaussian(world):.0f}")
+    if args.allreduce == "factored" or t_f < t_p:
+        reducer.note = (reducer.note + "; " if reducer.note else "") + detail
+        reducer.backend = "factored"
+        return factored_fn
+    reducer.note = (reducer.note + "; " if reducer.note else "") + "kept: " + detail
+    return plain
+
+
 def measure_viewer_pack_row():
     """Row F3 (trainer -> viewer hand-off, SURVEY.md §8 f) measured by its own harness, tools/bench_viewer_pack.py, in a
     SUBPROCESS after the headline measurement is complete: the row was built when round 1 had no GPU minutes left, so this
@@ -185,8 +242,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-rows", action="store_true", help="skip the sub-process measurement of the other section-8 rows")
     ap.add_argument("--allreduce", default="auto", choices=["auto", "nvls", "nccl", "factored"],
-                    help="gradient exchange: NVSwitch in-switch reduction over symmetric memory, plain NCCL, or (STAGED, not "
-                         "yet run on GPUs) the factored exchange: all-gather dL/dsh0, all-reduce 56 B/Gaussian, form dL/dshN locally")
+                    help="gradient exchange: NVSwitch in-switch reduction over symmetric memory, plain NCCL, or the factored "
+                         "exchange (all-gather dL/dsh0, all-reduce 56 B/Gaussian, form dL/dshN locally); auto = the fastest "
+                         "of them, the factored one only after it has reproduced the plain all-reduce on this run's gradients")
     args = ap.parse_args()
     global WORKLOAD
     if args.workload:
@@ -228,15 +286,12 @@ def main():
     reducer = GradientReducer(GradBuffers.numel_for(N, K - 1), dev, backend="nccl" if factored else args.allreduce)
     grads = GradBuffers.allocate(N, K - 1, dev, flat=reducer.flat)
     exchange = reducer.all_reduce
-    if factored and world > 1:
+    fx = None
+    if world > 1 and args.allreduce in ("auto", "factored"):
         from divshot_b200.dp import FactoredGradientExchange
         fx = FactoredGradientExchange(grads)
         campos = torch.tensor(np.asarray(sc.cameras[rank % len(sc.cameras)].campos, np.float32))
         fx.set_cameras(campos)
-        exchange = lambda: fx.exchange(params["means3D"], campos, deg)  # noqa: E731
-        reducer.backend = "factored"
-        reducer.note = (f"all-gather dL/dsh0 + all-reduce 56 B/Gaussian + local SH accumulation: "
-                        f"{fx.wire_bytes_per_gaussian(world):.0f} B/Gaussian received instead of {fx.plain_wire_bytes_per_gaussian(world):.0f}")
     rast = Rasterizer(local)
     rast.reserve(N, W, H, 0)
     img = torch.empty(3, H, W, device=dev)
@@ -246,6 +301,9 @@ def main():
     # host synchronisation (DVS_FLAG_DEFER_CHECK) — an overflow would surface as an error at rast.stats()
     rast.forward(cam, params, img, radii); rast.backward(dl, grads)
     rast.forward(cam, params, img, radii); rast.backward(dl, grads)
+
+    if fx is not None:
+        exchange = choose_exchange(args, reducer, fx, grads, params, campos, deg, dev, dist, torch)
 
     def step_resident():
         rast.forward(cam, params, img, radii, defer_check=True)

@@ -143,7 +143,9 @@ class FactoredGradientExchange:
         import ctypes as C
 
         from . import _cabi
-        cam_host = campos_all.cpu().contiguous()  # V x 3 floats; the kernel takes them by value
+        cam_host = getattr(self, "_cam_host", None)  # V x 3 floats on the host; the kernel takes them by value
+        if cam_host is None:
+            cam_host = campos_all.cpu().contiguous()
         st = torch.cuda.current_stream(out_shN.device).cuda_stream
         rc = _cabi.load().dvs_coll_sh_grad_from_dsh0(means.data_ptr(), cam_host.data_ptr(), dsh0_all.data_ptr(), self.N,
                                                      dsh0_all.shape[0], deg, out_shN.shape[1], out_shN.data_ptr(), C.c_void_p(st))
@@ -157,6 +159,7 @@ class FactoredGradientExchange:
                                         group=self.group)
         else:
             self.campos_all[0] = campos_local
+        self._cam_host = self.campos_all.cpu().contiguous()  # cached: no device->host copy (and no stream sync) per step
         self._cams_set = True
 
     def exchange(self, means: torch.Tensor, campos_local: torch.Tensor, deg: int):

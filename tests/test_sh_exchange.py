@@ -150,3 +150,83 @@ def test_factored_exchange_refuses_cpu_tensors():
     ex = FactoredGradientExchange(g)
     with pytest.raises(RuntimeError):
         ex._accumulate_cuda(torch.zeros(10, 3), torch.zeros(1, 3), torch.zeros(1, 10, 3), 3, g.shN)
+
+
+# ---- bench.py's collective decision (choose_exchange) on gloo: CUDA timing primitives are stubbed, the logic is real
+class _FakeEvent:
+    def __init__(self, enable_timing=True):
+        self.t = 0.0
+
+    def record(self):
+        import time
+        self.t = time.perf_counter()
+
+    def elapsed_time(self, other):
+        return (other.t - self.t) * 1e3
+
+
+def _choose_worker(rank, world, port, broken, q):
+    import types
+
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    from divshot_b200.dp import FactoredGradientExchange
+    from divshot_b200.rasterizer import GradBuffers
+    torch.cuda.synchronize = lambda *a, **k: None
+    torch.cuda.Event = _FakeEvent
+    deg, N = 2, 1200
+    sc = make_scene(N=N, width=64, height=48, sh_degree=deg, views=world, seed=78)
+    sc.log_scales += 0.8
+    KR = sc.shN.shape[1]
+    per_view = _per_view_grads(sc, deg)
+    mine = per_view[rank]
+    g = GradBuffers.allocate(N, KR, torch.device("cpu"))
+
+    def load_local():
+        g.means3D.copy_(torch.from_numpy(mine.dL_dmeans3D)); g.scales.copy_(torch.from_numpy(mine.dL_dscales))
+        g.quats.copy_(torch.from_numpy(mine.dL_dquats)); g.opacities.copy_(torch.from_numpy(mine.dL_dopacities))
+        g.sh0.copy_(torch.from_numpy(mine.dL_dsh0)); g.shN.copy_(torch.from_numpy(mine.dL_dshN))
+
+    def accumulate(means, campos_all, dsh0_all, deg_, out_shN):
+        out_shN.copy_(torch.from_numpy(host_sh_grad(means.numpy(), campos_all.numpy(), dsh0_all.numpy(), deg_, out_shN.shape[1])))
+        if broken and rank == 1:  # only ONE rank computes garbage: the vote must still be unanimous
+            out_shN.mul_(1.5)
+
+    reducer = types.SimpleNamespace(flat=g.flat, backend="nccl", note="", all_reduce=lambda: dist.all_reduce(g.flat))
+    fx = FactoredGradientExchange(g, accumulate=accumulate)
+    campos = torch.from_numpy(np.asarray(sc.cameras[rank].campos, np.float32))
+    fx.set_cameras(campos)
+    load_local()
+    args = types.SimpleNamespace(allreduce="auto")
+    fn = bench.choose_exchange(args, reducer, fx, g, {"means3D": torch.from_numpy(sc.means3D)}, campos, deg, torch.device("cpu"), dist, torch)
+    load_local()
+    fn()
+    tot = sum(x.dL_dshN.astype(np.float64) for x in per_view)
+    tot_m = sum(x.dL_dmeans3D.astype(np.float64) for x in per_view)
+    ok = (np.allclose(g.shN.numpy(), tot, rtol=2e-4, atol=2e-5 * np.abs(tot).max())
+          and np.allclose(g.means3D.numpy(), tot_m, rtol=2e-4, atol=2e-5 * np.abs(tot_m).max()))
+    q.put((rank, bool(ok), reducer.backend, reducer.note))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("broken", [False, True])
+def test_bench_adopts_the_factored_exchange_only_after_a_unanimous_self_check(broken):
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_choose_worker, args=(r, world, port, broken, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=300) for _ in range(world))
+    [p.join(timeout=60) for p in procs]
+    assert all(r[1] for r in res), res                       # whichever exchange was chosen sums correctly
+    assert res[0][2] == res[1][2], "ranks must agree on the exchange"
+    if broken:
+        assert res[0][2] == "nccl" and all("rejected" in r[3] for r in res)
+    else:
+        assert all(("factored exchange" in r[3]) for r in res)  # timed against the plain one, either may win on gloo
