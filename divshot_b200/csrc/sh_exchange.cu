@@ -19,37 +19,16 @@ __global__ void __launch_bounds__(SX_THREADS)
 sh_grad_from_dsh0_kernel(const float* __restrict__ means, Campos cams, const float* __restrict__ dsh0_all, int64_t N, int V, int deg,
                          int RW, float* __restrict__ out, int vec_ok) {
     __shared__ __align__(16) float s_rows[SX_THREADS * 45];
+    const dvs_shx::ExchangeArgs a{means, cams.p, dsh0_all, (long long)N, V, deg, RW, out, vec_ok};
     const int tid = threadIdx.x;
     const int64_t n_tiles = (N + SX_THREADS - 1) / SX_THREADS;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t base = tile * SX_THREADS;
         const int cnt = (int)(N - base < SX_THREADS ? N - base : SX_THREADS);
-        if (tid < cnt) {
-            const int64_t i = base + tid;
-            float acc[45];
-#pragma unroll
-            for (int k = 0; k < 45; k++) acc[k] = 0.0f;
-            const float mean[3] = {__ldg(means + 3 * i), __ldg(means + 3 * i + 1), __ldg(means + 3 * i + 2)};
-            for (int v = 0; v < V; v++) {
-                const float* d = dsh0_all + ((size_t)v * (size_t)N + (size_t)i) * 3;
-                const float dc[3] = {__ldg(d), __ldg(d + 1), __ldg(d + 2)};
-                dvs_shx::accumulate_view(deg, mean, cams.p + 3 * v, dc, acc);
-            }
-#pragma unroll
-            for (int k = 0; k < 45; k++)
-                if (k < RW) s_rows[tid * RW + k] = acc[k];
-        }
+        dvs_shx::exchange_compute(a, s_rows, tid, base, cnt);
         __syncthreads();
-        float* dst = out + base * RW;
-        const int n_words = cnt * RW;
-        if (vec_ok && ((base * RW) & 3) == 0) {  // 16-byte aligned start (always for RW = 45: base * 45, base % 128 == 0)
-            const int n_vec = n_words >> 2;
-            for (int k = tid; k < n_vec; k += SX_THREADS) reinterpret_cast<float4*>(dst)[k] = reinterpret_cast<const float4*>(s_rows)[k];
-            for (int k = (n_vec << 2) + tid; k < n_words; k += SX_THREADS) dst[k] = s_rows[k];
-        } else {
-            for (int k = tid; k < n_words; k += SX_THREADS) dst[k] = s_rows[k];
-        }
-        __syncthreads();
+        dvs_shx::exchange_store(a, s_rows, tid, SX_THREADS, base, cnt);
+        __syncthreads();  // the next trip overwrites s_rows
     }
 }
 }  // namespace

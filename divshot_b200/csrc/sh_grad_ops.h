@@ -66,4 +66,51 @@ DVS_SG_HD void accumulate_view(int deg, const float mean[3], const float campos[
     }
 }
 
+// ---- the kernel of sh_exchange.cu, written as the two phases a CTA runs between barriers, so that a host harness can run
+// the very same indexing (tile loop, shared-memory rows, 128-bit copy with scalar tail) thread by thread.
+struct ExchangeArgs {
+    const float* means;     // [N,3]
+    const float* campos;    // [V,3]
+    const float* dsh0_all;  // [V,N,3]
+    long long N;
+    int V, deg, RW;         // RW = 3 * sh_rest_alloc words per output row (<= 45)
+    float* out;             // [N,RW]
+    int vec_ok;             // out is 16-byte aligned
+};
+// phase 1: thread `tid` of the CTA that owns Gaussians [base, base + cnt) accumulates its row into rows[tid * RW ..]
+DVS_SG_HD void exchange_compute(const ExchangeArgs& a, float* rows, int tid, long long base, int cnt) {
+    if (tid >= cnt) return;
+    const long long i = base + tid;
+    float acc[45];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 45; k++) acc[k] = 0.0f;
+    const float mean[3] = {a.means[3 * i], a.means[3 * i + 1], a.means[3 * i + 2]};
+    for (int v = 0; v < a.V; v++) {
+        const float* d = a.dsh0_all + ((size_t)v * (size_t)a.N + (size_t)i) * 3;
+        const float dc[3] = {d[0], d[1], d[2]};
+        accumulate_view(a.deg, mean, a.campos + 3 * v, dc, acc);
+    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 45; k++)
+        if (k < a.RW) rows[tid * a.RW + k] = acc[k];
+}
+// phase 2: the CTA's rows are one contiguous span of the output: `nthreads` threads copy it, 128 bits at a time when the
+// span starts on a 16-byte boundary (always for RW = 45: base is a multiple of 128), scalar tail
+DVS_SG_HD void exchange_store(const ExchangeArgs& a, const float* rows, int tid, int nthreads, long long base, int cnt) {
+    float* dst = a.out + base * a.RW;
+    const int n_words = cnt * a.RW;
+    if (a.vec_ok && ((base * a.RW) & 3) == 0) {
+        struct alignas(16) V4 { float x, y, z, w; };
+        const int n_vec = n_words >> 2;
+        for (int k = tid; k < n_vec; k += nthreads) reinterpret_cast<V4*>(dst)[k] = reinterpret_cast<const V4*>(rows)[k];
+        for (int k = (n_vec << 2) + tid; k < n_words; k += nthreads) dst[k] = rows[k];
+    } else {
+        for (int k = tid; k < n_words; k += nthreads) dst[k] = rows[k];
+    }
+}
+
 }  // namespace dvs_shx

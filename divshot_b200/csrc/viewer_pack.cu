@@ -26,62 +26,30 @@ viewer_pack_kernel(const float* __restrict__ means, const float* __restrict__ sc
                    uint4* __restrict__ out_g, uint2* __restrict__ out_c, uint4* __restrict__ out_sh,
                    uint32_t* __restrict__ bbox, int shn_vec_ok) {
     __shared__ __align__(16) float s_shn[kThreads * kShRest];
+    const PackArgs a{means, scales, quats, opac, sh0, shN, (long long)N, reinterpret_cast<uint32_t*>(out_g),
+                     reinterpret_cast<uint32_t*>(out_c), reinterpret_cast<uint32_t*>(out_sh), shn_vec_ok};
     const int tid = threadIdx.x;
     float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     const int64_t n_tiles = (N + kThreads - 1) / kThreads;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t base = tile * kThreads;
         const int cnt = (int)(N - base < kThreads ? N - base : kThreads);
-        const float* src = shN + base * kShRest;  // base * 180 B: a multiple of 16 B because base is a multiple of 128
-        const int n_words = cnt * kShRest;
-        if (shn_vec_ok) {
-            const int n_vec = n_words >> 2;
-            const float4* src4 = reinterpret_cast<const float4*>(src);
-            float4* dst4 = reinterpret_cast<float4*>(s_shn);
-            for (int i = tid; i < n_vec; i += kThreads) dst4[i] = __ldg(src4 + i);
-            for (int i = (n_vec << 2) + tid; i < n_words; i += kThreads) s_shn[i] = __ldg(src + i);
-        } else {
-            for (int i = tid; i < n_words; i += kThreads) s_shn[i] = __ldg(src + i);
-        }
+        pack_stage(a, s_shn, tid, kThreads, base, cnt);
         __syncthreads();
-        if (tid < cnt) {
-            const int64_t i = base + tid;
-            const float pos[3] = {__ldg(means + 3 * i), __ldg(means + 3 * i + 1), __ldg(means + 3 * i + 2)};
-            const float ls[3] = {__ldg(scales + 3 * i), __ldg(scales + 3 * i + 1), __ldg(scales + 3 * i + 2)};
-            const float4 q4 = __ldg(reinterpret_cast<const float4*>(quats) + i);
-            const float q[4] = {q4.x, q4.y, q4.z, q4.w};
-            const float c0[3] = {__ldg(sh0 + 3 * i), __ldg(sh0 + 3 * i + 1), __ldg(sh0 + 3 * i + 2)};
-            uint32_t g[8], col[2], sh[16];
-            pack_geometry(pos, q, ls, __ldg(opac + i), g);
-            pack_color(c0, col);
-            float c[kShRest];
-#pragma unroll
-            for (int j = 0; j < kShRest; j++) c[j] = s_shn[tid * kShRest + j];
-            pack_sh_rest(c, sh);
-            out_g[2 * i] = make_uint4(g[0], g[1], g[2], g[3]);
-            out_g[2 * i + 1] = make_uint4(g[4], g[5], g[6], g[7]);
-            out_c[i] = make_uint2(col[0], col[1]);
-#pragma unroll
-            for (int k = 0; k < 4; k++) out_sh[4 * i + k] = make_uint4(sh[4 * k], sh[4 * k + 1], sh[4 * k + 2], sh[4 * k + 3]);
-#pragma unroll
-            for (int a = 0; a < 3; a++) {  // glm::min / glm::max: (y < x) ? y : x  and  (x < y) ? y : x
-                lo[a] = pos[a] < lo[a] ? pos[a] : lo[a];
-                hi[a] = hi[a] < pos[a] ? pos[a] : hi[a];
-            }
-        }
+        pack_compute(a, s_shn, tid, base, cnt, lo, hi);
         __syncthreads();  // the next trip overwrites s_shn
     }
 #pragma unroll
-    for (int a = 0; a < 3; a++) {
-        uint32_t l = f32_to_ordered(lo[a]), h = f32_to_ordered(hi[a]);
+    for (int k = 0; k < 3; k++) {
+        uint32_t l = f32_to_ordered(lo[k]), h = f32_to_ordered(hi[k]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             l = min(l, __shfl_xor_sync(0xffffffffu, l, o));
             h = max(h, __shfl_xor_sync(0xffffffffu, h, o));
         }
         if ((tid & 31) == 0) {
-            atomicMin(bbox + a, l);
-            atomicMax(bbox + 3 + a, h);
+            atomicMin(bbox + k, l);
+            atomicMax(bbox + 3 + k, h);
         }
     }
 }

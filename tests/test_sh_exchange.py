@@ -28,6 +28,7 @@ def _ops():
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wextra", "-I", os.path.dirname(hdr), src, "-o", out])
     L = C.CDLL(out)
     L.t_sh_grad_from_dsh0.argtypes = [C.c_void_p] * 3 + [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.t_sh_exchange_kernel_emulation.argtypes = [C.c_void_p] * 3 + [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
     return L
 
 
@@ -68,6 +69,25 @@ def test_factored_sh_gradient_equals_the_sum_of_the_per_view_gradients(deg, view
     assert_close(got, want, 2e-5, "factored dL_dshN")
     K1 = (deg + 1) ** 2 - 1
     assert not got[:, K1:].any(), "bands above the active degree stay zero"
+
+
+@pytest.mark.parametrize("N,V,deg,KR,grid,misalign", [(1000, 3, 3, 15, 4, 0), (128, 2, 2, 15, 1, 0), (129, 2, 1, 3, 7, 0), (1, 1, 3, 15, 2, 0),
+                                                      (777, 8, 3, 15, 3, 1), (5000, 2, 0, 15, 5, 0), (300, 2, 1, 5, 2, 0)])
+def test_kernel_indexing_thread_by_thread(N, V, deg, KR, grid, misalign):
+    """The two phase functions the CUDA kernel calls between its barriers, run for every (CTA, thread) on the host with
+    the kernel's own tile loop: partial last tile, vector / scalar store paths, rows narrower than 45 words, more CTAs than
+    tiles, an output that is not 16-byte aligned.  Must equal the plain per-Gaussian evaluation and touch nothing else."""
+    rng = np.random.default_rng(N * 7 + V)
+    means = rng.normal(0, 3, (N, 3)).astype(np.float32)
+    campos = rng.normal(0, 1, (V, 3)).astype(np.float32)
+    dsh0 = rng.normal(0, 1, (V, N, 3)).astype(np.float32)
+    dsh0[rng.random((V, N)) < 0.3] = 0
+    buf = np.full(N * KR * 3 + 8, 777.0, np.float32)
+    out = buf[4 + misalign:4 + misalign + N * KR * 3]
+    _ops().t_sh_exchange_kernel_emulation(_p(means), _p(campos), _p(dsh0), N, V, deg, KR, C.c_void_p(out.ctypes.data), grid)
+    want = host_sh_grad(means, campos, dsh0, deg, KR)
+    assert np.array_equal(out.reshape(N, KR, 3), want)
+    assert (buf[:4 + misalign] == 777.0).all() and (buf[4 + misalign + N * KR * 3:] == 777.0).all(), "wrote outside its rows"
 
 
 # ------------------------------------------------------------------------------------------------ gloo, world_size 2

@@ -57,6 +57,30 @@ def test_host_build_of_the_kernel_arithmetic_matches_the_frozen_reference_bytes(
     assert u.digest(*u.pack_with_host_ops(ops, u.make_model(N, seed, deg))) == GOLDEN[f"N{N}_seed{seed}_deg{deg}"]
 
 
+@pytest.mark.parametrize("N,grid,misalign", [(1000, 3, 0), (128, 1, 0), (129, 5, 0), (1, 2, 0), (777, 2, 1), (4096, 40, 0)])
+def test_kernel_indexing_thread_by_thread(ops, N, grid, misalign):
+    """The two phase functions the CUDA kernel calls between its barriers, run for every (CTA, thread) on the host with the
+    kernel's own tile loop: partial last tile, vector / scalar staging paths (shN not 16-byte aligned), more CTAs than tiles.
+    Must give the bytes of the plain per-Gaussian loop and leave guard words around every output untouched."""
+    m = u.make_model(max(N, 64), 40 + N)
+    m = {k: v[:N] for k, v in m.items()}
+    shn_buf = np.zeros(N * 45 + 8, np.float32)
+    shn = shn_buf[4 + misalign:4 + misalign + N * 45]
+    shn[:] = m["shN"].reshape(-1)
+    G = 0xDEADBEEF
+    bg, bc, bs = (np.full(n + 8, G, np.uint32) for n in (N * 8, N * 2, N * 16))
+    bb = np.zeros(6, np.uint32)
+    arrs = [np.ascontiguousarray(m[k]) for k in ("means", "scales", "quats", "opac", "sh0")]
+    ops.t_viewer_pack_kernel_emulation(*[u._p(a) for a in arrs], C.c_void_p(shn.ctypes.data), N, C.c_void_p(bg[4:].ctypes.data),
+                                       C.c_void_p(bc[4:].ctypes.data), C.c_void_p(bs[4:].ctypes.data), u._p(bb), grid)
+    g, c, sh, box = u.pack_with_host_ops(ops, m)
+    assert np.array_equal(bg[4:4 + N * 8].reshape(N, 8), g) and np.array_equal(bc[4:4 + N * 2].reshape(N, 2), c)
+    assert np.array_equal(bs[4:4 + N * 16].reshape(N, 16), sh)
+    assert np.array_equal(np.array([ops.t_ordered_to_f32(int(v)) for v in bb], np.float32).view(np.uint32), box.view(np.uint32))
+    for b, n in ((bg, N * 8), (bc, N * 2), (bs, N * 16)):
+        assert (b[:4] == G).all() and (b[4 + n:] == G).all(), "wrote outside its records"
+
+
 @needs_ref
 @pytest.mark.parametrize("N,seed,deg", [(30000, 21, 3), (4097, 22, 2), (64, 23, 0)])
 def test_host_build_matches_the_reference_quantiser_byte_for_byte(ops, N, seed, deg):

@@ -59,6 +59,7 @@ def host_ops():
                                "-I", os.path.dirname(hdr), src, "-o", out])
     L = C.CDLL(out)
     L.t_viewer_pack.argtypes = [C.c_void_p] * 6 + [C.c_longlong] + [C.c_void_p] * 4
+    L.t_viewer_pack_kernel_emulation.argtypes = [C.c_void_p] * 6 + [C.c_longlong] + [C.c_void_p] * 4 + [C.c_int]
     L.t_f32_to_f16_glm.argtypes, L.t_f32_to_f16_glm.restype = [C.c_float], C.c_uint32
     L.t_f32_to_ordered.argtypes, L.t_f32_to_ordered.restype = [C.c_float], C.c_uint32
     L.t_ordered_to_f32.argtypes, L.t_ordered_to_f32.restype = [C.c_uint32], C.c_float
