@@ -195,19 +195,20 @@ def choose_exchange(args, reducer, fx, grads, params, campos, deg, dev, dist, to
     return plain
 
 
-def measure_viewer_pack_row():
-    """Row F3 (trainer -> viewer hand-off, SURVEY.md §8 f) measured by its own harness, tools/bench_viewer_pack.py, in a
-    SUBPROCESS after the headline measurement is complete: the row was built when round 1 had no GPU minutes left, so this
-    is its first run on a B200 — a failure there must not be able to disturb the headline number (separate CUDA context,
-    time-boxed), and is reported as text instead."""
+def measure_row(tool):
+    """Rows F3 (trainer -> viewer hand-off) and F1 (refinement step) of SURVEY.md §8 f, each measured by its own harness
+    (tools/bench_viewer_pack.py, tools/bench_densify.py) in a SUBPROCESS after the headline measurement is complete: the
+    rows were built when round 1 had no GPU minutes left, so this is their first run on a B200 — a failure there must not
+    be able to disturb the headline number (separate CUDA context, time-boxed), and is reported as text instead."""
     try:
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_viewer_pack.py"), "--steps", "30", "--warmup", "5"],
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", tool), "--steps", "30", "--warmup", "5"],
                            capture_output=True, text=True, timeout=300, cwd=ROOT)
         rows = [l for l in r.stdout.splitlines() if l.startswith("{")]
         if r.returncode != 0 or not rows:
             return {"error": (r.stderr or r.stdout)[-600:]}
         d = json.loads(rows[-1])
-        return {k: d.get(k) for k in ("metric", "value", "unit", "ms_per_step", "config", "roofline", "e2e", "cpu_baseline", "gpu_launches")}
+        return {k: d.get(k) for k in ("metric", "value", "unit", "ms_per_step", "config", "roofline", "e2e", "cpu_baseline", "gpu_launches",
+                                      "passes", "refine_ms_per_call", "refine_ms_per_iteration") if k in d}
     except Exception as e:  # noqa: BLE001
         return {"error": repr(e)[:600]}
 
@@ -428,7 +429,7 @@ def main():
         line["cpu_baseline"] = {"value": n_s / best, "unit": "Gaussians/s", "cores": cores, "kind": "port",
                                 "sample": sample + f"; best of 3 ({best:.2f} s)"}
     if world == 1 and rank == 0 and not args.no_rows:
-        line["other_rows"] = {"F3_viewer_pack": measure_viewer_pack_row()}
+        line["other_rows"] = {"F3_viewer_pack": measure_row("bench_viewer_pack.py"), "F1_refinement": measure_row("bench_densify.py")}
     if rank == 0:
         sys.stdout.flush()
         os.dup2(real_stdout, 1)

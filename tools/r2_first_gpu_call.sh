@@ -15,6 +15,9 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --cs
     python tools/bench_viewer_pack.py --steps 3 --warmup 3 > /dev/null 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:viewer_pack_kernel -c 1 -f -o gpurun_out/viewer_pack_full \
     python tools/bench_viewer_pack.py --steps 1 --warmup 3 > /dev/null 2>&1
+# 2b. F1 measurement
+timeout 600 python tools/bench_densify.py > gpurun_out/bench_densify.json 2> gpurun_out/bench_densify.err
+cat gpurun_out/bench_densify.json
 # 3. the headline bench, unchanged code path (regression check against profiles/r1_final_bench.json: 1.049 ms/step)
 timeout 900 python bench.py > gpurun_out/bench_r2_start.json 2> gpurun_out/bench_r2_start.err
 tail -c 600 gpurun_out/bench_r2_start.json
