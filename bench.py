@@ -417,7 +417,9 @@ def main():
                 "d2h_bytes_per_step": 12 * P * world, "ms_per_step": ms_e2e / args.steps,
                 "api": "dvs_rast_step_host (C-ABI): pinned dL/dpix H2D, forward, image D2H, backward; parameters and "
                        "gradients device-resident as in the trainer"},
-        "gpu_launches": 10 * args.steps,
+        # 8 forward + 2 backward kernels of ours per step; with N > 1 one more when the exchange is ours too (the NVLS
+        # all-reduce kernel, or the SH accumulation kernel of the factored exchange)
+        "gpu_launches": (10 + (1 if world > 1 and reducer.backend in ("nvls", "factored") else 0)) * args.steps,
         "allreduce": ({"backend": reducer.backend, "note": reducer.note, "bytes": int(reducer.flat.numel()) * 4, "ms": ms_ar,
                        "busbw_GBps": (2 * (world - 1) / world * reducer.flat.numel() * 4 / 1e9 / (ms_ar * 1e-3))}
                       if world > 1 else None),
