@@ -289,10 +289,16 @@ def main():
     exchange = reducer.all_reduce
     fx = None
     if world > 1 and args.allreduce in ("auto", "factored"):
-        from divshot_b200.dp import FactoredGradientExchange
-        fx = FactoredGradientExchange(grads)
-        campos = torch.tensor(np.asarray(sc.cameras[rank % len(sc.cameras)].campos, np.float32))
-        fx.set_cameras(campos)
+        try:
+            from divshot_b200.dp import FactoredGradientExchange
+            fx = FactoredGradientExchange(grads)
+            campos = torch.tensor(np.asarray(sc.cameras[rank % len(sc.cameras)].campos, np.float32))
+            fx.set_cameras(campos)
+        except Exception as e:  # noqa: BLE001  (same code and arguments on every rank: fails on all of them or on none)
+            if args.allreduce == "factored":
+                raise
+            sys.stderr.write(f"factored exchange not set up: {type(e).__name__}: {e}\n")
+            fx = None
     rast = Rasterizer(local)
     rast.reserve(N, W, H, 0)
     img = torch.empty(3, H, W, device=dev)
