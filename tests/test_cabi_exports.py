@@ -60,3 +60,30 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_cabi.DvsCamera) == 4 * (16 + 16 + 3 + 2 + 2 + 3 + 1 + 3)
     assert ctypes.sizeof(_cabi.DvsParams) == 6 * 8 and ctypes.sizeof(_cabi.DvsGrads) == 8 * 8
     assert ctypes.sizeof(_cabi.DvsStats) == 5 * 8 + 3 * 4 + 4
+
+
+def test_new_entry_points_validate_their_arguments_without_a_gpu():
+    """Argument checks of the entry points added for rows F3 / F4 / §8(e) run before any CUDA call."""
+    from divshot_b200 import _cabi, build
+    L = _cabi.load()
+    E_INVALID = 1
+    lib_h = open(os.path.join(ROOT, "include", "dvs_rast.h")).read()
+    assert re.search(r"#define\s+DVS_E_INVALID\s+1\b", lib_h) or "DVS_E_INVALID" in lib_h
+    assert L.dvs_rast_forward_aux(None, None, None, None, None) != 0
+    assert L.dvs_rast_backward_aux(None, None, None, None, None, None, 0, None) != 0
+    # the SH exchange kernel: bad view counts / degrees / row widths are refused, an empty problem is a no-op
+    f = L.dvs_coll_sh_grad_from_dsh0
+    assert f(None, None, None, 10, 0, 3, 15, None, None) != 0       # no views
+    assert f(None, None, None, 10, 65, 3, 15, None, None) != 0      # more than 64 views
+    assert f(None, None, None, 10, 2, 4, 15, None, None) != 0       # degree > 3
+    assert f(None, None, None, 10, 2, 3, 8, None, None) != 0        # rows too narrow for the degree
+    assert f(None, None, None, 10, 2, 3, 15, None, None) != 0       # null pointers
+    assert f(None, None, None, 0, 2, 3, 15, None, None) == 0        # N = 0
+    g = ctypes.CDLL(build.build_gstrain())
+    g.dvs_viewer_pack.argtypes = [ctypes.c_void_p] * 6 + [ctypes.c_int64] + [ctypes.c_void_p] * 5
+    assert g.dvs_viewer_pack(None, None, None, None, None, None, -1, None, None, None, None, None) != 0
+    assert g.dvs_viewer_pack(None, None, None, None, None, None, 5, None, None, None, None, None) != 0  # no bbox buffer
+    import torch
+    if not torch.cuda.is_available():  # and without a device the launch itself fails loudly (no CPU path)
+        bb = (ctypes.c_uint32 * 6)()
+        assert g.dvs_viewer_pack(None, None, None, None, None, None, 0, None, None, None, bb, None) != 0
