@@ -34,6 +34,19 @@ namespace diverse {
 
 using namespace diverse;
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+extern "C" __attribute__((visibility("default"))) int ref_viewer_pack_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
 extern "C" __attribute__((visibility("default"))) int ref_viewer_pack(
     const float* pos_d, const float* scales_d, const float* rots_d, const float* opacities_d, const float* shs0_d,
     const float* shsn_d, long long num_gaussians, void* out_gaussians, void* out_colors, void* out_sh, float* bbox6) {
@@ -61,7 +74,9 @@ extern "C" __attribute__((visibility("default"))) int ref_viewer_pack(
     std::vector<PackedVertexSH> gaussians_sh_n(pos.size());
 #include "_ref/gen/vp_consts.inc"
     (void)t11; (void)t10;
-    for (size_t k = 0; k < gaussians.size(); k++) {  // parallel_for<size_t>(0, gaussians.size(), [&](size_t k) {
+    // parallel_for<size_t>(0, gaussians.size(), [&](size_t k) {  -- the reference's thread pool; OpenMP over the same body here
+#pragma omp parallel for schedule(static)
+    for (size_t k = 0; k < gaussians.size(); k++) {
 #include "_ref/gen/vp_body.inc"
     }
     memcpy(out_gaussians, gaussians.data(), gaussians.size() * sizeof(Gaussian));
