@@ -143,10 +143,11 @@ __global__ void k_adc_decide(Tensors p, const float* __restrict__ accum, const f
 }
 // appended element j: a copy of grow_list[j] (clone) or its second split sample; Adam moments of the new slot zeroed
 __global__ void k_adc_append(Tensors p, Tensors m1, Tensors m2, const int64_t* __restrict__ grow_list,
-                             const uint8_t* __restrict__ act, int64_t base, int64_t M, uint64_t seed) {
+                             const uint8_t* __restrict__ act, int64_t base, int64_t M, uint64_t seed, bool revised) {
     GRID_STRIDE(j, M) {
         const int64_t s = grow_list[j], d = base + j;
         copy_row(p, d, s);
+        if (revised) p.opac[d] = revised_opacity_logit(p.opac[s]);
         if (act[s] & ADC_SPLIT) {
             float e[4];
             normal2(seed, 4 * (uint64_t)s + 2, e[0], e[1]);
@@ -159,11 +160,14 @@ __global__ void k_adc_append(Tensors p, Tensors m1, Tensors m2, const int64_t* _
         zero_row(m2, d);
     }
 }
-// split originals become their own first sample (runs after k_adc_append, which reads the original mean / scale)
+// split originals become their own first sample (runs after k_adc_append, which reads the original mean / scale / opacity);
+// with `revised` every grown original (clone or split) takes the revised opacity its copy already has
 __global__ void k_adc_split_in_place(Tensors p, Tensors m1, Tensors m2, const uint8_t* __restrict__ act,
-                                     const uint8_t* __restrict__ grow, int64_t N, uint64_t seed) {
+                                     const uint8_t* __restrict__ grow, int64_t N, uint64_t seed, bool revised) {
     GRID_STRIDE(i, N) {
-        if (!grow[i] || !(act[i] & ADC_SPLIT)) continue;
+        if (!grow[i]) continue;
+        if (revised) p.opac[i] = revised_opacity_logit(p.opac[i]);
+        if (!(act[i] & ADC_SPLIT)) continue;
         float e[4];
         normal2(seed, 4 * (uint64_t)i, e[0], e[1]);
         normal2(seed, 4 * (uint64_t)i + 1, e[2], e[3]);
@@ -384,8 +388,8 @@ cudaError_t adc_refine(Workspace* ws, Tensors p, Tensors m1, Tensors m2, float* 
     const int64_t limit = std::min(cap_max, capacity);
     if (N - n_pruned + n_grow > limit || N + n_grow > capacity) n_grow = 0;  // no room: prune only this round
     if (n_grow > 0) {
-        DVS_LAUNCH(k_adc_append, n_grow, st, p, m1, m2, ws->list_a, ws->act, N, n_grow, seed);
-        DVS_LAUNCH(k_adc_split_in_place, N, st, p, m1, m2, ws->act, ws->flag_a, N, seed);
+        DVS_LAUNCH(k_adc_append, n_grow, st, p, m1, m2, ws->list_a, ws->act, N, n_grow, seed, cfg.revised_opacity);
+        DVS_LAUNCH(k_adc_split_in_place, N, st, p, m1, m2, ws->act, ws->flag_a, N, seed, cfg.revised_opacity);
     }
     const int64_t total = N + n_grow, K = total - n_pruned;
     // statistics restart after every refinement (also for the appended slots)
@@ -452,12 +456,12 @@ DVS_DENSIFY_EXPORT int dvs_densify_test_adc_accumulate(const float* mean2D_grad,
     return (int)adc_accumulate(mean2D_grad, mean2D_abs, radii, accum, denom, N, static_cast<cudaStream_t>(stream));
 }
 DVS_DENSIFY_EXPORT int dvs_densify_test_adc_refine(float* const* p6, float* const* m1_6, float* const* m2_6, float* accum, float* denom,
-                                      long long* N, long long capacity, long long cap_max, const float* cfg5,
+                                      long long* N, long long capacity, long long cap_max, const float* cfg6,
                                       unsigned long long seed, long long* report6, void* stream) {
     Workspace* ws = workspace_create();
     RefineReport rep;
     int64_t n = *N;
-    const AdcConfig c{cfg5[0], cfg5[1], cfg5[2], cfg5[3], cfg5[4]};
+    const AdcConfig c{cfg6[0], cfg6[1], cfg6[2], cfg6[3], cfg6[4], cfg6[5] != 0.0f};  // 6th: revisedOpacity
     const cudaError_t e = adc_refine(ws, tensors6(p6), tensors6(m1_6), tensors6(m2_6), accum, denom, &n, capacity,
                                                   cap_max, c, seed, static_cast<cudaStream_t>(stream), &rep);
     cudaStreamSynchronize(static_cast<cudaStream_t>(stream));

@@ -42,6 +42,7 @@ cudaError_t adc_accumulate(const float* mean2D_grad, const float* mean2D_abs, co
                            float* denom, int64_t N, cudaStream_t st);
 struct AdcConfig {
     float grad_threshold, percent_dense, extent, prune_opacity, prune_scale3d;
+    bool revised_opacity = false;  // `revisedOpacity`: clones / split samples get opacity 1 - sqrt(1 - o)
 };
 // clone / split / prune in place (holes left by pruning are filled from the tail; clones and second split samples are
 // appended).  Statistics are reset, Adam moments of new and split Gaussians zeroed.  *N is updated.

@@ -130,6 +130,13 @@ DVS_HD uint8_t adc_decide(float grad_accum, float denom, const float log_scale[3
     if (sigmoidf_(logit_opacity) < prune_opacity || smax > prune_scale3d * extent) act |= ADC_PRUNE;
     return act;
 }
+// `revisedOpacity` ("Revising Densification in Gaussian Splatting", arXiv 2404.06109, eq. 9): a cloned or split Gaussian
+// and its copy each get opacity 1 - sqrt(1 - o), so that the pair composites like the original instead of more opaquely
+DVS_HD float revised_opacity_logit(float logit) {
+    const float o = sigmoidf_(logit);
+    const float o2 = fminf(fmaxf(1.0f - sqrtf(1.0f - o), 1e-7f), 1.0f - 5.9604645e-8f);
+    return logitf_(o2);
+}
 // position of a split sample: mean + R diag(s) eps; its log-scale: log(s / 1.6)
 DVS_HD void adc_split_sample(const float mean[3], const float log_scale[3], const float quat[4], const float eps[3],
                              float out_mean[3], float out_log_scale[3]) {

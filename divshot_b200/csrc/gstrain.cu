@@ -210,6 +210,22 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     }
 }
 
+// `visibleAdam` (the "sparse Adam" of the 3DGS accelerations the closed trainer's flag is named after): only Gaussians the
+// current view saw (radius > 0) are stepped; the moments of the others are left untouched instead of decaying.
+__global__ void adam_visible_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                    float* __restrict__ v, size_t rows, int width, const int32_t* __restrict__ radii, float lr,
+                                    float b1, float b2, float eps, float c1, float c2) {
+    const size_t n = rows * (size_t)width;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        if (radii[i / (size_t)width] <= 0) continue;
+        const float gi = g[i];
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        p[i] -= lr * (mi * c1) / (sqrtf(vi * c2) + eps);
+    }
+}
+
 struct View {
     dvs_camera cam;
     float* d_target = nullptr;  // [3,H,W] device
@@ -344,9 +360,11 @@ struct GaussianTrainerImpl {
         cudaFree(d_accum); cudaFree(d_denom); cudaFree(d_mean2D); cudaFree(d_mean2D_abs); cudaFree(d_radii);
         d_accum = d_denom = d_mean2D = d_mean2D_abs = nullptr; d_radii = nullptr;
     }
+    bool want_radii = false;  // visibleAdam: the forward's radii are kept even outside the refinement window
     void allocate(int64_t cap) {  // arenas for `cap` Gaussians, zero-filled
         capacity = cap;
         params.alloc(capacity); grads.alloc(capacity); m1.alloc(capacity); m2.alloc(capacity);
+        if (want_radii && !refine_enabled) ck(cudaMalloc(&d_radii, capacity * sizeof(int32_t)), "cudaMalloc radii");
         if (refine_enabled) {  // refinement statistics and the buffers they are fed from
             ck(cudaMalloc(&d_accum, capacity * sizeof(float)), "cudaMalloc accum");
             ck(cudaMalloc(&d_denom, capacity * sizeof(float)), "cudaMalloc denom");
@@ -487,6 +505,7 @@ bool GaussianTrainerScene::loadTrainData(const std::string& path) {
             }
             I.capacity = plannedCapacity((int64_t)lo.size());
             I.refine_enabled = refinementPossible(config_);
+            I.want_radii = config_.visibleAdam;
             I.upload(means, ls, q, lo, sh0, shN);
             // target views on a ring, rendered from the ground truth with this rasterizer
             I.ensure_images((size_t)3 * W * H);
@@ -586,6 +605,7 @@ bool GaussianTrainerScene::loadTrainData(const std::string& path) {
             std::vector<float> shN((size_t)3 * KR * lo.size(), 0.f);
             I.capacity = plannedCapacity((int64_t)lo.size());
             I.refine_enabled = refinementPossible(config_);
+            I.want_radii = config_.visibleAdam;
             I.upload(means, ls, q, lo, sh0, shN);
         }
     } catch (const std::exception& e) {
@@ -655,7 +675,8 @@ void GaussianTrainerScene::trainStep() {
         if (config_.useAbsGrad) { G.mean2D_abs = I.d_mean2D_abs; bwd_flags |= DVS_FLAG_ABSGRAD; }
     }
     for (int attempt = 0;; attempt++) {
-        int rc = dvs_rast_forward(I.ctx, &cam, I.N, &P, I.d_render, (refining && !mcmc) ? I.d_radii : nullptr, I.stream);
+        const bool sparse_adam = config_.visibleAdam && I.d_radii;
+        int rc = dvs_rast_forward(I.ctx, &cam, I.N, &P, I.d_render, ((refining && !mcmc) || sparse_adam) ? I.d_radii : nullptr, I.stream);
         if (rc == DVS_E_OVERFLOW && attempt < 2) continue;
         ckr(rc, I.ctx, "forward");
         ck(cudaMemsetAsync(I.d_loss, 0, sizeof(float), I.stream), "memset loss");
@@ -682,16 +703,21 @@ void GaussianTrainerScene::trainStep() {
     const float lr_pos = std::exp((1.f - t) * std::log(config_.poslrInit) + t * std::log(config_.poslrFinal)) * I.scene_extent;
     const float b1 = 0.9f, b2 = 0.999f, eps = 1e-15f;
     const float c1 = 1.f / (1.f - std::pow(b1, (float)(step + 1))), c2 = 1.f / (1.f - std::pow(b2, (float)(step + 1)));
-    auto adam = [&](size_t off, size_t cnt, float lr) {
-        adam_kernel<<<1184, 256, 0, I.stream>>>(I.params.flat + off, I.grads.flat + off, I.m1.flat + off,
-                                                I.m2.flat + off, cnt, lr, b1, b2, eps, c1, c2);
+    const bool visible_only = config_.visibleAdam && I.d_radii;
+    auto adam = [&](size_t off, int width, float lr) {
+        if (visible_only)
+            adam_visible_kernel<<<1184, 256, 0, I.stream>>>(I.params.flat + off, I.grads.flat + off, I.m1.flat + off, I.m2.flat + off,
+                                                            (size_t)I.N, width, I.d_radii, lr, b1, b2, eps, c1, c2);
+        else
+            adam_kernel<<<1184, 256, 0, I.stream>>>(I.params.flat + off, I.grads.flat + off, I.m1.flat + off,
+                                                    I.m2.flat + off, (size_t)width * I.N, lr, b1, b2, eps, c1, c2);
     };
-    adam(I.params.off_means, 3 * I.N, lr_pos);
-    adam(I.params.off_scales, 3 * I.N, config_.scalinglr);
-    adam(I.params.off_quats, 4 * I.N, config_.rotationlr);
-    adam(I.params.off_opac, I.N, config_.opacitylr);
-    adam(I.params.off_sh0, 3 * I.N, config_.featurelr);
-    adam(I.params.off_shN, (size_t)3 * KR * I.N, config_.featurelr / 20.f);
+    adam(I.params.off_means, 3, lr_pos);
+    adam(I.params.off_scales, 3, config_.scalinglr);
+    adam(I.params.off_quats, 4, config_.rotationlr);
+    adam(I.params.off_opac, 1, config_.opacitylr);
+    adam(I.params.off_sh0, 3, config_.featurelr);
+    adam(I.params.off_shN, 3 * KR, config_.featurelr / 20.f);
     if (refining) {
         const uint64_t seed = 0x5DEECE66Dull * (uint64_t)(step + 1);
         if (mcmc)  // exploration noise after the optimizer step: Sigma eps gate(opacity) noiselr lr_xyz
@@ -704,7 +730,7 @@ void GaussianTrainerScene::trainStep() {
                                             config_.min_opacity, seed, I.stream, &I.last_report), "mcmc_refine");
             } else {
                 const dvs_densify::AdcConfig ac{config_.growGrad2d, 0.01f, I.scene_extent, config_.pruneOpacity,
-                                                config_.pruneScale3d};
+                                                config_.pruneScale3d, config_.revisedOpacity};
                 ck(dvs_densify::adc_refine(I.dws, I.T(I.params), I.T(I.m1), I.T(I.m2), I.d_accum, I.d_denom, &I.N,
                                            I.capacity, effectiveCapMax(config_), ac, seed, I.stream, &I.last_report), "adc_refine");
                 if (config_.resetAlphaEvery > 0 && step % config_.resetAlphaEvery == 0)

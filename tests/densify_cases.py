@@ -68,10 +68,10 @@ def _mcmc_refine(be, m, m1, m2, N, capacity, cap_max, min_opacity, seed):
     return P.get(), M1.get(), M2.get(), n.value, list(rep)
 
 
-def _adc_refine(be, m, m1, m2, accum, denom, N, capacity, cap_max, cfg, seed):
+def _adc_refine(be, m, m1, m2, accum, denom, N, capacity, cap_max, cfg, seed, revised=False):
     P, M1, M2 = _Dev(be, m), _Dev(be, m1), _Dev(be, m2)
     a, d = be.upload(accum), be.upload(denom)
-    c = (C.c_float * 5)(*cfg)
+    c = (C.c_float * 6)(*cfg, 1.0 if revised else 0.0)
     n, rep = C.c_longlong(N), (C.c_longlong * 6)()
     _ok(be.lib.dvs_densify_test_adc_refine(P.table, M1.table, M2.table, be.ptr(a), be.ptr(d), C.byref(n), capacity, cap_max, c, seed, rep, None))
     be.sync()
@@ -262,6 +262,23 @@ def case_adc_refine(be, ops):
     assert r["grown"] == 0
 
 
+def case_adc_revised_opacity(be, ops):
+    """`revisedOpacity`: both Gaussians a clone / split leaves carry 1 - sqrt(1 - o); everything else as without the flag."""
+    N, cap, seed = 4000, 8000, 99
+    before, accum, denom = _adc_model(N, cap, 4)
+    m1b, m2b = dr.moments_like(before, 2.0), dr.moments_like(before, 3.0)
+    split = _split_expect(ops, before, seed)
+    after, m1a, m2a, acc_a, den_a, N2, rep = _adc_refine(be, before, m1b, m2b, accum, denom, N, cap, 10 ** 9, CFG, seed, revised=True)
+    r = dr.check_adc_refine(before, after, m1b, m1a, m2b, m2a, accum, denom, acc_a, den_a, N, N2, cap, 10 ** 9, CFG, split, revised=True)
+    assert r["clones"] > 300 and r["splits"] > 50
+    plain, _, _, _, _, N3, _ = _adc_refine(be, before, m1b, m2b, accum, denom, N, cap, 10 ** 9, CFG, seed)
+    assert N3 == N2 and not np.array_equal(plain["opac"][:N2], after["opac"][:N2])
+    for k in ("means", "scales", "quats", "sh0", "shN"):
+        assert np.array_equal(plain[k][:N2], after[k][:N2]), k  # only the opacities differ
+    o = dr.sigmoid(before["opac"][:50]); o2 = dr.sigmoid(dr.revised_opacity_logit(before["opac"][:50]))
+    assert np.allclose(1 - (1 - o2) ** 2, o, atol=1e-6)  # the pair composites like the original
+
+
 def case_adc_edges(be, ops):
     N, cap, seed = 3000, 7000, 77
     before, accum, denom = _adc_model(N, cap, 6)
@@ -310,4 +327,4 @@ def case_adc_reset_opacity(be):
 
 CASES_PLAIN = (case_mcmc_relocation_of_the_dead, case_mcmc_growth, case_mcmc_both_phases_and_edges, case_mcmc_regularise,
                case_adc_accumulate, case_adc_reset_opacity)
-CASES_WITH_OPS = (case_mcmc_noise, case_adc_refine, case_adc_edges)
+CASES_WITH_OPS = (case_mcmc_noise, case_adc_refine, case_adc_edges, case_adc_revised_opacity)

@@ -141,8 +141,14 @@ def adc_actions(m, accum, denom, N, cfg):
     return act
 
 
+def revised_opacity_logit(logit):
+    """`revisedOpacity` (arXiv 2404.06109 eq. 9): each of the two Gaussians a clone / split leaves gets 1 - sqrt(1 - o)."""
+    o2 = 1.0 - np.sqrt(1.0 - sigmoid(logit))
+    return np.log(o2 / (1.0 - o2))
+
+
 def check_adc_refine(before, after, m1b, m1a, m2b, m2a, accum_b, denom_b, accum_a, denom_a, N, N_after, capacity,
-                     cap_max, cfg, split_expect=None):
+                     cap_max, cfg, split_expect=None, revised=False):
     """split_expect(i) -> (mean1, mean2, log_scale) of the two samples of split Gaussian i (from the host build of the
     same per-element code), or None to only check the scale."""
     act = adc_actions(before, accum_b, denom_b, N, cfg)
@@ -168,8 +174,12 @@ def check_adc_refine(before, after, m1b, m1a, m2b, m2a, accum_b, denom_b, accum_
         if pruned[i]:
             continue
         for r in rows_of[i]:
-            for k in ("sh0", "shN", "opac"):
+            for k in ("sh0", "shN"):
                 assert np.array_equal(after[k][r], before[k][i]), (k, i)
+            if revised and grow[i]:
+                assert abs(float(after["opac"][r]) - float(revised_opacity_logit(before["opac"][i]))) <= 2e-4 * max(1.0, abs(float(before["opac"][i]))), ("revised opacity", i)
+            else:
+                assert np.array_equal(after["opac"][r], before["opac"][i]), ("opac", i)
         if grow[i] and act[i] & ADC_SPLIT:
             for r in rows_of[i]:
                 assert np.allclose(after["scales"][r], before["scales"][i] - math.log(1.6), atol=1e-5), "split scale"
@@ -195,7 +205,7 @@ def check_adc_refine(before, after, m1b, m1a, m2b, m2a, accum_b, denom_b, accum_
                 splits=int((grow & ((act & ADC_SPLIT) != 0)).sum()))
 
 
-def emulate_adc_refine(m, m1, m2, accum, denom, N, capacity, cap_max, cfg, split_samples):
+def emulate_adc_refine(m, m1, m2, accum, denom, N, capacity, cap_max, cfg, split_samples, revised=False):
     """split_samples(i) -> (mean1, mean2, log_scale).  Same layout policy as the device code: appended elements at
     [N, N+n_grow), then holes below K filled from the tail in ascending order."""
     act = adc_actions(m, accum, denom, N, cfg)
@@ -208,6 +218,8 @@ def emulate_adc_refine(m, m1, m2, accum, denom, N, capacity, cap_max, cfg, split
         d = N + j
         for k in KEYS:
             m[k][d] = m[k][s]; m1[k][d] = 0; m2[k][d] = 0
+        if revised:
+            m["opac"][d] = m["opac"][s] = np.float32(revised_opacity_logit(m["opac"][s]))
         if act[s] & ADC_SPLIT:
             a, b, ls = split_samples(s)
             m["means"][d] = b; m["scales"][d] = ls

@@ -41,10 +41,11 @@ def test_trainer_refines_through_the_plugin_boundary(tmp_path):
     from divshot_b200 import build
     from test_plugin import LIB, _read_ply
     libs = build.build_all()
-    for strategy, expect_growth in (("1", True), ("0", None)):
-        out = str(tmp_path / f"refined_{strategy}.ply")
+    for strategy, expect_growth, extra in (("1", True, []), ("0", None, []), ("1", True, ["visibleAdam=1"]),
+                                           ("0", None, ["revisedOpacity=1", "visibleAdam=1"])):
+        out = str(tmp_path / f"refined_{strategy}_{len(extra)}.ply")
         r = subprocess.run([libs["gstrain_driver"], "synthetic:N=20000,W=320,H=240,views=4,deg=1", "600", out,
-                            "warmup=100", "refineEvery=100", "capMax=24000", "strategy=" + strategy],
+                            "warmup=100", "refineEvery=100", "capMax=24000", "strategy=" + strategy, *extra],
                            capture_output=True, text=True, env={**os.environ, "LD_LIBRARY_PATH": LIB}, timeout=600)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         n, props, rows = _read_ply(out)

@@ -3,7 +3,8 @@
 // save_splat_model -> delete_splat -> gstrain_destroy.  Used by tests/test_plugin.py on the GPU box, where the
 // reference sources (and therefore the real CLI build) may be absent.  Prints the loss trajectory.
 // Optional trailing key=value arguments set schedule fields the CLI takes as flags (main.cpp:19-70):
-// warmup= refineEvery= refineStop= resetAlphaEvery= capMax= strategy= (densifyStrategy: 0 ADC, 1 MCMC, 2 ADC+).
+// warmup= refineEvery= refineStop= resetAlphaEvery= capMax= strategy= (densifyStrategy: 0 ADC, 1 MCMC, 2 ADC+)
+// visibleAdam= revisedOpacity= (0 / 1).
 #include <dlfcn.h>
 
 #include <cstdio>
@@ -44,6 +45,8 @@ int main(int argc, char** argv) {
         else if (k == "resetAlphaEvery") cfg.resetAlphaEvery = v;
         else if (k == "capMax") cfg.capMax = v;
         else if (k == "strategy") cfg.densifyStrategy = v;
+        else if (k == "visibleAdam") cfg.visibleAdam = v != 0;
+        else if (k == "revisedOpacity") cfg.revisedOpacity = v != 0;
         else { std::fprintf(stderr, "unknown option %s\n", k.c_str()); return 6; }
     }
     auto* scene = (GaussianTrainerScene*)create(cfg, -1);
