@@ -24,6 +24,7 @@ struct Rasterizer : torch::CustomClassHolder {
     dvs_rast_ctx* ctx = nullptr;
     int64_t device = 0;
     std::vector<Tensor> saved;  // the six parameter tensors of the last forward (kept alive for backward)
+    int64_t last_h = 0, last_w = 0;
 
     explicit Rasterizer(int64_t dev) : device(dev) {
         TORCH_CHECK(dvs_rast_create((int)dev, &ctx) == DVS_OK,
@@ -66,6 +67,7 @@ struct Rasterizer : torch::CustomClassHolder {
         const int rc = dvs_rast_forward(ctx, &cam, N, &p, image.data_ptr<float>(), radii.data_ptr<int32_t>(), st);
         TORCH_CHECK(rc == DVS_OK, "dvs_rast_forward: ", dvs_rast_last_error(ctx));
         saved = {means3D, scales, quats, opacities, sh0, shN};
+        last_h = cam.height; last_w = cam.width;
         return {image, radii};
     }
 
@@ -87,6 +89,45 @@ struct Rasterizer : torch::CustomClassHolder {
         const int rc = dvs_rast_backward(ctx, &p, fptr(dl, "dL_dpix"), &gr, (uint32_t)flags, st);
         TORCH_CHECK(rc == DVS_OK, "dvs_rast_backward: ", dvs_rast_last_error(ctx));
         g.push_back(mean2D);  // screen-space gradient for the trainer's densification statistics
+        return g;
+    }
+
+    // Row F4 (dvs_rast_forward_aux / dvs_rast_backward_aux): depth / alpha [2,H,W] and normal [3,H,W] maps of the last forward
+    std::tuple<Tensor, Tensor> forward_aux() {
+        c10::cuda::CUDAGuard guard((c10::DeviceIndex)device);
+        TORCH_CHECK(saved.size() == 6, "forward_aux without forward");
+        TORCH_CHECK(last_h > 0 && last_w > 0, "forward_aux without forward");
+        auto opts = saved[0].options();
+        Tensor aux = torch::empty({2, last_h, last_w}, opts), normal = torch::empty({3, last_h, last_w}, opts);
+        dvs_params p{fptr(saved[0], "means3D"), fptr(saved[1], "scales"), fptr(saved[2], "quats"),
+                     fptr(saved[3], "opacities"), fptr(saved[4], "sh0"), fptr(saved[5], "shN")};
+        auto st = c10::cuda::getCurrentCUDAStream((c10::DeviceIndex)device).stream();
+        const int rc = dvs_rast_forward_aux(ctx, &p, aux.data_ptr<float>(), normal.data_ptr<float>(), st);
+        TORCH_CHECK(rc == DVS_OK, "dvs_rast_forward_aux: ", dvs_rast_last_error(ctx));
+        return {aux, normal};
+    }
+    // gradients of <image, dL_dpix> + <depth/alpha, dL_daux> + <normal, dL_dnormal>; an undefined / empty tensor = that loss is absent
+    std::vector<Tensor> backward_aux(const Tensor& dL_dpix, const Tensor& dL_daux, const Tensor& dL_dnormal, int64_t flags) {
+        c10::cuda::CUDAGuard guard((c10::DeviceIndex)device);
+        TORCH_CHECK(saved.size() == 6, "backward without forward");
+        std::vector<Tensor> g;
+        for (auto& t : saved) g.push_back(torch::empty_like(t));
+        Tensor mean2D = torch::empty({saved[0].size(0), 2}, saved[0].options());
+        dvs_params p{fptr(saved[0], "means3D"), fptr(saved[1], "scales"), fptr(saved[2], "quats"),
+                     fptr(saved[3], "opacities"), fptr(saved[4], "sh0"), fptr(saved[5], "shN")};
+        dvs_grads gr{};
+        gr.means3D = g[0].data_ptr<float>(); gr.scales = g[1].data_ptr<float>(); gr.quats = g[2].data_ptr<float>();
+        gr.opacities = g[3].data_ptr<float>(); gr.sh0 = g[4].data_ptr<float>();
+        gr.shN = g[5].numel() ? g[5].data_ptr<float>() : nullptr;
+        gr.mean2D = mean2D.data_ptr<float>();
+        Tensor dl = dL_dpix.contiguous();
+        Tensor da = dL_daux.defined() && dL_daux.numel() ? dL_daux.contiguous() : Tensor();
+        Tensor dn = dL_dnormal.defined() && dL_dnormal.numel() ? dL_dnormal.contiguous() : Tensor();
+        auto st = c10::cuda::getCurrentCUDAStream((c10::DeviceIndex)device).stream();
+        const int rc = dvs_rast_backward_aux(ctx, &p, fptr(dl, "dL_dpix"), da.defined() ? fptr(da, "dL_daux") : nullptr,
+                                             dn.defined() ? fptr(dn, "dL_dnormal") : nullptr, &gr, (uint32_t)flags, st);
+        TORCH_CHECK(rc == DVS_OK, "dvs_rast_backward_aux: ", dvs_rast_last_error(ctx));
+        g.push_back(mean2D);
         return g;
     }
 
@@ -117,6 +158,35 @@ struct RasterizeFn : torch::autograd::Function<RasterizeFn> {
     }
 };
 
+// autograd bridge with the auxiliary maps: image, radii, depth_alpha [2,H,W], normal [3,H,W] = dvs::rasterize_aux(...)
+struct RasterizeAuxFn : torch::autograd::Function<RasterizeAuxFn> {
+    static torch::autograd::variable_list forward(torch::autograd::AutogradContext* actx,
+                                                  const c10::intrusive_ptr<Rasterizer>& r, const Tensor& camera,
+                                                  const Tensor& means3D, const Tensor& scales, const Tensor& quats,
+                                                  const Tensor& opacities, const Tensor& sh0, const Tensor& shN) {
+        auto out = r->forward(camera, means3D.contiguous(), scales.contiguous(), quats.contiguous(),
+                              opacities.contiguous(), sh0.contiguous(), shN.contiguous());
+        auto aux = r->forward_aux();
+        actx->saved_data["rast"] = r;
+        actx->mark_non_differentiable({std::get<1>(out)});
+        return {std::get<0>(out), std::get<1>(out), std::get<0>(aux), std::get<1>(aux)};
+    }
+    static torch::autograd::variable_list backward(torch::autograd::AutogradContext* actx,
+                                                   torch::autograd::variable_list grad_out) {
+        auto r = actx->saved_data["rast"].toCustomClass<Rasterizer>();
+        Tensor dpix = grad_out[0].defined() ? grad_out[0] : torch::zeros({3, r->last_h, r->last_w}, r->saved[0].options());
+        auto g = r->backward_aux(dpix, grad_out[2], grad_out[3], 0);
+        return {Tensor(), Tensor(), g[0], g[1], g[2], g[3], g[4], g[5]};
+    }
+};
+
+std::tuple<Tensor, Tensor, Tensor, Tensor> rasterize_aux(const c10::intrusive_ptr<Rasterizer>& r, const Tensor& camera,
+                                                         const Tensor& means3D, const Tensor& scales, const Tensor& quats,
+                                                         const Tensor& opacities, const Tensor& sh0, const Tensor& shN) {
+    auto out = RasterizeAuxFn::apply(r, camera, means3D, scales, quats, opacities, sh0, shN);
+    return {out[0], out[1], out[2], out[3]};
+}
+
 std::tuple<Tensor, Tensor> rasterize(const c10::intrusive_ptr<Rasterizer>& r, const Tensor& camera,
                                      const Tensor& means3D, const Tensor& scales, const Tensor& quats,
                                      const Tensor& opacities, const Tensor& sh0, const Tensor& shN) {
@@ -129,11 +199,21 @@ TORCH_LIBRARY(dvs, m) {
         .def(torch::init<int64_t>())
         .def("forward", &Rasterizer::forward)
         .def("backward", &Rasterizer::backward)
+        .def("forward_aux", &Rasterizer::forward_aux)
+        .def("backward_aux", &Rasterizer::backward_aux)
         .def("stats", &Rasterizer::stats);
     m.def("rasterize(__torch__.torch.classes.dvs.Rasterizer r, Tensor camera, Tensor means3D, Tensor scales, "
           "Tensor quats, Tensor opacities, Tensor sh0, Tensor shN) -> (Tensor, Tensor)");
+    m.def("rasterize_aux(__torch__.torch.classes.dvs.Rasterizer r, Tensor camera, Tensor means3D, Tensor scales, "
+          "Tensor quats, Tensor opacities, Tensor sh0, Tensor shN) -> (Tensor, Tensor, Tensor, Tensor)");
 }
-TORCH_LIBRARY_IMPL(dvs, Autograd, m) { m.impl("rasterize", &rasterize); }
-TORCH_LIBRARY_IMPL(dvs, CUDA, m) { m.impl("rasterize", &rasterize); }
+TORCH_LIBRARY_IMPL(dvs, Autograd, m) {
+    m.impl("rasterize", &rasterize);
+    m.impl("rasterize_aux", &rasterize_aux);
+}
+TORCH_LIBRARY_IMPL(dvs, CUDA, m) {
+    m.impl("rasterize", &rasterize);
+    m.impl("rasterize_aux", &rasterize_aux);
+}
 
 }  // namespace dvs
