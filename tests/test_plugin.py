@@ -46,6 +46,21 @@ def test_reference_splatx_cli_builds_unmodified_against_our_header():
     assert out.returncode == 0 and "--inputPath" in out.stdout and "--maxIteration" in out.stdout
 
 
+def test_libtorch_library_loads_and_registers_both_operators():
+    """csrc/torch_binding.cpp: the library loads without a GPU, registers dvs::rasterize and dvs::rasterize_aux and the custom
+    class; constructing a Rasterizer without CUDA fails loudly (no CPU path)."""
+    import torch
+    libs = _build()
+    torch.classes.load_library(libs["libdvs_torch"])
+    s1 = [str(x) for x in torch._C._jit_get_schemas_for_operator("dvs::rasterize")]
+    s2 = [str(x) for x in torch._C._jit_get_schemas_for_operator("dvs::rasterize_aux")]
+    assert len(s1) == 1 and s1[0].endswith("-> (Tensor, Tensor)")
+    assert len(s2) == 1 and s2[0].endswith("-> (Tensor, Tensor, Tensor, Tensor)")
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            torch.classes.dvs.Rasterizer(0)
+
+
 def test_plugin_fails_loudly_without_cuda():
     import torch
     if torch.cuda.is_available():
