@@ -390,6 +390,50 @@ int write_spz(const std::string& path, const Cloud& c, uint32_t flags) {
 }
 
 // ---------------------------------------------------------------------------------------------- readers
+// Reduced PLY as GaussianModel::save_to_file reaches it (gaussian_model.cpp:445-448: the codebook / quantised / half-float
+// arguments keep their defaults, tiny_gsplat.hpp:625-636), i.e. the float branch of tiny_gsplat.cpp:398-630: the Gaussians
+// are grouped by SH degree into four `element vertex` blocks (input order inside a block) and a row of degree d is
+//   pos[3] | f_dc[3] | f_rest[3 ((d+1)^2 - 1)] | opacity | scale[3] | rot[4]        (all float32)
+// Quirk Q8, reproduced for byte parity: coefficient j is copied from &shs_n[i][j] — the 12 bytes starting at FLOAT j of the
+// 45-float row, i.e. the overlapping window [j, j+2] instead of [3j, 3j+2] (tiny_gsplat.cpp:533-534); the reader returns
+// exactly those windows.  DVS_IO_REDUCED_SH_FIXED writes the intended coefficients.
+int write_reduced_ply(const std::string& path, const Cloud& c, uint32_t flags) {
+    std::vector<int64_t> ids[4];
+    for (int64_t i = 0; i < c.N; i++) {
+        const int d = c.deg ? c.deg[i] : 3;
+        if (d >= 0 && d <= 3) ids[d].push_back(i);  // other degree values are in no block (as in the reference)
+    }
+    std::string h = "ply\nformat binary_little_endian 1.0\ncomment generated by diverseshot\n";
+    size_t bytes = 0;
+    for (int d = 0; d < 4; d++) {
+        const int coeffs = (d + 1) * (d + 1) - 1;
+        h += "element vertex " + std::to_string(ids[d].size()) + "\nproperty float x\nproperty float y\nproperty float z\n";
+        h += "property float f_dc_0\nproperty float f_dc_1\nproperty float f_dc_2\n";
+        for (int j = 0; j < coeffs; j++)
+            for (int ch = 0; ch < 3; ch++) h += "property float f_rest_" + std::to_string(3 * j + ch) + "\n";
+        h += "property float opacity\nproperty float scale_0\nproperty float scale_1\nproperty float scale_2\n";
+        h += "property float rot_0\nproperty float rot_1\nproperty float rot_2\nproperty float rot_3\n";
+        bytes += ids[d].size() * static_cast<size_t>(4 * (3 + 3 + 3 * coeffs + 1 + 3 + 4));
+    }
+    h += "end_header\n";
+    std::vector<float> body(bytes / 4);
+    float* w = body.data();
+    for (int d = 0; d < 4; d++) {
+        const int coeffs = (d + 1) * (d + 1) - 1;
+        for (const int64_t i : ids[d]) {
+            std::memcpy(w, c.pos + 3 * i, 12); w += 3;
+            std::memcpy(w, c.sh0 + 3 * i, 12); w += 3;
+            const float* rest = c.shN + 45 * i;
+            for (int j = 0; j < coeffs; j++, w += 3)
+                std::memcpy(w, (flags & DVS_IO_REDUCED_SH_FIXED) ? rest + 3 * j : rest + j, 12);
+            *w++ = c.opac[i];
+            std::memcpy(w, c.scale + 3 * i, 12); w += 3;
+            std::memcpy(w, c.rot + 4 * i, 16); w += 4;
+        }
+    }
+    return flush(path, h, reinterpret_cast<const uint8_t*>(body.data()), bytes) ? 0 : fail("cannot write " + path);
+}
+
 bool slurp(const std::string& path, std::vector<uint8_t>* out) {
     std::ifstream in(path, std::ios::binary | std::ios::ate);
     if (!in.good()) return false;
@@ -639,6 +683,79 @@ int64_t read_spz(const std::vector<uint8_t>& gz, float* rows, int64_t cap, uint3
     return static_cast<int64_t>(N);
 }
 
+// tiny_gsplat.cpp:817-992 (load_reduced_ply), float and half-float positions.  The header is read the way the reference
+// reads it: every `element vertex` line opens the next degree block, the line after it tells f16 from float positions, a
+// one-byte property type means a codebook-quantised file (written only by callers that pass a codebook; not supported).
+// Rows come back block by block (degree 0 first); coefficients a degree does not store stay 0.
+int64_t read_reduced_ply(const std::vector<uint8_t>& f, float* rows, int64_t cap) {
+    uint64_t count[4] = {0, 0, 0, 0};
+    int blocks = 0;
+    bool half = false, quantised = false;
+    size_t p = 0, body = 0;
+    bool after_element = false;
+    while (p < f.size()) {
+        const uint8_t* nl = static_cast<const uint8_t*>(std::memchr(f.data() + p, '\n', f.size() - p));
+        if (!nl) break;
+        const std::string line(reinterpret_cast<const char*>(f.data() + p), static_cast<size_t>(nl - (f.data() + p)));
+        p = static_cast<size_t>(nl - f.data()) + 1;
+        if (line == "end_header") { body = p; break; }
+        if (after_element) {
+            if (line.find("f16") != std::string::npos) half = true;
+            after_element = false;
+        }
+        if (line.find("element vertex") != std::string::npos) {
+            if (blocks >= 4) return fail("reduced PLY: more than four vertex blocks");
+            std::istringstream ss(line);
+            std::string a, b;
+            ss >> a >> b >> count[blocks++];
+            after_element = true;
+        }
+        if (line.find("property") != std::string::npos && blocks > 0) {
+            std::istringstream ss(line);
+            std::string a, type;
+            ss >> a >> type;
+            if (type == "u8") quantised = true;
+            else if (type != "float" && type != "uint" && type != "f16") return fail("reduced PLY: unrecognized type " + type);
+        }
+    }
+    if (!body) return fail("reduced PLY: no end_header");
+    if (blocks != 4) return fail("reduced PLY: expected four vertex blocks (one per SH degree)");
+    if (quantised) return fail("reduced PLY: codebook-quantised files are not supported");
+    const int64_t n = static_cast<int64_t>(count[0] + count[1] + count[2] + count[3]);
+    if (n <= 0) return fail("reduced PLY: no vertices");
+    const size_t xyz = half ? 6 : 12;
+    size_t need = 0;
+    for (int d = 0; d < 4; d++) need += count[d] * (xyz + 12 + 12 * ((d + 1) * (d + 1) - 1) + 4 + 12 + 16);
+    if (f.size() - body < need) return fail("reduced PLY: truncated payload");
+    if (!rows) return n;
+    const uint8_t* src = f.data() + body;
+    int64_t i = 0;
+    for (int d = 0; d < 4; d++) {
+        const int coeffs = (d + 1) * (d + 1) - 1;
+        const size_t stride = xyz + 12 + 12 * static_cast<size_t>(coeffs) + 4 + 12 + 16;
+        for (uint64_t k = 0; k < count[d]; k++, i++, src += stride) {
+            if (i >= cap) continue;
+            float* r = rows + i * kRow;
+            for (int a = 0; a < kRow; a++) r[a] = 0.f;
+            if (half) {
+                for (int a = 0; a < 3; a++) {
+                    uint16_t hv;
+                    std::memcpy(&hv, src + 2 * a, 2);
+                    r[a] = half_to_float(hv);
+                }
+            } else {
+                std::memcpy(r, src, 12);
+            }
+            std::memcpy(r + 3, src + xyz, 12 + 12 * static_cast<size_t>(coeffs));  // f_dc, then the stored coefficients in order
+            const uint8_t* t = src + xyz + 12 + 12 * static_cast<size_t>(coeffs);
+            std::memcpy(r + kRowOpacity, t, 4);
+            std::memcpy(r + kRowScale, t + 4, 12);
+            std::memcpy(r + kRowRot, t + 16, 16);
+        }
+    }
+    return n;
+}
+
 bool ends_with(const std::string& s, const char* suf) {
     const size_t n = std::strlen(suf);
     return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
@@ -651,7 +768,10 @@ extern "C" {
 DVS_API int dvs_model_format_from_path(const char* path) {
     if (!path) return 0;
     const std::string p(path);
-    if (ends_with(p, ".ply")) return p.find(".compressed") != std::string::npos ? DVS_FMT_COMPRESSED_PLY : DVS_FMT_PLY;
+    if (ends_with(p, ".ply")) {  // gaussian_model.cpp:439-451: ".compressed" is looked for first, then ".reduced"
+        if (p.find(".compressed") != std::string::npos) return DVS_FMT_COMPRESSED_PLY;
+        return p.find(".reduced") != std::string::npos ? DVS_FMT_REDUCED_PLY : DVS_FMT_PLY;
+    }
     if (ends_with(p, ".splat")) return DVS_FMT_SPLAT;
     if (ends_with(p, ".dvsplat")) return DVS_FMT_DVSPLAT;
     if (ends_with(p, ".spz")) return DVS_FMT_SPZ;
@@ -673,6 +793,7 @@ DVS_API int dvs_model_write(const char* path, int format, int64_t N, const float
         case DVS_FMT_COMPRESSED_PLY: return write_compressed_ply(path, c, flags);
         case DVS_FMT_DVSPLAT: return write_dvsplat(path, c);
         case DVS_FMT_SPZ: return write_spz(path, c, flags);
+        case DVS_FMT_REDUCED_PLY: return write_reduced_ply(path, c, flags);
         default: return fail(std::string("dvs_model_write: unknown model format for ") + path);
     }
 }
@@ -692,6 +813,7 @@ DVS_API int64_t dvs_model_read(const char* path, int format, float* rows, int64_
         case DVS_FMT_COMPRESSED_PLY: n = read_compressed_ply(f, rows, cap, &flags); break;
         case DVS_FMT_DVSPLAT: n = read_dvsplat(f, rows, cap); break;
         case DVS_FMT_SPZ: n = read_spz(f, rows, cap, &flags); break;
+        case DVS_FMT_REDUCED_PLY: n = read_reduced_ply(f, rows, cap); break;
         default: return fail(std::string("dvs_model_read: unknown model format for ") + path);
     }
     if (flags_out) *flags_out = flags;

@@ -8,6 +8,7 @@
  *                                                 save_spz_splats and the matching load_* functions
  *   external/tinygsplat/tiny_gsplat.cpp:168-241   PLY            :243-291  .splat      :293-395  compressed PLY
  *                                      :994-1117  .dvsplat       :1243-1272 .spz (-> external/spz/src/load-spz.cc)
+ *                                      :398-630   reduced PLY (float rows) and its reader :817-992
  *   diverse/source/assets/gaussian_model.cpp:439-463   dispatch by file extension (mirrored by DVS_FMT_AUTO)
  *
  * Parity: byte-identical files to the reference writers and value-identical rows to the reference readers, checked
@@ -28,17 +29,24 @@ extern "C" {
 #endif
 
 typedef enum dvs_model_format {
-    DVS_FMT_AUTO = 0,           /* by path: ".compressed" + .ply -> 3, .ply -> 1, .splat -> 2, .dvsplat -> 4, .spz -> 5 */
+    DVS_FMT_AUTO = 0,           /* by path: ".compressed" + .ply -> 3, ".reduced" + .ply -> 6, .ply -> 1, .splat -> 2,
+                                   .dvsplat -> 4, .spz -> 5 */
     DVS_FMT_PLY = 1,            /* 59 raw floats per vertex: x y z f_dc_0..2 f_rest_0..44 (channel-major) opacity scale_0..2 rot_0..3 */
     DVS_FMT_SPLAT = 2,          /* 32-byte records: pos f32x3, exp(scale) f32x3, RGBA u8x4, quaternion u8x4 */
     DVS_FMT_COMPRESSED_PLY = 3, /* 256-splat chunks in Morton order: 12 bound floats per chunk + 4 packed u32 per splat */
     DVS_FMT_DVSPLAT = 4,        /* 28-byte header, chunked 11-10-11 positions, u8-quantised attributes per SH degree block */
-    DVS_FMT_SPZ = 5             /* Niantic .spz v3 (gzip): 24-bit fixed-point positions, smallest-three quaternions */
+    DVS_FMT_SPZ = 5,            /* Niantic .spz v3 (gzip): 24-bit fixed-point positions, smallest-three quaternions */
+    DVS_FMT_REDUCED_PLY = 6     /* ".reduced" + .ply: four vertex elements, one per SH degree, each row holding only the
+                                   coefficients its degree uses (float rows: what the reference's dispatch writes) */
 } dvs_model_format;
 
 #define DVS_IO_ANTIALIASED 1u   /* model was trained with mip anti-aliasing (header comment / spz flag bit) */
 #define DVS_IO_SPZ_SH_FIXED 2u  /* write: index the .spz SH block as [p][15][3] instead of the reference's overlapping
                                    [p*15+j+c] (tiny_gsplat.cpp:1262-1267).  Default (flag clear) = reference bytes. */
+
+#define DVS_IO_REDUCED_SH_FIXED 4u /* write: coefficient j of a reduced-PLY row = shN[j][0..2]; default (flag clear) = the
+                                   reference's bytes, which copy the overlapping window shN_flat[j..j+2]
+                                   (tiny_gsplat.cpp:533-534) */
 
 #define DVS_IO_ROW_FLOATS 59    /* reader row = the reference's RichPoint: pos[3] shs[48] opacity scale[3] rot[4] */
 

@@ -67,7 +67,8 @@ void call_reference_load_ply(const std::string& p, std::vector<tinygsplat::RichP
 
 extern "C" {
 
-// format: 1 ply, 2 splat, 3 compressed ply, 4 dvsplat, 5 spz (same numbering as include/dvs_model_io.h)
+// format: 1 ply, 2 splat, 3 compressed ply, 4 dvsplat, 5 spz, 6 reduced ply (same numbering as include/dvs_model_io.h);
+// 7 = the reduced-PLY writer with halfFloat = true (not reachable from the reference's dispatch; feeds the reader test)
 __attribute__((visibility("default"))) int ref_save(int format, const char* path, long long N, const float* pos,
                                                     const float* sh0, const float* shn, const float* opac,
                                                     const float* scales, const float* rot, const uint8_t* degrees,
@@ -81,6 +82,8 @@ __attribute__((visibility("default"))) int ref_save(int format, const char* path
         case 3: ok = tinygsplat::save_compress_ply(p, c.pos, c.scales, c.shs, c.rot, c.opac, antialiased != 0); break;
         case 4: ok = tinygsplat::save_dvs_splat(p, c.pos, c.scales, c.sh0, c.shn, c.rot, c.opac, c.degrees); break;
         case 5: ok = tinygsplat::save_spz_splats(p, c.pos, c.scales, c.shs, c.rot, c.opac, antialiased != 0); break;
+        case 6: ok = tinygsplat::save_reduced_ply(p, c.pos, c.scales, c.sh0, c.shn, c.rot, c.opac, c.degrees); break;  // gaussian_model.cpp:447
+        case 7: ok = tinygsplat::save_reduced_ply(p, c.pos, c.scales, c.sh0, c.shn, c.rot, c.opac, c.degrees, {}, false, true); break;
         default: return -2;
     }
     return ok ? 0 : -1;
@@ -100,6 +103,7 @@ __attribute__((visibility("default"))) long long ref_load(int format, const char
         case 3: (void)tinygsplat::load_compress_ply(p, pts, aa); break;
         case 4: (void)tinygsplat::load_dvs_splat(p, pts); break;
         case 5: (void)tinygsplat::load_spz_splats(p, pts, aa); break;
+        case 6: case 7: (void)tinygsplat::load_reduced_ply(p, pts); break;
         default: return -2;
     }
     if (antialiased) *antialiased = aa ? 1 : 0;

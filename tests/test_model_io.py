@@ -19,7 +19,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libtinygsplat_ref.so")
 GOLDEN = os.path.join(ROOT, "tests", "golden", "model_io.json")
-FORMATS = {1: "model.ply", 2: "model.splat", 3: "model.compressed.ply", 4: "model.dvsplat", 5: "model.spz"}
+FORMATS = {1: "model.ply", 2: "model.splat", 3: "model.compressed.ply", 4: "model.dvsplat", 5: "model.spz",
+           6: "model.reduced.ply"}
 ROW = 59
 
 
@@ -119,6 +120,47 @@ def test_dvsplat_with_mixed_sh_degrees_equals_the_reference(ours, ref, tmp_path)
     assert open(a, "rb").read() == open(b, "rb").read()
 
 
+@pytest.mark.parametrize("N,seed", [(5000, 12), (3, 13), (257, 14)])
+def test_reduced_ply_with_mixed_sh_degrees_equals_the_reference(ours, ref, tmp_path, N, seed):
+    """Four per-degree vertex blocks (some possibly empty), rows of different widths; writer bytes, reader rows, and the
+    reader on the half-float-position variant only the reference writer can produce (tiny_gsplat.cpp:398-630, 817-992)."""
+    c = make_cloud(N, seed, "mixed")
+    a, b, h = (str(tmp_path / n) for n in ("a.reduced.ply", "b.reduced.ply", "h.reduced.ply"))
+    write_ours(ours, 6, a, c)
+    write_ref(ref, 6, b, c)
+    assert open(a, "rb").read() == open(b, "rb").read()
+    mine, _ = read_ours(ours, 6, b)
+    theirs, _ = read_ref(ref, 6, b, N)
+    assert np.array_equal(mine.view(np.uint32), theirs.view(np.uint32))
+    write_ref(ref, 7, h, c)  # format 7 of the shim: the same writer with halfFloat = true
+    mine, _ = read_ours(ours, 6, h)
+    theirs, _ = read_ref(ref, 7, h, N)
+    assert np.array_equal(mine.view(np.uint32), theirs.view(np.uint32))
+
+
+def test_reduced_ply_layout_and_the_fixed_sh_variant(ours, tmp_path):
+    """Without the reference: rows are grouped by degree in input order; the default writer reproduces the reference's
+    overlapping SH windows (quirk Q8: coefficient j = floats j..j+2 of the 45-float row), DVS_IO_REDUCED_SH_FIXED writes the
+    coefficients themselves and then the round trip is lossless for every coefficient a degree stores."""
+    c = make_cloud(900, 15, "mixed")
+    order = np.concatenate([np.flatnonzero(c["deg"] == d) for d in range(4)])
+    flat = c["shn"].reshape(-1, 45)
+    for flags, window in ((0, lambda i, j: flat[i, j:j + 3]), (4, lambda i, j: flat[i, 3 * j:3 * j + 3])):
+        p = str(tmp_path / f"m{flags}.reduced.ply")
+        write_ours(ours, 6, p, c, flags=flags)
+        r, _ = read_ours(ours, 0, p)  # DVS_FMT_AUTO picks the reduced reader from the name
+        assert r.shape[0] == 900
+        assert np.array_equal(r[:, :3], c["pos"][order]) and np.array_equal(r[:, 3:6], c["sh0"][order])
+        assert np.array_equal(r[:, 51], c["opac"][order]) and np.array_equal(r[:, 52:55], c["scale"][order])
+        assert np.array_equal(r[:, 55:], c["rot"][order])
+        for row, i in enumerate(order[::37]):
+            k = (int(c["deg"][i]) + 1) ** 2 - 1
+            got = r[row * 37, 6:51].reshape(15, 3)
+            assert all(np.array_equal(got[j], window(i, j)) for j in range(k)) and not got[k:].any()
+    head = open(p, "rb").read().split(b"end_header\n")[0]
+    assert head.count(b"element vertex") == 4 and b"comment generated by diverseshot" in head
+
+
 def test_degenerate_extents_and_extreme_values_equal_the_reference(ours, ref, tmp_path):
     """A planar cloud (zero extent in z: NaN Morton cell in the reference), saturating colours / opacities / scales,
     quaternions with negative and tied largest components, duplicate positions (equal Morton codes)."""
@@ -207,6 +249,7 @@ def test_auto_format_dispatch_and_errors(ours, tmp_path):
     f = ours.dvs_model_format_from_path
     assert f(b"/x/a.ply") == 1 and f(b"a.compressed.ply") == 3 and f(b"a.splat") == 2
     assert f(b"a.dvsplat") == 4 and f(b"a.spz") == 5 and f(b"a.obj") == 0 and f(None) == 0
+    assert f(b"a.reduced.ply") == 6 and f(b"a.reduced.compressed.ply") == 3  # ".compressed" is looked for first
     c = make_cloud(10, 1)
     rc = ours.dvs_model_write(str(tmp_path / "a.obj").encode(), 0, 10, _p(c["pos"]), _p(c["sh0"]), _p(c["shn"]),
                               _p(c["opac"]), _p(c["scale"]), _p(c["rot"]), None, 0)
