@@ -483,7 +483,7 @@ int64_t read_ply(const std::vector<uint8_t>& f, float* rows, int64_t cap, uint32
     if (h.antialiased) *flags |= DVS_IO_ANTIALIASED;
     const int64_t n = static_cast<int64_t>(h.vertices);
     if (n <= 0) return fail("PLY: no vertices");
-    if (f.size() - h.body < static_cast<size_t>(n) * h.stride) return fail("PLY: truncated payload");
+    if (h.stride == 0 || static_cast<uint64_t>(n) > (f.size() - h.body) / h.stride) return fail("PLY: truncated payload");  // (no product: a forged count cannot wrap it)
     if (!rows) return n;
     auto field = [&](const char* name) -> int64_t {
         auto it = h.offset.find(name);
@@ -543,7 +543,8 @@ int64_t read_compressed_ply(const std::vector<uint8_t>& f, float* rows, int64_t 
     if (h.antialiased) *flags |= DVS_IO_ANTIALIASED;
     const size_t N = h.vertices, chunks = h.chunks;
     if (N == 0 || chunks == 0) return fail("compressed PLY: no chunks / vertices");
-    if (f.size() - h.body < chunks * 48 + N * 16) return fail("compressed PLY: truncated payload");
+    if (N > (f.size() - h.body) / 16 || chunks > (f.size() - h.body) / 48 || f.size() - h.body < chunks * 48 + N * 16)
+        return fail("compressed PLY: truncated payload");
     if (!rows) return static_cast<int64_t>(N);
     const uint8_t* body = f.data() + h.body;
     const double inv_norm = 1.0 / (std::sqrt(2.0) * 0.5);
@@ -725,7 +726,11 @@ int64_t read_reduced_ply(const std::vector<uint8_t>& f, float* rows, int64_t cap
     if (n <= 0) return fail("reduced PLY: no vertices");
     const size_t xyz = half ? 6 : 12;
     size_t need = 0;
-    for (int d = 0; d < 4; d++) need += count[d] * (xyz + 12 + 12 * ((d + 1) * (d + 1) - 1) + 4 + 12 + 16);
+    for (int d = 0; d < 4; d++) {
+        const size_t stride = xyz + 12 + 12 * static_cast<size_t>((d + 1) * (d + 1) - 1) + 4 + 12 + 16;
+        if (count[d] > (f.size() - body) / stride) return fail("reduced PLY: truncated payload");  // also keeps `need` from wrapping
+        need += static_cast<size_t>(count[d]) * stride;
+    }
     if (f.size() - body < need) return fail("reduced PLY: truncated payload");
     if (!rows) return n;
     const uint8_t* src = f.data() + body;

@@ -31,7 +31,7 @@ def _p(a):
 @pytest.fixture(scope="module")
 def ours():
     from divshot_b200 import build
-    lib = C.CDLL(build.build_gstrain())
+    lib = C.CDLL(os.environ.get("DVS_MODEL_IO_LIB") or build.build_gstrain())  # tools/fuzz_model_io.sh points this at a sanitizer build
     lib.dvs_model_read.restype = C.c_int64
     lib.dvs_model_read.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
     lib.dvs_model_write.argtypes = [C.c_char_p, C.c_int, C.c_int64] + [C.c_void_p] * 7 + [C.c_uint32]
@@ -290,3 +290,35 @@ def test_writers_match_the_committed_reference_digests(ours, tmp_path):
             path = str(tmp_path / FORMATS[int(fmt_s)])
             write_ours(ours, int(fmt_s), path, c, flags=case["aa"])
             assert hashlib.sha256(open(path, "rb").read()).hexdigest() == digest, (case, fmt_s)
+
+
+def test_readers_reject_forged_counts_and_damaged_files(ours, tmp_path):
+    """Readers face files from anywhere (the viewer opens what the user drops on it): a header whose vertex count would wrap
+    the size computation, truncations and random damage must end in an error or a bounded read, never outside the file
+    (this test is also run under AddressSanitizer when the readers change: tools/fuzz_model_io.sh)."""
+    c = make_cloud(300, 71, "mixed")
+    rng = np.random.default_rng(5)
+    for fmt, name in FORMATS.items():
+        p = str(tmp_path / name)
+        write_ours(ours, fmt, p, c)
+        good = open(p, "rb").read()
+        if fmt in (1, 3, 6):  # text headers: forge the count
+            for forged in (b"18446744073709551615", b"4611686018427387904", b"99999999999"):
+                bad = good.replace(b"element vertex 300", b"element vertex " + forged, 1) if fmt != 6 else \
+                    good.replace(b"element vertex ", b"element vertex " + forged[:-1], 1)
+                q = str(tmp_path / ("forged_" + name))
+                open(q, "wb").write(bad)
+                assert ours.dvs_model_read(q.encode(), fmt, None, 0, None) < 0, (name, forged)
+        for trial in range(40):
+            b = bytearray(good)
+            if trial % 2:
+                b = b[:int(rng.integers(0, len(b)))]
+            else:
+                for _ in range(int(rng.integers(1, 12))):
+                    b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+            q = str(tmp_path / ("damaged_" + name))
+            open(q, "wb").write(bytes(b))
+            n = ours.dvs_model_read(q.encode(), fmt, None, 0, None)
+            if 0 < n <= 100000:
+                rows = np.zeros((n, ROW), np.float32)
+                assert ours.dvs_model_read(q.encode(), fmt, _p(rows), n, None) in (n, -1)
