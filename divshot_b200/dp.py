@@ -129,8 +129,11 @@ class FactoredGradientExchange:
         N = grads.opacities.shape[0]
         self.N = N
         off = lambda t: (t.data_ptr() - flat.data_ptr()) // 4  # noqa: E731
+        if grads.shN.numel() == 0:
+            raise ValueError("FactoredGradientExchange: no higher SH bands (degree 0), nothing to factor out")
         # arena order: quats | shN | means3D | scales | sh0 | opacities (rasterizer.GradBuffers.allocate)
-        assert off(grads.quats) < off(grads.shN) < off(grads.means3D) < off(grads.scales) < off(grads.sh0) < off(grads.opacities)
+        if not (off(grads.quats) < off(grads.shN) < off(grads.means3D) < off(grads.scales) < off(grads.sh0) < off(grads.opacities)):
+            raise ValueError("FactoredGradientExchange: unexpected gradient arena layout")
         self.range_a = flat[off(grads.quats):off(grads.quats) + 4 * N]
         self.range_b = flat[off(grads.means3D):off(grads.opacities) + N]
         self.dsh0_all = torch.zeros(self.world, N, 3, dtype=torch.float32, device=flat.device)

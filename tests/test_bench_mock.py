@@ -92,3 +92,66 @@ def test_row_harnesses_report_failure_as_text_without_a_gpu():
     for tool in ("bench_viewer_pack.py", "bench_densify.py"):
         r = bench.measure_row(tool)
         assert set(r) == {"error"} and "needs a GPU" in r["error"]
+
+
+def _bench_rank(rank, world, port, q):
+    """One rank of `bench.py --gpus 2` on stand-ins: gloo instead of NCCL, CPU tensors, the fake rasterizer."""
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import bench
+    from divshot_b200 import rasterizer
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK="0")
+    cpu = torch.device("cpu")
+    torch.cuda.set_device = lambda *a, **k: None
+    torch.cuda.synchronize = lambda *a, **k: None
+    torch.cuda.Event = _FakeEvent
+    torch.device = lambda *a, **k: cpu
+    torch.Tensor.pin_memory = lambda self, *a, **k: self
+    real_init = dist.init_process_group
+    dist.init_process_group = lambda backend, **kw: real_init("gloo", rank=rank, world_size=world)
+
+    class R(_FakeRasterizer):
+        def backward(self, dl, grads, **kw):
+            grads.flat.fill_(float(rank + 1))
+
+        def step_host(self, cam, params, grads, *a, **kw):
+            grads.flat.fill_(float(rank + 1))
+
+    rasterizer.Rasterizer = R
+    rasterizer.scene_to_device = lambda sc, dev: {"means3D": torch.from_numpy(sc.means3D)}
+    bench.measure_row = lambda tool: {"error": "mock"}
+    sys.argv = ["bench.py", "--gpus", str(world), "--steps", "2", "--warmup", "3", "--no-cpu", "--workload", "c2"]  # SH degree 1
+    r_fd, w_fd = os.pipe()
+    os.dup2(w_fd, 1)  # the JSON line goes to fd 1
+    bench.main()
+    sys.stdout.flush()
+    os.set_blocking(r_fd, False)  # bench keeps its own dup of fd 1 open: do not wait for an end-of-file
+    try:
+        text = os.read(r_fd, 1 << 20).decode()
+    except BlockingIOError:
+        text = ""
+    q.put((rank, text))
+
+
+def test_bench_two_ranks_on_stand_ins_print_one_line_and_keep_the_plain_exchange():
+    """N = 2 through main(): rank 0 alone prints the line; the factored exchange is set up, cannot run without CUDA, is voted
+    down on both ranks, and the plain all-reduce carries the run (allreduce.backend / note say so)."""
+    if torch.cuda.is_available():
+        pytest.skip("the real bench runs on a GPU box")
+    import socket
+
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_bench_rank, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = dict(q.get(timeout=300) for _ in range(2))
+    [p.join(timeout=60) for p in procs]
+    rows0 = [l for l in res[0].splitlines() if l.startswith("{")]
+    rows1 = [l for l in res[1].splitlines() if l.startswith("{")]
+    assert len(rows0) == 1 and not rows1
+    line = json.loads(rows0[0])
+    assert line["n_gpus"] == 2 and line["scaling"] == "weak" and line["allreduce"]["backend"] == "nccl"
+    assert "rejected" in line["allreduce"]["note"] and line["allreduce"]["ms"] > 0
+    assert line["gpu_launches"] == 20 and "other_rows" not in line
