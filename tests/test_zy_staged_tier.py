@@ -16,7 +16,8 @@ ROWS = [("F1 refinement step, masked loss", "test_zz_staged_densify.py"),
         ("F3 viewer hand-off", "test_viewer_pack.py"),
         ("F4 depth / alpha / normal maps (C-ABI and libtorch)", "test_aux_outputs.py"),
         ("8-B editor surface, splatx-cli", "test_zz_staged_editor_api.py"),
-        ("8-e SH accumulation kernel of the factored exchange", "test_sh_exchange.py")]
+        ("8-e SH accumulation kernel of the factored exchange", "test_sh_exchange.py"),
+        ("8-e ring views of the multi-GPU runs at full size", "test_zz_staged_views.py")]
 
 
 @pytest.mark.gpu
