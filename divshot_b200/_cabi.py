@@ -16,6 +16,7 @@ FLAG_ACCUMULATE = 2
 FLAG_ABSGRAD = 4
 FLAG_DEFER_CHECK = 8
 FLAG_ANTIALIAS = 16
+FLAG_TIGHT_LISTS = 32
 NUM_STAGES = 8
 
 (BUF_RADII, BUF_TILES_TOUCHED, BUF_DEPTH, BUF_MEAN2D, BUF_CONIC_OPACITY, BUF_RGB, BUF_CLAMPED, BUF_POINT_LIST,
@@ -48,7 +49,8 @@ class DvsGrads(C.Structure):
 class DvsStats(C.Structure):
     _fields_ = [("num_gaussians", C.c_int64), ("num_visible", C.c_int64), ("num_dups", C.c_int64),
                 ("dup_capacity", C.c_int64), ("max_tile_len", C.c_int64), ("tiles_x", C.c_int32),
-                ("tiles_y", C.c_int32), ("overflow", C.c_int32)]
+                ("tiles_y", C.c_int32), ("overflow", C.c_int32), ("reserved_", C.c_int32),
+                ("num_list_entries", C.c_int64)]
 
 
 _lib = None
@@ -59,10 +61,12 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise RuntimeError(f"{LIB_PATH} is missing: run `python -m divshot_b200.build` (or __graft_entry__.build()); "
+    # DVS_RAST_LIB: A/B measurements only (tools/ab_bench.py loads a variant build of the same C-ABI)
+    path = os.environ.get("DVS_RAST_LIB") or LIB_PATH
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: run `python -m divshot_b200.build` (or __graft_entry__.build()); "
                            "there is no CPU fallback for the rasterizer")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(path)
     L.dvs_rast_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
     L.dvs_rast_create.restype = C.c_int
     L.dvs_rast_destroy.argtypes = [C.c_void_p]

@@ -90,6 +90,47 @@ def build_rast(force: bool = False, verbose: bool = False) -> str:
     return so
 
 
+def build_variant(name: str, defines=(), rev: str | None = None, files=None) -> str:
+    """A/B experiments only: a second libdvsrast built with extra -D macros (and/or from the sources of an earlier git
+    revision `rev`) -> divshot_b200/lib/variants/libdvsrast_<name>.so; tools/ab_bench.py loads it through DVS_RAST_LIB.
+    The default build never depends on it."""
+    vdir = os.path.join(ROOT, "build", "variants", name)
+    vobj = os.path.join(vdir, "obj")
+    os.makedirs(vobj, exist_ok=True)
+    csrc, inc = CSRC, os.path.join(ROOT, "include")
+    if rev:
+        csrc, inc = os.path.join(vdir, "src", "csrc"), os.path.join(vdir, "src", "include")
+        for d in (csrc, inc):
+            shutil.rmtree(d, ignore_errors=True)
+            os.makedirs(d)
+        for sub, dst in (("divshot_b200/csrc", csrc), ("include", inc)):
+            names = subprocess.check_output(["git", "ls-tree", "--name-only", f"{rev}:{sub}"], cwd=ROOT, text=True).split()
+            for n in names:
+                with open(os.path.join(dst, n), "wb") as f:
+                    f.write(subprocess.check_output(["git", "show", f"{rev}:{sub}/{n}"], cwd=ROOT))
+    common = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-I", inc, "-I", csrc,
+              "--expt-relaxed-constexpr"]
+    procs, objs = [], []
+    for src, extra in CU_SOURCES.items():
+        s = os.path.join(csrc, src)
+        if not os.path.exists(s):
+            continue
+        o = os.path.join(vobj, src.replace(".cu", ".o"))
+        objs.append(o)
+        cmd = [nvcc(), "-ccbin", host_cxx(), *ARCH, *common, *extra, *[f"-D{d}" for d in defines], "-c", s, "-o", o]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            sys.stderr.write(f"--- {name}: {src} ---\n{out}\n")
+            raise RuntimeError(f"variant {name}: nvcc failed on {src}")
+    vout = os.path.join(OUT, "variants")
+    os.makedirs(vout, exist_ok=True)
+    so = os.path.join(vout, f"libdvsrast_{name}.so")
+    subprocess.check_call([nvcc(), "-ccbin", host_cxx(), *ARCH, "-shared", "-o", so, *objs, "-cudart", "static"])
+    return so
+
+
 def build_model_io(force: bool = False) -> str:
     """model_io.o: the host-only model writers/readers (include/dvs_model_io.h).  g++, -ffp-contract=off and the
     x86-64 baseline ISA (no FMA): its quantisers are literal operation sequences, byte-exact vs the reference."""

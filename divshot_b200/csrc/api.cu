@@ -20,6 +20,12 @@
 
 using namespace dvs;
 
+#ifdef DVS_NO_TILE_ORDER  // A/B only: compositing CTAs in raster order
+#define DVS_TILE_ORDER(ctx) nullptr
+#else
+#define DVS_TILE_ORDER(ctx) (ctx)->tile_order
+#endif
+
 struct dvs_rast_ctx {
     int device = 0;
     char err[512] = {0};
@@ -34,6 +40,7 @@ struct dvs_rast_ctx {
     uint32_t* tile_base = nullptr;  // T+1
     uint32_t* tile_cursor = nullptr;
     uint32_t* class_tiles = nullptr;  // [5][T] per-sort-class tile lists
+    uint32_t* tile_order = nullptr;   // [T] launch order of the compositing CTAs (longest lists first)
     // per-duplicate
     int64_t cap_dups = 0;   // entries plist (and, in two-pass mode, bins) can hold
     int64_t cap_bins = 0;   // entries of the bins arena (>= cap_dups; >= T * bin_stride in single-pass mode)
@@ -117,6 +124,7 @@ static int ensure_tiles(dvs_rast_ctx* ctx, int64_t T) {
     CK(regrow(ctx->tile_base, (size_t)T + 1));
     CK(regrow(ctx->tile_cursor, (size_t)T * TILE_CTR_STRIDE));
     CK(regrow(ctx->class_tiles, 5 * (size_t)T));
+    CK(regrow(ctx->tile_order, (size_t)T));
     ctx->cap_tiles = T;
     return DVS_OK;
 }
@@ -149,7 +157,9 @@ static int ensure_pix(dvs_rast_ctx* ctx, int64_t P) {
 
 static void publish_stats(dvs_rast_ctx* ctx) {
     ctx->st.num_visible = (int64_t)ctx->h_stats[0];
-    ctx->st.num_dups = (int64_t)ctx->h_info[0];
+    ctx->st.num_list_entries = (int64_t)ctx->h_info[0];
+    // D of SURVEY.md section 8(d) = sum of tiles_touched, whatever the lists hold (with DVS_FLAG_TIGHT_LISTS they hold fewer)
+    ctx->st.num_dups = (int64_t)ctx->h_stats[1];
     ctx->st.dup_capacity = ctx->cap_dups;
     ctx->st.max_tile_len = ctx->h_info[1];
 }
@@ -217,7 +227,7 @@ void dvs_rast_destroy(dvs_rast_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaFree(ctx->rec); cudaFree(ctx->aux); cudaFree(ctx->sgrad);
-    cudaFree(ctx->tile_count); cudaFree(ctx->tile_base); cudaFree(ctx->tile_cursor); cudaFree(ctx->class_tiles);
+    cudaFree(ctx->tile_count); cudaFree(ctx->tile_base); cudaFree(ctx->tile_cursor); cudaFree(ctx->class_tiles); cudaFree(ctx->tile_order);
     cudaFree(ctx->bins); cudaFree(ctx->plist);
     cudaFree(ctx->final_T); cudaFree(ctx->n_contrib); cudaFree(ctx->h2d_grad); cudaFree(ctx->d_image);
     cudaFree(ctx->rec_aux); cudaFree(ctx->aux_dz); cudaFree(ctx->aux_dn); cudaFree(ctx->aux_img); cudaFree(ctx->aux_T); cudaFree(ctx->aux_nc);
@@ -318,16 +328,17 @@ int dvs_rast_forward(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, const 
         CK(cudaMemsetAsync(ctx->stats, 0, 2 * sizeof(unsigned long long), st));
         CK(cudaMemsetAsync(ctx->info + 10, 0, sizeof(uint32_t), st));
         CK(cudaEventRecord(ctx->ev[0], st));
-        const FusedEmit fe{ctx->tile_cursor, ctx->bins, fused ? ctx->bin_stride : 0u, ctx->info + 10};
+        const FusedEmit fe{ctx->tile_cursor, ctx->bins, fused ? ctx->bin_stride : 0u, ctx->info + 10,
+                           (fused && (cam->flags & DVS_FLAG_TIGHT_LISTS)) ? 1u : 0u};
         CK(launch_preprocess_fwd(c, (int)N, prm, ctx->rec, ctx->aux, ctx->tile_count, out_radii, ctx->stats, fe, st));
         CK(cudaEventRecord(ctx->ev[1], st));
         if (fused) {
             CK(launch_tile_scan((int)T, ctx->tile_cursor, ctx->tile_base, nullptr, ctx->info, (uint32_t)ctx->cap_dups,
-                                ctx->class_tiles, st));
+                                ctx->class_tiles, ctx->tile_order, st));
             CK(cudaEventRecord(ctx->ev[2], st));
         } else {
             CK(launch_tile_scan((int)T, ctx->tile_count, ctx->tile_base, ctx->tile_cursor, ctx->info,
-                                (uint32_t)ctx->cap_dups, ctx->class_tiles, st));
+                                (uint32_t)ctx->cap_dups, ctx->class_tiles, ctx->tile_order, st));
             CK(cudaEventRecord(ctx->ev[2], st));
             CK(launch_emit(c, (int)N, ctx->aux, ctx->rec, ctx->tile_cursor, ctx->bins, (uint32_t)ctx->cap_dups, st));
         }
@@ -335,7 +346,7 @@ int dvs_rast_forward(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, const 
         CK(launch_tile_sort((int)T, fused ? ctx->bin_stride : 0u, ctx->tile_base, ctx->bins, ctx->plist, ctx->info,
                             ctx->class_tiles, st));
         CK(cudaEventRecord(ctx->ev[4], st));
-        CK(launch_render_fwd(c, ctx->tile_base, ctx->plist, ctx->rec, out_color, ctx->final_T, ctx->n_contrib,
+        CK(launch_render_fwd(c, DVS_TILE_ORDER(ctx), ctx->tile_base, ctx->plist, ctx->rec, out_color, ctx->final_T, ctx->n_contrib,
                              ctx->info, st));
         CK(cudaEventRecord(ctx->ev[5], st));
         CK(cudaMemcpyAsync(ctx->h_info, ctx->info, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -403,7 +414,8 @@ int dvs_rast_backward(dvs_rast_ctx* ctx, const dvs_params* params, const float* 
         if (!grads->means3D || !grads->scales || !grads->quats || !grads->opacities || !grads->sh0 ||
             (c.KR > 0 && !grads->shN))
             return fail(ctx, DVS_E_INVALID, "null gradient pointer");
-        if (!aligned16(grads->quats) || (c.KR > 0 && !aligned16(grads->shN)))
+        if (!aligned16(grads->means3D) || !aligned16(grads->scales) || !aligned16(grads->quats) ||
+            !aligned16(grads->opacities) || !aligned16(grads->sh0) || (c.KR > 0 && !aligned16(grads->shN)))
             return fail(ctx, DVS_E_INVALID, "gradient pointers must be 16-byte aligned");
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -416,7 +428,7 @@ int dvs_rast_backward(dvs_rast_ctx* ctx, const dvs_params* params, const float* 
                   (flags & DVS_FLAG_ABSGRAD) ? grads->mean2D_abs : nullptr, grads->mean2D};
     }
     CK(cudaEventRecord(ctx->ev[6], st));
-    CK(launch_render_bwd(c, ctx->tile_base, ctx->plist, ctx->rec, ctx->final_T, ctx->n_contrib, dL_dpix,
+    CK(launch_render_bwd(c, DVS_TILE_ORDER(ctx), ctx->tile_base, ctx->plist, ctx->rec, ctx->final_T, ctx->n_contrib, dL_dpix,
                          reinterpret_cast<float*>(ctx->sgrad), (flags & DVS_FLAG_ABSGRAD) && g.mean2D_abs,
                          ctx->info, st));
     CK(cudaEventRecord(ctx->ev[7], st));
@@ -458,14 +470,14 @@ int dvs_rast_forward_aux(dvs_rast_ctx* ctx, const dvs_params* params, float* out
     if ((rc = ensure_aux(ctx, N > 0 ? N : 1, P))) return rc;
     if (out_aux) {
         CK(launch_aux_records((int)N, ctx->rec, ctx->rec_aux, st));
-        CK(launch_render_fwd(c, ctx->tile_base, ctx->plist, ctx->rec_aux, ctx->aux_img, ctx->aux_T, ctx->aux_nc, ctx->info, st));
+        CK(launch_render_fwd(c, DVS_TILE_ORDER(ctx), ctx->tile_base, ctx->plist, ctx->rec_aux, ctx->aux_img, ctx->aux_T, ctx->aux_nc, ctx->info, st));
         CK(cudaMemcpyAsync(out_aux, ctx->aux_img, 2 * (size_t)P * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
     if (out_normal) {
         Params prm{};
         if (N > 0) prm = Params{params->means3D, params->scales, params->quats, params->opacities, params->sh0, params->shN};
         CK(launch_aux_normal_records(c, (int)N, prm, ctx->rec, ctx->rec_aux, st));
-        CK(launch_render_fwd(c, ctx->tile_base, ctx->plist, ctx->rec_aux, out_normal, ctx->aux_T, ctx->aux_nc, ctx->info, st));
+        CK(launch_render_fwd(c, DVS_TILE_ORDER(ctx), ctx->tile_base, ctx->plist, ctx->rec_aux, out_normal, ctx->aux_T, ctx->aux_nc, ctx->info, st));
     }
     return DVS_OK;
 }
@@ -487,7 +499,8 @@ int dvs_rast_backward_aux(dvs_rast_ctx* ctx, const dvs_params* params, const flo
         if (!grads->means3D || !grads->scales || !grads->quats || !grads->opacities || !grads->sh0 ||
             (c.KR > 0 && !grads->shN))
             return fail(ctx, DVS_E_INVALID, "null gradient pointer");
-        if (!aligned16(grads->quats) || (c.KR > 0 && !aligned16(grads->shN)))
+        if (!aligned16(grads->means3D) || !aligned16(grads->scales) || !aligned16(grads->quats) ||
+            !aligned16(grads->opacities) || !aligned16(grads->sh0) || (c.KR > 0 && !aligned16(grads->shN)))
             return fail(ctx, DVS_E_INVALID, "gradient pointers must be 16-byte aligned");
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -508,7 +521,7 @@ int dvs_rast_backward_aux(dvs_rast_ctx* ctx, const dvs_params* params, const flo
         CK(launch_aux_records((int)N, ctx->rec, ctx->rec_aux, st));
         CK(cudaMemcpyAsync(ctx->aux_img, dL_daux, 2 * (size_t)P * sizeof(float), cudaMemcpyDeviceToDevice, st));
         CK(cudaMemsetAsync(ctx->aux_img + 2 * (size_t)P, 0, (size_t)P * sizeof(float), st));
-        CK(launch_render_bwd(c0, ctx->tile_base, ctx->plist, ctx->rec_aux, ctx->final_T, ctx->n_contrib, ctx->aux_img,
+        CK(launch_render_bwd(c0, DVS_TILE_ORDER(ctx), ctx->tile_base, ctx->plist, ctx->rec_aux, ctx->final_T, ctx->n_contrib, ctx->aux_img,
                              reinterpret_cast<float*>(ctx->sgrad), false, ctx->info, st));
         // its colour sums are dL/dz: out of the records, so that the next pass finds slots 6-8 empty
         CK(launch_aux_extract((int)N, ctx->sgrad, ctx->aux_dz, st));
@@ -516,12 +529,12 @@ int dvs_rast_backward_aux(dvs_rast_ctx* ctx, const dvs_params* params, const flo
     if (dL_dnormal) {
         // 2. normal-map loss: colour triple = view-space normal; its colour sums are dL/dn
         CK(launch_aux_normal_records(c0, (int)N, prm, ctx->rec, ctx->rec_aux, st));
-        CK(launch_render_bwd(c0, ctx->tile_base, ctx->plist, ctx->rec_aux, ctx->final_T, ctx->n_contrib, dL_dnormal,
+        CK(launch_render_bwd(c0, DVS_TILE_ORDER(ctx), ctx->tile_base, ctx->plist, ctx->rec_aux, ctx->final_T, ctx->n_contrib, dL_dnormal,
                              reinterpret_cast<float*>(ctx->sgrad), false, ctx->info, st));
         CK(launch_aux_extract3((int)N, ctx->sgrad, ctx->aux_dn, st));
     }
     // 3. the colour loss adds its geometry sums on top, then the per-Gaussian backward consumes the total
-    CK(launch_render_bwd(c, ctx->tile_base, ctx->plist, ctx->rec, ctx->final_T, ctx->n_contrib, dL_dpix,
+    CK(launch_render_bwd(c, DVS_TILE_ORDER(ctx), ctx->tile_base, ctx->plist, ctx->rec, ctx->final_T, ctx->n_contrib, dL_dpix,
                          reinterpret_cast<float*>(ctx->sgrad), (flags & DVS_FLAG_ABSGRAD) && g.mean2D_abs, ctx->info, st));
     CK(cudaEventRecord(ctx->ev[7], st));
     CK(launch_preprocess_bwd(c, (int)N, prm, ctx->aux, ctx->sgrad, g, flags, st));
@@ -586,7 +599,7 @@ int dvs_rast_debug_read(dvs_rast_ctx* ctx, int which, void* dst, size_t dst_byte
     if (!ctx->have_fwd) return fail(ctx, DVS_E_STATE, "no forward to read from");
     CK(cudaSetDevice(ctx->device));
     CK(cudaDeviceSynchronize());
-    const size_t N = (size_t)ctx->N, D = (size_t)ctx->st.num_dups;
+    const size_t N = (size_t)ctx->N, D = (size_t)ctx->st.num_list_entries;
     const size_t T = (size_t)ctx->cam.gx * ctx->cam.gy, P = (size_t)ctx->cam.W * ctx->cam.H;
     auto need = [&](size_t b) -> int {
         return dst_bytes >= b ? DVS_OK : fail(ctx, DVS_E_INVALID, "debug_read: need %zu bytes, got %zu", b, dst_bytes);

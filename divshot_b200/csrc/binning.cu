@@ -34,14 +34,23 @@ __host__ __device__ __forceinline__ int sort_class_of(uint32_t n) {
 }
 
 constexpr int SCAN_MAX_PER_THREAD = 8;  // register-blocked fast path for T <= 8192 tiles
+// launch order of the compositing CTAs: a counting sort of the tiles by list length (descending, ORDER_BUCKETS buckets
+// of ORDER_GRAIN entries, the last one open-ended), so that the last wave of CTAs is made of short lists
+constexpr int ORDER_BUCKETS = 128;
+constexpr uint32_t ORDER_GRAIN = 32;
+__device__ __forceinline__ uint32_t order_bucket(uint32_t len) {  // bucket 0 = longest
+    return (uint32_t)(ORDER_BUCKETS - 1) - min(len / ORDER_GRAIN, (uint32_t)(ORDER_BUCKETS - 1));
+}
 
 __global__ void __launch_bounds__(SCAN_THREADS)
 tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_base,
                  uint32_t* __restrict__ tile_cursor /* nullptr: single-pass mode, counts ARE the cursors */,
                  uint32_t* __restrict__ info, uint32_t dup_capacity,
-                 uint32_t* __restrict__ class_tiles /* [NUM_SORT_CLASSES][T] */) {
+                 uint32_t* __restrict__ class_tiles /* [NUM_SORT_CLASSES][T] */,
+                 uint32_t* __restrict__ tile_order /* [T]: all tiles, longest lists first */) {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t warp_max[32];
+    __shared__ uint32_t s_hist[ORDER_BUCKETS + 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // chunked over [0,T) in slabs of SCAN_THREADS * SCAN_MAX_PER_THREAD; within a slab thread t owns the
     // SCAN_MAX_PER_THREAD consecutive tiles starting at slab + t * SCAN_MAX_PER_THREAD (all loads in flight at once)
@@ -136,14 +145,39 @@ tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint32_t* __res
         info[2] = ovf ? 1u : 0u;
         if (ovf) { info[3] += 1u; info[9] = (uint32_t)min(carry, 0xffffffffull); }  // sticky (deferred-check mode)
     }
+    if (tile_order) {
+        // tile_base[] was written by this CTA above: visible to all its threads after the barrier
+        for (int b = threadIdx.x; b <= ORDER_BUCKETS; b += SCAN_THREADS) s_hist[b] = 0u;
+        __syncthreads();
+        for (int t = threadIdx.x; t < T; t += SCAN_THREADS) atomicAdd(&s_hist[order_bucket(tile_base[t + 1] - tile_base[t])], 1u);
+        __syncthreads();
+        if (warp == 0) {  // exclusive scan of the ORDER_BUCKETS counts (4 per lane)
+            uint32_t v[ORDER_BUCKETS / 32], sum = 0;
+#pragma unroll
+            for (int q = 0; q < ORDER_BUCKETS / 32; q++) { v[q] = s_hist[lane * (ORDER_BUCKETS / 32) + q]; sum += v[q]; }
+            uint32_t inc = sum;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t nn = __shfl_up_sync(0xffffffffu, inc, off);
+                if (lane >= off) inc += nn;
+            }
+            uint32_t run = inc - sum;
+#pragma unroll
+            for (int q = 0; q < ORDER_BUCKETS / 32; q++) { s_hist[lane * (ORDER_BUCKETS / 32) + q] = run; run += v[q]; }
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < T; t += SCAN_THREADS)
+            tile_order[atomicAdd(&s_hist[order_bucket(tile_base[t + 1] - tile_base[t])], 1u)] = (uint32_t)t;
+    }
 }
 
 cudaError_t launch_tile_scan(int T, const uint32_t* tile_count, uint32_t* tile_base, uint32_t* tile_cursor,
-                             uint32_t* info, uint32_t dup_capacity, uint32_t* class_tiles, cudaStream_t st) {
+                             uint32_t* info, uint32_t dup_capacity, uint32_t* class_tiles, uint32_t* tile_order,
+                             cudaStream_t st) {
     cudaError_t e = cudaMemsetAsync(info + 4, 0, NUM_SORT_CLASSES * sizeof(uint32_t), st);
     if (e != cudaSuccess) return e;
     tile_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(T, tile_count, tile_base, tile_cursor, info, dup_capacity,
-                                                 class_tiles);
+                                                 class_tiles, tile_order);
     return cudaGetLastError();
 }
 
@@ -465,8 +499,8 @@ __global__ void unpack_kernel(int N, const float4* __restrict__ rec, int32_t* ra
     depth[i] = q2.y;
     mean2D[2 * i] = q0.x; mean2D[2 * i + 1] = q0.y;
     conic_opacity[4 * i] = rad > 0 ? q0.z / (-0.5f * LOG2E) : 0.f;
-    conic_opacity[4 * i + 1] = rad > 0 ? q0.w / (-LOG2E) : 0.f;
-    conic_opacity[4 * i + 2] = rad > 0 ? q1.x / (-0.5f * LOG2E) : 0.f;
+    conic_opacity[4 * i + 1] = rad > 0 ? q1.x / (-LOG2E) : 0.f;
+    conic_opacity[4 * i + 2] = rad > 0 ? q0.w / (-0.5f * LOG2E) : 0.f;
     conic_opacity[4 * i + 3] = rad > 0 ? exp2f(q1.y) : 0.f;
     rgb[3 * i] = q1.z; rgb[3 * i + 1] = q1.w; rgb[3 * i + 2] = q2.x;
     clamped[3 * i] = (tw >> 24) & 1; clamped[3 * i + 1] = (tw >> 25) & 1; clamped[3 * i + 2] = (tw >> 26) & 1;

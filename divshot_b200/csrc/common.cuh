@@ -2,8 +2,10 @@
 //
 // HBM layout (all arenas owned by dvs_rast_ctx, SoA inputs owned by the caller):
 //   rec   [N] x 48 B  screen record, three float4:
-//           q0 = { mean2D.x, mean2D.y, A2, B2 }          A2 = -0.5*log2(e)*conicA, B2 = -log2(e)*conicB
-//           q1 = { C2, lo, r, g }                        C2 = -0.5*log2(e)*conicC, lo = log2(opacity)
+//           q0 = { mean2D.x, mean2D.y, A2, C2 }          A2 = -0.5*log2(e)*conicA, C2 = -0.5*log2(e)*conicC
+//           q1 = { B2, lo, r, g }                        B2 = -log2(e)*conicB, lo = log2(opacity)
+//         ({mx, my} and {A2, C2} are the operand pairs of the compositors' packed FADD2 / FMUL2, so the record is staged
+//          into shared memory by verbatim 16-byte asynchronous copies and read back as aligned register pairs)
 //           q2 = { b, depth, radius (int bits), tiles_touched | clamped<<24 (uint bits) }
 //         so that alpha = ex2(A2*dx^2 + B2*dx*dy + C2*dy^2 + lo)  (one MUFU, no multiply by opacity)
 //   aux   [N] x 16 B  { minx|miny<<16, maxx|maxy<<16|clamped<<29, depth bits, 0 }
@@ -68,6 +70,7 @@ struct FusedEmit {
     unsigned long long* bins;
     uint32_t bin_stride;
     uint32_t* overflow_word;
+    uint32_t tight;  // DVS_FLAG_TIGHT_LISTS: entries whose sub-tile mask is empty are not emitted
 };
 
 // ---- small PTX wrappers -------------------------------------------------------------------
@@ -172,6 +175,13 @@ __device__ __forceinline__ void sts_f1(uint32_t a, float v) {
 __device__ __forceinline__ void sts_u1(uint32_t a, uint32_t v) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
+
+// 16-byte asynchronous global -> shared copy (LDGSTS; L2 only, the gathered records have no reuse inside an SM)
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP) ------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

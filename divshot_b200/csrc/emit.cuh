@@ -22,7 +22,7 @@ struct CullParams {  // per Gaussian
 __device__ __forceinline__ CullParams cull_params(const float4 q0, const float4 q1) {
     CullParams p;
     p.mx = q0.x; p.my = q0.y;
-    p.a = -q0.z; p.b = -q0.w; p.c = -q1.x;
+    p.a = -q0.z; p.b = -q1.x; p.c = -q0.w;  // record layout {mx, my, A2, C2} {B2, lo, r, g}
     p.m = (q1.y - ALPHA_MIN_LOG2) * 1.0001f + 1e-3f;
     const bool ok = p.a > 0.0f && p.c > 0.0f;
     p.hbc = ok ? __fdividef(-0.5f * p.b, p.c) : 0.0f;
@@ -73,7 +73,7 @@ __device__ __forceinline__ uint32_t sub_tile_mask(const CullParams& g, float X0,
 __device__ __forceinline__ void warp_emit(int gx, int id, int minx, int miny, int w, int area, uint32_t depth_bits,
                                           const CullParams& cp, uint32_t* __restrict__ tile_cursor,
                                           unsigned long long* __restrict__ bins, uint32_t bin_stride, uint32_t cap,
-                                          uint32_t* __restrict__ overflow_word) {
+                                          uint32_t* __restrict__ overflow_word, bool tight = false) {
     const int lane = threadIdx.x & 31;
     int incl = area;  // inclusive warp scan of the duplication counts
 #pragma unroll
@@ -116,19 +116,20 @@ __device__ __forceinline__ void warp_emit(int gx, int id, int minx, int miny, in
                 const int k = j - (s_incl - s_area);
                 const int ty = s_miny + k / s_w, tx = s_minx + k % s_w;
                 tile[u] = (uint32_t)(ty * gx + tx);
-#ifdef DVS_TIGHT_TILES
-                // EXPERIMENT (round-2 A/B, never in the default build): in single-pass mode an entry whose sub-tile mask is
-                // empty — no pixel of the tile reaches alpha >= 1/255, ~39 % of D at c3 (profiles/r1_pair_counts.md) — is not
-                // emitted at all: fewer atomics, shorter sorts and list scans, same image and gradients; the index outputs
-                // (ranges / point_list) then differ from the reference's whole-rectangle lists, and two-pass mode keeps them.
-                const uint32_t m8 = sub_tile_mask(g, (float)(tx * TILE), (float)(ty * TILE));
-                if (bin_stride && m8 == 0u) { ok[u] = false; continue; }
-                slot[u] = atomicAdd(tile_cursor + (size_t)tile[u] * TILE_CTR_STRIDE, 1u);
-#else
-                slot[u] = atomicAdd(tile_cursor + (size_t)tile[u] * TILE_CTR_STRIDE, 1u);
-                // the mask computation overlaps the atomic's round trip
-                const uint32_t m8 = sub_tile_mask(g, (float)(tx * TILE), (float)(ty * TILE));
-#endif
+                // the mask computation overlaps the atomic's round trip — unless the lists are TIGHT (DVS_FLAG_TIGHT_LISTS,
+                // single-pass mode only): an entry whose sub-tile mask is empty (no pixel of the tile reaches
+                // alpha >= 1/255; ~39 % of D at c3, profiles/r1_pair_counts.md) is then not emitted at all — fewer
+                // atomics, shorter sorts and list scans, the same image and gradients; the lists are the reference's
+                // whole-rectangle lists with exactly those entries removed (tested), and n_contrib counts in them
+                uint32_t m8;
+                if (tight) {
+                    m8 = sub_tile_mask(g, (float)(tx * TILE), (float)(ty * TILE));
+                    if (m8 == 0u) { ok[u] = false; continue; }
+                    slot[u] = atomicAdd(tile_cursor + (size_t)tile[u] * TILE_CTR_STRIDE, 1u);
+                } else {
+                    slot[u] = atomicAdd(tile_cursor + (size_t)tile[u] * TILE_CTR_STRIDE, 1u);
+                    m8 = sub_tile_mask(g, (float)(tx * TILE), (float)(ty * TILE));
+                }
                 key[u] = ((unsigned long long)s_depth << 32) | (((uint32_t)s_id << 8) | m8);
             }
         }

@@ -13,9 +13,11 @@ cudaError_t launch_preprocess_fwd(const Cam& cam, int N, const Params& prm, floa
                                   const FusedEmit& fe, cudaStream_t st);
 
 // A2/A5: exclusive scan of tile counts -> tile_base[T+1], cursor[T]; info[0]=D, info[1]=max len, info[2]=overflow,
-// info[4..8] = tiles per sort class, class_tiles[5][T] = their ids
+// info[4..8] = tiles per sort class, class_tiles[5][T] = their ids; tile_order[T] = all tiles, longest lists first
+// (the launch order of the compositing CTAs)
 cudaError_t launch_tile_scan(int T, const uint32_t* tile_count, uint32_t* tile_base, uint32_t* tile_cursor,
-                             uint32_t* info, uint32_t dup_capacity, uint32_t* class_tiles, cudaStream_t st);
+                             uint32_t* info, uint32_t dup_capacity, uint32_t* class_tiles, uint32_t* tile_order,
+                             cudaStream_t st);
 
 // A3 (two-pass mode): emit (depth | id | sub-tile mask) entries into per-tile bins
 cudaError_t launch_emit(const Cam& cam, int N, const uint4* aux, const float4* rec, uint32_t* tile_cursor,
@@ -26,14 +28,14 @@ cudaError_t launch_tile_sort(int T, uint32_t bin_stride, const uint32_t* tile_ba
                              uint32_t* plist, const uint32_t* info, const uint32_t* class_tiles, cudaStream_t st);
 
 // A6
-cudaError_t launch_render_fwd(const Cam& cam, const uint32_t* tile_base, const uint32_t* plist, const float4* rec,
-                              float* out_color, float* final_T, uint32_t* n_contrib, const uint32_t* info,
-                              cudaStream_t st);
+cudaError_t launch_render_fwd(const Cam& cam, const uint32_t* tile_order, const uint32_t* tile_base,
+                              const uint32_t* plist, const float4* rec, float* out_color, float* final_T,
+                              uint32_t* n_contrib, const uint32_t* info, cudaStream_t st);
 
 // A7
-cudaError_t launch_render_bwd(const Cam& cam, const uint32_t* tile_base, const uint32_t* plist, const float4* rec,
-                              const float* final_T, const uint32_t* n_contrib, const float* dL_dpix, float* sgrad,
-                              bool absgrad, const uint32_t* info, cudaStream_t st);
+cudaError_t launch_render_bwd(const Cam& cam, const uint32_t* tile_order, const uint32_t* tile_base,
+                              const uint32_t* plist, const float4* rec, const float* final_T, const uint32_t* n_contrib,
+                              const float* dL_dpix, float* sgrad, bool absgrad, const uint32_t* info, cudaStream_t st);
 
 // A8
 cudaError_t launch_preprocess_bwd(const Cam& cam, int N, const Params& prm, const uint4* aux, float4* sgrad,

@@ -272,8 +272,8 @@ preprocess_fwd_kernel(Cam cam, int N, Params prm, float4* __restrict__ rec, uint
                 o = o * sqrtf(fmaxf(0.0f, det0 / det));
             }
             const float lo = log2f(o);
-            q0 = make_float4(mx, my, (-0.5f * LOG2E) * cA, (-LOG2E) * cB);
-            q1 = make_float4((-0.5f * LOG2E) * cC, lo, col[0], col[1]);
+            q0 = make_float4(mx, my, (-0.5f * LOG2E) * cA, (-0.5f * LOG2E) * cC);
+            q1 = make_float4((-LOG2E) * cB, lo, col[0], col[1]);
             q2 = make_float4(col[2], t2, __int_as_float(radius), __uint_as_float(tiles | (clamped << 24)));
             // aux: tile rect, SH clamp mask (bits 29..31 of .y) and the depth key — all the emission kernel and
             // the preprocess backward need, so neither touches the 48-byte records
@@ -309,7 +309,7 @@ preprocess_fwd_kernel(Cam cam, int N, Params prm, float4* __restrict__ rec, uint
         // the tile bins have a fixed stride sized from an earlier forward (see api.cu)
         const CullParams cp = cull_params(q0, q1);
         warp_emit(cam.gx, i, minx, miny, maxx - minx, visible ? (int)tiles : 0, __float_as_uint(q2.y), cp,
-                  fe.tile_cursor, fe.bins, fe.bin_stride, 0u, fe.overflow_word);
+                  fe.tile_cursor, fe.bins, fe.bin_stride, 0u, fe.overflow_word, fe.tight != 0u);
     } else if (visible) {
         // two-pass binning: per-tile duplicate counts (RED, no return); overlaps the bulk stores
         for (int y = miny; y < maxy; y++)

@@ -8,7 +8,11 @@
 //     splats whose footprint reaches it and that lie in front of the warp's deepest last-contributor;
 //   * PHASE 1 (lane = pixel): the reverse walk proper.  Per (pixel, splat) pair only two numbers are
 //     produced: s = dL/dpower and w = alpha*T (colour weight).  They go to two per-warp shared-memory
-//     buffers S[slot][pixel], Wt[slot][pixel] (16 splats deep) — no cross-lane reduction here;
+//     buffers S[slot][pixel], Wt[slot][pixel] (16 splats deep) — no cross-lane reduction here.  The walk is one
+//     straight-line predicated sequence (no divergent branch); the colour recursion is carried as ONE scalar per
+//     pixel, (colour accumulated behind) . dL/dpix, instead of three channels; the slot's identity (its position in
+//     the sorted list) and mean are captured in the registers of lane `slot` (no shuffle, no shared-memory
+//     metadata).  ~45 issue slots and 11 shared-memory wavefronts per (warp, splat) visit (round 1: 56 and 14);
 //   * PHASE 2 (lane = splat x pixel-half): every 16 buffered splats the lanes switch roles.  Lane (k, h)
 //     walks 16 of the 32 pixels for splat k as 8 horizontally adjacent PAIRS held in packed fp32x2
 //     registers (FFMA2 / FMUL2 / FADD2, new on sm_100) and accumulates the nine sums
@@ -26,39 +30,49 @@ namespace dvs {
 
 constexpr int RB_THREADS = 256;
 #ifndef DVS_RB_ROUND
-#define DVS_RB_ROUND 256
+#define DVS_RB_ROUND 128
 #endif
 #ifndef DVS_RB_MINCTA
 #define DVS_RB_MINCTA 4
 #endif
-constexpr int RB_ROUND = DVS_RB_ROUND;  // entries staged per round (128: +1%; 64 with 5 CTAs/SM: no faster)
+constexpr int RB_ROUND = DVS_RB_ROUND;  // entries staged per round and buffer (two buffers)
 constexpr int RB_NB = 16;      // splats buffered per warp between phase 1 and phase 2
 constexpr int RB_SROW = 34;    // floats per buffer row (32 pixels + 2: the 64-bit pair loads of phase 2 are bank-conflict-free)
 
 struct RbSmem {
     // byte offsets inside dynamic shared memory
-    static constexpr int stage = 0;                              // RB_ROUND * 48
-    static constexpr int ent = stage + RB_ROUND * 48;            // RB_ROUND * 4
-    static constexpr int wmax = ent + RB_ROUND * 4;              // 8 * 4
+    static constexpr int stage = 0;                              // 2 buffers of RB_ROUND * 48
+    static constexpr int ent = stage + 2 * RB_ROUND * 48;        // 2 buffers of RB_ROUND * 4
+    static constexpr int wmax = ent + 2 * RB_ROUND * 4;          // 8 * 4
     static constexpr int warp0 = wmax + 64;                      // per-warp region start
     static constexpr int S = 0;                                  // RB_NB rows of RB_SROW floats: s = dL/dpower per (slot, pixel)
     static constexpr int Wt = S + RB_NB * RB_SROW * 4;           // same shape: w = alpha*T (colour weight)
-    static constexpr int meta = Wt + RB_NB * RB_SROW * 4;        // RB_NB * 8 words {entry word (id << 8 | mask), -, mx, my, A, B, C, -}
-    static constexpr int dpA = meta + RB_NB * 8 * 4;             // 16 pixel pairs x {r0, r1, g0, g1} of dL/dpix
+    static constexpr int dpA = Wt + RB_NB * RB_SROW * 4;         // 16 pixel pairs x {r0, r1, g0, g1} of dL/dpix
     static constexpr int dpB = dpA + 16 * 16;                    // 16 pixel pairs x {b0, b1}
     static constexpr int per_warp = dpB + 16 * 8;
     static constexpr int total = warp0 + (RB_THREADS / 32) * per_warp;
 };
 
+// Slot metadata captured by lane `slot` during phase 1 (lanes 16..31 hold nothing).
+struct RbSlot {
+    uint32_t gk;     // position of the entry in the sorted list (plist index)
+    float mx, my;    // mean2D
+};
+
 template <bool ABSGRAD>
 __device__ __forceinline__ void rb_phase2(uint32_t wbase, int nbuf, int lane, float px0f, float py0f,
-                                          float* __restrict__ sgrad) {
+                                          const RbSlot& mine, const uint32_t* __restrict__ plist,
+                                          const float4* __restrict__ rec, float* __restrict__ sgrad) {
     __syncwarp();
     const int k = lane & 15, h = lane >> 4;
-    const uint32_t mrow = wbase + RbSmem::meta + k * 32;
-    const float2 mxy = lds_f2(mrow + 8);
-    const float X = mxy.x - px0f;                     // dx of pixel column 0 of the sub-rectangle
-    const float Y = mxy.y - (py0f + (float)(2 * h));  // dy of the first of my two pixel rows
+    // both pixel-halves of slot k read the slot's identity from lane k; the entry word (Gaussian id) comes from the
+    // sorted list itself (one L1/L2 hit per slot and flush, issued first so that the moment passes hide it)
+    const uint32_t gk = __shfl_sync(0xffffffffu, mine.gk, k);
+    uint32_t eword = 0;
+    if (k < nbuf) eword = __ldg(plist + gk);
+    const float mx = __shfl_sync(0xffffffffu, mine.mx, k), my = __shfl_sync(0xffffffffu, mine.my, k);
+    const float X = mx - px0f;                     // dx of pixel column 0 of the sub-rectangle
+    const float Y = my - (py0f + (float)(2 * h));  // dy of the first of my two pixel rows
     const uint32_t srow = wbase + RbSmem::S + (k * RB_SROW + 16 * h) * 4;
     const f32x2 Xp = pk2(X, X - 1.0f), m2 = pk2(-2.0f, -2.0f), m1 = pk2(-1.0f, -1.0f);
     // My 16 pixels are 8 horizontally adjacent PAIRS (2 rows x 4 pairs); every quantity is carried as a packed
@@ -111,8 +125,10 @@ __device__ __forceinline__ void rb_phase2(uint32_t wbase, int nbuf, int lane, fl
     c2 += __shfl_xor_sync(0xffffffffu, c2, 16);
     float ax = 0.f, ay = 0.f;
     if (ABSGRAD) {  // Pass C: sum_pixels |dL/dmean2D contribution| (densification statistic), natural-units conic
-        const f32x2 cA = pk2(lds_f1(mrow + 16), lds_f1(mrow + 16)), cB = pk2(lds_f1(mrow + 20), lds_f1(mrow + 20)),
-                    cC = pk2(lds_f1(mrow + 24), lds_f1(mrow + 24));
+        // natural-units conic from the folded one in the record: A = -2 ln2 A2, B = -ln2 B2, C = -2 ln2 C2
+        const float4* r = rec + 3 * (size_t)(eword >> 8);  // (eword = 0 for unused slots: record 0, result discarded)
+        const float nA = __ldg(&r[0].z) * (-2.0f * LN2), nC = __ldg(&r[0].w) * (-2.0f * LN2), nB = __ldg(&r[1].x) * (-LN2);
+        const f32x2 cA = pk2(nA, nA), cB = pk2(nB, nB), cC = pk2(nC, nC);
         f32x2 bx = 0ull, by = 0ull;
         f32x2 dyp = pk2(Y, Y);
 #pragma unroll
@@ -135,7 +151,7 @@ __device__ __forceinline__ void rb_phase2(uint32_t wbase, int nbuf, int lane, fl
     // 128-bit vector reduction (REDG.E.ADD.F32x4) — 2 reduction instructions per 16 splats instead of 9, and
     // ~4x fewer L1TEX tag wavefronts (every lane's record is a different cache line)
     if (k < nbuf) {
-        float* g = sgrad + 12 * (size_t)(lds_u1(mrow) >> 8);
+        float* g = sgrad + 12 * (size_t)(eword >> 8);
         const float4 v = h ? make_float4(Syy, S0, c0, c1) : make_float4(Sx, Sy, Sxx, Sxy);
         red_add_f4(g + 4 * h, v);
         if (h == 0) {
@@ -148,8 +164,8 @@ __device__ __forceinline__ void rb_phase2(uint32_t wbase, int nbuf, int lane, fl
 
 template <bool ABSGRAD>
 __global__ void __launch_bounds__(RB_THREADS, DVS_RB_MINCTA)
-render_bwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const uint32_t* __restrict__ plist,
-                  const float4* __restrict__ rec, const float* __restrict__ final_T,
+render_bwd_kernel(Cam cam, const uint32_t* __restrict__ tile_order, const uint32_t* __restrict__ tile_base,
+                  const uint32_t* __restrict__ plist, const float4* __restrict__ rec, const float* __restrict__ final_T,
                   const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpix,
                   float* __restrict__ sgrad, const uint32_t* __restrict__ info) {
     extern __shared__ __align__(16) unsigned char rb_smem[];
@@ -157,7 +173,7 @@ render_bwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const uint32_
     uint32_t sb0 = smem_u32(rb_smem);
     asm volatile("" : "+r"(sb0));  // keep the shared base address in a register (no re-derivation per pair)
     const uint32_t sb = sb0 + RbSmem::stage, se = sb0 + RbSmem::ent, swm = sb0 + RbSmem::wmax;
-    const int tile = blockIdx.x;
+    const int tile = tile_order ? (int)tile_order[blockIdx.x] : (int)blockIdx.x;
     const int tx = tile % cam.gx, ty = tile / cam.gx;
     const uint32_t r0 = tile_base[tile], n = tile_base[tile + 1] - r0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -186,72 +202,80 @@ render_bwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const uint32_
     }
     const float nTf_bg = -T_final * (cam.bg[0] * dp0 + cam.bg[1] * dp1 + cam.bg[2] * dp2);
     float T = T_final;
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+    // accdp = (colour accumulated behind the current splat) . dL/dpix — the three-channel recursion
+    // R <- R + alpha (c - R) collapses to one scalar because only R . dL/dpix is ever used
+    float accdp = 0.f;
 
-    uint32_t wmax = last;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, off));
+    // deepest last contributor of the warp / of the tile.  REDUX results are warp-uniform by construction, which lets
+    // ptxas keep the whole loop nest below (bounds, buffer addresses, list positions) in uniform registers
+    const uint32_t wmax = __reduce_max_sync(0xffffffffu, last);
     if (lane == 0) sts_u1(swm + warp * 4, wmax);
     __syncthreads();
-    uint32_t cmax = 0;
-#pragma unroll
-    for (int w = 0; w < RB_THREADS / 32; w++) cmax = max(cmax, lds_u1(swm + w * 4));
+    uint32_t cmax = __reduce_max_sync(0xffffffffu, lds_u1(swm + (lane & (RB_THREADS / 32 - 1)) * 4));
     cmax = min(cmax, n);
     if (cmax == 0) return;
     const uint32_t wbit = 1u << warp;
-    int nbuf = 0;
-    // per-lane row addresses of the phase-1 buffer, kept in registers (no re-derivation from tid per pair)
-    uint32_t mySW = wbase + RbSmem::S + lane * 4;
-    uint32_t mmeta = wbase + RbSmem::meta;
-    asm volatile("" : "+r"(mySW), "+r"(mmeta));
+    const uint32_t row0 = wbase + RbSmem::S + lane * 4;
+    // byte offset of the buffer row being filled (slot * row pitch): a pure counter with a select-wrap, so that ptxas can
+    // prove it warp-uniform and keep it (and the whole loop nest) on the uniform datapath
+    constexpr uint32_t ROWB = RB_SROW * 4;
+    uint32_t rowoff = 0;
+    const uint32_t lane_row = (uint32_t)lane * ROWB;  // rowoff == lane_row <=> the slot being filled is `lane`
+    RbSlot mine = {0u, 0.f, 0.f};
+    const int glast = (int)(r0 + last);  // entry at list position g is in front of my last contributor iff g < glast
 
-    // staging is software-pipelined: while a round is being walked, the next round's entry words and records
-    // are already in flight into registers of the first RB_ROUND threads
-    uint32_t e_n = 0;
-    float4 q0_n = make_float4(0.f, 0.f, 0.f, 0.f), q1_n = q0_n;
-    float b_n = 0.f;
-    auto fetch = [&](int round) {
-        const uint32_t idx = (uint32_t)round * RB_ROUND + threadIdx.x;
-        e_n = 0;
-        if (idx < cmax) e_n = __ldg(plist + r0 + idx);
-        if (e_n & 0xffu) {
-            const float4* r = rec + 3 * (size_t)(e_n >> 8);
-            q0_n = __ldg(r);
-            q1_n = __ldg(r + 1);
-            b_n = __ldg(reinterpret_cast<const float*>(r + 2));
+    // staging: two buffers of RB_ROUND records + entry words; the NEXT round (the walk goes back to front) is copied in
+    // by 16-byte asynchronous copies (cp.async / LDGSTS) while the current one is walked — one CTA barrier per round and no
+    // staging registers (round 1 held the prefetched record in 10 registers across the walk)
+    auto stage = [&](uint32_t e, uint32_t buf) {
+        sts_u1(se + (buf * RB_ROUND + threadIdx.x) * 4, e);
+        if (e & 0xffu) {
+            const float4* r = rec + 3 * (size_t)(e >> 8);
+            const uint32_t dst = sb + buf * (RB_ROUND * 48) + threadIdx.x * 48;
+            cp_async16(dst, r);
+            cp_async16(dst + 16, r + 1);
+            cp_async16(dst + 32, r + 2);
         }
+        cp_async_commit();
+    };
+    auto entry_of = [&](int round) -> uint32_t {
+        const uint32_t idx = (uint32_t)round * RB_ROUND + threadIdx.x;
+        return (round >= 0 && idx < cmax) ? __ldg(plist + r0 + idx) : 0u;
     };
     const int rd0 = (int)((cmax - 1) / RB_ROUND);
-    if (threadIdx.x < RB_ROUND) fetch(rd0);
+    uint32_t e_n = 0;
+    if (threadIdx.x < RB_ROUND) {
+        stage(entry_of(rd0), (uint32_t)rd0 & 1u);
+        e_n = entry_of(rd0 - 1);
+    }
     for (int rd = rd0; rd >= 0; rd--) {
         const uint32_t base_idx = (uint32_t)rd * RB_ROUND;
-        __syncthreads();  // previous round fully consumed
-        if (threadIdx.x < RB_ROUND) {
-            sts_u1(se + threadIdx.x * 4, e_n);
-            if (e_n & 0xffu) {
-                // staged as {mx, my, A2, C2} {B2, lo, r, g} (register pairs for FADD2 / FMUL2, as in the forward)
-                sts_f4(sb + threadIdx.x * 48, make_float4(q0_n.x, q0_n.y, q0_n.z, q1_n.x));
-                sts_f4(sb + threadIdx.x * 48 + 16, make_float4(q0_n.w, q1_n.y, q1_n.z, q1_n.w));
-                sts_f1(sb + threadIdx.x * 48 + 32, b_n);
-            }
+        cp_async_wait0();  // my copies of round rd have landed
+        __syncthreads();   // ... and everyone's; everyone has finished round rd+1 (whose buffer is refilled below)
+        if (rd > 0 && threadIdx.x < RB_ROUND) {
+            stage(e_n, (uint32_t)(rd - 1) & 1u);
+            e_n = entry_of(rd - 2);
         }
-        __syncthreads();
-        if (rd > 0 && threadIdx.x < RB_ROUND) fetch(rd - 1);
+        const uint32_t sbr = sb + ((uint32_t)rd & 1u) * (RB_ROUND * 48), ser = se + ((uint32_t)rd & 1u) * (RB_ROUND * 4);
         if (base_idx >= wmax) continue;  // this warp's pixels all stopped earlier in the list
         const int cnt = (int)min((uint32_t)RB_ROUND, cmax - base_idx);
-        const int lastr = (int)last - (int)base_idx;  // entry k of this round is in front of my last contributor iff k < lastr
         for (int c = ((cnt - 1) >> 5) << 5; c >= 0; c -= 32) {
             if (base_idx + (uint32_t)c >= wmax) continue;
-            const uint32_t myw = lds_u1(se + (c + lane) * 4);
-            uint32_t bits = __ballot_sync(0xffffffffu, (myw & wbit) != 0u);
+            uint32_t bits = __ballot_sync(0xffffffffu, (lds_u1(ser + (c + lane) * 4) & wbit) != 0u);
+            uint32_t ea0 = sbr + (uint32_t)c * 48u;
+            int g0 = (int)(r0 + base_idx) + c;  // list position of the group's first entry
+            asm volatile("" : "+r"(ea0), "+r"(g0));  // per-group values: keep them in registers, do not re-derive per visit
             while (bits) {
-                const int j = 31 - __clz(bits);
-                bits &= ~(1u << j);
-                const int k = c + j;
-                const uint32_t ea = sb + k * 48;
+                uint32_t p, below;
+                asm("bfind.u32 %0, %1;" : "=r"(p) : "r"(bits));                     // highest set bit: FLO, no clz round trip
+                asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(below) : "r"(0), "r"(p));  // bits [0, p)
+                bits &= below;
+                const uint32_t ea = ea0 + p * 48u;
+                const int gk = g0 + (int)p;
                 f32x2 mxy, AC;
                 lds_p4(ea, mxy, AC);
                 const float4 q1 = lds_f4(ea + 16);  // {B2, lo, r, g}
+                const float cb = lds_f1(ea + 32);
                 float dx, dy, adx, cdy;
                 const f32x2 d = add2(mxy, npxy);    // same arithmetic, bit for bit, as the forward kernel
                 upk2(d, dx, dy);
@@ -259,69 +283,67 @@ render_bwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const uint32_
                 const float t = fmaf(q1.x, dy, adx);
                 const float pw = fmaf(cdy, dy, t * dx);
                 const float ee = pw + q1.y;
-                const bool act = k < lastr && pw <= 0.0f && ee >= ALPHA_MIN_LOG2;
-                if (!__any_sync(0xffffffffu, act)) continue;
+                // everything below is computed by every lane and committed under pa = the pair was blended by the forward
+                // (in front of my last contributor, power <= 0, alpha >= 1/255):
+                //   T <- T / (1 - alpha);  s = dL/dpower = 2^ee dL/dalpha (the 0.99 clamp is straight-through);  w = alpha T
+                //   dL/dalpha = (c . dp - accdp) T - T_final (bg . dp) / (1 - alpha);  accdp <- accdp + alpha (c . dp - accdp)
+                const float a_raw = ex2_approx(ee);
+                const float alpha = fminf(0.99f, a_raw);
+                const float rinv = rcp_approx(1.0f - alpha);
+                const float Tn = T * rinv;
+                const float cdp = fmaf(cb, dp2, fmaf(q1.w, dp1, q1.z * dp0));
+                const float dd = cdp - accdp;
+                const float dLa = fmaf(dd, Tn, nTf_bg * rinv);
                 float s = 0.f, wgt = 0.f;
-                if (act) {
-                    const float a_raw = ex2_approx(ee);
-                    const float alpha = fminf(0.99f, a_raw);
-                    const float rinv = rcp_approx(1.0f - alpha);
-                    T = T * rinv;
-                    wgt = alpha * T;
-                    const float cb = lds_f1(ea + 32);
-                    // R = colour accumulated behind this splat (what upstream calls accum_rec at the time of use);
-                    // dL/dalpha = sum_ch (c - R) dL/dpix, then R <- alpha c + (1 - alpha) R = R + alpha (c - R)
-                    const float d0 = q1.z - acc0, d1 = q1.w - acc1, d2 = cb - acc2;
-                    float dL_dalpha = d0 * dp0;
-                    dL_dalpha = fmaf(d1, dp1, dL_dalpha);
-                    dL_dalpha = fmaf(d2, dp2, dL_dalpha);
-                    acc0 = fmaf(alpha, d0, acc0);
-                    acc1 = fmaf(alpha, d1, acc1);
-                    acc2 = fmaf(alpha, d2, acc2);
-                    dL_dalpha = fmaf(dL_dalpha, T, nTf_bg * rinv);
-                    s = a_raw * dL_dalpha;  // dL/dpower (the 0.99 clamp is straight-through)
+                asm volatile(
+                    "{\n\t"
+                    ".reg .pred pa;\n\t"
+                    "setp.le.f32 pa, %4, 0f00000000;\n\t"
+                    "setp.ge.and.f32 pa, %5, 0fC0FFD1BE, pa;\n\t"
+                    "setp.lt.and.s32 pa, %6, %7, pa;\n\t"
+                    "@pa mov.f32 %0, %8;\n\t"
+                    "@pa fma.rn.f32 %1, %9, %10, %1;\n\t"
+                    "@pa mul.rn.f32 %2, %11, %12;\n\t"
+                    "@pa mul.rn.f32 %3, %9, %8;\n\t"
+                    "}"
+                    : "+f"(T), "+f"(accdp), "+f"(s), "+f"(wgt)
+                    : "f"(pw), "f"(ee), "r"(gk), "r"(glast), "f"(Tn), "f"(alpha), "f"(dd), "f"(a_raw), "f"(dLa));
+                const uint32_t rowp = row0 + rowoff;
+                sts_f1(rowp, s);
+                sts_f1(rowp + (RbSmem::Wt - RbSmem::S), wgt);
+                if (rowoff == lane_row) {  // lane `slot` keeps the slot's identity
+                    mine.gk = (uint32_t)gk;
+                    upk2(mxy, mine.mx, mine.my);
                 }
-                sts_f1(mySW + nbuf * (RB_SROW * 4), s);
-                sts_f1(mySW + nbuf * (RB_SROW * 4) + (RbSmem::Wt - RbSmem::S), wgt);
-                {   // slot metadata, stored by all lanes to one address with one value (a single wavefront each):
-                    // the entry word comes by shuffle from the lane that owns the ballot bit
-                    const uint32_t mrow = mmeta + nbuf * 32;
-                    sts_u1(mrow, __shfl_sync(0xffffffffu, myw, j));
-                    sts_p2(mrow + 8, mxy);
-                    if (ABSGRAD) {  // natural-units conic for the |dL/dmean2D| statistic
-                        float A2, C2;
-                        upk2(AC, A2, C2);
-                        sts_f2(mrow + 16, A2 * (-2.0f * LN2), q1.x * (-LN2));
-                        sts_f1(mrow + 24, C2 * (-2.0f * LN2));
-                    }
-                }
-                if (++nbuf == RB_NB) {
-                    rb_phase2<ABSGRAD>(wbase, RB_NB, lane, px0f, py0f, sgrad);
-                    nbuf = 0;
-                }
+                const bool full = rowoff == (RB_NB - 1) * ROWB;
+                rowoff = full ? 0u : rowoff + ROWB;
+                if (full) rb_phase2<ABSGRAD>(wbase, RB_NB, lane, px0f, py0f, mine, plist, rec, sgrad);
             }
         }
     }
-    if (nbuf) rb_phase2<ABSGRAD>(wbase, nbuf, lane, px0f, py0f, sgrad);  // rows k >= nbuf are masked at the RED
+    const int nbuf = (int)(rowoff / ROWB);
+    if (nbuf) rb_phase2<ABSGRAD>(wbase, nbuf, lane, px0f, py0f, mine, plist, rec, sgrad);  // rows k >= nbuf are masked at the RED
 }
 
-cudaError_t launch_render_bwd(const Cam& cam, const uint32_t* tile_base, const uint32_t* plist, const float4* rec,
-                              const float* final_T, const uint32_t* n_contrib, const float* dL_dpix, float* sgrad,
-                              bool absgrad, const uint32_t* info, cudaStream_t st) {
+cudaError_t launch_render_bwd(const Cam& cam, const uint32_t* tile_order, const uint32_t* tile_base,
+                              const uint32_t* plist, const float4* rec, const float* final_T, const uint32_t* n_contrib,
+                              const float* dL_dpix, float* sgrad, bool absgrad, const uint32_t* info, cudaStream_t st) {
     const int T = cam.gx * cam.gy;
     if (T <= 0) return cudaSuccess;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(render_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RbSmem::total);
-        cudaFuncSetAttribute(render_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RbSmem::total);
-        attr_done = true;
+    // the dynamic shared-memory limit is a per-device, per-function attribute: set it on every launch (cheap, and right
+    // for a process that drives several devices or several host threads)
+    cudaError_t e;
+    if (absgrad) {
+        e = cudaFuncSetAttribute(render_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RbSmem::total);
+        if (e != cudaSuccess) return e;
+        render_bwd_kernel<true><<<T, RB_THREADS, RbSmem::total, st>>>(cam, tile_order, tile_base, plist, rec, final_T,
+                                                                      n_contrib, dL_dpix, sgrad, info);
+    } else {
+        e = cudaFuncSetAttribute(render_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RbSmem::total);
+        if (e != cudaSuccess) return e;
+        render_bwd_kernel<false><<<T, RB_THREADS, RbSmem::total, st>>>(cam, tile_order, tile_base, plist, rec, final_T,
+                                                                       n_contrib, dL_dpix, sgrad, info);
     }
-    if (absgrad)
-        render_bwd_kernel<true><<<T, RB_THREADS, RbSmem::total, st>>>(cam, tile_base, plist, rec, final_T, n_contrib,
-                                                                      dL_dpix, sgrad, info);
-    else
-        render_bwd_kernel<false><<<T, RB_THREADS, RbSmem::total, st>>>(cam, tile_base, plist, rec, final_T, n_contrib,
-                                                                       dL_dpix, sgrad, info);
     return cudaGetLastError();
 }
 

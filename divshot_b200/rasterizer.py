@@ -194,7 +194,7 @@ class Rasterizer:
 
     def debug_read(self, which: int) -> np.ndarray:
         s = self.stats()
-        N, D = s["num_gaussians"], s["num_dups"]
+        N, D = s["num_gaussians"], s["num_list_entries"]
         T = s["tiles_x"] * s["tiles_y"]
         P = self._cam.width * self._cam.height
         shapes = {

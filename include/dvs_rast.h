@@ -50,6 +50,12 @@ extern "C" {
                                        made by a later call (non-blocking) or by dvs_rast_get_stats (blocking).  Only
                                        honoured once a synchronous forward has sized the arena. */
 
+#define DVS_FLAG_TIGHT_LISTS 32u    /* forward, only together with DVS_FLAG_DEFER_CHECK (the training-loop mode): entries whose
+                                       {alpha >= 1/255} footprint misses their tile are not put into the tile lists.  Image,
+                                       final_T and gradients are unchanged; point_list / ranges are the whole-rectangle lists
+                                       of the credited rasterizer with exactly those entries removed, and n_contrib counts
+                                       positions in the shortened lists.  Without the flag the lists are the reference's. */
+
 typedef struct dvs_rast_ctx dvs_rast_ctx;
 
 typedef struct dvs_camera {
@@ -93,6 +99,8 @@ typedef struct dvs_stats {
     int64_t max_tile_len;  /* longest tile list */
     int32_t tiles_x, tiles_y;
     int32_t overflow;      /* 1 if the last forward needed a bigger arena (it was re-run) */
+    int32_t reserved_;
+    int64_t num_list_entries; /* entries actually in the tile lists (= num_dups unless DVS_FLAG_TIGHT_LISTS) */
 } dvs_stats;
 
 /* ids of internal buffers readable through dvs_rast_debug_read (parity tests only) */

@@ -59,7 +59,8 @@ def test_struct_layouts_match_header():
     from divshot_b200 import _cabi
     assert ctypes.sizeof(_cabi.DvsCamera) == 4 * (16 + 16 + 3 + 2 + 2 + 3 + 1 + 3)
     assert ctypes.sizeof(_cabi.DvsParams) == 6 * 8 and ctypes.sizeof(_cabi.DvsGrads) == 8 * 8
-    assert ctypes.sizeof(_cabi.DvsStats) == 5 * 8 + 3 * 4 + 4
+    assert ctypes.sizeof(_cabi.DvsStats) == 5 * 8 + 4 * 4 + 8  # ... overflow, reserved_, num_list_entries
+    assert _cabi.DvsStats.num_list_entries.offset == 56 and _cabi.DvsStats.overflow.offset == 48
 
 
 def test_new_entry_points_validate_their_arguments_without_a_gpu():
