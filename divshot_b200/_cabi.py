@@ -26,6 +26,7 @@ EXPORTS = [
     "dvs_rast_create", "dvs_rast_destroy", "dvs_rast_last_error", "dvs_rast_version", "dvs_rast_reserve",
     "dvs_rast_forward", "dvs_rast_backward", "dvs_rast_step_host", "dvs_rast_get_stats", "dvs_rast_debug_read",
     "dvs_rast_stage_ms", "dvs_rast_stage_name", "dvs_rast_forward_aux", "dvs_rast_backward_aux",
+    "dvs_rast_set_profiling",
 ]
 COLL_EXPORTS = ["dvs_coll_allreduce_nvls", "dvs_coll_sh_grad_from_dsh0"]
 
@@ -92,6 +93,9 @@ def load():
     L.dvs_rast_step_host.restype = C.c_int
     L.dvs_rast_get_stats.argtypes = [C.c_void_p, C.POINTER(DvsStats)]
     L.dvs_rast_get_stats.restype = C.c_int
+    if hasattr(L, "dvs_rast_set_profiling"):  # (absent from the round-1 build the A/B harness can load)
+        L.dvs_rast_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        L.dvs_rast_set_profiling.restype = C.c_int
     L.dvs_rast_debug_read.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
     L.dvs_rast_debug_read.restype = C.c_int
     L.dvs_rast_stage_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float * NUM_STAGES)]

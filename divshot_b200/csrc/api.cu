@@ -20,10 +20,13 @@
 
 using namespace dvs;
 
-#ifdef DVS_NO_TILE_ORDER  // A/B only: compositing CTAs in raster order
-#define DVS_TILE_ORDER(ctx) nullptr
-#else
+// Launch order of the compositing CTAs: raster order.  -DDVS_TILE_ORDER_LPT makes the tile scan write a longest-list-first
+// order and the compositors follow it; measured at c3 it changes nothing (profiles/r2_ab1_loops_tight_lpt.json: 0.8855 ms
+// without vs 0.8889 ms with), so it is not in the default build.
+#ifdef DVS_TILE_ORDER_LPT
 #define DVS_TILE_ORDER(ctx) (ctx)->tile_order
+#else
+#define DVS_TILE_ORDER(ctx) nullptr
 #endif
 
 struct dvs_rast_ctx {
@@ -82,6 +85,11 @@ struct dvs_rast_ctx {
     cudaEvent_t ev_check = nullptr;
     bool pending_check = false;
     bool arena_sized = false;      // a synchronous forward has validated the capacity
+    // the tile scan leaves the tile counters, the V / D accumulators and the bin-overflow word zeroed for the next forward;
+    // anything that breaks that hand-over (first use, two-pass cursors, an error between launches) sets these and the
+    // next forward clears them with memsets
+    bool count_dirty = true, cursor_dirty = true, words_dirty = true;
+    bool profiling = true;         // record the per-stage CUDA events (dvs_rast_set_profiling)
     uint32_t seen_overflows = 0;   // value of the sticky device counter info[3] already handled
 };
 
@@ -99,6 +107,12 @@ static int fail(dvs_rast_ctx* c, int code, const char* fmt, ...) {
         cudaError_t e__ = (call);                                                                          \
         if (e__ != cudaSuccess)                                                                            \
             return fail(ctx, DVS_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+// per-stage timing events (only while profiling is on: dvs_rast_set_profiling)
+#define EV(i)                                                    \
+    do {                                                         \
+        if (ctx->profiling) CK(cudaEventRecord(ctx->ev[i], st)); \
     } while (0)
 
 template <typename T>
@@ -126,6 +140,7 @@ static int ensure_tiles(dvs_rast_ctx* ctx, int64_t T) {
     CK(regrow(ctx->class_tiles, 5 * (size_t)T));
     CK(regrow(ctx->tile_order, (size_t)T));
     ctx->cap_tiles = T;
+    ctx->count_dirty = ctx->cursor_dirty = true;
     return DVS_OK;
 }
 static int ensure_dups(dvs_rast_ctx* ctx, int64_t D) {
@@ -155,11 +170,14 @@ static int ensure_pix(dvs_rast_ctx* ctx, int64_t P) {
     return DVS_OK;
 }
 
+static inline uint64_t info_v(const dvs_rast_ctx* ctx) { return (uint64_t)ctx->h_info[12] | ((uint64_t)ctx->h_info[13] << 32); }
+static inline uint64_t info_d(const dvs_rast_ctx* ctx) { return (uint64_t)ctx->h_info[14] | ((uint64_t)ctx->h_info[15] << 32); }
+
 static void publish_stats(dvs_rast_ctx* ctx) {
-    ctx->st.num_visible = (int64_t)ctx->h_stats[0];
+    ctx->st.num_visible = (int64_t)info_v(ctx);
     ctx->st.num_list_entries = (int64_t)ctx->h_info[0];
     // D of SURVEY.md section 8(d) = sum of tiles_touched, whatever the lists hold (with DVS_FLAG_TIGHT_LISTS they hold fewer)
-    ctx->st.num_dups = (int64_t)ctx->h_stats[1];
+    ctx->st.num_dups = (int64_t)info_d(ctx);
     ctx->st.dup_capacity = ctx->cap_dups;
     ctx->st.max_tile_len = ctx->h_info[1];
 }
@@ -324,39 +342,47 @@ int dvs_rast_forward(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, const 
     const bool fused = defer && ctx->bin_stride > 0 && ctx->bin_stride_tiles == T &&
                        (int64_t)ctx->bin_stride * T <= ctx->cap_bins && !force_two_pass;
     for (int attempt = 0; attempt < 3; attempt++) {
-        CK(cudaMemsetAsync(fused ? ctx->tile_cursor : ctx->tile_count, 0, (size_t)T * TILE_CTR_STRIDE * sizeof(uint32_t), st));
-        CK(cudaMemsetAsync(ctx->stats, 0, 2 * sizeof(unsigned long long), st));
-        CK(cudaMemsetAsync(ctx->info + 10, 0, sizeof(uint32_t), st));
-        CK(cudaEventRecord(ctx->ev[0], st));
+        uint32_t* counters = fused ? ctx->tile_cursor : ctx->tile_count;
+        if (fused ? ctx->cursor_dirty : ctx->count_dirty)
+            CK(cudaMemsetAsync(counters, 0, (size_t)ctx->cap_tiles * TILE_CTR_STRIDE * sizeof(uint32_t), st));
+        if (ctx->words_dirty) {
+            CK(cudaMemsetAsync(ctx->stats, 0, 2 * sizeof(unsigned long long), st));
+            CK(cudaMemsetAsync(ctx->info + 10, 0, sizeof(uint32_t), st));
+        }
+        ctx->count_dirty = ctx->cursor_dirty = ctx->words_dirty = true;  // until the scan below has been enqueued
+        EV(0);
         const FusedEmit fe{ctx->tile_cursor, ctx->bins, fused ? ctx->bin_stride : 0u, ctx->info + 10,
                            (fused && (cam->flags & DVS_FLAG_TIGHT_LISTS)) ? 1u : 0u};
         CK(launch_preprocess_fwd(c, (int)N, prm, ctx->rec, ctx->aux, ctx->tile_count, out_radii, ctx->stats, fe, st));
-        CK(cudaEventRecord(ctx->ev[1], st));
+        EV(1);
         if (fused) {
             CK(launch_tile_scan((int)T, ctx->tile_cursor, ctx->tile_base, nullptr, ctx->info, (uint32_t)ctx->cap_dups,
-                                ctx->class_tiles, ctx->tile_order, st));
-            CK(cudaEventRecord(ctx->ev[2], st));
+                                ctx->class_tiles, DVS_TILE_ORDER(ctx), ctx->stats, st));
+            ctx->cursor_dirty = false;  // zeroed as read
+            ctx->count_dirty = false;   // untouched
+            EV(2);
         } else {
             CK(launch_tile_scan((int)T, ctx->tile_count, ctx->tile_base, ctx->tile_cursor, ctx->info,
-                                (uint32_t)ctx->cap_dups, ctx->class_tiles, ctx->tile_order, st));
-            CK(cudaEventRecord(ctx->ev[2], st));
+                                (uint32_t)ctx->cap_dups, ctx->class_tiles, DVS_TILE_ORDER(ctx), ctx->stats, st));
+            ctx->count_dirty = false;   // zeroed as read; tile_cursor now holds the emission cursors (dirty)
+            EV(2);
             CK(launch_emit(c, (int)N, ctx->aux, ctx->rec, ctx->tile_cursor, ctx->bins, (uint32_t)ctx->cap_dups, st));
         }
-        CK(cudaEventRecord(ctx->ev[3], st));
+        ctx->words_dirty = false;
+        EV(3);
         CK(launch_tile_sort((int)T, fused ? ctx->bin_stride : 0u, ctx->tile_base, ctx->bins, ctx->plist, ctx->info,
                             ctx->class_tiles, st));
-        CK(cudaEventRecord(ctx->ev[4], st));
+        EV(4);
         CK(launch_render_fwd(c, DVS_TILE_ORDER(ctx), ctx->tile_base, ctx->plist, ctx->rec, out_color, ctx->final_T, ctx->n_contrib,
                              ctx->info, st));
-        CK(cudaEventRecord(ctx->ev[5], st));
+        EV(5);
         CK(cudaMemcpyAsync(ctx->h_info, ctx->info, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(ctx->h_stats, ctx->stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         if (defer) {  // no host synchronisation: validated later by resolve_pending()
             CK(cudaEventRecord(ctx->ev_check, st));
             ctx->pending_check = true;
             ctx->cam = c; ctx->N = N;
             ctx->st.num_gaussians = N; ctx->st.tiles_x = c.gx; ctx->st.tiles_y = c.gy;
-            ctx->have_fwd = true; ctx->ev_fwd = true;
+            ctx->have_fwd = true; ctx->ev_fwd = ctx->profiling;
             return DVS_OK;
         }
         CK(cudaStreamSynchronize(st));
@@ -364,7 +390,7 @@ int dvs_rast_forward(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, const 
         if (!ctx->h_info[2]) break;
         // arena too small: grow to the exact need (+25%) and run the forward again
         ctx->st.overflow = 1;
-        const int64_t need = (int64_t)ctx->h_stats[1];
+        const int64_t need = (int64_t)info_d(ctx);
         if ((rc = ensure_dups(ctx, need + need / 4 + 4096))) return rc;
         if (attempt == 2) return fail(ctx, DVS_E_NOMEM, "binning arena overflow persisted");
     }
@@ -393,7 +419,7 @@ int dvs_rast_forward(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, const 
         ctx->arena_sized = true;
     }
     ctx->have_fwd = true;
-    ctx->ev_fwd = true;
+    ctx->ev_fwd = ctx->profiling;
     return DVS_OK;
 }
 
@@ -427,14 +453,14 @@ int dvs_rast_backward(dvs_rast_ctx* ctx, const dvs_params* params, const float* 
         g = Grads{grads->means3D, grads->scales, grads->quats, grads->opacities, grads->sh0, grads->shN,
                   (flags & DVS_FLAG_ABSGRAD) ? grads->mean2D_abs : nullptr, grads->mean2D};
     }
-    CK(cudaEventRecord(ctx->ev[6], st));
+    EV(6);
     CK(launch_render_bwd(c, DVS_TILE_ORDER(ctx), ctx->tile_base, ctx->plist, ctx->rec, ctx->final_T, ctx->n_contrib, dL_dpix,
                          reinterpret_cast<float*>(ctx->sgrad), (flags & DVS_FLAG_ABSGRAD) && g.mean2D_abs,
                          ctx->info, st));
-    CK(cudaEventRecord(ctx->ev[7], st));
+    EV(7);
     CK(launch_preprocess_bwd(c, (int)N, prm, ctx->aux, ctx->sgrad, g, flags, st));
-    CK(cudaEventRecord(ctx->ev[8], st));
-    ctx->ev_bwd = true;
+    EV(8);
+    ctx->ev_bwd = ctx->profiling;
     return DVS_OK;
 }
 
@@ -513,7 +539,7 @@ int dvs_rast_backward_aux(dvs_rast_ctx* ctx, const dvs_params* params, const flo
         g = Grads{grads->means3D, grads->scales, grads->quats, grads->opacities, grads->sh0, grads->shN,
                   (flags & DVS_FLAG_ABSGRAD) ? grads->mean2D_abs : nullptr, grads->mean2D};
     }
-    CK(cudaEventRecord(ctx->ev[6], st));
+    EV(6);
     Cam c0 = c;  // the auxiliary passes composite over a zero background
     c0.bg[0] = c0.bg[1] = c0.bg[2] = 0.0f;
     if (dL_daux) {
@@ -536,7 +562,7 @@ int dvs_rast_backward_aux(dvs_rast_ctx* ctx, const dvs_params* params, const flo
     // 3. the colour loss adds its geometry sums on top, then the per-Gaussian backward consumes the total
     CK(launch_render_bwd(c, DVS_TILE_ORDER(ctx), ctx->tile_base, ctx->plist, ctx->rec, ctx->final_T, ctx->n_contrib, dL_dpix,
                          reinterpret_cast<float*>(ctx->sgrad), (flags & DVS_FLAG_ABSGRAD) && g.mean2D_abs, ctx->info, st));
-    CK(cudaEventRecord(ctx->ev[7], st));
+    EV(7);
     CK(launch_preprocess_bwd(c, (int)N, prm, ctx->aux, ctx->sgrad, g, flags, st));
     // 4. dL/dmean += (row 2 of the view matrix) * dL/dz ;  dL/dquat += d n / d quat ^T dL/dn
     if (N > 0 && dL_daux) {
@@ -544,8 +570,8 @@ int dvs_rast_backward_aux(dvs_rast_ctx* ctx, const dvs_params* params, const flo
         CK(launch_aux_depth_grad((int)N, ctx->aux_dz, row2, g.means3D, st));
     }
     if (N > 0 && dL_dnormal) CK(launch_aux_normal_grad(c, (int)N, prm, ctx->aux_dn, g.quats, st));
-    CK(cudaEventRecord(ctx->ev[8], st));
-    ctx->ev_bwd = true;
+    EV(8);
+    ctx->ev_bwd = ctx->profiling;
     return DVS_OK;
 }
 
@@ -581,6 +607,13 @@ int dvs_rast_step_host(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, cons
     CK(cudaStreamWaitEvent(st, ctx->ev_d2h, 0));
     CK(cudaStreamSynchronize(st));
     return resolve_pending(ctx, true);  // DVS_E_OVERFLOW if a deferred-check forward overflowed (redo the step)
+}
+
+int dvs_rast_set_profiling(dvs_rast_ctx* ctx, int on) {
+    if (!ctx) return DVS_E_INVALID;
+    ctx->profiling = on != 0;
+    if (!ctx->profiling) ctx->ev_fwd = ctx->ev_bwd = false;
+    return DVS_OK;
 }
 
 int dvs_rast_get_stats(dvs_rast_ctx* ctx, dvs_stats* out) {

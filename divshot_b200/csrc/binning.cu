@@ -43,15 +43,21 @@ __device__ __forceinline__ uint32_t order_bucket(uint32_t len) {  // bucket 0 = 
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS)
-tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_base,
+tile_scan_kernel(int T, uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_base,
                  uint32_t* __restrict__ tile_cursor /* nullptr: single-pass mode, counts ARE the cursors */,
                  uint32_t* __restrict__ info, uint32_t dup_capacity,
                  uint32_t* __restrict__ class_tiles /* [NUM_SORT_CLASSES][T] */,
-                 uint32_t* __restrict__ tile_order /* [T]: all tiles, longest lists first */) {
+                 uint32_t* __restrict__ tile_order /* [T] or nullptr: all tiles, longest lists first */,
+                 unsigned long long* __restrict__ stats /* [2]: V, D accumulated by the preprocess kernel */) {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t warp_max[32];
     __shared__ uint32_t s_hist[ORDER_BUCKETS + 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // housekeeping that used to be four memset launches per forward: the per-class counters are zeroed here, the tile
+    // counters are zeroed as they are read (they are dead afterwards: the sort works from tile_base), and thread 0
+    // publishes and clears the forward's V / D accumulators and the bin-overflow word at the end
+    if (threadIdx.x < NUM_SORT_CLASSES) info[4 + threadIdx.x] = 0u;
+    __syncthreads();
     // chunked over [0,T) in slabs of SCAN_THREADS * SCAN_MAX_PER_THREAD; within a slab thread t owns the
     // SCAN_MAX_PER_THREAD consecutive tiles starting at slab + t * SCAN_MAX_PER_THREAD (all loads in flight at once)
     unsigned long long carry = 0;
@@ -65,6 +71,9 @@ tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint32_t* __res
             const int t = first + k;
             c[k] = t < T ? tile_count[(size_t)t * TILE_CTR_STRIDE] : 0u;
         }
+#pragma unroll
+        for (int k = 0; k < SCAN_MAX_PER_THREAD; k++)
+            if (first + k < T && c[k]) tile_count[(size_t)(first + k) * TILE_CTR_STRIDE] = 0u;
 #pragma unroll
         for (int k = 0; k < SCAN_MAX_PER_THREAD; k++) { sum += c[k]; mx = max(mx, c[k]); }
         uint32_t v = sum;  // inclusive warp scan of the per-thread sums
@@ -144,6 +153,11 @@ tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint32_t* __res
         const bool ovf = carry > (unsigned long long)dup_capacity || info[10] != 0u;  // info[10]: a fixed-stride bin overflowed
         info[2] = ovf ? 1u : 0u;
         if (ovf) { info[3] += 1u; info[9] = (uint32_t)min(carry, 0xffffffffull); }  // sticky (deferred-check mode)
+        info[10] = 0u;
+        // V and D of this forward -> info[12..15] (what the host reads back), accumulators cleared for the next one
+        const unsigned long long v = stats[0], d = stats[1];
+        info[12] = (uint32_t)v; info[13] = (uint32_t)(v >> 32); info[14] = (uint32_t)d; info[15] = (uint32_t)(d >> 32);
+        stats[0] = 0ull; stats[1] = 0ull;
     }
     if (tile_order) {
         // tile_base[] was written by this CTA above: visible to all its threads after the barrier
@@ -171,13 +185,11 @@ tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint32_t* __res
     }
 }
 
-cudaError_t launch_tile_scan(int T, const uint32_t* tile_count, uint32_t* tile_base, uint32_t* tile_cursor,
+cudaError_t launch_tile_scan(int T, uint32_t* tile_count, uint32_t* tile_base, uint32_t* tile_cursor,
                              uint32_t* info, uint32_t dup_capacity, uint32_t* class_tiles, uint32_t* tile_order,
-                             cudaStream_t st) {
-    cudaError_t e = cudaMemsetAsync(info + 4, 0, NUM_SORT_CLASSES * sizeof(uint32_t), st);
-    if (e != cudaSuccess) return e;
+                             unsigned long long* stats, cudaStream_t st) {
     tile_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(T, tile_count, tile_base, tile_cursor, info, dup_capacity,
-                                                 class_tiles, tile_order);
+                                                 class_tiles, tile_order, stats);
     return cudaGetLastError();
 }
 

@@ -13,11 +13,13 @@ cudaError_t launch_preprocess_fwd(const Cam& cam, int N, const Params& prm, floa
                                   const FusedEmit& fe, cudaStream_t st);
 
 // A2/A5: exclusive scan of tile counts -> tile_base[T+1], cursor[T]; info[0]=D, info[1]=max len, info[2]=overflow,
-// info[4..8] = tiles per sort class, class_tiles[5][T] = their ids; tile_order[T] = all tiles, longest lists first
-// (the launch order of the compositing CTAs)
-cudaError_t launch_tile_scan(int T, const uint32_t* tile_count, uint32_t* tile_base, uint32_t* tile_cursor,
+// info[4..8] = tiles per sort class, class_tiles[5][T] = their ids; tile_order[T] (optional) = all tiles, longest lists
+// first (a launch order for the compositing CTAs; measured useless at c3, profiles/r2_ab1_loops_tight_lpt.json).
+// Also the forward's housekeeping: zeroes the tile counters it has read, publishes V / D (stats -> info[12..15]) and
+// clears the accumulators and the bin-overflow word for the next forward (no memset launches in the step).
+cudaError_t launch_tile_scan(int T, uint32_t* tile_count, uint32_t* tile_base, uint32_t* tile_cursor,
                              uint32_t* info, uint32_t dup_capacity, uint32_t* class_tiles, uint32_t* tile_order,
-                             cudaStream_t st);
+                             unsigned long long* stats, cudaStream_t st);
 
 // A3 (two-pass mode): emit (depth | id | sub-tile mask) entries into per-tile bins
 cudaError_t launch_emit(const Cam& cam, int N, const uint4* aux, const float4* rec, uint32_t* tile_cursor,

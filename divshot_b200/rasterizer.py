@@ -182,6 +182,11 @@ class Rasterizer:
                                                  dL_dpix_host.data_ptr(), out_color_host.data_ptr(), flags,
                                                  C.c_void_p(st)))
 
+    def set_profiling(self, on: bool):
+        """Per-stage CUDA events on/off (off in a training loop; stage_ms() needs them on)."""
+        if hasattr(self._lib, "dvs_rast_set_profiling"):
+            self._check(self._lib.dvs_rast_set_profiling(self._h, int(on)))
+
     def stats(self) -> dict:
         s = _cabi.DvsStats()
         self._check(self._lib.dvs_rast_get_stats(self._h, C.byref(s)))

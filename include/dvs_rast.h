@@ -183,6 +183,10 @@ DVS_API int dvs_rast_step_host(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t
 
 DVS_API int dvs_rast_get_stats(dvs_rast_ctx* ctx, dvs_stats* out);
 
+/* Per-stage CUDA events (dvs_rast_stage_ms) are recorded only while profiling is on (default: on).  A training loop
+ * turns it off: nine event records per step are launch-queue work the step does not need. */
+DVS_API int dvs_rast_set_profiling(dvs_rast_ctx* ctx, int on);
+
 /* Copy an internal buffer of the last forward/backward to HOST memory (parity tests). */
 DVS_API int dvs_rast_debug_read(dvs_rast_ctx* ctx, int which, void* dst_host, size_t dst_bytes);
 
