@@ -242,6 +242,9 @@ def main():
     ap.add_argument("--workload", default=None, help="override: c2|c3|c5 (parity/bench exploration only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-rows", action="store_true", help="skip the sub-process measurement of the other section-8 rows")
+    ap.add_argument("--no-tight", action="store_true",
+                    help="timed steps keep the whole-rectangle tile lists (default: DVS_FLAG_TIGHT_LISTS — entries whose sub-tile "
+                         "mask is empty are not emitted; image and gradients are bit-identical, tests/test_gpu_parity.py)")
     ap.add_argument("--allreduce", default="auto", choices=["auto", "nvls", "nccl", "factored"],
                     help="gradient exchange: NVSwitch in-switch reduction over symmetric memory, plain NCCL, or the factored "
                          "exchange (all-gather dL/dsh0, all-reduce 56 B/Gaussian, form dL/dshN locally); auto = the fastest "
@@ -312,14 +315,15 @@ def main():
     if fx is not None:
         exchange = choose_exchange(args, reducer, fx, grads, params, campos, deg, dev, dist, torch)
 
+    # the training-loop mode: no host synchronisation per step, single-pass binning, tight tile lists
+    cam_defer = _cabi.DvsCamera.from_buffer_copy(cam)
+    cam_defer.flags |= _cabi.FLAG_DEFER_CHECK | (0 if args.no_tight else _cabi.FLAG_TIGHT_LISTS)
+
     def step_resident():
-        rast.forward(cam, params, img, radii, defer_check=True)
+        rast.forward(cam_defer, params, img, radii, defer_check=True)
         rast.backward(dl, grads)
         if world > 1:
             exchange()
-
-    cam_defer = _cabi.DvsCamera.from_buffer_copy(cam)
-    cam_defer.flags |= _cabi.FLAG_DEFER_CHECK
 
     def step_e2e():
         rast.step_host(cam_defer, params, grads, dl_host, img_host)
@@ -357,7 +361,7 @@ def main():
     stage_ms = {}
     reps = 5
     for _ in range(reps):
-        rast.forward(cam, params, img, radii, defer_check=True)  # same mode as the timed steps
+        rast.forward(cam_defer, params, img, radii, defer_check=True)  # same mode as the timed steps
         rast.backward(dl, grads)
         for k, v in rast.stage_ms().items():
             stage_ms[k] = stage_ms.get(k, 0.0) + v / reps
@@ -400,6 +404,10 @@ def main():
                                + (", NCCL all-reduce of the dense gradient arena" if world > 1 else ""),
                    "N": N, "width": W, "height": H, "sh_degree": deg, "views_per_step": world,
                    "visible": V, "duplicates": D, "tiles": T, "max_tile_len": st["max_tile_len"],
+                   "list_entries": st["num_list_entries"],
+                   "tile_lists": ("whole-rectangle (reference-exact)" if args.no_tight else
+                                  "tight: the reference-exact lists minus the entries whose sub-tile mask is empty "
+                                  "(DVS_FLAG_TIGHT_LISTS; image and gradients bit-identical, D counts all duplicates)"),
                    "l2": "inputs larger than L2 (params+grads 472 MB + 96 MB records/lists per step); no explicit flush",
                    "parallelism": f"dp{world} (view-sharded replicas)",
                    "host_sync": "none per step (binning arena validated by deferred check, DVS_FLAG_DEFER_CHECK; "

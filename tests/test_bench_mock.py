@@ -47,7 +47,7 @@ class _FakeRasterizer:
         return {k: 0.1 + 0.01 * i for i, k in enumerate(STAGES)}
 
     def stats(self):
-        return {"num_visible": 8000, "num_dups": 60000, "tiles_x": 16, "tiles_y": 16, "max_tile_len": 400}
+        return {"num_visible": 8000, "num_dups": 60000, "tiles_x": 16, "tiles_y": 16, "max_tile_len": 400, "num_list_entries": 40000}
 
     def close(self):
         pass

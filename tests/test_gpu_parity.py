@@ -332,3 +332,57 @@ def test_zero_gaussians(rast):
     g = GradBuffers.allocate(0, 0, dev)
     rast.backward(torch.ones(3, 34, 50, device=dev), g)
     torch.cuda.synchronize()
+
+
+def test_tight_lists_are_the_reference_lists_minus_empty_masks():
+    """DVS_FLAG_TIGHT_LISTS (training-loop mode, what bench.py times): entries whose sub-tile mask is empty are not emitted.
+    The tight lists must be exactly the reference-exact whole-rectangle lists with those entries removed (same order),
+    n_contrib must count in them, and image / final_T must be bit-identical, gradients equal up to atomic ordering."""
+    from divshot_b200.rasterizer import GradBuffers, Rasterizer, scene_to_device
+    sc = make_scene(N=8000, width=160, height=112, sh_degree=1, seed=93, normalise_quats=False, bg=(0.1, 0.3, 0.2))
+    sc.log_scales += 0.6
+    r = Rasterizer(0)
+    try:
+        dev = r.device
+        params = scene_to_device(sc, dev)
+        cam = _cabi.make_camera(sc.cameras[0], 1)
+        cam_t = _cabi.make_camera(sc.cameras[0], 1, flags=_cabi.FLAG_TIGHT_LISTS)
+        dl = torch.from_numpy(sc.dL_dpix[0]).to(dev)
+        r.forward(cam, params); r.forward(cam, params)      # synchronous: size the arena and the bin stride
+        f, _ = _oracle(sc, bwd=False)
+
+        def run(c):
+            img, _ = r.forward(c, params, defer_check=True)
+            g = GradBuffers.allocate(sc.N, 3, dev); r.backward(dl, g)
+            torch.cuda.synchronize()
+            return dict(img=img.cpu().numpy(), g=g.flat.cpu().numpy(), st=r.stats(), pl=r.debug_read(_cabi.BUF_POINT_LIST),
+                        rg=r.debug_read(_cabi.BUF_RANGES), mk=r.debug_read(_cabi.BUF_CULL_MASK),
+                        T=r.debug_read(_cabi.BUF_FINAL_T), nc=r.debug_read(_cabi.BUF_N_CONTRIB))
+        full, tight = run(cam), run(cam_t)
+        assert np.array_equal(full["pl"], f.point_list) and np.array_equal(full["rg"], f.ranges)
+        keep = full["mk"] != 0
+        assert 0.2 < keep.mean() < 0.95, "the scene must have both kinds of entries"
+        assert tight["st"]["num_dups"] == full["st"]["num_dups"] == f.D
+        assert tight["st"]["num_list_entries"] == int(keep.sum()) == tight["pl"].size
+        assert np.array_equal(tight["pl"], full["pl"][keep]), "tight list != full list minus empty-mask entries"
+        assert np.array_equal(tight["mk"], full["mk"][keep])
+        # ranges and n_contrib: positions in the tight lists = number of kept entries before the position in the full lists
+        before = np.concatenate([[0], np.cumsum(keep)]).astype(np.int64)
+        W, H = 160, 112
+        gx = (W + 15) // 16
+        for tile in range(full["rg"].shape[0]):
+            a, b = (int(v) for v in full["rg"][tile])
+            ta, tb = (int(v) for v in tight["rg"][tile])
+            assert tb - ta == before[b] - before[a]
+            if tb > ta:
+                assert ta == before[a]
+        ys, xs = np.mgrid[0:H, 0:W]
+        tile_of = (ys // 16) * gx + xs // 16
+        a_full = full["rg"][tile_of.ravel(), 0].astype(np.int64)
+        nc_f, nc_t = full["nc"].astype(np.int64), tight["nc"].astype(np.int64)
+        expect = np.where(nc_f > 0, before[a_full + nc_f] - before[a_full], 0)
+        assert np.array_equal(nc_t, expect), "n_contrib of the tight lists"
+        assert np.array_equal(tight["img"], full["img"]) and np.array_equal(tight["T"], full["T"])
+        assert rel_err(tight["g"], full["g"]) < 5e-5
+    finally:
+        r.close()
