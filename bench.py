@@ -76,12 +76,27 @@ class ClockSampler:
         return out
 
 
-# DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of each stage's kernels at c3 on one B200,
-# from the committed `ncu --set full` capture profiles/r1_v4_step_ncu_full.md (MB).  Only valid for workload c3.
-NCU_TRAFFIC_MB_C3 = {"preprocess_fwd": 236.79 + 96.09, "binning_sort": 0.23 + 61.45 + 4.09 + 0.1,
-                     "render_fwd": 39.36 + 3.66, "render_bwd": 62.05 + 2.20, "preprocess_bwd": 288.06 + 228.73}
-NCU_ISSUE_ACTIVE_PCT_C3 = {"preprocess_fwd": 71.3, "render_fwd": 89.1, "render_bwd": 72.6, "preprocess_bwd": 50.0}
-NCU_SMEM_WAVEFRONT_PCT_C3 = {"render_bwd": 64.6}  # l1tex__data_pipe_lsu_wavefronts_mem_shared, % of peak
+# Roofline side-fields (DRAM traffic per launch = dram__bytes_read.sum + dram__bytes_write.sum, issue-active %, shared-memory
+# wavefront %) come from the committed summary of the `ncu --set full --clock-control none` capture of the CURRENT build:
+# profiles/ncu_step.json, written by tools/ncu_summary.py from the .ncu-rep (never typed in by hand).  Valid for workload c3.
+STAGE_KERNELS = {"preprocess_fwd": ("preprocess_fwd_kernel",),
+                 "binning_sort": ("tile_scan_kernel", "emit_kernel", "tile_bucket_sort_kernel", "tile_bitonic_sort_kernel"),
+                 "render_fwd": ("render_fwd_kernel",), "render_bwd": ("render_bwd_kernel",),
+                 "preprocess_bwd": ("preprocess_bwd_kernel",)}
+
+
+def ncu_side_fields(stage):
+    """(traffic bytes per step, issue-active % and shared wavefront % of the stage's longest kernel, source) or Nones."""
+    p = os.path.join(ROOT, "profiles", "ncu_step.json")
+    if not os.path.exists(p):
+        return None, None, None, None
+    d = json.load(open(p))
+    ks = {k: v for k, v in d["kernels"].items() if k.split("<")[0] in STAGE_KERNELS[stage]}
+    if not ks:
+        return None, None, None, None
+    top = max(ks.values(), key=lambda v: v["time_us"])
+    return (sum(v["dram_MB"] for v in ks.values()) * 1e6, top["issue_active_pct"], top["smem_wavefront_pct"],
+            f"profiles/{d.get('summary', 'ncu_step.json')} (from {d['source']}, ncu --set full --clock-control none, per launch)")
 
 
 def algorithmic_bytes(N, K, V, D, T, P):
@@ -100,8 +115,9 @@ def algorithmic_bytes(N, K, V, D, T, P):
 _BEST_THREADS = None
 
 
-def run_cpu_sample(threads=0, reps=1, frac_lin=2):
-    """Oracle (port) fwd+bwd on a density-preserving 1/frac_lin^2 crop of the workload; returns Gaussians/s.
+def run_cpu_sample(threads=0, reps=1, frac_lin=1):
+    """Oracle (port) fwd+bwd on the workload itself (frac_lin = 1: the same configuration as the GPU arm; a density-preserving
+    1/frac_lin^2 crop is kept for exploration); returns Gaussians/s.
     threads <= 0: all the host threads it can use — the count is chosen once by timing the sample at the affinity
     count and at 1/2, 1/4, 1/8 of it (the OpenMP oracle stops scaling on large multi-socket hosts), best kept."""
     global _BEST_THREADS
@@ -132,7 +148,8 @@ def run_cpu_sample(threads=0, reps=1, frac_lin=2):
             _BEST_THREADS = min(timing, key=timing.get)
         threads = _BEST_THREADS
     times = [once(threads) for _ in range(reps)]
-    sample = (f"oracle port, density-preserving 1/{frac_lin * frac_lin} crop of {WORKLOAD}: {sc.N} Gaussians, "
+    what = f"the full workload {WORKLOAD}" if frac_lin == 1 else f"density-preserving 1/{frac_lin * frac_lin} crop of {WORKLOAD}"
+    sample = (f"oracle port, {what}: {sc.N} Gaussians, "
               f"{cam.width}x{cam.height}, SH deg {sc.sh_degree}, fwd+bwd, OpenMP over Gaussians/tiles, "
               f"{threads} threads (best of the affinity count and its 1/2, 1/4, 1/8)")
     return sc.N, times, threads, sample
@@ -220,12 +237,16 @@ def reference_arm(args):
     for _ in range(args.warmup):
         run_cpu_sample(reps=1)
     n, times, cores, sample = run_cpu_sample(reps=args.steps)
+    from divshot_b200.scenes import CONFIGS
+    _, _, W, H, deg, _ = CONFIGS[WORKLOAD]
     total = sum(times)
     val = n * args.steps / total
     line = {"impl": "reference", "metric": "fwd+bwd Gaussians/s", "value": val, "unit": "Gaussians/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{WORKLOAD} (1M Gaussians, 1600x1000, SH deg 3), CPU arm on a bounded sample"},
+            # the same workload as the GPU arm at N=1, whole (not a crop), on the host cores
+            "config": {"workload": f"{WORKLOAD}: {n} Gaussians, {W}x{H}, SH deg {deg}, 1 view per rank per step",
+                       "N": n, "width": W, "height": H, "sh_degree": deg, "views_per_step": 1},
             "cpu_baseline": {"value": val, "unit": "Gaussians/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "Gaussians/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -394,6 +415,9 @@ def main():
                   "frac_hbm": round(stage_bytes[k] / 1e9 / (merged[k] * 1e-3) / peak, 4) if merged[k] > 0 else None}
               for k in merged}
     dom_gbs = stage_bytes[dominant] / 1e9 / (merged[dominant] * 1e-3)
+    side = ncu_side_fields(dominant) if WORKLOAD == "c3" else (None, None, None, None)
+    for k in stages:  # DRAM traffic per stage from the same capture (well above alg_MB = wasted re-reads)
+        stages[k]["ncu_dram_MB"] = (round(ncu_side_fields(k)[0] / 1e6, 2) if WORKLOAD == "c3" and ncu_side_fields(k)[0] else None)
     step_gbs = total_bytes / 1e9 / (ms_step * 1e-3) if world == 1 else None
 
     line = {
@@ -414,10 +438,7 @@ def main():
                                 "single-pass binning into fixed-stride tile bins sized by the warm-up forwards)"},
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": dom_gbs, "peak": peak, "unit": "GB/s",
                      "frac": dom_gbs / peak,
-                     "traffic": (NCU_TRAFFIC_MB_C3.get(dominant, 0) * 1e6 if WORKLOAD == "c3" else None),
-                     "traffic_source": "profiles/r1_v4_step_ncu_full.md (ncu --set full, per launch)",
-                     "issue_active_pct": NCU_ISSUE_ACTIVE_PCT_C3.get(dominant) if WORKLOAD == "c3" else None,
-                     "smem_wavefront_pct": NCU_SMEM_WAVEFRONT_PCT_C3.get(dominant) if WORKLOAD == "c3" else None,
+                     "traffic": side[0], "traffic_source": side[3], "issue_active_pct": side[1], "smem_wavefront_pct": side[2],
                      "peak_source": peak_src,
                      "note": "algorithmic bytes per SURVEY.md §8(d) / CUDA-event stage time.  The dominant kernel is the "
                              "compositing backward: 256*D potential pair evaluations against ~0.12 GB of compulsory "

@@ -459,7 +459,13 @@ bool parse_ply_header(const std::vector<uint8_t>& f, PlyHeader* h) {
         const size_t e = nl ? static_cast<size_t>(nl - f.data()) : f.size();
         const std::string line(reinterpret_cast<const char*>(f.data() + p), e - p);
         p = e + 1;
-        if (line == "end_header") { h->body = p; return true; }
+        if (line == "end_header") {
+            // the payload starts after the newline that ends the header: a file that stops at "end_header" without one
+            // has no payload position (p would be size + 1 and every later size check would wrap)
+            if (!nl) { g_err = "PLY: truncated header"; return false; }
+            h->body = p;
+            return true;
+        }
         std::string a, b, name;
         std::istringstream ss(line);
         if (line.find("anti_aliasing=1") != std::string::npos) h->antialiased = true;

@@ -25,6 +25,16 @@ struct Rasterizer : torch::CustomClassHolder {
     int64_t device = 0;
     std::vector<Tensor> saved;  // the six parameter tensors of the last forward (kept alive for backward)
     int64_t last_h = 0, last_w = 0;
+    // The forward state (tile lists, final_T, n_contrib, records, camera) lives in the context, ONE copy: only the most
+    // recent forward can be differentiated.  Every forward bumps `generation`; the autograd nodes remember the value they
+    // were created with and refuse to run a backward against another forward's state (two views rendered with the same
+    // Rasterizer before (loss1 + loss2).backward() would otherwise get silently wrong gradients).  Use one Rasterizer per
+    // view that is alive at the same time.
+    int64_t generation = 0;
+    void check_generation(int64_t g) const {
+        TORCH_CHECK(g == generation, "dvs::Rasterizer: backward of forward #", g, " but the context holds the state of forward #",
+                    generation, " — a Rasterizer keeps ONE outstanding forward; render concurrent views with separate Rasterizers");
+    }
 
     explicit Rasterizer(int64_t dev) : device(dev) {
         TORCH_CHECK(dvs_rast_create((int)dev, &ctx) == DVS_OK,
@@ -68,6 +78,7 @@ struct Rasterizer : torch::CustomClassHolder {
         TORCH_CHECK(rc == DVS_OK, "dvs_rast_forward: ", dvs_rast_last_error(ctx));
         saved = {means3D, scales, quats, opacities, sh0, shN};
         last_h = cam.height; last_w = cam.width;
+        generation++;
         return {image, radii};
     }
 
@@ -147,12 +158,14 @@ struct RasterizeFn : torch::autograd::Function<RasterizeFn> {
         auto out = r->forward(camera, means3D.contiguous(), scales.contiguous(), quats.contiguous(),
                               opacities.contiguous(), sh0.contiguous(), shN.contiguous());
         actx->saved_data["rast"] = r;
+        actx->saved_data["generation"] = r->generation;
         actx->mark_non_differentiable({std::get<1>(out)});
         return {std::get<0>(out), std::get<1>(out)};
     }
     static torch::autograd::variable_list backward(torch::autograd::AutogradContext* actx,
                                                    torch::autograd::variable_list grad_out) {
         auto r = actx->saved_data["rast"].toCustomClass<Rasterizer>();
+        r->check_generation(actx->saved_data["generation"].toInt());
         auto g = r->backward(grad_out[0], 0);
         return {Tensor(), Tensor(), g[0], g[1], g[2], g[3], g[4], g[5]};
     }
@@ -168,12 +181,14 @@ struct RasterizeAuxFn : torch::autograd::Function<RasterizeAuxFn> {
                               opacities.contiguous(), sh0.contiguous(), shN.contiguous());
         auto aux = r->forward_aux();
         actx->saved_data["rast"] = r;
+        actx->saved_data["generation"] = r->generation;
         actx->mark_non_differentiable({std::get<1>(out)});
         return {std::get<0>(out), std::get<1>(out), std::get<0>(aux), std::get<1>(aux)};
     }
     static torch::autograd::variable_list backward(torch::autograd::AutogradContext* actx,
                                                    torch::autograd::variable_list grad_out) {
         auto r = actx->saved_data["rast"].toCustomClass<Rasterizer>();
+        r->check_generation(actx->saved_data["generation"].toInt());
         Tensor dpix = grad_out[0].defined() ? grad_out[0] : torch::zeros({3, r->last_h, r->last_w}, r->saved[0].options());
         auto g = r->backward_aux(dpix, grad_out[2], grad_out[3], 0);
         return {Tensor(), Tensor(), g[0], g[1], g[2], g[3], g[4], g[5]};

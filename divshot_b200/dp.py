@@ -163,12 +163,22 @@ class FactoredGradientExchange:
         else:
             self.campos_all[0] = campos_local
         self._cam_host = self.campos_all.cpu().contiguous()  # cached: no device->host copy (and no stream sync) per step
+        self._cam_local = campos_local.detach().to("cpu", torch.float32).reshape(3).clone()
         self._cams_set = True
 
     def exchange(self, means: torch.Tensor, campos_local: torch.Tensor, deg: int):
         if self.world == 1:
             return self.g
-        if not getattr(self, "_cams_set", False):
+        # the camera centres are gathered once per view assignment, not per step — but a rank whose view changed (the normal
+        # training loop round-robins the views) must not form dL/dshN with last step's directions: ranks vote (4 bytes) on
+        # "my centre differs from the cached one" and everybody re-gathers if anyone's did
+        mine = campos_local.detach().to("cpu", torch.float32).reshape(3)
+        changed = not getattr(self, "_cams_set", False) or not torch.equal(mine, self._cam_local)
+        if getattr(self, "_cams_set", False):
+            flag = torch.tensor([int(changed)], dtype=torch.int32, device=self.campos_all.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+            changed = bool(int(flag.item()))
+        if changed:
             self.set_cameras(campos_local)
         dist.all_gather_into_tensor(self.dsh0_all.view(-1), self.g.sh0.reshape(-1), group=self.group)
         dist.all_reduce(self.range_a, op=dist.ReduceOp.SUM, group=self.group)

@@ -71,6 +71,8 @@ class Rasterizer:
         self._h = h
         self._cam = None
         self._params = None
+        # the forward state lives in the context, one copy: autograd nodes remember the forward they belong to
+        self.generation = 0
 
     def close(self):
         if getattr(self, "_h", None):
@@ -115,6 +117,7 @@ class Rasterizer:
         if out_radii is None:
             out_radii = torch.empty(N, dtype=torch.int32, device=self.device)
         self._cam, self._params = cam, params
+        self.generation += 1
         st = torch.cuda.current_stream(self.device).cuda_stream
         self._check(self._lib.dvs_rast_forward(self._h, C.byref(cam), N, C.byref(self._pstruct(params)),
                                                out_color.data_ptr(), out_radii.data_ptr(), C.c_void_p(st)))
@@ -234,13 +237,20 @@ class _RasterizeFn(torch.autograd.Function):
                       opacities=opacities.contiguous().view(-1), sh0=sh0.contiguous(), shN=shN.contiguous())
         img, radii = rast.forward(cam, params)
         ctx.rast, ctx.params, ctx.shapes = rast, params, (opacities.shape, shN.shape)
+        ctx.generation = rast.generation
         ctx.mark_non_differentiable(radii)
         return img, radii
 
     @staticmethod
     def backward(ctx, dL_dimg, _):
+        if ctx.generation != ctx.rast.generation:
+            raise RasterizerError(
+                f"backward of forward #{ctx.generation} but the context holds the state of forward #{ctx.rast.generation}: a "
+                "Rasterizer keeps ONE outstanding forward (tile lists, final_T, camera); render concurrent views with "
+                "separate Rasterizers")
         N = ctx.params["means3D"].shape[0]
         g = GradBuffers.allocate(N, ctx.shapes[1][1], dL_dimg.device)
+        ctx.rast._params = ctx.params
         ctx.rast.backward(dL_dimg.contiguous(), g)
         return (None, None, g.means3D, g.scales, g.quats, g.opacities.view(ctx.shapes[0]), g.sh0, g.shN)
 

@@ -11,8 +11,6 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
-    config.addinivalue_line("markers", "gpu_staged: GPU test of code written while no GPU was available; not yet run on a "
-                                       "B200, therefore not part of the `-m gpu` tier (run with -m gpu_staged, then promote)")
 
 
 def pytest_collection_modifyitems(config, items):
@@ -25,5 +23,5 @@ def pytest_collection_modifyitems(config, items):
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for it in items:
-        if "gpu" in it.keywords or "gpu_staged" in it.keywords:
+        if "gpu" in it.keywords:
             it.add_marker(skip)

@@ -2,7 +2,7 @@
 a small `Backend` and run twice:
   * tests/test_densify_emul.py — on the CPU, against densify.cu compiled for the host (tests/native/densify_emul.cpp:
     the same kernel bodies as serial loops, the same host orchestration);
-  * tests/test_zz_staged_densify.py — on a B200, against the CUDA kernels in libgstrain.so (marker `gpu_staged`).
+  * tests/test_zz_gpu_densify.py — on a B200, against the CUDA kernels in libgstrain.so (marker `gpu`).
 Both call the same `dvs_densify_test_*` hooks; only the memory the pointers refer to differs."""
 import ctypes as C
 import math

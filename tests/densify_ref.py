@@ -1,7 +1,7 @@
 """Checkers for the trainer's refinement step (divshot_b200/csrc/densify.cu) plus a numpy emulation of
 its semantics.  The emulation exists so that the CPU suite can prove the CHECKERS right (they must accept the
-emulation's output and reject corrupted copies, tests/test_densify_ref.py) before the staged GPU tests
-(tests/test_zz_staged_densify.py) point them at the device code.  A model is a dict of float32 arrays
+emulation's output and reject corrupted copies, tests/test_densify_ref.py) before the GPU tests
+(tests/test_zz_gpu_densify.py) point them at the device code.  A model is a dict of float32 arrays
 {means[cap,3], scales[cap,3], quats[cap,4], opac[cap], sh0[cap,3], shN[cap,45]} of which the first N rows are live."""
 import math
 

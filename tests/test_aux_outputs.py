@@ -77,7 +77,7 @@ def test_normal_map_restatement_matches_float64_autograd(deg, seed, normq):
     assert np.abs(plain["quats"] - b["quats"]).max() > 1e-2 * np.abs(b["quats"]).max()
 
 
-@pytest.mark.gpu_staged
+@pytest.mark.gpu
 @pytest.mark.parametrize("deg,seed,bg,N,W,H", [(1, 11, (0, 0, 0), 1200, 64, 48), (3, 12, (0.3, 0.1, 0.7), 4000, 128, 96),
                                                 (2, 13, (1, 1, 1), 30000, 320, 200)])
 def test_cuda_aux_outputs_match_the_oracle_restatement(deg, seed, bg, N, W, H):
@@ -141,7 +141,7 @@ def test_cuda_aux_outputs_match_the_oracle_restatement(deg, seed, bg, N, W, H):
         r.close()
 
 
-@pytest.mark.gpu_staged
+@pytest.mark.gpu
 def test_libtorch_rasterize_aux_matches_c_abi():
     """torch.ops.dvs.rasterize_aux (csrc/torch_binding.cpp): image, radii, depth/alpha and normal maps with autograd through
     dvs_rast_backward_aux — against the Python / C-ABI path on the same scene."""

@@ -1,8 +1,8 @@
 """SURVEY.md §8 row F1 — divshot_b200/csrc/densify.cu executed on the CPU: the file is compiled for the host by
 tests/native/densify_emul.cpp (kernel bodies as serial loops, the two CUB primitives as plain loops, the CUDA runtime
 replaced by tests/native/cuda_host_shim.h), and driven through the same dvs_densify_test_* hooks and the same test
-bodies (tests/densify_cases.py) as the staged GPU tests.  What this cannot see: launch geometry, the CUB calls, and
-device libm rounding — those are what tests/test_zz_staged_densify.py is for."""
+bodies (tests/densify_cases.py) as the GPU tests.  What this cannot see: launch geometry, the CUB calls, and
+device libm rounding — those are what tests/test_zz_gpu_densify.py is for."""
 import ctypes as C
 import os
 import subprocess

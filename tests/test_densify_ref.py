@@ -1,5 +1,5 @@
 """The refinement-step checkers of tests/densify_ref.py must accept a faithful numpy emulation of the step and reject
-corrupted results — proven here on the CPU so that the staged GPU tests (tests/test_zz_staged_densify.py) can aim them
+corrupted results — proven here on the CPU so that the GPU tests (tests/test_zz_gpu_densify.py) can aim them
 at divshot_b200/csrc/densify.cu."""
 import ctypes as C
 

@@ -309,6 +309,18 @@ def test_readers_reject_forged_counts_and_damaged_files(ours, tmp_path):
                 q = str(tmp_path / ("forged_" + name))
                 open(q, "wb").write(bad)
                 assert ours.dvs_model_read(q.encode(), fmt, None, 0, None) < 0, (name, forged)
+                # the header ends the file WITHOUT a trailing newline: there is no payload position at all (the size checks
+                # used to wrap and the row loop read past the buffer)
+                cut = bad[:bad.index(b"end_header") + len(b"end_header")]
+                open(q, "wb").write(cut)
+                assert ours.dvs_model_read(q.encode(), fmt, None, 0, None) < 0, (name, "no newline after end_header")
+                err = ours.dvs_model_io_last_error()
+                assert b"truncated" in err or b"end_header" in err, err
+                rows = np.zeros((4, ROW), np.float32)
+                assert ours.dvs_model_read(q.encode(), fmt, _p(rows), 4, None) < 0
+            cut = good[:good.index(b"end_header") + len(b"end_header")]
+            open(q, "wb").write(cut)
+            assert ours.dvs_model_read(q.encode(), fmt, None, 0, None) < 0, (name, "header only, no newline")
         for trial in range(40):
             b = bytearray(good)
             if trial % 2:

@@ -148,6 +148,62 @@ def test_libtorch_custom_class_matches_c_abi():
 
 
 @pytest.mark.gpu
+def test_autograd_bridges_refuse_a_backward_against_another_forwards_state():
+    """One Rasterizer keeps ONE outstanding forward (tile lists, final_T, camera live in the context).  Two views rendered
+    with the same object before (loss1 + loss2).backward() must raise, not return view 1's gradients computed on view 2's
+    lists; with one Rasterizer per view the sum of both gradients comes out."""
+    import torch
+    from divshot_b200 import _cabi
+    from divshot_b200.rasterizer import Rasterizer, RasterizerError, rasterize_gaussians, scene_to_device
+    from divshot_b200.scenes import make_scene
+    libs = _build()
+    torch.classes.load_library(libs["libdvs_torch"])
+    sc = make_scene(N=3000, width=96, height=64, sh_degree=1, seed=9, views=2)
+    sc.log_scales += 0.8
+    dev = torch.device("cuda", 0)
+    params = scene_to_device(sc, dev)
+    names = ("means3D", "scales", "quats", "opacities", "sh0", "shN")
+
+    def packed(cam):
+        a = np.zeros(48, np.float32)
+        a[0:16] = cam.view; a[16:32] = cam.proj; a[32:35] = cam.campos
+        a[35:37] = (cam.tanfovx, cam.tanfovy); a[37:39] = (cam.width, cam.height); a[39:42] = cam.bg
+        a[42:46] = (1.0, 1, 3, 0)
+        return torch.from_numpy(a)
+    # libtorch operator
+    r = torch.classes.dvs.Rasterizer(0)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    i0, _ = torch.ops.dvs.rasterize(r, packed(sc.cameras[0]), *[leaves[k] for k in names])
+    i1, _ = torch.ops.dvs.rasterize(r, packed(sc.cameras[1]), *[leaves[k] for k in names])
+    with pytest.raises(RuntimeError, match="ONE outstanding forward"):
+        (i0.sum() + i1.sum()).backward()
+    # Python bridge: same rule; and the supported pattern (one Rasterizer per live view) sums both views' gradients
+    ra, rb = Rasterizer(0), Rasterizer(0)
+    try:
+        cams = [_cabi.make_camera(c, 1) for c in sc.cameras[:2]]
+        leaves = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+        j0, _ = rasterize_gaussians(ra, cams[0], *[leaves[k] for k in names])
+        j1, _ = rasterize_gaussians(ra, cams[1], *[leaves[k] for k in names])
+        with pytest.raises(RasterizerError, match="ONE outstanding forward"):
+            (j0.sum() + j1.sum()).backward()
+        single = []
+        for ras, cam in ((ra, cams[0]), (rb, cams[1])):
+            lv = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+            im, _ = rasterize_gaussians(ras, cam, *[lv[k] for k in names])
+            im.sum().backward()
+            single.append(lv["means3D"].grad.clone())
+        leaves = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+        k0, _ = rasterize_gaussians(ra, cams[0], *[leaves[k] for k in names])
+        k1, _ = rasterize_gaussians(rb, cams[1], *[leaves[k] for k in names])
+        (k0.sum() + k1.sum()).backward()
+        both = leaves["means3D"].grad
+        ref = single[0] + single[1]
+        assert float((both - ref).norm() / ref.norm()) < 1e-4
+    finally:
+        ra.close(); rb.close()
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("W,H,w", [(67, 45, 0.2), (128, 96, 0.0), (160, 100, 1.0)])
 def test_photometric_loss_matches_torch(W, H, w):
     """The trainer's fused (1-w)*L1 + w*(1-SSIM) loss and dL/dpixel vs a torch conv2d/autograd reference."""

@@ -2,7 +2,7 @@
 Gaussian), every rank all-gathers each view's dL/dsh0 (12 B per Gaussian) and forms sum_v B(dir_v) (x) dL/dsh0_v / SH_C0
 itself (divshot_b200/csrc/sh_grad_ops.h, sh_exchange.cu; divshot_b200/dp.py FactoredGradientExchange).
 CPU tier: the arithmetic (host build) against the oracle's per-view dL/dshN summed over views; the exchange logic with
-gloo at world_size 2.  GPU tier: staged."""
+gloo at world_size 2.  GPU tier: the kernel against the host build on a B200 (marker `gpu`)."""
 import ctypes as C
 import os
 import socket
@@ -137,7 +137,7 @@ def test_factored_exchange_world2_gloo():
     assert res[0][2] < res[0][3]  # fewer bytes on the wire than the plain all-reduce, already at 2 ranks
 
 
-@pytest.mark.gpu_staged
+@pytest.mark.gpu
 @pytest.mark.parametrize("N,V,deg,KR", [(5000, 8, 3, 15), (12345, 2, 2, 15), (129, 3, 1, 3), (1000, 1, 0, 0), (70000, 4, 3, 15)])
 def test_cuda_sh_accumulation_matches_the_host_build(N, V, deg, KR):
     from divshot_b200 import _cabi
@@ -162,7 +162,7 @@ def test_cuda_sh_accumulation_matches_the_host_build(N, V, deg, KR):
     assert_close(got, want, 1e-5, "dL_dshN")
 
 
-@pytest.mark.gpu_staged
+@pytest.mark.gpu
 def test_factored_exchange_refuses_cpu_tensors():
     from divshot_b200.dp import FactoredGradientExchange
     from divshot_b200.rasterizer import GradBuffers

@@ -4,8 +4,8 @@ The product quantises the raw parameters into the splat viewer's three buffers o
 the CPU in GaussianModel::create_gpu_buffer (diverse/source/assets/gaussian_model.cpp:115-212).  Parity is byte-exact
 and PINNED BY THE REFERENCE: oracle/_ref/libviewerpack_ref.so is those reference lines compiled unmodified with the
 reference's glm (oracle/ref_viewer_pack_shim.cpp).  CPU tier: the per-Gaussian arithmetic the kernel calls
-(viewer_pack_ops.h, host build) against the reference library and against digests frozen from it.  GPU tier (staged,
-written without a GPU): the kernel and the plugin path against the same bytes."""
+(viewer_pack_ops.h, host build) against the reference library and against digests frozen from it.  GPU tier (marker `gpu`,
+green on B200 since round 1): the kernel and the plugin path against the same bytes."""
 import ctypes as C
 import json
 import os
@@ -136,7 +136,7 @@ def test_plugin_library_exports_the_viewer_pack_abi_and_the_trainer_class():
     assert os.path.exists(build.build_editor_probe())
 
 
-# ------------------------------------------------------------------------------------------------ GPU (staged)
+# ------------------------------------------------------------------------------------------------ GPU
 def _device_pack(m):
     import torch
     from divshot_b200 import build
@@ -159,7 +159,7 @@ def _device_pack(m):
     return (g.cpu().numpy().view(np.uint32)[:N], c.cpu().numpy().view(np.uint32)[:N], sh.cpu().numpy().view(np.uint32)[:N], box)
 
 
-@pytest.mark.gpu_staged
+@pytest.mark.gpu
 @pytest.mark.parametrize("N,seed,deg", CASES + [(1000000, 9, 3)])
 def test_kernel_bytes_match_the_reference(ops, N, seed, deg):
     m = u.make_model(N, seed, deg)
@@ -171,7 +171,7 @@ def test_kernel_bytes_match_the_reference(ops, N, seed, deg):
         assert a.tobytes() == b.tobytes(), f"{name}: {np.argwhere(a.view(np.uint32) != b.view(np.uint32))[:5].tolist()}"
 
 
-@pytest.mark.gpu_staged
+@pytest.mark.gpu
 def test_kernel_empty_model_and_misuse():
     import torch
     from divshot_b200 import build
@@ -189,7 +189,7 @@ def test_kernel_empty_model_and_misuse():
     assert lib.dvs_viewer_pack(None, None, None, None, None, None, 5, None, None, None, None, None) != 0
 
 
-@pytest.mark.gpu_staged
+@pytest.mark.gpu
 def test_editor_style_hand_off_through_the_plugin(ops, tmp_path):
     """tools/editor_link_probe.cpp: train 30 iterations through the class interface, then the fused pack must equal the
     reference's CPU quantisation of the six getGaussian*Cpu() vectors taken at the same iteration."""

@@ -1,7 +1,6 @@
-"""STAGED (marker `gpu_staged`, not part of `-m gpu`): the refinement step of divshot_b200/csrc/densify.cu on a B200,
-through the dvs_densify_test_* hooks of libgstrain.so.  Written while no GPU was available to this round; the same test
-bodies (tests/densify_cases.py) pass on the CPU against the host build of the same source (tests/test_densify_emul.py).
-Promote to `gpu` after the first green run:  python -m pytest tests -m gpu_staged -q"""
+"""The refinement step of divshot_b200/csrc/densify.cu on a B200 (marker `gpu`; green on B200 since the round-1 driver run),
+through the dvs_densify_test_* hooks of libgstrain.so.  The same test bodies (tests/densify_cases.py) pass on the CPU
+against the host build of the same source (tests/test_densify_emul.py)."""
 import ctypes as C
 import os
 
@@ -11,7 +10,7 @@ import densify_cases as dc
 from test_densify_ops import ops  # noqa: F401
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-pytestmark = pytest.mark.gpu_staged
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")

@@ -43,7 +43,7 @@ def test_every_editor_method_is_exported_and_the_probe_links():
             assert r.returncode != 0 and "CUDA" in r.stderr
 
 
-@pytest.mark.gpu_staged
+@pytest.mark.gpu
 def test_editor_call_patterns_run(tmp_path):
     from divshot_b200 import build
     exe = build.build_editor_api_probe()
@@ -71,7 +71,7 @@ def test_editor_call_patterns_run(tmp_path):
     assert n == 5000 and np.isfinite(rows).all()
 
 
-@pytest.mark.gpu_staged
+@pytest.mark.gpu
 def test_reference_splatx_cli_end_to_end(tmp_path):
     """The unmodified application/splatx-cli trains through the plugin like diverseshot-cli does (tests/test_plugin.py)."""
     from divshot_b200 import build

@@ -1,4 +1,4 @@
-"""STAGED (marker `gpu_staged`): the views the multi-GPU runs render — cameras on a ring looking at (0, 0, 6), i.e. rotated
+"""The views the multi-GPU runs render — cameras on a ring looking at (0, 0, 6), i.e. rotated
 and translated views, not the identity camera of c3 / c5 — at FULL size (1 M Gaussians, 1600x1000): the bit-exact index
 outputs against digests of the oracle (tests/golden/fullsize_digests.json, made by make_fullsize_digests.py) and the
 size-independent properties of tests/props.py.  SURVEY.md §8 e: "tile/sort indices are per-view and stay bit-exact"."""
@@ -10,7 +10,7 @@ import pytest
 import props
 from divshot_b200.scenes import make_scene
 
-pytestmark = pytest.mark.gpu_staged
+pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
