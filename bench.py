@@ -155,37 +155,31 @@ def run_cpu_sample(threads=0, reps=1, frac_lin=1):
     return sc.N, times, threads, sample
 
 
-def choose_exchange(args, reducer, fx, grads, params, campos, deg, dev, dist, torch):
-    """N > 1: which gradient exchange the timed steps use.  `--allreduce factored` forces the factored exchange
-    (dp.FactoredGradientExchange: all-gather dL/dsh0, all-reduce 56 B/Gaussian, dL/dshN formed locally); `auto` adopts it only
-    if (1) on the real gradients of the warm-up step it reproduces the plain all-reduce of the whole arena (every tensor
-    within 1e-4, checked on every rank, decision taken collectively) and (2) it is faster here (3 timed runs each, max over
-    ranks).  Anything else keeps the reducer's own choice (NCCL / NVLS)."""
-    plain = reducer.all_reduce
+def choose_exchange(args, reducer, fx, grads, params, campos, deg, dev, dist, torch, fused=None, rerun_backward=None):
+    """N > 1: which gradient exchange the timed steps use.  Candidates next to the reducer's plain all-reduce (NCCL / our NVLS
+    kernel): `factored` (dp.FactoredGradientExchange: all-gather dL/dsh0, all-reduce 56 B/Gaussian with NCCL, dL/dshN formed by
+    our kernel) and `fused` (dp.FusedGradientExchange: the same exchange as ONE kernel of ours over NVSwitch multicast, device-side
+    barriers, and the backward stops writing the per-view dL/dshN).  `--allreduce factored|fused` forces one; `auto` adopts a
+    candidate only if (1) on the real gradients of the warm-up step it reproduces the plain NCCL all-reduce of the whole arena
+    (every tensor within 1e-4, checked on every rank, decision taken collectively so ranks can never disagree; the fused one also
+    in the mode the timed steps use: gradients of a backward that skipped dL/dshN) and (2) it is the fastest here (3 timed runs
+    each, max over ranks).  The returned callable carries `.bwd_flags` for the backward of the timed steps."""
     names = ("means3D", "scales", "quats", "opacities", "sh0", "shN")
-    ok = 1
-    err = float("nan")
-    try:
-        ref = reducer.flat.clone()
-        dist.all_reduce(ref)  # plain NCCL sum of the whole arena, the semantics to reproduce
-        ref_g = type(grads).allocate(grads.opacities.shape[0], grads.shN.shape[1], dev, flat=ref)
-        fx.exchange(params["means3D"], campos, deg)
-        torch.cuda.synchronize()
-        err = 0.0
-        for n in names:
-            a, b = getattr(grads, n).double(), getattr(ref_g, n).double()
-            if b.numel():
-                err = max(err, float((a - b).norm() / (b.norm() + 1e-30)))
-        ok = int(err < 1e-4)
-    except Exception as e:  # noqa: BLE001  (a local failure must not leave the ranks disagreeing: it becomes a vote)
-        ok = 0
-        sys.stderr.write(f"factored exchange unavailable: {type(e).__name__}: {e}\n")
-    vote = torch.tensor([ok], device=dev, dtype=torch.int32)
-    dist.all_reduce(vote, op=dist.ReduceOp.MIN)
-    if int(vote.item()) == 0:
-        if args.allreduce == "factored":
-            raise RuntimeError(f"--allreduce factored: the factored exchange does not reproduce the plain all-reduce (rel err {err:.2e})")
-        reducer.note += f"; factored exchange rejected by its self-check (rel err {err:.2e})"
+
+    def plain():
+        return reducer.all_reduce()
+    plain.bwd_flags = 0
+    cands = []
+    if fx is not None and args.allreduce in ("auto", "factored"):
+        f1 = lambda: fx.exchange(params["means3D"], campos, deg)  # noqa: E731
+        f1.bwd_flags = 0
+        cands.append(("factored", f1, fx))
+    if fused is not None and args.allreduce in ("auto", "fused"):
+        from divshot_b200 import _cabi
+        f2 = lambda: fused.exchange(params["means3D"], campos, deg)  # noqa: E731
+        f2.bwd_flags = _cabi.FLAG_SKIP_SHN_GRAD if rerun_backward is not None else 0
+        cands.append(("fused", f2, fused))
+    if not cands:
         return plain
 
     def timed_ms(fn, reps=3):
@@ -199,15 +193,64 @@ def choose_exchange(args, reducer, fx, grads, params, campos, deg, dev, dist, to
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    factored_fn = lambda: fx.exchange(params["means3D"], campos, deg)  # noqa: E731
-    t_f, t_p = timed_ms(factored_fn), timed_ms(plain)
+    local = reducer.flat.clone()  # this rank's own gradients: every candidate starts from them
+    ref = local.clone()
+    dist.all_reduce(ref)  # plain NCCL sum of the whole arena, the semantics to reproduce
+    ref_g = type(grads).allocate(grads.opacities.shape[0], grads.shN.shape[1], dev, flat=ref)
+
+    def worst_err():
+        torch.cuda.synchronize()
+        err = 0.0
+        for n in names:
+            a, b = getattr(grads, n).double(), getattr(ref_g, n).double()
+            if b.numel():
+                err = max(err, float((a - b).norm() / (b.norm() + 1e-30)))
+        return err
+
     world = dist.get_world_size()
-    detail = (f"factored exchange {t_f:.3f} ms vs {reducer.backend} all-reduce {t_p:.3f} ms; self-check rel err {err:.1e}; "
-              f"{fx.wire_bytes_per_gaussian(world):.0f} B/Gaussian received instead of {fx.plain_wire_bytes_per_gaussian(world):.0f}")
-    if args.allreduce == "factored" or t_f < t_p:
+    passed = {}
+    for name, fn, obj in cands:
+        ok, err = 1, float("nan")
+        try:
+            reducer.flat.copy_(local)
+            fn()
+            err = worst_err()
+            if err < 1e-4 and fn.bwd_flags and rerun_backward is not None:
+                rerun_backward(fn.bwd_flags)  # the mode of the timed steps: the backward no longer writes dL/dshN
+                fn()
+                err = max(err, worst_err())
+            ok = int(err < 1e-4)
+            if ok and hasattr(obj, "status") and obj.status():
+                ok = 0
+                sys.stderr.write(f"{name} exchange: a device-side barrier timed out\n")
+        except Exception as e:  # noqa: BLE001  (a local failure must not leave the ranks disagreeing: it becomes a vote)
+            ok = 0
+            sys.stderr.write(f"{name} exchange unavailable: {type(e).__name__}: {e}\n")
+        vote = torch.tensor([ok], device=dev, dtype=torch.int32)
+        dist.all_reduce(vote, op=dist.ReduceOp.MIN)
+        if int(vote.item()) == 0:
+            if args.allreduce == name:
+                raise RuntimeError(f"--allreduce {name}: the {name} exchange does not reproduce the plain all-reduce (rel err {err:.2e})")
+            reducer.note += f"; {name} exchange rejected by its self-check (rel err {err:.2e})"
+            continue
+        wire = obj.wire_bytes_per_gaussian(world) if name == "factored" else obj.wire_bytes_per_gaussian()
+        passed[name] = (timed_ms(fn), err, fn, wire)
+    if rerun_backward is not None:
+        rerun_backward(0)  # leave a complete set of local gradients behind
+    else:
+        reducer.flat.copy_(local)
+    if not passed:
+        return plain
+    t_p = timed_ms(plain)
+    plain_wire = 2 * (world - 1) / world * (56 + 12 * grads.shN.shape[1])
+    detail = "; ".join(f"{n} exchange {t:.3f} ms (self-check rel err {e:.1e}, {w:.0f} B/Gaussian received)" for n, (t, e, _, w) in passed.items())
+    detail += f" vs {reducer.backend} all-reduce {t_p:.3f} ms ({plain_wire:.0f} B/Gaussian)"
+    forced = args.allreduce if args.allreduce in passed else None
+    best = forced or min(passed, key=lambda n: passed[n][0])
+    if forced or passed[best][0] < t_p:
         reducer.note = (reducer.note + "; " if reducer.note else "") + detail
-        reducer.backend = "factored"
-        return factored_fn
+        reducer.backend = best
+        return passed[best][2]
     reducer.note = (reducer.note + "; " if reducer.note else "") + "kept: " + detail
     return plain
 
@@ -266,10 +309,13 @@ def main():
     ap.add_argument("--no-tight", action="store_true",
                     help="timed steps keep the whole-rectangle tile lists (default: DVS_FLAG_TIGHT_LISTS — entries whose sub-tile "
                          "mask is empty are not emitted; image and gradients are bit-identical, tests/test_gpu_parity.py)")
-    ap.add_argument("--allreduce", default="auto", choices=["auto", "nvls", "nccl", "factored"],
-                    help="gradient exchange: NVSwitch in-switch reduction over symmetric memory, plain NCCL, or the factored "
-                         "exchange (all-gather dL/dsh0, all-reduce 56 B/Gaussian, form dL/dshN locally); auto = the fastest "
-                         "of them, the factored one only after it has reproduced the plain all-reduce on this run's gradients")
+    ap.add_argument("--allreduce", default="auto", choices=["auto", "nvls", "nccl", "factored", "fused"],
+                    help="gradient exchange: NVSwitch in-switch reduction over symmetric memory, plain NCCL, the factored "
+                         "exchange (all-gather dL/dsh0, all-reduce 56 B/Gaussian, form dL/dshN locally: 3 NCCL calls + our kernel) "
+                         "or the same exchange fused into ONE kernel of ours over NVSwitch multicast; auto = the fastest of them, "
+                         "the factored / fused ones only after they have reproduced the plain all-reduce on this run's gradients")
+    ap.add_argument("--fused-ctas", type=int, default=0, help="fused exchange: CTAs of the kernel (0 = one per SM)")
+    ap.add_argument("--fused-reduce-ctas", type=int, default=0, help="fused exchange: CTAs that do the in-switch reduction (0 = half)")
     args = ap.parse_args()
     global WORKLOAD
     if args.workload:
@@ -308,15 +354,31 @@ def main():
     dl = dl_host.to(dev)
     img_host = torch.empty(3, H, W, dtype=torch.float32).pin_memory()
     factored = args.allreduce == "factored"
-    reducer = GradientReducer(GradBuffers.numel_for(N, K - 1), dev, backend="nccl" if factored else args.allreduce)
+    reducer = GradientReducer(GradBuffers.numel_for(N, K - 1), dev,
+                              backend="nccl" if factored else "auto" if args.allreduce == "fused" else args.allreduce)
     grads = GradBuffers.allocate(N, K - 1, dev, flat=reducer.flat)
     exchange = reducer.all_reduce
-    fx = None
+    fx = fused = None
+    campos = torch.tensor(np.asarray(sc.cameras[rank % len(sc.cameras)].campos, np.float32))
+    if world > 1 and args.allreduce in ("auto", "fused") and K > 1:
+        ok = 1
+        try:
+            from divshot_b200.dp import FusedGradientExchange
+            fused = FusedGradientExchange(grads, reducer, ctas=args.fused_ctas, reduce_ctas=args.fused_reduce_ctas)
+            fused.set_cameras(campos)
+        except Exception as e:  # noqa: BLE001
+            ok, fused = 0, None
+            if args.allreduce == "fused":
+                raise
+            sys.stderr.write(f"fused exchange not set up: {type(e).__name__}: {e}\n")
+        vote = torch.tensor([ok], device=dev, dtype=torch.int32)  # all ranks use it or none does
+        dist.all_reduce(vote, op=dist.ReduceOp.MIN)
+        if int(vote.item()) == 0:
+            fused = None
     if world > 1 and args.allreduce in ("auto", "factored"):
         try:
             from divshot_b200.dp import FactoredGradientExchange
             fx = FactoredGradientExchange(grads)
-            campos = torch.tensor(np.asarray(sc.cameras[rank % len(sc.cameras)].campos, np.float32))
             fx.set_cameras(campos)
         except Exception as e:  # noqa: BLE001  (same code and arguments on every rank: fails on all of them or on none)
             if args.allreduce == "factored":
@@ -333,8 +395,15 @@ def main():
     rast.forward(cam, params, img, radii); rast.backward(dl, grads)
     rast.forward(cam, params, img, radii); rast.backward(dl, grads)
 
-    if fx is not None:
-        exchange = choose_exchange(args, reducer, fx, grads, params, campos, deg, dev, dist, torch)
+    def rerun_backward(flags):
+        rast.forward(cam, params, img, radii)
+        rast.backward(dl, grads, flags=flags)
+
+    bwd_flags = 0
+    if fx is not None or fused is not None:
+        exchange = choose_exchange(args, reducer, fx, grads, params, campos, deg, dev, dist, torch, fused=fused,
+                                   rerun_backward=rerun_backward)
+        bwd_flags = getattr(exchange, "bwd_flags", 0)
 
     # the training-loop mode: no host synchronisation per step, single-pass binning, tight tile lists
     cam_defer = _cabi.DvsCamera.from_buffer_copy(cam)
@@ -342,14 +411,31 @@ def main():
 
     def step_resident():
         rast.forward(cam_defer, params, img, radii, defer_check=True)
-        rast.backward(dl, grads)
+        rast.backward(dl, grads, flags=bwd_flags)
         if world > 1:
             exchange()
 
+    # end to end through the C-ABI with HOST image buffers, as a pipelined trainer drives it (dvs_rast_step_host_async / _wait):
+    # two slots of pinned buffers; step k is queued (H2D of its dL/dpix, forward, D2H of its image, backward, the exchange) before
+    # the host waits for step k-1's image, so the copies of neighbouring steps overlap compute and the launch queue never drains.
+    # Every step's H2D and D2H are inside the timed region; drain() waits for the last image.
+    dl_hosts = [dl_host, dl_host.clone().pin_memory()]
+    img_hosts = [img_host, torch.empty_like(img_host).pin_memory()]
+    e2e_state = {"k": 0}
+
     def step_e2e():
-        rast.step_host(cam_defer, params, grads, dl_host, img_host)
+        k = e2e_state["k"]
+        rast.step_host_async(cam_defer, params, grads, dl_hosts[k & 1], img_hosts[k & 1], k & 1, flags=bwd_flags)
         if world > 1:
             exchange()
+        if k > 0:
+            rast.step_host_wait((k - 1) & 1)
+        e2e_state["k"] = k + 1
+
+    def drain_e2e():
+        if e2e_state["k"] > 0:
+            rast.step_host_wait((e2e_state["k"] - 1) & 1)
+    step_e2e.drain = drain_e2e
 
     def timed(fn, steps, warmup, sample_clocks=False):
         for _ in range(warmup):
@@ -363,6 +449,8 @@ def main():
         e0.record()
         for _ in range(steps):
             fn()
+        if hasattr(fn, "drain"):
+            fn.drain()  # the pipelined end-to-end loop: the last step's image has arrived on the host
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -450,11 +538,12 @@ def main():
         "stages": stages,
         "e2e": {"value": e2e_value, "unit": "Gaussians/s", "h2d_bytes_per_step": 12 * P * world,
                 "d2h_bytes_per_step": 12 * P * world, "ms_per_step": ms_e2e / args.steps,
-                "api": "dvs_rast_step_host (C-ABI): pinned dL/dpix H2D, forward, image D2H, backward; parameters and "
+                "api": "dvs_rast_step_host_async / dvs_rast_step_host_wait (C-ABI), two pipeline slots: every step copies its pinned "
+                       "dL/dpix H2D and its image D2H (the host waits for step k's image after queueing step k+1); parameters and "
                        "gradients device-resident as in the trainer"},
         # 8 forward + 2 backward kernels of ours per step; with N > 1 one more when the exchange is ours too (the NVLS
         # all-reduce kernel, or the SH accumulation kernel of the factored exchange)
-        "gpu_launches": (10 + (1 if world > 1 and reducer.backend in ("nvls", "factored") else 0)) * args.steps,
+        "gpu_launches": (10 + (1 if world > 1 and reducer.backend in ("nvls", "factored", "fused") else 0)) * args.steps,
         "allreduce": ({"backend": reducer.backend, "note": reducer.note, "bytes": int(reducer.flat.numel()) * 4, "ms": ms_ar,
                        "busbw_GBps": (2 * (world - 1) / world * reducer.flat.numel() * 4 / 1e9 / (ms_ar * 1e-3))}
                       if world > 1 else None),

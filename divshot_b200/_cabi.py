@@ -17,6 +17,7 @@ FLAG_ABSGRAD = 4
 FLAG_DEFER_CHECK = 8
 FLAG_ANTIALIAS = 16
 FLAG_TIGHT_LISTS = 32
+FLAG_SKIP_SHN_GRAD = 64
 NUM_STAGES = 8
 
 (BUF_RADII, BUF_TILES_TOUCHED, BUF_DEPTH, BUF_MEAN2D, BUF_CONIC_OPACITY, BUF_RGB, BUF_CLAMPED, BUF_POINT_LIST,
@@ -26,9 +27,9 @@ EXPORTS = [
     "dvs_rast_create", "dvs_rast_destroy", "dvs_rast_last_error", "dvs_rast_version", "dvs_rast_reserve",
     "dvs_rast_forward", "dvs_rast_backward", "dvs_rast_step_host", "dvs_rast_get_stats", "dvs_rast_debug_read",
     "dvs_rast_stage_ms", "dvs_rast_stage_name", "dvs_rast_forward_aux", "dvs_rast_backward_aux",
-    "dvs_rast_set_profiling",
+    "dvs_rast_set_profiling", "dvs_rast_step_host_async", "dvs_rast_step_host_wait",
 ]
-COLL_EXPORTS = ["dvs_coll_allreduce_nvls", "dvs_coll_sh_grad_from_dsh0"]
+COLL_EXPORTS = ["dvs_coll_allreduce_nvls", "dvs_coll_sh_grad_from_dsh0", "dvs_coll_exchange_fused", "dvs_coll_exchange_fused_grid"]
 
 
 class DvsCamera(C.Structure):
@@ -52,6 +53,16 @@ class DvsStats(C.Structure):
                 ("dup_capacity", C.c_int64), ("max_tile_len", C.c_int64), ("tiles_x", C.c_int32),
                 ("tiles_y", C.c_int32), ("overflow", C.c_int32), ("reserved_", C.c_int32),
                 ("num_list_entries", C.c_int64)]
+
+
+class DvsCollFused(C.Structure):
+    """dvs_coll_fused of include/dvs_rast.h (arguments of the fused multi-GPU gradient exchange kernel)."""
+    _fields_ = [("arena_mc", C.c_void_p), ("arena_local", C.c_void_p), ("gather_mc", C.c_void_p), ("gather_local", C.c_void_p),
+                ("signal_mc", C.c_void_p), ("signal_local", C.c_void_p), ("grid_counter", C.c_void_p), ("status", C.c_void_p),
+                ("means", C.c_void_p), ("campos", C.c_float * 48), ("N", C.c_int64), ("off_sh0", C.c_int64), ("off_shN", C.c_int64),
+                ("range_a", C.c_int64 * 2), ("range_b", C.c_int64 * 2), ("launch_index", C.c_uint64), ("rank", C.c_int32),
+                ("world", C.c_int32), ("sh_degree", C.c_int32), ("sh_rest_alloc", C.c_int32), ("ctas", C.c_int32),
+                ("reduce_ctas", C.c_int32)]
 
 
 _lib = None
@@ -91,6 +102,12 @@ def load():
     L.dvs_rast_step_host.argtypes = [C.c_void_p, C.POINTER(DvsCamera), C.c_int64, C.POINTER(DvsParams),
                                      C.POINTER(DvsGrads), C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
     L.dvs_rast_step_host.restype = C.c_int
+    if hasattr(L, "dvs_rast_step_host_async"):
+        L.dvs_rast_step_host_async.argtypes = [C.c_void_p, C.POINTER(DvsCamera), C.c_int64, C.POINTER(DvsParams),
+                                               C.POINTER(DvsGrads), C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
+        L.dvs_rast_step_host_async.restype = C.c_int
+        L.dvs_rast_step_host_wait.argtypes = [C.c_void_p, C.c_int]
+        L.dvs_rast_step_host_wait.restype = C.c_int
     L.dvs_rast_get_stats.argtypes = [C.c_void_p, C.POINTER(DvsStats)]
     L.dvs_rast_get_stats.restype = C.c_int
     if hasattr(L, "dvs_rast_set_profiling"):  # (absent from the round-1 build the A/B harness can load)
@@ -107,6 +124,10 @@ def load():
     L.dvs_coll_sh_grad_from_dsh0.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                              C.c_void_p]
     L.dvs_coll_sh_grad_from_dsh0.restype = C.c_int
+    L.dvs_coll_exchange_fused.argtypes = [C.POINTER(DvsCollFused), C.c_void_p]
+    L.dvs_coll_exchange_fused.restype = C.c_int
+    L.dvs_coll_exchange_fused_grid.argtypes = [C.c_int]
+    L.dvs_coll_exchange_fused_grid.restype = C.c_int
     _lib = L
     return L
 

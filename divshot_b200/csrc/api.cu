@@ -56,8 +56,8 @@ struct dvs_rast_ctx {
     int64_t cap_pix = 0;
     float* final_T = nullptr;
     uint32_t* n_contrib = nullptr;
-    float* h2d_grad = nullptr;   // [3P] staging for dvs_rast_step_host
-    float* d_image = nullptr;    // [3P]
+    float* h2d_grad[2] = {nullptr, nullptr};   // [3P] device staging of dL/dpix for dvs_rast_step_host*, one per pipeline slot
+    float* d_image[2] = {nullptr, nullptr};    // [3P] rendered image before its D2H, one per pipeline slot
     // F4 auxiliary outputs (dvs_rast_forward_aux / dvs_rast_backward_aux), allocated on first use
     int64_t cap_aux_gauss = 0, cap_aux_pix = 0;
     float4* rec_aux = nullptr;   // [3 cap] records with the colour replaced by (depth, 1, 0)
@@ -79,7 +79,9 @@ struct dvs_rast_ctx {
     cudaEvent_t ev[DVS_NUM_STAGES + 2] = {};
     // dvs_rast_step_host: copies run on their own stream so the H2D overlaps the forward and the D2H the backward
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_h2d = nullptr, ev_img = nullptr, ev_d2h = nullptr;
+    cudaEvent_t ev_img = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr}, ev_bwd_done[2] = {nullptr, nullptr};
+    bool slot_used[2] = {false, false};
     bool ev_fwd = false, ev_bwd = false;
     // deferred arena validation (DVS_FLAG_DEFER_CHECK)
     cudaEvent_t ev_check = nullptr;
@@ -164,8 +166,10 @@ static int ensure_pix(dvs_rast_ctx* ctx, int64_t P) {
     if (P <= ctx->cap_pix) return DVS_OK;
     CK(regrow(ctx->final_T, (size_t)P));
     CK(regrow(ctx->n_contrib, (size_t)P));
-    if (ctx->h2d_grad) { cudaFree(ctx->h2d_grad); ctx->h2d_grad = nullptr; }
-    if (ctx->d_image) { cudaFree(ctx->d_image); ctx->d_image = nullptr; }
+    for (int k = 0; k < 2; k++) {
+        if (ctx->h2d_grad[k]) { cudaFree(ctx->h2d_grad[k]); ctx->h2d_grad[k] = nullptr; }
+        if (ctx->d_image[k]) { cudaFree(ctx->d_image[k]); ctx->d_image[k] = nullptr; }
+    }
     ctx->cap_pix = P;
     return DVS_OK;
 }
@@ -228,9 +232,12 @@ int dvs_rast_create(int device, dvs_rast_ctx** out) {
     if (e == cudaSuccess) e = cudaMemset(ctx->info, 0, 16 * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_check, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_h2d, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_img, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_d2h, cudaEventDisableTiming);
+    for (int k = 0; e == cudaSuccess && k < 2; k++) {
+        e = cudaEventCreateWithFlags(&ctx->ev_h2d[k], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_d2h[k], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_bwd_done[k], cudaEventDisableTiming);
+    }
     if (e != cudaSuccess) {
         // the product path must fail loudly without a usable CUDA device: there is no CPU fallback.
         fprintf(stderr, "dvs_rast_create: CUDA unavailable on device %d: %s\n", device, cudaGetErrorString(e));
@@ -247,16 +254,20 @@ void dvs_rast_destroy(dvs_rast_ctx* ctx) {
     cudaFree(ctx->rec); cudaFree(ctx->aux); cudaFree(ctx->sgrad);
     cudaFree(ctx->tile_count); cudaFree(ctx->tile_base); cudaFree(ctx->tile_cursor); cudaFree(ctx->class_tiles); cudaFree(ctx->tile_order);
     cudaFree(ctx->bins); cudaFree(ctx->plist);
-    cudaFree(ctx->final_T); cudaFree(ctx->n_contrib); cudaFree(ctx->h2d_grad); cudaFree(ctx->d_image);
+    cudaFree(ctx->final_T); cudaFree(ctx->n_contrib);
+    for (int k = 0; k < 2; k++) { cudaFree(ctx->h2d_grad[k]); cudaFree(ctx->d_image[k]); }
     cudaFree(ctx->rec_aux); cudaFree(ctx->aux_dz); cudaFree(ctx->aux_dn); cudaFree(ctx->aux_img); cudaFree(ctx->aux_T); cudaFree(ctx->aux_nc);
     cudaFree(ctx->info); cudaFree(ctx->stats);
     cudaFreeHost(ctx->h_info); cudaFreeHost(ctx->h_stats);
     for (auto& e : ctx->ev)
         if (e) cudaEventDestroy(e);
     if (ctx->ev_check) cudaEventDestroy(ctx->ev_check);
-    if (ctx->ev_h2d) cudaEventDestroy(ctx->ev_h2d);
     if (ctx->ev_img) cudaEventDestroy(ctx->ev_img);
-    if (ctx->ev_d2h) cudaEventDestroy(ctx->ev_d2h);
+    for (int k = 0; k < 2; k++) {
+        if (ctx->ev_h2d[k]) cudaEventDestroy(ctx->ev_h2d[k]);
+        if (ctx->ev_d2h[k]) cudaEventDestroy(ctx->ev_d2h[k]);
+        if (ctx->ev_bwd_done[k]) cudaEventDestroy(ctx->ev_bwd_done[k]);
+    }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
 }
@@ -575,38 +586,74 @@ int dvs_rast_backward_aux(dvs_rast_ctx* ctx, const dvs_params* params, const flo
     return DVS_OK;
 }
 
+// One host-buffer step, QUEUED only (no host synchronisation): H2D of dL/dpix into the slot's device staging on the copy
+// stream (overlaps the forward, and the previous step's backward: it only waits for the backward that last READ this slot's
+// staging buffer), forward, D2H of the image on the copy stream (overlaps the backward), backward.
+static int step_host_enqueue(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, const dvs_params* params,
+                             const dvs_grads* grads, const float* dL_dpix_host, float* out_color_host, uint32_t bwd_flags,
+                             void* stream, int slot) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(ctx->device));
+    const int64_t P = (int64_t)cam->width * cam->height;
+    int rc;
+    if (P > ctx->cap_pix) {  // the per-pixel arenas are about to be re-allocated: nothing of an earlier step may be in flight
+        CK(cudaStreamSynchronize(st));
+        CK(cudaStreamSynchronize(ctx->copy_stream));
+        ctx->slot_used[0] = ctx->slot_used[1] = false;
+    }
+    if ((rc = ensure_pix(ctx, P))) return rc;
+    if (!ctx->h2d_grad[slot]) CK(cudaMalloc(reinterpret_cast<void**>(&ctx->h2d_grad[slot]), 3 * (size_t)ctx->cap_pix * sizeof(float)));
+    if (!ctx->d_image[slot]) CK(cudaMalloc(reinterpret_cast<void**>(&ctx->d_image[slot]), 3 * (size_t)ctx->cap_pix * sizeof(float)));
+    if (ctx->slot_used[slot]) {
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_bwd_done[slot], 0));  // the backward that read this staging buffer
+        CK(cudaStreamWaitEvent(st, ctx->ev_d2h[slot], 0));                     // the D2H that read this image buffer
+    } else {
+        CK(cudaEventRecord(ctx->ev_img, st));  // first use: order the copy after whatever the caller queued before this step
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_img, 0));
+    }
+    CK(cudaMemcpyAsync(ctx->h2d_grad[slot], dL_dpix_host, 3 * (size_t)P * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
+    CK(cudaEventRecord(ctx->ev_h2d[slot], ctx->copy_stream));
+    if ((rc = dvs_rast_forward(ctx, cam, N, params, ctx->d_image[slot], nullptr, stream))) return rc;
+    CK(cudaEventRecord(ctx->ev_img, st));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_img, 0));
+    CK(cudaMemcpyAsync(out_color_host, ctx->d_image[slot], 3 * (size_t)P * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_stream));
+    CK(cudaEventRecord(ctx->ev_d2h[slot], ctx->copy_stream));
+    CK(cudaStreamWaitEvent(st, ctx->ev_h2d[slot], 0));
+    if ((rc = dvs_rast_backward(ctx, params, ctx->h2d_grad[slot], grads, bwd_flags, stream))) return rc;
+    CK(cudaEventRecord(ctx->ev_bwd_done[slot], st));
+    ctx->slot_used[slot] = true;
+    return DVS_OK;
+}
+
 int dvs_rast_step_host(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, const dvs_params* params,
                        const dvs_grads* grads, const float* dL_dpix_host, float* out_color_host, uint32_t bwd_flags,
                        void* stream) {
     if (!ctx) return DVS_E_INVALID;
     if (!cam || !dL_dpix_host || !out_color_host) return fail(ctx, DVS_E_INVALID, "null host buffer");
+    int rc = step_host_enqueue(ctx, cam, N, params, grads, dL_dpix_host, out_color_host, bwd_flags, stream, 0);
+    if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    CK(cudaSetDevice(ctx->device));
-    const int64_t P = (int64_t)cam->width * cam->height;
-    int rc;
-    if ((rc = ensure_pix(ctx, P))) return rc;
-    if (!ctx->h2d_grad) CK(cudaMalloc(reinterpret_cast<void**>(&ctx->h2d_grad), 3 * (size_t)ctx->cap_pix * sizeof(float)));
-    if (!ctx->d_image) CK(cudaMalloc(reinterpret_cast<void**>(&ctx->d_image), 3 * (size_t)ctx->cap_pix * sizeof(float)));
-    // H2D of dL/dpix on the copy stream (overlaps the forward, which does not need it)
-    CK(cudaEventRecord(ctx->ev_img, st));  // orders the copy after whatever the caller queued before this step
-    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_img, 0));
-    CK(cudaMemcpyAsync(ctx->h2d_grad, dL_dpix_host, 3 * (size_t)P * sizeof(float), cudaMemcpyHostToDevice,
-                       ctx->copy_stream));
-    CK(cudaEventRecord(ctx->ev_h2d, ctx->copy_stream));
-    if ((rc = dvs_rast_forward(ctx, cam, N, params, ctx->d_image, nullptr, stream))) return rc;
-    // (with DVS_FLAG_DEFER_CHECK in cam->flags the forward above did not synchronise; the blocking settle of the
-    //  arena check happens below, after the whole step has been queued)
-    // D2H of the image on the copy stream (overlaps the backward)
-    CK(cudaEventRecord(ctx->ev_img, st));
-    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_img, 0));
-    CK(cudaMemcpyAsync(out_color_host, ctx->d_image, 3 * (size_t)P * sizeof(float), cudaMemcpyDeviceToHost,
-                       ctx->copy_stream));
-    CK(cudaEventRecord(ctx->ev_d2h, ctx->copy_stream));
-    CK(cudaStreamWaitEvent(st, ctx->ev_h2d, 0));
-    if ((rc = dvs_rast_backward(ctx, params, ctx->h2d_grad, grads, bwd_flags, stream))) return rc;
-    CK(cudaStreamWaitEvent(st, ctx->ev_d2h, 0));
+    CK(cudaStreamWaitEvent(st, ctx->ev_d2h[0], 0));
     CK(cudaStreamSynchronize(st));
     return resolve_pending(ctx, true);  // DVS_E_OVERFLOW if a deferred-check forward overflowed (redo the step)
+}
+
+int dvs_rast_step_host_async(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, const dvs_params* params,
+                             const dvs_grads* grads, const float* dL_dpix_host, float* out_color_host, uint32_t bwd_flags,
+                             int slot, void* stream) {
+    if (!ctx) return DVS_E_INVALID;
+    if (!cam || !dL_dpix_host || !out_color_host) return fail(ctx, DVS_E_INVALID, "null host buffer");
+    if (slot < 0 || slot > 1) return fail(ctx, DVS_E_INVALID, "slot must be 0 or 1");
+    return step_host_enqueue(ctx, cam, N, params, grads, dL_dpix_host, out_color_host, bwd_flags, stream, slot);
+}
+
+int dvs_rast_step_host_wait(dvs_rast_ctx* ctx, int slot) {
+    if (!ctx) return DVS_E_INVALID;
+    if (slot < 0 || slot > 1) return fail(ctx, DVS_E_INVALID, "slot must be 0 or 1");
+    if (!ctx->slot_used[slot]) return fail(ctx, DVS_E_STATE, "no step queued on slot %d", slot);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventSynchronize(ctx->ev_d2h[slot]));  // the slot's image is in out_color_host
+    return resolve_pending(ctx, false);           // report an overflowed deferred-check forward as soon as it is known
 }
 
 int dvs_rast_set_profiling(dvs_rast_ctx* ctx, int on) {

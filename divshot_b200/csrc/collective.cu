@@ -8,9 +8,11 @@
 // provides the multicast pointer of a symmetric allocation (torch.distributed._symmetric_memory) and
 // brackets the call with cross-rank barriers (all ranks' gradients written before; all shards stored after).
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "dvs_rast.h"
+#include "sh_grad_ops.h"
 
 namespace {
 
@@ -58,4 +60,193 @@ extern "C" DVS_API int dvs_coll_allreduce_nvls(void* multicast_ptr, size_t numel
     nvls_allreduce_kernel<<<ctas, AR_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<float4*>(multicast_ptr), numel_f32 / 4, rank, world);
     return cudaGetLastError() == cudaSuccess ? DVS_OK : DVS_E_CUDA;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// The fused exchange (dvs_coll_exchange_fused, include/dvs_rast.h): gather + in-switch reduction + local SH accumulation in
+// one persistent, co-resident grid with two device-side cross-rank barriers.
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+
+static_assert(sizeof(dvs_coll_fused) == 352 && offsetof(dvs_coll_fused, N) == 264 && offsetof(dvs_coll_fused, rank) == 328,
+              "dvs_coll_fused layout is part of the C-ABI (divshot_b200/_cabi.py: DvsCollFused)");
+constexpr int FX_THREADS = 512;            // one CTA per SM; a CTA forms 512 rows of dL/dshN per trip
+constexpr int FX_ROW_WORDS = 45;
+constexpr unsigned long long FX_TIMEOUT_NS = 2000000000ull;
+
+__device__ __forceinline__ void mm_st_f32(float* p, float v) {
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void mm_red_release_add_u32(uint32_t* p, uint32_t v) {
+    asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// wait until *p (monotonic counter) has reached `target`; wrap-safe comparison; false on timeout
+template <bool SYS>
+__device__ __forceinline__ bool wait_counter(const uint32_t* p, uint32_t target) {
+    const unsigned long long t0 = now_ns();
+    for (uint32_t spins = 0;; spins++) {
+        const uint32_t v = SYS ? ld_acquire_sys(p) : ld_acquire_gpu(p);
+        if ((int32_t)(v - target) >= 0) return true;
+        if ((spins & 1023u) == 1023u && now_ns() - t0 > FX_TIMEOUT_NS) return false;
+    }
+}
+
+// Cross-rank barrier number `seq` (0, 1, 2, ... over the life of the buffers) of a co-resident grid of G CTAs on each of
+// W ranks: every CTA arrives on the local counter; CTA 0 waits for its grid, then adds 1 to the symmetric counter in ALL
+// replicas with one multimem.red.release; every CTA polls the local replica until all W ranks have done so.
+__device__ __forceinline__ void cross_rank_barrier(const dvs_coll_fused& a, uint32_t seq, uint32_t* s_fail) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();  // this CTA's multimem / global stores are ordered before its arrival
+        atomicAdd(a.grid_counter, 1u);
+        bool ok = true;
+        if (blockIdx.x == 0) {
+            ok = wait_counter<false>(a.grid_counter, (seq + 1u) * gridDim.x);
+            __threadfence_system();
+            mm_red_release_add_u32(a.signal_mc, 1u);
+        }
+        ok = wait_counter<true>(a.signal_local, (seq + 1u) * (uint32_t)a.world) && ok;
+        if (!ok) {
+            *s_fail = 1u;
+            if (a.status) atomicExch(a.status, seq + 1u);
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(FX_THREADS, 1)
+fused_exchange_kernel(const dvs_coll_fused a) {
+    extern __shared__ __align__(16) float s_rows[];  // FX_THREADS rows of dL/dshN
+    __shared__ uint32_t s_fail;
+    if (threadIdx.x == 0) s_fail = 0u;
+    const uint32_t seq0 = (uint32_t)(a.launch_index * 2ull);
+    const size_t gtid = (size_t)blockIdx.x * FX_THREADS + threadIdx.x, gsize = (size_t)gridDim.x * FX_THREADS;
+
+    // ---- 1. gather: my dL/dsh0 -> slice `rank` of every replica of the gather area
+    {
+        const size_t n = 3 * (size_t)a.N;
+        const float* src = a.arena_local + a.off_sh0;
+        float* dst = reinterpret_cast<float*>(a.gather_mc) + (size_t)a.rank * n;
+        if ((n & 3) == 0) {
+            const float4* s4 = reinterpret_cast<const float4*>(src);
+            float4* d4 = reinterpret_cast<float4*>(dst);
+            const size_t nv = n >> 2;
+            size_t i = gtid;
+            for (; i + 3 * gsize < nv; i += 4 * gsize) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) v[u] = s4[i + u * gsize];
+#pragma unroll
+                for (int u = 0; u < 4; u++) mm_st(d4 + i + u * gsize, v[u]);
+            }
+            for (; i < nv; i += gsize) mm_st(d4 + i, s4[i]);
+        } else {
+            for (size_t i = gtid; i < n; i += gsize) mm_st_f32(dst + i, src[i]);
+        }
+    }
+    // ---- 2. every rank's slice has landed everywhere; every rank's gradients are final
+    cross_rank_barrier(a, seq0, &s_fail);
+    if (s_fail) return;
+
+    if ((int)blockIdx.x < a.reduce_ctas) {
+        // ---- 3a. in-switch sum of the two reduced ranges: rank r owns shard r of each
+        const size_t rtid = (size_t)blockIdx.x * FX_THREADS + threadIdx.x, rsize = (size_t)a.reduce_ctas * FX_THREADS;
+        float4* mc = reinterpret_cast<float4*>(a.arena_mc);
+#pragma unroll 1
+        for (int r = 0; r < 2; r++) {
+            const size_t v0 = (size_t)(r ? a.range_b[0] : a.range_a[0]) >> 2, v1 = (size_t)(r ? a.range_b[1] : a.range_a[1]) >> 2;
+            const size_t nv = v1 - v0, per = (nv + a.world - 1) / a.world;
+            const size_t lo = v0 + per * a.rank, hi = (lo + per < v1) ? lo + per : v1;
+            size_t i = lo + rtid;
+            for (; i + 3 * rsize < hi; i += 4 * rsize) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) v[u] = mm_ld_reduce(mc + i + u * rsize);
+#pragma unroll
+                for (int u = 0; u < 4; u++) mm_st(mc + i + u * rsize, v[u]);
+            }
+            for (; i < hi; i += rsize) mm_st(mc + i, mm_ld_reduce(mc + i));
+        }
+    } else if (a.sh_rest_alloc > 0) {
+        // ---- 3b. dL/dshN of all N Gaussians from the gathered slices (local replica), into the local arena
+        float* out = a.arena_local + a.off_shN;
+        const dvs_shx::ExchangeArgs x{a.means, a.campos, a.gather_local, (long long)a.N, a.world, a.sh_degree,
+                                      3 * a.sh_rest_alloc, out, (reinterpret_cast<uintptr_t>(out) & 15u) == 0 ? 1 : 0};
+        const int64_t n_tiles = (a.N + FX_THREADS - 1) / FX_THREADS;
+        const int workers = (int)gridDim.x - a.reduce_ctas;
+        for (int64_t tile = (int64_t)blockIdx.x - a.reduce_ctas; tile < n_tiles; tile += workers) {
+            const int64_t base = tile * FX_THREADS;
+            const int cnt = (int)(a.N - base < FX_THREADS ? a.N - base : FX_THREADS);
+            dvs_shx::exchange_compute(x, s_rows, threadIdx.x, base, cnt);
+            __syncthreads();
+            dvs_shx::exchange_store(x, s_rows, threadIdx.x, FX_THREADS, base, cnt);
+            __syncthreads();
+        }
+    }
+    // ---- 4. every shard has been re-broadcast: the arena is complete on every rank
+    cross_rank_barrier(a, seq0 + 1u, &s_fail);
+}
+
+int fused_grid(int ctas) {
+    int dev = 0, sms = 148, per_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t smem = (size_t)FX_THREADS * FX_ROW_WORDS * sizeof(float);
+    if (cudaFuncSetAttribute(fused_exchange_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_exchange_kernel, FX_THREADS, smem) != cudaSuccess || per_sm < 1)
+        return 0;
+    const int cap = sms * per_sm;
+    if (ctas <= 0) ctas = sms;
+    return ctas < cap ? ctas : cap;
+}
+
+}  // namespace
+
+extern "C" DVS_API int dvs_coll_exchange_fused_grid(int ctas) { return fused_grid(ctas); }
+
+extern "C" DVS_API int dvs_coll_exchange_fused(const dvs_coll_fused* args, void* stream) {
+    if (!args) return DVS_E_INVALID;
+    dvs_coll_fused a = *args;
+    if (!a.arena_mc || !a.arena_local || !a.gather_mc || !a.gather_local || !a.signal_mc || !a.signal_local || !a.grid_counter ||
+        !a.means)
+        return DVS_E_INVALID;
+    if (a.world < 1 || a.world > 16 || a.rank < 0 || a.rank >= a.world || a.N < 0 || a.sh_degree < 0 || a.sh_degree > 3 ||
+        a.sh_rest_alloc < 0 || a.sh_rest_alloc > 15 || (a.sh_degree + 1) * (a.sh_degree + 1) - 1 > a.sh_rest_alloc)
+        return DVS_E_INVALID;
+    const int64_t offs[6] = {a.off_sh0, a.off_shN, a.range_a[0], a.range_a[1], a.range_b[0], a.range_b[1]};
+    for (int64_t o : offs)
+        if (o < 0 || (o & 3)) return DVS_E_INVALID;
+    if (a.range_a[1] < a.range_a[0] || a.range_b[1] < a.range_b[0]) return DVS_E_INVALID;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(a.arena_mc) | reinterpret_cast<uintptr_t>(a.arena_local) |
+                         reinterpret_cast<uintptr_t>(a.gather_mc) | reinterpret_cast<uintptr_t>(a.gather_local);
+    if (al & 15u) return DVS_E_INVALID;
+    if (a.N == 0) return DVS_OK;
+    const int grid = fused_grid(a.ctas);
+    if (grid < 2) return DVS_E_CUDA;
+    a.ctas = grid;
+    if (a.reduce_ctas <= 0) a.reduce_ctas = grid / 2;
+    if (a.reduce_ctas >= grid) a.reduce_ctas = grid - 1;   // at least one CTA forms dL/dshN
+    if (a.sh_rest_alloc == 0) a.reduce_ctas = grid;        // nothing to form: everybody reduces
+    const size_t smem = (size_t)FX_THREADS * FX_ROW_WORDS * sizeof(float);
+    void* kargs[] = {&a};
+    // cooperative launch: the device-side barriers need every CTA resident (fails instead of deadlocking otherwise)
+    const cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(fused_exchange_kernel), dim3(grid), dim3(FX_THREADS),
+                                                      kargs, smem, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? DVS_OK : DVS_E_CUDA;
 }

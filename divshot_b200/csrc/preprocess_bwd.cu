@@ -51,6 +51,9 @@ preprocess_bwd_kernel(Cam cam, int N, Params prm, const uint4* __restrict__ aux,
     const int i = blockIdx.x * PB_THREADS + threadIdx.x;
     const int warp_first = blockIdx.x * PB_THREADS + warp * 32;
     const bool accumulate = flags & DVS_FLAG_ACCUMULATE;
+    // DVS_FLAG_SKIP_SHN_GRAD: dL/dshN is not written here (180 of the 236 B per Gaussian of this kernel's output at degree 3) —
+    // the fused multi-GPU exchange forms the SUMMED dL/dshN of all views from their dL/dsh0 (collective.cu)
+    const bool write_shn = !(flags & DVS_FLAG_SKIP_SHN_GRAD) || accumulate;
     uint64_t* bar = reinterpret_cast<uint64_t*>(pb_smem) + warp;
     unsigned char* base = pb_smem + 64 + (size_t)warp * L.total;
     float* s_means = reinterpret_cast<float*>(base + L.means);
@@ -370,7 +373,7 @@ preprocess_bwd_kernel(Cam cam, int N, Params prm, const uint4* __restrict__ aux,
             bulk_s2g(g.quats + 4 * (size_t)warp_first, s_quats, 32 * 16);
             bulk_s2g(g.opacities + warp_first, s_opac, 32 * 4);
             bulk_s2g(g.sh0 + 3 * (size_t)warp_first, s_sh0, 32 * 12);
-            if (row > 0) bulk_s2g(g.shN + (size_t)warp_first * row, mysh, 32u * (uint32_t)row * 4u);
+            if (row > 0 && write_shn) bulk_s2g(g.shN + (size_t)warp_first * row, mysh, 32u * (uint32_t)row * 4u);
             if (any_vis) bulk_s2g(sgrad + 3 * (size_t)warp_first, s_sg, 32 * 48);
             bulk_commit();
             bulk_wait_read0();
@@ -408,7 +411,7 @@ preprocess_bwd_kernel(Cam cam, int N, Params prm, const uint4* __restrict__ aux,
         }
     }
     // SH rest gradients: coalesced stores of the staged rows
-    if (row > 0) {
+    if (row > 0 && write_shn) {
         __syncwarp();
         float* dst = g.shN + (size_t)warp_first * row;
         const int nvec = nflt >> 2;

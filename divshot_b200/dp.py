@@ -194,3 +194,98 @@ class FactoredGradientExchange:
     @staticmethod
     def plain_wire_bytes_per_gaussian(world: int, sh_rest: int = 15) -> float:
         return 2 * (world - 1) / world * (56 + 12 * sh_rest)
+
+
+class FusedGradientExchange:
+    """The whole exchange as ONE kernel of ours over NVSwitch multicast (csrc/collective.cu, dvs_coll_exchange_fused): every rank
+    multicasts its dL/dsh0 (multimem.st), a device-side cross-rank barrier (multimem.red on a symmetric counter), then half of the
+    CTAs sum the 56 B per Gaussian of everything-but-shN in the switch (multimem.ld_reduce / multimem.st) while the other half
+    form the summed dL/dshN locally from the gathered slices, and a second device-side barrier.  No NCCL call, no host
+    synchronisation, one launch.  Needs the gradient arena in symmetric memory with a multicast mapping (GradientReducer with
+    backend nvls/auto provides it: pass its `flat` and handle) and one view per rank and step.
+
+    With `skip_shn_write` the caller passes DVS_FLAG_SKIP_SHN_GRAD to the backward: the per-view dL/dshN (180 B per Gaussian) is
+    then never written to HBM at all, the kernel writes the sum.
+    """
+
+    def __init__(self, grads, reducer: "GradientReducer", group=None, ctas: int = 0, reduce_ctas: int = 0):
+        import ctypes as C
+
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import _cabi
+        if reducer._hdl is None or reducer.flat.data_ptr() != grads.flat.data_ptr():
+            raise RuntimeError("FusedGradientExchange: the gradient arena must be the reducer's symmetric (NVLS) buffer")
+        if grads.shN.numel() == 0:
+            raise ValueError("FusedGradientExchange: no higher SH bands (degree 0), nothing to factor out")
+        self.g, self.group = grads, group
+        self._C, self._cabi, self._lib = C, _cabi, _cabi.load()
+        hdl = reducer._hdl
+        self.world, self.rank = hdl.world_size, hdl.rank
+        if self.world > 16:
+            raise ValueError("FusedGradientExchange: at most 16 ranks")
+        dev = grads.flat.device
+        N = grads.opacities.shape[0]
+        self.N = N
+        group_name = (group or dist.group.WORLD).group_name
+        self.gather = symm_mem.empty(self.world * 3 * N + 4, dtype=torch.float32, device=dev)
+        self._gh = symm_mem.rendezvous(self.gather, group_name)
+        self.signal = symm_mem.empty(64, dtype=torch.int32, device=dev)
+        self.signal.zero_()
+        self._sh = symm_mem.rendezvous(self.signal, group_name)
+        if not getattr(self._gh, "multicast_ptr", 0) or not getattr(self._sh, "multicast_ptr", 0):
+            raise RuntimeError("FusedGradientExchange: no NVLS multicast mapping for the gather / signal buffers")
+        self.local_words = torch.zeros(64, dtype=torch.int32, device=dev)  # [0] grid counter, [32] status
+        flat = grads.flat
+        off = lambda t: (t.data_ptr() - flat.data_ptr()) // 4  # noqa: E731
+        if not (off(grads.quats) < off(grads.shN) < off(grads.means3D) < off(grads.scales) < off(grads.sh0) < off(grads.opacities)):
+            raise ValueError("FusedGradientExchange: unexpected gradient arena layout")
+        a = _cabi.DvsCollFused()
+        a.arena_mc, a.arena_local = hdl.multicast_ptr, flat.data_ptr()
+        a.gather_mc, a.gather_local = self._gh.multicast_ptr, self.gather.data_ptr()
+        a.signal_mc, a.signal_local = self._sh.multicast_ptr, self.signal.data_ptr()
+        a.grid_counter, a.status = self.local_words.data_ptr(), self.local_words.data_ptr() + 128
+        a.N, a.off_sh0, a.off_shN = N, off(grads.sh0), off(grads.shN)
+        a.range_a[0], a.range_a[1] = off(grads.quats), off(grads.quats) + 4 * N
+        end_b = (off(grads.opacities) + N + 3) // 4 * 4  # the pad floats behind the last tensor are zero on every rank
+        a.range_b[0], a.range_b[1] = off(grads.means3D), min(end_b, flat.numel())
+        a.rank, a.world, a.sh_rest_alloc = self.rank, self.world, grads.shN.shape[1]
+        a.ctas, a.reduce_ctas = ctas, reduce_ctas
+        self._args = a
+        self.launches = 0
+        self.grid = self._lib.dvs_coll_exchange_fused_grid(ctas)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group)  # every rank's signal word is zero before anybody's first kernel touches it
+
+    def set_cameras(self, campos_local: torch.Tensor):
+        """All ranks' camera centres -> the kernel's by-value argument (gather once per view assignment; 12 bytes per rank)."""
+        dev = self.g.flat.device
+        allc = torch.zeros(self.world, 3, dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(allc.view(-1), campos_local.to(dev, torch.float32).reshape(3).contiguous(), group=self.group)
+        host = allc.cpu().reshape(-1).tolist()
+        for k, v in enumerate(host):
+            self._args.campos[k] = v
+        self._cam_local = campos_local.detach().to("cpu", torch.float32).reshape(3).clone()
+
+    def exchange(self, means: torch.Tensor, campos_local: torch.Tensor, deg: int):
+        if getattr(self, "_cam_local", None) is None:
+            self.set_cameras(campos_local)
+        elif not torch.equal(campos_local.detach().to("cpu", torch.float32).reshape(3), self._cam_local):
+            # a changed view must be re-announced by EVERY rank in the same step (collective): callers that change views call
+            # set_cameras() on all ranks; a silent local change would form dL/dshN with stale directions
+            raise RuntimeError("FusedGradientExchange: this rank's camera changed; call set_cameras() on every rank first")
+        a = self._args
+        a.means, a.sh_degree, a.launch_index = means.data_ptr(), deg, self.launches
+        st = torch.cuda.current_stream(self.g.flat.device).cuda_stream
+        rc = self._lib.dvs_coll_exchange_fused(self._C.byref(a), self._C.c_void_p(st))
+        if rc != 0:
+            raise RuntimeError(f"dvs_coll_exchange_fused failed ({rc})")
+        self.launches += 1
+        return self.g
+
+    def status(self) -> int:
+        """Non-zero if a device-side barrier timed out (synchronises)."""
+        return int(self.local_words[32].item())
+
+    def wire_bytes_per_gaussian(self) -> float:
+        return self.world * 12 + 56 * (1 + 1 / self.world)

@@ -185,6 +185,26 @@ class Rasterizer:
                                                  dL_dpix_host.data_ptr(), out_color_host.data_ptr(), flags,
                                                  C.c_void_p(st)))
 
+    def step_host_async(self, cam, params: dict, grads: GradBuffers, dL_dpix_host: torch.Tensor,
+                        out_color_host: torch.Tensor, slot: int, flags: int = 0):
+        """Pipelined end-to-end step (dvs_rast_step_host_async): queues H2D, forward, D2H, backward on `slot` and returns;
+        step_host_wait(slot) blocks until that step's image is in out_color_host."""
+        N = params["means3D"].shape[0]
+        g = _cabi.DvsGrads()
+        for n in PARAM_NAMES:
+            t = getattr(grads, n)
+            if t.numel() > 0:
+                setattr(g, n, t.data_ptr())
+        self._cam, self._params = cam, params
+        self.generation += 1
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self._lib.dvs_rast_step_host_async(self._h, C.byref(cam), N, C.byref(self._pstruct(params)), C.byref(g),
+                                                       dL_dpix_host.data_ptr(), out_color_host.data_ptr(), flags, slot,
+                                                       C.c_void_p(st)))
+
+    def step_host_wait(self, slot: int):
+        self._check(self._lib.dvs_rast_step_host_wait(self._h, slot))
+
     def set_profiling(self, on: bool):
         """Per-stage CUDA events on/off (off in a training loop; stage_ms() needs them on)."""
         if hasattr(self._lib, "dvs_rast_set_profiling"):

@@ -50,6 +50,8 @@ extern "C" {
                                        made by a later call (non-blocking) or by dvs_rast_get_stats (blocking).  Only
                                        honoured once a synchronous forward has sized the arena. */
 
+#define DVS_FLAG_SKIP_SHN_GRAD 64u  /* backward: do not write grads->shN (180 of the 236 B per Gaussian at SH degree 3): the caller forms
+                                     * the summed dL/dshN itself from every view's dL/dsh0 (dvs_coll_exchange_fused); not with ACCUMULATE */
 #define DVS_FLAG_TIGHT_LISTS 32u    /* forward, only together with DVS_FLAG_DEFER_CHECK (the training-loop mode): entries whose
                                        {alpha >= 1/255} footprint misses their tile are not put into the tile lists.  Image,
                                        final_T and gradients are unchanged; point_list / ranges are the whole-rectangle lists
@@ -181,6 +183,22 @@ DVS_API int dvs_rast_step_host(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t
                                const dvs_grads* grads, const float* dL_dpix_host, float* out_color_host,
                                uint32_t bwd_flags, void* stream);
 
+/*
+ * The same step, PIPELINED: dvs_rast_step_host_async only queues the work of one step on `slot` (0 or 1: its own device
+ * staging buffers and events) and returns; dvs_rast_step_host_wait(slot) blocks until that step's image has arrived in its
+ * out_color_host.  A trainer alternates the slots and waits for step k only after queueing step k+1, so step k+1's H2D
+ * overlaps step k's backward, step k's D2H overlaps step k+1's forward, and the launch queue never drains:
+ *     async(slot 0); async(slot 1); wait(0); async(slot 0); wait(1); ...
+ * The host buffers of a slot must stay untouched between its async and its wait; whatever else the caller queues on
+ * `stream` after the call (the multi-GPU gradient exchange, the optimiser) runs after the step's backward with no host
+ * synchronisation in between.  Use DVS_FLAG_DEFER_CHECK in cam->flags (a synchronous forward would stall the pipeline);
+ * wait() reports an overflowed deferred-check forward (DVS_E_OVERFLOW) as soon as it is known.
+ */
+DVS_API int dvs_rast_step_host_async(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, const dvs_params* params,
+                                     const dvs_grads* grads, const float* dL_dpix_host, float* out_color_host,
+                                     uint32_t bwd_flags, int slot, void* stream);
+DVS_API int dvs_rast_step_host_wait(dvs_rast_ctx* ctx, int slot);
+
 DVS_API int dvs_rast_get_stats(dvs_rast_ctx* ctx, dvs_stats* out);
 
 /* Per-stage CUDA events (dvs_rast_stage_ms) are recorded only while profiling is on (default: on).  A training loop
@@ -216,6 +234,48 @@ DVS_API int dvs_coll_allreduce_nvls(void* multicast_ptr, size_t numel_f32, int r
  */
 DVS_API int dvs_coll_sh_grad_from_dsh0(const float* means, const float* campos_all_host, const float* dsh0_all, int64_t N,
                                        int num_views, int sh_degree, int sh_rest_alloc, float* out_dshN, void* stream);
+
+/*
+ * The whole multi-GPU gradient exchange of SURVEY.md section 8(e) as ONE kernel over NVSwitch multicast (NVLS) mappings —
+ * gather, in-switch reduction, cross-rank barriers and the local SH accumulation fused (one view per rank and step):
+ *   1. gather : every rank multicasts its dL/dsh0 [N,3] (12 B per Gaussian) into slice `rank` of a symmetric gather area
+ *               with multimem.st — one store lands in all `world` replicas;
+ *   2. barrier: all ranks' gathers have landed and all ranks' backward passes are complete (multimem.red on a symmetric
+ *               counter word + acquire polling of the local replica; no host involvement);
+ *   3. the first `reduce_ctas` CTAs sum everything except dL/dshN (two ranges of the arena, 56 B per Gaussian) in the switch:
+ *               rank r reduces shard r with multimem.ld_reduce and re-broadcasts it with multimem.st; the other CTAs
+ *               meanwhile form  dL/dshN[i] = sum_v B(dir_{v,i}) (x) dL/dsh0_v[i] / SH_C0  from the gathered slices (HBM-bound)
+ *               straight into the local arena — the NVLink-bound and the HBM-bound halves overlap;
+ *   4. barrier: every shard has been re-broadcast (the arena may be read / overwritten again).
+ * Bytes received per GPU and Gaussian: 12 W + 56 (1 + 1/W) instead of 236 (1 + 1/W) for the plain in-switch all-reduce.
+ * All pointers are device addresses of this rank.  `*_mc` are the multicast addresses, `*_local` this rank's unicast
+ * addresses of the same symmetric allocations (torch.distributed._symmetric_memory or cuMulticast*).  The words behind
+ * `signal_*` and `grid_counter` must be zero before the FIRST call and are owned by the kernel afterwards; `launch_index` is
+ * 0, 1, 2, ... and every rank must make the same sequence of calls.  `status` (device, may be NULL) is set non-zero if a
+ * barrier timed out (~2 s): the kernel then ends without hanging and the results are invalid.
+ * Offsets are in floats from the start of the arena, multiples of 4.  N % 4 must be 0 for the vector path (else scalar).
+ */
+typedef struct dvs_coll_fused {
+    void* arena_mc;
+    float* arena_local;
+    void* gather_mc;            /* [world][3 N] floats */
+    float* gather_local;
+    uint32_t* signal_mc;
+    uint32_t* signal_local;
+    uint32_t* grid_counter;
+    uint32_t* status;
+    const float* means;         /* [N,3] parameters (view directions) */
+    float campos[16 * 3];       /* camera centre of every rank's view */
+    int64_t N;
+    int64_t off_sh0, off_shN;   /* dL/dsh0 [N,3] (source of the gather), dL/dshN [N,sh_rest_alloc,3] (written locally) */
+    int64_t range_a[2], range_b[2]; /* [begin, end) of the two reduced ranges */
+    uint64_t launch_index;
+    int32_t rank, world, sh_degree, sh_rest_alloc;
+    int32_t ctas, reduce_ctas;  /* <= 0: defaults (one CTA per SM; half of them reduce) */
+} dvs_coll_fused;
+DVS_API int dvs_coll_exchange_fused(const dvs_coll_fused* args, void* stream);
+/* grid size dvs_coll_exchange_fused will use on the current device for `ctas` (the co-residency bound applied) */
+DVS_API int dvs_coll_exchange_fused_grid(int ctas);
 
 #ifdef __cplusplus
 }

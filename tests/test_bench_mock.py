@@ -43,6 +43,12 @@ class _FakeRasterizer:
     def step_host(self, *a, **kw):
         self.calls += 1
 
+    def step_host_async(self, *a, **kw):
+        self.calls += 1
+
+    def step_host_wait(self, slot):
+        pass
+
     def stage_ms(self):
         return {k: 0.1 + 0.01 * i for i, k in enumerate(STAGES)}
 
@@ -115,6 +121,9 @@ def _bench_rank(rank, world, port, q):
             grads.flat.fill_(float(rank + 1))
 
         def step_host(self, cam, params, grads, *a, **kw):
+            grads.flat.fill_(float(rank + 1))
+
+        def step_host_async(self, cam, params, grads, *a, **kw):
             grads.flat.fill_(float(rank + 1))
 
     rasterizer.Rasterizer = R

@@ -386,3 +386,70 @@ def test_tight_lists_are_the_reference_lists_minus_empty_masks():
         assert rel_err(tight["g"], full["g"]) < 5e-5
     finally:
         r.close()
+
+
+def test_pipelined_host_step_matches_the_synchronous_one():
+    """dvs_rast_step_host_async / dvs_rast_step_host_wait (two pipeline slots, what bench.py's e2e loop drives): each step's
+    image arrives in its own pinned buffer, the gradients after step k are those of step k's dL/dpix."""
+    from divshot_b200.rasterizer import GradBuffers, Rasterizer, scene_to_device
+    sc = make_scene(N=7000, width=144, height=96, sh_degree=1, seed=97, views=2, bg=(0.2, 0.1, 0.3))
+    sc.log_scales += 0.7
+    r = Rasterizer(0)
+    try:
+        dev = r.device
+        params = scene_to_device(sc, dev)
+        cams = [_cabi.make_camera(c, 1) for c in sc.cameras]
+        cams_d = [_cabi.make_camera(c, 1, flags=_cabi.FLAG_DEFER_CHECK | _cabi.FLAG_TIGHT_LISTS) for c in sc.cameras]
+        dls = [torch.from_numpy(sc.dL_dpix[v]).pin_memory() for v in range(2)]
+        want_img, want_g = [], []
+        for v in range(2):  # references: the device-resident path
+            img, _ = r.forward(cams[v], params)
+            g = GradBuffers.allocate(sc.N, 3, dev); r.backward(dls[v].to(dev), g)
+            torch.cuda.synchronize()
+            want_img.append(img.cpu()); want_g.append(g.flat.cpu().numpy())
+        imgs = [torch.zeros(3, 96, 144).pin_memory() for _ in range(2)]
+        g = GradBuffers.allocate(sc.N, 3, dev)
+        # synchronous host step
+        r.step_host(cams_d[0], params, g, dls[0], imgs[0])
+        assert torch.equal(imgs[0], want_img[0]) and rel_err(g.flat.cpu().numpy(), want_g[0]) < 5e-5
+        # pipelined: views alternate, the wait for step k comes after step k+1 was queued
+        steps = 6
+        for k in range(steps):
+            imgs[k & 1].zero_() if k < 2 else None
+            r.step_host_async(cams_d[k & 1], params, g, dls[k & 1], imgs[k & 1], k & 1)
+            if k > 0:
+                r.step_host_wait((k - 1) & 1)
+                assert torch.equal(imgs[(k - 1) & 1], want_img[(k - 1) & 1]), f"image of step {k - 1}"
+        r.step_host_wait((steps - 1) & 1)
+        torch.cuda.synchronize()
+        assert torch.equal(imgs[(steps - 1) & 1], want_img[(steps - 1) & 1])
+        assert rel_err(g.flat.cpu().numpy(), want_g[(steps - 1) & 1]) < 5e-5
+        assert r.stats()["overflow"] == 0
+    finally:
+        r.close()
+
+
+def test_backward_can_skip_the_shN_gradient():
+    """DVS_FLAG_SKIP_SHN_GRAD (the fused multi-GPU exchange forms the summed dL/dshN itself): every other gradient is
+    unchanged and grads.shN is not touched."""
+    from divshot_b200.rasterizer import GradBuffers, Rasterizer, scene_to_device
+    sc = make_scene(N=5000, width=112, height=80, sh_degree=3, seed=99)
+    sc.log_scales += 0.7
+    r = Rasterizer(0)
+    try:
+        dev = r.device
+        params = scene_to_device(sc, dev)
+        cam = _cabi.make_camera(sc.cameras[0], 3)
+        dl = torch.from_numpy(sc.dL_dpix[0]).to(dev)
+        r.forward(cam, params)
+        g0 = GradBuffers.allocate(sc.N, 15, dev); r.backward(dl, g0)
+        r.forward(cam, params)
+        g1 = GradBuffers.allocate(sc.N, 15, dev); g1.shN.fill_(7.0)
+        r.backward(dl, g1, flags=_cabi.FLAG_SKIP_SHN_GRAD)
+        torch.cuda.synchronize()
+        assert bool((g1.shN == 7.0).all()), "dL/dshN must not be written"
+        assert g0.shN.abs().max() > 0
+        for k in ("means3D", "scales", "quats", "opacities", "sh0"):
+            assert rel_err(getattr(g1, k).cpu().numpy(), getattr(g0, k).cpu().numpy()) < 5e-5, k
+    finally:
+        r.close()
