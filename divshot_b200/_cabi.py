@@ -27,7 +27,7 @@ EXPORTS = [
     "dvs_rast_create", "dvs_rast_destroy", "dvs_rast_last_error", "dvs_rast_version", "dvs_rast_reserve",
     "dvs_rast_forward", "dvs_rast_backward", "dvs_rast_step_host", "dvs_rast_get_stats", "dvs_rast_debug_read",
     "dvs_rast_stage_ms", "dvs_rast_stage_name", "dvs_rast_forward_aux", "dvs_rast_backward_aux",
-    "dvs_rast_set_profiling", "dvs_rast_step_host_async", "dvs_rast_step_host_wait",
+    "dvs_rast_set_profiling", "dvs_rast_step_host_async", "dvs_rast_step_host_wait", "dvs_rast_device_overflow_word",
 ]
 COLL_EXPORTS = ["dvs_coll_allreduce_nvls", "dvs_coll_sh_grad_from_dsh0", "dvs_coll_exchange_fused", "dvs_coll_exchange_fused_grid"]
 

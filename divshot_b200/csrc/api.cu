@@ -78,7 +78,9 @@ struct dvs_rast_ctx {
     dvs_stats st{};
     cudaEvent_t ev[DVS_NUM_STAGES + 2] = {};
     // dvs_rast_step_host: copies run on their own stream so the H2D overlaps the forward and the D2H the backward
-    cudaStream_t copy_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;      // host -> device (dL/dpix)
+    cudaStream_t copy_stream_out = nullptr;  // device -> host (image): its own stream, so a step's H2D is not queued behind the
+                                             // previous step's D2H (PCIe is full duplex)
     cudaEvent_t ev_img = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr}, ev_bwd_done[2] = {nullptr, nullptr};
     bool slot_used[2] = {false, false};
@@ -232,6 +234,7 @@ int dvs_rast_create(int device, dvs_rast_ctx** out) {
     if (e == cudaSuccess) e = cudaMemset(ctx->info, 0, 16 * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_check, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream_out, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_img, cudaEventDisableTiming);
     for (int k = 0; e == cudaSuccess && k < 2; k++) {
         e = cudaEventCreateWithFlags(&ctx->ev_h2d[k], cudaEventDisableTiming);
@@ -269,6 +272,7 @@ void dvs_rast_destroy(dvs_rast_ctx* ctx) {
         if (ctx->ev_bwd_done[k]) cudaEventDestroy(ctx->ev_bwd_done[k]);
     }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->copy_stream_out) cudaStreamDestroy(ctx->copy_stream_out);
     delete ctx;
 }
 
@@ -599,6 +603,7 @@ static int step_host_enqueue(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N
     if (P > ctx->cap_pix) {  // the per-pixel arenas are about to be re-allocated: nothing of an earlier step may be in flight
         CK(cudaStreamSynchronize(st));
         CK(cudaStreamSynchronize(ctx->copy_stream));
+        CK(cudaStreamSynchronize(ctx->copy_stream_out));
         ctx->slot_used[0] = ctx->slot_used[1] = false;
     }
     if ((rc = ensure_pix(ctx, P))) return rc;
@@ -615,9 +620,9 @@ static int step_host_enqueue(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N
     CK(cudaEventRecord(ctx->ev_h2d[slot], ctx->copy_stream));
     if ((rc = dvs_rast_forward(ctx, cam, N, params, ctx->d_image[slot], nullptr, stream))) return rc;
     CK(cudaEventRecord(ctx->ev_img, st));
-    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_img, 0));
-    CK(cudaMemcpyAsync(out_color_host, ctx->d_image[slot], 3 * (size_t)P * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_stream));
-    CK(cudaEventRecord(ctx->ev_d2h[slot], ctx->copy_stream));
+    CK(cudaStreamWaitEvent(ctx->copy_stream_out, ctx->ev_img, 0));
+    CK(cudaMemcpyAsync(out_color_host, ctx->d_image[slot], 3 * (size_t)P * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_stream_out));
+    CK(cudaEventRecord(ctx->ev_d2h[slot], ctx->copy_stream_out));
     CK(cudaStreamWaitEvent(st, ctx->ev_h2d[slot], 0));
     if ((rc = dvs_rast_backward(ctx, params, ctx->h2d_grad[slot], grads, bwd_flags, stream))) return rc;
     CK(cudaEventRecord(ctx->ev_bwd_done[slot], st));
@@ -655,6 +660,8 @@ int dvs_rast_step_host_wait(dvs_rast_ctx* ctx, int slot) {
     CK(cudaEventSynchronize(ctx->ev_d2h[slot]));  // the slot's image is in out_color_host
     return resolve_pending(ctx, false);           // report an overflowed deferred-check forward as soon as it is known
 }
+
+const uint32_t* dvs_rast_device_overflow_word(const dvs_rast_ctx* ctx) { return ctx ? ctx->info + 2 : nullptr; }
 
 int dvs_rast_set_profiling(dvs_rast_ctx* ctx, int on) {
     if (!ctx) return DVS_E_INVALID;

@@ -123,7 +123,8 @@ __global__ void k_regularise(Tensors p, Tensors g, int64_t N, float w_o, float w
 
 // ---------------------------------------------------------------------------------------------- ADC kernels
 __global__ void k_adc_accumulate(const float* __restrict__ g2, const float* __restrict__ gabs, const int32_t* __restrict__ radii,
-                                 float* __restrict__ accum, float* __restrict__ denom, int64_t N) {
+                                 float* __restrict__ accum, float* __restrict__ denom, int64_t N, const uint32_t* __restrict__ skip) {
+    if (skip && *skip) return;  // the step's forward overflowed its arena: no gradients were produced, nothing to count
     GRID_STRIDE(i, N) {
         if (radii[i] <= 0) continue;
         const float* g = gabs ? gabs : g2;
@@ -367,9 +368,9 @@ cudaError_t mcmc_regularise(Tensors p, Tensors g, int64_t N, float w_o, float w_
 
 // ---------------------------------------------------------------------------------------------- ADC
 cudaError_t adc_accumulate(const float* mean2D_grad, const float* mean2D_abs, const int32_t* radii, float* accum,
-                           float* denom, int64_t N, cudaStream_t st) {
+                           float* denom, int64_t N, cudaStream_t st, const uint32_t* skip) {
     if (N <= 0) return cudaSuccess;
-    DVS_LAUNCH(k_adc_accumulate, N, st, mean2D_grad, mean2D_abs, radii, accum, denom, N);
+    DVS_LAUNCH(k_adc_accumulate, N, st, mean2D_grad, mean2D_abs, radii, accum, denom, N, skip);
     return cudaGetLastError();
 }
 

@@ -38,8 +38,9 @@ cudaError_t mcmc_regularise(Tensors p, Tensors g, int64_t N, float w_o, float w_
 
 // ---- densifyStrategy 0 / 2 (ADC): statistics after every backward, refinement every `refineEvery` iterations
 // accum[i] += ||mean2D_grad[i]|| (or the abs-grad sum when `abs_grad` != nullptr), denom[i] += 1 for visible i
+// (`skip`: optional device word, non-zero = this step produced no gradients — its forward overflowed — and is not counted)
 cudaError_t adc_accumulate(const float* mean2D_grad, const float* mean2D_abs, const int32_t* radii, float* accum,
-                           float* denom, int64_t N, cudaStream_t st);
+                           float* denom, int64_t N, cudaStream_t st, const uint32_t* skip = nullptr);
 struct AdcConfig {
     float grad_threshold, percent_dense, extent, prune_opacity, prune_scale3d;
     bool revised_opacity = false;  // `revisedOpacity`: clones / split samples get opacity 1 - sqrt(1 - o)

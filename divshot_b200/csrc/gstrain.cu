@@ -197,32 +197,65 @@ __global__ void mask_grad_kernel(float* __restrict__ dL_dpix, const float* __res
         dL_dpix[i] *= mask[i % P];
 }
 
-// fused Adam over one parameter group (4 streams in, 3 out, 128-bit where aligned is left to the compiler)
-__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                            float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps, float c1,
-                            float c2) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const float gi = g[i];
-        const float mi = b1 * m[i] + (1.f - b1) * gi;
-        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-        m[i] = mi; v[i] = vi;
-        p[i] -= lr * (mi * c1) / (sqrtf(vi * c2) + eps);
-    }
+// Fused multi-tensor Adam: ONE launch steps all six parameter groups of the flat arenas (params / grads / two moments share
+// one layout), each with its own learning rate — 16 B of the four streams per element and thread, 128-bit accesses (group
+// offsets are multiples of 4 floats; a group's last partial vector is done element-wise).  `radii` != nullptr is `visibleAdam`
+// (the "sparse Adam" of the 3DGS accelerations the closed trainer's flag is named after): only Gaussians the current view saw
+// (radius > 0) are stepped, the moments of the others are left untouched instead of decaying.
+// `skip` (device word, may be null): non-zero = the step's forward overflowed its binning arena and produced no image and no
+// gradients (info[2] of the rasterizer context) — the update must not run (a zero gradient still moves every parameter
+// through the decaying first moment); the step is redone by the host.
+struct AdamGroup { size_t off, n; float lr; int width; };
+struct AdamGroups { AdamGroup g[6]; };
+
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float lr, float b1, float b2, float eps, float c1, float c2) {
+    m = b1 * m + (1.f - b1) * g;
+    v = b2 * v + (1.f - b2) * g * g;
+    p -= lr * (m * c1) / (sqrtf(v * c2) + eps);
 }
 
-// `visibleAdam` (the "sparse Adam" of the 3DGS accelerations the closed trainer's flag is named after): only Gaussians the
-// current view saw (radius > 0) are stepped; the moments of the others are left untouched instead of decaying.
-__global__ void adam_visible_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                    float* __restrict__ v, size_t rows, int width, const int32_t* __restrict__ radii, float lr,
-                                    float b1, float b2, float eps, float c1, float c2) {
-    const size_t n = rows * (size_t)width;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        if (radii[i / (size_t)width] <= 0) continue;
-        const float gi = g[i];
-        const float mi = b1 * m[i] + (1.f - b1) * gi;
-        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-        m[i] = mi; v[i] = vi;
-        p[i] -= lr * (mi * c1) / (sqrtf(vi * c2) + eps);
+__global__ void __launch_bounds__(256)
+adam_fused_kernel(float* __restrict__ P, const float* __restrict__ G, float* __restrict__ M, float* __restrict__ V,
+                  const AdamGroups groups, const int32_t* __restrict__ radii, const uint32_t* __restrict__ skip, float b1,
+                  float b2, float eps, float c1, float c2) {
+    if (skip && *skip) return;
+    const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
+#pragma unroll 1
+    for (int k = 0; k < 6; k++) {
+        const AdamGroup gr = groups.g[k];
+        if (gr.n == 0) continue;
+        float4* p4 = reinterpret_cast<float4*>(P + gr.off);
+        const float4* g4 = reinterpret_cast<const float4*>(G + gr.off);
+        float4* m4 = reinterpret_cast<float4*>(M + gr.off);
+        float4* v4 = reinterpret_cast<float4*>(V + gr.off);
+        const size_t nv = gr.n >> 2;
+        for (size_t i = tid; i < nv; i += nthr) {
+            float4 p = p4[i], m = m4[i], v = v4[i];
+            const float4 g = g4[i];
+            if (radii) {
+                const size_t e = 4 * i;
+                const bool s0 = radii[e / gr.width] > 0, s1 = radii[(e + 1) / gr.width] > 0, s2 = radii[(e + 2) / gr.width] > 0,
+                           s3 = radii[(e + 3) / gr.width] > 0;
+                if (!(s0 || s1 || s2 || s3)) continue;
+                if (s0) adam_one(p.x, g.x, m.x, v.x, gr.lr, b1, b2, eps, c1, c2);
+                if (s1) adam_one(p.y, g.y, m.y, v.y, gr.lr, b1, b2, eps, c1, c2);
+                if (s2) adam_one(p.z, g.z, m.z, v.z, gr.lr, b1, b2, eps, c1, c2);
+                if (s3) adam_one(p.w, g.w, m.w, v.w, gr.lr, b1, b2, eps, c1, c2);
+            } else {
+                adam_one(p.x, g.x, m.x, v.x, gr.lr, b1, b2, eps, c1, c2);
+                adam_one(p.y, g.y, m.y, v.y, gr.lr, b1, b2, eps, c1, c2);
+                adam_one(p.z, g.z, m.z, v.z, gr.lr, b1, b2, eps, c1, c2);
+                adam_one(p.w, g.w, m.w, v.w, gr.lr, b1, b2, eps, c1, c2);
+            }
+            p4[i] = p; m4[i] = m; v4[i] = v;
+        }
+        for (size_t e = (nv << 2) + tid; e < gr.n; e += nthr) {  // the group's last partial vector
+            if (radii && radii[e / gr.width] <= 0) continue;
+            const size_t j = gr.off + e;
+            float p = P[j], m = M[j], v = V[j];
+            adam_one(p, G[j], m, v, gr.lr, b1, b2, eps, c1, c2);
+            P[j] = p; M[j] = m; V[j] = v;
+        }
     }
 }
 
@@ -261,6 +294,16 @@ struct Arena {  // one flat buffer, six 16-byte-aligned views (same order as Gra
     float* sh0() const { return flat + off_sh0; }
     float* opac() const { return flat + off_opac; }
 };
+
+// groups in arena order: quats | shN | means | scales | sh0 | opac  (lrs[] in the same order)
+void launch_adam_fused(const Arena& layout, const float* grads, float* m1, float* m2, int64_t N, const float lrs[6],
+                       const int32_t* radii, const uint32_t* skip, float b1, float b2, float eps, float c1, float c2, cudaStream_t st) {
+    AdamGroups g;
+    const size_t offs[6] = {layout.off_quats, layout.off_shN, layout.off_means, layout.off_scales, layout.off_sh0, layout.off_opac};
+    const int widths[6] = {4, 3 * KR, 3, 3, 3, 1};
+    for (int k = 0; k < 6; k++) g.g[k] = AdamGroup{offs[k], (size_t)widths[k] * (size_t)N, lrs[k], widths[k]};
+    adam_fused_kernel<<<148 * 8, 256, 0, st>>>(layout.flat, grads, m1, m2, g, radii, skip, b1, b2, eps, c1, c2);
+}
 
 void make_projection(dvs_camera& c, const float Rt[12], int W, int H, float fx, float fy, float Pflat[16] = nullptr) {
     // view (world->camera), flat [4c+r]
@@ -661,8 +704,11 @@ void GaussianTrainerScene::trainStep() {
     dvs_params P = I.P();
     dvs_grads G = I.G();
     // Steps run without any host synchronisation (DVS_FLAG_DEFER_CHECK; honoured once a synchronous forward has
-    // sized the binning arena).  A late DVS_E_OVERFLOW means a deferred step overflowed the arena: its kernels
-    // exited early (zero gradients, so the Adam update it fed was harmless) and this step is simply redone.
+    // sized the binning arena).  A late DVS_E_OVERFLOW means a deferred step overflowed the arena: its compositing and
+    // backward kernels exited early, and the kernels queued behind them that would move the model on such a step — the
+    // fused Adam update, the ADC statistics — read the rasterizer's device overflow word and do nothing (a zero gradient
+    // would still move every parameter through the decaying first moment).  The MCMC regulariser only adds to the (unused)
+    // gradients and the exploration noise is a zero-mean perturbation applied every step anyway.  The step is then redone.
     // refinement window (densify.cu): warmupLength < step < refineStopIter; MCMC is strategy 1, ADC 0 and 2
     const bool refining = I.dws && step > config_.warmupLength && step < config_.refineStopIter;
     const bool mcmc = config_.densifyStrategy == 1;
@@ -696,7 +742,7 @@ void GaussianTrainerScene::trainStep() {
             ck(dvs_densify::mcmc_regularise(I.T(I.params), I.T(I.grads), I.N, 0.01f, 0.01f, I.stream), "mcmc_regularise");
         else
             ck(dvs_densify::adc_accumulate(I.d_mean2D, config_.useAbsGrad ? I.d_mean2D_abs : nullptr, I.d_radii, I.d_accum,
-                                           I.d_denom, I.N, I.stream), "adc_accumulate");
+                                           I.d_denom, I.N, I.stream, dvs_rast_device_overflow_word(I.ctx)), "adc_accumulate");
     }
     // Adam, per-group learning rates (GaussianTrainConfig); position lr decays exponentially init -> final
     const float t = std::min(1.f, (float)step / (float)std::max(1, config_.numIters));
@@ -704,20 +750,11 @@ void GaussianTrainerScene::trainStep() {
     const float b1 = 0.9f, b2 = 0.999f, eps = 1e-15f;
     const float c1 = 1.f / (1.f - std::pow(b1, (float)(step + 1))), c2 = 1.f / (1.f - std::pow(b2, (float)(step + 1)));
     const bool visible_only = config_.visibleAdam && I.d_radii;
-    auto adam = [&](size_t off, int width, float lr) {
-        if (visible_only)
-            adam_visible_kernel<<<1184, 256, 0, I.stream>>>(I.params.flat + off, I.grads.flat + off, I.m1.flat + off, I.m2.flat + off,
-                                                            (size_t)I.N, width, I.d_radii, lr, b1, b2, eps, c1, c2);
-        else
-            adam_kernel<<<1184, 256, 0, I.stream>>>(I.params.flat + off, I.grads.flat + off, I.m1.flat + off,
-                                                    I.m2.flat + off, (size_t)width * I.N, lr, b1, b2, eps, c1, c2);
-    };
-    adam(I.params.off_means, 3, lr_pos);
-    adam(I.params.off_scales, 3, config_.scalinglr);
-    adam(I.params.off_quats, 4, config_.rotationlr);
-    adam(I.params.off_opac, 1, config_.opacitylr);
-    adam(I.params.off_sh0, 3, config_.featurelr);
-    adam(I.params.off_shN, 3 * KR, config_.featurelr / 20.f);
+    {   // one launch for all six groups (per-group learning rates)
+        const float lrs[6] = {config_.rotationlr, config_.featurelr / 20.f, lr_pos, config_.scalinglr, config_.featurelr, config_.opacitylr};
+        launch_adam_fused(I.params, I.grads.flat, I.m1.flat, I.m2.flat, I.N, lrs, visible_only ? I.d_radii : nullptr,
+                          dvs_rast_device_overflow_word(I.ctx), b1, b2, eps, c1, c2, I.stream);
+    }
     if (refining) {
         const uint64_t seed = 0x5DEECE66Dull * (uint64_t)(step + 1);
         if (mcmc)  // exploration noise after the optimizer step: Sigma eps gate(opacity) noiselr lr_xyz
@@ -1059,6 +1096,28 @@ void GaussianTrainerScene::getFocusRegionTransformFlat(float m[16]) const {
 // The nine plugin symbols (gs_train.cpp:24,105-110,144-150,178-179) + the two the loader probes
 // (plugin.cpp:97,110: get_description / create_instance — logged, not fatal, if missing).
 extern "C" {
+// test hook: `steps` fused-Adam updates (the trainer's own kernel and arena layout) of device arenas laid out for `capacity`
+// rows with `N` live ones; lrs[] in arena order quats | shN | means | scales | sh0 | opac; returns the arena size in floats
+GS_EXPORT int64_t gstrain_test_adam(float* params, const float* grads, float* m1, float* m2, int64_t N, int64_t capacity,
+                                    const float* lrs, float b1, float b2, float eps, int first_step, int steps,
+                                    const int32_t* radii, const uint32_t* skip, void* stream) {
+    Arena lay;
+    lay.layout(capacity);
+    if (!params) return (int64_t)lay.total;
+    lay.flat = params;
+    for (int t = first_step; t < first_step + steps; t++) {
+        const float c1 = 1.f / (1.f - std::pow(b1, (float)(t + 1))), c2 = 1.f / (1.f - std::pow(b2, (float)(t + 1)));
+        launch_adam_fused(lay, grads, m1, m2, N, lrs, radii, skip, b1, b2, eps, c1, c2, static_cast<cudaStream_t>(stream));
+    }
+    return cudaGetLastError() == cudaSuccess ? (int64_t)lay.total : -1;
+}
+// float offsets of the six tensors inside an arena of `capacity` rows (arena order), for tests and tools
+GS_EXPORT void gstrain_arena_offsets(int64_t capacity, int64_t out[6]) {
+    Arena lay;
+    lay.layout(capacity);
+    const size_t o[6] = {lay.off_quats, lay.off_shN, lay.off_means, lay.off_scales, lay.off_sh0, lay.off_opac};
+    for (int k = 0; k < 6; k++) out[k] = (int64_t)o[k];
+}
 GS_EXPORT void gstrain_init() {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)

@@ -201,6 +201,12 @@ DVS_API int dvs_rast_step_host_wait(dvs_rast_ctx* ctx, int slot);
 
 DVS_API int dvs_rast_get_stats(dvs_rast_ctx* ctx, dvs_stats* out);
 
+/* DEVICE address of the word the last forward set non-zero if its binning arena overflowed (the compositing and backward
+ * kernels of that step then exit early and produce nothing).  With DVS_FLAG_DEFER_CHECK the host learns of it one call
+ * later (DVS_E_OVERFLOW, redo the step); kernels the caller queues behind the step (optimiser, statistics) read this word
+ * and skip their update, so a step that produced no gradients does not move the model. */
+DVS_API const uint32_t* dvs_rast_device_overflow_word(const dvs_rast_ctx* ctx);
+
 /* Per-stage CUDA events (dvs_rast_stage_ms) are recorded only while profiling is on (default: on).  A training loop
  * turns it off: nine event records per step are launch-queue work the step does not need. */
 DVS_API int dvs_rast_set_profiling(dvs_rast_ctx* ctx, int on);

@@ -271,3 +271,73 @@ def test_model_writers_ply_and_splat(tmp_path):
     assert (np.abs(raw[:, 27].astype(int) - a.astype(int)) <= 1).all()
     q = rot / np.linalg.norm(rot, axis=1, keepdims=True)
     assert (np.abs(raw[:, 28:32].astype(int) - np.clip(q * 128 + 128, 0, 255).astype(np.uint8).astype(int)) <= 1).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("visible_only", [False, True])
+def test_fused_adam_matches_torch_optim_adam(visible_only):
+    """F1: the trainer's ONE-launch multi-tensor Adam (six groups, per-group learning rates, the trainer's own arena layout
+    with capacity > N) against torch.optim.Adam in fp32 over 10 steps with fresh gradients each step: <= 1e-6.  With
+    `visible_only` (GaussianTrainConfig::visibleAdam) only rows with radius > 0 move, the others keep their moments; the
+    device skip word (an overflowed step) makes the update a no-op."""
+    import ctypes as C
+
+    import torch
+    libs = _build()
+    lib = C.CDLL(libs["libgstrain"])
+    lib.gstrain_test_adam.restype = C.c_int64
+    lib.gstrain_test_adam.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_int64, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int,
+                                                         C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.gstrain_arena_offsets.argtypes = [C.c_int64, C.c_void_p]
+    N, cap = 5003, 6001   # odd sizes: group tails that are not a multiple of four floats
+    dev = torch.device("cuda", 0)
+    total = lib.gstrain_test_adam(None, None, None, None, N, cap, None, 0.9, 0.999, 1e-15, 0, 0, None, None, None)
+    offs = (C.c_int64 * 6)()
+    lib.gstrain_arena_offsets(cap, offs)
+    widths = [4, 45, 3, 3, 3, 1]                      # quats | shN | means | scales | sh0 | opac
+    lrs = np.array([1e-3, 1.25e-4, 1.6e-4, 5e-3, 2.5e-3, 5e-2], np.float32)
+    gen = torch.Generator(device="cpu"); gen.manual_seed(11)
+    P = torch.randn(total, generator=gen).to(dev)
+    M1, M2 = torch.zeros(total, device=dev), torch.zeros(total, device=dev)
+    radii = (torch.rand(N, generator=gen) > 0.4).to(torch.int32).to(dev)
+    views = [P[o:o + w * N] for o, w in zip(offs, widths)]
+    ref = [v.clone().requires_grad_(True) for v in views]
+    opt = torch.optim.Adam([{"params": [r], "lr": float(lr)} for r, lr in zip(ref, lrs)], betas=(0.9, 0.999), eps=1e-15)
+    before = P.clone()
+    skip = torch.zeros(1, dtype=torch.int32, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for step in range(10):
+        G = torch.randn(total, generator=gen).to(dev) * (10.0 ** float(torch.randint(-4, 2, (1,), generator=gen)))
+        for r, o, w in zip(ref, offs, widths):
+            g = G[o:o + w * N].clone()
+            if visible_only:  # rows the view did not see: zero gradient AND (reference) no decay of the moments -> emulate by masking
+                g = g.view(N, w) * (radii > 0).view(N, 1)
+                g = g.reshape(-1)
+            r.grad = g
+        if not visible_only:
+            opt.step()
+        rc = lib.gstrain_test_adam(P.data_ptr(), G.data_ptr(), M1.data_ptr(), M2.data_ptr(), N, cap, lrs.ctypes.data, 0.9, 0.999, 1e-15,
+                                   step, 1, radii.data_ptr() if visible_only else None, skip.data_ptr(), st)
+        assert rc == total
+    torch.cuda.synchronize()
+    if not visible_only:
+        for v, r, w in zip(views, ref, widths):
+            err = float((v - r.detach()).abs().max() / (r.detach().abs().max() + 1e-30))
+            assert err <= 1e-6, (w, err)
+    else:
+        for v, o, w in zip(views, offs, widths):
+            moved = (v.view(N, w) != before[o:o + w * N].view(N, w)).any(dim=1)
+            assert bool((moved == (radii > 0)).all()), f"group of width {w}: exactly the visible rows move"
+            assert not M1[o:o + w * N].view(N, w)[radii <= 0].any() and not M2[o:o + w * N].view(N, w)[radii <= 0].any()
+    # nothing outside the live rows of the six groups is touched (capacity padding, alignment gaps)
+    mask = torch.ones(total, dtype=torch.bool, device=dev)
+    for o, w in zip(offs, widths):
+        mask[o:o + w * N] = False
+    assert torch.equal(P[mask], before[mask]) and not M1[mask].any()
+    # an overflowed step (device skip word set) must not move anything
+    snap, s1 = P.clone(), M1.clone()
+    skip.fill_(1)
+    lib.gstrain_test_adam(P.data_ptr(), G.data_ptr(), M1.data_ptr(), M2.data_ptr(), N, cap, lrs.ctypes.data, 0.9, 0.999, 1e-15, 10, 1,
+                          None, skip.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert torch.equal(P, snap) and torch.equal(M1, s1)
