@@ -306,6 +306,9 @@ def main():
     ap.add_argument("--workload", default=None, help="override: c2|c3|c5 (parity/bench exploration only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-rows", action="store_true", help="skip the sub-process measurement of the other section-8 rows")
+    ap.add_argument("--no-bind", action="store_true",
+                    help="do not pin the process to the CPUs of its GPU's NUMA node (default: pinned, so that the pinned host "
+                         "buffers of the end-to-end path are node-local; the CPU baseline leg runs with the original affinity)")
     ap.add_argument("--no-tight", action="store_true",
                     help="timed steps keep the whole-rectangle tile lists (default: DVS_FLAG_TIGHT_LISTS — entries whose sub-tile "
                          "mask is empty are not emitted; image and gradients are bit-identical, tests/test_gpu_parity.py)")
@@ -338,6 +341,11 @@ def main():
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch N>1 with torch.distributed.run)"
+    affinity0 = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    bind_note = "not bound (--no-bind)"
+    if not args.no_bind:
+        from divshot_b200.hostbind import bind_to_gpu_numa_node
+        bind_note = bind_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -521,7 +529,7 @@ def main():
                                   "tight: the reference-exact lists minus the entries whose sub-tile mask is empty "
                                   "(DVS_FLAG_TIGHT_LISTS; image and gradients bit-identical, D counts all duplicates)"),
                    "l2": "inputs larger than L2 (params+grads 472 MB + 96 MB records/lists per step); no explicit flush",
-                   "parallelism": f"dp{world} (view-sharded replicas)",
+                   "parallelism": f"dp{world} (view-sharded replicas)", "host_binding": bind_note,
                    "host_sync": "none per step (binning arena validated by deferred check, DVS_FLAG_DEFER_CHECK; "
                                 "single-pass binning into fixed-stride tile bins sized by the warm-up forwards)"},
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": dom_gbs, "peak": peak, "unit": "GB/s",
@@ -549,6 +557,8 @@ def main():
                       if world > 1 else None),
         "clocks": clocks,
     }
+    if affinity0 is not None:
+        os.sched_setaffinity(0, affinity0)  # the CPU legs below use every core the process was given
     if world == 1 and rank == 0 and not args.no_cpu:
         n_s, times, cores, sample = run_cpu_sample(reps=3)
         best = min(times)

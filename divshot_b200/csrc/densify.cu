@@ -58,9 +58,17 @@ __global__ void k_weights(const float* __restrict__ opac, int64_t N, float min_o
         weight[i] = (d && dead_get_zero) ? 0.0 : (double)o;
     }
 }
-__global__ void k_sample(const double* __restrict__ cdf, int64_t N, int64_t M, uint64_t seed, int64_t* __restrict__ src,
-                         int32_t* __restrict__ count) {
+// The sample count is `M`, or — when `M_dev` is given — the count a preceding compaction left on the DEVICE (no host
+// read-back between the kernels): *M_dev if 0 < *M_dev < N, else 0 (nothing dead, or everything dead: nothing to relocate).
+__device__ __forceinline__ int64_t effective_count(int64_t M, const int64_t* M_dev, int64_t N) {
+    if (!M_dev) return M;
+    const int64_t d = *M_dev;
+    return (d > 0 && d < N) ? d : 0;
+}
+__global__ void k_sample(const double* __restrict__ cdf, int64_t N, int64_t M, const int64_t* __restrict__ M_dev, uint64_t seed,
+                         int64_t* __restrict__ src, int32_t* __restrict__ count) {
     const double total = cdf[N - 1];
+    M = effective_count(M, M_dev, N);
     GRID_STRIDE(j, M) {
         int64_t idx = sample_cdf(cdf, N, uniform01(seed, (uint64_t)j) * total);
         while (idx > 0 && cdf[idx] == cdf[idx - 1]) idx--;  // never land on a zero-weight entry (u rounded up to the total)
@@ -82,8 +90,9 @@ __global__ void k_reloc_values(Tensors p, const int32_t* __restrict__ count, int
 }
 // copy j: Gaussian src[j] -> slot (dst_list ? dst_list[j] : dst_base + j), with the relocation rule's opacity / scale
 __global__ void k_copy_relocated(Tensors p, Tensors m1, Tensors m2, const int64_t* __restrict__ src,
-                                 const int64_t* __restrict__ dst_list, int64_t dst_base, int64_t M,
-                                 const float* __restrict__ tmp_opac, const float* __restrict__ tmp_scale) {
+                                 const int64_t* __restrict__ dst_list, int64_t dst_base, int64_t M, const int64_t* __restrict__ M_dev,
+                                 int64_t N, const float* __restrict__ tmp_opac, const float* __restrict__ tmp_scale) {
+    M = effective_count(M, M_dev, N);
     GRID_STRIDE(j, M) {
         const int64_t s = src[j], d = dst_list ? dst_list[j] : dst_base + j;
         copy_row(p, d, s);
@@ -314,14 +323,15 @@ static cudaError_t read_counts(Workspace* ws, int n, cudaStream_t st) {
 }
 
 // sample M sources from [0, N) with probability ~ weight, apply the relocation rule to sources and copies
-static cudaError_t sample_and_copy(Workspace* ws, Tensors p, Tensors m1, Tensors m2, int64_t N, int64_t M,
+// (M_dev != nullptr: the number of samples is on the device, M is only its upper bound — launch geometry)
+static cudaError_t sample_and_copy(Workspace* ws, Tensors p, Tensors m1, Tensors m2, int64_t N, int64_t M, const int64_t* M_dev,
                                    const int64_t* dst_list, int64_t dst_base, float min_opacity, uint64_t seed,
                                    cudaStream_t st) {
     CKC(inclusive_sum(ws, ws->weight, ws->cdf, N, st));
     CKC(cudaMemsetAsync(ws->count, 0, (size_t)N * sizeof(int32_t), st));
-    DVS_LAUNCH(k_sample, M, st, ws->cdf, N, M, seed, ws->list_b, ws->count);
+    DVS_LAUNCH(k_sample, M, st, ws->cdf, N, M, M_dev, seed, ws->list_b, ws->count);
     DVS_LAUNCH(k_reloc_values, N, st, p, ws->count, N, min_opacity, ws->binom, ws->tmp_opac, ws->tmp_scale);
-    DVS_LAUNCH(k_copy_relocated, M, st, p, m1, m2, ws->list_b, dst_list, dst_base, M, ws->tmp_opac, ws->tmp_scale);
+    DVS_LAUNCH(k_copy_relocated, M, st, p, m1, m2, ws->list_b, dst_list, dst_base, M, M_dev, N, ws->tmp_opac, ws->tmp_scale);
     DVS_LAUNCH(k_commit_sources, N, st, p, m1, m2, ws->count, N, ws->tmp_opac, ws->tmp_scale);
     return cudaGetLastError();
 }
@@ -335,19 +345,20 @@ cudaError_t mcmc_refine(Workspace* ws, Tensors p, Tensors m1, Tensors m2, int64_
     // 1. relocate the dead onto the living
     DVS_LAUNCH(k_weights, N, st, p.opac, N, min_opacity, true, ws->weight, ws->flag_a);
     CKC(select_indices(ws, ws->flag_a, N, ws->list_a, 0, st));
-    CKC(read_counts(ws, 1, st));
-    const int64_t n_dead = ws->h_num[0];
-    if (rep) rep->dead = n_dead;
-    if (n_dead > 0 && n_dead < N) {
-        CKC(sample_and_copy(ws, p, m1, m2, N, n_dead, ws->list_a, 0, min_opacity, seed, st));
-        if (rep) rep->relocated = n_dead;
+    // the number of dead Gaussians stays on the device: the sampling / copy kernels read it there (launched for the upper
+    // bound N), so the refinement queues without a host synchronisation.  Only a caller that wants the report pays for one.
+    CKC(sample_and_copy(ws, p, m1, m2, N, N, ws->d_num, ws->list_a, 0, min_opacity, seed, st));
+    if (rep) {
+        CKC(read_counts(ws, 1, st));
+        rep->dead = ws->h_num[0];
+        rep->relocated = (rep->dead > 0 && rep->dead < N) ? rep->dead : 0;
     }
     // 2. grow by 5 %, bounded by capMax and by what the arenas hold
     const int64_t target = std::min<int64_t>(std::min<int64_t>(cap_max, capacity), (int64_t)(1.05 * (double)N));
     const int64_t n_new = std::max<int64_t>(0, target - N);
     if (n_new > 0) {
         DVS_LAUNCH(k_weights, N, st, p.opac, N, min_opacity, false, ws->weight, nullptr);
-        CKC(sample_and_copy(ws, p, m1, m2, N, n_new, nullptr, N, min_opacity, seed ^ 0xA5A5A5A5A5A5A5A5ull, st));
+        CKC(sample_and_copy(ws, p, m1, m2, N, n_new, nullptr, nullptr, N, min_opacity, seed ^ 0xA5A5A5A5A5A5A5A5ull, st));
         *N_io = N + n_new;
         if (rep) rep->added = n_new;
     }
@@ -435,13 +446,13 @@ static void report6_out(const RefineReport& r, long long* o) {
 DVS_DENSIFY_EXPORT int dvs_densify_test_mcmc_refine(float* const* p6, float* const* m1_6, float* const* m2_6, long long* N,
                                        long long capacity, long long cap_max, float min_opacity,
                                        unsigned long long seed, long long* report6, void* stream) {
-    Workspace* ws = workspace_create();
+    // (the workspace persists across calls like the trainer's; report6 == nullptr: no report, no host synchronisation)
+    static Workspace* ws = workspace_create();
     RefineReport rep;
     int64_t n = *N;
     const cudaError_t e = mcmc_refine(ws, tensors6(p6), tensors6(m1_6), tensors6(m2_6), &n, capacity, cap_max,
-                                                   min_opacity, seed, static_cast<cudaStream_t>(stream), &rep);
-    cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
-    workspace_destroy(ws);
+                                                   min_opacity, seed, static_cast<cudaStream_t>(stream), report6 ? &rep : nullptr);
+    if (report6) cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
     *N = n;
     report6_out(rep, report6);
     return (int)e;

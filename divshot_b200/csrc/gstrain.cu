@@ -764,7 +764,7 @@ void GaussianTrainerScene::trainStep() {
             I.last_report = dvs_densify::RefineReport{};
             if (mcmc) {
                 ck(dvs_densify::mcmc_refine(I.dws, I.T(I.params), I.T(I.m1), I.T(I.m2), &I.N, I.capacity, effectiveCapMax(config_),
-                                            config_.min_opacity, seed, I.stream, &I.last_report), "mcmc_refine");
+                                            config_.min_opacity, seed, I.stream, config_.verbose ? &I.last_report : nullptr), "mcmc_refine");  // (the report costs a host sync)
             } else {
                 const dvs_densify::AdcConfig ac{config_.growGrad2d, 0.01f, I.scene_extent, config_.pruneOpacity,
                                                 config_.pruneScale3d, config_.revisedOpacity};
