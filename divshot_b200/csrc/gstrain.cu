@@ -23,6 +23,8 @@
 // (x y z, f_dc_0..2, f_rest_0..44 channel-major, opacity, scale_0..2, rot_0..3; raw parameters) or the 32-byte
 // `.splat` records of tiny_gsplat.cpp:243-291.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
@@ -333,7 +335,112 @@ void make_projection(dvs_camera& c, const float Rt[12], int W, int H, float fx, 
 
 }  // namespace
 
+// ---- view-sharded data parallelism behind the plugin boundary (SURVEY.md §8 e) ---------------------------------------------
+// One process per GPU, each running the UNMODIFIED caller (diverseshot-cli / gstrain_driver) against this plugin; rank, world
+// size and device come from the environment a launcher sets (DVS_RANK / DVS_WORLD_SIZE / DVS_LOCAL_RANK, else the RANK /
+// WORLD_SIZE / LOCAL_RANK of torch.distributed.run).  Every rank holds the whole model, renders ITS view of the step's batch
+// (dp.views_for_rank: view (step * world + rank) mod views) and the per-Gaussian gradients are summed over ranks before the
+// optimiser — so all ranks step identically and the run equals a single-GPU run that accumulates the same batch of views.
+// NCCL is loaded at run time (dlopen libnccl.so.2): a single-GPU run needs no NCCL at all.  The NCCL unique id travels through
+// a file (DVS_NCCL_ID_FILE, default /tmp/dvs_nccl_id.<MASTER_PORT>): rank 0 writes it, the others wait for it.
+struct DpComm {
+    typedef struct ncclComm* comm_t;
+    struct unique_id { char internal[128]; };
+    int rank = 0, world = 1, local = 0;
+    void* lib = nullptr;
+    comm_t comm = nullptr;
+    int (*GetUniqueId)(unique_id*) = nullptr;
+    int (*CommInitRank)(comm_t*, int, unique_id, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*CommDestroy)(comm_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    static constexpr int kFloat32 = 7, kSum = 0;  // ncclFloat32, ncclSum (stable across NCCL 2.x)
+
+    static int env_int(const char* a, const char* b, int dflt) {
+        const char* v = std::getenv(a);
+        if (!v || !*v) v = std::getenv(b);
+        return (v && *v) ? std::atoi(v) : dflt;
+    }
+    void read_env() {
+        world = std::max(1, env_int("DVS_WORLD_SIZE", "WORLD_SIZE", 1));
+        rank = env_int("DVS_RANK", "RANK", 0);
+        local = env_int("DVS_LOCAL_RANK", "LOCAL_RANK", rank);
+        if (rank < 0 || rank >= world) throw std::runtime_error("gstrain: rank outside [0, world size)");
+    }
+    void nccl(int rc, const char* what) const {
+        if (rc != 0) throw std::runtime_error(std::string("gstrain: ") + what + ": " + (GetErrorString ? GetErrorString(rc) : "NCCL error"));
+    }
+    static std::string id_file() {
+        if (const char* f = std::getenv("DVS_NCCL_ID_FILE")) return f;
+        const char* port = std::getenv("MASTER_PORT");
+        return std::string("/tmp/dvs_nccl_id.") + (port ? port : "default");
+    }
+    void init() {  // the CUDA device of this rank is already current
+        if (world <= 1) return;
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+            if (lib) break;
+        }
+        if (!lib) throw std::runtime_error(std::string("gstrain: world size > 1 needs NCCL (dlopen libnccl.so.2 failed: ") + dlerror() + ")");
+        auto sym = [&](const char* n) {
+            void* p = dlsym(lib, n);
+            if (!p) throw std::runtime_error(std::string("gstrain: NCCL symbol missing: ") + n);
+            return p;
+        };
+        GetUniqueId = (int (*)(unique_id*))sym("ncclGetUniqueId");
+        CommInitRank = (int (*)(comm_t*, int, unique_id, int))sym("ncclCommInitRank");
+        AllReduce = (int (*)(const void*, void*, size_t, int, int, comm_t, cudaStream_t))sym("ncclAllReduce");
+        GroupStart = (int (*)())sym("ncclGroupStart");
+        GroupEnd = (int (*)())sym("ncclGroupEnd");
+        CommDestroy = (int (*)(comm_t))sym("ncclCommDestroy");
+        GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+        unique_id id{};
+        const std::string path = id_file();
+        if (rank == 0) {
+            nccl(GetUniqueId(&id), "ncclGetUniqueId");
+            const std::string tmp = path + ".tmp";
+            std::ofstream f(tmp, std::ios::binary | std::ios::trunc);
+            f.write(id.internal, sizeof id.internal);
+            f.close();
+            if (!f.good() || std::rename(tmp.c_str(), path.c_str()) != 0) throw std::runtime_error("gstrain: cannot write " + path);
+        } else {
+            bool got = false;
+            for (int tries = 0; tries < 1200 && !got; tries++) {  // up to 120 s
+                std::ifstream f(path, std::ios::binary);
+                if (f.good()) {
+                    f.read(id.internal, sizeof id.internal);
+                    got = f.gcount() == (std::streamsize)sizeof id.internal;
+                }
+                if (!got) usleep(100000);
+            }
+            if (!got) throw std::runtime_error("gstrain: rank 0 never published the NCCL id at " + path);
+        }
+        nccl(CommInitRank(&comm, world, id, rank), "ncclCommInitRank");
+        if (rank == 0) {  // every rank has joined once ncclCommInitRank returns: the id file is spent
+            std::remove(path.c_str());
+        }
+    }
+    // in-place sum over ranks of several device ranges, one NCCL group (one fused launch)
+    void all_reduce_sum(std::initializer_list<std::pair<float*, size_t>> ranges, cudaStream_t st) const {
+        if (world <= 1) return;
+        nccl(GroupStart(), "ncclGroupStart");
+        for (auto& r : ranges)
+            if (r.second) nccl(AllReduce(r.first, r.first, r.second, kFloat32, kSum, comm, st), "ncclAllReduce");
+        nccl(GroupEnd(), "ncclGroupEnd");
+    }
+    void destroy() {
+        if (comm && CommDestroy) CommDestroy(comm);
+        comm = nullptr;
+        if (lib) dlclose(lib);
+        lib = nullptr;
+    }
+};
+
 struct GaussianTrainerImpl {
+    DpComm dp;                     // view-sharded data parallelism (world size 1: inert)
+    int batch_views = 1;           // views rendered per step on this GPU before the optimiser (DVS_BATCH_VIEWS; gradients accumulate)
     dvs_rast_ctx* ctx = nullptr;
     cudaStream_t stream = nullptr;
     int64_t N = 0;
@@ -358,6 +465,7 @@ struct GaussianTrainerImpl {
     int32_t* d_radii = nullptr;    // [capacity] radii of the last forward
     bool refine_enabled = false;   // the schedule reaches the refinement window (set before upload)
     bool resync_next = false;      // N changed: the next forward re-sizes the binning arena synchronously
+    int load_itr = -1;             // create_splat(config, loadItr): resume from the model file at config.modelPath at this iteration
     dvs_densify::RefineReport last_report;
     // The editor drives trainStep from a worker thread and reads the model from its UI thread (editor.cpp:1559-1574 vs
     // :1603-1620): every public entry that touches the device state takes this lock, so a reader never sees the model
@@ -453,16 +561,25 @@ struct GaussianTrainerImpl {
 
 // -------------------------------------------------------------------------------------------------
 GaussianTrainerScene::GaussianTrainerScene(const GaussianTrainConfig& config, int loadItr) : config_(config) {
-    (void)loadItr;
     impl_ = new GaussianTrainerImpl();
+    impl_->load_itr = loadItr;
     int dev = 0;
+    impl_->dp.read_env();
+    if (const char* b = std::getenv("DVS_BATCH_VIEWS")) impl_->batch_views = std::max(1, std::atoi(b));
     // no CPU fallback: without a CUDA device the constructor throws (the CLI then aborts, gs_train.cpp does not catch)
+    if (impl_->dp.world > 1) {  // one process per GPU: this rank's device
+        int ndev = 0;
+        ck(cudaGetDeviceCount(&ndev), "cudaGetDeviceCount");
+        if (ndev <= 0) throw std::runtime_error("gstrain: no CUDA device");
+        ck(cudaSetDevice(impl_->dp.local % ndev), "cudaSetDevice");
+    }
     ck(cudaGetDevice(&dev), "cudaGetDevice");
     ck(cudaStreamCreateWithFlags(&impl_->stream, cudaStreamNonBlocking), "cudaStreamCreate");
     int rc = dvs_rast_create(dev, &impl_->ctx);
     if (rc != DVS_OK) throw std::runtime_error("gstrain: dvs_rast_create failed (no usable CUDA device)");
     ck(cudaMalloc(&impl_->d_loss, sizeof(float)), "cudaMalloc loss");
     ck(cudaMallocHost(&impl_->h_loss, sizeof(float)), "cudaMallocHost loss");
+    impl_->dp.init();  // world size > 1: joins the NCCL communicator of the run (collective: every rank constructs its scene)
 }
 
 GaussianTrainerScene::~GaussianTrainerScene() {
@@ -476,6 +593,7 @@ GaussianTrainerScene::~GaussianTrainerScene() {
     if (impl_->vp_stream) cudaStreamDestroy(impl_->vp_stream);
     dvs_densify::workspace_destroy(impl_->dws);
     cudaFreeHost(impl_->h_loss);
+    impl_->dp.destroy();
     if (impl_->ctx) dvs_rast_destroy(impl_->ctx);
     if (impl_->stream) cudaStreamDestroy(impl_->stream);
     delete impl_;
@@ -672,6 +790,43 @@ bool GaussianTrainerScene::loadTrainData(const std::string& path) {
         pt.a = 255;
     }
     trainSetup();
+    // `--load_itr K` (main.cpp:40-41 -> create_splat(config, K), gs_train.cpp:107): resume from the model this trainer saved
+    // at config.modelPath (save_splat_model; any format of the F2 readers) and continue the schedule — learning-rate decay,
+    // SH degree, refinement windows — at iteration K.  The checkpoint is the parameters only: the Adam
+    // moments restart from zero.  A missing / unreadable file is an error: silently training from scratch at iteration K
+    // would be worse.
+    if (I.load_itr >= 0) {
+        if (!resumeFromModelFile(config_.modelPath)) {
+            std::fprintf(stderr, "gstrain: --load_itr %d: cannot resume from '%s': %s\n", I.load_itr, config_.modelPath.c_str(),
+                         dvs_model_io_last_error());
+            status_ = TrainingStatus::Loading_Failed;
+            return false;
+        }
+        curIteration = I.load_itr;
+    }
+    return true;
+}
+
+bool GaussianTrainerScene::resumeFromModelFile(const std::string& path) {
+    std::lock_guard<std::recursive_mutex> lock(impl_->mu);
+    auto& I = *impl_;
+    if (path.empty()) return false;
+    const int fmt = dvs_model_format_from_path(path.c_str());
+    const int64_t n = dvs_model_read(path.c_str(), fmt ? fmt : DVS_FMT_PLY, nullptr, 0, nullptr);
+    if (n <= 0) return false;
+    std::vector<float> rows((size_t)n * DVS_IO_ROW_FLOATS);
+    if (dvs_model_read(path.c_str(), fmt ? fmt : DVS_FMT_PLY, rows.data(), n, nullptr) != n) return false;
+    // reader row = RichPoint: pos[3] | f_dc[3] | f_rest[45] channel-major (f_rest[c*15 + j] = shN[j][c]) | opacity | scale[3] | rot[4]
+    std::vector<float> pos(3 * (size_t)n), sh0(3 * (size_t)n), shn((size_t)3 * KR * n), op((size_t)n), sc(3 * (size_t)n), rot(4 * (size_t)n);
+    for (int64_t i = 0; i < n; i++) {
+        const float* r = rows.data() + (size_t)i * DVS_IO_ROW_FLOATS;
+        for (int k = 0; k < 3; k++) { pos[3 * i + k] = r[k]; sh0[3 * i + k] = r[3 + k]; sc[3 * i + k] = r[52 + k]; }
+        for (int j = 0; j < KR; j++)
+            for (int c = 0; c < 3; c++) shn[(size_t)3 * KR * i + 3 * j + c] = r[6 + c * KR + j];
+        op[i] = r[51];
+        for (int k = 0; k < 4; k++) rot[4 * i + k] = r[55 + k];
+    }
+    updateTensorFromHost(pos.data(), rot.data(), sc.data(), op.data(), sh0.data(), shn.data(), n);
     return true;
 }
 
@@ -697,10 +852,10 @@ void GaussianTrainerScene::trainStep() {
         I.last_step = now; I.have_last_step = true;
     }
     const int step = curIteration;
-    View& vw = I.views[(size_t)step % I.views.size()];
-    dvs_camera cam = vw.cam;
-    cam.sh_degree = std::min(I.max_degree, step / 1000);  // progressive SH degree (every 1000 iterations)
-    const size_t n = (size_t)3 * cam.width * cam.height;
+    // The step's batch: `batch_views` views on this GPU (gradients accumulate), times the ranks of a data-parallel run; rank r
+    // takes views (step * world + r) * batch + j  (mod the view count) — dp.views_for_rank of the Python harness.
+    const int B = I.batch_views, world = I.dp.world;
+    const bool batched = B > 1 || world > 1;
     dvs_params P = I.P();
     dvs_grads G = I.G();
     // Steps run without any host synchronisation (DVS_FLAG_DEFER_CHECK; honoured once a synchronous forward has
@@ -709,51 +864,71 @@ void GaussianTrainerScene::trainStep() {
     // fused Adam update, the ADC statistics — read the rasterizer's device overflow word and do nothing (a zero gradient
     // would still move every parameter through the decaying first moment).  The MCMC regulariser only adds to the (unused)
     // gradients and the exploration noise is a zero-mean perturbation applied every step anyway.  The step is then redone.
+    // (A batched / data-parallel step always applies its update: the overflowed view contributes zero gradients to the sum
+    // and every rank must step identically.)
     // refinement window (densify.cu): warmupLength < step < refineStopIter; MCMC is strategy 1, ADC 0 and 2
     const bool refining = I.dws && step > config_.warmupLength && step < config_.refineStopIter;
     const bool mcmc = config_.densifyStrategy == 1;
-    if (!I.resync_next) cam.flags |= DVS_FLAG_DEFER_CHECK;
+    uint32_t cam_flags = 0u;
+    if (!I.resync_next) cam_flags |= DVS_FLAG_DEFER_CHECK;
     I.resync_next = false;
-    if (config_.mipAntiliased) cam.flags |= DVS_FLAG_ANTIALIAS;  // --mipAntiliased (main.cpp, docs/userGuide.md:58)
+    if (config_.mipAntiliased) cam_flags |= DVS_FLAG_ANTIALIAS;  // --mipAntiliased (main.cpp, docs/userGuide.md:58)
     uint32_t bwd_flags = 0u;
-    if (refining && !mcmc) {  // ADC feeds on the screen-space gradient of every step
+    if (refining && !mcmc) {  // ADC feeds on the screen-space gradient of every view
         G.mean2D = I.d_mean2D;
         if (config_.useAbsGrad) { G.mean2D_abs = I.d_mean2D_abs; bwd_flags |= DVS_FLAG_ABSGRAD; }
     }
-    for (int attempt = 0;; attempt++) {
-        const bool sparse_adam = config_.visibleAdam && I.d_radii;
-        int rc = dvs_rast_forward(I.ctx, &cam, I.N, &P, I.d_render, ((refining && !mcmc) || sparse_adam) ? I.d_radii : nullptr, I.stream);
-        if (rc == DVS_E_OVERFLOW && attempt < 2) continue;
-        ckr(rc, I.ctx, "forward");
-        ck(cudaMemsetAsync(I.d_loss, 0, sizeof(float), I.stream), "memset loss");
-        const size_t npix = (size_t)cam.width * cam.height;
-        if (vw.d_mask) mask_blend_kernel<<<1184, 256, 0, I.stream>>>(I.d_render, vw.d_target, vw.d_mask, npix);
-        launch_photometric_loss(I.d_render, vw.d_target, I.d_dLdpix, I.d_loss, I.d_scratch, cam.width, cam.height,
-                                std::min(1.f, std::max(0.f, config_.ssimWeight)), I.stream);
-        if (vw.d_mask) mask_grad_kernel<<<1184, 256, 0, I.stream>>>(I.d_dLdpix, vw.d_mask, npix);
-        rc = dvs_rast_backward(I.ctx, &P, I.d_dLdpix, &G, bwd_flags, I.stream);
-        if (rc == DVS_E_OVERFLOW && attempt < 2) continue;
-        ckr(rc, I.ctx, "backward");
-        break;
-    }
-    (void)n;
-    if (refining) {
-        if (mcmc)  // L1 regularisers of the MCMC strategy: 0.01 mean(opacity) + 0.01 mean(scale)
-            ck(dvs_densify::mcmc_regularise(I.T(I.params), I.T(I.grads), I.N, 0.01f, 0.01f, I.stream), "mcmc_regularise");
-        else
+    // visibleAdam steps only the rows the step's view saw; with several views per step there is no single view: dense Adam
+    const bool sparse_adam = config_.visibleAdam && I.d_radii && !batched;
+    const uint32_t* skip_word = batched ? nullptr : dvs_rast_device_overflow_word(I.ctx);
+    ck(cudaMemsetAsync(I.d_loss, 0, sizeof(float), I.stream), "memset loss");
+    for (int j = 0; j < B; j++) {
+        const size_t vi = (((size_t)step * (size_t)world + (size_t)I.dp.rank) * (size_t)B + (size_t)j) % I.views.size();
+        View& vw = I.views[vi];
+        dvs_camera cam = vw.cam;
+        cam.flags |= cam_flags;
+        cam.sh_degree = std::min(I.max_degree, step / 1000);  // progressive SH degree (every 1000 iterations)
+        const uint32_t flags_j = bwd_flags | (j > 0 ? DVS_FLAG_ACCUMULATE : 0u);
+        if (j > 0 && refining && !mcmc) {  // the screen-space statistics are per view: start each view's from zero
+            ck(cudaMemsetAsync(I.d_mean2D, 0, 2 * (size_t)I.N * sizeof(float), I.stream), "memset mean2D");
+            if (config_.useAbsGrad) ck(cudaMemsetAsync(I.d_mean2D_abs, 0, 2 * (size_t)I.N * sizeof(float), I.stream), "memset mean2D_abs");
+        }
+        for (int attempt = 0;; attempt++) {
+            int rc = dvs_rast_forward(I.ctx, &cam, I.N, &P, I.d_render, ((refining && !mcmc) || sparse_adam) ? I.d_radii : nullptr, I.stream);
+            if (rc == DVS_E_OVERFLOW && attempt < 2) { cam.flags &= ~DVS_FLAG_DEFER_CHECK; continue; }
+            ckr(rc, I.ctx, "forward");
+            const size_t npix = (size_t)cam.width * cam.height;
+            if (vw.d_mask) mask_blend_kernel<<<1184, 256, 0, I.stream>>>(I.d_render, vw.d_target, vw.d_mask, npix);
+            launch_photometric_loss(I.d_render, vw.d_target, I.d_dLdpix, I.d_loss, I.d_scratch, cam.width, cam.height,
+                                    std::min(1.f, std::max(0.f, config_.ssimWeight)), I.stream);
+            if (vw.d_mask) mask_grad_kernel<<<1184, 256, 0, I.stream>>>(I.d_dLdpix, vw.d_mask, npix);
+            rc = dvs_rast_backward(I.ctx, &P, I.d_dLdpix, &G, flags_j, I.stream);
+            if (rc == DVS_E_OVERFLOW && attempt < 2) { cam.flags &= ~DVS_FLAG_DEFER_CHECK; continue; }
+            ckr(rc, I.ctx, "backward");
+            break;
+        }
+        if (refining && !mcmc)
             ck(dvs_densify::adc_accumulate(I.d_mean2D, config_.useAbsGrad ? I.d_mean2D_abs : nullptr, I.d_radii, I.d_accum,
-                                           I.d_denom, I.N, I.stream, dvs_rast_device_overflow_word(I.ctx)), "adc_accumulate");
+                                           I.d_denom, I.N, I.stream, skip_word), "adc_accumulate");
     }
+    // data parallel: ONE exchange step — the sum over ranks of the six live gradient ranges (one NCCL group = one fused launch)
+    if (world > 1) {
+        const size_t n = (size_t)I.N;
+        I.dp.all_reduce_sum({{I.grads.quats(), 4 * n}, {I.grads.shN(), (size_t)3 * KR * n}, {I.grads.means(), 3 * n},
+                             {I.grads.scales(), 3 * n}, {I.grads.sh0(), 3 * n}, {I.grads.opac(), n}}, I.stream);
+    }
+    if (refining && mcmc)  // L1 regularisers of the MCMC strategy: 0.01 mean(opacity) + 0.01 mean(scale), once per step
+        ck(dvs_densify::mcmc_regularise(I.T(I.params), I.T(I.grads), I.N, 0.01f, 0.01f, I.stream), "mcmc_regularise");
     // Adam, per-group learning rates (GaussianTrainConfig); position lr decays exponentially init -> final
     const float t = std::min(1.f, (float)step / (float)std::max(1, config_.numIters));
     const float lr_pos = std::exp((1.f - t) * std::log(config_.poslrInit) + t * std::log(config_.poslrFinal)) * I.scene_extent;
     const float b1 = 0.9f, b2 = 0.999f, eps = 1e-15f;
     const float c1 = 1.f / (1.f - std::pow(b1, (float)(step + 1))), c2 = 1.f / (1.f - std::pow(b2, (float)(step + 1)));
-    const bool visible_only = config_.visibleAdam && I.d_radii;
+    const bool visible_only = sparse_adam;
     {   // one launch for all six groups (per-group learning rates)
         const float lrs[6] = {config_.rotationlr, config_.featurelr / 20.f, lr_pos, config_.scalinglr, config_.featurelr, config_.opacitylr};
-        launch_adam_fused(I.params, I.grads.flat, I.m1.flat, I.m2.flat, I.N, lrs, visible_only ? I.d_radii : nullptr,
-                          dvs_rast_device_overflow_word(I.ctx), b1, b2, eps, c1, c2, I.stream);
+        launch_adam_fused(I.params, I.grads.flat, I.m1.flat, I.m2.flat, I.N, lrs, visible_only ? I.d_radii : nullptr, skip_word, b1, b2,
+                          eps, c1, c2, I.stream);
     }
     if (refining) {
         const uint64_t seed = 0x5DEECE66Dull * (uint64_t)(step + 1);
@@ -766,6 +941,8 @@ void GaussianTrainerScene::trainStep() {
                 ck(dvs_densify::mcmc_refine(I.dws, I.T(I.params), I.T(I.m1), I.T(I.m2), &I.N, I.capacity, effectiveCapMax(config_),
                                             config_.min_opacity, seed, I.stream, config_.verbose ? &I.last_report : nullptr), "mcmc_refine");  // (the report costs a host sync)
             } else {
+                if (world > 1)  // every rank accumulated the statistics of ITS views: refine on their sum, identically everywhere
+                    I.dp.all_reduce_sum({{I.d_accum, (size_t)I.N}, {I.d_denom, (size_t)I.N}}, I.stream);
                 const dvs_densify::AdcConfig ac{config_.growGrad2d, 0.01f, I.scene_extent, config_.pruneOpacity,
                                                 config_.pruneScale3d, config_.revisedOpacity};
                 ck(dvs_densify::adc_refine(I.dws, I.T(I.params), I.T(I.m1), I.T(I.m2), I.d_accum, I.d_denom, &I.N,
@@ -781,10 +958,11 @@ void GaussianTrainerScene::trainStep() {
                              (long long)I.last_report.cloned, (long long)I.last_report.pruned);
         }
     }
-    ck(cudaMemcpyAsync(I.h_loss, I.d_loss, sizeof(float), cudaMemcpyDeviceToHost, I.stream), "loss D2H");
-    if (step % 100 == 0 || config_.verbose) {
+    if (step % 100 == 0 || config_.verbose) {  // the reported loss: mean over the step's views (all ranks')
+        if (world > 1) I.dp.all_reduce_sum({{I.d_loss, 1}}, I.stream);
+        ck(cudaMemcpyAsync(I.h_loss, I.d_loss, sizeof(float), cudaMemcpyDeviceToHost, I.stream), "loss D2H");
         ck(cudaStreamSynchronize(I.stream), "sync");
-        loss_ = *I.h_loss;
+        loss_ = *I.h_loss / (float)(B * world);
     }
     ck(cudaGetLastError(), "train_step kernels");
     status_ = TrainingStatus::Training;

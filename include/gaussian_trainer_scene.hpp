@@ -178,6 +178,7 @@ public:
     void getCameraPosXYZ(int i, float p[3]) const;               // camera centre in world space
 
     // ---- the rest of the surface the editor calls (SURVEY.md §8-B "methods used by the editor")
+    bool resumeFromModelFile(const std::string& path);  // what create_splat(config, loadItr >= 0) does after load_train_data
     void resetGaussian();                    // back to the initial parameters, optimizer state and iteration 0 (inspector_panel.cpp:837,1017)
     void setDensifyStrategy(int strategy);   // 0 ADC, 1 MCMC, 2 ADC+ (inspector_panel.cpp:789); statistics restart
     float getProgressOnCurrentPhase() const;               // 0..1 (scene_view_panel.cpp:1022)

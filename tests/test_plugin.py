@@ -341,3 +341,32 @@ def test_fused_adam_matches_torch_optim_adam(visible_only):
                           None, skip.data_ptr(), st)
     torch.cuda.synchronize()
     assert torch.equal(P, snap) and torch.equal(M1, s1)
+
+
+@pytest.mark.gpu
+def test_load_itr_resumes_from_the_saved_model(tmp_path):
+    """`--load_itr K` -> create_splat(config, K) (main.cpp:40-41, gs_train.cpp:107): the plugin reads the model it saved at
+    config.modelPath with the F2 readers and continues the schedule at iteration K."""
+    libs = _build()
+    env = {**os.environ, "LD_LIBRARY_PATH": LIB}
+    data = "synthetic:N=8000,W=192,H=128,views=4,deg=1"
+    out = str(tmp_path / "resume.ply")
+    r = subprocess.run([libs["gstrain_driver"], data, "60", out, "lossCheck=0"], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and "steps 60" in r.stdout, r.stdout + r.stderr
+    saved = open(out, "rb").read()
+    # resume at 60 with nothing left to do: get_cur_step says 60, and saving again writes the very same model
+    r = subprocess.run([libs["gstrain_driver"], data, "60", out, "lossCheck=0", "loadItr=60"], capture_output=True, text=True, env=env,
+                       timeout=300)
+    assert r.returncode == 0 and "steps 60" in r.stdout and "from step 60" in r.stdout, r.stdout + r.stderr
+    assert open(out, "rb").read() == saved, "a resumed model must round-trip bit for bit through the PLY writer / reader"
+    # resume and train on: 20 more steps, starting from iteration 60
+    r = subprocess.run([libs["gstrain_driver"], data, "80", out, "lossCheck=0", "loadItr=60"], capture_output=True, text=True, env=env,
+                       timeout=300)
+    assert r.returncode == 0 and "steps 80" in r.stdout and "from step 60" in r.stdout, r.stdout + r.stderr
+    n, props, rows = _read_ply(out)
+    n0, _, rows0 = _read_ply(str(tmp_path / "resume.ply"))
+    assert n == 8000 and np.isfinite(rows).all()
+    # a missing checkpoint is an error, not a silent start from scratch
+    r = subprocess.run([libs["gstrain_driver"], data, "80", str(tmp_path / "nothing_here.ply"), "lossCheck=0", "loadItr=60"],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode != 0 and "cannot resume" in (r.stdout + r.stderr)

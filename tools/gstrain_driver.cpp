@@ -4,9 +4,14 @@
 // reference sources (and therefore the real CLI build) may be absent.  Prints the loss trajectory.
 // Optional trailing key=value arguments set schedule fields the CLI takes as flags (main.cpp:19-70):
 // warmup= refineEvery= refineStop= resetAlphaEvery= capMax= strategy= (densifyStrategy: 0 ADC, 1 MCMC, 2 ADC+)
-// visibleAdam= revisedOpacity= (0 / 1).
+// visibleAdam= revisedOpacity= (0 / 1); loadItr= (create_splat's second argument: resume from the model at <out> at that
+// iteration, main.cpp:40-41); lossCheck=0 (exit 0 even if the loss did not fall by 20 %: short resume / timing runs).
+// Data parallel: start one process per GPU with RANK / WORLD_SIZE / LOCAL_RANK (or DVS_*) set, e.g. under
+// `python -m torch.distributed.run --no-python`; every rank runs this same loop, rank 0's output file is the model.
+// Prints the loss trajectory and the training rate (iterations/s over the loop, wall clock).
 #include <dlfcn.h>
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -33,6 +38,7 @@ int main(int argc, char** argv) {
     init();
     GaussianTrainConfig cfg;
     cfg.sourcePath = data; cfg.modelPath = out; cfg.numIters = iters; cfg.verbose = true;
+    int load_itr = -1, loss_check = 1;
     for (int a = 4; a < argc; a++) {
         const std::string kv = argv[a];
         const size_t eq = kv.find('=');
@@ -47,11 +53,17 @@ int main(int argc, char** argv) {
         else if (k == "strategy") cfg.densifyStrategy = v;
         else if (k == "visibleAdam") cfg.visibleAdam = v != 0;
         else if (k == "revisedOpacity") cfg.revisedOpacity = v != 0;
+        else if (k == "loadItr") load_itr = v;
+        else if (k == "lossCheck") loss_check = v;
+        else if (k == "verbose") cfg.verbose = v != 0;
+        else if (k == "numIters") cfg.numIters = v;  // the schedule's length when it differs from the steps run here
         else { std::fprintf(stderr, "unknown option %s\n", k.c_str()); return 6; }
     }
-    auto* scene = (GaussianTrainerScene*)create(cfg, -1);
+    auto* scene = (GaussianTrainerScene*)create(cfg, load_itr);
     if (!load(scene, data)) { std::fprintf(stderr, "load_train_data failed\n"); return 4; }
     float first = -1.f, last = -1.f;
+    const int start_step = cur(scene);
+    const auto t0 = std::chrono::steady_clock::now();
     while (true) {
         const int i = cur(scene);
         if (i >= iters) break;
@@ -60,10 +72,13 @@ int main(int argc, char** argv) {
         if (i == 0) first = last;
         if (i % 50 == 0) std::printf("iter %d loss %.6f\n", i, last);
     }
-    save(scene);
-    std::printf("steps %d first_loss %.6f last_loss %.6f\n", cur(scene), first, last);
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    const char* rk = std::getenv("DVS_RANK") ? std::getenv("DVS_RANK") : std::getenv("RANK");
+    if (!rk || std::atoi(rk) == 0) save(scene);  // data parallel: every rank holds the same model, rank 0 writes it
+    std::printf("steps %d first_loss %.6f last_loss %.6f its_per_s %.1f (from step %d)\n", cur(scene), first, last,
+                secs > 0 ? (cur(scene) - start_step) / secs : 0.0, start_step);
     del(scene);
     destroy();
     dlclose(h);
-    return last < 0.8f * first ? 0 : 5;
+    return (!loss_check || last < 0.8f * first) ? 0 : 5;
 }
