@@ -134,7 +134,11 @@ __global__ void __launch_bounds__(FX_THREADS, 1)
 fused_exchange_kernel(const dvs_coll_fused a) {
     extern __shared__ __align__(16) float s_rows[];  // FX_THREADS rows of dL/dshN
     __shared__ uint32_t s_fail;
+    __shared__ long long s_tile;
     if (threadIdx.x == 0) s_fail = 0u;
+    // the tile counter of step 3b (second local word): reset by CTA 0 before it arrives at the first barrier, which every
+    // other CTA passes only after CTA 0 has arrived
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.grid_counter[1] = 0u;
     const uint32_t seq0 = (uint32_t)(a.launch_index * 2ull);
     const size_t gtid = (size_t)blockIdx.x * FX_THREADS + threadIdx.x, gsize = (size_t)gridDim.x * FX_THREADS;
 
@@ -183,15 +187,21 @@ fused_exchange_kernel(const dvs_coll_fused a) {
             }
             for (; i < hi; i += rsize) mm_st(mc + i, mm_ld_reduce(mc + i));
         }
-    } else if (a.sh_rest_alloc > 0) {
-        // ---- 3b. dL/dshN of all N Gaussians from the gathered slices (local replica), into the local arena
+    }
+    if (a.sh_rest_alloc > 0) {
+        // ---- 3b. dL/dshN of all N Gaussians from the gathered slices (local replica), into the local arena.  Tiles of
+        // FX_THREADS rows are handed out by an atomic counter: the CTAs that did not reduce start at once, the others join as
+        // soon as their share of 3a is issued — the NVLink-bound and the HBM-bound halves overlap without a tuned split.
         float* out = a.arena_local + a.off_shN;
         const dvs_shx::ExchangeArgs x{a.means, a.campos, a.gather_local, (long long)a.N, a.world, a.sh_degree,
                                       3 * a.sh_rest_alloc, out, (reinterpret_cast<uintptr_t>(out) & 15u) == 0 ? 1 : 0};
-        const int64_t n_tiles = (a.N + FX_THREADS - 1) / FX_THREADS;
-        const int workers = (int)gridDim.x - a.reduce_ctas;
-        for (int64_t tile = (int64_t)blockIdx.x - a.reduce_ctas; tile < n_tiles; tile += workers) {
-            const int64_t base = tile * FX_THREADS;
+        const long long n_tiles = (a.N + FX_THREADS - 1) / FX_THREADS;
+        for (;;) {
+            if (threadIdx.x == 0) s_tile = (long long)atomicAdd(a.grid_counter + 1, 1u);
+            __syncthreads();
+            const long long tile = s_tile;
+            if (tile >= n_tiles) break;
+            const long long base = tile * FX_THREADS;
             const int cnt = (int)(a.N - base < FX_THREADS ? a.N - base : FX_THREADS);
             dvs_shx::exchange_compute(x, s_rows, threadIdx.x, base, cnt);
             __syncthreads();
@@ -240,8 +250,8 @@ extern "C" DVS_API int dvs_coll_exchange_fused(const dvs_coll_fused* args, void*
     const int grid = fused_grid(a.ctas);
     if (grid < 2) return DVS_E_CUDA;
     a.ctas = grid;
-    if (a.reduce_ctas <= 0) a.reduce_ctas = grid / 2;
-    if (a.reduce_ctas >= grid) a.reduce_ctas = grid - 1;   // at least one CTA forms dL/dshN
+    if (a.reduce_ctas <= 0) a.reduce_ctas = grid / 3;      // enough requests in flight for the switch; they join step 3b afterwards
+    if (a.reduce_ctas > grid) a.reduce_ctas = grid;
     if (a.sh_rest_alloc == 0) a.reduce_ctas = grid;        // nothing to form: everybody reduces
     const size_t smem = (size_t)FX_THREADS * FX_ROW_WORDS * sizeof(float);
     void* kargs[] = {&a};

@@ -114,7 +114,14 @@ __device__ __forceinline__ void warp_emit(int gx, int id, int minx, int miny, in
             key[u] = 0ull;
             if (ok[u]) {
                 const int k = j - (s_incl - s_area);
-                const int ty = s_miny + k / s_w, tx = s_minx + k % s_w;
+                // row / column of item k inside the rect (k / w, k % w) without the ~20-instruction integer division:
+                // float reciprocal estimate (k + 0.5 keeps the quotient away from integers by >= 0.5 / w, far above the
+                // rounding error for k < 2^24), then an exact integer fix-up so the result never depends on rounding
+                int q = __float2int_rz(((float)k + 0.5f) * __frcp_rn((float)s_w));
+                int r = k - q * s_w;
+                if (r < 0) { q -= 1; r += s_w; }
+                if (r >= s_w) { q += 1; r -= s_w; }
+                const int ty = s_miny + q, tx = s_minx + r;
                 tile[u] = (uint32_t)(ty * gx + tx);
                 // the mask computation overlaps the atomic's round trip — unless the lists are TIGHT (DVS_FLAG_TIGHT_LISTS,
                 // single-pass mode only): an entry whose sub-tile mask is empty (no pixel of the tile reaches

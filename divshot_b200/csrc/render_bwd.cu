@@ -55,8 +55,7 @@ struct RbSmem {
 
 // Slot metadata captured by lane `slot` during phase 1 (lanes 16..31 hold nothing).
 struct RbSlot {
-    uint32_t gk;     // position of the entry in the sorted list (plist index)
-    float mx, my;    // mean2D
+    uint32_t gk;     // position of the entry in the sorted list (plist index); the mean is re-read from the record in phase 2
 };
 
 template <bool ABSGRAD>
@@ -70,14 +69,36 @@ __device__ __forceinline__ void rb_phase2(uint32_t wbase, int nbuf, int lane, fl
     const uint32_t gk = __shfl_sync(0xffffffffu, mine.gk, k);
     uint32_t eword = 0;
     if (k < nbuf) eword = __ldg(plist + gk);
-    const float mx = __shfl_sync(0xffffffffu, mine.mx, k), my = __shfl_sync(0xffffffffu, mine.my, k);
-    const float X = mx - px0f;                     // dx of pixel column 0 of the sub-rectangle
-    const float Y = my - (py0f + (float)(2 * h));  // dy of the first of my two pixel rows
+    // the slot's mean: the first 8 bytes of its record (an L2 hit: the record was staged for this tile moments ago); two
+    // dependent loads per slot and FLUSH instead of two register moves per VISIT, issued before the colour pass hides them
+    const float2 mxy = __ldg(reinterpret_cast<const float2*>(rec + 3 * (size_t)(eword >> 8)));
     const uint32_t srow = wbase + RbSmem::S + (k * RB_SROW + 16 * h) * 4;
-    const f32x2 Xp = pk2(X, X - 1.0f), m2 = pk2(-2.0f, -2.0f), m1 = pk2(-1.0f, -1.0f);
     // My 16 pixels are 8 horizontally adjacent PAIRS (2 rows x 4 pairs); every quantity is carried as a packed
     // fp32x2 {even pixel, odd pixel}: 10 FFMA2/FMUL2/FADD2 per pair instead of 24 scalar operations.
-    // Pass A: the six geometric moments of s.
+    // Pass B first (it needs nothing of the slot's record): colour sums  sum_pixels w * dL/dpix[ch].
+    float c0, c1, c2;
+    {
+        f32x2 a0 = 0ull, a1 = 0ull, a2 = 0ull;
+        const uint32_t wrow = srow + (RbSmem::Wt - RbSmem::S);
+        const uint32_t pa = wbase + RbSmem::dpA + 8 * h * 16, pb = wbase + RbSmem::dpB + 8 * h * 8;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const f32x2 w = lds_p2(wrow + 8 * q);
+            f32x2 rr, gg;
+            lds_p4(pa + 16 * q, rr, gg);
+            const f32x2 bb = lds_p2(pb + 8 * q);
+            a0 = fma2(w, rr, a0);
+            a1 = fma2(w, gg, a1);
+            a2 = fma2(w, bb, a2);
+        }
+        c0 = sum2(a0); c1 = sum2(a1); c2 = sum2(a2);
+    }
+    c0 += __shfl_xor_sync(0xffffffffu, c0, 16); c1 += __shfl_xor_sync(0xffffffffu, c1, 16);
+    c2 += __shfl_xor_sync(0xffffffffu, c2, 16);
+    // Pass A: the six geometric moments of s about the slot's mean.
+    const float X = mxy.x - px0f;                     // dx of pixel column 0 of the sub-rectangle
+    const float Y = mxy.y - (py0f + (float)(2 * h));  // dy of the first of my two pixel rows
+    const f32x2 Xp = pk2(X, X - 1.0f), m2 = pk2(-2.0f, -2.0f), m1 = pk2(-1.0f, -1.0f);
     f32x2 aS0 = 0ull, aSx = 0ull, aSy = 0ull, aSxx = 0ull, aSxy = 0ull, aSyy = 0ull;
     {
         f32x2 dyp = pk2(Y, Y);
@@ -103,26 +124,6 @@ __device__ __forceinline__ void rb_phase2(uint32_t wbase, int nbuf, int lane, fl
     S0 += __shfl_xor_sync(0xffffffffu, S0, 16); Sx += __shfl_xor_sync(0xffffffffu, Sx, 16);
     Sy += __shfl_xor_sync(0xffffffffu, Sy, 16); Sxx += __shfl_xor_sync(0xffffffffu, Sxx, 16);
     Sxy += __shfl_xor_sync(0xffffffffu, Sxy, 16); Syy += __shfl_xor_sync(0xffffffffu, Syy, 16);
-    // Pass B: colour sums  sum_pixels w * dL/dpix[ch].
-    float c0, c1, c2;
-    {
-        f32x2 a0 = 0ull, a1 = 0ull, a2 = 0ull;
-        const uint32_t wrow = srow + (RbSmem::Wt - RbSmem::S);
-        const uint32_t pa = wbase + RbSmem::dpA + 8 * h * 16, pb = wbase + RbSmem::dpB + 8 * h * 8;
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            const f32x2 w = lds_p2(wrow + 8 * q);
-            f32x2 rr, gg;
-            lds_p4(pa + 16 * q, rr, gg);
-            const f32x2 bb = lds_p2(pb + 8 * q);
-            a0 = fma2(w, rr, a0);
-            a1 = fma2(w, gg, a1);
-            a2 = fma2(w, bb, a2);
-        }
-        c0 = sum2(a0); c1 = sum2(a1); c2 = sum2(a2);
-    }
-    c0 += __shfl_xor_sync(0xffffffffu, c0, 16); c1 += __shfl_xor_sync(0xffffffffu, c1, 16);
-    c2 += __shfl_xor_sync(0xffffffffu, c2, 16);
     float ax = 0.f, ay = 0.f;
     if (ABSGRAD) {  // Pass C: sum_pixels |dL/dmean2D contribution| (densification statistic), natural-units conic
         // natural-units conic from the folded one in the record: A = -2 ln2 A2, B = -ln2 B2, C = -2 ln2 C2
@@ -221,7 +222,7 @@ render_bwd_kernel(Cam cam, const uint32_t* __restrict__ tile_order, const uint32
     constexpr uint32_t ROWB = RB_SROW * 4;
     uint32_t rowoff = 0;
     const uint32_t lane_row = (uint32_t)lane * ROWB;  // rowoff == lane_row <=> the slot being filled is `lane`
-    RbSlot mine = {0u, 0.f, 0.f};
+    RbSlot mine = {0u};
     const int glast = (int)(r0 + last);  // entry at list position g is in front of my last contributor iff g < glast
 
     // staging: two buffers of RB_ROUND records + entry words; the NEXT round (the walk goes back to front) is copied in
@@ -283,41 +284,48 @@ render_bwd_kernel(Cam cam, const uint32_t* __restrict__ tile_order, const uint32
                 const float t = fmaf(q1.x, dy, adx);
                 const float pw = fmaf(cdy, dy, t * dx);
                 const float ee = pw + q1.y;
-                // everything below is computed by every lane and committed under pa = the pair was blended by the forward
-                // (in front of my last contributor, power <= 0, alpha >= 1/255):
+                // pa = the pair was blended by the forward: in front of my last contributor, power <= 0, alpha >= 1/255.
+                // The pair's raw alpha is SELECTED to 0 otherwise, which turns every update below into an exact no-op for it
+                // (accdp + 0 * dd = accdp, s = w = 0) and T is stepped by a predicated multiply — one select and one predicated
+                // instruction instead of four predicated commits:
                 //   T <- T / (1 - alpha);  s = dL/dpower = 2^ee dL/dalpha (the 0.99 clamp is straight-through);  w = alpha T
                 //   dL/dalpha = (c . dp - accdp) T - T_final (bg . dp) / (1 - alpha);  accdp <- accdp + alpha (c . dp - accdp)
-                const float a_raw = ex2_approx(ee);
-                const float alpha = fminf(0.99f, a_raw);
-                const float rinv = rcp_approx(1.0f - alpha);
-                const float Tn = T * rinv;
-                const float cdp = fmaf(cb, dp2, fmaf(q1.w, dp1, q1.z * dp0));
-                const float dd = cdp - accdp;
-                const float dLa = fmaf(dd, Tn, nTf_bg * rinv);
-                float s = 0.f, wgt = 0.f;
-                asm volatile(
-                    "{\n\t"
+                float a_raw = ex2_approx(ee), alpha, rinv;
+                asm("{\n\t"
                     ".reg .pred pa;\n\t"
+                    ".reg .f32 om;\n\t"
                     "setp.le.f32 pa, %4, 0f00000000;\n\t"
                     "setp.ge.and.f32 pa, %5, 0fC0FFD1BE, pa;\n\t"
                     "setp.lt.and.s32 pa, %6, %7, pa;\n\t"
-                    "@pa mov.f32 %0, %8;\n\t"
-                    "@pa fma.rn.f32 %1, %9, %10, %1;\n\t"
-                    "@pa mul.rn.f32 %2, %11, %12;\n\t"
-                    "@pa mul.rn.f32 %3, %9, %8;\n\t"
+                    "selp.f32 %0, %0, 0f00000000, pa;\n\t"
+                    "min.f32 %1, %0, 0f3F7D70A4;\n\t"
+                    "sub.rn.f32 om, 0f3F800000, %1;\n\t"
+                    "rcp.approx.ftz.f32 %2, om;\n\t"
+                    "@pa mul.rn.f32 %3, %3, %2;\n\t"
                     "}"
-                    : "+f"(T), "+f"(accdp), "+f"(s), "+f"(wgt)
-                    : "f"(pw), "f"(ee), "r"(gk), "r"(glast), "f"(Tn), "f"(alpha), "f"(dd), "f"(a_raw), "f"(dLa));
+                    : "+f"(a_raw), "=f"(alpha), "=f"(rinv), "+f"(T)
+                    : "f"(pw), "f"(ee), "r"(gk), "r"(glast));
+                const float cdp = fmaf(cb, dp2, fmaf(q1.w, dp1, q1.z * dp0));
+                const float dd = cdp - accdp;
+                const float dLa = fmaf(dd, T, nTf_bg * rinv);
+                accdp = fmaf(alpha, dd, accdp);
+                const float s = a_raw * dLa, wgt = alpha * T;
                 const uint32_t rowp = row0 + rowoff;
                 sts_f1(rowp, s);
                 sts_f1(rowp + (RbSmem::Wt - RbSmem::S), wgt);
-                if (rowoff == lane_row) {  // lane `slot` keeps the slot's identity
-                    mine.gk = (uint32_t)gk;
-                    upk2(mxy, mine.mx, mine.my);
+                // lane `slot` keeps the slot's identity (its list position): one compare + one predicated move
+                asm("{\n\t"
+                    ".reg .pred ps;\n\t"
+                    "setp.eq.u32 ps, %1, %2;\n\t"
+                    "@ps mov.u32 %0, %3;\n\t"
+                    "}"
+                    : "+r"(mine.gk)
+                    : "r"(rowoff), "r"(lane_row), "r"(gk));
+                rowoff += ROWB;
+                if (rowoff == RB_NB * ROWB) {  // 16 slots buffered: switch roles, reduce, send
+                    rb_phase2<ABSGRAD>(wbase, RB_NB, lane, px0f, py0f, mine, plist, rec, sgrad);
+                    rowoff = 0u;
                 }
-                const bool full = rowoff == (RB_NB - 1) * ROWB;
-                rowoff = full ? 0u : rowoff + ROWB;
-                if (full) rb_phase2<ABSGRAD>(wbase, RB_NB, lane, px0f, py0f, mine, plist, rec, sgrad);
             }
         }
     }

@@ -87,10 +87,24 @@ DVS_SG_HD void exchange_compute(const ExchangeArgs& a, float* rows, int tid, lon
 #endif
     for (int k = 0; k < 45; k++) acc[k] = 0.0f;
     const float mean[3] = {a.means[3 * i], a.means[3 * i + 1], a.means[3 * i + 2]};
-    for (int v = 0; v < a.V; v++) {
-        const float* d = a.dsh0_all + ((size_t)v * (size_t)a.N + (size_t)i) * 3;
-        const float dc[3] = {d[0], d[1], d[2]};
-        accumulate_view(a.deg, mean, a.campos + 3 * v, dc, acc);
+    // views in groups of four: the twelve loads of a group are issued before any of its arithmetic, so a thread waits for
+    // memory once per four views instead of once per view (the kernel runs at low occupancy — 45 accumulators per thread —
+    // and was latency-bound with one dependent load per view)
+    for (int v0 = 0; v0 < a.V; v0 += 4) {
+        float dc[4][3];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int u = 0; u < 4; u++) {
+            const int v = v0 + u < a.V ? v0 + u : a.V - 1;  // (clamped: a harmless repeat of the last view's load)
+            const float* d = a.dsh0_all + ((size_t)v * (size_t)a.N + (size_t)i) * 3;
+            dc[u][0] = d[0]; dc[u][1] = d[1]; dc[u][2] = d[2];
+        }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int u = 0; u < 4; u++)
+            if (v0 + u < a.V) accumulate_view(a.deg, mean, a.campos + 3 * (v0 + u), dc[u], acc);
     }
 #if defined(__CUDA_ARCH__)
 #pragma unroll

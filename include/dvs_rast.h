@@ -249,14 +249,16 @@ DVS_API int dvs_coll_sh_grad_from_dsh0(const float* means, const float* campos_a
  *   2. barrier: all ranks' gathers have landed and all ranks' backward passes are complete (multimem.red on a symmetric
  *               counter word + acquire polling of the local replica; no host involvement);
  *   3. the first `reduce_ctas` CTAs sum everything except dL/dshN (two ranges of the arena, 56 B per Gaussian) in the switch:
- *               rank r reduces shard r with multimem.ld_reduce and re-broadcasts it with multimem.st; the other CTAs
- *               meanwhile form  dL/dshN[i] = sum_v B(dir_{v,i}) (x) dL/dsh0_v[i] / SH_C0  from the gathered slices (HBM-bound)
- *               straight into the local arena — the NVLink-bound and the HBM-bound halves overlap;
+ *               rank r reduces shard r with multimem.ld_reduce and re-broadcasts it with multimem.st; all CTAs (those first
+ *               ones as soon as their requests are issued) form  dL/dshN[i] = sum_v B(dir_{v,i}) (x) dL/dsh0_v[i] / SH_C0  from
+ *               the gathered slices (HBM-bound, tiles handed out by an atomic counter) straight into the local arena — the
+ *               NVLink-bound and the HBM-bound halves overlap;
  *   4. barrier: every shard has been re-broadcast (the arena may be read / overwritten again).
  * Bytes received per GPU and Gaussian: 12 W + 56 (1 + 1/W) instead of 236 (1 + 1/W) for the plain in-switch all-reduce.
  * All pointers are device addresses of this rank.  `*_mc` are the multicast addresses, `*_local` this rank's unicast
  * addresses of the same symmetric allocations (torch.distributed._symmetric_memory or cuMulticast*).  The words behind
- * `signal_*` and `grid_counter` must be zero before the FIRST call and are owned by the kernel afterwards; `launch_index` is
+ * `signal_*` and `grid_counter` (TWO words: grid arrivals, tile counter) must be zero before the FIRST call and are owned by the
+ * kernel afterwards; `launch_index` is
  * 0, 1, 2, ... and every rank must make the same sequence of calls.  `status` (device, may be NULL) is set non-zero if a
  * barrier timed out (~2 s): the kernel then ends without hanging and the results are invalid.
  * Offsets are in floats from the start of the arena, multiples of 4.  N % 4 must be 0 for the vector path (else scalar).
@@ -277,7 +279,7 @@ typedef struct dvs_coll_fused {
     int64_t range_a[2], range_b[2]; /* [begin, end) of the two reduced ranges */
     uint64_t launch_index;
     int32_t rank, world, sh_degree, sh_rest_alloc;
-    int32_t ctas, reduce_ctas;  /* <= 0: defaults (one CTA per SM; half of them reduce) */
+    int32_t ctas, reduce_ctas;  /* <= 0: defaults (one CTA per SM; a third of them issue the in-switch reduction first) */
 } dvs_coll_fused;
 DVS_API int dvs_coll_exchange_fused(const dvs_coll_fused* args, void* stream);
 /* grid size dvs_coll_exchange_fused will use on the current device for `ctas` (the co-residency bound applied) */
