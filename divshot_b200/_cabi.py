@@ -57,10 +57,10 @@ class DvsStats(C.Structure):
 
 class DvsCollFused(C.Structure):
     """dvs_coll_fused of include/dvs_rast.h (arguments of the fused multi-GPU gradient exchange kernel)."""
-    _fields_ = [("arena_mc", C.c_void_p), ("arena_local", C.c_void_p), ("gather_mc", C.c_void_p), ("gather_local", C.c_void_p),
+    _fields_ = [("arena_mc", C.c_void_p), ("arena_local", C.c_void_p), ("arena_peers", C.c_void_p * 16), ("sh0_tmp", C.c_void_p),
                 ("signal_mc", C.c_void_p), ("signal_local", C.c_void_p), ("grid_counter", C.c_void_p), ("status", C.c_void_p),
                 ("means", C.c_void_p), ("campos", C.c_float * 48), ("N", C.c_int64), ("off_sh0", C.c_int64), ("off_shN", C.c_int64),
-                ("range_a", C.c_int64 * 2), ("range_b", C.c_int64 * 2), ("launch_index", C.c_uint64), ("rank", C.c_int32),
+                ("ranges", (C.c_int64 * 2) * 3), ("launch_index", C.c_uint64), ("rank", C.c_int32),
                 ("world", C.c_int32), ("sh_degree", C.c_int32), ("sh_rest_alloc", C.c_int32), ("ctas", C.c_int32),
                 ("reduce_ctas", C.c_int32)]
 

@@ -64,20 +64,18 @@ extern "C" DVS_API int dvs_coll_allreduce_nvls(void* multicast_ptr, size_t numel
 
 
 // ------------------------------------------------------------------------------------------------------------------
-// The fused exchange (dvs_coll_exchange_fused, include/dvs_rast.h): gather + in-switch reduction + local SH accumulation in
-// one persistent, co-resident grid with two device-side cross-rank barriers.
+// The fused exchange (dvs_coll_exchange_fused, include/dvs_rast.h): in-switch reduction + peer reads + local SH accumulation
+// in one persistent, co-resident grid with two device-side cross-rank barriers.
 // ------------------------------------------------------------------------------------------------------------------
 namespace {
 
-static_assert(sizeof(dvs_coll_fused) == 352 && offsetof(dvs_coll_fused, N) == 264 && offsetof(dvs_coll_fused, rank) == 328,
+static_assert(sizeof(dvs_coll_fused) == 488 && offsetof(dvs_coll_fused, sh0_tmp) == 144 && offsetof(dvs_coll_fused, N) == 384 &&
+                  offsetof(dvs_coll_fused, rank) == 464,
               "dvs_coll_fused layout is part of the C-ABI (divshot_b200/_cabi.py: DvsCollFused)");
 constexpr int FX_THREADS = 512;            // one CTA per SM; a CTA forms 512 rows of dL/dshN per trip
 constexpr int FX_ROW_WORDS = 45;
 constexpr unsigned long long FX_TIMEOUT_NS = 2000000000ull;
 
-__device__ __forceinline__ void mm_st_f32(float* p, float v) {
-    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
-}
 __device__ __forceinline__ void mm_red_release_add_u32(uint32_t* p, uint32_t v) {
     asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -89,6 +87,12 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// peer memory: system-scope relaxed load — never served from this SM's L1, which is not coherent with another GPU's writes
+__device__ __forceinline__ float ld_peer_f32(const float* p) {
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ unsigned long long now_ns() {
@@ -113,7 +117,7 @@ __device__ __forceinline__ bool wait_counter(const uint32_t* p, uint32_t target)
 __device__ __forceinline__ void cross_rank_barrier(const dvs_coll_fused& a, uint32_t seq, uint32_t* s_fail) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence_system();  // this CTA's multimem / global stores are ordered before its arrival
+        __threadfence_system();  // this CTA's multimem / global stores and peer loads are ordered before its arrival
         atomicAdd(a.grid_counter, 1u);
         bool ok = true;
         if (blockIdx.x == 0) {
@@ -130,51 +134,63 @@ __device__ __forceinline__ void cross_rank_barrier(const dvs_coll_fused& a, uint
     __syncthreads();
 }
 
+// step 3 for the FX_THREADS Gaussians [base, base + cnt): thread `tid` reads its Gaussian's dL/dsh0 row of every view from
+// that rank's arena (views in groups of four: twelve peer loads in flight before any arithmetic), accumulates dL/dshN into
+// the shared rows and the summed dL/dsh0 into sh0_tmp
+__device__ __forceinline__ void fused_tile_compute(const dvs_coll_fused& a, float* rows, int tid, long long base, int cnt) {
+    if (tid >= cnt) return;
+    const long long i = base + tid;
+    float acc[45];
+#pragma unroll
+    for (int k = 0; k < 45; k++) acc[k] = 0.0f;
+    const float mean[3] = {a.means[3 * i], a.means[3 * i + 1], a.means[3 * i + 2]};
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
+    const size_t row = (size_t)a.off_sh0 + 3 * (size_t)i;
+    for (int v0 = 0; v0 < a.world; v0 += 4) {
+        float dc[4][3];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int v = v0 + u < a.world ? v0 + u : a.world - 1;  // (clamped: a harmless repeat of the last view's load)
+            const float* d = a.arena_peers[v] + row;
+            dc[u][0] = ld_peer_f32(d); dc[u][1] = ld_peer_f32(d + 1); dc[u][2] = ld_peer_f32(d + 2);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (v0 + u < a.world) {
+                dvs_shx::accumulate_view(a.sh_degree, mean, a.campos + 3 * (v0 + u), dc[u], acc);
+                s0 += dc[u][0]; s1 += dc[u][1]; s2 += dc[u][2];
+            }
+    }
+    const int RW = 3 * a.sh_rest_alloc;
+#pragma unroll
+    for (int k = 0; k < 45; k++)
+        if (k < RW) rows[tid * RW + k] = acc[k];
+    a.sh0_tmp[3 * i] = s0; a.sh0_tmp[3 * i + 1] = s1; a.sh0_tmp[3 * i + 2] = s2;
+}
+
 __global__ void __launch_bounds__(FX_THREADS, 1)
 fused_exchange_kernel(const dvs_coll_fused a) {
     extern __shared__ __align__(16) float s_rows[];  // FX_THREADS rows of dL/dshN
     __shared__ uint32_t s_fail;
     __shared__ long long s_tile;
     if (threadIdx.x == 0) s_fail = 0u;
-    // the tile counter of step 3b (second local word): reset by CTA 0 before it arrives at the first barrier, which every
+    // the tile counter of step 3 (second local word): reset by CTA 0 before it arrives at the first barrier, which every
     // other CTA passes only after CTA 0 has arrived
     if (blockIdx.x == 0 && threadIdx.x == 0) a.grid_counter[1] = 0u;
     const uint32_t seq0 = (uint32_t)(a.launch_index * 2ull);
-    const size_t gtid = (size_t)blockIdx.x * FX_THREADS + threadIdx.x, gsize = (size_t)gridDim.x * FX_THREADS;
 
-    // ---- 1. gather: my dL/dsh0 -> slice `rank` of every replica of the gather area
-    {
-        const size_t n = 3 * (size_t)a.N;
-        const float* src = a.arena_local + a.off_sh0;
-        float* dst = reinterpret_cast<float*>(a.gather_mc) + (size_t)a.rank * n;
-        if ((n & 3) == 0) {
-            const float4* s4 = reinterpret_cast<const float4*>(src);
-            float4* d4 = reinterpret_cast<float4*>(dst);
-            const size_t nv = n >> 2;
-            size_t i = gtid;
-            for (; i + 3 * gsize < nv; i += 4 * gsize) {
-                float4 v[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) v[u] = s4[i + u * gsize];
-#pragma unroll
-                for (int u = 0; u < 4; u++) mm_st(d4 + i + u * gsize, v[u]);
-            }
-            for (; i < nv; i += gsize) mm_st(d4 + i, s4[i]);
-        } else {
-            for (size_t i = gtid; i < n; i += gsize) mm_st_f32(dst + i, src[i]);
-        }
-    }
-    // ---- 2. every rank's slice has landed everywhere; every rank's gradients are final
+    // ---- 1. every rank's gradients are final
     cross_rank_barrier(a, seq0, &s_fail);
     if (s_fail) return;
 
     if ((int)blockIdx.x < a.reduce_ctas) {
-        // ---- 3a. in-switch sum of the two reduced ranges: rank r owns shard r of each
+        // ---- 2. in-switch sum of the reduced ranges: rank r owns shard r of each
         const size_t rtid = (size_t)blockIdx.x * FX_THREADS + threadIdx.x, rsize = (size_t)a.reduce_ctas * FX_THREADS;
         float4* mc = reinterpret_cast<float4*>(a.arena_mc);
 #pragma unroll 1
-        for (int r = 0; r < 2; r++) {
-            const size_t v0 = (size_t)(r ? a.range_b[0] : a.range_a[0]) >> 2, v1 = (size_t)(r ? a.range_b[1] : a.range_a[1]) >> 2;
+        for (int r = 0; r < 3; r++) {
+            const size_t v0 = (size_t)a.ranges[r][0] >> 2, v1 = (size_t)a.ranges[r][1] >> 2;
+            if (v1 <= v0) continue;
             const size_t nv = v1 - v0, per = (nv + a.world - 1) / a.world;
             const size_t lo = v0 + per * a.rank, hi = (lo + per < v1) ? lo + per : v1;
             size_t i = lo + rtid;
@@ -188,12 +204,10 @@ fused_exchange_kernel(const dvs_coll_fused a) {
             for (; i < hi; i += rsize) mm_st(mc + i, mm_ld_reduce(mc + i));
         }
     }
-    if (a.sh_rest_alloc > 0) {
-        // ---- 3b. dL/dshN of all N Gaussians from the gathered slices (local replica), into the local arena.  Tiles of
-        // FX_THREADS rows are handed out by an atomic counter: the CTAs that did not reduce start at once, the others join as
-        // soon as their share of 3a is issued — the NVLink-bound and the HBM-bound halves overlap without a tuned split.
+    {
+        // ---- 3. dL/dshN and the summed dL/dsh0 of all N Gaussians from every rank's dL/dsh0 (peer loads)
         float* out = a.arena_local + a.off_shN;
-        const dvs_shx::ExchangeArgs x{a.means, a.campos, a.gather_local, (long long)a.N, a.world, a.sh_degree,
+        const dvs_shx::ExchangeArgs x{a.means, a.campos, nullptr, (long long)a.N, a.world, a.sh_degree,
                                       3 * a.sh_rest_alloc, out, (reinterpret_cast<uintptr_t>(out) & 15u) == 0 ? 1 : 0};
         const long long n_tiles = (a.N + FX_THREADS - 1) / FX_THREADS;
         for (;;) {
@@ -203,14 +217,22 @@ fused_exchange_kernel(const dvs_coll_fused a) {
             if (tile >= n_tiles) break;
             const long long base = tile * FX_THREADS;
             const int cnt = (int)(a.N - base < FX_THREADS ? a.N - base : FX_THREADS);
-            dvs_shx::exchange_compute(x, s_rows, threadIdx.x, base, cnt);
+            fused_tile_compute(a, s_rows, threadIdx.x, base, cnt);
             __syncthreads();
-            dvs_shx::exchange_store(x, s_rows, threadIdx.x, FX_THREADS, base, cnt);
+            if (a.sh_rest_alloc > 0) dvs_shx::exchange_store(x, s_rows, threadIdx.x, FX_THREADS, base, cnt);
             __syncthreads();
         }
     }
-    // ---- 4. every shard has been re-broadcast: the arena is complete on every rank
+    // ---- 4. every shard has been re-broadcast and nobody reads this rank's per-view dL/dsh0 any more
     cross_rank_barrier(a, seq0 + 1u, &s_fail);
+    if (s_fail) return;
+    {
+        const size_t n = 3 * (size_t)a.N, gtid = (size_t)blockIdx.x * FX_THREADS + threadIdx.x, gsize = (size_t)gridDim.x * FX_THREADS;
+        float* dst = a.arena_local + a.off_sh0;
+        const size_t nv = n >> 2;  // off_sh0 is a multiple of 4 floats and sh0_tmp is 16-byte aligned
+        for (size_t i = gtid; i < nv; i += gsize) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(a.sh0_tmp)[i];
+        for (size_t i = (nv << 2) + gtid; i < n; i += gsize) dst[i] = a.sh0_tmp[i];
+    }
 }
 
 int fused_grid(int ctas) {
@@ -233,26 +255,26 @@ extern "C" DVS_API int dvs_coll_exchange_fused_grid(int ctas) { return fused_gri
 extern "C" DVS_API int dvs_coll_exchange_fused(const dvs_coll_fused* args, void* stream) {
     if (!args) return DVS_E_INVALID;
     dvs_coll_fused a = *args;
-    if (!a.arena_mc || !a.arena_local || !a.gather_mc || !a.gather_local || !a.signal_mc || !a.signal_local || !a.grid_counter ||
-        !a.means)
+    if (!a.arena_mc || !a.arena_local || !a.sh0_tmp || !a.signal_mc || !a.signal_local || !a.grid_counter || !a.means)
         return DVS_E_INVALID;
     if (a.world < 1 || a.world > 16 || a.rank < 0 || a.rank >= a.world || a.N < 0 || a.sh_degree < 0 || a.sh_degree > 3 ||
         a.sh_rest_alloc < 0 || a.sh_rest_alloc > 15 || (a.sh_degree + 1) * (a.sh_degree + 1) - 1 > a.sh_rest_alloc)
         return DVS_E_INVALID;
-    const int64_t offs[6] = {a.off_sh0, a.off_shN, a.range_a[0], a.range_a[1], a.range_b[0], a.range_b[1]};
-    for (int64_t o : offs)
-        if (o < 0 || (o & 3)) return DVS_E_INVALID;
-    if (a.range_a[1] < a.range_a[0] || a.range_b[1] < a.range_b[0]) return DVS_E_INVALID;
+    for (int r = 0; r < a.world; r++)
+        if (!a.arena_peers[r]) return DVS_E_INVALID;
+    if (a.off_sh0 < 0 || (a.off_sh0 & 3) || a.off_shN < 0 || (a.off_shN & 3)) return DVS_E_INVALID;
+    for (int r = 0; r < 3; r++)
+        if (a.ranges[r][0] < 0 || (a.ranges[r][0] & 3) || (a.ranges[r][1] & 3) || a.ranges[r][1] < a.ranges[r][0]) return DVS_E_INVALID;
     const uintptr_t al = reinterpret_cast<uintptr_t>(a.arena_mc) | reinterpret_cast<uintptr_t>(a.arena_local) |
-                         reinterpret_cast<uintptr_t>(a.gather_mc) | reinterpret_cast<uintptr_t>(a.gather_local);
+                         reinterpret_cast<uintptr_t>(a.sh0_tmp);
     if (al & 15u) return DVS_E_INVALID;
     if (a.N == 0) return DVS_OK;
     const int grid = fused_grid(a.ctas);
-    if (grid < 2) return DVS_E_CUDA;
+    if (grid < 1) return DVS_E_CUDA;
     a.ctas = grid;
-    if (a.reduce_ctas <= 0) a.reduce_ctas = grid / 3;      // enough requests in flight for the switch; they join step 3b afterwards
+    if (a.reduce_ctas <= 0) a.reduce_ctas = grid / 3;      // enough requests in flight for the switch; they join step 3 afterwards
     if (a.reduce_ctas > grid) a.reduce_ctas = grid;
-    if (a.sh_rest_alloc == 0) a.reduce_ctas = grid;        // nothing to form: everybody reduces
+    if (a.reduce_ctas < 1) a.reduce_ctas = 1;
     const size_t smem = (size_t)FX_THREADS * FX_ROW_WORDS * sizeof(float);
     void* kargs[] = {&a};
     // cooperative launch: the device-side barriers need every CTA resident (fails instead of deadlocking otherwise)

@@ -197,15 +197,16 @@ class FactoredGradientExchange:
 
 
 class FusedGradientExchange:
-    """The whole exchange as ONE kernel of ours over NVSwitch multicast (csrc/collective.cu, dvs_coll_exchange_fused): every rank
-    multicasts its dL/dsh0 (multimem.st), a device-side cross-rank barrier (multimem.red on a symmetric counter), then half of the
-    CTAs sum the 56 B per Gaussian of everything-but-shN in the switch (multimem.ld_reduce / multimem.st) while the other half
-    form the summed dL/dshN locally from the gathered slices, and a second device-side barrier.  No NCCL call, no host
-    synchronisation, one launch.  Needs the gradient arena in symmetric memory with a multicast mapping (GradientReducer with
-    backend nvls/auto provides it: pass its `flat` and handle) and one view per rank and step.
+    """The whole exchange as ONE kernel of ours over NVSwitch (csrc/collective.cu, dvs_coll_exchange_fused): a device-side
+    cross-rank barrier (multimem.red on a symmetric counter), then a third of the CTAs sum the 44 B per Gaussian of
+    quats | means, scales | opacities in the switch (multimem.ld_reduce / multimem.st) while all CTAs read every view's 12 B per
+    Gaussian of dL/dsh0 straight from that rank's arena (NVLink peer loads) and form the summed dL/dshN and dL/dsh0 locally,
+    and a second device-side barrier.  No NCCL call, no host synchronisation, no staging buffer, one launch.  Needs the gradient
+    arena in symmetric memory with a multicast mapping (GradientReducer with backend nvls/auto provides it: pass its `flat` and
+    handle) and one view per rank and step.
 
-    With `skip_shn_write` the caller passes DVS_FLAG_SKIP_SHN_GRAD to the backward: the per-view dL/dshN (180 B per Gaussian) is
-    then never written to HBM at all, the kernel writes the sum.
+    With `DVS_FLAG_SKIP_SHN_GRAD` in the backward the per-view dL/dshN (180 B per Gaussian) is never written to HBM at all: the
+    kernel writes the sum.
     """
 
     def __init__(self, grads, reducer: "GradientReducer", group=None, ctas: int = 0, reduce_ctas: int = 0):
@@ -228,27 +229,35 @@ class FusedGradientExchange:
         N = grads.opacities.shape[0]
         self.N = N
         group_name = (group or dist.group.WORLD).group_name
-        self.gather = symm_mem.empty(self.world * 3 * N + 4, dtype=torch.float32, device=dev)
-        self._gh = symm_mem.rendezvous(self.gather, group_name)
         self.signal = symm_mem.empty(64, dtype=torch.int32, device=dev)
         self.signal.zero_()
         self._sh = symm_mem.rendezvous(self.signal, group_name)
-        if not getattr(self._gh, "multicast_ptr", 0) or not getattr(self._sh, "multicast_ptr", 0):
-            raise RuntimeError("FusedGradientExchange: no NVLS multicast mapping for the gather / signal buffers")
-        self.local_words = torch.zeros(64, dtype=torch.int32, device=dev)  # [0] grid counter, [32] status
+        if not getattr(self._sh, "multicast_ptr", 0):
+            raise RuntimeError("FusedGradientExchange: no NVLS multicast mapping for the signal buffer")
+        peers = list(hdl.buffer_ptrs)
+        if len(peers) != self.world or not all(peers):
+            raise RuntimeError("FusedGradientExchange: the symmetric arena has no peer mappings")
+        self.local_words = torch.zeros(64, dtype=torch.int32, device=dev)  # [0] grid counter, [1] tile counter, [32] status
+        self.sh0_tmp = torch.zeros((3 * N + 3) // 4 * 4, dtype=torch.float32, device=dev)
         flat = grads.flat
         off = lambda t: (t.data_ptr() - flat.data_ptr()) // 4  # noqa: E731
+        # arena order: quats | shN | means3D | scales | sh0 | opacities (rasterizer.GradBuffers.allocate)
         if not (off(grads.quats) < off(grads.shN) < off(grads.means3D) < off(grads.scales) < off(grads.sh0) < off(grads.opacities)):
             raise ValueError("FusedGradientExchange: unexpected gradient arena layout")
         a = _cabi.DvsCollFused()
         a.arena_mc, a.arena_local = hdl.multicast_ptr, flat.data_ptr()
-        a.gather_mc, a.gather_local = self._gh.multicast_ptr, self.gather.data_ptr()
+        for r, ptr in enumerate(peers):
+            a.arena_peers[r] = ptr
+        a.sh0_tmp = self.sh0_tmp.data_ptr()
         a.signal_mc, a.signal_local = self._sh.multicast_ptr, self.signal.data_ptr()
         a.grid_counter, a.status = self.local_words.data_ptr(), self.local_words.data_ptr() + 128
         a.N, a.off_sh0, a.off_shN = N, off(grads.sh0), off(grads.shN)
-        a.range_a[0], a.range_a[1] = off(grads.quats), off(grads.quats) + 4 * N
-        end_b = (off(grads.opacities) + N + 3) // 4 * 4  # the pad floats behind the last tensor are zero on every rank
-        a.range_b[0], a.range_b[1] = off(grads.means3D), min(end_b, flat.numel())
+        a.ranges[0][0], a.ranges[0][1] = off(grads.quats), off(grads.quats) + 4 * N
+        a.ranges[1][0], a.ranges[1][1] = off(grads.means3D), off(grads.sh0)  # means3D | scales (+ alignment pad, zero everywhere)
+        end_c = min((off(grads.opacities) + N + 3) // 4 * 4, flat.numel())   # the pad floats behind the last tensor are zero
+        a.ranges[2][0], a.ranges[2][1] = off(grads.opacities), end_c
+        for r in range(3):
+            assert a.ranges[r][0] % 4 == 0 and a.ranges[r][1] % 4 == 0, "GradBuffers keeps every tensor 16-byte aligned"
         a.rank, a.world, a.sh_rest_alloc = self.rank, self.world, grads.shN.shape[1]
         a.ctas, a.reduce_ctas = ctas, reduce_ctas
         self._args = a
@@ -288,4 +297,4 @@ class FusedGradientExchange:
         return int(self.local_words[32].item())
 
     def wire_bytes_per_gaussian(self) -> float:
-        return self.world * 12 + 56 * (1 + 1 / self.world)
+        return (self.world - 1) * 12 + 44 * (1 + 1 / self.world)

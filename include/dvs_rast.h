@@ -242,32 +242,37 @@ DVS_API int dvs_coll_sh_grad_from_dsh0(const float* means, const float* campos_a
                                        int num_views, int sh_degree, int sh_rest_alloc, float* out_dshN, void* stream);
 
 /*
- * The whole multi-GPU gradient exchange of SURVEY.md section 8(e) as ONE kernel over NVSwitch multicast (NVLS) mappings —
- * gather, in-switch reduction, cross-rank barriers and the local SH accumulation fused (one view per rank and step):
- *   1. gather : every rank multicasts its dL/dsh0 [N,3] (12 B per Gaussian) into slice `rank` of a symmetric gather area
- *               with multimem.st — one store lands in all `world` replicas;
- *   2. barrier: all ranks' gathers have landed and all ranks' backward passes are complete (multimem.red on a symmetric
- *               counter word + acquire polling of the local replica; no host involvement);
- *   3. the first `reduce_ctas` CTAs sum everything except dL/dshN (two ranges of the arena, 56 B per Gaussian) in the switch:
- *               rank r reduces shard r with multimem.ld_reduce and re-broadcasts it with multimem.st; all CTAs (those first
- *               ones as soon as their requests are issued) form  dL/dshN[i] = sum_v B(dir_{v,i}) (x) dL/dsh0_v[i] / SH_C0  from
- *               the gathered slices (HBM-bound, tiles handed out by an atomic counter) straight into the local arena — the
- *               NVLink-bound and the HBM-bound halves overlap;
- *   4. barrier: every shard has been re-broadcast (the arena may be read / overwritten again).
- * Bytes received per GPU and Gaussian: 12 W + 56 (1 + 1/W) instead of 236 (1 + 1/W) for the plain in-switch all-reduce.
- * All pointers are device addresses of this rank.  `*_mc` are the multicast addresses, `*_local` this rank's unicast
- * addresses of the same symmetric allocations (torch.distributed._symmetric_memory or cuMulticast*).  The words behind
- * `signal_*` and `grid_counter` (TWO words: grid arrivals, tile counter) must be zero before the FIRST call and are owned by the
- * kernel afterwards; `launch_index` is
- * 0, 1, 2, ... and every rank must make the same sequence of calls.  `status` (device, may be NULL) is set non-zero if a
- * barrier timed out (~2 s): the kernel then ends without hanging and the results are invalid.
- * Offsets are in floats from the start of the arena, multiples of 4.  N % 4 must be 0 for the vector path (else scalar).
+ * The whole multi-GPU gradient exchange of SURVEY.md section 8(e) as ONE kernel over NVSwitch peer and multicast (NVLS)
+ * mappings — in-switch reduction, peer reads, device-side cross-rank barriers and the local SH accumulation fused (one view
+ * per rank and step).  Per view the gradient of the higher SH bands is the outer product B(dir) (x) dL/dcolour and the band-0
+ * gradient the rasterizer writes is SH_C0 * dL/dcolour, so instead of summing the 180 B per Gaussian of dL/dshN over ranks
+ * every rank forms that sum itself from the 12 B per Gaussian of each view's dL/dsh0:
+ *   1. barrier: all ranks' backward passes are complete (multimem.red on a symmetric counter word + acquire polling of
+ *               the local replica; no host involvement);
+ *   2. the first `reduce_ctas` CTAs sum quats | means, scales | opacities (three ranges of the arena, 44 B per Gaussian) in
+ *               the switch: rank r reduces shard r with multimem.ld_reduce and re-broadcasts it with multimem.st;
+ *   3. all CTAs (those first ones as soon as their requests are issued) read every view's dL/dsh0 row straight from that
+ *               rank's arena over NVLink (peer loads, L1 bypassed) and form
+ *                   dL/dshN[i] = sum_v B(dir_{v,i}) (x) dL/dsh0_v[i] / SH_C0      and      dL/dsh0[i] = sum_v dL/dsh0_v[i]
+ *               (same order on every rank: bit-identical results) — dL/dshN goes into the local arena, the summed dL/dsh0
+ *               into `sh0_tmp` because the peers are still reading this rank's per-view dL/dsh0 (HBM-bound, tiles handed out
+ *               by an atomic counter; the NVLink-bound and the HBM-bound work overlap);
+ *   4. barrier: every shard has been re-broadcast and every peer read is done; `sh0_tmp` is copied into place.
+ * Bytes received per GPU and Gaussian: 12 (W - 1) + 44 (1 + 1/W) (8 ranks: 134) instead of 236 (1 + 1/W) = 266 for the plain
+ * in-switch all-reduce.
+ * All pointers are device addresses of this rank.  `arena_mc` is the multicast address, `arena_local` this rank's unicast
+ * address and `arena_peers[r]` rank r's arena as mapped into this process (torch.distributed._symmetric_memory:
+ * multicast_ptr / buffer_ptrs, or cuMulticast* / cuMemMap); `sh0_tmp`: 3 N floats of plain device memory.  The words behind
+ * `signal_*` and `grid_counter` (TWO words: grid arrivals, tile counter) must be zero before the FIRST call and are owned by
+ * the kernel afterwards; `launch_index` is 0, 1, 2, ... and every rank must make the same sequence of calls.  `status`
+ * (device, may be NULL) is set non-zero if a barrier timed out (~2 s): the kernel then ends without hanging and the results
+ * are invalid.  Offsets are in floats from the start of the arena, multiples of 4.
  */
 typedef struct dvs_coll_fused {
     void* arena_mc;
     float* arena_local;
-    void* gather_mc;            /* [world][3 N] floats */
-    float* gather_local;
+    const float* arena_peers[16];
+    float* sh0_tmp;
     uint32_t* signal_mc;
     uint32_t* signal_local;
     uint32_t* grid_counter;
@@ -275,8 +280,8 @@ typedef struct dvs_coll_fused {
     const float* means;         /* [N,3] parameters (view directions) */
     float campos[16 * 3];       /* camera centre of every rank's view */
     int64_t N;
-    int64_t off_sh0, off_shN;   /* dL/dsh0 [N,3] (source of the gather), dL/dshN [N,sh_rest_alloc,3] (written locally) */
-    int64_t range_a[2], range_b[2]; /* [begin, end) of the two reduced ranges */
+    int64_t off_sh0, off_shN;   /* dL/dsh0 [N,3] (read from every rank, summed), dL/dshN [N,sh_rest_alloc,3] (written locally) */
+    int64_t ranges[3][2];       /* [begin, end) of the ranges reduced in the switch (empty ranges allowed) */
     uint64_t launch_index;
     int32_t rank, world, sh_degree, sh_rest_alloc;
     int32_t ctas, reduce_ctas;  /* <= 0: defaults (one CTA per SM; a third of them issue the in-switch reduction first) */

@@ -62,7 +62,8 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_cabi.DvsStats) == 5 * 8 + 4 * 4 + 8  # ... overflow, reserved_, num_list_entries
     assert _cabi.DvsStats.num_list_entries.offset == 56 and _cabi.DvsStats.overflow.offset == 48
     # dvs_coll_fused (static_assert'ed to the same numbers in csrc/collective.cu)
-    assert ctypes.sizeof(_cabi.DvsCollFused) == 352 and _cabi.DvsCollFused.N.offset == 264 and _cabi.DvsCollFused.rank.offset == 328
+    assert ctypes.sizeof(_cabi.DvsCollFused) == 488 and _cabi.DvsCollFused.sh0_tmp.offset == 144
+    assert _cabi.DvsCollFused.N.offset == 384 and _cabi.DvsCollFused.rank.offset == 464
 
 
 def test_new_entry_points_validate_their_arguments_without_a_gpu():
