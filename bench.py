@@ -473,7 +473,11 @@ def main():
 
     warm = max(args.warmup, 3)
     sampler_all = ClockSampler(local)  # nvidia-smi sampling across warm-up + all timed regions (>= a few samples)
+    # the library's per-stage CUDA events (nine records per step) are a measuring device, not part of the step: off in the
+    # timed loops as in a training loop, on for the per-stage breakdown below
+    rast.set_profiling(False)
     ms_total, _ = timed(step_resident, args.steps, warm)
+    rast.set_profiling(True)
     # per-stage device times (CUDA events recorded on the launch stream inside the library), averaged over a few steps
     stage_ms = {}
     reps = 5
@@ -483,6 +487,7 @@ def main():
         for k, v in rast.stage_ms().items():
             stage_ms[k] = stage_ms.get(k, 0.0) + v / reps
     st = rast.stats()
+    rast.set_profiling(False)
     ms_e2e, _ = timed(step_e2e, args.steps, warm)
     # keep the GPU under the same load a little longer so the 100 ms nvidia-smi sampler sees it
     t_end = time.time() + 0.6

@@ -56,6 +56,7 @@ struct dvs_rast_ctx {
     int64_t cap_pix = 0;
     float* final_T = nullptr;
     uint32_t* n_contrib = nullptr;
+    const float* bg_image = nullptr;  // caller-owned per-pixel background [3,H,W] (dvs_rast_set_background), or null
     float* h2d_grad[2] = {nullptr, nullptr};   // [3P] device staging of dL/dpix for dvs_rast_step_host*, one per pipeline slot
     float* d_image[2] = {nullptr, nullptr};    // [3P] rendered image before its D2H, one per pipeline slot
     // F4 auxiliary outputs (dvs_rast_forward_aux / dvs_rast_backward_aux), allocated on first use
@@ -332,6 +333,7 @@ int dvs_rast_forward(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, const 
     c.deg = cam->sh_degree; c.KR = cam->sh_rest_alloc;
     c.flags = cam->flags;
     c.gx = (c.W + TILE - 1) / TILE; c.gy = (c.H + TILE - 1) / TILE;
+    c.bg_image = ctx->bg_image;
     const int64_t T = (int64_t)c.gx * c.gy, P = (int64_t)c.W * c.H;
     if (T >= (1 << 24) || c.gx > 65535 || c.gy > 65535) return fail(ctx, DVS_E_UNSUPPORTED, "image too large");
 
@@ -505,6 +507,7 @@ int dvs_rast_forward_aux(dvs_rast_ctx* ctx, const dvs_params* params, float* out
     CK(cudaSetDevice(ctx->device));
     Cam c = ctx->cam;
     c.bg[0] = c.bg[1] = c.bg[2] = 0.0f;
+    c.bg_image = nullptr;
     const int64_t N = ctx->N, P = (int64_t)c.W * c.H;
     int rc;
     if (out_normal && N > 0 && (rc = check_params(ctx, params, c.KR))) return rc;
@@ -557,6 +560,7 @@ int dvs_rast_backward_aux(dvs_rast_ctx* ctx, const dvs_params* params, const flo
     EV(6);
     Cam c0 = c;  // the auxiliary passes composite over a zero background
     c0.bg[0] = c0.bg[1] = c0.bg[2] = 0.0f;
+    c0.bg_image = nullptr;
     if (dL_daux) {
         // 1. depth / alpha loss: same reverse walk, colour triple (depth, 1, 0), third plane of dL zero
         CK(launch_aux_records((int)N, ctx->rec, ctx->rec_aux, st));
@@ -659,6 +663,21 @@ int dvs_rast_step_host_wait(dvs_rast_ctx* ctx, int slot) {
     CK(cudaSetDevice(ctx->device));
     CK(cudaEventSynchronize(ctx->ev_d2h[slot]));  // the slot's image is in out_color_host
     return resolve_pending(ctx, false);           // report an overflowed deferred-check forward as soon as it is known
+}
+
+int dvs_rast_set_background(dvs_rast_ctx* ctx, const float* bg_image) {
+    if (!ctx) return DVS_E_INVALID;
+    ctx->bg_image = bg_image;
+    return DVS_OK;
+}
+
+int dvs_rast_background_grad(dvs_rast_ctx* ctx, const float* dL_dpix, float* dL_dbg, void* stream) {
+    if (!ctx) return DVS_E_INVALID;
+    if (!dL_dpix || !dL_dbg) return fail(ctx, DVS_E_INVALID, "null dL_dpix / dL_dbg");
+    if (!ctx->have_fwd) return fail(ctx, DVS_E_STATE, "background_grad without a forward on this context");
+    CK(cudaSetDevice(ctx->device));
+    CK(launch_background_grad((int64_t)ctx->cam.W * ctx->cam.H, ctx->final_T, dL_dpix, dL_dbg, ctx->info, static_cast<cudaStream_t>(stream)));
+    return DVS_OK;
 }
 
 const uint32_t* dvs_rast_device_overflow_word(const dvs_rast_ctx* ctx) { return ctx ? ctx->info + 2 : nullptr; }

@@ -141,4 +141,20 @@ cudaError_t launch_aux_depth_grad(int N, const float* dz, const float view_row2[
     return cudaGetLastError();
 }
 
+__global__ void background_grad_kernel(int64_t P, const float* __restrict__ final_T, const float* __restrict__ dL_dpix,
+                                       float* __restrict__ dL_dbg, const uint32_t* __restrict__ info) {
+    const bool dead = info[2] != 0u;  // the forward overflowed its arena: no image, no transmittance
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
+        const float T = dead ? 0.f : final_T[p];
+        dL_dbg[p] = T * dL_dpix[p];
+        dL_dbg[P + p] = T * dL_dpix[P + p];
+        dL_dbg[2 * P + p] = T * dL_dpix[2 * P + p];
+    }
+}
+cudaError_t launch_background_grad(int64_t P, const float* final_T, const float* dL_dpix, float* dL_dbg, const uint32_t* info,
+                                   cudaStream_t st) {
+    if (P > 0) background_grad_kernel<<<148 * 8, 256, 0, st>>>(P, final_T, dL_dpix, dL_dbg, info);
+    return cudaGetLastError();
+}
+
 }  // namespace dvs

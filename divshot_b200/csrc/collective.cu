@@ -134,10 +134,34 @@ __device__ __forceinline__ void cross_rank_barrier(const dvs_coll_fused& a, uint
     __syncthreads();
 }
 
-// step 3 for the FX_THREADS Gaussians [base, base + cnt): thread `tid` reads its Gaussian's dL/dsh0 row of every view from
-// that rank's arena (views in groups of four: twelve peer loads in flight before any arithmetic), accumulates dL/dshN into
-// the shared rows and the summed dL/dsh0 into sh0_tmp
-__device__ __forceinline__ void fused_tile_compute(const dvs_coll_fused& a, float* rows, int tid, long long base, int cnt) {
+__device__ __forceinline__ float4 ld_peer_f4(const float* p) {
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+// step 3a for the FX_THREADS Gaussians [base, base + cnt): the CTA copies the dL/dsh0 rows of its tile from EVERY rank's arena
+// into shared memory — the tile is one contiguous, 16-byte aligned span of 12 cnt bytes per rank, read as 128-bit peer loads
+// (a row-wise 3 x 32-bit read would fetch every 32-byte sector three times over NVLink), up to eight ranks' loads in flight per
+// thread before the first is consumed
+__device__ __forceinline__ void fused_tile_stage(const dvs_coll_fused& a, float* stage, int tid, long long base, int cnt) {
+    const size_t row0 = (size_t)a.off_sh0 + 3 * (size_t)base;
+    const int n_words = 3 * cnt, n_vec = n_words >> 2;
+    for (int v0 = 0; v0 < a.world; v0 += 8) {
+        float4 r[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+            if (v0 + u < a.world && tid < n_vec) r[u] = ld_peer_f4(a.arena_peers[v0 + u] + row0 + 4 * (size_t)tid);
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+            if (v0 + u < a.world && tid < n_vec) reinterpret_cast<float4*>(stage + (size_t)(v0 + u) * (3 * FX_THREADS))[tid] = r[u];
+    }
+    for (int w = (n_vec << 2) + tid; w < n_words; w += FX_THREADS)  // the last, partial tile only
+        for (int v = 0; v < a.world; v++) stage[(size_t)v * (3 * FX_THREADS) + w] = ld_peer_f32(a.arena_peers[v] + row0 + w);
+}
+// step 3b: thread `tid` accumulates its Gaussian's dL/dshN row into the shared rows and the summed dL/dsh0 into sh0_tmp
+__device__ __forceinline__ void fused_tile_compute(const dvs_coll_fused& a, const float* stage, float* rows, int tid, long long base,
+                                                   int cnt) {
     if (tid >= cnt) return;
     const long long i = base + tid;
     float acc[45];
@@ -145,21 +169,11 @@ __device__ __forceinline__ void fused_tile_compute(const dvs_coll_fused& a, floa
     for (int k = 0; k < 45; k++) acc[k] = 0.0f;
     const float mean[3] = {a.means[3 * i], a.means[3 * i + 1], a.means[3 * i + 2]};
     float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
-    const size_t row = (size_t)a.off_sh0 + 3 * (size_t)i;
-    for (int v0 = 0; v0 < a.world; v0 += 4) {
-        float dc[4][3];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int v = v0 + u < a.world ? v0 + u : a.world - 1;  // (clamped: a harmless repeat of the last view's load)
-            const float* d = a.arena_peers[v] + row;
-            dc[u][0] = ld_peer_f32(d); dc[u][1] = ld_peer_f32(d + 1); dc[u][2] = ld_peer_f32(d + 2);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-            if (v0 + u < a.world) {
-                dvs_shx::accumulate_view(a.sh_degree, mean, a.campos + 3 * (v0 + u), dc[u], acc);
-                s0 += dc[u][0]; s1 += dc[u][1]; s2 += dc[u][2];
-            }
+    for (int v = 0; v < a.world; v++) {
+        const float* d = stage + (size_t)v * (3 * FX_THREADS) + 3 * tid;  // stride 3 words: conflict-free
+        const float dc[3] = {d[0], d[1], d[2]};
+        dvs_shx::accumulate_view(a.sh_degree, mean, a.campos + 3 * v, dc, acc);
+        s0 += dc[0]; s1 += dc[1]; s2 += dc[2];
     }
     const int RW = 3 * a.sh_rest_alloc;
 #pragma unroll
@@ -170,7 +184,8 @@ __device__ __forceinline__ void fused_tile_compute(const dvs_coll_fused& a, floa
 
 __global__ void __launch_bounds__(FX_THREADS, 1)
 fused_exchange_kernel(const dvs_coll_fused a) {
-    extern __shared__ __align__(16) float s_rows[];  // FX_THREADS rows of dL/dshN
+    extern __shared__ __align__(16) float s_rows[];  // FX_THREADS rows of dL/dshN, then `world` x FX_THREADS staged dL/dsh0 rows
+    float* s_stage = s_rows + FX_THREADS * FX_ROW_WORDS;
     __shared__ uint32_t s_fail;
     __shared__ long long s_tile;
     if (threadIdx.x == 0) s_fail = 0u;
@@ -217,7 +232,9 @@ fused_exchange_kernel(const dvs_coll_fused a) {
             if (tile >= n_tiles) break;
             const long long base = tile * FX_THREADS;
             const int cnt = (int)(a.N - base < FX_THREADS ? a.N - base : FX_THREADS);
-            fused_tile_compute(a, s_rows, threadIdx.x, base, cnt);
+            fused_tile_stage(a, s_stage, threadIdx.x, base, cnt);
+            __syncthreads();
+            fused_tile_compute(a, s_stage, s_rows, threadIdx.x, base, cnt);
             __syncthreads();
             if (a.sh_rest_alloc > 0) dvs_shx::exchange_store(x, s_rows, threadIdx.x, FX_THREADS, base, cnt);
             __syncthreads();
@@ -235,11 +252,13 @@ fused_exchange_kernel(const dvs_coll_fused a) {
     }
 }
 
-int fused_grid(int ctas) {
+size_t fused_smem(int world) { return (size_t)FX_THREADS * (FX_ROW_WORDS + 3 * (size_t)(world > 0 ? world : 1)) * sizeof(float); }
+
+int fused_grid(int ctas, int world) {
     int dev = 0, sms = 148, per_sm = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const size_t smem = (size_t)FX_THREADS * FX_ROW_WORDS * sizeof(float);
+    const size_t smem = fused_smem(world);
     if (cudaFuncSetAttribute(fused_exchange_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_exchange_kernel, FX_THREADS, smem) != cudaSuccess || per_sm < 1)
         return 0;
@@ -250,7 +269,7 @@ int fused_grid(int ctas) {
 
 }  // namespace
 
-extern "C" DVS_API int dvs_coll_exchange_fused_grid(int ctas) { return fused_grid(ctas); }
+extern "C" DVS_API int dvs_coll_exchange_fused_grid(int ctas, int world) { return fused_grid(ctas, world); }
 
 extern "C" DVS_API int dvs_coll_exchange_fused(const dvs_coll_fused* args, void* stream) {
     if (!args) return DVS_E_INVALID;
@@ -269,13 +288,13 @@ extern "C" DVS_API int dvs_coll_exchange_fused(const dvs_coll_fused* args, void*
                          reinterpret_cast<uintptr_t>(a.sh0_tmp);
     if (al & 15u) return DVS_E_INVALID;
     if (a.N == 0) return DVS_OK;
-    const int grid = fused_grid(a.ctas);
+    const int grid = fused_grid(a.ctas, a.world);
     if (grid < 1) return DVS_E_CUDA;
     a.ctas = grid;
     if (a.reduce_ctas <= 0) a.reduce_ctas = grid / 3;      // enough requests in flight for the switch; they join step 3 afterwards
     if (a.reduce_ctas > grid) a.reduce_ctas = grid;
     if (a.reduce_ctas < 1) a.reduce_ctas = 1;
-    const size_t smem = (size_t)FX_THREADS * FX_ROW_WORDS * sizeof(float);
+    const size_t smem = fused_smem(a.world);
     void* kargs[] = {&a};
     // cooperative launch: the device-side barriers need every CTA resident (fails instead of deadlocking otherwise)
     const cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(fused_exchange_kernel), dim3(grid), dim3(FX_THREADS),

@@ -42,6 +42,7 @@ struct Cam {
     int deg, KR;
     uint32_t flags;
     int gx, gy;
+    const float* bg_image;  // optional per-pixel background [3,H,W] (dvs_rast_set_background: the trainer's sky model); null: bg[]
 };
 
 struct Params {

@@ -53,6 +53,10 @@ cudaError_t launch_aux_normal_records(const Cam& cam, int N, const Params& prm, 
 cudaError_t launch_aux_extract3(int N, float4* sgrad, float* dn, cudaStream_t st);
 cudaError_t launch_aux_normal_grad(const Cam& cam, int N, const Params& prm, const float* dn, float* dquats, cudaStream_t st);
 
+// background model: dL/dbg[ch][p] = final_T[p] * dL/dpix[ch][p]  (out = C + final_T * bg)
+cudaError_t launch_background_grad(int64_t P, const float* final_T, const float* dL_dpix, float* dL_dbg, const uint32_t* info,
+                                   cudaStream_t st);
+
 // debug helpers (parity tests): unpack records into the upstream-style arrays
 cudaError_t launch_unpack(int N, const float4* rec, int32_t* radii, uint32_t* tiles, float* depth, float* mean2D,
                           float* conic_opacity, float* rgb, uint8_t* clamped, cudaStream_t st);

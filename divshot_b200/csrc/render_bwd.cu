@@ -201,7 +201,11 @@ render_bwd_kernel(Cam cam, const uint32_t* __restrict__ tile_order, const uint32
         sts_f1(wbase + RbSmem::dpA + pr * 16 + 8 + odd * 4, dp1);
         sts_f1(wbase + RbSmem::dpB + pr * 8 + odd * 4, dp2);
     }
-    const float nTf_bg = -T_final * (cam.bg[0] * dp0 + cam.bg[1] * dp1 + cam.bg[2] * dp2);
+    float b0 = cam.bg[0], b1 = cam.bg[1], b2 = cam.bg[2];
+    if (cam.bg_image && inside) {  // per-pixel background (sky model)
+        b0 = __ldg(cam.bg_image + pix); b1 = __ldg(cam.bg_image + P + pix); b2 = __ldg(cam.bg_image + 2 * P + pix);
+    }
+    const float nTf_bg = -T_final * (b0 * dp0 + b1 * dp1 + b2 * dp2);
     float T = T_final;
     // accdp = (colour accumulated behind the current splat) . dL/dpix — the three-channel recursion
     // R <- R + alpha (c - R) collapses to one scalar because only R . dL/dpix is ever used

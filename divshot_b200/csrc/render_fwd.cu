@@ -151,9 +151,13 @@ render_fwd_kernel(Cam cam, const uint32_t* __restrict__ tile_order, const uint32
         const size_t pix = (size_t)py * cam.W + px;
         final_T[pix] = Tb;
         n_contrib[pix] = last;
-        out_color[pix] = fmaf(Tb, cam.bg[0], C0);
-        out_color[P + pix] = fmaf(Tb, cam.bg[1], C1);
-        out_color[2 * P + pix] = fmaf(Tb, cam.bg[2], C2);
+        float b0 = cam.bg[0], b1 = cam.bg[1], b2 = cam.bg[2];
+        if (cam.bg_image) {  // per-pixel background (sky model): out = C + T_final * bg(pixel)
+            b0 = __ldg(cam.bg_image + pix); b1 = __ldg(cam.bg_image + P + pix); b2 = __ldg(cam.bg_image + 2 * P + pix);
+        }
+        out_color[pix] = fmaf(Tb, b0, C0);
+        out_color[P + pix] = fmaf(Tb, b1, C1);
+        out_color[2 * P + pix] = fmaf(Tb, b2, C2);
     }
 }
 

@@ -262,7 +262,7 @@ class FusedGradientExchange:
         a.ctas, a.reduce_ctas = ctas, reduce_ctas
         self._args = a
         self.launches = 0
-        self.grid = self._lib.dvs_coll_exchange_fused_grid(ctas)
+        self.grid = self._lib.dvs_coll_exchange_fused_grid(ctas, self.world)
         torch.cuda.synchronize(dev)
         dist.barrier(group)  # every rank's signal word is zero before anybody's first kernel touches it
 

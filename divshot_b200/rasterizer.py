@@ -205,6 +205,21 @@ class Rasterizer:
     def step_host_wait(self, slot: int):
         self._check(self._lib.dvs_rast_step_host_wait(self._h, slot))
 
+    def set_background(self, bg_image: torch.Tensor | None):
+        """Per-pixel background [3,H,W] (the trainer's sky model, GaussianTrainConfig::enableBg) for every later forward /
+        backward of this context; None restores the camera's constant background.  The tensor is kept alive here."""
+        if bg_image is not None:
+            assert bg_image.is_cuda and bg_image.dtype == torch.float32 and bg_image.is_contiguous() and bg_image.dim() == 3
+        self._bg = bg_image
+        self._check(self._lib.dvs_rast_set_background(self._h, bg_image.data_ptr() if bg_image is not None else None))
+
+    def background_grad(self, dL_dpix: torch.Tensor) -> torch.Tensor:
+        """dL/dbg = final_T * dL/dpix [3,H,W] of the last forward."""
+        out = torch.empty_like(dL_dpix)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self._lib.dvs_rast_background_grad(self._h, dL_dpix.data_ptr(), out.data_ptr(), C.c_void_p(st)))
+        return out
+
     def set_profiling(self, on: bool):
         """Per-stage CUDA events on/off (off in a training loop; stage_ms() needs them on)."""
         if hasattr(self._lib, "dvs_rast_set_profiling"):

@@ -175,6 +175,16 @@ DVS_API int dvs_rast_backward_aux(dvs_rast_ctx* ctx, const dvs_params* params, c
                                   const float* dL_dnormal, const dvs_grads* grads, uint32_t flags, void* stream);
 
 /*
+ * Background model (GaussianTrainConfig::enableBg, "Create Sky Model" docs/userGuide.md:53): a caller-owned per-pixel
+ * background image [3,H,W] (device) replaces the constant camera background in every later forward / backward of this
+ * context — out = C + final_T * bg(pixel) — until it is reset with NULL.  The image must match the camera's size and stay
+ * valid from the forward to its backward.  dvs_rast_background_grad writes dL/dbg = final_T * dL/dpix [3,H,W] of the last
+ * forward (what the caller's sky model differentiates through).
+ */
+DVS_API int dvs_rast_set_background(dvs_rast_ctx* ctx, const float* bg_image);
+DVS_API int dvs_rast_background_grad(dvs_rast_ctx* ctx, const float* dL_dpix, float* dL_dbg, void* stream);
+
+/*
  * Host-buffer step (the end-to-end path a trainer without device-resident images uses):
  * copies dL_dpix_host (pinned or pageable) to the device, runs forward + backward with the
  * device-resident parameters/gradients, copies the rendered image back to out_color_host.
@@ -287,8 +297,8 @@ typedef struct dvs_coll_fused {
     int32_t ctas, reduce_ctas;  /* <= 0: defaults (one CTA per SM; a third of them issue the in-switch reduction first) */
 } dvs_coll_fused;
 DVS_API int dvs_coll_exchange_fused(const dvs_coll_fused* args, void* stream);
-/* grid size dvs_coll_exchange_fused will use on the current device for `ctas` (the co-residency bound applied) */
-DVS_API int dvs_coll_exchange_fused_grid(int ctas);
+/* grid size dvs_coll_exchange_fused will use on the current device for `ctas` and `world` ranks (the co-residency bound applied) */
+DVS_API int dvs_coll_exchange_fused_grid(int ctas, int world);
 
 #ifdef __cplusplus
 }

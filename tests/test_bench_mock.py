@@ -49,6 +49,9 @@ class _FakeRasterizer:
     def step_host_wait(self, slot):
         pass
 
+    def set_profiling(self, on):
+        pass
+
     def stage_ms(self):
         return {k: 0.1 + 0.01 * i for i, k in enumerate(STAGES)}
 

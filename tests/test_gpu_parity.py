@@ -453,3 +453,55 @@ def test_backward_can_skip_the_shN_gradient():
             assert rel_err(getattr(g1, k).cpu().numpy(), getattr(g0, k).cpu().numpy()) < 5e-5, k
     finally:
         r.close()
+
+
+def test_per_pixel_background_forward_and_backward(rast):
+    """dvs_rast_set_background (GaussianTrainConfig::enableBg, the sky model's input): out = C + final_T * bg(pixel).
+    Forward against the oracle by linearity in the background (image over black + final_T * bg); backward against three
+    oracle backward passes: the loss <out, dL> = <image_0, dL> + sum_p final_T(p) s(p) with s = bg . dL per pixel, and the
+    oracle differentiates the second term as backward(bg = (1,0,0), dL' = (s,0,0)) - backward(bg = 0, dL')."""
+    from divshot_b200.rasterizer import GradBuffers, scene_to_device
+    sc = make_scene(N=4000, width=112, height=80, sh_degree=1, seed=111, normalise_quats=False, bg=(0.0, 0.0, 0.0))
+    sc.log_scales += 0.5
+    sc.logit_opac -= 1.0  # translucent: the background shows through
+    dev = rast.device
+    H, W = 80, 112
+    rng = np.random.default_rng(3)
+    bg_img = rng.uniform(0, 1, (3, H, W)).astype(np.float32)
+    dl = sc.dL_dpix[0]
+    params = scene_to_device(sc, dev)
+    cam = _cabi.make_camera(sc.cameras[0], 1)
+    f, b0 = _oracle(sc)
+    try:
+        rast.set_background(torch.from_numpy(bg_img).to(dev))
+        img, _ = rast.forward(cam, params)
+        g = GradBuffers.allocate(sc.N, 3, dev)
+        dl_d = torch.from_numpy(dl).to(dev)
+        rast.backward(dl_d, g)
+        dbg = rast.background_grad(dl_d)
+        torch.cuda.synchronize()
+    finally:
+        rast.set_background(None)
+    T = f.final_T.reshape(H, W)
+    want_img = f.image + T[None] * bg_img
+    ok = (f.fragile == 0).reshape(H, W)
+    e = elem_err(img.cpu().numpy(), want_img)
+    assert e[:, ok].max() <= TOL, e[:, ok].max()
+    assert_close(dbg.cpu().numpy()[:, ok], (T[None] * dl)[:, ok], 1e-3, "dL/dbg = final_T * dL/dpix")
+    # backward: b0 (black background, dL) + [backward(bg=(1,0,0), dL') - backward(bg=0, dL')], dL' = (bg . dL, 0, 0)
+    s = (bg_img * dl).sum(0)
+    dlp = np.zeros_like(dl); dlp[0] = s
+    import dataclasses
+    oc1 = orc_cam(dataclasses.replace(sc.cameras[0], bg=np.array([1.0, 0.0, 0.0], np.float32)), 1, sh_rest_alloc=sc.shN.shape[1])
+    oc0 = orc_cam(sc.cameras[0], 1, sh_rest_alloc=sc.shN.shape[1])
+    f1 = orc.forward(oc1, *scene_arrays(sc))
+    b1 = orc.backward(oc1, f1, *scene_arrays(sc), dlp)
+    b2 = orc.backward(oc0, f, *scene_arrays(sc), dlp)
+    for k, name in [("means3D", "dL_dmeans3D"), ("scales", "dL_dscales"), ("quats", "dL_dquats"), ("opacities", "dL_dopacities"),
+                    ("sh0", "dL_dsh0"), ("shN", "dL_dshN")]:
+        ref = getattr(b0, name).astype(np.float64) + getattr(b1, name).astype(np.float64) - getattr(b2, name).astype(np.float64)
+        got = getattr(g, k).cpu().numpy()
+        assert_close_robust(got, ref.reshape(got.shape), 2e-4, f"per-pixel background: dL_d{k}")
+    # and the constant background is back afterwards
+    img2, _ = rast.forward(cam, params)
+    assert_close(img2.cpu().numpy()[:, ok], f.image[:, ok], TOL, "constant background restored")

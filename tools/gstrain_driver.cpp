@@ -11,6 +11,7 @@
 // Prints the loss trajectory and the training rate (iterations/s over the loop, wall clock).
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -63,10 +64,13 @@ int main(int argc, char** argv) {
     if (!load(scene, data)) { std::fprintf(stderr, "load_train_data failed\n"); return 4; }
     float first = -1.f, last = -1.f;
     const int start_step = cur(scene);
-    const auto t0 = std::chrono::steady_clock::now();
+    // the rate is measured after a few warm-up steps (first-use allocations, NCCL's lazy connection set-up)
+    const int timed_from = start_step + std::min(20, std::max(0, (iters - start_step) / 4));
+    auto t0 = std::chrono::steady_clock::now();
     while (true) {
         const int i = cur(scene);
         if (i >= iters) break;
+        if (i == timed_from) t0 = std::chrono::steady_clock::now();
         step(scene);
         last = scene->getCurrentLoss();
         if (i == 0) first = last;
@@ -76,7 +80,7 @@ int main(int argc, char** argv) {
     const char* rk = std::getenv("DVS_RANK") ? std::getenv("DVS_RANK") : std::getenv("RANK");
     if (!rk || std::atoi(rk) == 0) save(scene);  // data parallel: every rank holds the same model, rank 0 writes it
     std::printf("steps %d first_loss %.6f last_loss %.6f its_per_s %.1f (from step %d)\n", cur(scene), first, last,
-                secs > 0 ? (cur(scene) - start_step) / secs : 0.0, start_step);
+                secs > 0 ? (cur(scene) - timed_from) / secs : 0.0, start_step);
     del(scene);
     destroy();
     dlclose(h);
