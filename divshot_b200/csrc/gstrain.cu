@@ -44,6 +44,7 @@
 #include "dvs_rast.h"
 #include "dvs_viewer_pack.h"
 #include "gaussian_trainer_scene.hpp"
+#include "sh_grad_ops.h"
 
 #define GS_EXPORT __attribute__((visibility("default")))
 
@@ -261,6 +262,79 @@ adam_fused_kernel(float* __restrict__ P, const float* __restrict__ G, float* __r
     }
 }
 
+// ---- background ("sky") model: GaussianTrainConfig::enableBg, "Create Sky Model" (docs/userGuide.md:53) -------------------
+// What lies behind the splats — sky, far scenery the point cloud does not cover — is a smooth function of the viewing
+// direction: 9 real SH coefficients (degree 2) per colour channel, 27 learnable floats.  Every step the model is evaluated per
+// pixel into a background image the rasterizer composites over (out = C + final_T * bg(pixel), dvs_rast_set_background), and
+// its gradient is the SH-weighted sum of dL/dbg = final_T * dL/dpix over the pixels (dvs_rast_background_grad).  The closed
+// trainer's sky model is absent from the reference: parity unpinned; the arithmetic is checked against
+// numpy (tests/test_plugin.py).  The model file formats have no field for it: it lives with the trainer object.
+constexpr int SKY_K = 9;
+struct SkyCam { float Rt[9]; float tanx, tany; int W, H; };  // rotation rows of the view matrix (world -> camera)
+
+__device__ __forceinline__ void sky_basis(const SkyCam& c, int px, int py, float Y[SKY_K]) {
+    // pixel centre -> NDC (the inverse of ndc2Pix, gsplat_vs.hlsl:211-214) -> camera ray -> world direction
+    const float nx = (2.0f * (float)px + 1.0f) / (float)c.W - 1.0f, ny = (2.0f * (float)py + 1.0f) / (float)c.H - 1.0f;
+    const float rx = nx * c.tanx, ry = ny * c.tany, rz = 1.0f;
+    float dx = c.Rt[0] * rx + c.Rt[3] * ry + c.Rt[6] * rz, dy = c.Rt[1] * rx + c.Rt[4] * ry + c.Rt[7] * rz,
+          dz = c.Rt[2] * rx + c.Rt[5] * ry + c.Rt[8] * rz;  // R^T ray
+    const float li = rsqrtf(dx * dx + dy * dy + dz * dz);
+    dx *= li; dy *= li; dz *= li;
+    float b[15];
+    dvs_shx::sh_rest_basis(2, dx, dy, dz, b);
+    Y[0] = dvs_shx::kC0;
+#pragma unroll
+    for (int k = 1; k < SKY_K; k++) Y[k] = b[k - 1];
+}
+__global__ void sky_eval_kernel(SkyCam c, const float* __restrict__ coef /* [9][3] */, float* __restrict__ bg /* [3,H,W] */) {
+    const size_t P = (size_t)c.W * c.H;
+    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < P; p += (size_t)gridDim.x * blockDim.x) {
+        float Y[SKY_K];
+        sky_basis(c, (int)(p % c.W), (int)(p / c.W), Y);
+        float r = 0.f, g = 0.f, b = 0.f;
+#pragma unroll
+        for (int k = 0; k < SKY_K; k++) { r += Y[k] * coef[3 * k]; g += Y[k] * coef[3 * k + 1]; b += Y[k] * coef[3 * k + 2]; }
+        bg[p] = r; bg[P + p] = g; bg[2 * P + p] = b;
+    }
+}
+// dL/dcoef[k][ch] += sum_p Y_k(dir_p) * dL/dbg[ch][p]: per-thread partial sums over a grid-stride loop, warp shuffles, one
+// atomic per (warp, coefficient, channel)
+__global__ void sky_grad_kernel(SkyCam c, const float* __restrict__ dbg /* [3,H,W] */, float* __restrict__ dcoef /* [9][3] */) {
+    const size_t P = (size_t)c.W * c.H;
+    float acc[3 * SKY_K];
+#pragma unroll
+    for (int k = 0; k < 3 * SKY_K; k++) acc[k] = 0.f;
+    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < P; p += (size_t)gridDim.x * blockDim.x) {
+        float Y[SKY_K];
+        sky_basis(c, (int)(p % c.W), (int)(p / c.W), Y);
+        const float r = dbg[p], g = dbg[P + p], b = dbg[2 * P + p];
+#pragma unroll
+        for (int k = 0; k < SKY_K; k++) { acc[3 * k] += Y[k] * r; acc[3 * k + 1] += Y[k] * g; acc[3 * k + 2] += Y[k] * b; }
+    }
+#pragma unroll
+    for (int k = 0; k < 3 * SKY_K; k++) {
+        float v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(dcoef + k, v);
+    }
+}
+__global__ void sky_adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, float lr,
+                                float b1, float b2, float eps, float c1, float c2) {
+    const int i = threadIdx.x;
+    if (i < 3 * SKY_K) {
+        adam_one(p[i], g[i], m[i], v[i], lr, b1, b2, eps, c1, c2);
+        g[i] = 0.f;  // the gradient accumulator starts the next step from zero
+    }
+}
+static SkyCam sky_cam(const dvs_camera& cam) {
+    SkyCam c;
+    for (int r = 0; r < 3; r++)
+        for (int k = 0; k < 3; k++) c.Rt[3 * r + k] = cam.view[4 * k + r];  // view is flat [4 c + r]: rotation rows
+    c.tanx = cam.tanfovx; c.tany = cam.tanfovy; c.W = cam.width; c.H = cam.height;
+    return c;
+}
+
 struct View {
     dvs_camera cam;
     float* d_target = nullptr;  // [3,H,W] device
@@ -465,6 +539,11 @@ struct GaussianTrainerImpl {
     int32_t* d_radii = nullptr;    // [capacity] radii of the last forward
     bool refine_enabled = false;   // the schedule reaches the refinement window (set before upload)
     bool resync_next = false;      // N changed: the next forward re-sizes the binning arena synchronously
+    // background model (enableBg): 27 SH coefficients, their gradient and Adam moments [4][27], the per-pixel image and dL/dbg
+    float* d_sky = nullptr;
+    float* d_bg_img = nullptr;
+    float* d_dbg = nullptr;
+    size_t sky_img_cap = 0;
     int load_itr = -1;             // create_splat(config, loadItr): resume from the model file at config.modelPath at this iteration
     dvs_densify::RefineReport last_report;
     // The editor drives trainStep from a worker thread and reads the model from its UI thread (editor.cpp:1559-1574 vs
@@ -588,6 +667,7 @@ GaussianTrainerScene::~GaussianTrainerScene() {
     for (auto& v : impl_->views) { cudaFree(v.d_target); cudaFree(v.d_mask); }
     impl_->release_model();
     cudaFree(impl_->d_render); cudaFree(impl_->d_dLdpix); cudaFree(impl_->d_scratch); cudaFree(impl_->d_loss);
+    cudaFree(impl_->d_sky); cudaFree(impl_->d_bg_img); cudaFree(impl_->d_dbg);
     for (auto& v : impl_->vp) { cudaFree(v.d); if (v.h) cudaFreeHost(v.h); if (v.ready) cudaEventDestroy(v.ready); }
     if (impl_->vp_packed) cudaEventDestroy(impl_->vp_packed);
     if (impl_->vp_stream) cudaStreamDestroy(impl_->vp_stream);
@@ -893,6 +973,22 @@ void GaussianTrainerScene::trainStep() {
             ck(cudaMemsetAsync(I.d_mean2D, 0, 2 * (size_t)I.N * sizeof(float), I.stream), "memset mean2D");
             if (config_.useAbsGrad) ck(cudaMemsetAsync(I.d_mean2D_abs, 0, 2 * (size_t)I.N * sizeof(float), I.stream), "memset mean2D_abs");
         }
+        if (config_.enableBg) {  // evaluate the sky model for this camera; the rasterizer composites over it
+            const size_t need = (size_t)3 * cam.width * cam.height;
+            if (!I.d_sky) {
+                ck(cudaMalloc(&I.d_sky, 4 * 3 * SKY_K * sizeof(float)), "cudaMalloc sky");
+                ck(cudaMemsetAsync(I.d_sky, 0, 4 * 3 * SKY_K * sizeof(float), I.stream), "memset sky");
+            }
+            if (need > I.sky_img_cap) {
+                ck(cudaStreamSynchronize(I.stream), "sync");
+                cudaFree(I.d_bg_img); cudaFree(I.d_dbg);
+                ck(cudaMalloc(&I.d_bg_img, need * sizeof(float)), "cudaMalloc sky image");
+                ck(cudaMalloc(&I.d_dbg, need * sizeof(float)), "cudaMalloc sky gradient image");
+                I.sky_img_cap = need;
+            }
+            sky_eval_kernel<<<148 * 4, 256, 0, I.stream>>>(sky_cam(cam), I.d_sky, I.d_bg_img);
+            ckr(dvs_rast_set_background(I.ctx, I.d_bg_img), I.ctx, "set_background");
+        }
         for (int attempt = 0;; attempt++) {
             int rc = dvs_rast_forward(I.ctx, &cam, I.N, &P, I.d_render, ((refining && !mcmc) || sparse_adam) ? I.d_radii : nullptr, I.stream);
             if (rc == DVS_E_OVERFLOW && attempt < 2) { cam.flags &= ~DVS_FLAG_DEFER_CHECK; continue; }
@@ -907,6 +1003,10 @@ void GaussianTrainerScene::trainStep() {
             ckr(rc, I.ctx, "backward");
             break;
         }
+        if (config_.enableBg) {  // dL/dsky += sum_p Y(dir_p) final_T(p) dL/dpix(p)
+            ckr(dvs_rast_background_grad(I.ctx, I.d_dLdpix, I.d_dbg, I.stream), I.ctx, "background_grad");
+            sky_grad_kernel<<<148 * 2, 256, 0, I.stream>>>(sky_cam(cam), I.d_dbg, I.d_sky + 3 * SKY_K);
+        }
         if (refining && !mcmc)
             ck(dvs_densify::adc_accumulate(I.d_mean2D, config_.useAbsGrad ? I.d_mean2D_abs : nullptr, I.d_radii, I.d_accum,
                                            I.d_denom, I.N, I.stream, skip_word), "adc_accumulate");
@@ -917,6 +1017,7 @@ void GaussianTrainerScene::trainStep() {
         I.dp.all_reduce_sum({{I.grads.quats(), 4 * n}, {I.grads.shN(), (size_t)3 * KR * n}, {I.grads.means(), 3 * n},
                              {I.grads.scales(), 3 * n}, {I.grads.sh0(), 3 * n}, {I.grads.opac(), n}}, I.stream);
     }
+    if (world > 1 && config_.enableBg) I.dp.all_reduce_sum({{I.d_sky + 3 * SKY_K, (size_t)3 * SKY_K}}, I.stream);
     if (refining && mcmc)  // L1 regularisers of the MCMC strategy: 0.01 mean(opacity) + 0.01 mean(scale), once per step
         ck(dvs_densify::mcmc_regularise(I.T(I.params), I.T(I.grads), I.N, 0.01f, 0.01f, I.stream), "mcmc_regularise");
     // Adam, per-group learning rates (GaussianTrainConfig); position lr decays exponentially init -> final
@@ -930,6 +1031,9 @@ void GaussianTrainerScene::trainStep() {
         launch_adam_fused(I.params, I.grads.flat, I.m1.flat, I.m2.flat, I.N, lrs, visible_only ? I.d_radii : nullptr, skip_word, b1, b2,
                           eps, c1, c2, I.stream);
     }
+    if (config_.enableBg && I.d_sky)
+        sky_adam_kernel<<<1, 32, 0, I.stream>>>(I.d_sky, I.d_sky + 3 * SKY_K, I.d_sky + 6 * SKY_K, I.d_sky + 9 * SKY_K, config_.featurelr, b1,
+                                               b2, eps, c1, c2);
     if (refining) {
         const uint64_t seed = 0x5DEECE66Dull * (uint64_t)(step + 1);
         if (mcmc)  // exploration noise after the optimizer step: Sigma eps gate(opacity) noiselr lr_xyz
@@ -1288,6 +1392,15 @@ GS_EXPORT int64_t gstrain_test_adam(float* params, const float* grads, float* m1
         launch_adam_fused(lay, grads, m1, m2, N, lrs, radii, skip, b1, b2, eps, c1, c2, static_cast<cudaStream_t>(stream));
     }
     return cudaGetLastError() == cudaSuccess ? (int64_t)lay.total : -1;
+}
+// test hooks of the background model: bg[3,H,W] = sky(coef[9][3]) for a camera; dcoef[9][3] += sum_p Y(dir_p) dbg[:, p]
+GS_EXPORT int gstrain_test_sky_eval(const dvs_camera* cam, const float* coef, float* bg, void* stream) {
+    sky_eval_kernel<<<148 * 4, 256, 0, static_cast<cudaStream_t>(stream)>>>(sky_cam(*cam), coef, bg);
+    return (int)cudaGetLastError();
+}
+GS_EXPORT int gstrain_test_sky_grad(const dvs_camera* cam, const float* dbg, float* dcoef, void* stream) {
+    sky_grad_kernel<<<148 * 2, 256, 0, static_cast<cudaStream_t>(stream)>>>(sky_cam(*cam), dbg, dcoef);
+    return (int)cudaGetLastError();
 }
 // float offsets of the six tensors inside an arena of `capacity` rows (arena order), for tests and tools
 GS_EXPORT void gstrain_arena_offsets(int64_t capacity, int64_t out[6]) {
