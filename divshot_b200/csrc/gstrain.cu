@@ -431,6 +431,9 @@ struct DpComm {
     int (*CommDestroy)(comm_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
     static constexpr int kFloat32 = 7, kSum = 0;  // ncclFloat32, ncclSum (stable across NCCL 2.x)
+    // DVS_DP_TIMING=1: device time of every gradient exchange (CUDA events, resolved when the scene is destroyed)
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
 
     static int env_int(const char* a, const char* b, int dflt) {
         const char* v = std::getenv(a);
@@ -442,6 +445,7 @@ struct DpComm {
         rank = env_int("DVS_RANK", "RANK", 0);
         local = env_int("DVS_LOCAL_RANK", "LOCAL_RANK", rank);
         if (rank < 0 || rank >= world) throw std::runtime_error("gstrain: rank outside [0, world size)");
+        timing = std::getenv("DVS_DP_TIMING") != nullptr;
     }
     void nccl(int rc, const char* what) const {
         if (rc != 0) throw std::runtime_error(std::string("gstrain: ") + what + ": " + (GetErrorString ? GetErrorString(rc) : "NCCL error"));
@@ -497,14 +501,37 @@ struct DpComm {
         }
     }
     // in-place sum over ranks of several device ranges, one NCCL group (one fused launch)
-    void all_reduce_sum(std::initializer_list<std::pair<float*, size_t>> ranges, cudaStream_t st) const {
+    void all_reduce_sum(std::initializer_list<std::pair<float*, size_t>> ranges, cudaStream_t st, bool time_it = false) {
         if (world <= 1) return;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (timing && time_it && timed.size() < 4096) {
+            cudaEventCreate(&e0); cudaEventCreate(&e1);
+            cudaEventRecord(e0, st);
+        }
         nccl(GroupStart(), "ncclGroupStart");
         for (auto& r : ranges)
             if (r.second) nccl(AllReduce(r.first, r.first, r.second, kFloat32, kSum, comm, st), "ncclAllReduce");
         nccl(GroupEnd(), "ncclGroupEnd");
+        if (e0) {
+            cudaEventRecord(e1, st);
+            timed.emplace_back(e0, e1);
+        }
+    }
+    void report_timing() {
+        if (timed.empty()) return;
+        cudaDeviceSynchronize();
+        double sum = 0.0; size_t n = 0;
+        for (size_t k = timed.size() / 4; k < timed.size(); k++) {  // the first quarter is warm-up
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, timed[k].first, timed[k].second) == cudaSuccess) { sum += ms; n++; }
+        }
+        for (auto& p : timed) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+        timed.clear();
+        if (n) std::fprintf(stderr, "gstrain: rank %d: gradient exchange %.3f ms per step (device time incl. waiting for the slowest rank, %zu steps)\n",
+                            rank, sum / (double)n, n);
     }
     void destroy() {
+        report_timing();
         if (comm && CommDestroy) CommDestroy(comm);
         comm = nullptr;
         if (lib) dlclose(lib);
@@ -1015,7 +1042,7 @@ void GaussianTrainerScene::trainStep() {
     if (world > 1) {
         const size_t n = (size_t)I.N;
         I.dp.all_reduce_sum({{I.grads.quats(), 4 * n}, {I.grads.shN(), (size_t)3 * KR * n}, {I.grads.means(), 3 * n},
-                             {I.grads.scales(), 3 * n}, {I.grads.sh0(), 3 * n}, {I.grads.opac(), n}}, I.stream);
+                             {I.grads.scales(), 3 * n}, {I.grads.sh0(), 3 * n}, {I.grads.opac(), n}}, I.stream, true);
     }
     if (world > 1 && config_.enableBg) I.dp.all_reduce_sum({{I.d_sky + 3 * SKY_K, (size_t)3 * SKY_K}}, I.stream);
     if (refining && mcmc)  // L1 regularisers of the MCMC strategy: 0.01 mean(opacity) + 0.01 mean(scale), once per step
