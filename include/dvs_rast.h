@@ -294,7 +294,7 @@ typedef struct dvs_coll_fused {
     int64_t ranges[3][2];       /* [begin, end) of the ranges reduced in the switch (empty ranges allowed) */
     uint64_t launch_index;
     int32_t rank, world, sh_degree, sh_rest_alloc;
-    int32_t ctas, reduce_ctas;  /* <= 0: defaults (one CTA per SM; a third of them issue the in-switch reduction first) */
+    int32_t ctas, reduce_ctas;  /* <= 0: defaults (one CTA per SM; a sixth of them issue the in-switch reduction first) */
 } dvs_coll_fused;
 DVS_API int dvs_coll_exchange_fused(const dvs_coll_fused* args, void* stream);
 /* grid size dvs_coll_exchange_fused will use on the current device for `ctas` and `world` ranks (the co-residency bound applied) */
