@@ -134,29 +134,31 @@ __device__ __forceinline__ void cross_rank_barrier(const dvs_coll_fused& a, uint
     __syncthreads();
 }
 
+__device__ __forceinline__ float4 ld_peer_f4(const float* p) {
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
 // step 3a for the FX_THREADS Gaussians [base, base + cnt): the CTA copies the dL/dsh0 rows of its tile from EVERY rank's arena
-// into shared memory — the tile is one contiguous, 16-byte aligned span of 12 cnt bytes per rank, moved by 16-byte
-// ASYNCHRONOUS copies (cp.async.cg / LDGSTS: peer memory -> shared, no registers, L1 bypassed; a row-wise 3 x 32-bit read
-// would fetch every 32-byte sector three times over NVLink).  The copies of tile t+1 are issued before tile t is processed, so
-// the NVLink round trip (several microseconds) hides behind the arithmetic and the HBM stores of the current tile.
-__device__ __forceinline__ void cp_async16_peer(float* smem_dst, const float* gmem_src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
-                 "l"(__cvta_generic_to_global(gmem_src))
-                 : "memory");
-}
-__device__ __forceinline__ void fused_tile_issue(const dvs_coll_fused& a, float* stage, int tid, long long base, int cnt) {
-    const size_t row0 = (size_t)a.off_sh0 + 3 * (size_t)base;
-    const int n_vec = (3 * cnt) >> 2;
-    if (tid < n_vec)
-        for (int v = 0; v < a.world; v++)
-            cp_async16_peer(stage + (size_t)v * (3 * FX_THREADS) + 4 * tid, a.arena_peers[v] + row0 + 4 * (size_t)tid);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-}
-// (after the tile's asynchronous copies have landed) the words of a partial last tile that do not fill a 16-byte vector
-__device__ __forceinline__ void fused_tile_tail(const dvs_coll_fused& a, float* stage, int tid, long long base, int cnt) {
+// into shared memory — the tile is one contiguous, 16-byte aligned span of 12 cnt bytes per rank, read as 128-bit peer loads
+// (a row-wise 3 x 32-bit read would fetch every 32-byte sector three times over NVLink), up to eight ranks' loads in flight per
+// thread before the first is consumed.  (A/B, 8 ranks, c3: the same copies as 16-byte cp.async / LDGSTS peer reads with two
+// staging buffers — next tile in flight while the current one is processed — took 0.47 ms instead of 0.33 ms: asynchronous
+// copies from PEER memory are slow on this platform; profiles/r2_d_bench_n8_cpasync_rejected.json.)
+__device__ __forceinline__ void fused_tile_stage(const dvs_coll_fused& a, float* stage, int tid, long long base, int cnt) {
     const size_t row0 = (size_t)a.off_sh0 + 3 * (size_t)base;
     const int n_words = 3 * cnt, n_vec = n_words >> 2;
-    for (int w = (n_vec << 2) + tid; w < n_words; w += FX_THREADS)
+    for (int v0 = 0; v0 < a.world; v0 += 8) {
+        float4 r[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+            if (v0 + u < a.world && tid < n_vec) r[u] = ld_peer_f4(a.arena_peers[v0 + u] + row0 + 4 * (size_t)tid);
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+            if (v0 + u < a.world && tid < n_vec) reinterpret_cast<float4*>(stage + (size_t)(v0 + u) * (3 * FX_THREADS))[tid] = r[u];
+    }
+    for (int w = (n_vec << 2) + tid; w < n_words; w += FX_THREADS)  // the last, partial tile only
         for (int v = 0; v < a.world; v++) stage[(size_t)v * (3 * FX_THREADS) + w] = ld_peer_f32(a.arena_peers[v] + row0 + w);
 }
 // step 3b: thread `tid` accumulates its Gaussian's dL/dshN row into the shared rows and the summed dL/dsh0 into sh0_tmp
@@ -225,54 +227,19 @@ fused_exchange_kernel(const dvs_coll_fused a) {
         const dvs_shx::ExchangeArgs x{a.means, a.campos, nullptr, (long long)a.N, a.world, a.sh_degree,
                                       3 * a.sh_rest_alloc, out, (reinterpret_cast<uintptr_t>(out) & 15u) == 0 ? 1 : 0};
         const long long n_tiles = (a.N + FX_THREADS - 1) / FX_THREADS;
-        // two staging buffers when they fit (<= 8 ranks): tile t+1 streams in while tile t is processed
-        const bool dbl = a.world <= 8;
-        const size_t stage_words = (size_t)a.world * (3 * FX_THREADS);
-        auto grab = [&]() -> long long {  // next tile index for the whole CTA (>= n_tiles: none left)
-            __syncthreads();              // (everybody has read the previous value)
+        for (;;) {
             if (threadIdx.x == 0) s_tile = (long long)atomicAdd(a.grid_counter + 1, 1u);
             __syncthreads();
-            return s_tile;
-        };
-        auto span = [&](long long tile, long long& base, int& cnt) {
-            base = tile * FX_THREADS;
-            cnt = (int)(a.N - base < FX_THREADS ? a.N - base : FX_THREADS);
-        };
-        long long tile = grab(), base = 0;
-        int cnt = 0, buf = 0;
-        if (tile < n_tiles) {
-            span(tile, base, cnt);
-            fused_tile_issue(a, s_stage, threadIdx.x, base, cnt);
-        }
-        while (tile < n_tiles) {
-            float* cur = s_stage + (dbl ? (size_t)buf * stage_words : 0);
-            long long next = n_tiles, nbase = 0;
-            int ncnt = 0;
-            if (dbl) {  // issue the next tile's copies into the other buffer, then wait for the current tile's only
-                next = grab();
-                if (next < n_tiles) {
-                    span(next, nbase, ncnt);
-                    fused_tile_issue(a, s_stage + (size_t)(buf ^ 1) * stage_words, threadIdx.x, nbase, ncnt);
-                    asm volatile("cp.async.wait_group 1;" ::: "memory");
-                } else {
-                    asm volatile("cp.async.wait_group 0;" ::: "memory");
-                }
-            } else {
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-            }
-            fused_tile_tail(a, cur, threadIdx.x, base, cnt);
+            const long long tile = s_tile;
+            if (tile >= n_tiles) break;
+            const long long base = tile * FX_THREADS;
+            const int cnt = (int)(a.N - base < FX_THREADS ? a.N - base : FX_THREADS);
+            fused_tile_stage(a, s_stage, threadIdx.x, base, cnt);
             __syncthreads();
-            fused_tile_compute(a, cur, s_rows, threadIdx.x, base, cnt);
+            fused_tile_compute(a, s_stage, s_rows, threadIdx.x, base, cnt);
             __syncthreads();
             if (a.sh_rest_alloc > 0) dvs_shx::exchange_store(x, s_rows, threadIdx.x, FX_THREADS, base, cnt);
-            if (!dbl) {
-                next = grab();
-                if (next < n_tiles) {
-                    span(next, nbase, ncnt);
-                    fused_tile_issue(a, s_stage, threadIdx.x, nbase, ncnt);
-                }
-            }
-            tile = next; base = nbase; cnt = ncnt; buf ^= 1;
+            __syncthreads();
         }
     }
     // ---- 4. every shard has been re-broadcast and nobody reads this rank's per-view dL/dsh0 any more
@@ -287,10 +254,7 @@ fused_exchange_kernel(const dvs_coll_fused a) {
     }
 }
 
-size_t fused_smem(int world) {  // dL/dshN rows + one (more than 8 ranks) or two staging buffers of `world` x FX_THREADS dL/dsh0 rows
-    const size_t w = (size_t)(world > 0 ? world : 1);
-    return (size_t)FX_THREADS * (FX_ROW_WORDS + 3 * w * (w <= 8 ? 2 : 1)) * sizeof(float);
-}
+size_t fused_smem(int world) { return (size_t)FX_THREADS * (FX_ROW_WORDS + 3 * (size_t)(world > 0 ? world : 1)) * sizeof(float); }
 
 int fused_grid(int ctas, int world) {
     int dev = 0, sms = 148, per_sm = 0;
@@ -329,8 +293,8 @@ extern "C" DVS_API int dvs_coll_exchange_fused(const dvs_coll_fused* args, void*
     const int grid = fused_grid(a.ctas, a.world);
     if (grid < 1) return DVS_E_CUDA;
     a.ctas = grid;
-    if (a.reduce_ctas <= 0) a.reduce_ctas = grid / 6;      // enough requests in flight for the switch (measured: 24 of 148 CTAs
-                                                           // beat 49 and 74 at 8 ranks); they join step 3 afterwards
+    if (a.reduce_ctas <= 0) a.reduce_ctas = grid / 6;      // enough requests in flight for the switch (measured at 8 ranks: 24 of
+                                                           // 148 CTAs 0.326 ms, 49: 0.335 ms); they join step 3 afterwards
     if (a.reduce_ctas > grid) a.reduce_ctas = grid;
     if (a.reduce_ctas < 1) a.reduce_ctas = 1;
     const size_t smem = fused_smem(a.world);

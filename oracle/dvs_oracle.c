@@ -729,3 +729,261 @@ void orc_preprocess_bwd(const orc_camera* cam, int32_t N, const float* means3D, 
         }
     }
 }
+
+/* =====================================================================================================================
+ * 2DGS ("surfel") variant — GaussianTrainConfig::modelType = 1 (application/diverseshot-cli/source/main.cpp:28,
+ * gs_train.cpp:68, docs/userGuide.md:38).  TEST INFRASTRUCTURE like the rest of this file.
+ *
+ * PARITY UNPINNED: DIVSHOT's 2DGS rasterizer is in the same closed plugin as the 3DGS one.  This
+ * restates the published algorithm the option is named after — "2D Gaussian Splatting for Geometrically Accurate Radiance
+ * Fields" (Huang et al., SIGGRAPH 2024) and its public rasterizer's semantics:
+ *   S.1 a Gaussian is a flat disk: tangents t_u = R[:,0], t_v = R[:,1] with scales (s_u, s_v) (the third scale is
+ *       ignored), normal R[:,2].  The homography of the splat's local (u, v, 1) to homogeneous PIXEL coordinates is
+ *           M = Npix * Proj * [ s_u t_u | s_v t_v | p ; 0 0 1 ],   rows Tu, Tv, Tw  (x_h, y_h, w_h),
+ *       Npix = [[W/2, 0, 0, (W-1)/2], [0, H/2, 0, (H-1)/2], [0, 0, 0, 1]] (the same pixel-centre map as ndc2Pix).
+ *       Screen bounds from M (3-sigma): tp = (9, 9, -1), dist = sum tp_j Tw_j^2 (0 -> invisible), f = tp / dist,
+ *       centre c = (sum f Tu Tw, sum f Tv Tw), half extent e = sqrt(max(1e-4, c^2 - (sum f Tu^2, sum f Tv^2))),
+ *       radius = ceil(max(e_x, e_y, 3 * 0.707106)); tile rect, depth key (view z), cull (z <= 0.2) and colour as 3DGS.
+ *   S.2 per pixel (x, y) and splat: k = x Tw - Tu, l = y Tw - Tv, pv = k x l (pv.z == 0 -> skip), (u, v) = pv.xy / pv.z,
+ *       rho3d = u^2 + v^2; object-space low-pass: rho2d = 2 |c - (x, y)|^2; rho = min(rho3d, rho2d);
+ *       depth = rho3d <= rho2d ? u Tw.x + v Tw.y + Tw.z : Tw.z (< 0.2 -> skip); alpha = min(0.99, o exp(-rho / 2));
+ *       then exactly the 3DGS compositing rules (alpha < 1/255 skip, T < 1e-4 stop, n_contrib, final_T).
+ *   S.3 / S.4 analytic backward to M (9), c (2), opacity, colour and on to the stored parameters; decisions carry no
+ *       gradient, the 0.99 clamp is straight-through.
+ * Pinned by tests/autograd_ref_2dgs.py (float64 autograd of S.1-S.2) and closed-form cases (tests/test_oracle_2dgs.py).
+ * ===================================================================================================================== */
+#define SRF_FILTER_INV_SQ 2.0f
+#define SRF_FILTER_3SIGMA (3.0f * 0.707106f)
+
+/* homography rows from the activated surfel: T[0..2] = Tu, T[3..5] = Tv, T[6..8] = Tw (index j: u, v, 1) */
+static inline void srf_transmat(const orc_camera* cam, const float* p, const float s[3], float R[3][3], float T[9]) {
+    const float hw = 0.5f * (float)cam->width, hh = 0.5f * (float)cam->height;
+    const float ow = 0.5f * (float)(cam->width - 1), oh = 0.5f * (float)(cam->height - 1);
+    for (int j = 0; j < 3; j++) {
+        float v[3], w1;
+        if (j < 2) { for (int a = 0; a < 3; a++) v[a] = R[a][j] * s[j]; w1 = 0.0f; }
+        else { v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; w1 = 1.0f; }
+        const float* m = cam->proj;
+        const float cx = fmaf(m[0], v[0], fmaf(m[4], v[1], fmaf(m[8], v[2], m[12] * w1)));
+        const float cy = fmaf(m[1], v[0], fmaf(m[5], v[1], fmaf(m[9], v[2], m[13] * w1)));
+        const float cw = fmaf(m[3], v[0], fmaf(m[7], v[1], fmaf(m[11], v[2], m[15] * w1)));
+        T[j] = fmaf(hw, cx, ow * cw);
+        T[3 + j] = fmaf(hh, cy, oh * cw);
+        T[6 + j] = cw;
+    }
+}
+
+void orc2_preprocess_fwd(const orc_camera* cam, int32_t N, const float* means3D, const float* scales,
+                         const float* quats, const float* opacities, const float* sh0, const float* shN,
+                         float* depth, int32_t* radii, float* mean2D, float* transmat /*[N,9]*/, float* opacity_act,
+                         float* rgb, uint8_t* clamped, uint32_t* tiles_touched, int32_t* rect) {
+    const int gx = (cam->width + TILE - 1) / TILE, gy = (cam->height + TILE - 1) / TILE;
+    const int deg = cam->sh_degree, K = (deg + 1) * (deg + 1), KR = cam->sh_rest_alloc;
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < N; i++) {
+        radii[i] = 0; tiles_touched[i] = 0; depth[i] = 0.0f; opacity_act[i] = 0.0f;
+        mean2D[2 * i] = mean2D[2 * i + 1] = 0.0f;
+        for (int k = 0; k < 9; k++) transmat[9 * i + k] = 0.0f;
+        for (int k = 0; k < 4; k++) rect[4 * i + k] = 0;
+        for (int k = 0; k < 3; k++) { rgb[3 * i + k] = 0.0f; clamped[3 * i + k] = 0; }
+        const float* p = means3D + 3 * (size_t)i;
+        float t[3];
+        xform43(cam->view, p, t);
+        if (t[2] <= 0.2f) continue;
+        act_t a; activate(cam, scales, quats, opacities, i, &a);
+        float R[3][3], T[9];
+        quat_to_R(a.q, R);
+        srf_transmat(cam, p, a.s, R, T);
+        const float tp[3] = {9.0f, 9.0f, -1.0f};
+        const float dist = fmaf(tp[0] * T[6], T[6], fmaf(tp[1] * T[7], T[7], tp[2] * T[8] * T[8]));
+        if (dist == 0.0f) continue;
+        const float f[3] = {tp[0] / dist, tp[1] / dist, tp[2] / dist};
+        const float cx = fmaf(f[0] * T[0], T[6], fmaf(f[1] * T[1], T[7], f[2] * T[2] * T[8]));
+        const float cy = fmaf(f[0] * T[3], T[6], fmaf(f[1] * T[4], T[7], f[2] * T[5] * T[8]));
+        const float qx = fmaf(f[0] * T[0], T[0], fmaf(f[1] * T[1], T[1], f[2] * T[2] * T[2]));
+        const float qy = fmaf(f[0] * T[3], T[3], fmaf(f[1] * T[4], T[4], f[2] * T[5] * T[5]));
+        const float ex = sqrtf(fmaxf(1e-4f, fmaf(cx, cx, -qx))), ey = sqrtf(fmaxf(1e-4f, fmaf(cy, cy, -qy)));
+        const float rad_f = ceilf(fmaxf(fmaxf(ex, ey), SRF_FILTER_3SIGMA));
+        if (!(rad_f < 1.0e9f)) continue; /* degenerate homography (NaN / inf extent) */
+        const int32_t rad = f2i_rz(rad_f);
+        const float radf = (float)rad;
+        const int32_t minx = imin(gx, imax(0, f2i_rz((cx - radf) * 0.0625f)));
+        const int32_t miny = imin(gy, imax(0, f2i_rz((cy - radf) * 0.0625f)));
+        const int32_t maxx = imin(gx, imax(0, f2i_rz((cx + radf + 15.0f) * 0.0625f)));
+        const int32_t maxy = imin(gy, imax(0, f2i_rz((cy + radf + 15.0f) * 0.0625f)));
+        const int64_t area = (int64_t)(maxx - minx) * (int64_t)(maxy - miny);
+        if (area <= 0) continue;
+        float dir[3] = {p[0] - cam->campos[0], p[1] - cam->campos[1], p[2] - cam->campos[2]};
+        const float len = sqrtf(fmaf(dir[0], dir[0], fmaf(dir[1], dir[1], dir[2] * dir[2])));
+        const float linv = 1.0f / len;
+        dir[0] *= linv; dir[1] *= linv; dir[2] *= linv;
+        float bas[16]; sh_basis(deg, dir, bas);
+        for (int ch = 0; ch < 3; ch++) {
+            float acc = bas[0] * sh0[3 * (size_t)i + ch];
+            for (int k = 1; k < K; k++) acc = fmaf(bas[k], shN[3 * ((size_t)i * KR + (k - 1)) + ch], acc);
+            acc += 0.5f;
+            clamped[3 * i + ch] = acc < 0.0f;
+            rgb[3 * i + ch] = fmaxf(acc, 0.0f);
+        }
+        depth[i] = t[2];
+        radii[i] = rad;
+        mean2D[2 * i] = cx; mean2D[2 * i + 1] = cy;
+        for (int k = 0; k < 9; k++) transmat[9 * i + k] = T[k];
+        opacity_act[i] = a.o;
+        tiles_touched[i] = (uint32_t)area;
+        rect[4 * i] = minx; rect[4 * i + 1] = miny; rect[4 * i + 2] = maxx; rect[4 * i + 3] = maxy;
+    }
+}
+
+/* one (pixel, surfel) evaluation of S.2; returns 0 if the pair is skipped before the alpha test */
+typedef struct { float u, v, pz, rho3d, rho2d, dx, dy, G, alpha; float k[3], l[3]; int use3d; } srf_pair_t;
+static inline int srf_pair(const float* T, float cx, float cy, float o, float pxf, float pyf, srf_pair_t* r) {
+    for (int j = 0; j < 3; j++) { r->k[j] = fmaf(pxf, T[6 + j], -T[j]); r->l[j] = fmaf(pyf, T[6 + j], -T[3 + j]); }
+    const float p0 = fmaf(r->k[1], r->l[2], -(r->k[2] * r->l[1]));
+    const float p1 = fmaf(r->k[2], r->l[0], -(r->k[0] * r->l[2]));
+    const float p2 = fmaf(r->k[0], r->l[1], -(r->k[1] * r->l[0]));
+    if (p2 == 0.0f) return 0;
+    r->pz = p2; r->u = p0 / p2; r->v = p1 / p2;
+    r->rho3d = fmaf(r->u, r->u, r->v * r->v);
+    r->dx = cx - pxf; r->dy = cy - pyf;
+    r->rho2d = SRF_FILTER_INV_SQ * fmaf(r->dx, r->dx, r->dy * r->dy);
+    r->use3d = r->rho3d <= r->rho2d;
+    const float rho = r->use3d ? r->rho3d : r->rho2d;
+    const float dep = r->use3d ? fmaf(r->u, T[6], fmaf(r->v, T[7], T[8])) : T[8];
+    if (dep < 0.2f) return 0;
+    r->G = expf(-0.5f * rho);
+    r->alpha = fminf(0.99f, o * r->G);
+    return 1;
+}
+
+void orc2_render_fwd(const orc_camera* cam, const uint32_t* ranges, const uint32_t* point_list, const float* mean2D,
+                     const float* transmat, const float* opacity_act, const float* rgb, float* out_color,
+                     float* final_T, uint32_t* n_contrib, uint8_t* fragile, int32_t threads) {
+    const int W = cam->width, H = cam->height;
+    const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+    const size_t P = (size_t)W * H;
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int tile = 0; tile < gx * gy; tile++) {
+        const uint32_t r0 = ranges[2 * tile], r1 = ranges[2 * tile + 1];
+        const int tx0 = (tile % gx) * TILE, ty0 = (tile / gx) * TILE;
+        for (int ly = 0; ly < TILE; ly++)
+            for (int lx = 0; lx < TILE; lx++) {
+                const int px = tx0 + lx, py = ty0 + ly;
+                if (px >= W || py >= H) continue;
+                float T = 1.0f, C[3] = {0, 0, 0};
+                uint32_t contributor = 0, last = 0;
+                uint8_t frag = 0;
+                for (uint32_t j = r0; j < r1; j++) {
+                    contributor++;
+                    const uint32_t g = point_list[j];
+                    srf_pair_t q;
+                    if (!srf_pair(transmat + 9 * (size_t)g, mean2D[2 * g], mean2D[2 * g + 1], opacity_act[g], (float)px, (float)py, &q))
+                        continue;
+                    const float araw = opacity_act[g] * q.G;
+                    if (fabsf(araw - (1.0f / 255.0f)) <= (1.0f / 255.0f) * 1e-4f) frag = 1;
+                    if (fabsf(q.rho3d - q.rho2d) <= 1e-5f * fmaxf(q.rho3d, q.rho2d)) frag = 1;
+                    if (q.alpha < 1.0f / 255.0f) continue;
+                    const float test_T = T * (1.0f - q.alpha);
+                    if (fabsf(test_T - 1e-4f) <= 1e-4f * 2e-3f) frag = 1;
+                    if (test_T < 1e-4f) break;
+                    const float w = q.alpha * T;
+                    C[0] += rgb[3 * g] * w; C[1] += rgb[3 * g + 1] * w; C[2] += rgb[3 * g + 2] * w;
+                    T = test_T;
+                    last = contributor;
+                }
+                const size_t pix = (size_t)py * W + px;
+                final_T[pix] = T;
+                n_contrib[pix] = last;
+                if (fragile) fragile[pix] = frag;
+                for (int ch = 0; ch < 3; ch++) out_color[ch * P + pix] = C[ch] + T * cam->bg[ch];
+            }
+    }
+}
+
+/* S.3: reverse walk; per-surfel sums in double (see atomic_addd).  Outputs zeroed then accumulated:
+ * dL_dT [N,9], dL_dmean2D [N,2] (pixel units, NOT ndc-scaled), dL_dopacity [N] (w.r.t. the activated opacity), dL_dcolor [N,3] */
+void orc2_render_bwd(const orc_camera* cam, int32_t N, const uint32_t* ranges, const uint32_t* point_list,
+                     const float* mean2D, const float* transmat, const float* opacity_act, const float* rgb,
+                     const float* final_T, const uint32_t* n_contrib, const float* dL_dpix, float* dL_dT,
+                     float* dL_dmean2D, float* dL_dopacity, float* dL_dcolor, int32_t threads) {
+    const int W = cam->width, H = cam->height;
+    const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+    const size_t P = (size_t)W * H;
+    double* acc = (double*)calloc((size_t)(N > 0 ? N : 1) * 15, sizeof(double));
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int tile = 0; tile < gx * gy; tile++) {
+        const uint32_t r0 = ranges[2 * tile], r1 = ranges[2 * tile + 1];
+        const int tx0 = (tile % gx) * TILE, ty0 = (tile / gx) * TILE;
+        for (int ly = 0; ly < TILE; ly++)
+            for (int lx = 0; lx < TILE; lx++) {
+                const int px = tx0 + lx, py = ty0 + ly;
+                if (px >= W || py >= H) continue;
+                const size_t pix = (size_t)py * W + px;
+                const float pxf = (float)px, pyf = (float)py;
+                const float T_final = final_T[pix];
+                float T = T_final;
+                const uint32_t last = n_contrib[pix];
+                const float dp[3] = {dL_dpix[pix], dL_dpix[P + pix], dL_dpix[2 * P + pix]};
+                float accum[3] = {0, 0, 0}, last_alpha = 0.0f, last_color[3] = {0, 0, 0};
+                for (uint32_t j = r1; j-- > r0;) {
+                    const uint32_t contributor = j - r0; /* 0-based index of the entry */
+                    if (contributor >= last) continue;
+                    const uint32_t g = point_list[j];
+                    const float* Tm = transmat + 9 * (size_t)g;
+                    srf_pair_t q;
+                    if (!srf_pair(Tm, mean2D[2 * g], mean2D[2 * g + 1], opacity_act[g], pxf, pyf, &q)) continue;
+                    if (q.alpha < 1.0f / 255.0f) continue;
+                    T = T / (1.0f - q.alpha);
+                    float dL_dalpha = 0.0f;
+                    double* A = acc + 15 * (size_t)g;
+                    for (int ch = 0; ch < 3; ch++) {
+                        const float c = rgb[3 * g + ch];
+                        accum[ch] = last_alpha * last_color[ch] + (1.0f - last_alpha) * accum[ch];
+                        last_color[ch] = c;
+                        dL_dalpha += (c - accum[ch]) * dp[ch];
+                        atomic_addd(A + 12 + ch, (double)(q.alpha * T * dp[ch]));
+                    }
+                    dL_dalpha *= T;
+                    last_alpha = q.alpha;
+                    float bg_dot = 0.0f;
+                    for (int ch = 0; ch < 3; ch++) bg_dot += cam->bg[ch] * dp[ch];
+                    dL_dalpha += (-T_final / (1.0f - q.alpha)) * bg_dot;
+                    const float dL_dG = opacity_act[g] * dL_dalpha;
+                    atomic_addd(A + 11, (double)(q.G * dL_dalpha));
+                    if (q.use3d) {
+                        /* G = exp(-(u^2 + v^2) / 2): dL/du = -G u dL/dG; (u, v) = pv.xy / pv.z, pv = k x l */
+                        const float dLu = dL_dG * -q.G * q.u, dLv = dL_dG * -q.G * q.v;
+                        const float dsx = dLu / q.pz, dsy = dLv / q.pz;
+                        const float dpv[3] = {dsx, dsy, -(dsx * q.u + dsy * q.v)};
+                        /* pv = k x l: dL/dk = l x dpv, dL/dl = dpv x k */
+                        const float dk[3] = {q.l[1] * dpv[2] - q.l[2] * dpv[1], q.l[2] * dpv[0] - q.l[0] * dpv[2],
+                                             q.l[0] * dpv[1] - q.l[1] * dpv[0]};
+                        const float dl[3] = {dpv[1] * q.k[2] - dpv[2] * q.k[1], dpv[2] * q.k[0] - dpv[0] * q.k[2],
+                                             dpv[0] * q.k[1] - dpv[1] * q.k[0]};
+                        for (int c = 0; c < 3; c++) {
+                            atomic_addd(A + c, (double)(-dk[c]));                          /* k = x Tw - Tu */
+                            atomic_addd(A + 3 + c, (double)(-dl[c]));                      /* l = y Tw - Tv */
+                            atomic_addd(A + 6 + c, (double)(pxf * dk[c] + pyf * dl[c]));
+                        }
+                    } else {
+                        /* G = exp(-|c - pix|^2): low-pass branch, gradient to the projected centre */
+                        atomic_addd(A + 9, (double)(dL_dG * -q.G * SRF_FILTER_INV_SQ * q.dx));
+                        atomic_addd(A + 10, (double)(dL_dG * -q.G * SRF_FILTER_INV_SQ * q.dy));
+                    }
+                }
+            }
+    }
+    for (size_t i = 0; i < (size_t)N; i++) {
+        for (int k = 0; k < 9; k++) dL_dT[9 * i + k] = (float)acc[15 * i + k];
+        dL_dmean2D[2 * i] = (float)acc[15 * i + 9]; dL_dmean2D[2 * i + 1] = (float)acc[15 * i + 10];
+        dL_dopacity[i] = (float)acc[15 * i + 11];
+        for (int k = 0; k < 3; k++) dL_dcolor[3 * i + k] = (float)acc[15 * i + 12 + k];
+    }
+    free(acc);
+}
