@@ -987,3 +987,128 @@ void orc2_render_bwd(const orc_camera* cam, int32_t N, const uint32_t* ranges, c
     }
     free(acc);
 }
+
+/* S.4: per-surfel backward to the stored parameters (double arithmetic like orc_preprocess_bwd).  Inputs: dL/dT [N,9],
+ * dL/dmean2D [N,2] (pixel units), dL/dopacity (activated), dL/dcolor.  The third scale receives no gradient. */
+void orc2_preprocess_bwd(const orc_camera* cam, int32_t N, const float* means3D, const float* scales,
+                         const float* quats, const float* opacities, const float* sh0, const float* shN,
+                         const int32_t* radii, const uint8_t* clamped, const float* dL_dT, const float* dL_dmean2D,
+                         const float* dL_dopacity_act, const float* dL_dcolor, float* dL_dmeans3D,
+                         float* dL_dscales, float* dL_dquats, float* dL_dopacities, float* dL_dsh0, float* dL_dshN) {
+    const int deg = cam->sh_degree, K = (deg + 1) * (deg + 1), KR = cam->sh_rest_alloc;
+    const double hw = 0.5 * cam->width, hh = 0.5 * cam->height, ow = 0.5 * (cam->width - 1), oh = 0.5 * (cam->height - 1);
+    (void)sh0;
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < N; i++) {
+        for (int k = 0; k < 3; k++) { dL_dmeans3D[3 * i + k] = 0; dL_dscales[3 * i + k] = 0; dL_dsh0[3 * i + k] = 0; }
+        for (int k = 0; k < 4; k++) dL_dquats[4 * i + k] = 0;
+        dL_dopacities[i] = 0;
+        for (int k = 0; k < 3 * KR; k++) dL_dshN[3 * (size_t)KR * i + k] = 0;
+        if (radii[i] <= 0) continue;
+        const float* pf = means3D + 3 * (size_t)i;
+        const double p[3] = {pf[0], pf[1], pf[2]};
+        act_t a; activate(cam, scales, quats, opacities, i, &a);
+        float Rf[3][3], Tf[9];
+        quat_to_R(a.q, Rf);
+        srf_transmat(cam, pf, a.s, Rf, Tf);
+        double T[9], dT[9];
+        for (int k = 0; k < 9; k++) { T[k] = Tf[k]; dT[k] = dL_dT[9 * (size_t)i + k]; }
+        /* 1. projected centre -> T */
+        {
+            const double tp[3] = {9.0, 9.0, -1.0};
+            const double dist = tp[0] * T[6] * T[6] + tp[1] * T[7] * T[7] + tp[2] * T[8] * T[8];
+            double cx = 0, cy = 0, f[3];
+            for (int j = 0; j < 3; j++) { f[j] = tp[j] / dist; cx += f[j] * T[j] * T[6 + j]; cy += f[j] * T[3 + j] * T[6 + j]; }
+            const double gx_ = dL_dmean2D[2 * i], gy_ = dL_dmean2D[2 * i + 1];
+            for (int j = 0; j < 3; j++) {
+                dT[j] += gx_ * f[j] * T[6 + j];
+                dT[3 + j] += gy_ * f[j] * T[6 + j];
+                dT[6 + j] += gx_ * (f[j] * T[j] - 2.0 * cx * f[j] * T[6 + j]) + gy_ * (f[j] * T[3 + j] - 2.0 * cy * f[j] * T[6 + j]);
+            }
+        }
+        /* 2./3. T -> clip columns -> (L0, L1, p) through Proj^T */
+        double dvec[3][3];
+        for (int j = 0; j < 3; j++) {
+            const double dcx = hw * dT[j], dcy = hh * dT[3 + j], dcw = ow * dT[j] + oh * dT[3 + j] + dT[6 + j];
+            for (int r = 0; r < 3; r++)
+                dvec[j][r] = (double)cam->proj[4 * r + 0] * dcx + (double)cam->proj[4 * r + 1] * dcy + (double)cam->proj[4 * r + 3] * dcw;
+        }
+        double dmean[3] = {dvec[2][0], dvec[2][1], dvec[2][2]};
+        /* 4. SH: colour -> coefficients and -> direction -> mean (as orc_preprocess_bwd) */
+        {
+            const double dir_o[3] = {p[0] - cam->campos[0], p[1] - cam->campos[1], p[2] - cam->campos[2]};
+            const double len = sqrt(dir_o[0] * dir_o[0] + dir_o[1] * dir_o[1] + dir_o[2] * dir_o[2]);
+            const float df[3] = {(float)(dir_o[0] / len), (float)(dir_o[1] / len), (float)(dir_o[2] / len)};
+            const double d[3] = {dir_o[0] / len, dir_o[1] / len, dir_o[2] / len};
+            double dcol[3];
+            for (int ch = 0; ch < 3; ch++) dcol[ch] = clamped[3 * i + ch] ? 0.0 : (double)dL_dcolor[3 * i + ch];
+            float basf[16]; memset(basf, 0, sizeof basf);
+            sh_basis(deg, df, basf);
+            for (int ch = 0; ch < 3; ch++) dL_dsh0[3 * i + ch] = (float)((double)basf[0] * dcol[ch]);
+            for (int k = 1; k < K; k++)
+                for (int ch = 0; ch < 3; ch++) dL_dshN[3 * ((size_t)i * KR + (k - 1)) + ch] = (float)((double)basf[k] * dcol[ch]);
+            /* d basis / d direction by central differences of the float64 basis would be circular: analytic, as in A8 */
+            const double X = d[0], Y = d[1], Z = d[2];
+            double gb[16][3]; memset(gb, 0, sizeof gb);
+            if (deg >= 1) { gb[1][1] = -SH_C1; gb[2][2] = SH_C1; gb[3][0] = -SH_C1; }
+            if (deg >= 2) {
+                const double xx = X * X, yy = Y * Y, zz = Z * Z;
+                gb[4][0] = SH_C2[0] * Y; gb[4][1] = SH_C2[0] * X;
+                gb[5][1] = SH_C2[1] * Z; gb[5][2] = SH_C2[1] * Y;
+                gb[6][0] = SH_C2[2] * -2.0 * X; gb[6][1] = SH_C2[2] * -2.0 * Y; gb[6][2] = SH_C2[2] * 4.0 * Z;
+                gb[7][0] = SH_C2[3] * Z; gb[7][2] = SH_C2[3] * X;
+                gb[8][0] = SH_C2[4] * 2.0 * X; gb[8][1] = SH_C2[4] * -2.0 * Y;
+                if (deg >= 3) {
+                    gb[9][0] = SH_C3[0] * 6.0 * X * Y; gb[9][1] = SH_C3[0] * (3.0 * xx - 3.0 * yy);
+                    gb[10][0] = SH_C3[1] * Y * Z; gb[10][1] = SH_C3[1] * X * Z; gb[10][2] = SH_C3[1] * X * Y;
+                    gb[11][0] = SH_C3[2] * -2.0 * X * Y; gb[11][1] = SH_C3[2] * (4.0 * zz - xx - 3.0 * yy);
+                    gb[11][2] = SH_C3[2] * 8.0 * Y * Z;
+                    gb[12][0] = SH_C3[3] * -6.0 * X * Z; gb[12][1] = SH_C3[3] * -6.0 * Y * Z;
+                    gb[12][2] = SH_C3[3] * (6.0 * zz - 3.0 * xx - 3.0 * yy);
+                    gb[13][0] = SH_C3[4] * (4.0 * zz - 3.0 * xx - yy); gb[13][1] = SH_C3[4] * -2.0 * X * Y;
+                    gb[13][2] = SH_C3[4] * 8.0 * X * Z;
+                    gb[14][0] = SH_C3[5] * 2.0 * X * Z; gb[14][1] = SH_C3[5] * -2.0 * Y * Z; gb[14][2] = SH_C3[5] * (xx - yy);
+                    gb[15][0] = SH_C3[6] * (3.0 * xx - 3.0 * yy); gb[15][1] = SH_C3[6] * -6.0 * X * Y;
+                }
+            }
+            double ddir[3] = {0, 0, 0};
+            for (int k = 1; k < K; k++) {
+                double sk = 0.0;
+                for (int ch = 0; ch < 3; ch++) sk += (double)shN[3 * ((size_t)i * KR + (k - 1)) + ch] * dcol[ch];
+                ddir[0] += gb[k][0] * sk; ddir[1] += gb[k][1] * sk; ddir[2] += gb[k][2] * sk;
+            }
+            const double dd = d[0] * ddir[0] + d[1] * ddir[1] + d[2] * ddir[2];
+            for (int c = 0; c < 3; c++) dmean[c] += (ddir[c] - d[c] * dd) / len;
+        }
+        for (int c = 0; c < 3; c++) dL_dmeans3D[3 * i + c] = (float)dmean[c];
+        /* 5. (L0, L1) = (s_u R[:,0], s_v R[:,1]) -> scales, rotation; 6. activations */
+        {
+            const double s[3] = {a.s[0], a.s[1], a.s[2]};
+            const double q[4] = {a.q[0], a.q[1], a.q[2], a.q[3]};
+            const double r = q[0], x = q[1], y = q[2], z = q[3];
+            double ds[3] = {0, 0, 0}, dR[3][3];
+            for (int k = 0; k < 3; k++) for (int c = 0; c < 3; c++) dR[c][k] = 0.0;
+            for (int k = 0; k < 2; k++)
+                for (int c = 0; c < 3; c++) { ds[k] += (double)Rf[c][k] * dvec[k][c]; dR[c][k] = s[k] * dvec[k][c]; }
+            double dq[4];
+            dq[0] = 2.0 * (z * (dR[1][0] - dR[0][1]) + y * (dR[0][2] - dR[2][0]) + x * (dR[2][1] - dR[1][2]));
+            dq[1] = 2.0 * (y * (dR[0][1] + dR[1][0]) + z * (dR[0][2] + dR[2][0]) + r * (dR[2][1] - dR[1][2])) -
+                    4.0 * x * (dR[1][1] + dR[2][2]);
+            dq[2] = 2.0 * (x * (dR[0][1] + dR[1][0]) + r * (dR[0][2] - dR[2][0]) + z * (dR[1][2] + dR[2][1])) -
+                    4.0 * y * (dR[0][0] + dR[2][2]);
+            dq[3] = 2.0 * (r * (dR[1][0] - dR[0][1]) + x * (dR[0][2] + dR[2][0]) + y * (dR[1][2] + dR[2][1])) -
+                    4.0 * z * (dR[0][0] + dR[1][1]);
+            const double o = a.o;
+            if (cam->flags & ORC_FLAG_INPUT_ACTIVATED) {
+                for (int k = 0; k < 3; k++) dL_dscales[3 * i + k] = (float)(ds[k] * cam->scale_modifier);
+                for (int k = 0; k < 4; k++) dL_dquats[4 * i + k] = (float)dq[k];
+                dL_dopacities[i] = dL_dopacity_act[i];
+            } else {
+                for (int k = 0; k < 3; k++) dL_dscales[3 * i + k] = (float)(ds[k] * s[k]);
+                const double qd = q[0] * dq[0] + q[1] * dq[1] + q[2] * dq[2] + q[3] * dq[3];
+                for (int k = 0; k < 4; k++) dL_dquats[4 * i + k] = (float)((dq[k] - q[k] * qd) / (double)a.qlen);
+                dL_dopacities[i] = (float)((double)dL_dopacity_act[i] * o * (1.0 - o));
+            }
+        }
+    }
+}

@@ -98,6 +98,26 @@ void orc_preprocess_bwd(const orc_camera* cam, int32_t N,
                         float* dL_dmeans3D, float* dL_dscales, float* dL_dquats,
                         float* dL_dopacities, float* dL_dsh0, float* dL_dshN);
 
+/* ---- 2DGS ("surfel") variant, GaussianTrainConfig::modelType = 1 (spec: the S.1-S.4 comment in dvs_oracle.c).  Binning and
+ * sorting are shared with the 3DGS path (orc_scan_tiles, orc_bin_sort on depth / radii / rect). */
+void orc2_preprocess_fwd(const orc_camera* cam, int32_t N, const float* means3D, const float* scales,
+                         const float* quats, const float* opacities, const float* sh0, const float* shN,
+                         float* depth, int32_t* radii, float* mean2D /*[N,2]*/, float* transmat /*[N,9]: Tu, Tv, Tw*/,
+                         float* opacity_act /*[N]*/, float* rgb, uint8_t* clamped, uint32_t* tiles_touched, int32_t* rect);
+void orc2_render_fwd(const orc_camera* cam, const uint32_t* ranges, const uint32_t* point_list, const float* mean2D,
+                     const float* transmat, const float* opacity_act, const float* rgb, float* out_color,
+                     float* final_T, uint32_t* n_contrib, uint8_t* fragile, int32_t threads);
+void orc2_render_bwd(const orc_camera* cam, int32_t N, const uint32_t* ranges, const uint32_t* point_list,
+                     const float* mean2D, const float* transmat, const float* opacity_act, const float* rgb,
+                     const float* final_T, const uint32_t* n_contrib, const float* dL_dpix, float* dL_dT /*[N,9]*/,
+                     float* dL_dmean2D /*[N,2], pixel units*/, float* dL_dopacity /*[N]*/, float* dL_dcolor /*[N,3]*/,
+                     int32_t threads);
+void orc2_preprocess_bwd(const orc_camera* cam, int32_t N, const float* means3D, const float* scales,
+                         const float* quats, const float* opacities, const float* sh0, const float* shN,
+                         const int32_t* radii, const uint8_t* clamped, const float* dL_dT, const float* dL_dmean2D,
+                         const float* dL_dopacity_act, const float* dL_dcolor, float* dL_dmeans3D,
+                         float* dL_dscales, float* dL_dquats, float* dL_dopacities, float* dL_dsh0, float* dL_dshN);
+
 /* OpenMP thread count for all oracle stages (n <= 0: leave as is) */
 void orc_set_threads(int32_t n);
 
