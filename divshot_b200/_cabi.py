@@ -18,6 +18,7 @@ FLAG_DEFER_CHECK = 8
 FLAG_ANTIALIAS = 16
 FLAG_TIGHT_LISTS = 32
 FLAG_SKIP_SHN_GRAD = 64
+FLAG_MODEL_2DGS = 128
 NUM_STAGES = 8
 
 (BUF_RADII, BUF_TILES_TOUCHED, BUF_DEPTH, BUF_MEAN2D, BUF_CONIC_OPACITY, BUF_RGB, BUF_CLAMPED, BUF_POINT_LIST,

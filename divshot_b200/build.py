@@ -32,6 +32,7 @@ CU_SOURCES = {
     "aux_outputs.cu": [],
     "collective.cu": [],
     "sh_exchange.cu": [],
+    "surfel.cu": [],
 }
 
 

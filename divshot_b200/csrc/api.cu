@@ -37,6 +37,11 @@ struct dvs_rast_ctx {
     float4* rec = nullptr;
     uint4* aux = nullptr;
     float4* sgrad = nullptr;
+    // 2DGS (DVS_FLAG_MODEL_2DGS): 64-byte homography records and screen-gradient records, allocated on first use
+    int64_t cap_surfel = 0;
+    float4* rec2 = nullptr;
+    float4* sgrad2 = nullptr;
+    bool surfel_fwd = false;  // the last forward was a 2DGS one (the backward follows it)
     // per-tile
     int64_t cap_tiles = 0;
     uint32_t* tile_count = nullptr;
@@ -255,7 +260,7 @@ int dvs_rast_create(int device, dvs_rast_ctx** out) {
 void dvs_rast_destroy(dvs_rast_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->rec); cudaFree(ctx->aux); cudaFree(ctx->sgrad);
+    cudaFree(ctx->rec); cudaFree(ctx->aux); cudaFree(ctx->sgrad); cudaFree(ctx->rec2); cudaFree(ctx->sgrad2);
     cudaFree(ctx->tile_count); cudaFree(ctx->tile_base); cudaFree(ctx->tile_cursor); cudaFree(ctx->class_tiles); cudaFree(ctx->tile_order);
     cudaFree(ctx->bins); cudaFree(ctx->plist);
     cudaFree(ctx->final_T); cudaFree(ctx->n_contrib);
@@ -352,12 +357,19 @@ int dvs_rast_forward(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, const 
     if (N > 0) prm = Params{params->means3D, params->scales, params->quats, params->opacities, params->sh0, params->shN};
     ctx->have_fwd = false;
     ctx->st.overflow = 0;
+    const bool surfel = (cam->flags & DVS_FLAG_MODEL_2DGS) != 0;
+    if (surfel && ctx->cap_gauss > ctx->cap_surfel) {
+        CK(regrow(ctx->rec2, 4 * (size_t)ctx->cap_gauss));
+        CK(regrow(ctx->sgrad2, 4 * (size_t)ctx->cap_gauss));
+        CK(cudaMemset(ctx->sgrad2, 0, 4 * (size_t)ctx->cap_gauss * sizeof(float4)));
+        ctx->cap_surfel = ctx->cap_gauss;
+    }
     // single-pass binning: only in deferred-check mode, with a bin stride sized by an earlier synchronous forward
     // of the same tile grid (an overflowing bin is reported like an arena overflow: DVS_E_OVERFLOW, redo the step)
     // (DVS_TWO_PASS=1 in the environment forces two-pass binning: A/B measurements only)
     static const bool force_two_pass = getenv("DVS_TWO_PASS") != nullptr;
     const bool fused = defer && ctx->bin_stride > 0 && ctx->bin_stride_tiles == T &&
-                       (int64_t)ctx->bin_stride * T <= ctx->cap_bins && !force_two_pass;
+                       (int64_t)ctx->bin_stride * T <= ctx->cap_bins && !force_two_pass && !surfel;
     for (int attempt = 0; attempt < 3; attempt++) {
         uint32_t* counters = fused ? ctx->tile_cursor : ctx->tile_count;
         if (fused ? ctx->cursor_dirty : ctx->count_dirty)
@@ -370,7 +382,10 @@ int dvs_rast_forward(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, const 
         EV(0);
         const FusedEmit fe{ctx->tile_cursor, ctx->bins, fused ? ctx->bin_stride : 0u, ctx->info + 10,
                            (fused && (cam->flags & DVS_FLAG_TIGHT_LISTS)) ? 1u : 0u};
-        CK(launch_preprocess_fwd(c, (int)N, prm, ctx->rec, ctx->aux, ctx->tile_count, out_radii, ctx->stats, fe, st));
+        if (surfel)
+            CK(launch_surfel_preprocess_fwd(c, (int)N, prm, ctx->rec, ctx->rec2, ctx->aux, ctx->tile_count, out_radii, ctx->stats, st));
+        else
+            CK(launch_preprocess_fwd(c, (int)N, prm, ctx->rec, ctx->aux, ctx->tile_count, out_radii, ctx->stats, fe, st));
         EV(1);
         if (fused) {
             CK(launch_tile_scan((int)T, ctx->tile_cursor, ctx->tile_base, nullptr, ctx->info, (uint32_t)ctx->cap_dups,
@@ -390,9 +405,13 @@ int dvs_rast_forward(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, const 
         CK(launch_tile_sort((int)T, fused ? ctx->bin_stride : 0u, ctx->tile_base, ctx->bins, ctx->plist, ctx->info,
                             ctx->class_tiles, st));
         EV(4);
-        CK(launch_render_fwd(c, DVS_TILE_ORDER(ctx), ctx->tile_base, ctx->plist, ctx->rec, out_color, ctx->final_T, ctx->n_contrib,
-                             ctx->info, st));
+        if (surfel)
+            CK(launch_surfel_render_fwd(c, ctx->tile_base, ctx->plist, ctx->rec2, out_color, ctx->final_T, ctx->n_contrib, ctx->info, st));
+        else
+            CK(launch_render_fwd(c, DVS_TILE_ORDER(ctx), ctx->tile_base, ctx->plist, ctx->rec, out_color, ctx->final_T, ctx->n_contrib,
+                                 ctx->info, st));
         EV(5);
+        ctx->surfel_fwd = surfel;
         CK(cudaMemcpyAsync(ctx->h_info, ctx->info, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         if (defer) {  // no host synchronisation: validated later by resolve_pending()
             CK(cudaEventRecord(ctx->ev_check, st));
@@ -471,6 +490,15 @@ int dvs_rast_backward(dvs_rast_ctx* ctx, const dvs_params* params, const float* 
                   (flags & DVS_FLAG_ABSGRAD) ? grads->mean2D_abs : nullptr, grads->mean2D};
     }
     EV(6);
+    if (ctx->surfel_fwd) {  // the 2DGS forward's backward
+        CK(launch_surfel_render_bwd(c, ctx->tile_base, ctx->plist, ctx->rec2, ctx->final_T, ctx->n_contrib, dL_dpix,
+                                    reinterpret_cast<float*>(ctx->sgrad2), ctx->info, st));
+        EV(7);
+        CK(launch_surfel_preprocess_bwd(c, (int)N, prm, ctx->aux, ctx->sgrad2, g, flags, st));
+        EV(8);
+        ctx->ev_bwd = ctx->profiling;
+        return DVS_OK;
+    }
     CK(launch_render_bwd(c, DVS_TILE_ORDER(ctx), ctx->tile_base, ctx->plist, ctx->rec, ctx->final_T, ctx->n_contrib, dL_dpix,
                          reinterpret_cast<float*>(ctx->sgrad), (flags & DVS_FLAG_ABSGRAD) && g.mean2D_abs,
                          ctx->info, st));

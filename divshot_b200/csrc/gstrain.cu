@@ -795,6 +795,7 @@ bool GaussianTrainerScene::loadTrainData(const std::string& path) {
                 vw.name = "synthetic_view_" + std::to_string(v);
                 make_projection(vw.cam, Rt, (int)W, (int)H, vw.fx, vw.fy, vw.P);
                 vw.cam.sh_degree = I.max_degree;
+                if (config_.modelType == 1) vw.cam.flags |= DVS_FLAG_MODEL_2DGS;  // the ground truth of a 2DGS run is rendered as surfels
                 ck(cudaMalloc(&vw.d_target, (size_t)3 * W * H * sizeof(float)), "cudaMalloc target");
                 dvs_params P = I.P();
                 ckr(dvs_rast_forward(I.ctx, &vw.cam, I.N, &P, vw.d_target, nullptr, I.stream), I.ctx, "render target");
@@ -980,6 +981,7 @@ void GaussianTrainerScene::trainStep() {
     if (!I.resync_next) cam_flags |= DVS_FLAG_DEFER_CHECK;
     I.resync_next = false;
     if (config_.mipAntiliased) cam_flags |= DVS_FLAG_ANTIALIAS;  // --mipAntiliased (main.cpp, docs/userGuide.md:58)
+    if (config_.modelType == 1) cam_flags |= DVS_FLAG_MODEL_2DGS;  // --modelType 1: 2D Gaussian splatting (main.cpp:28, gs_train.cpp:68)
     uint32_t bwd_flags = 0u;
     if (refining && !mcmc) {  // ADC feeds on the screen-space gradient of every view
         G.mean2D = I.d_mean2D;

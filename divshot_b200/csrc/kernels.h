@@ -53,6 +53,19 @@ cudaError_t launch_aux_normal_records(const Cam& cam, int N, const Params& prm, 
 cudaError_t launch_aux_extract3(int N, float4* sgrad, float* dn, cudaStream_t st);
 cudaError_t launch_aux_normal_grad(const Cam& cam, int N, const Params& prm, const float* dn, float* dquats, cudaStream_t st);
 
+// 2DGS ("surfel") variant, GaussianTrainConfig::modelType = 1 (preprocess_fwd.cu / surfel.cu): per-Gaussian forward into the
+// 64-byte homography records rec2 (+ a 3DGS-shaped stand-in in rec, aux, tile counts, so binning / sorting run unchanged),
+// compositing forward, reverse-walk backward into the 64-byte records sgrad2, per-Gaussian backward
+cudaError_t launch_surfel_preprocess_fwd(const Cam& cam, int N, const Params& prm, float4* rec, float4* rec2, uint4* aux,
+                                         uint32_t* tile_count, int32_t* out_radii, unsigned long long* stats, cudaStream_t st);
+cudaError_t launch_surfel_render_fwd(const Cam& cam, const uint32_t* tile_base, const uint32_t* plist, const float4* rec2,
+                                     float* out_color, float* final_T, uint32_t* n_contrib, const uint32_t* info, cudaStream_t st);
+cudaError_t launch_surfel_render_bwd(const Cam& cam, const uint32_t* tile_base, const uint32_t* plist, const float4* rec2,
+                                     const float* final_T, const uint32_t* n_contrib, const float* dL_dpix, float* sgrad2,
+                                     const uint32_t* info, cudaStream_t st);
+cudaError_t launch_surfel_preprocess_bwd(const Cam& cam, int N, const Params& prm, const uint4* aux, float4* sgrad2, const Grads& g,
+                                         uint32_t flags, cudaStream_t st);
+
 // background model: dL/dbg[ch][p] = final_T[p] * dL/dpix[ch][p]  (out = C + final_T * bg)
 cudaError_t launch_background_grad(int64_t P, const float* final_T, const float* dL_dpix, float* dL_dbg, const uint32_t* info,
                                    cudaStream_t st);

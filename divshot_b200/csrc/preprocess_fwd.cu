@@ -351,4 +351,166 @@ cudaError_t launch_preprocess_fwd(const Cam& cam, int N, const Params& prm, floa
     return cudaGetLastError();
 }
 
+// =====================================================================================================================
+// 2DGS ("surfel") per-Gaussian forward — GaussianTrainConfig::modelType = 1 (main.cpp:28, gs_train.cpp:68,
+// docs/userGuide.md:38; DIVSHOT's own 2DGS rasterizer is in the closed plugin, so the algorithm is the published one:
+// Huang et al., "2D Gaussian Splatting for Geometrically Accurate Radiance Fields", restated as S.1 in oracle/dvs_oracle.c).
+// A Gaussian is a flat disk with tangents R[:,0], R[:,1] and scales (s_u, s_v); the homography
+//     M = Npix * Proj * [ s_u t_u | s_v t_v | p ; 0 0 1 ]          (rows Tu, Tv, Tw: homogeneous PIXEL coordinates of (u, v, 1))
+// is the surfel's screen record.  Bounds (3 sigma) come from M; tile rect, depth key, culling and colour are the 3DGS ones,
+// so binning / sorting run unchanged on the `aux` words and on a 3DGS-shaped stand-in record (mean2D, colour, depth, radius,
+// tiles; zero conic = "no sub-tile culling").  Same TU as A1 because it is the same contract: literal operation sequence,
+// -fmad=false, bit-identical radii / rects / depth keys / centres / colours to the oracle.  One thread per Gaussian, plain
+// loads: this variant is built for correctness first (DESIGN.md section 9 lists what a tuned version would change).
+// rec2 (64 B): {Tu.x, Tu.y, Tu.z, Tv.x} {Tv.y, Tv.z, Tw.x, Tw.y} {Tw.z, cx, cy, opacity} {r, g, b, depth}
+// =====================================================================================================================
+template <int DEG>
+__global__ void __launch_bounds__(128)
+surfel_preprocess_fwd_kernel(Cam cam, int N, Params prm, float4* __restrict__ rec, float4* __restrict__ rec2,
+                             uint4* __restrict__ aux, uint32_t* __restrict__ tile_count, int32_t* __restrict__ out_radii,
+                             unsigned long long* __restrict__ stats) {
+    constexpr int K = (DEG + 1) * (DEG + 1);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool visible = false;
+    uint32_t tiles = 0;
+    if (i < N) {
+        float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0, q2 = q0;
+        float4 s0r = q0, s1r = q0, s2r = q0, s3r = q0;
+        uint4 ax = make_uint4(0u, 0u, 0u, 0u);
+        int rad = 0;
+        const float px = prm.means3D[3 * (size_t)i], py = prm.means3D[3 * (size_t)i + 1], pz = prm.means3D[3 * (size_t)i + 2];
+        const float* V = cam.view;
+        const float* P = cam.proj;
+        const float t2 = fmaf(V[2], px, fmaf(V[6], py, fmaf(V[10], pz, V[14])));
+        do {
+            if (t2 <= 0.2f) break;
+            float s[3], qr, qx, qy, qz, o;
+            {
+                const float a0 = prm.scales[3 * (size_t)i], a1 = prm.scales[3 * (size_t)i + 1], a2 = prm.scales[3 * (size_t)i + 2];
+                const float4 qq = reinterpret_cast<const float4*>(prm.quats)[i];
+                const float oo = prm.opacities[i];
+                if (cam.flags & DVS_FLAG_INPUT_ACTIVATED) {
+                    s[0] = cam.scale_modifier * a0; s[1] = cam.scale_modifier * a1; s[2] = cam.scale_modifier * a2;
+                    qr = qq.x; qx = qq.y; qy = qq.z; qz = qq.w;
+                    o = oo;
+                } else {
+                    s[0] = cam.scale_modifier * det_expf(a0);
+                    s[1] = cam.scale_modifier * det_expf(a1);
+                    s[2] = cam.scale_modifier * det_expf(a2);
+                    const float n2 = fmaf(qq.x, qq.x, fmaf(qq.y, qq.y, fmaf(qq.z, qq.z, qq.w * qq.w)));
+                    const float inv = 1.0f / sqrtf(n2);
+                    qr = qq.x * inv; qx = qq.y * inv; qy = qq.z * inv; qz = qq.w * inv;
+                    o = 1.0f / (1.0f + det_expf(-oo));
+                }
+            }
+            float R[3][3];
+            R[0][0] = fmaf(-2.0f, fmaf(qz, qz, qy * qy), 1.0f);
+            R[0][1] = 2.0f * fmaf(qx, qy, -(qr * qz));
+            R[0][2] = 2.0f * fmaf(qx, qz, qr * qy);
+            R[1][0] = 2.0f * fmaf(qx, qy, qr * qz);
+            R[1][1] = fmaf(-2.0f, fmaf(qz, qz, qx * qx), 1.0f);
+            R[1][2] = 2.0f * fmaf(qy, qz, -(qr * qx));
+            R[2][0] = 2.0f * fmaf(qx, qz, -(qr * qy));
+            R[2][1] = 2.0f * fmaf(qy, qz, qr * qx);
+            R[2][2] = fmaf(-2.0f, fmaf(qy, qy, qx * qx), 1.0f);
+            // homography rows: T[j] = Tu_j, T[3 + j] = Tv_j, T[6 + j] = Tw_j for the columns j = u, v, 1
+            const float hw = 0.5f * (float)cam.W, hh = 0.5f * (float)cam.H;
+            const float ow = 0.5f * (float)(cam.W - 1), oh = 0.5f * (float)(cam.H - 1);
+            float T[9];
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                float v0, v1, v2, w1;
+                if (j < 2) { v0 = R[0][j] * s[j]; v1 = R[1][j] * s[j]; v2 = R[2][j] * s[j]; w1 = 0.0f; }
+                else { v0 = px; v1 = py; v2 = pz; w1 = 1.0f; }
+                const float cx = fmaf(P[0], v0, fmaf(P[4], v1, fmaf(P[8], v2, P[12] * w1)));
+                const float cy = fmaf(P[1], v0, fmaf(P[5], v1, fmaf(P[9], v2, P[13] * w1)));
+                const float cw = fmaf(P[3], v0, fmaf(P[7], v1, fmaf(P[11], v2, P[15] * w1)));
+                T[j] = fmaf(hw, cx, ow * cw);
+                T[3 + j] = fmaf(hh, cy, oh * cw);
+                T[6 + j] = cw;
+            }
+            const float tp0 = 9.0f, tp1 = 9.0f, tp2 = -1.0f;
+            const float dist = fmaf(tp0 * T[6], T[6], fmaf(tp1 * T[7], T[7], tp2 * T[8] * T[8]));
+            if (dist == 0.0f) break;
+            const float f0 = tp0 / dist, f1 = tp1 / dist, f2 = tp2 / dist;
+            const float cx = fmaf(f0 * T[0], T[6], fmaf(f1 * T[1], T[7], f2 * T[2] * T[8]));
+            const float cy = fmaf(f0 * T[3], T[6], fmaf(f1 * T[4], T[7], f2 * T[5] * T[8]));
+            const float qxx = fmaf(f0 * T[0], T[0], fmaf(f1 * T[1], T[1], f2 * T[2] * T[2]));
+            const float qyy = fmaf(f0 * T[3], T[3], fmaf(f1 * T[4], T[4], f2 * T[5] * T[5]));
+            const float ex = sqrtf(fmaxf(1e-4f, fmaf(cx, cx, -qxx))), ey = sqrtf(fmaxf(1e-4f, fmaf(cy, cy, -qyy)));
+            const float rad_f = ceilf(fmaxf(fmaxf(ex, ey), 3.0f * 0.707106f));
+            if (!(rad_f < 1.0e9f)) break;  // degenerate homography (NaN / inf extent)
+            const int radius = (int)rad_f;
+            const float radf = (float)radius;
+            const int rminx = min(cam.gx, max(0, (int)((cx - radf) * 0.0625f)));
+            const int rminy = min(cam.gy, max(0, (int)((cy - radf) * 0.0625f)));
+            const int rmaxx = min(cam.gx, max(0, (int)((cx + radf + 15.0f) * 0.0625f)));
+            const int rmaxy = min(cam.gy, max(0, (int)((cy + radf + 15.0f) * 0.0625f)));
+            const long long area = (long long)(rmaxx - rminx) * (long long)(rmaxy - rminy);
+            if (area <= 0) break;
+            float d0 = px - cam.campos[0], d1 = py - cam.campos[1], d2 = pz - cam.campos[2];
+            const float len = sqrtf(fmaf(d0, d0, fmaf(d1, d1, d2 * d2)));
+            const float linv = 1.0f / len;
+            d0 *= linv; d1 *= linv; d2 *= linv;
+            float bas[16];
+            sh_basis_dev(DEG, d0, d1, d2, bas);
+            float col[3];
+            uint32_t clamped = 0;
+            const float* myrow = prm.shN + (size_t)i * 3 * cam.KR;
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+                float acc = bas[0] * prm.sh0[3 * (size_t)i + ch];
+#pragma unroll
+                for (int k = 1; k < K; k++) acc = fmaf(bas[k], myrow[3 * (k - 1) + ch], acc);
+                acc += 0.5f;
+                if (acc < 0.0f) clamped |= 1u << ch;
+                col[ch] = fmaxf(acc, 0.0f);
+            }
+            visible = true;
+            tiles = (uint32_t)area;
+            rad = radius;
+            // 3DGS-shaped stand-in (zero conic: every sub-tile box passes) for the emission kernel and the debug unpackers
+            q0 = make_float4(cx, cy, 0.f, 0.f);
+            q1 = make_float4(0.f, log2f(o), col[0], col[1]);
+            q2 = make_float4(col[2], t2, __int_as_float(radius), __uint_as_float(tiles | (clamped << 24)));
+            s0r = make_float4(T[0], T[1], T[2], T[3]);
+            s1r = make_float4(T[4], T[5], T[6], T[7]);
+            s2r = make_float4(T[8], cx, cy, o);
+            s3r = make_float4(col[0], col[1], col[2], t2);
+            ax = make_uint4((uint32_t)rminx | ((uint32_t)rminy << 16), (uint32_t)rmaxx | ((uint32_t)rmaxy << 16) | (clamped << 29),
+                            __float_as_uint(t2), 0u);
+            for (int y = rminy; y < rmaxy; y++)
+                for (int x = rminx; x < rmaxx; x++) atomicAdd(tile_count + (size_t)(y * cam.gx + x) * TILE_CTR_STRIDE, 1u);
+        } while (false);
+        float4* r = rec + 3 * (size_t)i;
+        r[0] = q0; r[1] = q1; r[2] = q2;
+        float4* r2 = rec2 + 4 * (size_t)i;
+        r2[0] = s0r; r2[1] = s1r; r2[2] = s2r; r2[3] = s3r;
+        aux[i] = ax;
+        if (out_radii) out_radii[i] = rad;
+    }
+    const unsigned vm = __ballot_sync(0xffffffffu, visible);
+    uint32_t tsum = tiles;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, off);
+    if (lane == 0 && vm) {
+        atomicAdd(stats + 0, (unsigned long long)__popc(vm));
+        atomicAdd(stats + 1, (unsigned long long)tsum);
+    }
+}
+
+cudaError_t launch_surfel_preprocess_fwd(const Cam& cam, int N, const Params& prm, float4* rec, float4* rec2, uint4* aux,
+                                         uint32_t* tile_count, int32_t* out_radii, unsigned long long* stats, cudaStream_t st) {
+    if (N <= 0) return cudaSuccess;
+    const int grid = (N + 127) / 128;
+    switch (cam.deg) {
+        case 0: surfel_preprocess_fwd_kernel<0><<<grid, 128, 0, st>>>(cam, N, prm, rec, rec2, aux, tile_count, out_radii, stats); break;
+        case 1: surfel_preprocess_fwd_kernel<1><<<grid, 128, 0, st>>>(cam, N, prm, rec, rec2, aux, tile_count, out_radii, stats); break;
+        case 2: surfel_preprocess_fwd_kernel<2><<<grid, 128, 0, st>>>(cam, N, prm, rec, rec2, aux, tile_count, out_radii, stats); break;
+        default: surfel_preprocess_fwd_kernel<3><<<grid, 128, 0, st>>>(cam, N, prm, rec, rec2, aux, tile_count, out_radii, stats); break;
+    }
+    return cudaGetLastError();
+}
+
 }  // namespace dvs

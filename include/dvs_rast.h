@@ -52,6 +52,10 @@ extern "C" {
 
 #define DVS_FLAG_SKIP_SHN_GRAD 64u  /* backward: do not write grads->shN (180 of the 236 B per Gaussian at SH degree 3): the caller forms
                                      * the summed dL/dshN itself from every view's dL/dsh0 (dvs_coll_exchange_fused); not with ACCUMULATE */
+#define DVS_FLAG_MODEL_2DGS 128u    /* forward (the backward follows the forward's model): 2D Gaussian splatting, GaussianTrainConfig::modelType
+                                     * = 1 — a Gaussian is a flat disk (tangents R[:,0], R[:,1], scales[0..1]; scales[2] ignored, gradient 0),
+                                     * rendered by ray-splat intersection with the object-space low-pass filter; same tensors, same outputs.
+                                     * Two-pass binning, whole-rectangle lists (DEFER_CHECK is honoured, TIGHT_LISTS / ANTIALIAS ignored) */
 #define DVS_FLAG_TIGHT_LISTS 32u    /* forward, only together with DVS_FLAG_DEFER_CHECK (the training-loop mode): entries whose
                                        {alpha >= 1/255} footprint misses their tile are not put into the tile lists.  Image,
                                        final_T and gradients are unchanged; point_list / ranges are the whole-rectangle lists
