@@ -268,7 +268,7 @@ def measure_row(tool):
             return {"error": (r.stderr or r.stdout)[-600:]}
         d = json.loads(rows[-1])
         return {k: d.get(k) for k in ("metric", "value", "unit", "ms_per_step", "config", "roofline", "e2e", "cpu_baseline", "gpu_launches",
-                                      "passes", "refine_ms_per_call", "refine_ms_per_iteration") if k in d}
+                                      "passes", "refine_ms_per_call", "refine_ms_per_iteration", "model_2dgs") if k in d}
     except Exception as e:  # noqa: BLE001
         return {"error": repr(e)[:600]}
 
@@ -570,7 +570,8 @@ def main():
         line["cpu_baseline"] = {"value": n_s / best, "unit": "Gaussians/s", "cores": cores, "kind": "port",
                                 "sample": sample + f"; best of 3 ({best:.2f} s)"}
     if world == 1 and rank == 0 and not args.no_rows:
-        line["other_rows"] = {"F3_viewer_pack": measure_row("bench_viewer_pack.py"), "F1_refinement": measure_row("bench_densify.py")}
+        line["other_rows"] = {"F3_viewer_pack": measure_row("bench_viewer_pack.py"), "F1_refinement": measure_row("bench_densify.py"),
+                              "F1_train_step": measure_row("bench_trainstep.py")}
     if rank == 0:
         sys.stdout.flush()
         os.dup2(real_stdout, 1)

@@ -335,6 +335,78 @@ static SkyCam sky_cam(const dvs_camera& cam) {
     return c;
 }
 
+// ---- normal-consistency loss: GaussianTrainConfig::normalConsistencyLoss (gs_train.cpp:79-84, docs/userGuide.md:52-58) -----
+// The loss of the 2DGS paper (its eq. 14) on the maps dvs_rast_forward_aux renders: the rendered normal map N = sum_k w_k n_k
+// must agree with the normal of the rendered SURFACE, taken from the depth map by finite differences:
+//     D = depth / alpha (alpha > 1e-6, else 0);  P(x, y) = D(x, y) * ray(x, y),  ray = (ndc_x tan_x, ndc_y tan_y, 1);
+//     n_d = normalize( (P(x+1, y) - P(x-1, y)) x (P(x, y+1) - P(x, y-1)) )   (interior pixels);
+//     L = lambda / (W H) * sum_p ( 1 - alpha_p (N_p . n_d,p) )               (alpha_p as a constant weight).
+// Gradients go to the normal map directly and to depth / alpha of the four neighbours through n_d; dvs_rast_backward_aux
+// carries them on to the Gaussians.  The closed trainer's loss is absent from the reference: parity
+// unpinned, the kernel is checked against torch autograd of the same formula (tests/test_plugin.py).
+__global__ void normal_consistency_kernel(int W, int H, float tanx, float tany, const float* __restrict__ aux /* [2,H,W] */,
+                                          const float* __restrict__ nrm /* [3,H,W] */, float lam_over_p, float* __restrict__ loss,
+                                          float* __restrict__ d_aux /* [2,H,W], zeroed */, float* __restrict__ d_nrm /* [3,H,W] */) {
+    const size_t P = (size_t)W * H;
+    float local = 0.f;
+    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < P; p += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(p % W), y = (int)(p / W);
+        float gn0 = 0.f, gn1 = 0.f, gn2 = 0.f;
+        if (x > 0 && y > 0 && x < W - 1 && y < H - 1) {
+            const size_t q[4] = {p + 1, p - 1, p + (size_t)W, p - (size_t)W};  // x+1, x-1, y+1, y-1
+            const int qx[4] = {x + 1, x - 1, x, x}, qy[4] = {y, y, y + 1, y - 1};
+            float Dq[4], Aq[4], ray[4][2], Pq[4][3];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                Aq[k] = aux[P + q[k]];
+                Dq[k] = Aq[k] > 1e-6f ? aux[q[k]] / Aq[k] : 0.f;
+                ray[k][0] = ((2.f * (float)qx[k] + 1.f) / (float)W - 1.f) * tanx;
+                ray[k][1] = ((2.f * (float)qy[k] + 1.f) / (float)H - 1.f) * tany;
+                Pq[k][0] = Dq[k] * ray[k][0]; Pq[k][1] = Dq[k] * ray[k][1]; Pq[k][2] = Dq[k];
+            }
+            const float dx[3] = {Pq[0][0] - Pq[1][0], Pq[0][1] - Pq[1][1], Pq[0][2] - Pq[1][2]};
+            const float dy[3] = {Pq[2][0] - Pq[3][0], Pq[2][1] - Pq[3][1], Pq[2][2] - Pq[3][2]};
+            const float c[3] = {dx[1] * dy[2] - dx[2] * dy[1], dx[2] * dy[0] - dx[0] * dy[2], dx[0] * dy[1] - dx[1] * dy[0]};
+            const float len = sqrtf(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+            const float a = aux[P + p];
+            if (len > 1e-20f) {
+                const float n[3] = {c[0] / len, c[1] / len, c[2] / len};
+                const float N0 = nrm[p], N1 = nrm[P + p], N2 = nrm[2 * P + p];
+                local += lam_over_p * (1.f - a * (N0 * n[0] + N1 * n[1] + N2 * n[2]));
+                gn0 = -lam_over_p * a * n[0]; gn1 = -lam_over_p * a * n[1]; gn2 = -lam_over_p * a * n[2];
+                // dL/dn_d = -lam a N  ->  dL/dc = (I - n n^T) / |c| dL/dn_d  ->  dL/ddx = dy x dL/dc,  dL/ddy = dL/dc x dx
+                const float g[3] = {-lam_over_p * a * N0, -lam_over_p * a * N1, -lam_over_p * a * N2};
+                const float ng = n[0] * g[0] + n[1] * g[1] + n[2] * g[2];
+                const float dc[3] = {(g[0] - n[0] * ng) / len, (g[1] - n[1] * ng) / len, (g[2] - n[2] * ng) / len};
+                const float ddx[3] = {dy[1] * dc[2] - dy[2] * dc[1], dy[2] * dc[0] - dy[0] * dc[2], dy[0] * dc[1] - dy[1] * dc[0]};
+                const float ddy[3] = {dc[1] * dx[2] - dc[2] * dx[1], dc[2] * dx[0] - dc[0] * dx[2], dc[0] * dx[1] - dc[1] * dx[0]};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float* dd = k < 2 ? ddx : ddy;
+                    const float sgn = (k & 1) ? -1.f : 1.f;
+                    const float dD = sgn * (ray[k][0] * dd[0] + ray[k][1] * dd[1] + dd[2]);  // P = D (ray_x, ray_y, 1)
+                    if (Aq[k] > 1e-6f) {
+                        atomicAdd(d_aux + q[k], dD / Aq[k]);                    // D = depth / alpha
+                        atomicAdd(d_aux + P + q[k], -dD * Dq[k] / Aq[k]);
+                    }
+                }
+            } else {
+                local += lam_over_p;
+            }
+        }
+        d_nrm[p] = gn0; d_nrm[P + p] = gn1; d_nrm[2 * P + p] = gn2;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local != 0.f) atomicAdd(loss, local);
+}
+static void launch_normal_consistency(int W, int H, float tanx, float tany, const float* aux, const float* nrm, float lambda, float* loss,
+                                      float* d_aux, float* d_nrm, cudaStream_t st) {
+    const size_t P = (size_t)W * H;
+    cudaMemsetAsync(d_aux, 0, 2 * P * sizeof(float), st);
+    normal_consistency_kernel<<<148 * 4, 256, 0, st>>>(W, H, tanx, tany, aux, nrm, lambda / (float)P, loss, d_aux, d_nrm);
+}
+
 struct View {
     dvs_camera cam;
     float* d_target = nullptr;  // [3,H,W] device
@@ -566,6 +638,9 @@ struct GaussianTrainerImpl {
     int32_t* d_radii = nullptr;    // [capacity] radii of the last forward
     bool refine_enabled = false;   // the schedule reaches the refinement window (set before upload)
     bool resync_next = false;      // N changed: the next forward re-sizes the binning arena synchronously
+    // normalConsistencyLoss: the auxiliary maps of the step and their gradients [2P | 3P | 2P | 3P]
+    float* d_ncl = nullptr;
+    size_t ncl_cap = 0;
     // background model (enableBg): 27 SH coefficients, their gradient and Adam moments [4][27], the per-pixel image and dL/dbg
     float* d_sky = nullptr;
     float* d_bg_img = nullptr;
@@ -694,7 +769,7 @@ GaussianTrainerScene::~GaussianTrainerScene() {
     for (auto& v : impl_->views) { cudaFree(v.d_target); cudaFree(v.d_mask); }
     impl_->release_model();
     cudaFree(impl_->d_render); cudaFree(impl_->d_dLdpix); cudaFree(impl_->d_scratch); cudaFree(impl_->d_loss);
-    cudaFree(impl_->d_sky); cudaFree(impl_->d_bg_img); cudaFree(impl_->d_dbg);
+    cudaFree(impl_->d_sky); cudaFree(impl_->d_bg_img); cudaFree(impl_->d_dbg); cudaFree(impl_->d_ncl);
     for (auto& v : impl_->vp) { cudaFree(v.d); if (v.h) cudaFreeHost(v.h); if (v.ready) cudaEventDestroy(v.ready); }
     if (impl_->vp_packed) cudaEventDestroy(impl_->vp_packed);
     if (impl_->vp_stream) cudaStreamDestroy(impl_->vp_stream);
@@ -1027,7 +1102,24 @@ void GaussianTrainerScene::trainStep() {
             launch_photometric_loss(I.d_render, vw.d_target, I.d_dLdpix, I.d_loss, I.d_scratch, cam.width, cam.height,
                                     std::min(1.f, std::max(0.f, config_.ssimWeight)), I.stream);
             if (vw.d_mask) mask_grad_kernel<<<1184, 256, 0, I.stream>>>(I.d_dLdpix, vw.d_mask, npix);
-            rc = dvs_rast_backward(I.ctx, &P, I.d_dLdpix, &G, flags_j, I.stream);
+            // normalConsistencyLoss (3DGS model; from a quarter of the schedule on, at most iteration 7000 as in the 2DGS paper):
+            // render depth / alpha / normal maps, add lambda * L_n to the loss, and backpropagate through the maps as well
+            const bool ncl = config_.normalConsistencyLoss && config_.modelType == 0 && step >= std::min(7000, config_.numIters / 4);
+            if (ncl) {
+                if (5 * npix > I.ncl_cap) {
+                    ck(cudaStreamSynchronize(I.stream), "sync");
+                    cudaFree(I.d_ncl);
+                    ck(cudaMalloc(&I.d_ncl, 10 * npix * sizeof(float)), "cudaMalloc normal-consistency maps");
+                    I.ncl_cap = 5 * npix;
+                }
+                float *m_aux = I.d_ncl, *m_nrm = I.d_ncl + 2 * npix, *g_aux = I.d_ncl + 5 * npix, *g_nrm = I.d_ncl + 7 * npix;
+                rc = dvs_rast_forward_aux(I.ctx, &P, m_aux, m_nrm, I.stream);
+                ckr(rc, I.ctx, "forward_aux");
+                launch_normal_consistency(cam.width, cam.height, cam.tanfovx, cam.tanfovy, m_aux, m_nrm, 0.05f, I.d_loss, g_aux, g_nrm, I.stream);
+                rc = dvs_rast_backward_aux(I.ctx, &P, I.d_dLdpix, g_aux, g_nrm, &G, flags_j, I.stream);
+            } else {
+                rc = dvs_rast_backward(I.ctx, &P, I.d_dLdpix, &G, flags_j, I.stream);
+            }
             if (rc == DVS_E_OVERFLOW && attempt < 2) { cam.flags &= ~DVS_FLAG_DEFER_CHECK; continue; }
             ckr(rc, I.ctx, "backward");
             break;
@@ -1421,6 +1513,12 @@ GS_EXPORT int64_t gstrain_test_adam(float* params, const float* grads, float* m1
         launch_adam_fused(lay, grads, m1, m2, N, lrs, radii, skip, b1, b2, eps, c1, c2, static_cast<cudaStream_t>(stream));
     }
     return cudaGetLastError() == cudaSuccess ? (int64_t)lay.total : -1;
+}
+// test hook of the normal-consistency loss: loss (accumulated into *loss), dL/d(depth, alpha) [2,H,W], dL/dnormal [3,H,W]
+GS_EXPORT int gstrain_test_normal_consistency(int W, int H, float tanx, float tany, const float* aux, const float* nrm, float lambda,
+                                              float* loss, float* d_aux, float* d_nrm, void* stream) {
+    launch_normal_consistency(W, H, tanx, tany, aux, nrm, lambda, loss, d_aux, d_nrm, static_cast<cudaStream_t>(stream));
+    return (int)cudaGetLastError();
 }
 // test hooks of the background model: bg[3,H,W] = sky(coef[9][3]) for a camera; dcoef[9][3] += sum_p Y(dir_p) dbg[:, p]
 GS_EXPORT int gstrain_test_sky_eval(const dvs_camera* cam, const float* coef, float* bg, void* stream) {

@@ -89,7 +89,7 @@ def test_bench_main_assembles_the_contract_line(monkeypatch, capfd):
     assert line["n_gpus"] == 1 and line["steps"] == 3 and line["gpu_launches"] == 30 and line["vs_baseline"] is None
     assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
     assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
-    assert set(line["other_rows"]) == {"F3_viewer_pack", "F1_refinement"}
+    assert set(line["other_rows"]) == {"F3_viewer_pack", "F1_refinement", "F1_train_step"}
     assert "workload" in line["config"] and line["config"]["workload"].startswith("c1")
 
 
@@ -98,7 +98,7 @@ def test_row_harnesses_report_failure_as_text_without_a_gpu():
         pytest.skip("GPU present")
     sys.path.insert(0, ROOT)
     import bench
-    for tool in ("bench_viewer_pack.py", "bench_densify.py"):
+    for tool in ("bench_viewer_pack.py", "bench_densify.py", "bench_trainstep.py"):
         r = bench.measure_row(tool)
         assert set(r) == {"error"} and "needs a GPU" in r["error"]
 

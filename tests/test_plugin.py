@@ -417,3 +417,55 @@ def test_sky_model_kernels_match_numpy_and_training_with_enableBg_runs(tmp_path)
     r = subprocess.run([libs["gstrain_driver"], "synthetic:N=8000,W=192,H=128,views=4,deg=1", "150", str(tmp_path / "sky.ply"), "enableBg=1"],
                        capture_output=True, text=True, env={**os.environ, "LD_LIBRARY_PATH": LIB}, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr  # exit 0 <=> loss fell by > 20 %
+
+
+@pytest.mark.gpu
+def test_normal_consistency_loss_matches_torch_autograd_and_trains(tmp_path):
+    """GaussianTrainConfig::normalConsistencyLoss (gs_train.cpp:79-84): the 2DGS paper's normal-consistency loss on the depth /
+    alpha / normal maps of dvs_rast_forward_aux.  The kernel's loss and its gradients w.r.t. all three maps against torch
+    autograd of the same formula (float64); then the trainer loop with the flag on (aux forward + backward every step)."""
+    import ctypes as C
+
+    import torch
+    libs = _build()
+    lib = C.CDLL(libs["libgstrain"])
+    lib.gstrain_test_normal_consistency.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
+                                                    C.c_void_p, C.c_void_p, C.c_void_p]
+    W, H, tanx, tany, lam = 61, 47, 0.6, 0.45, 0.05
+    dev = torch.device("cuda", 0)
+    gen = torch.Generator(device="cpu"); gen.manual_seed(21)
+    alpha = torch.rand(H, W, generator=gen) * 0.9 + 0.05
+    alpha[5:9, 7:12] = 0.0                                   # a hole: D = 0 there, no gradient through it
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float64), torch.arange(W, dtype=torch.float64), indexing="ij")
+    surf = 3.0 + 0.02 * xs + 0.01 * ys + 0.3 * torch.sin(xs / 7.0) * torch.cos(ys / 5.0) + 0.02 * torch.rand(H, W, generator=gen).double()
+    depth = (surf * alpha.double()).float()                   # depth map = sum w z = D * alpha
+    nrm = torch.randn(3, H, W, generator=gen) * 0.5
+    aux = torch.stack([depth, alpha]).contiguous()
+    # torch reference (float64)
+    a64 = aux.double().clone().requires_grad_(True); n64 = nrm.double().clone().requires_grad_(True)
+    A = a64[1]
+    D = torch.where(A > 1e-6, a64[0] / torch.where(A > 1e-6, A, torch.ones_like(A)), torch.zeros_like(A))
+    rx = ((2 * xs + 1) / W - 1) * tanx; ry = ((2 * ys + 1) / H - 1) * tany
+    Pt = torch.stack([D * rx, D * ry, D], 0)
+    dx = Pt[:, 1:-1, 2:] - Pt[:, 1:-1, :-2]; dy = Pt[:, 2:, 1:-1] - Pt[:, :-2, 1:-1]
+    c = torch.cross(dx, dy, dim=0)
+    ln = c.norm(dim=0)
+    ok = ln > 1e-20
+    nd = c / torch.where(ok, ln, torch.ones_like(ln))[None]
+    err = torch.where(ok, 1 - A.detach()[1:-1, 1:-1] * (n64[:, 1:-1, 1:-1] * nd).sum(0), torch.ones_like(ln))
+    loss_ref = lam / (W * H) * err.sum()
+    loss_ref.backward()
+    # ours
+    t_aux, t_nrm = aux.to(dev), nrm.to(dev).contiguous()
+    loss = torch.zeros(1, device=dev); d_aux = torch.full((2, H, W), 7.0, device=dev); d_nrm = torch.full((3, H, W), 7.0, device=dev)
+    rc = lib.gstrain_test_normal_consistency(W, H, tanx, tany, t_aux.data_ptr(), t_nrm.data_ptr(), lam, loss.data_ptr(), d_aux.data_ptr(),
+                                             d_nrm.data_ptr(), None)
+    torch.cuda.synchronize()
+    assert rc == 0
+    assert abs(float(loss) - float(loss_ref)) <= 1e-5 * abs(float(loss_ref))
+    for got, ref, name in [(d_nrm.cpu().double(), n64.grad, "dL/dnormal"), (d_aux.cpu().double(), a64.grad, "dL/d(depth, alpha)")]:
+        scale = float(ref.abs().max())
+        assert scale > 0 and float((got - ref).abs().max()) <= 2e-4 * scale, name
+    r = subprocess.run([libs["gstrain_driver"], "synthetic:N=8000,W=192,H=128,views=4,deg=1", "120", str(tmp_path / "ncl.ply"), "normalLoss=1",
+                        "numIters=120"], capture_output=True, text=True, env={**os.environ, "LD_LIBRARY_PATH": LIB}, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr

@@ -1,0 +1,73 @@
+#!/usr/bin/env python
+"""Measurement for row F1 (the trainer step around the rasterizer), same conventions as bench.py: one JSON line.
+
+  python tools/bench_trainstep.py [--n 1000000] [--iters 300]
+
+Runs the plugin's own loop (tools/gstrain_driver.cpp: dlopen libgstrain.so, create_splat -> load_train_data -> train_step x K,
+the caller of application/diverseshot-cli/source/gs_train.cpp:152-167) on a c3-sized synthetic scene (1 M Gaussians, 1600x1000,
+SH degree 3, 8 ring views) and reports iterations/s after warm-up (wall clock over the loop: launches are asynchronous, the
+loop is queue-bound only at its end) for the 3DGS model, and for the 2DGS model (modelType = 1) at a smaller step count.
+A step = forward + fused L1/SSIM loss + backward + ONE fused Adam launch over all six groups (no refinement window in this run).
+HBM roofline of the step: the rasterizer's algorithmic bytes (from bench.py) + loss (render, target read,
+dL/dpix written: 36 B/pixel + 9 SSIM planes written and read: 72 B/pixel) + Adam (4 streams read, 3 written: 28 B per parameter)."""
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def run(driver, data, iters, extra, lib_dir):
+    with tempfile.TemporaryDirectory() as td:
+        r = subprocess.run([driver, data, str(iters), os.path.join(td, "m.ply"), "lossCheck=0", "verbose=0", "warmup=1000000"] + extra,
+                           capture_output=True, text=True, env={**os.environ, "LD_LIBRARY_PATH": lib_dir}, timeout=280)
+    m = re.search(r"its_per_s ([0-9.]+)", r.stdout)
+    if r.returncode != 0 or not m:
+        raise RuntimeError((r.stdout + r.stderr)[-600:])
+    return float(m.group(1))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=1000000)
+    ap.add_argument("--iters", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=0); ap.add_argument("--warmup", type=int, default=0)  # (bench.py's measure_row passes these)
+    a = ap.parse_args()
+    import torch
+    from bench import _peaks, algorithmic_bytes
+    from divshot_b200 import build
+    assert torch.cuda.is_available(), "needs a GPU (no CPU path in the product)"
+    libs = build.build_all(torch_binding=False)
+    lib_dir = os.path.join(ROOT, "divshot_b200", "lib")
+    W, H, deg, N = 1600, 1000, 3, a.n
+    data = f"synthetic:N={N},W={W},H={H},views=8,deg={deg}"
+    # numIters large: the progressive SH schedule (one band per 1000 iterations) stays at degree 0 in a short run, so the
+    # measured step is the degree-0 step of the first thousand iterations of a real run
+    its3 = run(libs["gstrain_driver"], data, a.iters, ["numIters=30000"], lib_dir)
+    its2 = run(libs["gstrain_driver"], data, max(60, a.iters // 3), ["numIters=30000", "modelType=1"], lib_dir)
+    peak, src = _peaks()
+    K, P, T = (deg + 1) ** 2, W * H, ((W + 15) // 16) * ((H + 15) // 16)
+    V, D = int(0.80 * N), int(7.6 * N)  # c3's measured visibility / duplication (bench.py reports the exact figures)
+    _, rast_bytes = algorithmic_bytes(N, K, V, D, T, P)
+    step_bytes = rast_bytes + (36 + 72) * P + 28 * (11 + 3 * (K - 1) + 3) * N
+    ms3 = 1e3 / its3
+    ach = step_bytes / 1e9 / (ms3 * 1e-3)
+    print(json.dumps({
+        "metric": "train_step iterations/s (plugin loop)", "value": its3, "unit": "iterations/s", "n_gpus": 1, "ms_per_step": ms3,
+        "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"F1: {N} Gaussians, {W}x{H}, 8 ring views, SH storage degree {deg} (progressive: active degree 0 in this "
+                               "window), forward + L1/SSIM loss + backward + fused Adam through libgstrain.so's train_step"},
+        "roofline": {"bound": "hbm", "kernel": "whole train_step", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                     "traffic": None, "peak_source": src, "alg_bytes_per_launch": step_bytes},
+        "model_2dgs": {"iterations_per_s": its2, "ms_per_step": 1e3 / its2,
+                       "note": "modelType = 1 (csrc/surfel.cu): correct, untuned compositor (one thread per pixel, no sub-tile masks)"},
+        "cpu_baseline": None, "gpu_launches": None}))
+
+
+if __name__ == "__main__":
+    main()

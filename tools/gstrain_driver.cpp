@@ -4,7 +4,7 @@
 // reference sources (and therefore the real CLI build) may be absent.  Prints the loss trajectory.
 // Optional trailing key=value arguments set schedule fields the CLI takes as flags (main.cpp:19-70):
 // warmup= refineEvery= refineStop= resetAlphaEvery= capMax= strategy= (densifyStrategy: 0 ADC, 1 MCMC, 2 ADC+)
-// visibleAdam= revisedOpacity= enableBg= (0 / 1); modelType= (0 3DGS, 1 2DGS); loadItr= (create_splat's second argument: resume from the model at <out> at that
+// visibleAdam= revisedOpacity= enableBg= (0 / 1); modelType= (0 3DGS, 1 2DGS); normalLoss= (0 / 1); loadItr= (create_splat's second argument: resume from the model at <out> at that
 // iteration, main.cpp:40-41); lossCheck=0 (exit 0 even if the loss did not fall by 20 %: short resume / timing runs).
 // Data parallel: start one process per GPU with RANK / WORLD_SIZE / LOCAL_RANK (or DVS_*) set, e.g. under
 // `python -m torch.distributed.run --no-python`; every rank runs this same loop, rank 0's output file is the model.
@@ -56,6 +56,7 @@ int main(int argc, char** argv) {
         else if (k == "revisedOpacity") cfg.revisedOpacity = v != 0;
         else if (k == "enableBg") cfg.enableBg = v != 0;
         else if (k == "modelType") cfg.modelType = v;
+        else if (k == "normalLoss") cfg.normalConsistencyLoss = v != 0;
         else if (k == "loadItr") load_itr = v;
         else if (k == "lossCheck") loss_check = v;
         else if (k == "verbose") cfg.verbose = v != 0;
