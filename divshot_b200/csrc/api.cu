@@ -41,6 +41,7 @@ struct dvs_rast_ctx {
     int64_t cap_surfel = 0;
     float4* rec2 = nullptr;
     float4* sgrad2 = nullptr;
+    float4* cull2 = nullptr;  // [cap][2] sub-tile cull ellipses of the surfels
     bool surfel_fwd = false;  // the last forward was a 2DGS one (the backward follows it)
     // per-tile
     int64_t cap_tiles = 0;
@@ -260,7 +261,7 @@ int dvs_rast_create(int device, dvs_rast_ctx** out) {
 void dvs_rast_destroy(dvs_rast_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->rec); cudaFree(ctx->aux); cudaFree(ctx->sgrad); cudaFree(ctx->rec2); cudaFree(ctx->sgrad2);
+    cudaFree(ctx->rec); cudaFree(ctx->aux); cudaFree(ctx->sgrad); cudaFree(ctx->rec2); cudaFree(ctx->sgrad2); cudaFree(ctx->cull2);
     cudaFree(ctx->tile_count); cudaFree(ctx->tile_base); cudaFree(ctx->tile_cursor); cudaFree(ctx->class_tiles); cudaFree(ctx->tile_order);
     cudaFree(ctx->bins); cudaFree(ctx->plist);
     cudaFree(ctx->final_T); cudaFree(ctx->n_contrib);
@@ -361,6 +362,7 @@ int dvs_rast_forward(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, const 
     if (surfel && ctx->cap_gauss > ctx->cap_surfel) {
         CK(regrow(ctx->rec2, 4 * (size_t)ctx->cap_gauss));
         CK(regrow(ctx->sgrad2, 4 * (size_t)ctx->cap_gauss));
+        CK(regrow(ctx->cull2, 2 * (size_t)ctx->cap_gauss));
         CK(cudaMemset(ctx->sgrad2, 0, 4 * (size_t)ctx->cap_gauss * sizeof(float4)));
         ctx->cap_surfel = ctx->cap_gauss;
     }
@@ -383,7 +385,7 @@ int dvs_rast_forward(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, const 
         const FusedEmit fe{ctx->tile_cursor, ctx->bins, fused ? ctx->bin_stride : 0u, ctx->info + 10,
                            (fused && (cam->flags & DVS_FLAG_TIGHT_LISTS)) ? 1u : 0u};
         if (surfel)
-            CK(launch_surfel_preprocess_fwd(c, (int)N, prm, ctx->rec, ctx->rec2, ctx->aux, ctx->tile_count, out_radii, ctx->stats, st));
+            CK(launch_surfel_preprocess_fwd(c, (int)N, prm, ctx->rec, ctx->rec2, ctx->cull2, ctx->aux, ctx->tile_count, out_radii, ctx->stats, st));
         else
             CK(launch_preprocess_fwd(c, (int)N, prm, ctx->rec, ctx->aux, ctx->tile_count, out_radii, ctx->stats, fe, st));
         EV(1);
@@ -398,7 +400,8 @@ int dvs_rast_forward(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, const 
                                 (uint32_t)ctx->cap_dups, ctx->class_tiles, DVS_TILE_ORDER(ctx), ctx->stats, st));
             ctx->count_dirty = false;   // zeroed as read; tile_cursor now holds the emission cursors (dirty)
             EV(2);
-            CK(launch_emit(c, (int)N, ctx->aux, ctx->rec, ctx->tile_cursor, ctx->bins, (uint32_t)ctx->cap_dups, st));
+            CK(launch_emit(c, (int)N, ctx->aux, surfel ? ctx->cull2 : ctx->rec, surfel ? 2 : 3, ctx->tile_cursor, ctx->bins,
+                           (uint32_t)ctx->cap_dups, st));
         }
         ctx->words_dirty = false;
         EV(3);

@@ -200,7 +200,7 @@ cudaError_t launch_tile_scan(int T, uint32_t* tile_count, uint32_t* tile_base, u
 constexpr int EMIT_THREADS = 256;
 
 __global__ void __launch_bounds__(EMIT_THREADS)
-emit_kernel(int gx, int N, const uint4* __restrict__ aux, const float4* __restrict__ rec,
+emit_kernel(int gx, int N, const uint4* __restrict__ aux, const float4* __restrict__ rec, int stride,
             uint32_t* __restrict__ tile_cursor, unsigned long long* __restrict__ bins, uint32_t cap) {
     const int i = blockIdx.x * EMIT_THREADS + threadIdx.x;
     uint4 ax = make_uint4(0, 0, 0, 0);
@@ -209,14 +209,14 @@ emit_kernel(int gx, int N, const uint4* __restrict__ aux, const float4* __restri
     const int w = (int)(ax.y & 0xffff) - minx, h = (int)((ax.y >> 16) & 0x1fff) - miny;
     const int area = (w > 0 && h > 0) ? w * h : 0;
     CullParams cp = {0.f, 0.f, 1.f, 0.f, 1.f, -1.f, 0.f, 0.f};
-    if (area > 0) cp = cull_params(__ldg(rec + 3 * (size_t)i), __ldg(rec + 3 * (size_t)i + 1));
+    if (area > 0) cp = cull_params(__ldg(rec + (size_t)stride * i), __ldg(rec + (size_t)stride * i + 1));
     warp_emit(gx, i, minx, miny, w, area, ax.z, cp, tile_cursor, bins, /*bin_stride=*/0u, cap, nullptr);
 }
 
-cudaError_t launch_emit(const Cam& cam, int N, const uint4* aux, const float4* rec, uint32_t* tile_cursor,
+cudaError_t launch_emit(const Cam& cam, int N, const uint4* aux, const float4* cull, int cull_stride, uint32_t* tile_cursor,
                         unsigned long long* bins, uint32_t dup_capacity, cudaStream_t st) {
     if (N <= 0) return cudaSuccess;
-    emit_kernel<<<(N + EMIT_THREADS - 1) / EMIT_THREADS, EMIT_THREADS, 0, st>>>(cam.gx, N, aux, rec, tile_cursor,
+    emit_kernel<<<(N + EMIT_THREADS - 1) / EMIT_THREADS, EMIT_THREADS, 0, st>>>(cam.gx, N, aux, cull, cull_stride, tile_cursor,
                                                                                  bins, dup_capacity);
     return cudaGetLastError();
 }

@@ -22,7 +22,9 @@ cudaError_t launch_tile_scan(int T, uint32_t* tile_count, uint32_t* tile_base, u
                              unsigned long long* stats, cudaStream_t st);
 
 // A3 (two-pass mode): emit (depth | id | sub-tile mask) entries into per-tile bins
-cudaError_t launch_emit(const Cam& cam, int N, const uint4* aux, const float4* rec, uint32_t* tile_cursor,
+// (`cull`: where the sub-tile cull ellipse of Gaussian i lies — cull[cull_stride * i], cull[cull_stride * i + 1] in the layout
+//  cull_params() reads: the 48-byte records themselves (stride 3) or the 2DGS path's own two words (stride 2))
+cudaError_t launch_emit(const Cam& cam, int N, const uint4* aux, const float4* cull, int cull_stride, uint32_t* tile_cursor,
                         unsigned long long* bins, uint32_t dup_capacity, cudaStream_t st);
 
 // A4: tile-local sort (CUB-free) -> plist (id<<8 | mask), tile-major
@@ -56,7 +58,7 @@ cudaError_t launch_aux_normal_grad(const Cam& cam, int N, const Params& prm, con
 // 2DGS ("surfel") variant, GaussianTrainConfig::modelType = 1 (preprocess_fwd.cu / surfel.cu): per-Gaussian forward into the
 // 64-byte homography records rec2 (+ a 3DGS-shaped stand-in in rec, aux, tile counts, so binning / sorting run unchanged),
 // compositing forward, reverse-walk backward into the 64-byte records sgrad2, per-Gaussian backward
-cudaError_t launch_surfel_preprocess_fwd(const Cam& cam, int N, const Params& prm, float4* rec, float4* rec2, uint4* aux,
+cudaError_t launch_surfel_preprocess_fwd(const Cam& cam, int N, const Params& prm, float4* rec, float4* rec2, float4* cull2, uint4* aux,
                                          uint32_t* tile_count, int32_t* out_radii, unsigned long long* stats, cudaStream_t st);
 cudaError_t launch_surfel_render_fwd(const Cam& cam, const uint32_t* tile_base, const uint32_t* plist, const float4* rec2,
                                      float* out_color, float* final_T, uint32_t* n_contrib, const uint32_t* info, cudaStream_t st);

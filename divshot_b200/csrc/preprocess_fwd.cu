@@ -367,6 +367,7 @@ cudaError_t launch_preprocess_fwd(const Cam& cam, int N, const Params& prm, floa
 template <int DEG>
 __global__ void __launch_bounds__(128)
 surfel_preprocess_fwd_kernel(Cam cam, int N, Params prm, float4* __restrict__ rec, float4* __restrict__ rec2,
+                             float4* __restrict__ cull2 /* [N][2]: the sub-tile cull ellipse, in the layout cull_params() reads */,
                              uint4* __restrict__ aux, uint32_t* __restrict__ tile_count, int32_t* __restrict__ out_radii,
                              unsigned long long* __restrict__ stats) {
     constexpr int K = (DEG + 1) * (DEG + 1);
@@ -377,6 +378,7 @@ surfel_preprocess_fwd_kernel(Cam cam, int N, Params prm, float4* __restrict__ re
     if (i < N) {
         float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0, q2 = q0;
         float4 s0r = q0, s1r = q0, s2r = q0, s3r = q0;
+        float4 k0 = q0, k1 = q0;  // zero conic: "no culling" (cull_params: every box passes)
         uint4 ax = make_uint4(0u, 0u, 0u, 0u);
         int rad = 0;
         const float px = prm.means3D[3 * (size_t)i], py = prm.means3D[3 * (size_t)i + 1], pz = prm.means3D[3 * (size_t)i + 2];
@@ -478,6 +480,37 @@ surfel_preprocess_fwd_kernel(Cam cam, int N, Params prm, float4* __restrict__ re
             s1r = make_float4(T[4], T[5], T[6], T[7]);
             s2r = make_float4(T[8], cx, cy, o);
             s3r = make_float4(col[0], col[1], col[2], t2);
+            // ---- sub-tile cull ellipse (ours; outside the bit-exact contract, conservative by construction + margins) ----
+            // alpha >= 1/255 needs rho = min(rho3d, rho2d) <= m2 = 2 ln(255 o).  {rho3d <= m2} is the projected disk u^2 + v^2 <=
+            // m2, whose exact screen AABB comes from M like the 3-sigma bounds (tp = (m2, m2, -1)) as long as the disk lies in
+            // front of the camera plane (dist_k < 0); {rho2d <= m2} is the disk of radius sqrt(m2 / 2) around the 3-sigma centre.
+            // The axis-aligned ellipse with semi-axes sqrt(2) x the half sizes of the rectangle around both contains it, and is
+            // what emission tests the tile's eight 8x4-pixel boxes against (emit.cuh: sub_tile_mask).
+            {
+                const float m2 = 2.0f * logf(255.0f * o) * 1.0001f + 1e-3f;
+                if (!(m2 > 0.0f)) {
+                    k0 = make_float4(cx, cy, -1.0f, -1.0f);
+                    k1 = make_float4(0.f, ALPHA_MIN_LOG2 - 1.0f, 0.f, 0.f);  // m < 0: the mask is empty, no pixel can blend it
+                } else {
+                    const float dist_k = m2 * (T[6] * T[6] + T[7] * T[7]) - T[8] * T[8];
+                    if (dist_k < -1e-6f * T[8] * T[8]) {
+                        const float g0 = m2 / dist_k, g2 = -1.0f / dist_k;
+                        const float kx = g0 * (T[0] * T[6] + T[1] * T[7]) + g2 * T[2] * T[8];
+                        const float ky = g0 * (T[3] * T[6] + T[4] * T[7]) + g2 * T[5] * T[8];
+                        const float hx = kx * kx - (g0 * (T[0] * T[0] + T[1] * T[1]) + g2 * T[2] * T[2]);
+                        const float hy = ky * ky - (g0 * (T[3] * T[3] + T[4] * T[4]) + g2 * T[5] * T[5]);
+                        const float exk = sqrtf(fmaxf(1e-4f, hx)), eyk = sqrtf(fmaxf(1e-4f, hy));
+                        const float rf = sqrtf(0.5f * m2);
+                        const float xlo = fminf(kx - exk, cx - rf), xhi = fmaxf(kx + exk, cx + rf);
+                        const float ylo = fminf(ky - eyk, cy - rf), yhi = fmaxf(ky + eyk, cy + rf);
+                        const float sx = 1.4143f * (0.5f * (xhi - xlo) * 1.001f + 0.05f), sy = 1.4143f * (0.5f * (yhi - ylo) * 1.001f + 0.05f);
+                        if (sx < 1.0e6f && sy < 1.0e6f) {  // (NaN / inf bounds: keep "no culling")
+                            k0 = make_float4(0.5f * (xlo + xhi), 0.5f * (ylo + yhi), -1.0f / (sx * sx), -1.0f / (sy * sy));
+                            k1 = make_float4(0.f, ALPHA_MIN_LOG2 + 1.0f, 0.f, 0.f);  // test: dx^2 / sx^2 + dy^2 / sy^2 <= ~1
+                        }
+                    }
+                }
+            }
             ax = make_uint4((uint32_t)rminx | ((uint32_t)rminy << 16), (uint32_t)rmaxx | ((uint32_t)rmaxy << 16) | (clamped << 29),
                             __float_as_uint(t2), 0u);
             for (int y = rminy; y < rmaxy; y++)
@@ -487,6 +520,7 @@ surfel_preprocess_fwd_kernel(Cam cam, int N, Params prm, float4* __restrict__ re
         r[0] = q0; r[1] = q1; r[2] = q2;
         float4* r2 = rec2 + 4 * (size_t)i;
         r2[0] = s0r; r2[1] = s1r; r2[2] = s2r; r2[3] = s3r;
+        cull2[2 * (size_t)i] = k0; cull2[2 * (size_t)i + 1] = k1;
         aux[i] = ax;
         if (out_radii) out_radii[i] = rad;
     }
@@ -500,15 +534,15 @@ surfel_preprocess_fwd_kernel(Cam cam, int N, Params prm, float4* __restrict__ re
     }
 }
 
-cudaError_t launch_surfel_preprocess_fwd(const Cam& cam, int N, const Params& prm, float4* rec, float4* rec2, uint4* aux,
+cudaError_t launch_surfel_preprocess_fwd(const Cam& cam, int N, const Params& prm, float4* rec, float4* rec2, float4* cull2, uint4* aux,
                                          uint32_t* tile_count, int32_t* out_radii, unsigned long long* stats, cudaStream_t st) {
     if (N <= 0) return cudaSuccess;
     const int grid = (N + 127) / 128;
     switch (cam.deg) {
-        case 0: surfel_preprocess_fwd_kernel<0><<<grid, 128, 0, st>>>(cam, N, prm, rec, rec2, aux, tile_count, out_radii, stats); break;
-        case 1: surfel_preprocess_fwd_kernel<1><<<grid, 128, 0, st>>>(cam, N, prm, rec, rec2, aux, tile_count, out_radii, stats); break;
-        case 2: surfel_preprocess_fwd_kernel<2><<<grid, 128, 0, st>>>(cam, N, prm, rec, rec2, aux, tile_count, out_radii, stats); break;
-        default: surfel_preprocess_fwd_kernel<3><<<grid, 128, 0, st>>>(cam, N, prm, rec, rec2, aux, tile_count, out_radii, stats); break;
+        case 0: surfel_preprocess_fwd_kernel<0><<<grid, 128, 0, st>>>(cam, N, prm, rec, rec2, cull2, aux, tile_count, out_radii, stats); break;
+        case 1: surfel_preprocess_fwd_kernel<1><<<grid, 128, 0, st>>>(cam, N, prm, rec, rec2, cull2, aux, tile_count, out_radii, stats); break;
+        case 2: surfel_preprocess_fwd_kernel<2><<<grid, 128, 0, st>>>(cam, N, prm, rec, rec2, cull2, aux, tile_count, out_radii, stats); break;
+        default: surfel_preprocess_fwd_kernel<3><<<grid, 128, 0, st>>>(cam, N, prm, rec, rec2, cull2, aux, tile_count, out_radii, stats); break;
     }
     return cudaGetLastError();
 }

@@ -12,11 +12,12 @@
 //     depth = rho3d <= rho2d ? u Tw.x + v Tw.y + Tw.z : Tw.z  (< 0.2: skip),  alpha = min(0.99, o exp(-rho / 2))
 //   then the 3DGS compositing rules (alpha < 1/255 skip, T (1 - alpha) < 1e-4 stop, n_contrib, final_T, background).
 //
-// Design: correctness first.  One CTA per 16x16 tile, one thread per pixel, 64-byte records staged 256 per round in shared
-// memory; the backward reduces its 15 per-pair sums over the warp with shuffles (skipped when no lane of the warp blended the
-// pair) and sends them with one 128-bit vector reduction per four floats.  The 3DGS path's sub-tile masks, packed fp32x2
-// arithmetic and two-phase backward are NOT applied here yet: this variant runs at roughly a third of
-// the 3DGS path's speed.
+// Design: correctness first.  One CTA per 16x16 tile, warp w = the 8x4-pixel sub-rectangle (w & 1, w >> 1), 64-byte records
+// staged 256 per round in shared memory; a warp skips every surfel whose sub-tile mask bit is clear (the mask is computed at
+// emission from a conservative axis-aligned ellipse around the surfel's alpha >= 1/255 support, preprocess_fwd.cu); the
+// backward also stops at the warp's deepest last contributor, reduces its 15 per-pair sums over the warp with shuffles (skipped
+// when no lane blended the pair) and sends them with one 128-bit vector reduction per four floats.  The 3DGS path's packed
+// fp32x2 arithmetic, straight-line predicated loops and two-phase backward are NOT applied here.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -59,11 +60,16 @@ surfel_render_fwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const 
                          const float4* __restrict__ rec2, float* __restrict__ out_color, float* __restrict__ final_T,
                          uint32_t* __restrict__ n_contrib, const uint32_t* __restrict__ info) {
     __shared__ float4 s_rec[SF_THREADS * 4];
+    __shared__ uint32_t s_mask[SF_THREADS];
     if (info[2]) return;
     const int tile = blockIdx.x;
     const int tx = tile % cam.gx, ty = tile / cam.gx;
     const uint32_t r0 = tile_base[tile], n = tile_base[tile + 1] - r0;
-    const int px = tx * TILE + (threadIdx.x & 15), py = ty * TILE + (threadIdx.x >> 4);
+    // warp w owns the 8x4-pixel sub-rectangle (w & 1, w >> 1) of the tile, like the 3DGS compositor: a whole warp skips a
+    // surfel whose cull ellipse misses its 32 pixels (sub-tile mask bit w of the list entry, computed at emission)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t wbit = 1u << warp;
+    const int px = tx * TILE + (warp & 1) * 8 + (lane & 7), py = ty * TILE + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = px < cam.W && py < cam.H;
     const float pxf = (float)px, pyf = (float)py;
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
@@ -73,13 +79,19 @@ surfel_render_fwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const 
         if (__syncthreads_count(done) == SF_THREADS) break;
         const uint32_t idx = base + threadIdx.x;
         if (idx < n) {
-            const float4* r = rec2 + 4 * (size_t)(__ldg(plist + r0 + idx) >> 8);
-            s_rec[4 * threadIdx.x] = __ldg(r); s_rec[4 * threadIdx.x + 1] = __ldg(r + 1);
-            s_rec[4 * threadIdx.x + 2] = __ldg(r + 2); s_rec[4 * threadIdx.x + 3] = __ldg(r + 3);
+            const uint32_t e = __ldg(plist + r0 + idx);
+            s_mask[threadIdx.x] = e & 0xffu;
+            if (e & 0xffu) {
+                const float4* r = rec2 + 4 * (size_t)(e >> 8);
+                s_rec[4 * threadIdx.x] = __ldg(r); s_rec[4 * threadIdx.x + 1] = __ldg(r + 1);
+                s_rec[4 * threadIdx.x + 2] = __ldg(r + 2); s_rec[4 * threadIdx.x + 3] = __ldg(r + 3);
+            }
         }
         __syncthreads();
         const uint32_t cnt = min((uint32_t)SF_THREADS, n - base);
+        if (__all_sync(0xffffffffu, done)) continue;
         for (uint32_t j = 0; j < cnt && !done; j++) {
+            if (!(s_mask[j] & wbit)) continue;  // (warp-uniform)
             SurfelPair q;
             if (!surfel_pair(s_rec[4 * j], s_rec[4 * j + 1], s_rec[4 * j + 2], pxf, pyf, q)) continue;
             if (q.alpha < 1.0f / 255.0f) continue;
@@ -116,11 +128,12 @@ surfel_render_bwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const 
     const int tile = blockIdx.x;
     const int tx = tile % cam.gx, ty = tile / cam.gx;
     const uint32_t r0 = tile_base[tile], n = tile_base[tile + 1] - r0;
-    const int px = tx * TILE + (threadIdx.x & 15), py = ty * TILE + (threadIdx.x >> 4);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t wbit = 1u << warp;
+    const int px = tx * TILE + (warp & 1) * 8 + (lane & 7), py = ty * TILE + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = px < cam.W && py < cam.H;
     const float pxf = (float)px, pyf = (float)py;
     const size_t P = (size_t)cam.W * cam.H, pix = (size_t)py * cam.W + px;
-    const int lane = threadIdx.x & 31;
     const float T_final = inside ? final_T[pix] : 0.f;
     const uint32_t last = inside ? n_contrib[pix] : 0u;
     float dp0 = 0.f, dp1 = 0.f, dp2 = 0.f, b0 = cam.bg[0], b1 = cam.bg[1], b2 = cam.bg[2];
@@ -131,22 +144,28 @@ surfel_render_bwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const 
     const float bg_dot = b0 * dp0 + b1 * dp1 + b2 * dp2;
     float T = T_final, acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;
     if (!__syncthreads_or(last != 0u)) return;  // no pixel of the tile blended anything
+    const uint32_t wlast = __reduce_max_sync(0xffffffffu, last);  // deepest last contributor of the warp
     const int rounds = (int)((n + SF_THREADS - 1) / SF_THREADS);
     for (int rd = rounds - 1; rd >= 0; rd--) {
         const uint32_t base = (uint32_t)rd * SF_THREADS;
         __syncthreads();
         const uint32_t idx = base + threadIdx.x;
         if (idx < n) {
-            const uint32_t id = __ldg(plist + r0 + idx) >> 8;
-            s_id[threadIdx.x] = id;
-            const float4* r = rec2 + 4 * (size_t)id;
-            s_rec[4 * threadIdx.x] = __ldg(r); s_rec[4 * threadIdx.x + 1] = __ldg(r + 1);
-            s_rec[4 * threadIdx.x + 2] = __ldg(r + 2); s_rec[4 * threadIdx.x + 3] = __ldg(r + 3);
+            const uint32_t e = __ldg(plist + r0 + idx);
+            s_id[threadIdx.x] = e;  // id << 8 | sub-tile mask
+            if (e & 0xffu) {
+                const float4* r = rec2 + 4 * (size_t)(e >> 8);
+                s_rec[4 * threadIdx.x] = __ldg(r); s_rec[4 * threadIdx.x + 1] = __ldg(r + 1);
+                s_rec[4 * threadIdx.x + 2] = __ldg(r + 2); s_rec[4 * threadIdx.x + 3] = __ldg(r + 3);
+            }
         }
         __syncthreads();
         const int cnt = (int)min((uint32_t)SF_THREADS, n - base);
+        if (base >= wlast) continue;  // this warp's pixels all stopped earlier in the list
         for (int j = cnt - 1; j >= 0; j--) {
+            if (!(s_id[j] & wbit)) continue;  // (warp-uniform) the surfel's cull ellipse misses this warp's 32 pixels
             const uint32_t contributor = base + (uint32_t)j;  // 0-based index of the entry in the tile's list
+            if (contributor >= wlast) continue;
             float g[15];
 #pragma unroll
             for (int k = 0; k < 15; k++) g[k] = 0.f;
@@ -190,7 +209,7 @@ surfel_render_bwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const 
                 for (int o = 16; o > 0; o >>= 1) g[k] += __shfl_xor_sync(0xffffffffu, g[k], o);
             }
             if (lane < 4) {
-                float* dst = sgrad2 + 16 * (size_t)s_id[j] + 4 * lane;
+                float* dst = sgrad2 + 16 * (size_t)(s_id[j] >> 8) + 4 * lane;
                 const float4 v = lane == 0 ? make_float4(g[0], g[1], g[2], g[3])
                                : lane == 1 ? make_float4(g[4], g[5], g[6], g[7])
                                : lane == 2 ? make_float4(g[8], g[9], g[10], g[11])

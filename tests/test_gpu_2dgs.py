@@ -111,3 +111,49 @@ def test_2dgs_trains_through_the_plugin(tmp_path):
     r = subprocess.run([libs["gstrain_driver"], "synthetic:N=20000,W=320,H=240,views=4,deg=1", "300", str(tmp_path / "m2d.ply"), "modelType=1"],
                        capture_output=True, text=True, env={**os.environ, "LD_LIBRARY_PATH": lib_dir}, timeout=300)
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+def test_2dgs_cull_masks_are_conservative(rast):
+    """Every (pixel, surfel) pair the oracle's rule blends (alpha >= 1/255 after the S.2 tests) lies in an 8x4 sub-rectangle
+    whose mask bit is set — the compositor skips whole warps on that bit, so a missing bit would silently drop light."""
+    from divshot_b200.rasterizer import scene_to_device
+    sc = make_scene(N=2500, width=96, height=64, sh_degree=0, seed=231, normalise_quats=False)
+    sc.log_scales += 1.2
+    sc.logit_opac[::3] += 3.0   # some nearly opaque surfels: widest alpha support
+    sc.logit_opac[1::7] -= 6.0  # some below 1/255: empty masks
+    params = scene_to_device(sc, rast.device)
+    cam = _cabi.make_camera(sc.cameras[0], 0, flags=_cabi.FLAG_MODEL_2DGS)
+    rast.forward(cam, params)
+    mask = rast.debug_read(_cabi.BUF_CULL_MASK)
+    f = orc.forward2d(orc_cam(sc.cameras[0], 0), *scene_arrays(sc), render=False)
+    assert np.array_equal(rast.debug_read(_cabi.BUF_POINT_LIST), f.point_list)
+    W, H = 96, 64
+    gx = (W + 15) // 16
+    bad = kept = total = 0
+    for tile in range(f.ranges.shape[0]):
+        r0, r1 = (int(v) for v in f.ranges[tile])
+        x0, y0 = (tile % gx) * 16, (tile // gx) * 16
+        ys, xs = np.mgrid[y0:y0 + 16, x0:x0 + 16].astype(np.float64)
+        for j in range(r0, r1):
+            g = int(f.point_list[j])
+            T = f.transmat[g].astype(np.float64)
+            Tu, Tv, Tw = T[0:3], T[3:6], T[6:9]
+            k = xs[..., None] * Tw - Tu; l = ys[..., None] * Tw - Tv
+            pv = np.cross(k, l)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                u, v = pv[..., 0] / pv[..., 2], pv[..., 1] / pv[..., 2]
+            rho3d = u * u + v * v
+            rho2d = 2.0 * ((f.mean2D[g, 0] - xs) ** 2 + (f.mean2D[g, 1] - ys) ** 2)
+            use3d = rho3d <= rho2d
+            dep = np.where(use3d, u * Tw[0] + v * Tw[1] + Tw[2], Tw[2])
+            alpha = np.minimum(0.99, f.opacity[g] * np.exp(-0.5 * np.minimum(rho3d, rho2d)))
+            contrib = (pv[..., 2] != 0) & (dep >= 0.2) & (alpha >= 1 / 255) & (xs < W) & (ys < H)
+            sub = contrib.reshape(4, 4, 2, 8).any(axis=(1, 3))  # [row(4), col(2)]
+            m = int(mask[j])
+            total += 8; kept += bin(m).count("1")
+            for r in range(4):
+                for c in range(2):
+                    if sub[r, c] and not (m >> (2 * r + c)) & 1:
+                        bad += 1
+    assert bad == 0, f"{bad} contributing sub-rectangles without their mask bit"
+    assert kept < 0.8 * total, f"the masks cull nothing ({kept} of {total} bits set)"

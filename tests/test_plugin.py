@@ -3,6 +3,7 @@
 and — on a GPU — trains through that boundary; the libtorch CustomClassHolder matches the C-ABI path."""
 import os
 import struct
+import re
 import subprocess
 
 import numpy as np
@@ -466,6 +467,12 @@ def test_normal_consistency_loss_matches_torch_autograd_and_trains(tmp_path):
     for got, ref, name in [(d_nrm.cpu().double(), n64.grad, "dL/dnormal"), (d_aux.cpu().double(), a64.grad, "dL/d(depth, alpha)")]:
         scale = float(ref.abs().max())
         assert scale > 0 and float((got - ref).abs().max()) <= 2e-4 * scale, name
+    # the trainer loop with the flag on: from iteration 30 (a quarter of the schedule) every step renders the maps, adds
+    # lambda * L_n (<= 0.05, so the reported loss is not comparable before / after) and backpropagates through them
     r = subprocess.run([libs["gstrain_driver"], "synthetic:N=8000,W=192,H=128,views=4,deg=1", "120", str(tmp_path / "ncl.ply"), "normalLoss=1",
-                        "numIters=120"], capture_output=True, text=True, env={**os.environ, "LD_LIBRARY_PATH": LIB}, timeout=300)
+                        "numIters=120", "lossCheck=0"], capture_output=True, text=True, env={**os.environ, "LD_LIBRARY_PATH": LIB}, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
+    m = re.search(r"first_loss ([0-9.]+) last_loss ([0-9.]+)", r.stdout)
+    assert m and float(m.group(2)) < float(m.group(1)) + 0.01, r.stdout
+    n, _, rows = _read_ply(str(tmp_path / "ncl.ply"))
+    assert n == 8000 and np.isfinite(rows).all()
