@@ -195,6 +195,10 @@ __global__ void mask_blend_kernel(float* __restrict__ render, const float* __res
         render[i] = fmaf(m, render[i] - target[i], target[i]);
     }
 }
+__global__ void unpack_u8_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = (float)src[i] / 255.f;  // the same value the fp32 path uploads (rgb / 255.f)
+}
 __global__ void mask_grad_kernel(float* __restrict__ dL_dpix, const float* __restrict__ mask, size_t P) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < 3 * P; i += (size_t)gridDim.x * blockDim.x)
         dL_dpix[i] *= mask[i % P];
@@ -409,7 +413,8 @@ static void launch_normal_consistency(int W, int H, float tanx, float tany, cons
 
 struct View {
     dvs_camera cam;
-    float* d_target = nullptr;  // [3,H,W] device
+    float* d_target = nullptr;  // [3,H,W] device, fp32 — or, with GSPackLevel::PackF32ToU8 and 8-bit source images:
+    uint8_t* d_target_u8 = nullptr;  // [3,H,W] device, the image's own bytes (a quarter of the memory; unpacked per step)
     float* d_mask = nullptr;    // [H,W] device, optional (useMask)
     float Rt[12] = {0};         // world -> camera rows [R | t] as loaded
     float P[16] = {0};          // the perspective matrix alone, flat [4c+r]
@@ -638,6 +643,8 @@ struct GaussianTrainerImpl {
     int32_t* d_radii = nullptr;    // [capacity] radii of the last forward
     bool refine_enabled = false;   // the schedule reaches the refinement window (set before upload)
     bool resync_next = false;      // N changed: the next forward re-sizes the binning arena synchronously
+    float* d_target_f32 = nullptr;  // PackF32ToU8: the current view's image unpacked to fp32
+    size_t target_f32_cap = 0;
     // normalConsistencyLoss: the auxiliary maps of the step and their gradients [2P | 3P | 2P | 3P]
     float* d_ncl = nullptr;
     size_t ncl_cap = 0;
@@ -766,7 +773,8 @@ GaussianTrainerScene::GaussianTrainerScene(const GaussianTrainConfig& config, in
 GaussianTrainerScene::~GaussianTrainerScene() {
     if (!impl_) return;
     cudaDeviceSynchronize();
-    for (auto& v : impl_->views) { cudaFree(v.d_target); cudaFree(v.d_mask); }
+    for (auto& v : impl_->views) { cudaFree(v.d_target); cudaFree(v.d_target_u8); cudaFree(v.d_mask); }
+    cudaFree(impl_->d_target_f32);
     impl_->release_model();
     cudaFree(impl_->d_render); cudaFree(impl_->d_dLdpix); cudaFree(impl_->d_scratch); cudaFree(impl_->d_loss);
     cudaFree(impl_->d_sky); cudaFree(impl_->d_bg_img); cudaFree(impl_->d_dbg); cudaFree(impl_->d_ncl);
@@ -913,8 +921,19 @@ bool GaussianTrainerScene::loadTrainData(const std::string& path) {
                 vw.fx = fx; vw.fy = fy; vw.name = img;
                 std::memcpy(vw.Rt, Rt, sizeof Rt);
                 make_projection(vw.cam, Rt, W, H, fx, fy, vw.P);
-                ck(cudaMalloc(&vw.d_target, host.size() * sizeof(float)), "cudaMalloc target");
-                ck(cudaMemcpy(vw.d_target, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice), "upload image");
+                if (config_.packLevel & PackF32ToU8) {
+                    // `packLevel & PackF32ToU8` (gs_train.cpp:90-96, the CLI default): training images stay 8-bit on the device —
+                    // 3 instead of 12 bytes per pixel, lossless for 8-bit sources — and are unpacked into one fp32 scratch
+                    // image per step (a 5 us kernel at 1600x1000)
+                    std::vector<unsigned char> planar((size_t)3 * W * H);
+                    for (size_t p = 0; p < (size_t)W * H; p++)
+                        for (int c = 0; c < 3; c++) planar[c * (size_t)W * H + p] = rgb[3 * p + c];
+                    ck(cudaMalloc(&vw.d_target_u8, planar.size()), "cudaMalloc target (u8)");
+                    ck(cudaMemcpy(vw.d_target_u8, planar.data(), planar.size(), cudaMemcpyHostToDevice), "upload image (u8)");
+                } else {
+                    ck(cudaMalloc(&vw.d_target, host.size() * sizeof(float)), "cudaMalloc target");
+                    ck(cudaMemcpy(vw.d_target, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice), "upload image");
+                }
                 if (config_.useMask) {  // optional <image>.mask.pgm (binary P5, same size): 255 = train on this pixel
                     std::ifstream mf(path + "/" + img + ".mask.pgm", std::ios::binary);
                     std::string mm; int mw = 0, mh = 0, mv = 0;
@@ -1098,8 +1117,19 @@ void GaussianTrainerScene::trainStep() {
             if (rc == DVS_E_OVERFLOW && attempt < 2) { cam.flags &= ~DVS_FLAG_DEFER_CHECK; continue; }
             ckr(rc, I.ctx, "forward");
             const size_t npix = (size_t)cam.width * cam.height;
-            if (vw.d_mask) mask_blend_kernel<<<1184, 256, 0, I.stream>>>(I.d_render, vw.d_target, vw.d_mask, npix);
-            launch_photometric_loss(I.d_render, vw.d_target, I.d_dLdpix, I.d_loss, I.d_scratch, cam.width, cam.height,
+            const float* target = vw.d_target;
+            if (!target) {  // PackF32ToU8: the view's image is held as bytes
+                if (3 * npix > I.target_f32_cap) {
+                    ck(cudaStreamSynchronize(I.stream), "sync");
+                    cudaFree(I.d_target_f32);
+                    ck(cudaMalloc(&I.d_target_f32, 3 * npix * sizeof(float)), "cudaMalloc unpacked target");
+                    I.target_f32_cap = 3 * npix;
+                }
+                unpack_u8_kernel<<<148 * 4, 256, 0, I.stream>>>(vw.d_target_u8, I.d_target_f32, 3 * npix);
+                target = I.d_target_f32;
+            }
+            if (vw.d_mask) mask_blend_kernel<<<1184, 256, 0, I.stream>>>(I.d_render, target, vw.d_mask, npix);
+            launch_photometric_loss(I.d_render, target, I.d_dLdpix, I.d_loss, I.d_scratch, cam.width, cam.height,
                                     std::min(1.f, std::max(0.f, config_.ssimWeight)), I.stream);
             if (vw.d_mask) mask_grad_kernel<<<1184, 256, 0, I.stream>>>(I.d_dLdpix, vw.d_mask, npix);
             // normalConsistencyLoss (3DGS model; from a quarter of the schedule on, at most iteration 7000 as in the 2DGS paper):
@@ -1425,7 +1455,16 @@ GsImageView GaussianTrainerScene::getSplatImageView(int id) {
     View& v = I.views.at((size_t)id);
     const size_t P = (size_t)v.cam.width * v.cam.height;
     if (v.rgba.empty()) {
-        const std::vector<float> chw = I.download(v.d_target, 3 * P);
+        std::vector<float> chw;
+        if (v.d_target) {
+            chw = I.download(v.d_target, 3 * P);
+        } else {  // PackF32ToU8: the bytes themselves
+            std::vector<uint8_t> b(3 * P);
+            cudaDeviceSynchronize();
+            cudaMemcpy(b.data(), v.d_target_u8, 3 * P, cudaMemcpyDeviceToHost);
+            chw.resize(3 * P);
+            for (size_t k = 0; k < 3 * P; k++) chw[k] = b[k] / 255.f;
+        }
         v.rgba.resize(4 * P);
         for (size_t p = 0; p < P; p++) {
             for (int c = 0; c < 3; c++) v.rgba[4 * p + c] = (uint8_t)std::lround(255.f * std::min(1.f, std::max(0.f, chw[c * P + p])));

@@ -476,3 +476,53 @@ def test_normal_consistency_loss_matches_torch_autograd_and_trains(tmp_path):
     assert m and float(m.group(2)) < float(m.group(1)) + 0.01, r.stdout
     n, _, rows = _read_ply(str(tmp_path / "ncl.ply"))
     assert n == 8000 and np.isfinite(rows).all()
+
+
+@pytest.mark.gpu
+def test_dataset_directory_loader_and_packed_training_images(tmp_path):
+    """load_train_data on a DIRECTORY (cameras.txt + binary PPM images + points.txt, the format documented in gstrain.cu) and
+    GSPackLevel::PackF32ToU8 (gs_train.cpp:90-96, the CLI default): 8-bit images stay 8-bit on the device and are unpacked per
+    step.  The images are renders of a synthetic scene by this rasterizer, quantised to 8 bits; training from the scene's point
+    cloud must reduce the loss, and the packed run must train exactly like the fp32 run (same target values)."""
+    import torch
+    from divshot_b200 import _cabi
+    from divshot_b200.rasterizer import Rasterizer, scene_to_device
+    from divshot_b200.scenes import make_scene
+    libs = _build()
+    W, H = 160, 112
+    sc = make_scene(N=6000, width=W, height=H, sh_degree=0, seed=41, views=4)
+    sc.log_scales += 0.9
+    d = tmp_path / "data"
+    d.mkdir()
+    r = Rasterizer(0)
+    lines = []
+    try:
+        params = scene_to_device(sc, r.device)
+        for v, cam in enumerate(sc.cameras):
+            img, _ = r.forward(_cabi.make_camera(cam, 0), params)
+            u8 = (img.clamp(0, 1) * 255 + 0.5).to(torch.uint8).permute(1, 2, 0).contiguous().cpu().numpy()
+            with open(d / f"view{v}.ppm", "wb") as f:
+                f.write(f"P6\n{W} {H}\n255\n".encode()); f.write(u8.tobytes())
+            V = np.asarray(cam.view, np.float64).reshape(4, 4).T      # flat [4 c + r] -> matrix[r][c]
+            Rt = V[:3, :].reshape(-1)
+            lines.append(f"view{v}.ppm {W} {H} {W / (2 * cam.tanfovx):.9g} {H / (2 * cam.tanfovy):.9g} " + " ".join(f"{x:.9g}" for x in Rt))
+    finally:
+        r.close()
+    (d / "cameras.txt").write_text("# image W H fx fy R|t rows\n" + "\n".join(lines) + "\n")
+    rgb = np.clip((0.28209479177387814 * sc.sh0 + 0.5) * 255, 0, 255)
+    (d / "points.txt").write_text("\n".join(f"{p[0]:.7g} {p[1]:.7g} {p[2]:.7g} {c[0]:.0f} {c[1]:.0f} {c[2]:.0f}" for p, c in zip(sc.means3D, rgb)) + "\n")
+    env = {**os.environ, "LD_LIBRARY_PATH": LIB}
+    outs = {}
+    for name, pack in (("packed", 1), ("fp32", 0)):
+        out = str(tmp_path / f"{name}.ply")
+        rr = subprocess.run([libs["gstrain_driver"], str(d), "200", out, "lossCheck=0", f"packLevel={pack}"], capture_output=True, text=True,
+                            env=env, timeout=300)
+        assert rr.returncode == 0, rr.stdout + rr.stderr
+        m = re.search(r"first_loss ([0-9.]+) last_loss ([0-9.]+)", rr.stdout)
+        assert m and float(m.group(2)) < 0.8 * float(m.group(1)), rr.stdout
+        outs[name] = (_read_ply(out)[2], float(m.group(2)))
+    assert outs["packed"][0].shape == outs["fp32"][0].shape == (6000, 59)
+    assert abs(outs["packed"][1] - outs["fp32"][1]) <= 2e-3 * outs["fp32"][1], "same targets, same training"
+    # a directory without cameras.txt is refused
+    rr = subprocess.run([libs["gstrain_driver"], str(tmp_path), "5", str(tmp_path / "x.ply")], capture_output=True, text=True, env=env, timeout=120)
+    assert rr.returncode != 0

@@ -56,6 +56,7 @@ int main(int argc, char** argv) {
         else if (k == "revisedOpacity") cfg.revisedOpacity = v != 0;
         else if (k == "enableBg") cfg.enableBg = v != 0;
         else if (k == "modelType") cfg.modelType = v;
+        else if (k == "packLevel") cfg.packLevel = v;
         else if (k == "normalLoss") cfg.normalConsistencyLoss = v != 0;
         else if (k == "loadItr") load_itr = v;
         else if (k == "lossCheck") loss_check = v;
