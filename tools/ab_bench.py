@@ -3,7 +3,7 @@
 
   python tools/ab_bench.py --variants r1 default default+tight v_x+tight --workload c3 --steps 30 --out gpurun_out/ab.json
 
-A variant is `<lib>[+tight][+twopass]`: <lib> = "default" (divshot_b200/lib/libdvsrast.so) or the name of a
+A variant is `<lib>[+tight][+twopass][+absgrad][+2dgs]`: <lib> = "default" (divshot_b200/lib/libdvsrast.so) or the name of a
 `divshot_b200.build.build_variant` build (divshot_b200/lib/variants/libdvsrast_<lib>.so).  Each variant runs in its
 own process (fresh CUDA context, DVS_RAST_LIB), renders the workload, and is compared with the FIRST variant's outputs:
 image bit-identical?, max abs image difference, n_contrib equal?, norm-wise relative error of every gradient tensor.
@@ -39,6 +39,7 @@ def child(args):
     spec = args.child.split("+")
     tight, twopass = "tight" in spec[1:], "twopass" in spec[1:]
     absgrad = "absgrad" in spec[1:]
+    surfel = "2dgs" in spec[1:]  # the 2DGS variant (DVS_FLAG_MODEL_2DGS): its stage times; the comparison columns are meaningless
     _, N, W, H, deg, _ = CONFIGS[args.workload]
     K = (deg + 1) ** 2
     sc = make_scene(args.workload)
@@ -47,6 +48,8 @@ def child(args):
     flags = 0
     if tight:
         flags |= getattr(_cabi, "FLAG_TIGHT_LISTS", 32)
+    if surfel:
+        flags |= getattr(_cabi, "FLAG_MODEL_2DGS", 128)
     cam = _cabi.make_camera(sc.cameras[0], deg, flags=flags)
     dl = torch.from_numpy(sc.dL_dpix[0]).to(dev)
     grads = GradBuffers.allocate(N, K - 1, dev)
