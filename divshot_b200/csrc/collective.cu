@@ -9,6 +9,7 @@
 // brackets the call with cross-rank barriers (all ranks' gradients written before; all shards stored after).
 #include <cuda_runtime.h>
 #include <stddef.h>
+#include <stdlib.h>
 #include <stdint.h>
 
 #include "dvs_rast.h"
@@ -72,7 +73,9 @@ namespace {
 static_assert(sizeof(dvs_coll_fused) == 488 && offsetof(dvs_coll_fused, sh0_tmp) == 144 && offsetof(dvs_coll_fused, N) == 384 &&
                   offsetof(dvs_coll_fused, rank) == 464,
               "dvs_coll_fused layout is part of the C-ABI (divshot_b200/_cabi.py: DvsCollFused)");
-constexpr int FX_THREADS = 512;            // one CTA per SM; a CTA forms 512 rows of dL/dshN per trip
+// CTA shapes of the fused kernel: 512 threads x 1 CTA per SM, or 256 threads x 2 CTAs per SM (two independent tile pipelines
+// per SM: one CTA's NVLink round trip hides behind the other's arithmetic and stores).  Both are compiled; the 256 x 2 shape
+// is the default, DVS_FX_THREADS=512 selects the other (A/B at 8 ranks in profiles/r2_scaling.md).
 constexpr int FX_ROW_WORDS = 45;
 constexpr unsigned long long FX_TIMEOUT_NS = 2000000000ull;
 
@@ -146,6 +149,7 @@ __device__ __forceinline__ float4 ld_peer_f4(const float* p) {
 // thread before the first is consumed.  (A/B, 8 ranks, c3: the same copies as 16-byte cp.async / LDGSTS peer reads with two
 // staging buffers — next tile in flight while the current one is processed — took 0.47 ms instead of 0.33 ms: asynchronous
 // copies from PEER memory are slow on this platform; profiles/r2_d_bench_n8_cpasync_rejected.json.)
+template <int FX_THREADS>
 __device__ __forceinline__ void fused_tile_stage(const dvs_coll_fused& a, float* stage, int tid, long long base, int cnt) {
     const size_t row0 = (size_t)a.off_sh0 + 3 * (size_t)base;
     const int n_words = 3 * cnt, n_vec = n_words >> 2;
@@ -162,6 +166,7 @@ __device__ __forceinline__ void fused_tile_stage(const dvs_coll_fused& a, float*
         for (int v = 0; v < a.world; v++) stage[(size_t)v * (3 * FX_THREADS) + w] = ld_peer_f32(a.arena_peers[v] + row0 + w);
 }
 // step 3b: thread `tid` accumulates its Gaussian's dL/dshN row into the shared rows and the summed dL/dsh0 into sh0_tmp
+template <int FX_THREADS>
 __device__ __forceinline__ void fused_tile_compute(const dvs_coll_fused& a, const float* stage, float* rows, int tid, long long base,
                                                    int cnt) {
     if (tid >= cnt) return;
@@ -184,7 +189,8 @@ __device__ __forceinline__ void fused_tile_compute(const dvs_coll_fused& a, cons
     a.sh0_tmp[3 * i] = s0; a.sh0_tmp[3 * i + 1] = s1; a.sh0_tmp[3 * i + 2] = s2;
 }
 
-__global__ void __launch_bounds__(FX_THREADS, 1)
+template <int FX_THREADS>
+__global__ void __launch_bounds__(FX_THREADS, 512 / FX_THREADS)
 fused_exchange_kernel(const dvs_coll_fused a) {
     extern __shared__ __align__(16) float s_rows[];  // FX_THREADS rows of dL/dshN, then `world` x FX_THREADS staged dL/dsh0 rows
     float* s_stage = s_rows + FX_THREADS * FX_ROW_WORDS;
@@ -234,9 +240,9 @@ fused_exchange_kernel(const dvs_coll_fused a) {
             if (tile >= n_tiles) break;
             const long long base = tile * FX_THREADS;
             const int cnt = (int)(a.N - base < FX_THREADS ? a.N - base : FX_THREADS);
-            fused_tile_stage(a, s_stage, threadIdx.x, base, cnt);
+            fused_tile_stage<FX_THREADS>(a, s_stage, threadIdx.x, base, cnt);
             __syncthreads();
-            fused_tile_compute(a, s_stage, s_rows, threadIdx.x, base, cnt);
+            fused_tile_compute<FX_THREADS>(a, s_stage, s_rows, threadIdx.x, base, cnt);
             __syncthreads();
             if (a.sh_rest_alloc > 0) dvs_shx::exchange_store(x, s_rows, threadIdx.x, FX_THREADS, base, cnt);
             __syncthreads();
@@ -254,18 +260,29 @@ fused_exchange_kernel(const dvs_coll_fused a) {
     }
 }
 
-size_t fused_smem(int world) { return (size_t)FX_THREADS * (FX_ROW_WORDS + 3 * (size_t)(world > 0 ? world : 1)) * sizeof(float); }
+int fused_threads() {
+    static const int t = [] {
+        const char* e = getenv("DVS_FX_THREADS");
+        return (e && atoi(e) == 512) ? 512 : 256;
+    }();
+    return t;
+}
+size_t fused_smem(int world, int threads) { return (size_t)threads * (FX_ROW_WORDS + 3 * (size_t)(world > 0 ? world : 1)) * sizeof(float); }
+const void* fused_kernel(int threads) {
+    return threads == 512 ? reinterpret_cast<const void*>(fused_exchange_kernel<512>) : reinterpret_cast<const void*>(fused_exchange_kernel<256>);
+}
 
+// co-resident grid: `ctas` <= 0 -> every CTA slot of the device (SMs x CTAs per SM of the chosen shape)
 int fused_grid(int ctas, int world) {
     int dev = 0, sms = 148, per_sm = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const size_t smem = fused_smem(world);
-    if (cudaFuncSetAttribute(fused_exchange_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_exchange_kernel, FX_THREADS, smem) != cudaSuccess || per_sm < 1)
-        return 0;
+    const int threads = fused_threads();
+    const size_t smem = fused_smem(world, threads);
+    if (cudaFuncSetAttribute(fused_kernel(threads), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_kernel(threads), threads, smem) != cudaSuccess || per_sm < 1) return 0;
     const int cap = sms * per_sm;
-    if (ctas <= 0) ctas = sms;
+    if (ctas <= 0) ctas = cap;
     return ctas < cap ? ctas : cap;
 }
 
@@ -297,10 +314,11 @@ extern "C" DVS_API int dvs_coll_exchange_fused(const dvs_coll_fused* args, void*
                                                            // 148 CTAs 0.326 ms, 49: 0.335 ms); they join step 3 afterwards
     if (a.reduce_ctas > grid) a.reduce_ctas = grid;
     if (a.reduce_ctas < 1) a.reduce_ctas = 1;
-    const size_t smem = fused_smem(a.world);
+    const int threads = fused_threads();
+    const size_t smem = fused_smem(a.world, threads);
     void* kargs[] = {&a};
     // cooperative launch: the device-side barriers need every CTA resident (fails instead of deadlocking otherwise)
-    const cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(fused_exchange_kernel), dim3(grid), dim3(FX_THREADS),
-                                                      kargs, smem, static_cast<cudaStream_t>(stream));
+    const cudaError_t e = cudaLaunchCooperativeKernel(fused_kernel(threads), dim3(grid), dim3(threads), kargs, smem,
+                                                      static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? DVS_OK : DVS_E_CUDA;
 }
