@@ -482,10 +482,12 @@ surfel_preprocess_fwd_kernel(Cam cam, int N, Params prm, float4* __restrict__ re
             s3r = make_float4(col[0], col[1], col[2], t2);
             // ---- sub-tile cull ellipse (ours; outside the bit-exact contract, conservative by construction + margins) ----
             // alpha >= 1/255 needs rho = min(rho3d, rho2d) <= m2 = 2 ln(255 o).  {rho3d <= m2} is the projected disk u^2 + v^2 <=
-            // m2, whose exact screen AABB comes from M like the 3-sigma bounds (tp = (m2, m2, -1)) as long as the disk lies in
-            // front of the camera plane (dist_k < 0); {rho2d <= m2} is the disk of radius sqrt(m2 / 2) around the 3-sigma centre.
-            // The axis-aligned ellipse with semi-axes sqrt(2) x the half sizes of the rectangle around both contains it, and is
-            // what emission tests the tile's eight 8x4-pixel boxes against (emit.cuh: sub_tile_mask).
+            // m2: an ellipse on screen as long as the disk lies in front of the camera plane (dist_k < 0), with centre k and
+            // shape matrix S (the pixel set is (x - k)^T S^-1 (x - k) <= 1) given by the DUAL conic M diag(m2, m2, -1) M^T —
+            // the same well-conditioned expressions as the 3-sigma bounds above, plus the xy term; they are evaluated in pixel
+            // coordinates relative to the 3-sigma centre so that the products stay small.  {rho2d <= m2} is the disk of radius
+            // sqrt(m2 / 2) around the 3-sigma centre.  The ellipse with shape S + r^2 I, r = that radius + |k - centre|, contains
+            // both; its conic is what emission tests the tile's eight 8x4-pixel boxes against (emit.cuh: sub_tile_mask).
             {
                 const float m2 = 2.0f * logf(255.0f * o) * 1.0001f + 1e-3f;
                 if (!(m2 > 0.0f)) {
@@ -494,18 +496,32 @@ surfel_preprocess_fwd_kernel(Cam cam, int N, Params prm, float4* __restrict__ re
                 } else {
                     const float dist_k = m2 * (T[6] * T[6] + T[7] * T[7]) - T[8] * T[8];
                     if (dist_k < -1e-6f * T[8] * T[8]) {
+                        const float u0 = fmaf(-cx, T[6], T[0]), u1 = fmaf(-cx, T[7], T[1]), u2 = fmaf(-cx, T[8], T[2]);
+                        const float v0 = fmaf(-cy, T[6], T[3]), v1 = fmaf(-cy, T[7], T[4]), v2 = fmaf(-cy, T[8], T[5]);
                         const float g0 = m2 / dist_k, g2 = -1.0f / dist_k;
-                        const float kx = g0 * (T[0] * T[6] + T[1] * T[7]) + g2 * T[2] * T[8];
-                        const float ky = g0 * (T[3] * T[6] + T[4] * T[7]) + g2 * T[5] * T[8];
-                        const float hx = kx * kx - (g0 * (T[0] * T[0] + T[1] * T[1]) + g2 * T[2] * T[2]);
-                        const float hy = ky * ky - (g0 * (T[3] * T[3] + T[4] * T[4]) + g2 * T[5] * T[5]);
-                        const float exk = sqrtf(fmaxf(1e-4f, hx)), eyk = sqrtf(fmaxf(1e-4f, hy));
-                        const float rf = sqrtf(0.5f * m2);
-                        const float xlo = fminf(kx - exk, cx - rf), xhi = fmaxf(kx + exk, cx + rf);
-                        const float ylo = fminf(ky - eyk, cy - rf), yhi = fmaxf(ky + eyk, cy + rf);
+                        const float kx = g0 * (u0 * T[6] + u1 * T[7]) + g2 * u2 * T[8];
+                        const float ky = g0 * (v0 * T[6] + v1 * T[7]) + g2 * v2 * T[8];
+                        float hx = kx * kx - (g0 * (u0 * u0 + u1 * u1) + g2 * u2 * u2);
+                        float hy = ky * ky - (g0 * (v0 * v0 + v1 * v1) + g2 * v2 * v2);
+                        float hxy = kx * ky - (g0 * (u0 * v0 + u1 * v1) + g2 * u2 * v2);
+                        hx = fmaxf(hx, 0.0f); hy = fmaxf(hy, 0.0f);
+                        const float lim = sqrtf(hx * hy);
+                        hxy = fminf(fmaxf(hxy, -lim), lim);
+                        const float r = sqrtf(0.5f * m2) + sqrtf(kx * kx + ky * ky) + 0.25f;
+                        const float sxx = fmaf(hx, 1.002f, r * r), syy = fmaf(hy, 1.002f, r * r), sxy = hxy * 1.002f;
+                        const float det = sxx * syy - sxy * sxy;
+                        // the axis-aligned alternative (semi-axes sqrt(2) x the half sizes of the rectangle around both sets):
+                        // smaller when the two centres are far apart relative to the ellipse (strong perspective)
+                        const float exk = sqrtf(fmaxf(1e-4f, hx)), eyk = sqrtf(fmaxf(1e-4f, hy)), rf = sqrtf(0.5f * m2);
+                        const float xlo = fminf(kx - exk, -rf), xhi = fmaxf(kx + exk, rf);
+                        const float ylo = fminf(ky - eyk, -rf), yhi = fmaxf(ky + eyk, rf);
                         const float sx = 1.4143f * (0.5f * (xhi - xlo) * 1.001f + 0.05f), sy = 1.4143f * (0.5f * (yhi - ylo) * 1.001f + 0.05f);
-                        if (sx < 1.0e6f && sy < 1.0e6f) {  // (NaN / inf bounds: keep "no culling")
-                            k0 = make_float4(0.5f * (xlo + xhi), 0.5f * (ylo + yhi), -1.0f / (sx * sx), -1.0f / (sy * sy));
+                        if (sxx < 1.0e12f && syy < 1.0e12f && det > 0.0f && det < sx * sx * sy * sy) {
+                            const float idet = 1.0f / det;
+                            k0 = make_float4(cx + kx, cy + ky, -syy * idet, -sxx * idet);
+                            k1 = make_float4(2.0f * sxy * idet, ALPHA_MIN_LOG2 + 1.0f, 0.f, 0.f);  // test: d^T (S + r^2 I)^-1 d <= ~1
+                        } else if (sx < 1.0e6f && sy < 1.0e6f) {  // (NaN / inf bounds: keep "no culling")
+                            k0 = make_float4(cx + 0.5f * (xlo + xhi), cy + 0.5f * (ylo + yhi), -1.0f / (sx * sx), -1.0f / (sy * sy));
                             k1 = make_float4(0.f, ALPHA_MIN_LOG2 + 1.0f, 0.f, 0.f);  // test: dx^2 / sx^2 + dy^2 / sy^2 <= ~1
                         }
                     }

@@ -28,7 +28,7 @@ constexpr int SF_THREADS = 256;
 constexpr float SF_FILTER_INV_SQ = 2.0f;
 
 struct SurfelPair {
-    float u, v, pz, G, alpha, dx, dy;
+    float u, v, pz, ipz, G, alpha, dx, dy;
     float k0, k1, k2, l0, l1, l2;
     bool use3d;
 };
@@ -42,7 +42,8 @@ __device__ __forceinline__ bool surfel_pair(const float4 a, const float4 b, cons
     const float p2 = fmaf(r.k0, r.l1, -(r.k1 * r.l0));
     if (p2 == 0.0f) return false;
     r.pz = p2;
-    r.u = p0 / p2; r.v = p1 / p2;
+    r.ipz = rcp_approx(p2);  // (a denormal p2 gives inf / NaN here: rho3d <= rho2d is then false and the low-pass branch is taken)
+    r.u = p0 * r.ipz; r.v = p1 * r.ipz;
     const float rho3d = fmaf(r.u, r.u, r.v * r.v);
     r.dx = c.y - pxf; r.dy = c.z - pyf;
     const float rho2d = SF_FILTER_INV_SQ * fmaf(r.dx, r.dx, r.dy * r.dy);
@@ -90,18 +91,24 @@ surfel_render_fwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const 
         __syncthreads();
         const uint32_t cnt = min((uint32_t)SF_THREADS, n - base);
         if (__all_sync(0xffffffffu, done)) continue;
-        for (uint32_t j = 0; j < cnt && !done; j++) {
+        // warp-uniform walk: every lane evaluates the pair, finished lanes just stop updating (no per-lane branches around
+        // the arithmetic); the warp leaves the round once all 32 pixels are done (checked every 8 visited surfels)
+        uint32_t visited = 0;
+        for (uint32_t j = 0; j < cnt; j++) {
             if (!(s_mask[j] & wbit)) continue;  // (warp-uniform)
             SurfelPair q;
-            if (!surfel_pair(s_rec[4 * j], s_rec[4 * j + 1], s_rec[4 * j + 2], pxf, pyf, q)) continue;
-            if (q.alpha < 1.0f / 255.0f) continue;
+            bool ok = surfel_pair(s_rec[4 * j], s_rec[4 * j + 1], s_rec[4 * j + 2], pxf, pyf, q);
+            ok = ok && !done && q.alpha >= 1.0f / 255.0f;
             const float test_T = T * (1.0f - q.alpha);
-            if (test_T < 1e-4f) { done = true; break; }
-            const float w = q.alpha * T;
-            const float4 col = s_rec[4 * j + 3];
-            C0 = fmaf(col.x, w, C0); C1 = fmaf(col.y, w, C1); C2 = fmaf(col.z, w, C2);
-            T = test_T;
-            last = base + j + 1u;
+            if (ok && test_T < 1e-4f) { done = true; ok = false; }
+            if (ok) {
+                const float w = q.alpha * T;
+                const float4 col = s_rec[4 * j + 3];
+                C0 = fmaf(col.x, w, C0); C1 = fmaf(col.y, w, C1); C2 = fmaf(col.z, w, C2);
+                T = test_T;
+                last = base + j + 1u;
+            }
+            if ((++visited & 7u) == 0u && __all_sync(0xffffffffu, done)) break;
         }
     }
     if (inside) {
@@ -166,16 +173,17 @@ surfel_render_bwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const 
             if (!(s_id[j] & wbit)) continue;  // (warp-uniform) the surfel's cull ellipse misses this warp's 32 pixels
             const uint32_t contributor = base + (uint32_t)j;  // 0-based index of the entry in the tile's list
             if (contributor >= wlast) continue;
-            float g[15];
+            float g[16];
 #pragma unroll
-            for (int k = 0; k < 15; k++) g[k] = 0.f;
+            for (int k = 0; k < 16; k++) g[k] = 0.f;
             bool active = false;
             SurfelPair q;
             const float4 ra = s_rec[4 * j], rb = s_rec[4 * j + 1], rc = s_rec[4 * j + 2];
             if (contributor < last && surfel_pair(ra, rb, rc, pxf, pyf, q) && q.alpha >= 1.0f / 255.0f) {
                 active = true;
                 const float4 col = s_rec[4 * j + 3];
-                T = T / (1.0f - q.alpha);
+                const float inv_1ma = rcp_approx(1.0f - q.alpha);
+                T = T * inv_1ma;
                 acc0 = last_alpha * lc0 + (1.0f - last_alpha) * acc0;
                 acc1 = last_alpha * lc1 + (1.0f - last_alpha) * acc1;
                 acc2 = last_alpha * lc2 + (1.0f - last_alpha) * acc2;
@@ -185,12 +193,12 @@ surfel_render_bwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const 
                 g[12] = wgt * dp0; g[13] = wgt * dp1; g[14] = wgt * dp2;
                 dL_dalpha *= T;
                 last_alpha = q.alpha;
-                dL_dalpha += (-T_final / (1.0f - q.alpha)) * bg_dot;
+                dL_dalpha += (-T_final * inv_1ma) * bg_dot;
                 const float dL_dG = rc.w * dL_dalpha;
                 g[11] = q.G * dL_dalpha;
                 if (q.use3d) {
                     const float dLu = dL_dG * -q.G * q.u, dLv = dL_dG * -q.G * q.v;
-                    const float dsx = dLu / q.pz, dsy = dLv / q.pz;
+                    const float dsx = dLu * q.ipz, dsy = dLv * q.ipz;
                     const float d0 = dsx, d1 = dsy, d2 = -(dsx * q.u + dsy * q.v);
                     const float dk0 = q.l1 * d2 - q.l2 * d1, dk1 = q.l2 * d0 - q.l0 * d2, dk2 = q.l0 * d1 - q.l1 * d0;
                     const float dl0 = d1 * q.k2 - d2 * q.k1, dl1 = d2 * q.k0 - d0 * q.k2, dl2 = d0 * q.k1 - d1 * q.k0;
@@ -203,18 +211,37 @@ surfel_render_bwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const 
                 }
             }
             if (!__any_sync(0xffffffffu, active)) continue;
+            // warp sum of the 15 values by recursive halving: at each level a lane keeps one half of its values and trades the
+            // other half with its partner, so 8 + 4 + 2 + 1 + 1 shuffles leave lane L with the warp total of value L >> 1
+            // (instead of 15 x 5 shuffles for 15 full butterflies); four more shuffles gather them for the vector reductions
+            {
+                const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4, h1 = lane & 2;
+                float a[8], b[4], c[2];
 #pragma unroll
-            for (int k = 0; k < 15; k++) {
+                for (int k = 0; k < 8; k++) {
+                    const float send = h4 ? g[k] : g[k + 8], keep = h4 ? g[k + 8] : g[k];
+                    a[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                }
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) g[k] += __shfl_xor_sync(0xffffffffu, g[k], o);
-            }
-            if (lane < 4) {
-                float* dst = sgrad2 + 16 * (size_t)(s_id[j] >> 8) + 4 * lane;
-                const float4 v = lane == 0 ? make_float4(g[0], g[1], g[2], g[3])
-                               : lane == 1 ? make_float4(g[4], g[5], g[6], g[7])
-                               : lane == 2 ? make_float4(g[8], g[9], g[10], g[11])
-                                           : make_float4(g[12], g[13], g[14], 0.f);
-                red_add_f4(dst, v);
+                for (int k = 0; k < 4; k++) {
+                    const float send = h3 ? a[k] : a[k + 4], keep = h3 ? a[k + 4] : a[k];
+                    b[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                }
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    const float send = h2 ? b[k] : b[k + 2], keep = h2 ? b[k + 2] : b[k];
+                    c[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                }
+                float t = (h1 ? c[1] : c[0]) + __shfl_xor_sync(0xffffffffu, h1 ? c[0] : c[1], 2);
+                t += __shfl_xor_sync(0xffffffffu, t, 1);
+                // lane L holds the total of value (L >> 1) & 15 with bit order: bit1 -> 1, bit2 -> 2, bit3 -> 4, bit4 -> 8
+                const int src = 8 * (lane & 3);
+                float4 v;
+                v.x = __shfl_sync(0xffffffffu, t, src);
+                v.y = __shfl_sync(0xffffffffu, t, src + 2);
+                v.z = __shfl_sync(0xffffffffu, t, src + 4);
+                v.w = __shfl_sync(0xffffffffu, t, src + 6);
+                if (lane < 4) red_add_f4(sgrad2 + 16 * (size_t)(s_id[j] >> 8) + 4 * lane, v);
             }
         }
     }
