@@ -13,8 +13,8 @@
 //   then the 3DGS compositing rules (alpha < 1/255 skip, T (1 - alpha) < 1e-4 stop, n_contrib, final_T, background).
 //
 // Design: correctness first.  One CTA per 16x16 tile, warp w = the 8x4-pixel sub-rectangle (w & 1, w >> 1), 64-byte records
-// staged 256 per round in shared memory; a warp skips every surfel whose sub-tile mask bit is clear (the mask is computed at
-// emission from a conservative axis-aligned ellipse around the surfel's alpha >= 1/255 support, preprocess_fwd.cu); the
+// staged 256 per round in shared memory; a warp visits only the surfels whose sub-tile mask bit is set (ballots over the staged
+// list; the mask is computed at emission from the surfel's projected alpha >= 1/255 ellipse, preprocess_fwd.cu); the
 // backward also stops at the warp's deepest last contributor, reduces its 15 per-pair sums over the warp with shuffles (skipped
 // when no lane blended the pair) and sends them with one 128-bit vector reduction per four floats.  The 3DGS path's packed
 // fp32x2 arithmetic, straight-line predicated loops and two-phase backward are NOT applied here.
@@ -92,23 +92,31 @@ surfel_render_fwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const 
         const uint32_t cnt = min((uint32_t)SF_THREADS, n - base);
         if (__all_sync(0xffffffffu, done)) continue;
         // warp-uniform walk: every lane evaluates the pair, finished lanes just stop updating (no per-lane branches around
-        // the arithmetic); the warp leaves the round once all 32 pixels are done (checked every 8 visited surfels)
+        // the arithmetic); the warp leaves the round once all 32 pixels are done (checked every 8 visited surfels).
+        // the warp's entries of this round as 32-bit masks (one ballot per 32 list entries), walked by find-first-set: the
+        // loop costs nothing for the entries whose cull ellipse misses this warp's pixels
         uint32_t visited = 0;
-        for (uint32_t j = 0; j < cnt; j++) {
-            if (!(s_mask[j] & wbit)) continue;  // (warp-uniform)
-            SurfelPair q;
-            bool ok = surfel_pair(s_rec[4 * j], s_rec[4 * j + 1], s_rec[4 * j + 2], pxf, pyf, q);
-            ok = ok && !done && q.alpha >= 1.0f / 255.0f;
-            const float test_T = T * (1.0f - q.alpha);
-            if (ok && test_T < 1e-4f) { done = true; ok = false; }
-            if (ok) {
-                const float w = q.alpha * T;
-                const float4 col = s_rec[4 * j + 3];
-                C0 = fmaf(col.x, w, C0); C1 = fmaf(col.y, w, C1); C2 = fmaf(col.z, w, C2);
-                T = test_T;
-                last = base + j + 1u;
+        bool stop = false;
+        for (uint32_t g0 = 0; g0 < cnt && !stop; g0 += 32) {
+            const uint32_t jj = g0 + lane;
+            uint32_t m = __ballot_sync(0xffffffffu, jj < cnt && (s_mask[jj] & wbit));
+            while (m) {
+                const uint32_t j = g0 + (uint32_t)__ffs((int)m) - 1u;
+                m &= m - 1u;
+                SurfelPair q;
+                bool ok = surfel_pair(s_rec[4 * j], s_rec[4 * j + 1], s_rec[4 * j + 2], pxf, pyf, q);
+                ok = ok && !done && q.alpha >= 1.0f / 255.0f;
+                const float test_T = T * (1.0f - q.alpha);
+                if (ok && test_T < 1e-4f) { done = true; ok = false; }
+                if (ok) {
+                    const float w = q.alpha * T;
+                    const float4 col = s_rec[4 * j + 3];
+                    C0 = fmaf(col.x, w, C0); C1 = fmaf(col.y, w, C1); C2 = fmaf(col.z, w, C2);
+                    T = test_T;
+                    last = base + j + 1u;
+                }
+                if ((++visited & 7u) == 0u && __all_sync(0xffffffffu, done)) { stop = true; break; }
             }
-            if ((++visited & 7u) == 0u && __all_sync(0xffffffffu, done)) break;
         }
     }
     if (inside) {
@@ -169,10 +177,16 @@ surfel_render_bwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const 
         __syncthreads();
         const int cnt = (int)min((uint32_t)SF_THREADS, n - base);
         if (base >= wlast) continue;  // this warp's pixels all stopped earlier in the list
-        for (int j = cnt - 1; j >= 0; j--) {
-            if (!(s_id[j] & wbit)) continue;  // (warp-uniform) the surfel's cull ellipse misses this warp's 32 pixels
+        // the warp's entries of this round as 32-bit masks (one ballot per 32 list entries: cull bit set, not past the warp's
+        // deepest last contributor), walked from the top bit down
+        for (int g0 = ((cnt - 1) >> 5) << 5; g0 >= 0; g0 -= 32) {
+          const int jj = g0 + lane;
+          uint32_t m = __ballot_sync(0xffffffffu, jj < cnt && (s_id[jj] & wbit) && base + (uint32_t)jj < wlast);
+          while (m) {
+            const int bit = 31 - __clz((int)m);
+            m ^= 1u << bit;
+            const int j = g0 + bit;
             const uint32_t contributor = base + (uint32_t)j;  // 0-based index of the entry in the tile's list
-            if (contributor >= wlast) continue;
             float g[16];
 #pragma unroll
             for (int k = 0; k < 16; k++) g[k] = 0.f;
@@ -243,6 +257,7 @@ surfel_render_bwd_kernel(Cam cam, const uint32_t* __restrict__ tile_base, const 
                 v.w = __shfl_sync(0xffffffffu, t, src + 6);
                 if (lane < 4) red_add_f4(sgrad2 + 16 * (size_t)(s_id[j] >> 8) + 4 * lane, v);
             }
+          }
         }
     }
 }

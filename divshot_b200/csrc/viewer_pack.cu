@@ -3,15 +3,17 @@
 // of every Gaussian once and writes 104 B of viewer records, 340 B/Gaussian of compulsory traffic.
 //
 // Layout of the work: a CTA of 128 threads owns 128 consecutive Gaussians per trip of a grid-stride loop.  The only wide
-// row, shN (180 B per Gaussian), is a contiguous 23 KB span for the CTA: it is staged into shared memory with 128-bit
-// loads (every sector fully used) and each thread then reads its own row at stride 45 words (odd: conflict-free).  The
-// five narrow rows (12-16 B) are read directly; a warp's loads of one array cover one contiguous 384-512 B span.
-// Records leave as 128-bit stores.  The bounding box is kept in registers across trips, reduced by shuffles, and leaves
-// as six integer atomics per warp at the end (order-preserving float -> uint map).  Grid = a multiple of the SM count.
+// row, shN (180 B per Gaussian), is a contiguous 23 KB span for the CTA: it is staged into shared memory with asynchronous
+// 128-bit copies (every sector fully used, 12 in flight per thread) and each thread then reads its own row at stride 45
+// words (odd: conflict-free).  The five narrow rows (12-16 B) are read directly; a warp's loads of one array cover one
+// contiguous 384-512 B span.  Records leave as 128-bit stores.  The bounding box is kept in registers across trips, reduced
+// by shuffles, and leaves as six integer atomics per warp at the end (order-preserving float -> uint map).
+// Grid = SM count x the CTAs that are resident at once (one wave).
 // Compiled with -fmad=false (viewer_pack_ops.h is a literal operation sequence).
 #include <cuda_runtime.h>
 
 #include <cfloat>
+#include <cstdlib>
 
 #include "dvs_viewer_pack.h"
 #include "viewer_pack_ops.h"
@@ -19,8 +21,32 @@
 namespace {
 using namespace dvs_vp;
 constexpr int kThreads = 128;
+constexpr int kCtasPerSm = 8;  // default register budget: 8 x 128 x 64 registers, 8 x 23.5 KB of staged rows per SM (DVS_VP_CTAS=6|7|8)
 
-__global__ void __launch_bounds__(kThreads)
+// Stage the CTA's contiguous span of shN rows into shared memory with asynchronous 16-byte copies (LDGSTS): all of a thread's
+// (up to) 12 copies are in flight at once and none passes through registers.  The plain loop of viewer_pack_ops.h (pack_stage,
+// kept for the host harness: same indexing) left ONE 16-byte load per thread in flight — a tile's staging then cost 12 memory
+// latencies back to back, two thirds of the kernel's time (round-2 ncu: long-scoreboard stalls 3.4 per issue, 2.8 TB/s).
+__device__ __forceinline__ void stage_rows_async(const PackArgs& a, float* s_shn, int tid, long long base, int cnt) {
+    const float* src = a.shN + base * kShRest;
+    const int n_words = cnt * kShRest;
+    if (a.shn_vec_ok) {
+        const int n_vec = n_words >> 2;
+        const unsigned dst0 = (unsigned)__cvta_generic_to_shared(s_shn);
+#pragma unroll
+        for (int it = 0; it < (kThreads * kShRest / 4 + kThreads - 1) / kThreads; it++) {
+            const int i = tid + it * kThreads;
+            if (i < n_vec) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + 16u * (unsigned)i), "l"(src + 4 * i) : "memory");
+        }
+        for (int i = (n_vec << 2) + tid; i < n_words; i += kThreads) s_shn[i] = src[i];
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    } else {
+        pack_stage(a, s_shn, tid, kThreads, base, cnt);
+    }
+}
+
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(kThreads, MIN_CTAS)
 viewer_pack_kernel(const float* __restrict__ means, const float* __restrict__ scales, const float* __restrict__ quats,
                    const float* __restrict__ opac, const float* __restrict__ sh0, const float* __restrict__ shN, int64_t N,
                    uint4* __restrict__ out_g, uint2* __restrict__ out_c, uint4* __restrict__ out_sh,
@@ -34,7 +60,7 @@ viewer_pack_kernel(const float* __restrict__ means, const float* __restrict__ sc
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t base = tile * kThreads;
         const int cnt = (int)(N - base < kThreads ? N - base : kThreads);
-        pack_stage(a, s_shn, tid, kThreads, base, cnt);
+        stage_rows_async(a, s_shn, tid, base, cnt);
         __syncthreads();
         pack_compute(a, s_shn, tid, base, cnt, lo, hi);
         __syncthreads();  // the next trip overwrites s_shn
@@ -77,10 +103,25 @@ DVS_VP_EXPORT int dvs_viewer_pack(const float* means, const float* scales, const
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t n_tiles = (N + kThreads - 1) / kThreads;
-    const int64_t grid = n_tiles < (int64_t)sms * 8 ? n_tiles : (int64_t)sms * 8;  // 8 CTAs of 128 threads per SM
-    viewer_pack_kernel<<<(unsigned)grid, kThreads, 0, st>>>(means, scales, quats, opacities, sh0, shN, N,
-                                                           static_cast<uint4*>(out_gaussians), static_cast<uint2*>(out_colors),
-                                                           static_cast<uint4*>(out_sh), bbox_ordered, misaligned(shN, 16) ? 0 : 1);
+    // exactly one resident wave (ncu, round 2: 8 CTAs per SM were launched where 6 fit, and the 1/3 wave left over ran at a
+    // third of the occupancy for as long as the first)
+    using Kernel = void (*)(const float*, const float*, const float*, const float*, const float*, const float*, int64_t, uint4*,
+                            uint2*, uint4*, uint32_t*, int);
+    static Kernel kernel = nullptr;
+    static int resident = 0;
+    if (!kernel) {
+        int want = kCtasPerSm;
+        if (const char* e = getenv("DVS_VP_CTAS")) want = atoi(e);
+        kernel = want <= 6 ? viewer_pack_kernel<6> : want == 7 ? viewer_pack_kernel<7> : viewer_pack_kernel<8>;
+        int occ = 0;
+        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, 0) != cudaSuccess || occ < 1) occ = 4;
+        resident = occ;
+    }
+    const int64_t grid = n_tiles < (int64_t)sms * resident ? n_tiles : (int64_t)sms * resident;
+    kernel<<<(unsigned)grid, kThreads, 0, st>>>(means, scales, quats, opacities, sh0, shN, N, static_cast<uint4*>(out_gaussians),
+                                                static_cast<uint2*>(out_colors), static_cast<uint4*>(out_sh), bbox_ordered,
+                                                misaligned(shN, 16) ? 0 : 1);
     return (int)cudaGetLastError();
 }
 

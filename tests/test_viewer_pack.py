@@ -214,3 +214,14 @@ def test_editor_style_hand_off_through_the_plugin(ops, tmp_path):
     ref = u.pack_with_reference(m) if os.path.exists(u.REF_SO) else u.pack_with_host_ops(ops, m)
     for name, a, b in zip(("gaussians", "colors", "sh", "bbox"), (g, c, sh, box), ref):
         assert a.tobytes() == b.tobytes(), name
+
+
+def test_float_quantiser_equals_the_double_expression(tmp_path):
+    """quantise_unit<S> (the float / integer form the kernel uses instead of float -> double -> int64 conversions) against the
+    reference's literal double expression (pack_utils.h:56-67): every 1009th float of [-1.125, 1.125] plus 64 floats either side of
+    every k / S boundary, both widths.  (stride 1 — all 2.1e9 floats — was run when the form was written: 0 mismatches.)"""
+    exe = str(tmp_path / "quantise_check")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fopenmp", "-ffp-contract=off", "-I", os.path.join(ROOT, "divshot_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "native", "viewer_pack_quantise_check.cpp"), "-o", exe])
+    r = subprocess.run([exe, "1009"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "mismatches_11bit 0 mismatches_10bit 0" in r.stdout, r.stdout + r.stderr

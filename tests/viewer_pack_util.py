@@ -39,6 +39,14 @@ def make_model(N, seed, active_degree=3):
         m["shN"][16] = -np.abs(m["shN"][16]); m["shN"][16, 0] = -1e-3
         m["shN"][22] = 1e-30; m["shN"][22, 0] = -5.0   # quirk taken to the limit: c[0]/max = -5e30, beyond int64 after scaling
         m["shN"][23] = 0; m["shN"][23, 0] = -2.0       # scale stays +0 after the loop?  no: max(-2, |0|) = 0 -> no division
+        # rows around the guards of the kernel's short-form division / float quantiser (viewer_pack_ops.h: pack_sh_rest_from)
+        m["shN"][24] = m["shN"][24] * np.float32(2.0 ** -58)           # whole row tiny but inside the short form's range
+        m["shN"][25, 5] = np.float32(2.0 ** -63)                       # one magnitude below it: the guarded general form
+        m["shN"][26] = np.where(np.arange(45) % 2 == 0, 0.37, -0.37)   # every quotient exactly +-1
+        m["shN"][27] = (2.0 * np.arange(45) * 45 / 2047.0 - 1.0); m["shN"][27, 44] = 1.0  # scale 1, values on k / S boundaries
+        m["shN"][28] = m["shN"][28] * np.float32(2.0 ** 58)            # large row, still inside
+        m["shN"][29] = m["shN"][29] * np.float32(2.0 ** 70)            # scale above the range: general form
+        m["shN"][30] = 0; m["shN"][30, 9] = 0.25; m["shN"][30, 10] = -0.0  # zeros of both signs beside one non-zero
         m["sh0"][17] = [-1.7724539, 1.7724539, 0.0]    # colours at 0 / 1 / 0.5
         m["sh0"][18] = [1e-12, -1e-12, 300.0]
         m["means"][19] = [-0.0, 0.0, 1e-42]            # signed zero, float subnormal
