@@ -469,7 +469,11 @@ cudaError_t launch_tile_sort(int T, uint32_t bin_stride, const uint32_t* tile_ba
     // In single-pass mode no tile can hold more than bin_stride entries (a longer one overflows its bin and the
     // step is redone), so the kernels of the length classes above that bound are not launched at all.
     const uint32_t max_len = bin_stride ? bin_stride : 0xffffffffu;
-    static bool attr_done = false;
+    // (the dynamic shared-memory limit is a per-device, per-function attribute: once per device, not once per process)
+    static bool attr_done_dev[64] = {};
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    bool& attr_done = attr_done_dev[cur_dev & 63];
     if (!attr_done) {
         cudaFuncSetAttribute(tile_bucket_sort_kernel<256, 1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)bucket_smem_bytes<1024, true>());

@@ -5,8 +5,8 @@
 // Layout of the work: a CTA of 128 threads owns 128 consecutive Gaussians per trip of a grid-stride loop.  The only wide
 // row, shN (180 B per Gaussian), is a contiguous 23 KB span for the CTA: it is staged into shared memory with asynchronous
 // 128-bit copies (every sector fully used, 12 in flight per thread) and each thread then reads its own row at stride 45
-// words (odd: conflict-free).  The five narrow rows (12-16 B) are read directly; a warp's loads of one array cover one
-// contiguous 384-512 B span.  Records leave as 128-bit stores.  The bounding box is kept in registers across trips, reduced
+// words (odd: conflict-free).  The five narrow rows (12-16 B) are read directly and packed while those copies are in
+// flight; a warp's loads of one array cover one contiguous 384-512 B span.  Records leave as 128-bit stores.  The bounding box is kept in registers across trips, reduced
 // by shuffles, and leaves as six integer atomics per warp at the end (order-preserving float -> uint map).
 // Grid = SM count x the CTAs that are resident at once (one wave).
 // Compiled with -fmad=false (viewer_pack_ops.h is a literal operation sequence).
@@ -24,7 +24,8 @@ constexpr int kThreads = 128;
 constexpr int kCtasPerSm = 8;  // default register budget: 8 x 128 x 64 registers, 8 x 23.5 KB of staged rows per SM (DVS_VP_CTAS=6|7|8)
 
 // Stage the CTA's contiguous span of shN rows into shared memory with asynchronous 16-byte copies (LDGSTS): all of a thread's
-// (up to) 12 copies are in flight at once and none passes through registers.  The plain loop of viewer_pack_ops.h (pack_stage,
+// (up to) 12 copies are in flight at once and none passes through registers; the caller waits for them (cp.async.wait_group 0,
+// then the CTA barrier) only after it has packed the narrow rows.  The plain loop of viewer_pack_ops.h (pack_stage,
 // kept for the host harness: same indexing) left ONE 16-byte load per thread in flight — a tile's staging then cost 12 memory
 // latencies back to back, two thirds of the kernel's time (round-2 ncu: long-scoreboard stalls 3.4 per issue, 2.8 TB/s).
 __device__ __forceinline__ void stage_rows_async(const PackArgs& a, float* s_shn, int tid, long long base, int cnt) {
@@ -39,7 +40,7 @@ __device__ __forceinline__ void stage_rows_async(const PackArgs& a, float* s_shn
             if (i < n_vec) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + 16u * (unsigned)i), "l"(src + 4 * i) : "memory");
         }
         for (int i = (n_vec << 2) + tid; i < n_words; i += kThreads) s_shn[i] = src[i];
-        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
     } else {
         pack_stage(a, s_shn, tid, kThreads, base, cnt);
     }
@@ -60,9 +61,11 @@ viewer_pack_kernel(const float* __restrict__ means, const float* __restrict__ sc
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t base = tile * kThreads;
         const int cnt = (int)(N - base < kThreads ? N - base : kThreads);
-        stage_rows_async(a, s_shn, tid, base, cnt);
+        stage_rows_async(a, s_shn, tid, base, cnt);   // copies in flight ...
+        pack_narrow(a, tid, base, cnt, lo, hi);       // ... while the narrow rows are loaded, packed and stored
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
-        pack_compute(a, s_shn, tid, base, cnt, lo, hi);
+        pack_wide(a, s_shn, tid, base, cnt);
         __syncthreads();  // the next trip overwrites s_shn
     }
 #pragma unroll
@@ -108,8 +111,9 @@ DVS_VP_EXPORT int dvs_viewer_pack(const float* means, const float* scales, const
     using Kernel = void (*)(const float*, const float*, const float*, const float*, const float*, const float*, int64_t, uint4*,
                             uint2*, uint4*, uint32_t*, int);
     static Kernel kernel = nullptr;
-    static int resident = 0;
-    if (!kernel) {
+    static int resident_dev[64] = {};  // (attributes and occupancy are per device)
+    int& resident = resident_dev[dev & 63];
+    if (!kernel || resident == 0) {
         int want = kCtasPerSm;
         if (const char* e = getenv("DVS_VP_CTAS")) want = atoi(e);
         kernel = want <= 6 ? viewer_pack_kernel<6> : want == 7 ? viewer_pack_kernel<7> : viewer_pack_kernel<8>;

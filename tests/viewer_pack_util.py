@@ -47,6 +47,8 @@ def make_model(N, seed, active_degree=3):
         m["shN"][28] = m["shN"][28] * np.float32(2.0 ** 58)            # large row, still inside
         m["shN"][29] = m["shN"][29] * np.float32(2.0 ** 70)            # scale above the range: general form
         m["shN"][30] = 0; m["shN"][30, 9] = 0.25; m["shN"][30, 10] = -0.0  # zeros of both signs beside one non-zero
+        m["shN"][31, 3] = 1e-40; m["shN"][31, 4] = -1e-37; m["shN"][31, 5] = -1e-45   # subnormal / tiny numerators, ordinary scale
+        m["shN"][32, 0] = -np.abs(m["shN"][32]).max() * np.float32(1.0000001)         # c[0] negative, just past the scale
         m["sh0"][17] = [-1.7724539, 1.7724539, 0.0]    # colours at 0 / 1 / 0.5
         m["sh0"][18] = [1e-12, -1e-12, 300.0]
         m["means"][19] = [-0.0, 0.0, 1e-42]            # signed zero, float subnormal
