@@ -21,7 +21,8 @@
 namespace {
 using namespace dvs_vp;
 constexpr int kThreads = 128;
-constexpr int kCtasPerSm = 8;  // default register budget: 8 x 128 x 64 registers, 8 x 23.5 KB of staged rows per SM (DVS_VP_CTAS=6|7|8)
+constexpr int kCtasPerSm = 6;  // default register budget: 6 CTAs per SM (85 registers; measured 0.0715 ms against 0.0755 ms with 8 x 64)
+constexpr int kPrefetch = 1;   // DVS_VP_CTAS=5|6|8 and DVS_VP_PREFETCH=0|1 select the other instantiations (A/B)
 
 // Stage the CTA's contiguous span of shN rows into shared memory with asynchronous 16-byte copies (LDGSTS): all of a thread's
 // (up to) 12 copies are in flight at once and none passes through registers; the caller waits for them (cp.async.wait_group 0,
@@ -46,7 +47,9 @@ __device__ __forceinline__ void stage_rows_async(const PackArgs& a, float* s_shn
     }
 }
 
-template <int MIN_CTAS>
+// PREFETCH: the narrow rows of the CTA's NEXT tile are loaded into registers before the wide half of the current one runs,
+// so their latency (the top stall of the plain form: 14 % of the samples) hides behind ~700 instructions of arithmetic.
+template <int MIN_CTAS, bool PREFETCH>
 __global__ void __launch_bounds__(kThreads, MIN_CTAS)
 viewer_pack_kernel(const float* __restrict__ means, const float* __restrict__ scales, const float* __restrict__ quats,
                    const float* __restrict__ opac, const float* __restrict__ sh0, const float* __restrict__ shN, int64_t N,
@@ -58,11 +61,19 @@ viewer_pack_kernel(const float* __restrict__ means, const float* __restrict__ sc
     const int tid = threadIdx.x;
     float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     const int64_t n_tiles = (N + kThreads - 1) / kThreads;
+    NarrowRows rows{};
+    if (PREFETCH && (int64_t)blockIdx.x * kThreads + tid < N) rows = load_narrow(a, (int64_t)blockIdx.x * kThreads + tid);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t base = tile * kThreads;
         const int cnt = (int)(N - base < kThreads ? N - base : kThreads);
         stage_rows_async(a, s_shn, tid, base, cnt);   // copies in flight ...
-        pack_narrow(a, tid, base, cnt, lo, hi);       // ... while the narrow rows are loaded, packed and stored
+        if (PREFETCH) {                               // ... while the narrow rows are packed and stored
+            if (tid < cnt) pack_narrow_rows(a, rows, base + tid, lo, hi);
+            const int64_t nxt = (tile + gridDim.x) * kThreads + tid;
+            if (nxt < N) rows = load_narrow(a, nxt);
+        } else {
+            pack_narrow(a, tid, base, cnt, lo, hi);
+        }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         pack_wide(a, s_shn, tid, base, cnt);
@@ -114,9 +125,11 @@ DVS_VP_EXPORT int dvs_viewer_pack(const float* means, const float* scales, const
     static int resident_dev[64] = {};  // (attributes and occupancy are per device)
     int& resident = resident_dev[dev & 63];
     if (!kernel || resident == 0) {
-        int want = kCtasPerSm;
+        int want = kCtasPerSm, prefetch = kPrefetch;
         if (const char* e = getenv("DVS_VP_CTAS")) want = atoi(e);
-        kernel = want <= 6 ? viewer_pack_kernel<6> : want == 7 ? viewer_pack_kernel<7> : viewer_pack_kernel<8>;
+        if (const char* e = getenv("DVS_VP_PREFETCH")) prefetch = atoi(e);
+        kernel = prefetch ? (want <= 5 ? viewer_pack_kernel<5, true> : want == 6 ? viewer_pack_kernel<6, true> : viewer_pack_kernel<8, true>)
+                          : (want <= 5 ? viewer_pack_kernel<5, false> : want == 6 ? viewer_pack_kernel<6, false> : viewer_pack_kernel<8, false>);
         int occ = 0;
         cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, 0) != cudaSuccess || occ < 1) occ = 4;
