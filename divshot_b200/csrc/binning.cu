@@ -16,11 +16,16 @@
 //
 // Roofline: HBM-light (8 B written + 8 B read + 4 B written per duplicate); sort is shared-memory /
 // issue bound.  Algorithmic bytes per SURVEY.md §8(d): 28 B per duplicate (we move 20).
+#include <cooperative_groups.h>
+
+#include <cstdlib>
+
 #include "common.cuh"
 #include "emit.cuh"
 #include "kernels.h"
 
 namespace dvs {
+namespace cg = cooperative_groups;
 
 // ---------------------------------------------------------------------------------------------
 // A2/A5: single-CTA exclusive scan over tile counts (T <= ~65k), warp-shuffle based.
@@ -185,11 +190,143 @@ tile_scan_kernel(int T, uint32_t* __restrict__ tile_count, uint32_t* __restrict_
     }
 }
 
+// The same scan spread over a thread-block CLUSTER of 8 CTAs (8 SMs).  The single-CTA form above is bound by what one SM's
+// load/store path can do with sector-granular traffic — the counters are padded to one 32-byte sector each (so that the
+// preprocess kernel's atomics do not collide), which makes T sector reads, T sector writes (zeroing) and, with eight
+// consecutive tiles per thread, 32-sector tile_base / class-list stores per warp: ~20 us at c3 (6300 tiles), 2.3 % of the
+// step and a serial link between the preprocess and sort kernels.  Here CTA r of the cluster owns tiles [r * 1024 * per,
+// (r + 1) * 1024 * per), `per` consecutive tiles per thread (1 up to 8192 tiles: lanes <-> consecutive tiles, so the
+// tile_base stores coalesce), publishes its total and maximum in its own shared memory, and after ONE cluster barrier
+// reads the other seven through distributed shared memory to form its prefix: no global flags, no second launch.
+constexpr int SCAN_CLUSTER = 8;
+constexpr int SCAN_CLUSTER_MAX_PER = 4;  // up to 32768 tiles; beyond that the single-CTA kernel runs
+
+__global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SCAN_THREADS)
+tile_scan_cluster_kernel(int T, int per, uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_base,
+                         uint32_t* __restrict__ tile_cursor, uint32_t* __restrict__ info, uint32_t dup_capacity,
+                         uint32_t* __restrict__ class_tiles, unsigned long long* __restrict__ stats) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t warp_max[32];
+    __shared__ uint32_t s_pub[2];  // this CTA's total and maximum, read by the whole cluster
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned rank = cluster.block_rank();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (rank == 0 && threadIdx.x < NUM_SORT_CLASSES) info[4 + threadIdx.x] = 0u;  // (ordered before the atomics by the cluster barrier)
+    const int first = ((int)rank * SCAN_THREADS + (int)threadIdx.x) * per;
+    uint32_t c[SCAN_CLUSTER_MAX_PER];
+    uint32_t sum = 0, mx = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_CLUSTER_MAX_PER; k++) {
+        const int t = first + k;
+        c[k] = (k < per && t < T) ? tile_count[(size_t)t * TILE_CTR_STRIDE] : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < SCAN_CLUSTER_MAX_PER; k++) {
+        if (c[k]) tile_count[(size_t)(first + k) * TILE_CTR_STRIDE] = 0u;  // dead after this read: zeroed for the next forward
+        sum += c[k];
+        mx = max(mx, c[k]);
+    }
+    uint32_t v = sum;  // inclusive warp scan of the per-thread sums
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, v, off);
+        if (lane >= off) v += n;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    if (lane == 31) warp_sums[warp] = v;
+    if (lane == 0) warp_max[warp] = mx;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = warp_sums[lane], m = warp_max[lane];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, w, off);
+            if (lane >= off) w += n;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, off));
+        warp_sums[lane] = w;  // inclusive over warps
+        if (lane == 31) { s_pub[0] = w; s_pub[1] = m; }
+    }
+    cluster.sync();  // (also the CTA barrier for warp_sums)
+    unsigned long long before = 0, total = 0;
+    uint32_t gmax = 0;
+#pragma unroll
+    for (unsigned r = 0; r < SCAN_CLUSTER; r++) {
+        const uint32_t* p = cluster.map_shared_rank(s_pub, r);
+        const uint32_t t = p[0];
+        if (r < rank) before += t;
+        total += t;
+        gmax = max(gmax, p[1]);
+    }
+    uint32_t run = (uint32_t)before + (warp ? warp_sums[warp - 1] : 0u) + v - sum;
+    // per-class work lists for the sort kernels (info[4+q] = count of class q), as in the single-CTA kernel
+    uint32_t mycnt[NUM_SORT_CLASSES];
+#pragma unroll
+    for (int q = 0; q < NUM_SORT_CLASSES; q++) mycnt[q] = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_CLUSTER_MAX_PER; k++)
+        if (c[k]) {
+            const int cls = sort_class_of(c[k]);
+#pragma unroll
+            for (int q = 0; q < NUM_SORT_CLASSES; q++) mycnt[q] += (cls == q) ? 1u : 0u;
+        }
+    uint32_t slot[NUM_SORT_CLASSES];
+#pragma unroll
+    for (int q = 0; q < NUM_SORT_CLASSES; q++) {
+        uint32_t inc = mycnt[q];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, inc, off);
+            if (lane >= off) inc += n;
+        }
+        const uint32_t wtot = __shfl_sync(0xffffffffu, inc, 31);
+        uint32_t b = 0;
+        if (lane == 0 && wtot) b = atomicAdd(info + 4 + q, wtot);
+        slot[q] = __shfl_sync(0xffffffffu, b, 0) + inc - mycnt[q];
+    }
+#pragma unroll
+    for (int k = 0; k < SCAN_CLUSTER_MAX_PER; k++) {
+        const int t = first + k;
+        if (k < per && t < T) {
+            tile_base[t] = run;
+            if (tile_cursor) tile_cursor[(size_t)t * TILE_CTR_STRIDE] = run;
+            if (c[k]) {
+                const int cls = sort_class_of(c[k]);
+#pragma unroll
+                for (int q = 0; q < NUM_SORT_CLASSES; q++)
+                    if (cls == q) class_tiles[(size_t)q * T + slot[q]++] = (uint32_t)t;
+            }
+        }
+        run += c[k];
+    }
+    if (rank == 0 && threadIdx.x == 0) {
+        tile_base[T] = (uint32_t)total;
+        info[0] = (uint32_t)total;
+        info[1] = gmax;
+        const bool ovf = total > (unsigned long long)dup_capacity || info[10] != 0u;  // info[10]: a fixed-stride bin overflowed
+        info[2] = ovf ? 1u : 0u;
+        if (ovf) { info[3] += 1u; info[9] = (uint32_t)min(total, 0xffffffffull); }  // sticky (deferred-check mode)
+        info[10] = 0u;
+        const unsigned long long vv = stats[0], d = stats[1];
+        info[12] = (uint32_t)vv; info[13] = (uint32_t)(vv >> 32); info[14] = (uint32_t)d; info[15] = (uint32_t)(d >> 32);
+        stats[0] = 0ull; stats[1] = 0ull;
+    }
+    cluster.sync();  // no CTA leaves while another may still read its s_pub
+}
+
 cudaError_t launch_tile_scan(int T, uint32_t* tile_count, uint32_t* tile_base, uint32_t* tile_cursor,
                              uint32_t* info, uint32_t dup_capacity, uint32_t* class_tiles, uint32_t* tile_order,
                              unsigned long long* stats, cudaStream_t st) {
-    tile_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(T, tile_count, tile_base, tile_cursor, info, dup_capacity,
-                                                 class_tiles, tile_order, stats);
+    static const bool single = [] { const char* e = getenv("DVS_SCAN_SINGLE_CTA"); return e && atoi(e) != 0; }();  // A/B switch
+    const int per = (T + SCAN_CLUSTER * SCAN_THREADS - 1) / (SCAN_CLUSTER * SCAN_THREADS);
+    if (!single && !tile_order && per <= SCAN_CLUSTER_MAX_PER)
+        tile_scan_cluster_kernel<<<SCAN_CLUSTER, SCAN_THREADS, 0, st>>>(T, per < 1 ? 1 : per, tile_count, tile_base, tile_cursor, info,
+                                                                       dup_capacity, class_tiles, stats);
+    else
+        tile_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(T, tile_count, tile_base, tile_cursor, info, dup_capacity,
+                                                     class_tiles, tile_order, stats);
     return cudaGetLastError();
 }
 
