@@ -477,6 +477,11 @@ def main():
     # timed loops as in a training loop, on for the per-stage breakdown below
     rast.set_profiling(False)
     ms_total, _ = timed(step_resident, args.steps, warm)
+    # kernels of the library per step: the context's own launch counter (dvs_rast_kernel_launches) around one more step
+    try:
+        l0 = rast.kernel_launches(); step_resident(); launches_per_step = rast.kernel_launches() - l0
+    except Exception:  # an older library without the counter: preprocess, scan, 3 sort classes, 2 compositing, per-Gaussian backward
+        launches_per_step = 8
     rast.set_profiling(True)
     # per-stage device times (CUDA events recorded on the launch stream inside the library), averaged over a few steps
     stage_ms = {}
@@ -554,9 +559,10 @@ def main():
                 "api": "dvs_rast_step_host_async / dvs_rast_step_host_wait (C-ABI), two pipeline slots: every step copies its pinned "
                        "dL/dpix H2D and its image D2H (the host waits for step k's image after queueing step k+1); parameters and "
                        "gradients device-resident as in the trainer"},
-        # 8 forward + 2 backward kernels of ours per step; with N > 1 one more when the exchange is ours too (the NVLS
-        # all-reduce kernel, or the SH accumulation kernel of the factored exchange)
-        "gpu_launches": (10 + (1 if world > 1 and reducer.backend in ("nvls", "factored", "fused") else 0)) * args.steps,
+        # kernels of ours in the timed region: the rasterizer's own count per step (6 forward + 2 backward at c3); with N > 1
+        # one more when the exchange is ours too (the fused exchange / NVLS all-reduce kernel, or the SH accumulation kernel
+        # of the factored exchange)
+        "gpu_launches": (launches_per_step + (1 if world > 1 and reducer.backend in ("nvls", "factored", "fused") else 0)) * args.steps,
         "allreduce": ({"backend": reducer.backend, "note": reducer.note, "bytes": int(reducer.flat.numel()) * 4, "ms": ms_ar,
                        "busbw_GBps": (2 * (world - 1) / world * reducer.flat.numel() * 4 / 1e9 / (ms_ar * 1e-3))}
                       if world > 1 else None),

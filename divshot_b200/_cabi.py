@@ -29,7 +29,7 @@ EXPORTS = [
     "dvs_rast_forward", "dvs_rast_backward", "dvs_rast_step_host", "dvs_rast_get_stats", "dvs_rast_debug_read",
     "dvs_rast_stage_ms", "dvs_rast_stage_name", "dvs_rast_forward_aux", "dvs_rast_backward_aux",
     "dvs_rast_set_profiling", "dvs_rast_step_host_async", "dvs_rast_step_host_wait", "dvs_rast_device_overflow_word",
-    "dvs_rast_set_background", "dvs_rast_background_grad",
+    "dvs_rast_set_background", "dvs_rast_background_grad", "dvs_rast_kernel_launches",
 ]
 COLL_EXPORTS = ["dvs_coll_allreduce_nvls", "dvs_coll_sh_grad_from_dsh0", "dvs_coll_exchange_fused", "dvs_coll_exchange_fused_grid"]
 
@@ -110,6 +110,9 @@ def load():
         L.dvs_rast_step_host_async.restype = C.c_int
         L.dvs_rast_step_host_wait.argtypes = [C.c_void_p, C.c_int]
         L.dvs_rast_step_host_wait.restype = C.c_int
+    if hasattr(L, "dvs_rast_kernel_launches"):
+        L.dvs_rast_kernel_launches.argtypes = [C.c_void_p]
+        L.dvs_rast_kernel_launches.restype = C.c_uint64
     if hasattr(L, "dvs_rast_set_background"):
         L.dvs_rast_set_background.argtypes = [C.c_void_p, C.c_void_p]
         L.dvs_rast_set_background.restype = C.c_int

@@ -32,6 +32,7 @@ using namespace dvs;
 struct dvs_rast_ctx {
     int device = 0;
     char err[512] = {0};
+    unsigned long long kernel_launches = 0;  // kernels of ours enqueued through this context so far
     // per-Gaussian arenas
     int64_t cap_gauss = 0;
     float4* rec = nullptr;
@@ -113,8 +114,11 @@ static int fail(dvs_rast_ctx* c, int code, const char* fmt, ...) {
     }
     return code;
 }
+// (every CK(launch_*(...)) is one kernel launch of ours — launch_tile_sort adds its extra kernels itself — counted for
+// dvs_rast_kernel_launches)
 #define CK(call)                                                                                           \
     do {                                                                                                   \
+        if (__builtin_strncmp(#call, "launch_", 7) == 0) ctx->kernel_launches++;                           \
         cudaError_t e__ = (call);                                                                          \
         if (e__ != cudaSuccess)                                                                            \
             return fail(ctx, DVS_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
@@ -407,6 +411,7 @@ int dvs_rast_forward(dvs_rast_ctx* ctx, const dvs_camera* cam, int64_t N, const 
         EV(3);
         CK(launch_tile_sort((int)T, fused ? ctx->bin_stride : 0u, ctx->tile_base, ctx->bins, ctx->plist, ctx->info,
                             ctx->class_tiles, st));
+        ctx->kernel_launches += (unsigned long long)(tile_sort_launch_count(fused ? ctx->bin_stride : 0u) - 1);
         EV(4);
         if (surfel)
             CK(launch_surfel_render_fwd(c, ctx->tile_base, ctx->plist, ctx->rec2, out_color, ctx->final_T, ctx->n_contrib, ctx->info, st));
@@ -712,6 +717,7 @@ int dvs_rast_background_grad(dvs_rast_ctx* ctx, const float* dL_dpix, float* dL_
 }
 
 const uint32_t* dvs_rast_device_overflow_word(const dvs_rast_ctx* ctx) { return ctx ? ctx->info + 2 : nullptr; }
+uint64_t dvs_rast_kernel_launches(const dvs_rast_ctx* ctx) { return ctx ? (uint64_t)ctx->kernel_launches : 0u; }
 
 int dvs_rast_set_profiling(dvs_rast_ctx* ctx, int on) {
     if (!ctx) return DVS_E_INVALID;

@@ -600,6 +600,11 @@ constexpr size_t bucket_smem_bytes() {
            260 * 4 + (size_t)NMAX * 2;
 }
 
+int tile_sort_launch_count(uint32_t bin_stride) {  // how many kernels launch_tile_sort enqueues (same conditions as below)
+    const uint32_t max_len = bin_stride ? bin_stride : 0xffffffffu;
+    return 2 + (max_len > 2048u ? 1 : 0) + (max_len > 4096u ? 1 : 0) + (max_len > 16384u ? 1 : 0);
+}
+
 cudaError_t launch_tile_sort(int T, uint32_t bin_stride, const uint32_t* tile_base, unsigned long long* bins,
                              uint32_t* plist, const uint32_t* info, const uint32_t* class_tiles, cudaStream_t st) {
     if (T <= 0) return cudaSuccess;

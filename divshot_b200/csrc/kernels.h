@@ -28,6 +28,7 @@ cudaError_t launch_emit(const Cam& cam, int N, const uint4* aux, const float4* c
                         unsigned long long* bins, uint32_t dup_capacity, cudaStream_t st);
 
 // A4: tile-local sort (CUB-free) -> plist (id<<8 | mask), tile-major
+int tile_sort_launch_count(uint32_t bin_stride);
 cudaError_t launch_tile_sort(int T, uint32_t bin_stride, const uint32_t* tile_base, unsigned long long* bins,
                              uint32_t* plist, const uint32_t* info, const uint32_t* class_tiles, cudaStream_t st);
 

@@ -205,6 +205,10 @@ class Rasterizer:
     def step_host_wait(self, slot: int):
         self._check(self._lib.dvs_rast_step_host_wait(self._h, slot))
 
+    def kernel_launches(self) -> int:
+        """Kernels of the library enqueued through this context so far (dvs_rast_kernel_launches)."""
+        return int(self._lib.dvs_rast_kernel_launches(self._h))
+
     def set_background(self, bg_image: torch.Tensor | None):
         """Per-pixel background [3,H,W] (the trainer's sky model, GaussianTrainConfig::enableBg) for every later forward /
         backward of this context; None restores the camera's constant background.  The tensor is kept alive here."""

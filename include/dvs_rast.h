@@ -221,6 +221,10 @@ DVS_API int dvs_rast_get_stats(dvs_rast_ctx* ctx, dvs_stats* out);
  * and skip their update, so a step that produced no gradients does not move the model. */
 DVS_API const uint32_t* dvs_rast_device_overflow_word(const dvs_rast_ctx* ctx);
 
+/* Number of CUDA kernels of this library enqueued through the context so far (forward, backward, auxiliary passes; copies and
+ * memsets are not kernels).  bench.py reports the difference over its timed region as `gpu_launches`. */
+DVS_API uint64_t dvs_rast_kernel_launches(const dvs_rast_ctx* ctx);
+
 /* Per-stage CUDA events (dvs_rast_stage_ms) are recorded only while profiling is on (default: on).  A training loop
  * turns it off: nine event records per step are launch-queue work the step does not need. */
 DVS_API int dvs_rast_set_profiling(dvs_rast_ctx* ctx, int on);

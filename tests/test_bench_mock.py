@@ -52,6 +52,9 @@ class _FakeRasterizer:
     def set_profiling(self, on):
         pass
 
+    def kernel_launches(self):  # 6 forward + 2 backward kernels per step, like the library's counter at c3
+        return 4 * self.calls
+
     def stage_ms(self):
         return {k: 0.1 + 0.01 * i for i, k in enumerate(STAGES)}
 
@@ -86,7 +89,7 @@ def test_bench_main_assembles_the_contract_line(monkeypatch, capfd):
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
                 "dtype", "data", "config", "roofline", "e2e", "gpu_launches", "clocks", "stages", "other_rows"):
         assert key in line, key
-    assert line["n_gpus"] == 1 and line["steps"] == 3 and line["gpu_launches"] == 30 and line["vs_baseline"] is None
+    assert line["n_gpus"] == 1 and line["steps"] == 3 and line["gpu_launches"] == 24 and line["vs_baseline"] is None
     assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
     assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
     assert set(line["other_rows"]) == {"F3_viewer_pack", "F1_refinement", "F1_train_step"}
@@ -166,4 +169,4 @@ def test_bench_two_ranks_on_stand_ins_print_one_line_and_keep_the_plain_exchange
     line = json.loads(rows0[0])
     assert line["n_gpus"] == 2 and line["scaling"] == "weak" and line["allreduce"]["backend"] == "nccl"
     assert "rejected" in line["allreduce"]["note"] and line["allreduce"]["ms"] > 0
-    assert line["gpu_launches"] == 20 and "other_rows" not in line
+    assert line["gpu_launches"] == 2 * 4 and "other_rows" not in line  # (the stand-in counts its forward only)
