@@ -65,8 +65,8 @@ def main():
         "roofline": {"bound": "hbm", "kernel": "whole train_step", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "traffic": None, "peak_source": src, "alg_bytes_per_launch": step_bytes},
         "model_2dgs": {"iterations_per_s": its2, "ms_per_step": 1e3 / its2,
-                       "note": "modelType = 1 (csrc/surfel.cu): correct, lightly tuned compositor (sub-tile masks; no packed arithmetic, "
-                               "shuffle-tree reduction in the backward)"},
+                       "note": "modelType = 1 (csrc/surfel.cu): exact projected-ellipse sub-tile masks, ballot-driven list walks, "
+                               "recursive-halving warp sums; no two-phase backward, no packed arithmetic (DESIGN.md section 8)"},
         "cpu_baseline": None, "gpu_launches": None}))
 
 
