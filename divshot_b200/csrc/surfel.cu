@@ -12,12 +12,14 @@
 //     depth = rho3d <= rho2d ? u Tw.x + v Tw.y + Tw.z : Tw.z  (< 0.2: skip),  alpha = min(0.99, o exp(-rho / 2))
 //   then the 3DGS compositing rules (alpha < 1/255 skip, T (1 - alpha) < 1e-4 stop, n_contrib, final_T, background).
 //
-// Design: correctness first.  One CTA per 16x16 tile, warp w = the 8x4-pixel sub-rectangle (w & 1, w >> 1), 64-byte records
-// staged 256 per round in shared memory; a warp visits only the surfels whose sub-tile mask bit is set (ballots over the staged
-// list; the mask is computed at emission from the surfel's projected alpha >= 1/255 ellipse, preprocess_fwd.cu); the
-// backward also stops at the warp's deepest last contributor, reduces its 15 per-pair sums over the warp with shuffles (skipped
-// when no lane blended the pair) and sends them with one 128-bit vector reduction per four floats.  The 3DGS path's packed
-// fp32x2 arithmetic, straight-line predicated loops and two-phase backward are NOT applied here.
+// Design.  One CTA per 16x16 tile, warp w = the 8x4-pixel sub-rectangle (w & 1, w >> 1), 64-byte records staged 256 per round
+// in shared memory.  A warp visits only the surfels whose sub-tile mask bit is set: one ballot per 32 staged list entries,
+// walked by find-first-set (the mask is computed at emission from the surfel's projected alpha >= 1/255 ellipse,
+// preprocess_fwd.cu).  The pair evaluation uses reciprocals (rcp.approx) instead of IEEE divisions.  The backward also stops at
+// the warp's deepest last contributor, sums its 15 per-pair values over the warp by RECURSIVE HALVING (20 shuffles instead of
+// 15 x 5; skipped when no lane blended the pair) and sends them with one 128-bit vector reduction per four floats.  The
+// per-Gaussian backward stages its shN / dL/dshN rows through shared memory.  Not applied here (DESIGN.md sections 8, 9): the
+// 3DGS path's packed fp32x2 arithmetic, predicated straight-line loops and two-phase backward.
 #include <cstdlib>
 
 #include "common.cuh"
