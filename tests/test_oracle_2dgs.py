@@ -71,3 +71,75 @@ def test_analytic_backward_matches_float64_autograd():
         got = getattr(b, name)
         assert_close_robust(got, ref.reshape(got.shape), 1e-4, name)
     assert not b.dL_dscales[:, 2].any(), "the third scale of a surfel has no gradient"
+
+
+def _cull_ellipse(T, o, cx, cy):
+    """numpy (float32) restatement of the sub-tile cull ellipse of csrc/preprocess_fwd.cu (surfel_preprocess_fwd_kernel): centre and
+    conic (a, b, c) of the set emission tests the 8x4-pixel boxes against (a dx^2 + b dx dy + c dy^2 <= ~1), or None = no culling."""
+    f = np.float32
+    m2 = f(2.0) * np.log(f(255.0) * o) * f(1.0001) + f(1e-3)
+    if not m2 > 0:
+        return "empty"
+    dist_k = m2 * (T[6] * T[6] + T[7] * T[7]) - T[8] * T[8]
+    if not dist_k < f(-1e-6) * T[8] * T[8]:
+        return None
+    u = T[0:3] - cx * T[6:9]; v = T[3:6] - cy * T[6:9]; w = T[6:9]
+    g0 = m2 / dist_k; g2 = f(-1.0) / dist_k
+    kx = g0 * (u[0] * w[0] + u[1] * w[1]) + g2 * u[2] * w[2]
+    ky = g0 * (v[0] * w[0] + v[1] * w[1]) + g2 * v[2] * w[2]
+    hx = max(kx * kx - (g0 * (u[0] * u[0] + u[1] * u[1]) + g2 * u[2] * u[2]), f(0))
+    hy = max(ky * ky - (g0 * (v[0] * v[0] + v[1] * v[1]) + g2 * v[2] * v[2]), f(0))
+    hxy = kx * ky - (g0 * (u[0] * v[0] + u[1] * v[1]) + g2 * u[2] * v[2])
+    lim = np.sqrt(hx * hy); hxy = min(max(hxy, -lim), lim)
+    rf = np.sqrt(f(0.5) * m2)
+    r = rf + np.sqrt(kx * kx + ky * ky) + f(0.25)
+    sxx = hx * f(1.002) + r * r; syy = hy * f(1.002) + r * r; sxy = hxy * f(1.002)
+    det = sxx * syy - sxy * sxy
+    exk = np.sqrt(max(f(1e-4), hx)); eyk = np.sqrt(max(f(1e-4), hy))
+    xlo, xhi = min(kx - exk, -rf), max(kx + exk, rf)
+    ylo, yhi = min(ky - eyk, -rf), max(ky + eyk, rf)
+    sx = f(1.4143) * (f(0.5) * (xhi - xlo) * f(1.001) + f(0.05)); sy = f(1.4143) * (f(0.5) * (yhi - ylo) * f(1.001) + f(0.05))
+    if sxx < 1e12 and syy < 1e12 and det > 0 and det < sx * sx * sy * sy:
+        return (cx + kx, cy + ky, syy / det, f(-2.0) * sxy / det, sxx / det)
+    if sx < 1e6 and sy < 1e6:
+        return (cx + f(0.5) * (xlo + xhi), cy + f(0.5) * (ylo + yhi), f(1.0) / (sx * sx), f(0.0), f(1.0) / (sy * sy))
+    return None
+
+
+def test_cull_ellipse_contains_every_pixel_the_oracle_blends():
+    """The surfel cull ellipse (exact projected alpha >= 1/255 ellipse from the dual conic, inflated to contain the low-pass disk;
+    DESIGN.md section 8) is conservative: every (pixel, surfel) pair that passes the oracle's S.2 tests lies inside it.  The
+    kernel's construction is restated in numpy above; the GPU tier checks the kernel's actual mask bits the same way."""
+    total = outside = culled_all = 0
+    for seed, (N, W, H, ls) in enumerate([(700, 96, 64, 1.2), (500, 128, 80, 0.3), (300, 160, 100, 2.0)]):
+        sc = make_scene(N=N, width=W, height=H, sh_degree=0, seed=431 + seed, normalise_quats=False)
+        sc.log_scales += ls
+        sc.logit_opac[::3] += 3.0
+        sc.logit_opac[1::7] -= 6.0
+        f = orc.forward2d(orc_cam(sc.cameras[0], 0), *scene_arrays(sc), render=False)
+        ys, xs = np.mgrid[0:H, 0:W].astype(np.float64)
+        for g in np.nonzero(np.asarray(f.radii) > 0)[0]:
+            T = f.transmat[g].astype(np.float32)
+            o = np.float32(f.opacity[g]); cx, cy = f.mean2D[g].astype(np.float32)
+            Td = T.astype(np.float64); Tu, Tv, Tw = Td[0:3], Td[3:6], Td[6:9]
+            k = xs[..., None] * Tw - Tu; l = ys[..., None] * Tw - Tv
+            pv = np.cross(k, l)
+            with np.errstate(all="ignore"):
+                uu, vv = pv[..., 0] / pv[..., 2], pv[..., 1] / pv[..., 2]
+            rho3d = uu * uu + vv * vv
+            rho2d = 2.0 * ((cx - xs) ** 2 + (cy - ys) ** 2)
+            dep = np.where(rho3d <= rho2d, uu * Tw[0] + vv * Tw[1] + Tw[2], Tw[2])
+            alpha = np.minimum(0.99, o * np.exp(-0.5 * np.minimum(rho3d, rho2d)))
+            contrib = (pv[..., 2] != 0) & (dep >= 0.2) & (alpha >= 1 / 255)
+            total += int(contrib.sum())
+            e = _cull_ellipse(T, o, cx, cy)
+            if e is None:
+                continue
+            if isinstance(e, str):  # opacity below 1/255: the mask is empty and nothing may blend
+                outside += int(contrib.sum()); culled_all += 1
+                continue
+            ex, ey, a, b, c = (np.float64(t) for t in e)
+            dx, dy = ex - xs, ey - ys
+            outside += int((contrib & ~(a * dx * dx + b * dx * dy + c * dy * dy <= 1.0011)).sum())
+    assert total > 200000 and culled_all > 10
+    assert outside == 0
