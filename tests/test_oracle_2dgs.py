@@ -143,3 +143,35 @@ def test_cull_ellipse_contains_every_pixel_the_oracle_blends():
             outside += int((contrib & ~(a * dx * dx + b * dx * dy + c * dy * dy <= 1.0011)).sum())
     assert total > 200000 and culled_all > 10
     assert outside == 0
+
+
+def test_recursive_halving_warp_sum_leaves_value_i_on_lanes_2i_and_2i_plus_1():
+    """The backward's warp reduction (csrc/surfel.cu): 16 values per lane are summed over the 32 lanes with 8 + 4 + 2 + 1 + 1
+    butterfly shuffles by keeping one half and trading the other at every level; lane L must end with the warp total of value
+    L >> 1, which the four gather shuffles (source lane 8 (lane & 3) + 2 c) then turn into the float4 of lanes 0..3.  Emulated
+    lane by lane in numpy with the kernel's own select / shuffle pattern."""
+    rng = np.random.default_rng(5)
+    g = rng.integers(-1000, 1000, (32, 16)).astype(np.float64)  # [lane][value]; integers: exact sums in any order
+    lane = np.arange(32)
+
+    def shfl_xor(v, m):
+        return v[lane ^ m]
+
+    def level(vals, bit, half):
+        h = (lane & bit) != 0
+        out = []
+        for k in range(half):
+            send = np.where(h, vals[k], vals[k + half]); keep = np.where(h, vals[k + half], vals[k])
+            out.append(keep + shfl_xor(send, bit))
+        return out
+
+    a = level([g[:, k] for k in range(16)], 16, 8)
+    b = level(a, 8, 4)
+    c = level(b, 4, 2)
+    t = level(c, 2, 1)[0]
+    t = t + shfl_xor(t, 1)
+    want = g.sum(axis=0)
+    assert np.array_equal(t, want[lane >> 1])
+    for ln in range(4):  # the gather for the four 128-bit reductions
+        got = [t[8 * (ln & 3) + 2 * cc] for cc in range(4)]
+        assert got == [want[4 * ln + cc] for cc in range(4)]
